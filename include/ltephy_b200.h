@@ -1,0 +1,172 @@
+/*
+ * ltephy_b200.h -- C-ABI of the B200-native LTE PHY decode path (libltephy_b200.so).
+ *
+ * Tier 1 (this file): batched, plain-C entry points.  A "batch" is n independent subframes (the
+ * reference's unit of parallel work: one SubframeWorker each, src/src/Phy.cc:29-54).
+ *   phase A  = what srsran_ue_dl_decode_fft_estimate + the per-candidate srsran_pdcch_dci_decode calls
+ *              compute (src/src/DCISearch.cc:562, lib/src/phy/falcon_phch/falcon_pdcch.c:110-170):
+ *              OFDM rx, CRS channel estimate, PCFICH, PDCCH LLRs, and the FULL blind-decode table
+ *              T[location][payload size] -> {CRC remainder (RNTI), payload bits}
+ *   search   = host replay of FALCON's tree walk (src/src/DCISearch.cc:102-528) over that table,
+ *              in subframe order, with the RNTI history (lib/src/util/RNTIManager.cc)
+ *   phase B  = srsran_ue_dl_decode_pdsch for every accepted DL grant (src/src/DL_Sniffer_PDSCH.cc:997)
+ * Tier 2 (ltephy_srsran_compat.h): the srsRAN/FALCON names on top of tier 1.
+ *
+ * Error convention follows the reference (falcon_pdcch.c:121,131): 0 success, -1 error,
+ * -2 invalid inputs.  A failed decode is NOT an error: it is crc == 0 in the result.
+ * No CPU fallback exists: every entry point fails with LTEPHY_ERROR if no CUDA device is usable.
+ */
+#ifndef LTEPHY_B200_H
+#define LTEPHY_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LTEPHY_SUCCESS 0
+#define LTEPHY_ERROR -1
+#define LTEPHY_ERROR_INVALID_INPUTS -2
+
+#define LTEPHY_MAX_PRB 110
+#define LTEPHY_MAX_CCE 88
+#define LTEPHY_MAX_LOC 160       /* MAX_CANDIDATES_BLIND, lib/include/falcon/phy/falcon_ue/falcon_ue_dl.h:39 */
+#define LTEPHY_SEARCH_MAX_CCE 84 /* MAX_NUM_OF_CCE, lib/include/falcon/phy/falcon_phch/falcon_pdcch.h:36 */
+#define LTEPHY_NOF_FORMATS 9     /* falcon_ue_all_formats, src/src/DCISearch.cc:84-95 */
+#define LTEPHY_MAX_SIZES 8       /* distinct DCI payload sizes among the 9 formats */
+
+typedef struct ltephy ltephy_t;
+
+typedef struct {
+  uint32_t nof_prb;        /* 15..100 (control region needs > 10) */
+  uint32_t nof_ports;      /* CRS ports 1|2 */
+  uint32_t cell_id;        /* PCI */
+  uint32_t nof_rx;         /* rx antennas 1|2 */
+  uint32_t max_subframes;  /* batch capacity */
+  uint32_t max_grants;     /* phase-B capacity per batch (0 = 24 * max_subframes) */
+  uint32_t turbo_max_iter; /* max-log-MAP iterations, >= 1 */
+  int32_t  device;         /* CUDA device ordinal */
+  uint32_t flags;          /* LTEPHY_FLAG_* */
+  uint32_t reserved[7];
+} ltephy_cfg_t;
+
+#define LTEPHY_FLAG_SKIP_LOW_POWER 1u /* do not decode locations covering a CCE with mean|LLR| < 0.7 (they are never consulted) */
+
+/* ---- phase A results --------------------------------------------------------------------- */
+typedef struct {
+  uint32_t tti;
+  uint32_t cfi;
+  uint32_t nof_cce;
+  uint32_t nof_locations;
+  float    pcfich_corr[3];
+  float    noise[2][2], rsrp[2][2]; /* [port][ant] -> chest_res.snr_ant_port_db */
+  float    noise_avg, rsrp_avg;
+  float    cfo_re, cfo_im;
+  float    snr_db; /* host: 10 log10f(rsrp_avg / noise_avg)   -> q->chest_res.snr_db (DCISearch.cc:568) */
+  float    cfo;    /*                                          -> q->chest_res.cfo   (SubframeWorker.cc:203) */
+  float    rb_power[LTEPHY_MAX_PRB];  /* linear mean RE power, antenna 0 (SubframePower.cc:18-58) */
+  float    cce_power[LTEPHY_MAX_CCE]; /* mean |LLR| per CCE (falcon_pdcch.c:595-620) */
+} ltephy_sf_info_t;
+
+typedef struct {
+  uint64_t bits;  /* payload, bit i of the DCI at position (63 - i) */
+  uint16_t rnti;  /* CRC remainder = parity XOR crc16 (falcon_pdcch.c:142-143) */
+  uint8_t  valid; /* 1 decoded; 0 skipped (no such location / all-zero LLRs / low power with the flag set) */
+  uint8_t  pad[5];
+} ltephy_cand_t;
+
+/* ---- phase B ------------------------------------------------------------------------------ */
+enum { LTEPHY_TX_PORT0 = 0, LTEPHY_TX_DIVERSITY = 1, LTEPHY_TX_CDD = 2, LTEPHY_TX_SPATIALMUX = 3 };
+
+typedef struct {
+  uint32_t sf;              /* index of the subframe inside the current batch */
+  uint16_t rnti;
+  uint8_t  tx_scheme;       /* LTEPHY_TX_* -- srsran_pdsch_grant_t.tx_scheme */
+  uint8_t  nof_tb;
+  uint32_t prb_mask[2][4];  /* per slot, bit (prb & 31) of word (prb >> 5) */
+  uint32_t nof_re;          /* srsran_pdsch_grant_t.nof_re */
+  struct {
+    int32_t tbs;            /* bits, <= 0 disables the TB */
+    uint8_t qm;             /* 2,4,6,8 */
+    uint8_t rv;
+    uint8_t enabled;
+    uint8_t pad;
+  } tb[2];
+} ltephy_grant_t;
+
+typedef struct {
+  uint8_t  crc;             /* srsran_pdsch_res_t.crc */
+  uint8_t  avg_iters;       /* mean turbo iterations over the code blocks (rounded up) */
+  uint16_t nof_cb;
+  uint32_t payload_off;     /* byte offset of srsran_pdsch_res_t.payload in the payload buffer */
+  uint32_t payload_len;     /* tbs / 8 */
+} ltephy_tb_result_t;
+
+/* ---- accepted DCI (output of the host search) --------------------------------------------- */
+typedef struct {
+  uint32_t sf;
+  uint16_t rnti;
+  uint8_t  format;          /* index into the 9-format list */
+  uint8_t  L;               /* after disambiguation */
+  uint16_t ncce;
+  uint16_t nof_bits;
+  uint64_t bits;
+  uint32_t histogram_value; /* hist_max_format_value handed to DCICollection::addCandidate */
+} ltephy_dci_t;
+
+/* ---- lifecycle ---------------------------------------------------------------------------- */
+int  ltephy_create(const ltephy_cfg_t* cfg, ltephy_t** out);
+void ltephy_destroy(ltephy_t* h);
+const char* ltephy_last_error(void);
+
+/* static geometry queries (host only) */
+uint32_t ltephy_sf_len(const ltephy_t* h);                          /* cf32 samples per antenna-subframe */
+uint32_t ltephy_nof_cce(const ltephy_t* h, uint32_t cfi);
+uint32_t ltephy_nof_sizes(const ltephy_t* h);                       /* distinct DCI payload sizes */
+uint32_t ltephy_dci_size(const ltephy_t* h, uint32_t format);       /* srsran_dci_format_sizeof */
+uint32_t ltephy_size_index(const ltephy_t* h, uint32_t format);     /* format -> column of the candidate table */
+uint32_t ltephy_locations(const ltephy_t* h, uint32_t cfi, uint16_t* ncce, uint8_t* L, uint32_t max); /* falcon_pdcch.c:321-356 */
+
+/* ---- phase A ------------------------------------------------------------------------------ */
+/* iq: n * nof_rx * sf_len cf32 (interleaved re,im), subframe-major then antenna; host memory
+ * (pinned memory makes the copy asynchronous).  tti[i] = 10*sfn + sf_idx.  Asynchronous. */
+int ltephy_submit_iq(ltephy_t* h, const float* iq, const uint32_t* tti, uint32_t n);
+/* same, but iq already lives in device memory (used to time the kernels alone) */
+int ltephy_submit_iq_device(ltephy_t* h, const void* iq_dev, const uint32_t* tti, uint32_t n);
+/* blocks until phase A of the current batch is done and copies its results to the host:
+ * info[n], cands[n][LTEPHY_MAX_LOC][LTEPHY_MAX_SIZES] */
+int ltephy_get_phase_a(ltephy_t* h, ltephy_sf_info_t* info, ltephy_cand_t* cands);
+
+/* ---- phase B ------------------------------------------------------------------------------ */
+int ltephy_submit_grants(ltephy_t* h, const ltephy_grant_t* grants, uint32_t n);
+/* results[n][2]; payload receives the TB bytes back to back */
+int ltephy_get_phase_b(ltephy_t* h, ltephy_tb_result_t* results, uint8_t* payload, size_t payload_cap);
+
+/* ---- stand-alone batched kernels (BASELINE.json configs 3 and 4) --------------------------- */
+/* llr: n subframes x 72*LTEPHY_MAX_CCE float LLRs (host); cfi[n]; fills cands[n][MAX_LOC][MAX_SIZES] */
+int ltephy_dci_sweep(ltephy_t* h, const float* llr, const uint32_t* cfi, uint32_t n, ltephy_cand_t* cands);
+/* ncb code blocks of size K, d: ncb x 3*(K+4) conditioned int16 streams (host);
+ * bits: ncb x K decoded bits (one per byte); iters/crc_ok per code block; crc_type 0 none,1 CRC24A,2 CRC24B */
+int ltephy_turbo_batch(ltephy_t* h, const int16_t* d, uint32_t K, uint32_t ncb, uint32_t max_iter, int crc_type, uint8_t* bits,
+                       uint8_t* iters, uint8_t* crc_ok);
+
+/* ---- debug / parity taps: copy an internal device buffer of the current batch to the host -- */
+enum {
+  LTEPHY_TAP_SYM = 0, /* cf32 [n][rx][14][12*nof_prb]          q->sf_symbols */
+  LTEPHY_TAP_CE  = 1, /* cf32 [n][port][rx][14][12*nof_prb]    q->chest_res.ce */
+  LTEPHY_TAP_LLR = 2, /* f32  [n][72*LTEPHY_MAX_CCE]           q->pdcch.llr */
+  LTEPHY_TAP_PDSCH_LLR = 3, /* int16, all codewords of the submitted grants back to back */
+  LTEPHY_TAP_TURBO_IN = 4   /* int16 conditioned streams (debug) */
+};
+int ltephy_tap(ltephy_t* h, int what, void* dst, size_t bytes);
+
+/* timing of the last batch, from CUDA events on the library's stream (ms): [0] H2D+phase A, [1] phase B */
+int ltephy_last_timing(ltephy_t* h, float ms[4]);
+/* number of kernel launches issued by the library since creation */
+uint64_t ltephy_launch_count(const ltephy_t* h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,207 @@
+"""ctypes binding of include/ltephy_b200.h (the tier-1 C-ABI).  Host arrays in, host arrays out;
+all compute happens in the CUDA library.  Fails loudly if the library is missing or unusable."""
+import ctypes as C
+import os
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libltephy_b200.so")
+
+MAX_PRB, MAX_CCE, MAX_LOC, MAX_SIZES, NOF_FORMATS = 110, 88, 160, 8, 9
+LLR_STRIDE = 72 * MAX_CCE
+TX_PORT0, TX_DIVERSITY, TX_CDD, TX_SPATIALMUX = 0, 1, 2, 3
+TAP_SYM, TAP_CE, TAP_LLR, TAP_PDSCH_LLR, TAP_TURBO_IN = 0, 1, 2, 3, 4
+FLAG_SKIP_LOW_POWER = 1
+
+
+class Cfg(C.Structure):
+    _fields_ = [("nof_prb", C.c_uint32), ("nof_ports", C.c_uint32), ("cell_id", C.c_uint32), ("nof_rx", C.c_uint32),
+                ("max_subframes", C.c_uint32), ("max_grants", C.c_uint32), ("turbo_max_iter", C.c_uint32), ("device", C.c_int32),
+                ("flags", C.c_uint32), ("reserved", C.c_uint32 * 7)]
+
+
+class SfInfo(C.Structure):
+    _fields_ = [("tti", C.c_uint32), ("cfi", C.c_uint32), ("nof_cce", C.c_uint32), ("nof_locations", C.c_uint32),
+                ("pcfich_corr", C.c_float * 3), ("noise", (C.c_float * 2) * 2), ("rsrp", (C.c_float * 2) * 2),
+                ("noise_avg", C.c_float), ("rsrp_avg", C.c_float), ("cfo_re", C.c_float), ("cfo_im", C.c_float),
+                ("snr_db", C.c_float), ("cfo", C.c_float), ("rb_power", C.c_float * MAX_PRB), ("cce_power", C.c_float * MAX_CCE)]
+
+
+class Cand(C.Structure):
+    _fields_ = [("bits", C.c_uint64), ("rnti", C.c_uint16), ("valid", C.c_uint8), ("pad", C.c_uint8 * 5)]
+
+
+class GrantTb(C.Structure):
+    _fields_ = [("tbs", C.c_int32), ("qm", C.c_uint8), ("rv", C.c_uint8), ("enabled", C.c_uint8), ("pad", C.c_uint8)]
+
+
+class Grant(C.Structure):
+    _fields_ = [("sf", C.c_uint32), ("rnti", C.c_uint16), ("tx_scheme", C.c_uint8), ("nof_tb", C.c_uint8),
+                ("prb_mask", (C.c_uint32 * 4) * 2), ("nof_re", C.c_uint32), ("tb", GrantTb * 2)]
+
+
+class TbResult(C.Structure):
+    _fields_ = [("crc", C.c_uint8), ("avg_iters", C.c_uint8), ("nof_cb", C.c_uint16), ("payload_off", C.c_uint32), ("payload_len", C.c_uint32)]
+
+
+CAND_DTYPE = np.dtype([("bits", "<u8"), ("rnti", "<u2"), ("valid", "u1"), ("pad", "u1", 5)])
+assert CAND_DTYPE.itemsize == C.sizeof(Cand) == 16
+
+_lib = None
+
+
+def load_library(build_if_missing=True):
+    """Loads libltephy_b200.so; there is no fallback implementation."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if build_if_missing:
+        from . import build as _b
+        _b.build()
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError("libltephy_b200.so is missing: build it with __graft_entry__.build(); there is no CPU fallback")
+    L = C.CDLL(LIB_PATH)
+    P = C.c_void_p
+    L.ltephy_create.argtypes = [C.POINTER(Cfg), C.POINTER(P)]
+    L.ltephy_destroy.argtypes = [P]
+    L.ltephy_last_error.restype = C.c_char_p
+    for f in ("ltephy_sf_len", "ltephy_nof_sizes"):
+        getattr(L, f).argtypes = [P]
+        getattr(L, f).restype = C.c_uint32
+    for f in ("ltephy_nof_cce", "ltephy_dci_size", "ltephy_size_index"):
+        getattr(L, f).argtypes = [P, C.c_uint32]
+        getattr(L, f).restype = C.c_uint32
+    L.ltephy_locations.argtypes = [P, C.c_uint32, P, P, C.c_uint32]
+    L.ltephy_locations.restype = C.c_uint32
+    L.ltephy_submit_iq.argtypes = [P, P, P, C.c_uint32]
+    L.ltephy_submit_iq_device.argtypes = [P, P, P, C.c_uint32]
+    L.ltephy_get_phase_a.argtypes = [P, P, P]
+    L.ltephy_submit_grants.argtypes = [P, P, C.c_uint32]
+    L.ltephy_get_phase_b.argtypes = [P, P, P, C.c_size_t]
+    L.ltephy_dci_sweep.argtypes = [P, P, P, C.c_uint32, P]
+    L.ltephy_turbo_batch.argtypes = [P, P, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, P, P, P]
+    L.ltephy_tap.argtypes = [P, C.c_int, P, C.c_size_t]
+    L.ltephy_last_timing.argtypes = [P, P]
+    L.ltephy_launch_count.argtypes = [P]
+    L.ltephy_launch_count.restype = C.c_uint64
+    _lib = L
+    return L
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class LtePhy:
+    """One PHY context (cell + batch capacity) on one GPU."""
+
+    def __init__(self, nof_prb, nof_ports, cell_id, nof_rx, max_subframes=16, turbo_max_iter=8, device=0, flags=0):
+        self.L = load_library()
+        cfg = Cfg(nof_prb=nof_prb, nof_ports=nof_ports, cell_id=cell_id, nof_rx=nof_rx, max_subframes=max_subframes,
+                  turbo_max_iter=turbo_max_iter, device=device, flags=flags)
+        self.cfg = cfg
+        self.h = C.c_void_p()
+        r = self.L.ltephy_create(C.byref(cfg), C.byref(self.h))
+        if r != 0:
+            raise RuntimeError("ltephy_create failed (%d): %s" % (r, self.L.ltephy_last_error().decode()))
+        self.sf_len = self.L.ltephy_sf_len(self.h)
+        self.nsc = 12 * nof_prb
+        self.n = 0
+
+    def close(self):
+        if self.h:
+            self.L.ltephy_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _chk(self, r, what):
+        if r != 0:
+            raise RuntimeError("%s failed (%d): %s" % (what, r, self.L.ltephy_last_error().decode()))
+
+    # ---- geometry
+    def nof_cce(self, cfi):
+        return self.L.ltephy_nof_cce(self.h, cfi)
+
+    def sizes(self):
+        return [self.L.ltephy_dci_size(self.h, f) for f in range(NOF_FORMATS)], [self.L.ltephy_size_index(self.h, f) for f in range(NOF_FORMATS)]
+
+    def locations(self, cfi):
+        nc = np.zeros(MAX_LOC, np.uint16)
+        L = np.zeros(MAX_LOC, np.uint8)
+        n = self.L.ltephy_locations(self.h, cfi, _p(nc), _p(L), MAX_LOC)
+        return nc[:n].copy(), L[:n].copy()
+
+    # ---- phase A
+    def submit_iq(self, iq, tti):
+        """iq: complex64 [n][nof_rx][sf_len]"""
+        iq = np.ascontiguousarray(iq, np.complex64)
+        tti = np.ascontiguousarray(tti, np.uint32)
+        n = len(tti)
+        assert iq.shape == (n, self.cfg.nof_rx, self.sf_len), iq.shape
+        self._keep = (iq, tti)
+        self._chk(self.L.ltephy_submit_iq(self.h, _p(iq), _p(tti), n), "submit_iq")
+        self.n = n
+
+    def get_phase_a(self, want_cands=True):
+        info = (SfInfo * self.n)()
+        cands = np.zeros((self.n, MAX_LOC, MAX_SIZES), CAND_DTYPE) if want_cands else None
+        self._chk(self.L.ltephy_get_phase_a(self.h, info, _p(cands) if want_cands else None), "get_phase_a")
+        return info, cands
+
+    def tap(self, what, shape, dtype):
+        out = np.zeros(shape, dtype)
+        self._chk(self.L.ltephy_tap(self.h, what, _p(out), out.nbytes), "tap")
+        return out
+
+    # ---- phase B
+    def submit_grants(self, grants):
+        arr = (Grant * max(1, len(grants)))(*grants)
+        self._grants = arr
+        self._ng = len(grants)
+        self._chk(self.L.ltephy_submit_grants(self.h, arr, len(grants)), "submit_grants")
+
+    def get_phase_b(self, payload_cap=None):
+        res = (TbResult * max(1, 2 * self._ng))()
+        cap = payload_cap or (self._ng * 2 * 13000 + 64)
+        pl = np.zeros(cap, np.uint8)
+        self._chk(self.L.ltephy_get_phase_b(self.h, res, _p(pl), cap), "get_phase_b")
+        return res, pl
+
+    # ---- stand-alone kernels
+    def dci_sweep(self, llr, cfi):
+        llr = np.ascontiguousarray(llr, np.float32)
+        cfi = np.ascontiguousarray(cfi, np.uint32)
+        n = len(cfi)
+        assert llr.shape == (n, LLR_STRIDE)
+        cands = np.zeros((n, MAX_LOC, MAX_SIZES), CAND_DTYPE)
+        self._chk(self.L.ltephy_dci_sweep(self.h, _p(llr), _p(cfi), n, _p(cands)), "dci_sweep")
+        return cands
+
+    def turbo_batch(self, d, K, max_iter, crc_type):
+        d = np.ascontiguousarray(d, np.int16)
+        ncb = d.shape[0]
+        assert d.shape == (ncb, 3 * (K + 4))
+        bits = np.zeros((ncb, K), np.uint8)
+        iters = np.zeros(ncb, np.uint8)
+        ok = np.zeros(ncb, np.uint8)
+        self._chk(self.L.ltephy_turbo_batch(self.h, _p(d), K, ncb, max_iter, crc_type, _p(bits), _p(iters), _p(ok)), "turbo_batch")
+        return bits, iters, ok
+
+    def timing(self):
+        t = (C.c_float * 4)()
+        self.L.ltephy_last_timing(self.h, t)
+        return list(t)
+
+    def launch_count(self):
+        return int(self.L.ltephy_launch_count(self.h))
+
+
+def cand_bits(c, nbits):
+    """uint64 payload -> array of nbits bits (bit i at position 63-i)."""
+    v = int(c)
+    return np.array([(v >> (63 - i)) & 1 for i in range(nbits)], np.uint8)

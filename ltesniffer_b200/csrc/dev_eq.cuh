@@ -1,0 +1,66 @@
+// dev_eq.cuh -- per-RE equalisers shared by the PDCCH and PDSCH kernels (zero forcing: the reference
+// leaves decoder_type = 0).  Operation order mirrors the CPU oracle exactly.
+#pragma once
+#include "dev_common.cuh"
+
+struct SfView {
+  const float2* y[2];    // per antenna [14*nsc]
+  const float2* h[2][2]; // [port][ant]
+};
+
+__device__ __forceinline__ float2 eq_port0(const DevCell& c, const SfView& v, uint32_t idx)
+{
+  float nr = 0.0f, ni = 0.0f, den = 0.0f;
+  for (uint32_t a = 0; a < c.nof_rx; a++) {
+    const float2 y = v.y[a][idx], h = v.h[0][a][idx];
+    nr  = nr + (y.x * h.x + y.y * h.y);
+    ni  = ni + (y.y * h.x - y.x * h.y);
+    den = den + (h.x * h.x + h.y * h.y);
+  }
+  return make_float2(nr / den, ni / den);
+}
+__device__ __forceinline__ void eq_sfbc(const DevCell& c, const SfView& v, uint32_t i0, uint32_t i1, float2& x0, float2& x1)
+{
+  float n0r = 0.0f, n0i = 0.0f, n1r = 0.0f, n1i = 0.0f, d0 = 0.0f, d1 = 0.0f;
+  for (uint32_t a = 0; a < c.nof_rx; a++) {
+    const float2 r0 = v.y[a][i0], r1 = v.y[a][i1];
+    const float2 h00 = v.h[0][a][i0], h01 = v.h[0][a][i1], h10 = v.h[1][a][i0], h11 = v.h[1][a][i1];
+    n0r = n0r + ((h00.x * r0.x + h00.y * r0.y) + (h11.x * r1.x + h11.y * r1.y));
+    n0i = n0i + ((h00.x * r0.y - h00.y * r0.x) + (h11.y * r1.x - h11.x * r1.y));
+    n1r = n1r + ((h01.x * r1.x + h01.y * r1.y) - (h10.x * r0.x + h10.y * r0.y));
+    n1i = n1i + ((h01.x * r1.y - h01.y * r1.x) - (h10.y * r0.x - h10.x * r0.y));
+    d0  = d0 + ((h00.x * h00.x + h00.y * h00.y) + (h11.x * h11.x + h11.y * h11.y));
+    d1  = d1 + ((h01.x * h01.x + h01.y * h01.y) + (h10.x * h10.x + h10.y * h10.y));
+  }
+  const float s2 = 1.41421354f;
+  x0             = make_float2((n0r / d0) * s2, (n0i / d0) * s2);
+  x1             = make_float2((n1r / d1) * s2, (n1i / d1) * s2);
+}
+__device__ __forceinline__ void eq_cdd(const SfView& v, uint32_t idx, bool odd, float2& x0, float2& x1)
+{
+  const float2 r0 = v.y[0][idx], r1 = v.y[1][idx];
+  const float2 h00 = v.h[0][0][idx], h10 = v.h[0][1][idx], h01 = v.h[1][0][idx], h11 = v.h[1][1][idx];
+  const float  s = odd ? -1.0f : 1.0f;
+  const float2 e00 = make_float2(h00.x + s * h01.x, h00.y + s * h01.y), e01 = make_float2(h00.x - s * h01.x, h00.y - s * h01.y);
+  const float2 e10 = make_float2(h10.x + s * h11.x, h10.y + s * h11.y), e11 = make_float2(h10.x - s * h11.x, h10.y - s * h11.y);
+  const float2 det = make_float2((e00.x * e11.x - e00.y * e11.y) - (e01.x * e10.x - e01.y * e10.y),
+                                 (e00.x * e11.y + e00.y * e11.x) - (e01.x * e10.y + e01.y * e10.x));
+  const float2 a0  = make_float2((e11.x * r0.x - e11.y * r0.y) - (e01.x * r1.x - e01.y * r1.y),
+                                 (e11.x * r0.y + e11.y * r0.x) - (e01.x * r1.y + e01.y * r1.x));
+  const float2 a1  = make_float2((e00.x * r1.x - e00.y * r1.y) - (e10.x * r0.x - e10.y * r0.y),
+                                 (e00.x * r1.y + e00.y * r1.x) - (e10.x * r0.y + e10.y * r0.x));
+  const float dd = det.x * det.x + det.y * det.y;
+  x0 = make_float2(((a0.x * det.x + a0.y * det.y) / dd) * 2.0f, ((a0.y * det.x - a0.x * det.y) / dd) * 2.0f);
+  x1 = make_float2(((a1.x * det.x + a1.y * det.y) / dd) * 2.0f, ((a1.y * det.x - a1.x * det.y) / dd) * 2.0f);
+}
+__device__ __forceinline__ SfView make_view(const DevCell& c, const float2* sym, const float2* ce, uint32_t sf)
+{
+  SfView         v;
+  const uint32_t g = 14 * c.nsc;
+  for (uint32_t a = 0; a < 2; a++) {
+    v.y[a] = sym + ((size_t)sf * c.nof_rx + (a < c.nof_rx ? a : 0)) * g;
+    for (uint32_t p = 0; p < 2; p++)
+      v.h[p][a] = ce + (((size_t)sf * c.nof_ports + (p < c.nof_ports ? p : 0)) * c.nof_rx + (a < c.nof_rx ? a : 0)) * g;
+  }
+  return v;
+}

@@ -1,0 +1,327 @@
+// k_frontend.cu -- sm_100a kernels K1 (OFDM rx), K2 (CRS channel estimate), K3+K4 (PCFICH + PDCCH LLR),
+// K10 (per-RB power).  Together they replace srsran_ue_dl_decode_fft_estimate as called from
+// DCISearch::search (reference src/src/DCISearch.cc:562) and SubframePower::computePower
+// (src/src/SubframePower.cc:18-58).  Compiled with -fmad=false: every float expression is evaluated
+// in the order written, which is the order of the CPU oracle, so results are compared bit-for-bit.
+#include "dev_common.cuh"
+#include "dev_eq.cuh"
+
+// =================================================================================================
+// K1: batched OFDM receive.  One CTA per (symbol, antenna, subframe): the fft-sample window after the
+// cyclic prefix is staged into shared memory with one TMA bulk copy (cp.async.bulk -> UBLKCP),
+// bit-reversed, then log2(fft) radix-2 DIT stages are executed three at a time from registers.
+// HBM traffic per antenna-subframe: 30720 cf32 read once (coalesced 16 KB bursts), 16800 cf32 written.
+// =================================================================================================
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+template <int G> // G = number of radix-2 stages fused in this pass (1..3)
+__device__ __forceinline__ void fft_pass(float2* work, const float2* __restrict__ tw, uint32_t n, uint32_t s0, uint32_t tid, uint32_t nthreads)
+{
+  constexpr uint32_t GS = 1u << G;      // elements per group
+  const uint32_t     h0 = 1u << (s0 - 1); // half size of the first stage of the pass
+  for (uint32_t gid = tid; gid < n / GS; gid += nthreads) {
+    const uint32_t base = (gid / h0) * (h0 * GS) + (gid % h0);
+    float2         v[GS];
+#pragma unroll
+    for (uint32_t j = 0; j < GS; j++) v[j] = work[base + j * h0];
+#pragma unroll
+    for (uint32_t ss = 0; ss < (uint32_t)G; ss++) {
+      const uint32_t half = h0 << ss, step = n / (2 * half);
+#pragma unroll
+      for (uint32_t j = 0; j < GS; j++) {
+        if (j & (1u << ss)) continue;
+        const uint32_t pos = (gid % h0) + (j & ((1u << ss) - 1)) * h0; // index inside the half block
+        const float2   w   = tw[pos * step];
+        const float2   a = v[j], b = v[j + (1u << ss)];
+        const float    tr = w.x * b.x - w.y * b.y;
+        const float    ti = w.x * b.y + w.y * b.x;
+        v[j]              = make_float2(a.x + tr, a.y + ti);
+        v[j + (1u << ss)] = make_float2(a.x - tr, a.y - ti);
+      }
+    }
+#pragma unroll
+    for (uint32_t j = 0; j < GS; j++) work[base + j * h0] = v[j];
+  }
+}
+
+__global__ void __launch_bounds__(256) ofdm_rx_kernel(const __grid_constant__ DevCell c, const float2* __restrict__ iq, float2* __restrict__ sym)
+{
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  float2*   stage = reinterpret_cast<float2*>(smem_raw);            // [fft]
+  float2*   work  = stage + c.fft;                                   // [fft]
+  float2*   tw    = work + c.fft;                                    // [fft/2]
+  __shared__ __align__(8) unsigned long long mbar;
+
+  const uint32_t l = blockIdx.x, a = blockIdx.y, sf = blockIdx.z, tid = threadIdx.x, nt = blockDim.x, n = c.fft;
+  const float2*  src = iq + ((size_t)sf * c.nof_rx + a) * c.sf_len + c.sym_off[l];
+  const bool     bulk_ok = ((reinterpret_cast<uintptr_t>(src) & 15u) == 0) && ((n * 8u) % 16u == 0);
+
+  if (bulk_ok) {
+    if (tid == 0) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&mbar)));
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (tid == 0) {
+      const uint32_t bytes = n * 8u;
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&mbar)), "r"(bytes) : "memory");
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(stage)),
+                   "l"(src), "r"(bytes), "r"(smem_u32(&mbar))
+                   : "memory");
+    }
+  }
+  for (uint32_t i = tid; i < n / 2; i += nt) tw[i] = c.tw[i]; // overlaps with the bulk copy
+  if (bulk_ok) {
+    uint32_t done = 0;
+    while (!done) {
+      asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                   : "=r"(done)
+                   : "r"(smem_u32(&mbar)), "r"(0u)
+                   : "memory");
+    }
+  } else {
+    for (uint32_t i = tid; i < n; i += nt) stage[i] = src[i];
+  }
+  __syncthreads();
+  for (uint32_t i = tid; i < n; i += nt) work[__brev(i) >> (32 - c.log2n)] = stage[i];
+  __syncthreads();
+  uint32_t s = 1;
+  while (s + 2 <= c.log2n) {
+    fft_pass<3>(work, tw, n, s, tid, nt);
+    __syncthreads();
+    s += 3;
+  }
+  if (s + 1 <= c.log2n) {
+    fft_pass<2>(work, tw, n, s, tid, nt);
+    __syncthreads();
+    s += 2;
+  }
+  if (s <= c.log2n) {
+    fft_pass<1>(work, tw, n, s, tid, nt);
+    __syncthreads();
+  }
+  float2*        dst = sym + (((size_t)sf * c.nof_rx + a) * 14 + l) * c.nsc;
+  const uint32_t h   = c.nsc / 2;
+  for (uint32_t k = tid; k < c.nsc; k += nt) dst[k] = work[k < h ? n - h + k : k - h + 1];
+}
+
+// =================================================================================================
+// K2: CRS channel estimate for one (port, antenna, subframe) per CTA.
+// Reads 800 pilots (+ CRS table), writes ce[14][nsc].  Restates srsran_chest_dl_estimate_cfg with the
+// reference's cfg (src/src/SubframeWorker.cc:376-400).
+// =================================================================================================
+__device__ __forceinline__ float2 f_interp(const DevCell& c, const float2* sm, uint32_t np, uint32_t off, uint32_t k)
+{
+  int m = ((int)k - (int)off) / 6;
+  if ((int)k < (int)off) m = 0;
+  if (m > (int)np - 2) m = (int)np - 2;
+  const int    j  = (int)k - (6 * m + (int)off);
+  const float  cc = c.interp_c[j + 5];
+  const float2 A = sm[m], B = sm[m + 1];
+  return make_float2(A.x + (B.x - A.x) * cc, A.y + (B.y - A.y) * cc);
+}
+
+__global__ void __launch_bounds__(256) chest_kernel(const __grid_constant__ DevCell c, const float2* __restrict__ sym, float2* __restrict__ ce,
+                                                    DevSfInfo* __restrict__ info)
+{
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const uint32_t np = 2 * c.nof_prb, nsc = c.nsc;
+  float2*        ls = reinterpret_cast<float2*>(smem_raw); // [4][np]
+  float2*        sm = ls + NPILSYM * np;                   // [4][np]
+  __shared__ float red[NPILSYM][2];
+  __shared__ float cfo_s[2];
+
+  const uint32_t p = blockIdx.x / c.nof_rx, a = blockIdx.x % c.nof_rx, sf = blockIdx.y, tid = threadIdx.x, nt = blockDim.x;
+  const uint32_t sf_idx = info[sf].tti % 10;
+  const float2*  y      = sym + ((size_t)sf * c.nof_rx + a) * 14 * nsc;
+  const float2*  pil    = c.crs + ((size_t)sf_idx * 2 + p) * NPILSYM * np;
+  const uint32_t PL[NPILSYM] = {0, 4, 7, 11};
+
+  for (uint32_t i = tid; i < NPILSYM * np; i += nt) {
+    const uint32_t li = i / np, m = i % np, l = PL[li], off = c.crs_off[p][li & 1];
+    const float2   v = y[l * nsc + 6 * m + off], q = pil[li * np + m];
+    ls[i]            = make_float2(v.x * q.x + v.y * q.y, v.y * q.x - v.x * q.y);
+  }
+  __syncthreads();
+  for (uint32_t i = tid; i < NPILSYM * np; i += nt) {
+    const uint32_t li = i / np, m = i % np;
+    float          ar = 0.0f, ai = 0.0f, ws = 0.0f;
+#pragma unroll
+    for (int j = 0; j < 5; j++) {
+      const int mm = (int)m + j - 2;
+      if (mm < 0 || mm >= (int)np) continue;
+      ar = ar + c.filt[j] * ls[li * np + mm].x;
+      ai = ai + c.filt[j] * ls[li * np + mm].y;
+      ws = ws + c.filt[j];
+    }
+    sm[i] = make_float2(ar / ws, ai / ws);
+  }
+  __syncthreads();
+  const uint32_t warp = tid >> 5, lane = tid & 31;
+  if (warp < NPILSYM) {
+    float pn = 0.0f, pp = 0.0f;
+    for (uint32_t m = lane; m < np; m += 32) {
+      const float2 s = sm[warp * np + m], r = ls[warp * np + m];
+      const float  dr = r.x - s.x, di = r.y - s.y;
+      pn = pn + (dr * dr + di * di);
+      pp = pp + (s.x * s.x + s.y * s.y);
+    }
+    pn = warp_tree_sum(pn);
+    pp = warp_tree_sum(pp);
+    if (lane == 0) red[warp][0] = pn, red[warp][1] = pp;
+  } else if (warp == NPILSYM && p == 0 && a == 0) {
+    float cr = 0.0f, ci = 0.0f;
+    for (uint32_t m = lane; m < np; m += 32) {
+      const float2 u = ls[0 * np + m], v = ls[2 * np + m];
+      cr = cr + (u.x * v.x + u.y * v.y);
+      ci = ci + (u.x * v.y - u.y * v.x);
+    }
+    cr = warp_tree_sum(cr);
+    ci = warp_tree_sum(ci);
+    if (lane == 0) cfo_s[0] = cr, cfo_s[1] = ci;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    float nsum = 0.0f, psum = 0.0f;
+    for (int li = 0; li < NPILSYM; li++) {
+      nsum = nsum + red[li][0];
+      psum = psum + red[li][1];
+    }
+    const float cnt   = (float)(NPILSYM * np);
+    info[sf].noise[p][a] = (nsum / cnt) / c.noise_corr;
+    info[sf].rsrp[p][a]  = psum / cnt;
+    if (p == 0 && a == 0) {
+      info[sf].cfo_re = cfo_s[0];
+      info[sf].cfo_im = cfo_s[1];
+    }
+  }
+  float2* out = ce + (((size_t)sf * c.nof_ports + p) * c.nof_rx + a) * 14 * nsc;
+  for (uint32_t i = tid; i < 14 * nsc; i += nt) {
+    const uint32_t l = i / nsc, k = i % nsc, ia = c.t_ia[l], ib = c.t_ib[l];
+    const float    t = c.t_frac[l];
+    const float2   A = f_interp(c, sm + ia * np, np, c.crs_off[p][ia & 1], k);
+    const float2   B = f_interp(c, sm + ib * np, np, c.crs_off[p][ib & 1], k);
+    float2         r;
+    if (l < 11)
+      r = make_float2(A.x + (B.x - A.x) * t, A.y + (B.y - A.y) * t);
+    else
+      r = make_float2(B.x + (B.x - A.x) * t, B.y + (B.y - A.y) * t);
+    out[i] = r;
+  }
+}
+
+// =================================================================================================
+// K10: per-PRB mean RE power of antenna 0 (SubframePower::computePower).
+// =================================================================================================
+__global__ void __launch_bounds__(128) rb_power_kernel(const __grid_constant__ DevCell c, const float2* __restrict__ sym, DevSfInfo* __restrict__ info)
+{
+  const uint32_t sf = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  const float2*  y = sym + (size_t)sf * c.nof_rx * 14 * c.nsc;
+  for (uint32_t prb = warp; prb < c.nof_prb; prb += nw) {
+    float acc = 0.0f;
+    for (uint32_t i = lane; i < 168; i += 32) {
+      const float2 v = y[(i / 12) * c.nsc + 12 * prb + (i % 12)];
+      acc = acc + (v.x * v.x + v.y * v.y);
+    }
+    acc = warp_tree_sum(acc);
+    if (lane == 0) info[sf].rb_power[prb] = acc / 168.0f;
+  }
+}
+
+// =================================================================================================
+// K3 + K4: PCFICH decode, then PDCCH REG gather + equalise (MRC / SFBC, zero forcing) + QPSK soft
+// demodulation + descrambling -> llr[nof_cce * 72], then per-CCE mean |LLR|
+// (srsran_pcfich_decode, srsran_pdcch_extract_llr, srsran_pdcch_cce_avg_llr_power falcon_pdcch.c:595-620).
+// =================================================================================================
+
+__global__ void __launch_bounds__(256) pdcch_llr_kernel(const __grid_constant__ DevCell c, const float2* __restrict__ sym, const float2* __restrict__ ce,
+                                                        float* __restrict__ llr_all, DevSfInfo* __restrict__ info)
+{
+  __shared__ uint32_t cfi_s;
+  const uint32_t sf = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
+  const uint32_t sf_idx = info[sf].tti % 10;
+  const SfView   v      = make_view(c, sym, ce, sf);
+  const float    ms2    = -1.41421354f;
+  if (tid == 0) {
+    float    llr[32];
+    float2   d[16];
+    if (c.nof_ports == 1) {
+      for (int i = 0; i < 16; i++) d[i] = eq_port0(c, v, c.pcfich_idx[i]);
+    } else {
+      for (int i = 0; i < 16; i += 2) eq_sfbc(c, v, c.pcfich_idx[i], c.pcfich_idx[i + 1], d[i], d[i + 1]);
+    }
+    const uint32_t scr = c.pcfich_scr[sf_idx];
+    for (int i = 0; i < 16; i++) {
+      const float a = d[i].x * ms2, b = d[i].y * ms2;
+      llr[2 * i]     = ((scr >> (2 * i)) & 1u) ? -a : a;
+      llr[2 * i + 1] = ((scr >> (2 * i + 1)) & 1u) ? -b : b;
+    }
+    // codewords 36.212 Table 5.3.4-1: period-3 patterns 011, 101, 110
+    uint32_t best = 0;
+    float    corr[3];
+    for (uint32_t cw = 0; cw < 3; cw++) {
+      float acc = 0.0f;
+      for (int i = 0; i < 32; i++) {
+        const bool bit = ((i + (3 - cw) % 3) % 3) != 0; // cw0: 0,1,1  cw1: 1,0,1  cw2: 1,1,0
+        acc            = acc + (bit ? llr[i] : -llr[i]);
+      }
+      corr[cw] = acc;
+      if (acc > corr[best]) best = cw;
+    }
+    for (int i = 0; i < 3; i++) info[sf].pcfich_corr[i] = corr[i];
+    info[sf].cfi           = best + 1;
+    info[sf].nof_cce       = c.nof_cce[best];
+    info[sf].nof_locations = c.nloc[best];
+    cfi_s                  = best + 1;
+  }
+  __syncthreads();
+  const uint32_t  cfi = cfi_s, nof_cce = c.nof_cce[cfi - 1], nq = nof_cce * 9;
+  const uint16_t* map = c.pdcch_idx[cfi - 1];
+  const uint32_t* scr = c.pdcch_scr + (size_t)sf_idx * c.pdcch_scr_words;
+  float*          llr = llr_all + (size_t)sf * LLR_STRIDE;
+  for (uint32_t q = tid; q < nq; q += nt) {
+    uint32_t idx[4];
+    float2   d[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) idx[j] = map[4 * q + j];
+    if (c.nof_ports == 1) {
+#pragma unroll
+      for (int j = 0; j < 4; j++) d[j] = eq_port0(c, v, idx[j]);
+    } else {
+      eq_sfbc(c, v, idx[0], idx[1], d[0], d[1]);
+      eq_sfbc(c, v, idx[2], idx[3], d[2], d[3]);
+    }
+    const uint32_t sb = (scr[(8 * q) >> 5] >> ((8 * q) & 31)) & 0xFFu;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      const float a = d[j].x * ms2, b = d[j].y * ms2;
+      llr[8 * q + 2 * j]     = ((sb >> (2 * j)) & 1u) ? -a : a;
+      llr[8 * q + 2 * j + 1] = ((sb >> (2 * j + 1)) & 1u) ? -b : b;
+    }
+  }
+  for (uint32_t i = nq * 8 + tid; i < LLR_STRIDE; i += nt) llr[i] = 0.0f;
+  __syncthreads();
+  for (uint32_t cce = tid; cce < LTEPHY_MAX_CCE; cce += nt) {
+    float pw = 0.0f;
+    if (cce < nof_cce) {
+      double m = 0.0;
+      for (int i = 0; i < 72; i++) m += (double)fabsf(llr[cce * 72 + i]);
+      pw = (float)(m / 72.0);
+    }
+    info[sf].cce_power[cce] = pw;
+  }
+}
+
+// ---- launchers ----------------------------------------------------------------------------------
+extern "C" void launch_frontend(const DevCell& c, const float2* iq, float2* sym, float2* ce, float* llr, DevSfInfo* info, uint32_t n,
+                                cudaStream_t st, uint64_t* launches)
+{
+  const uint32_t fft_threads = c.fft / 8 < 32 ? 32 : c.fft / 8;
+  const size_t   smem_fft    = (size_t)c.fft * 8 * 2 + (size_t)c.fft * 4;
+  ofdm_rx_kernel<<<dim3(14, c.nof_rx, n), fft_threads, smem_fft, st>>>(c, iq, sym);
+  const size_t smem_ch = (size_t)2 * NPILSYM * 2 * c.nof_prb * sizeof(float2);
+  chest_kernel<<<dim3(c.nof_ports * c.nof_rx, n), 256, smem_ch, st>>>(c, sym, ce, info);
+  rb_power_kernel<<<n, 128, 0, st>>>(c, sym, info);
+  pdcch_llr_kernel<<<n, 256, 0, st>>>(c, sym, ce, llr, info);
+  *launches += 4;
+}

@@ -1,0 +1,377 @@
+// k_turbo.cu -- K8: max-log-MAP turbo decoder, batched over every code block of the batch.
+// One CTA decodes a PAIR of code blocks of equal size K: the two trellises live in the low and high
+// halves of packed int16x2 registers (VIADD.16x2 / VIADDMNMX.S16x2 / VIMNMX.S16x2), one thread per
+// 32-step window, 8 state metrics per thread in registers, window-boundary metrics carried over from
+// the previous iteration (next-iteration initialisation), alpha kept in shared memory for 16 steps at a
+// time.  Restates the srsran_tdec_* behaviour reached through srsran_dlsch_decode2 (reference
+// src/src/DL_Sniffer_PDSCH.cc:997): int16 LLRs, CRC24B/CRC24A early stop, at least one iteration.
+// The arithmetic is the CPU oracle's (oracle/lte_oracle.c, siso()): outputs are offset-invariant, so
+// the int16 normalisation schedule below does not change any decision.
+#include "dev_common.cuh"
+
+#define TD_WL 32
+#define TD_HALF 16
+#define TD_NINF (-8192)
+
+__device__ __forceinline__ uint32_t vadd(uint32_t a, uint32_t b) { return __vadd2(a, b); }
+__device__ __forceinline__ uint32_t vneg(uint32_t a) { return __vneg2(a); }
+__device__ __forceinline__ uint32_t vamax(uint32_t a, uint32_t b, uint32_t c) { return __viaddmax_s16x2(a, b, c); } // max(a+b, c)
+__device__ __forceinline__ uint32_t vmax(uint32_t a, uint32_t b) { return __vmaxs2(a, b); }
+__device__ __forceinline__ uint32_t pk2(int lo, int hi) { return ((uint32_t)lo & 0xFFFFu) | ((uint32_t)hi << 16); }
+__device__ __forceinline__ int      lo_s(uint32_t v) { return (int)(short)(v & 0xFFFFu); }
+__device__ __forceinline__ int      hi_s(uint32_t v) { return (int)(short)(v >> 16); }
+
+struct St8 {
+  uint32_t s[8];
+};
+
+__device__ __forceinline__ void alpha_step(St8& a, uint32_t g0, uint32_t g1, uint32_t ng0, uint32_t ng1)
+{
+  St8 n;
+  n.s[0] = vamax(a.s[0], ng0, vadd(a.s[1], g0));
+  n.s[4] = vamax(a.s[0], g0, vadd(a.s[1], ng0));
+  n.s[1] = vamax(a.s[2], g1, vadd(a.s[3], ng1));
+  n.s[5] = vamax(a.s[2], ng1, vadd(a.s[3], g1));
+  n.s[2] = vamax(a.s[4], ng1, vadd(a.s[5], g1));
+  n.s[6] = vamax(a.s[4], g1, vadd(a.s[5], ng1));
+  n.s[3] = vamax(a.s[6], g0, vadd(a.s[7], ng0));
+  n.s[7] = vamax(a.s[6], ng0, vadd(a.s[7], g0));
+  a      = n;
+}
+__device__ __forceinline__ void norm8(St8& a)
+{
+  const uint32_t r = vneg(a.s[0]);
+#pragma unroll
+  for (int i = 0; i < 8; i++) a.s[i] = vadd(a.s[i], r);
+}
+// beta update + LLR numerators. b = beta_{k+1} in, beta_k out; al = alpha_k.
+__device__ __forceinline__ void beta_llr_step(St8& b, const St8& al, uint32_t g0, uint32_t g1, uint32_t ng0, uint32_t ng1, uint32_t& m1, uint32_t& m0)
+{
+  uint32_t c0[8], c1[8];
+  c0[0] = vadd(b.s[0], ng0), c1[0] = vadd(b.s[4], g0);
+  c0[1] = vadd(b.s[4], ng0), c1[1] = vadd(b.s[0], g0);
+  c0[2] = vadd(b.s[5], ng1), c1[2] = vadd(b.s[1], g1);
+  c0[3] = vadd(b.s[1], ng1), c1[3] = vadd(b.s[5], g1);
+  c0[4] = vadd(b.s[2], ng1), c1[4] = vadd(b.s[6], g1);
+  c0[5] = vadd(b.s[6], ng1), c1[5] = vadd(b.s[2], g1);
+  c0[6] = vadd(b.s[7], ng0), c1[6] = vadd(b.s[3], g0);
+  c0[7] = vadd(b.s[3], ng0), c1[7] = vadd(b.s[7], g0);
+  m1    = vadd(al.s[0], c1[0]);
+  m0    = vadd(al.s[0], c0[0]);
+#pragma unroll
+  for (int s = 1; s < 8; s++) {
+    m1 = vamax(al.s[s], c1[s], m1);
+    m0 = vamax(al.s[s], c0[s], m0);
+  }
+#pragma unroll
+  for (int s = 0; s < 8; s++) b.s[s] = vmax(c0[s], c1[s]);
+}
+__device__ __forceinline__ int ext_of(int L, int xa)
+{
+  int e = (3 * (L - 2 * xa)) >> 3;
+  return e > 511 ? 511 : (e < -511 ? -511 : e);
+}
+
+struct TurboView {
+  uint32_t *sysT, *p1T, *p2T, *aprT, *extT, *tails;
+  uint32_t* bnd; // [2 siso][2 (A,B)][NW][8]
+  const uint16_t* piT;
+  uint32_t  K, NW;
+};
+
+// one SISO pass for window w.  IL = second constituent decoder (interleaved order).
+template <bool IL>
+__device__ __forceinline__ void siso_pass(const TurboView& tv, uint4* alpha_s, uint32_t* bits_s, uint32_t w, uint32_t nthreads, bool active,
+                                          const uint32_t* btail)
+{
+  const uint32_t  K = tv.K, NW = tv.NW, tid = threadIdx.x;
+  const uint32_t  k0 = w * TD_WL, len = active ? min((uint32_t)TD_WL, K - k0) : 0;
+  uint32_t*       A  = tv.bnd + (size_t)(IL ? 2 : 0) * NW * 8;
+  uint32_t*       B  = A + (size_t)NW * 8;
+  const uint32_t* par = IL ? tv.p2T : tv.p1T;
+  const uint32_t* apr = IL ? tv.extT : tv.aprT;
+  uint32_t*       out = IL ? tv.aprT : tv.extT;
+
+  St8 a0, b;
+  if (active) {
+#pragma unroll
+    for (int s = 0; s < 8; s++) {
+      a0.s[s] = (w == 0) ? (s ? pk2(TD_NINF, TD_NINF) : 0u) : A[(size_t)w * 8 + s];
+      b.s[s]  = (w == NW - 1) ? btail[s] : B[(size_t)w * 8 + s];
+    }
+  }
+  __syncthreads(); // every window has read its boundaries before anybody overwrites them
+
+  auto load = [&](uint32_t j, uint32_t& xa, uint32_t& p, uint32_t& pos) {
+    if (!IL) {
+      pos = j * NW + w;
+      xa  = vadd(tv.sysT[pos], apr[pos]);
+    } else {
+      const uint32_t pi = tv.piT[j * NW + w];
+      pos               = (pi & 31u) * NW + (pi >> 5);
+      xa                = vadd(tv.sysT[pos], apr[pos]);
+    }
+    p = par[j * NW + w];
+  };
+
+  if (active) {
+    // ---- forward over the whole window (no storage) to get alpha at TD_HALF and at the end --------
+    St8 a = a0, amid = a0;
+    for (uint32_t j = 0; j < len; j++) {
+      if (j == TD_HALF) amid = a;
+      uint32_t xa, p, pos;
+      load(j, xa, p, pos);
+      const uint32_t g0 = vadd(xa, p), g1 = vadd(xa, vneg(p));
+      alpha_step(a, g0, g1, vneg(g0), vneg(g1));
+      if ((j & 3u) == 3u) norm8(a);
+    }
+    norm8(a);
+    if (w + 1 < NW) {
+#pragma unroll
+      for (int s = 0; s < 8; s++) A[(size_t)(w + 1) * 8 + s] = a.s[s];
+    }
+    // ---- two half windows: forward with storage, then backward with LLR/extrinsic -----------------
+    for (int hw = (len > TD_HALF ? 1 : 0); hw >= 0; hw--) {
+      const uint32_t j0 = hw ? TD_HALF : 0, j1 = hw ? len : min(len, (uint32_t)TD_HALF);
+      St8            af = hw ? amid : a0;
+      for (uint32_t j = j0; j < j1; j++) {
+        alpha_s[((j - j0) * 2 + 0) * nthreads + tid] = make_uint4(af.s[0], af.s[1], af.s[2], af.s[3]);
+        alpha_s[((j - j0) * 2 + 1) * nthreads + tid] = make_uint4(af.s[4], af.s[5], af.s[6], af.s[7]);
+        uint32_t xa, p, pos;
+        load(j, xa, p, pos);
+        const uint32_t g0 = vadd(xa, p), g1 = vadd(xa, vneg(p));
+        alpha_step(af, g0, g1, vneg(g0), vneg(g1));
+        if ((j & 3u) == 3u) norm8(af);
+      }
+      for (int j = (int)j1 - 1; j >= (int)j0; j--) {
+        uint32_t xa, p, pos;
+        load((uint32_t)j, xa, p, pos);
+        const uint32_t g0 = vadd(xa, p), g1 = vadd(xa, vneg(p));
+        const uint4    u0 = alpha_s[((j - j0) * 2 + 0) * nthreads + tid], u1 = alpha_s[((j - j0) * 2 + 1) * nthreads + tid];
+        St8            al;
+        al.s[0] = u0.x, al.s[1] = u0.y, al.s[2] = u0.z, al.s[3] = u0.w, al.s[4] = u1.x, al.s[5] = u1.y, al.s[6] = u1.z, al.s[7] = u1.w;
+        uint32_t m1, m0;
+        beta_llr_step(b, al, g0, g1, vneg(g0), vneg(g1), m1, m0);
+        if ((j & 3) == 0) norm8(b);
+        const int Ll = lo_s(m1) - lo_s(m0), Lh = hi_s(m1) - hi_s(m0);
+        out[pos]     = pk2(ext_of(Ll, lo_s(xa)), ext_of(Lh, hi_s(xa)));
+        if (IL) {
+          const uint32_t pi = tv.piT[(uint32_t)j * NW + w]; // natural bit index
+          if (Ll > 0) atomicOr(&bits_s[pi >> 5], 0x80000000u >> (pi & 31u));
+          if (Lh > 0) atomicOr(&bits_s[(TD_WL * 6) + (pi >> 5)], 0x80000000u >> (pi & 31u));
+        }
+      }
+    }
+    norm8(b);
+    if (w > 0) {
+#pragma unroll
+      for (int s = 0; s < 8; s++) B[(size_t)(w - 1) * 8 + s] = b.s[s];
+    }
+  }
+  __syncthreads();
+}
+
+// GF(2) helpers for the parallel CRC24: (a * b) mod poly, degrees < 24
+__device__ __forceinline__ uint32_t gf_mulmod24(uint32_t a, uint32_t b, uint32_t poly)
+{
+  uint32_t r = 0;
+#pragma unroll 4
+  for (int i = 0; i < 24; i++) {
+    if ((b >> i) & 1u) r ^= a;
+    a <<= 1;
+    if (a & 0x1000000u) a ^= poly;
+  }
+  return r;
+}
+__device__ __forceinline__ uint32_t gf_mod24(uint32_t v, uint32_t nbits, uint32_t poly)
+{
+  uint32_t r = 0;
+  for (uint32_t i = 0; i < nbits; i++) {
+    r = (r << 1) | ((v >> (31 - i)) & 1u);
+    if (r & 0x1000000u) r ^= poly;
+  }
+  return r;
+}
+
+__global__ void __launch_bounds__(192) turbo_kernel(const DevPair* __restrict__ pairs, uint32_t* __restrict__ pool, const uint16_t* __restrict__ pi_pool,
+                                                    const uint32_t* __restrict__ pi_off, const uint32_t* __restrict__ xpowA,
+                                                    const uint32_t* __restrict__ xpowB, uint8_t* __restrict__ payload, uint8_t* __restrict__ cb_iters,
+                                                    uint8_t* __restrict__ cb_crc, uint32_t max_iter)
+{
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  uint4*             alpha_s = reinterpret_cast<uint4*>(smem_raw); // [TD_HALF][2][nthreads]
+  __shared__ uint32_t bits_s[2 * TD_WL * 6];                       // 2 x 6144 bits
+  __shared__ uint32_t btail[2][8];
+  __shared__ uint32_t red_s[8];
+  __shared__ uint32_t done_s[2];
+
+  const DevPair  P = pairs[blockIdx.x];
+  const uint32_t K = P.K, NW = P.NW, tid = threadIdx.x, nthreads = blockDim.x;
+  const bool     active = tid < NW;
+  TurboView      tv;
+  tv.sysT  = pool + P.buf_off;
+  tv.p1T   = tv.sysT + 32 * NW;
+  tv.p2T   = tv.p1T + 32 * NW;
+  tv.aprT  = tv.p2T + 32 * NW;
+  tv.extT  = tv.aprT + 32 * NW;
+  tv.tails = tv.extT + 32 * NW;
+  tv.bnd   = tv.tails + 12;
+  tv.piT   = pi_pool + pi_off[blockIdx.x];
+  tv.K = K, tv.NW = NW;
+
+  // boundary metrics start "unknown" (all zero); apr starts at zero (buffers are cleared by the host)
+  for (uint32_t i = tid; i < 4 * NW * 8; i += nthreads) tv.bnd[i] = 0u;
+  if (tid < 2) done_s[tid] = (tid < P.ncb) ? 0u : 1u;
+  if (tid == 0) {
+    // beta at K from the termination bits, both constituent codes, both code blocks (scalar int32)
+    for (int dec = 0; dec < 2; dec++) {
+      // d0 = xK, zK+1, x'K, z'K+1 ; d1 = zK, xK+2, z'K, x'K+2 ; d2 = xK+1, zK+2, x'K+1, z'K+2
+      const uint32_t* T = tv.tails;
+      uint32_t        tx[3], tz[3];
+      if (dec == 0) {
+        tx[0] = T[0], tx[1] = T[8], tx[2] = T[5];
+        tz[0] = T[4], tz[1] = T[1], tz[2] = T[9];
+      } else {
+        tx[0] = T[2], tx[1] = T[10], tx[2] = T[7];
+        tz[0] = T[6], tz[1] = T[3], tz[2] = T[11];
+      }
+      const uint8_t NEXT[8][2] = {{0, 4}, {4, 0}, {5, 1}, {1, 5}, {2, 6}, {6, 2}, {7, 3}, {3, 7}};
+      const uint8_t PAR[8][2]  = {{0, 1}, {0, 1}, {1, 0}, {1, 0}, {1, 0}, {1, 0}, {0, 1}, {0, 1}};
+      for (int h = 0; h < 2; h++) {
+        int bt[8], bn[8];
+        for (int s = 0; s < 8; s++) bt[s] = s ? TD_NINF : 0;
+        for (int k = 2; k >= 0; k--) {
+          const int x = h ? hi_s(tx[k]) : lo_s(tx[k]), z = h ? hi_s(tz[k]) : lo_s(tz[k]);
+          for (int s = 0; s < 8; s++) {
+            int best = -(1 << 30);
+            for (int u = 0; u < 2; u++) {
+              const int g = (u ? x : -x) + (PAR[s][u] ? z : -z), v = bt[NEXT[s][u]] + g;
+              best        = v > best ? v : best;
+            }
+            bn[s] = best;
+          }
+          for (int s = 0; s < 8; s++) bt[s] = bn[s];
+        }
+        const int ref = bt[0];
+        for (int s = 0; s < 8; s++) {
+          const int      v = bt[s] - ref;
+          const uint32_t o = btail[dec][s];
+          btail[dec][s]    = h ? ((o & 0xFFFFu) | ((uint32_t)v << 16)) : ((uint32_t)v & 0xFFFFu);
+        }
+      }
+    }
+  }
+  __syncthreads();
+
+  uint32_t it = 0;
+  while (it < max_iter) {
+    for (uint32_t i = tid; i < 2 * TD_WL * 6; i += nthreads) bits_s[i] = 0u;
+    siso_pass<false>(tv, alpha_s, bits_s, tid, nthreads, active, btail[0]);
+    siso_pass<true>(tv, alpha_s, bits_s, tid, nthreads, active, btail[1]);
+    it++;
+    // ---- CRC over the K decided bits of each code block -------------------------------------------
+    bool all_done = true;
+    for (uint32_t h = 0; h < 2; h++) {
+      if (done_s[h]) continue;
+      const uint32_t ct = P.crc_type[h];
+      bool           ok = false;
+      if (ct) {
+        const uint32_t  poly = ct == 1 ? 0x1864CFBu : 0x1800063u;
+        const uint32_t* xp   = ct == 1 ? xpowA : xpowB;
+        uint32_t        r    = 0;
+        if (active) {
+          const uint32_t k0 = tid * TD_WL, nb = min((uint32_t)TD_WL, K - k0), after = K - k0 - nb;
+          r                 = gf_mulmod24(gf_mod24(bits_s[h * TD_WL * 6 + tid], nb, poly), xp[after >> 3], poly);
+        }
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) r ^= __shfl_xor_sync(0xffffffffu, r, off);
+        if ((tid & 31u) == 0) red_s[tid >> 5] = r;
+        __syncthreads();
+        uint32_t tot = 0;
+        for (uint32_t i = 0; i < (nthreads + 31) / 32; i++) tot ^= red_s[i];
+        ok = (tot == 0);
+        __syncthreads();
+      }
+      if (ok || it == max_iter) {
+        // emit the data bits (skip fillers, drop the CB CRC when C > 1): byte aligned by construction
+        const uint32_t nbytes = P.out_bits[h] >> 3, skip = P.out_skip[h];
+        for (uint32_t i = tid; i < nbytes; i += nthreads) {
+          const uint32_t bit0 = skip + 8 * i;
+          payload[P.out_byte[h] + i] = (uint8_t)((bits_s[h * TD_WL * 6 + (bit0 >> 5)] >> (24 - (bit0 & 31u))) & 0xFFu);
+        }
+        if (tid == 0) {
+          cb_iters[P.cb_index[h]] = (uint8_t)it;
+          cb_crc[P.cb_index[h]]   = ok ? 1 : 0;
+          done_s[h]               = 1;
+        }
+      } else
+        all_done = false;
+    }
+    __syncthreads();
+    if (all_done) break;
+  }
+}
+
+// ---- transport-block CRC24A over the assembled payload (tbs/8 data bytes + 3 CRC bytes) -------------
+__global__ void __launch_bounds__(256) tb_crc_kernel(const DevTb* __restrict__ tbs, const uint8_t* __restrict__ payload,
+                                                     const uint8_t* __restrict__ cb_crc, const uint8_t* __restrict__ cb_iters,
+                                                     const uint32_t* __restrict__ xpowA, ltephy_tb_result_t* __restrict__ res)
+{
+  __shared__ uint32_t red_s[8];
+  const DevTb&    tb = tbs[blockIdx.x];
+  const uint32_t  tid = threadIdx.x, n = tb.nbytes + 3;
+  const uint8_t*  p = payload + tb.byte_off;
+  uint32_t        r = 0;
+  // each thread folds a contiguous run of bytes, then shifts it to its position
+  const uint32_t per = (n + blockDim.x - 1) / blockDim.x, b0 = tid * per, b1 = min(n, b0 + per);
+  if (b0 < b1) {
+    uint32_t v = 0;
+    for (uint32_t i = b0; i < b1; i++) {
+      for (int bit = 7; bit >= 0; bit--) {
+        v = (v << 1) | ((p[i] >> bit) & 1u);
+        if (v & 0x1000000u) v ^= 0x1864CFBu;
+      }
+    }
+    r = gf_mulmod24(v, xpowA[n - b1], 0x1864CFBu);
+  }
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) r ^= __shfl_xor_sync(0xffffffffu, r, off);
+  if ((tid & 31u) == 0) red_s[tid >> 5] = r;
+  __syncthreads();
+  if (tid == 0) {
+    uint32_t tot = 0;
+    for (uint32_t i = 0; i < blockDim.x / 32; i++) tot ^= red_s[i];
+    uint32_t ok = (tot == 0), its = 0;
+    for (uint32_t i = 0; i < tb.ncb; i++) {
+      if (tb.ncb > 1 && !cb_crc[tb.cb_first + i]) ok = 0;
+      its += cb_iters[tb.cb_first + i];
+    }
+    res[blockIdx.x].crc       = (uint8_t)ok;
+    res[blockIdx.x].avg_iters = (uint8_t)((its + tb.ncb - 1) / tb.ncb);
+    res[blockIdx.x].nof_cb    = (uint16_t)tb.ncb;
+  }
+}
+
+extern "C" void launch_turbo(const DevPair* pairs, uint32_t npairs, uint32_t max_threads, uint32_t* pool, const uint16_t* pi_pool,
+                             const uint32_t* pi_off, const uint32_t* xpowA, const uint32_t* xpowB, uint8_t* payload, uint8_t* cb_iters,
+                             uint8_t* cb_crc, uint32_t max_iter, cudaStream_t st, uint64_t* launches)
+{
+  if (!npairs) return;
+  uint32_t nthreads = ((max_threads + 31) / 32) * 32;
+  if (nthreads < 32) nthreads = 32;
+  const size_t smem = (size_t)TD_HALF * 2 * nthreads * sizeof(uint4);
+  static bool  attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(turbo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024);
+    attr_set = true;
+  }
+  turbo_kernel<<<npairs, nthreads, smem, st>>>(pairs, pool, pi_pool, pi_off, xpowA, xpowB, payload, cb_iters, cb_crc, max_iter);
+  *launches += 1;
+}
+extern "C" void launch_tb_crc(const DevTb* tbs, uint32_t ntb, const uint8_t* payload, const uint8_t* cb_crc, const uint8_t* cb_iters,
+                              const uint32_t* xpowA, ltephy_tb_result_t* res, cudaStream_t st, uint64_t* launches)
+{
+  if (!ntb) return;
+  tb_crc_kernel<<<ntb, 256, 0, st>>>(tbs, payload, cb_crc, cb_iters, xpowA, res);
+  *launches += 1;
+}

@@ -1,0 +1,194 @@
+// k_viterbi.cu -- K5: exhaustive blind-DCI decode.  One warp decodes TWO PDCCH candidates of the same
+// payload size at once (their path metrics share registers as packed int16x2, VIADD.16x2 / VIMNMX.S16x2);
+// the 64 trellis states are spread two per lane.  Restates srsran_pdcch_dci_decode as called from
+// srsran_pdcch_decode_msg_limit_avg_llr_power (reference lib/src/phy/falcon_phch/falcon_pdcch.c:110-170):
+// conv rate-dematch with accumulation, uint8 quantisation (gain 32 / max|x|), K=7 r=1/3 tail-biting
+// Viterbi run over three concatenated copies of which the middle one is kept, CRC16, RNTI = parity ^ crc.
+// The table T[location][size] this kernel fills is what DCISearch::inspect_dci_location_recursively
+// (src/src/DCISearch.cc:102-447) consults one entry at a time.
+#include "dev_common.cuh"
+
+#define VIT_KMAX 80          // nof_bits <= 64 -> K = nof_bits + 16 <= 80
+#define VIT_WARPS 4
+#define VIT_RENORM 16
+
+struct __align__(16) VitWarpSmem {
+  float    rm[2][3 * VIT_KMAX]; // dematched soft bits, stream-major
+  uint32_t R[3][VIT_KMAX];      // quantised symbols 2q-255, packed (cand0 lo, cand1 hi)
+  uint32_t S[VIT_KMAX][4];      // branch metrics for output patterns (1,o1,o2), packed
+  uint4    dec[2 * VIT_KMAX];   // survivor decisions of steps K..3K-1: {c0 even, c0 odd, c1 even, c1 odd}
+  uint32_t data[2][3];          // decoded K bits per candidate
+};
+
+__device__ __forceinline__ uint32_t pk(int lo, int hi) { return ((uint32_t)lo & 0xFFFFu) | ((uint32_t)hi << 16); }
+__device__ __forceinline__ int      lo16(uint32_t v) { return (int)(short)(v & 0xFFFFu); }
+__device__ __forceinline__ int      hi16(uint32_t v) { return (int)(short)(v >> 16); }
+
+__global__ void __launch_bounds__(VIT_WARPS * 32) dci_viterbi_kernel(const __grid_constant__ DevCell c, const float* __restrict__ llr_all,
+                                                                      const DevSfInfo* __restrict__ info, ltephy_cand_t* __restrict__ cands)
+{
+  __shared__ VitWarpSmem sm_all[VIT_WARPS];
+  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t pair = blockIdx.x * VIT_WARPS + warp, si = blockIdx.y, sf = blockIdx.z;
+  VitWarpSmem&   sm   = sm_all[warp];
+
+  const uint32_t cfi = info[sf].cfi;
+  if (cfi < 1 || cfi > 3) return;
+  const uint32_t nloc = c.nloc[cfi - 1];
+  if (2 * pair >= nloc) return;
+  const uint32_t nb = c.sizes[si], K = nb + 16, n3 = 3 * K;
+  const float*   llr = llr_all + (size_t)sf * LLR_STRIDE;
+  const uint16_t* tab = c.conv_tab[si];
+
+  // ---- prologue: rate-dematch (accumulating), quantise -------------------------------------------
+  bool     valid[2];
+  uint32_t loc_i[2];
+  for (int cd = 0; cd < 2; cd++) {
+    loc_i[cd] = 2 * pair + cd;
+    valid[cd] = loc_i[cd] < nloc;
+    uint32_t ncce = 0, L = 0;
+    if (valid[cd]) {
+      const uint32_t e = c.loc_tab[cfi - 1][loc_i[cd]];
+      ncce = e & 0xFFu, L = e >> 8;
+      if (c.flags & LTEPHY_FLAG_SKIP_LOW_POWER)
+        for (uint32_t i = ncce; i < ncce + (1u << L); i++)
+          if (info[sf].cce_power[i] < 0.7f) valid[cd] = false;
+    }
+    const uint32_t E  = 72u << L;
+    const float*   e  = llr + 72 * ncce;
+    float          mx = 0.0f;
+    for (uint32_t j = lane; j < n3; j += 32) {
+      float acc = 0.0f;
+      if (valid[cd])
+        for (uint32_t k = j; k < E; k += n3) acc = acc + e[k];
+      sm.rm[cd][tab[j]] = acc;
+      mx                = fmaxf(mx, fabsf(acc));
+    }
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, off));
+    if (!(mx > 0.0f)) valid[cd] = false;
+    const float gain = valid[cd] ? 32.0f / mx : 0.0f;
+    __syncwarp();
+    for (uint32_t j = lane; j < n3; j += 32) {
+      float v = sm.rm[cd][j] * gain + 127.5f;
+      v       = fminf(fmaxf(v, 0.0f), 255.0f);
+      const int r = 2 * (int)v - 255;
+      uint16_t* dst = reinterpret_cast<uint16_t*>(&sm.R[j / K][j % K]);
+      dst[cd]       = (uint16_t)(short)r;
+    }
+    __syncwarp();
+  }
+  if (!valid[0] && !valid[1]) {
+    if (lane < 2 && loc_i[lane] < LTEPHY_MAX_LOC) {
+      ltephy_cand_t o{};
+      cands[((size_t)sf * LTEPHY_MAX_LOC + loc_i[lane]) * LTEPHY_MAX_SIZES + si] = o;
+    }
+    return;
+  }
+  // branch-metric table: patterns (o0,o1,o2) = (1,0,0),(1,0,1),(1,1,0),(1,1,1); bm = sum (o ? +r : -r)
+  for (uint32_t k = lane; k < K; k += 32) {
+    const uint32_t r0 = sm.R[0][k], r1 = sm.R[1][k], r2 = sm.R[2][k];
+    const uint32_t n1 = __vneg2(r1), n2 = __vneg2(r2);
+    sm.S[k][0] = __vadd2(__vadd2(r0, n1), n2);
+    sm.S[k][1] = __vadd2(__vadd2(r0, n1), r2);
+    sm.S[k][2] = __vadd2(__vadd2(r0, r1), n2);
+    sm.S[k][3] = __vadd2(__vadd2(r0, r1), r2);
+  }
+  __syncwarp();
+
+  // ---- per-lane constants: lane j owns old states j and j+32, produces new states 2j and 2j+1 ------
+  // state bit i = c_{k-1-i}; outputs for (state j < 32, input 0): parity(j & mask); polys 133,171,165
+  const uint32_t o0 = __popc(lane & 0x36u) & 1u, o1 = __popc(lane & 0x27u) & 1u, o2 = __popc(lane & 0x2Bu) & 1u;
+  const uint32_t sidx = o0 ? (o1 * 2 + o2) : ((o1 ^ 1u) * 2 + (o2 ^ 1u));
+  const bool     sneg = !o0; // m = bm(j, input 0) = o0 ? S[sidx] : -S[sidx]
+  const uint32_t odd  = lane & 1u, lo_half = lane < 16;
+  const uint32_t src1 = odd ? 16 + (lane >> 1) : (lane >> 1);
+  const uint32_t src2 = odd ? (lane >> 1) : 16 + (lane >> 1);
+
+  uint32_t X0 = 0, X1 = 0; // packed path metrics of states j and j+32
+  for (uint32_t t = 0; t < n3; t++) {
+    const uint32_t k  = t < K ? t : (t < 2 * K ? t - K : t - 2 * K);
+    uint32_t       m  = sm.S[k][sidx];
+    uint32_t       mn = __vneg2(m);
+    if (sneg) {
+      const uint32_t tmp = m;
+      m = mn, mn = tmp;
+    }
+    // new 2j   (input 0): max(X0 + m, X1 - m) ; new 2j+1 (input 1): max(X0 - m, X1 + m); ties keep the j branch
+    bool           p0h, p0l, p1h, p1l;
+    const uint32_t N0 = __vibmax_s16x2(__vadd2(X0, m), __vadd2(X1, mn), &p0h, &p0l);
+    const uint32_t N1 = __vibmax_s16x2(__vadd2(X0, mn), __vadd2(X1, m), &p1h, &p1l);
+    if (t >= K) {
+      uint4 d;
+      d.x = __ballot_sync(0xffffffffu, !p0l); // cand0, new state 2j   -> bit j
+      d.y = __ballot_sync(0xffffffffu, !p1l); // cand0, new state 2j+1
+      d.z = __ballot_sync(0xffffffffu, !p0h); // cand1
+      d.w = __ballot_sync(0xffffffffu, !p1h);
+      if (lane == 0) sm.dec[t - K] = d;
+    }
+    // re-distribute: lane j needs new[j], new[j+32]
+    const uint32_t v1 = lo_half ? N0 : N1, v2 = lo_half ? N1 : N0;
+    const uint32_t r1 = __shfl_sync(0xffffffffu, v1, src1), r2 = __shfl_sync(0xffffffffu, v2, src2);
+    X0 = odd ? r2 : r1;
+    X1 = odd ? r1 : r2;
+    if ((t % VIT_RENORM) == VIT_RENORM - 1) {
+      const uint32_t ref = __vneg2(__shfl_sync(0xffffffffu, X0, 0));
+      X0 = __vadd2(X0, ref);
+      X1 = __vadd2(X1, ref);
+    }
+  }
+  __syncwarp();
+  // ---- best final state (lowest index on ties), per candidate ------------------------------------
+  int best_s[2];
+  for (int cd = 0; cd < 2; cd++) {
+    int v0 = cd ? hi16(X0) : lo16(X0), v1 = cd ? hi16(X1) : lo16(X1);
+    int bv = v0, bs = (int)lane;
+    if (v1 > bv) bv = v1, bs = (int)lane + 32;
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) {
+      const int ov = __shfl_xor_sync(0xffffffffu, bv, off), os = __shfl_xor_sync(0xffffffffu, bs, off);
+      if (ov > bv || (ov == bv && os < bs)) bv = ov, bs = os;
+    }
+    best_s[cd] = bs;
+  }
+  // ---- traceback (lanes 0,1: one candidate each), steps 3K-1 .. K, keep K..2K-1 --------------------
+  if (lane < 2) {
+    const int cd = (int)lane;
+    uint32_t  st = (uint32_t)best_s[cd];
+    uint32_t  w[3] = {0, 0, 0};
+    for (int t = (int)n3 - 1; t >= (int)K; t--) {
+      if (t < (int)(2 * K)) {
+        const uint32_t i = (uint32_t)t - K; // data bit index
+        w[i >> 5] |= (st & 1u) << (31 - (i & 31));
+      }
+      const uint4    d    = sm.dec[t - (int)K];
+      const uint32_t word = cd ? ((st & 1u) ? d.w : d.z) : ((st & 1u) ? d.y : d.x);
+      st                  = (st >> 1) | (((word >> (st >> 1)) & 1u) << 5);
+    }
+    // CRC16 (poly 0x11021, zero init) over the first nb bits; RNTI = received parity ^ computed
+    uint32_t reg = 0;
+    for (uint32_t i = 0; i < nb + 16; i++) {
+      const uint32_t bit = i < nb ? (w[i >> 5] >> (31 - (i & 31))) & 1u : 0u;
+      reg                = (reg << 1) | bit;
+      if (reg & 0x10000u) reg ^= 0x11021u;
+    }
+    uint32_t par = 0;
+    for (uint32_t i = nb; i < nb + 16; i++) par = (par << 1) | ((w[i >> 5] >> (31 - (i & 31))) & 1u);
+    ltephy_cand_t o{};
+    uint64_t      bits = ((uint64_t)w[0] << 32) | (uint64_t)w[1];
+    if (nb < 64) bits &= ~((~0ull) >> nb);
+    o.bits  = bits;
+    o.rnti  = (uint16_t)((par ^ reg) & 0xFFFFu);
+    o.valid = valid[cd] ? 1 : 0;
+    if (!valid[cd]) o.bits = 0, o.rnti = 0;
+    if (loc_i[cd] < LTEPHY_MAX_LOC) cands[((size_t)sf * LTEPHY_MAX_LOC + loc_i[cd]) * LTEPHY_MAX_SIZES + si] = o;
+  }
+}
+
+extern "C" void launch_viterbi(const DevCell& c, const float* llr, const DevSfInfo* info, ltephy_cand_t* cands, uint32_t n, cudaStream_t st,
+                               uint64_t* launches)
+{
+  const uint32_t max_pairs = (LTEPHY_MAX_LOC / 2 + VIT_WARPS - 1) / VIT_WARPS;
+  dci_viterbi_kernel<<<dim3(max_pairs, c.nsizes, n), VIT_WARPS * 32, 0, st>>>(c, llr, info, cands);
+  *launches += 1;
+}

@@ -1,0 +1,737 @@
+// ltephy_capi.cu -- C-ABI (include/ltephy_b200.h) of the B200 LTE PHY library: device memory, table
+// caches, job construction for phase A / phase B and kernel launches on one CUDA stream.
+// There is no CPU fallback: creation fails when no CUDA device can be used.
+#include "../../include/ltephy_b200.h"
+#include "dev_common.cuh"
+#include "lte_host.hpp"
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <tuple>
+#include <vector>
+
+extern "C" {
+void launch_frontend(const DevCell&, const float2*, float2*, float2*, float*, DevSfInfo*, uint32_t, cudaStream_t, uint64_t*);
+void launch_viterbi(const DevCell&, const float*, const DevSfInfo*, ltephy_cand_t*, uint32_t, cudaStream_t, uint64_t*);
+void launch_pdsch_front(const DevCell&, const DevGrant*, uint32_t, uint32_t, const float2*, const float2*, const uint32_t*, const uint32_t*, uint32_t,
+                        uint32_t*, short*, cudaStream_t, uint64_t*);
+void launch_rm_turbo_rx(const DevCb*, uint32_t, const DevPair*, const short*, const uint32_t*, uint32_t*, cudaStream_t, uint64_t*);
+void launch_turbo(const DevPair*, uint32_t, uint32_t, uint32_t*, const uint16_t*, const uint32_t*, const uint32_t*, const uint32_t*, uint8_t*, uint8_t*,
+                  uint8_t*, uint32_t, cudaStream_t, uint64_t*);
+void launch_tb_crc(const DevTb*, uint32_t, const uint8_t*, const uint8_t*, const uint8_t*, const uint32_t*, ltephy_tb_result_t*, cudaStream_t,
+                   uint64_t*);
+}
+
+static thread_local std::string g_err;
+static int fail(int code, const char* fmt, ...)
+{
+  char    buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return code;
+}
+#define CU(x)                                                                                      \
+  do {                                                                                             \
+    cudaError_t e_ = (x);                                                                          \
+    if (e_ != cudaSuccess) return fail(LTEPHY_ERROR, "%s: %s", #x, cudaGetErrorString(e_));        \
+  } while (0)
+
+template <typename T>
+struct DevBuf { // growable device buffer
+  T*     p   = nullptr;
+  size_t cap = 0;
+  int    reserve(size_t n)
+  {
+    if (n <= cap) return 0;
+    size_t want = n + n / 4 + 1024;
+    if (p) {
+      cudaDeviceSynchronize();
+      cudaFree(p);
+      p = nullptr;
+    }
+    if (cudaMalloc(&p, want * sizeof(T)) != cudaSuccess) {
+      cap = 0;
+      return -1;
+    }
+    cap = want;
+    return 0;
+  }
+  void release()
+  {
+    if (p) cudaFree(p);
+    p = nullptr, cap = 0;
+  }
+};
+template <typename T>
+struct PinBuf { // growable pinned host buffer
+  T*     p   = nullptr;
+  size_t cap = 0;
+  int    reserve(size_t n)
+  {
+    if (n <= cap) return 0;
+    size_t want = n + n / 4 + 1024;
+    if (p) cudaFreeHost(p);
+    p = nullptr;
+    if (cudaMallocHost(&p, want * sizeof(T)) != cudaSuccess) {
+      cap = 0;
+      return -1;
+    }
+    cap = want;
+    return 0;
+  }
+  void release()
+  {
+    if (p) cudaFreeHost(p);
+    p = nullptr, cap = 0;
+  }
+};
+
+struct ltephy {
+  ltephy_cfg_t       cfg{};
+  ltehost::Cell      cell;
+  ltehost::CtrlMap   cm;
+  ltehost::SizeTable st;
+  DevCell            dc{};
+  cudaStream_t       stream = nullptr;
+  cudaEvent_t        ev[6]{};
+  std::vector<void*> tables; // device tables freed at destroy
+  uint64_t           launches = 0;
+
+  // phase A
+  DevBuf<float2>        d_iq, d_sym, d_ce;
+  DevBuf<float>         d_llr;
+  DevBuf<DevSfInfo>     d_info;
+  DevBuf<ltephy_cand_t> d_cands;
+  PinBuf<DevSfInfo>     h_info;
+  uint32_t              n_cur = 0;
+  std::vector<uint8_t>  re_cnt; // [3 sf class][3 cfi][14][nof_prb]
+
+  // phase B
+  std::vector<DevGrant> grants;
+  std::vector<DevCb>    cbs;
+  std::vector<DevPair>  pairs;
+  std::vector<DevTb>    tbs;
+  std::vector<uint32_t> pair_pi_off;
+  std::vector<uint32_t> tb_slot; // result slot [grant*2 + tb] -> tb index or ~0
+  DevBuf<DevGrant>      d_grants;
+  DevBuf<DevCb>         d_cbs;
+  DevBuf<DevPair>       d_pairs;
+  DevBuf<DevTb>         d_tbs;
+  DevBuf<uint32_t>      d_pair_pi_off;
+  DevBuf<uint32_t>      d_seq, d_rm, d_turbo;
+  DevBuf<short>         d_pllr;
+  DevBuf<uint16_t>      d_pi;
+  DevBuf<uint8_t>       d_payload, d_cb_iters, d_cb_crc;
+  DevBuf<ltephy_tb_result_t> d_res;
+  PinBuf<ltephy_tb_result_t> h_res;
+  PinBuf<uint8_t>            h_payload;
+  size_t                     payload_bytes = 0, pllr_elems = 0;
+  uint32_t *                 d_gold_x1 = nullptr, *d_gold_basis = nullptr, gold_words = 0;
+  uint32_t *                 d_xpowA = nullptr, *d_xpowB = nullptr;
+  std::map<std::tuple<uint32_t, uint32_t, uint32_t>, std::pair<uint32_t, uint32_t>> rm_cache; // (K,F,rv) -> (offset, nn)
+  size_t                                                                            rm_used = 0;
+  std::map<uint32_t, uint32_t>                                                      pi_cache; // K -> offset
+  size_t                                                                            pi_used = 0;
+  std::map<uint32_t, ltehost::Segm>                                                 segm_cache;
+  float                                                                             t_ms[4]{};
+};
+
+template <typename T>
+static T* upload(ltephy* h, const T* src, size_t n)
+{
+  T* d = nullptr;
+  if (cudaMalloc(&d, n * sizeof(T)) != cudaSuccess) return nullptr;
+  cudaMemcpy(d, src, n * sizeof(T), cudaMemcpyHostToDevice);
+  h->tables.push_back(d);
+  return d;
+}
+
+extern "C" const char* ltephy_last_error(void) { return g_err.c_str(); }
+
+extern "C" int ltephy_create(const ltephy_cfg_t* cfg, ltephy_t** out)
+{
+  if (!cfg || !out) return fail(LTEPHY_ERROR_INVALID_INPUTS, "null argument");
+  if (cfg->nof_prb <= 10 || cfg->nof_prb > 100 || cfg->nof_ports < 1 || cfg->nof_ports > 2 || cfg->nof_rx < 1 || cfg->nof_rx > 2 ||
+      cfg->max_subframes == 0)
+    return fail(LTEPHY_ERROR_INVALID_INPUTS, "unsupported cell/batch configuration");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(LTEPHY_ERROR, "no CUDA device: this library has no CPU path");
+  CU(cudaSetDevice(cfg->device));
+  ltephy* h = new ltephy();
+  h->cfg    = *cfg;
+  if (!h->cfg.turbo_max_iter) h->cfg.turbo_max_iter = 8;
+  if (!h->cfg.max_grants) h->cfg.max_grants = 24 * cfg->max_subframes;
+  h->cell = {cfg->nof_prb, cfg->nof_ports, cfg->cell_id, cfg->nof_rx};
+  if (!ltehost::build_ctrl_map(h->cell, h->cm)) {
+    delete h;
+    return fail(LTEPHY_ERROR_INVALID_INPUTS, "control region map failed");
+  }
+  h->st = ltehost::dci_size_table(h->cell);
+  CU(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  for (auto& e : h->ev) CU(cudaEventCreate(&e));
+
+  DevCell& c = h->dc;
+  c.nof_prb = cfg->nof_prb, c.nof_ports = cfg->nof_ports, c.cell_id = cfg->cell_id, c.nof_rx = cfg->nof_rx;
+  c.fft = ltehost::fft_size(cfg->nof_prb), c.nsc = 12 * cfg->nof_prb, c.sf_len = 15 * c.fft;
+  for (c.log2n = 0; (1u << c.log2n) < c.fft; c.log2n++) {
+  }
+  uint32_t pos = 0;
+  for (uint32_t l = 0; l < 14; l++) {
+    pos += ltehost::cp_len(c.fft, l % 7);
+    c.sym_off[l] = pos;
+    pos += c.fft;
+  }
+  for (int p = 0; p < 2; p++) {
+    c.crs_off[p][0] = ltehost::crs_offset(h->cell, p, 0);
+    c.crs_off[p][1] = ltehost::crs_offset(h->cell, p, 4);
+  }
+  { // smoothing filter {4,1} (src/src/SubframeWorker.cc:379-389), evaluated exactly like the oracle
+    float s = 0.0f;
+    for (int i = 0; i < 5; i++) {
+      c.filt[i] = (float)std::exp(-(double)((i - 2) * (i - 2)) / 2.0);
+      s         = s + c.filt[i];
+    }
+    float s2 = 0.0f;
+    for (int i = 0; i < 5; i++) {
+      c.filt[i] = c.filt[i] / s;
+      s2        = s2 + c.filt[i] * c.filt[i];
+    }
+    c.noise_corr = (1.0f - 2.0f * c.filt[2]) + s2;
+    for (int j = -5; j <= 11; j++) c.interp_c[j + 5] = (float)j / 6.0f;
+    for (uint32_t l = 0; l < 14; l++) {
+      if (l < 4)
+        c.t_ia[l] = 0, c.t_ib[l] = 1, c.t_frac[l] = (float)l / 4.0f;
+      else if (l < 7)
+        c.t_ia[l] = 1, c.t_ib[l] = 2, c.t_frac[l] = (float)(l - 4) / 3.0f;
+      else if (l < 11)
+        c.t_ia[l] = 2, c.t_ib[l] = 3, c.t_frac[l] = (float)(l - 7) / 4.0f;
+      else
+        c.t_ia[l] = 2, c.t_ib[l] = 3, c.t_frac[l] = (float)(l - 11) / 4.0f;
+    }
+  }
+  { // twiddles
+    std::vector<float2> tw(c.fft / 2);
+    for (uint32_t k = 0; k < c.fft / 2; k++) {
+      double a = -2.0 * M_PI * (double)k / (double)c.fft;
+      tw[k]    = make_float2((float)std::cos(a), (float)std::sin(a));
+    }
+    c.tw = upload(h, tw.data(), tw.size());
+  }
+  {
+    auto crs = ltehost::crs_table(h->cell);
+    c.crs    = reinterpret_cast<const float2*>(upload(h, crs.data(), crs.size()));
+  }
+  c.nsizes = (uint32_t)h->st.sizes.size();
+  if (c.nsizes > LTEPHY_MAX_SIZES) return fail(LTEPHY_ERROR, "too many distinct DCI sizes");
+  for (uint32_t i = 0; i < c.nsizes; i++) {
+    c.sizes[i]    = h->st.sizes[i];
+    auto t        = ltehost::conv_rm_table(c.sizes[i] + 16);
+    c.conv_tab[i] = upload(h, t.data(), t.size());
+  }
+  for (uint32_t cfi = 0; cfi < 3; cfi++) {
+    c.nof_cce[cfi] = h->cm.nof_cce[cfi];
+    c.pdcch_idx[cfi] = upload(h, h->cm.pdcch_idx[cfi].data(), h->cm.pdcch_idx[cfi].size());
+    auto                  locs = ltehost::all_locations(c.nof_cce[cfi]);
+    std::vector<uint16_t> lt;
+    for (auto& l : locs) lt.push_back((uint16_t)(l.ncce | (l.L << 8)));
+    c.nloc[cfi]    = (uint32_t)lt.size();
+    c.loc_tab[cfi] = upload(h, lt.data(), lt.size());
+  }
+  memcpy(c.pcfich_idx, h->cm.pcfich_idx, sizeof(c.pcfich_idx));
+  {
+    c.pdcch_scr_words = (LTEPHY_MAX_CCE * 72 + 31) / 32;
+    std::vector<uint32_t> scr(10 * c.pdcch_scr_words);
+    for (uint32_t sf = 0; sf < 10; sf++) {
+      auto w = ltehost::gold_words((sf << 9) + c.cell_id, LTEPHY_MAX_CCE * 72);
+      std::copy(w.begin(), w.end(), scr.begin() + sf * c.pdcch_scr_words);
+      c.pcfich_scr[sf] = ltehost::gold_words((sf + 1) * (2 * c.cell_id + 1) * 512u + c.cell_id, 32)[0];
+    }
+    c.pdcch_scr = upload(h, scr.data(), scr.size());
+  }
+  c.flags = cfg->flags;
+  { // Gold basis for PDSCH descrambling: up to 14*nsc*8 bits per codeword
+    auto gb         = ltehost::gold_basis(14 * c.nsc * 8);
+    h->gold_words   = gb.nwords;
+    h->d_gold_x1    = upload(h, gb.x1.data(), gb.x1.size());
+    h->d_gold_basis = upload(h, gb.basis.data(), gb.basis.size());
+    auto xa = ltehost::crc24_xpow8(ltehost::CRC24A, 16384), xb = ltehost::crc24_xpow8(ltehost::CRC24B, 1024);
+    h->d_xpowA = upload(h, xa.data(), xa.size());
+    h->d_xpowB = upload(h, xb.data(), xb.size());
+  }
+  { // data-RE count per (subframe class, cfi, symbol, prb)
+    const uint32_t N = c.nof_prb;
+    h->re_cnt.resize((size_t)3 * 3 * 14 * N);
+    const uint32_t cls_sf[3] = {0, 5, 1};
+    uint16_t       kk[12];
+    for (uint32_t cls = 0; cls < 3; cls++)
+      for (uint32_t cfi = 1; cfi <= 3; cfi++)
+        for (uint32_t l = 0; l < 14; l++)
+          for (uint32_t prb = 0; prb < N; prb++)
+            h->re_cnt[((cls * 3 + (cfi - 1)) * 14 + l) * N + prb] = (uint8_t)ltehost::pdsch_re_in_prb(h->cell, cls_sf[cls], cfi, l, prb, kk);
+  }
+  const size_t S = cfg->max_subframes, g = (size_t)14 * c.nsc;
+  if (h->d_iq.reserve(S * c.nof_rx * c.sf_len) || h->d_sym.reserve(S * c.nof_rx * g) || h->d_ce.reserve(S * c.nof_ports * c.nof_rx * g) ||
+      h->d_llr.reserve(S * LLR_STRIDE) || h->d_info.reserve(S) || h->d_cands.reserve(S * LTEPHY_MAX_LOC * LTEPHY_MAX_SIZES) ||
+      h->h_info.reserve(S) || h->d_rm.reserve((size_t)16 << 20) || h->d_pi.reserve((size_t)188 * 6144)) {
+    ltephy_destroy(h);
+    return fail(LTEPHY_ERROR, "device allocation failed");
+  }
+  CU(cudaMemset(h->d_cands.p, 0, h->d_cands.cap * sizeof(ltephy_cand_t)));
+  *out = h;
+  return LTEPHY_SUCCESS;
+}
+
+extern "C" void ltephy_destroy(ltephy_t* h)
+{
+  if (!h) return;
+  cudaDeviceSynchronize();
+  for (void* p : h->tables) cudaFree(p);
+  h->d_iq.release(), h->d_sym.release(), h->d_ce.release(), h->d_llr.release(), h->d_info.release(), h->d_cands.release();
+  h->h_info.release(), h->d_grants.release(), h->d_cbs.release(), h->d_pairs.release(), h->d_tbs.release(), h->d_pair_pi_off.release();
+  h->d_seq.release(), h->d_rm.release(), h->d_turbo.release(), h->d_pllr.release(), h->d_pi.release(), h->d_payload.release();
+  h->d_cb_iters.release(), h->d_cb_crc.release(), h->d_res.release(), h->h_res.release(), h->h_payload.release();
+  for (auto& e : h->ev)
+    if (e) cudaEventDestroy(e);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+}
+
+extern "C" uint32_t ltephy_sf_len(const ltephy_t* h) { return h->dc.sf_len; }
+extern "C" uint32_t ltephy_nof_cce(const ltephy_t* h, uint32_t cfi) { return cfi >= 1 && cfi <= 3 ? h->dc.nof_cce[cfi - 1] : 0; }
+extern "C" uint32_t ltephy_nof_sizes(const ltephy_t* h) { return h->dc.nsizes; }
+extern "C" uint32_t ltephy_dci_size(const ltephy_t* h, uint32_t f) { return f < LTEPHY_NOF_FORMATS ? h->st.sizes[h->st.index_of[f]] : 0; }
+extern "C" uint32_t ltephy_size_index(const ltephy_t* h, uint32_t f) { return f < LTEPHY_NOF_FORMATS ? h->st.index_of[f] : 0; }
+extern "C" uint32_t ltephy_locations(const ltephy_t* h, uint32_t cfi, uint16_t* ncce, uint8_t* L, uint32_t max)
+{
+  if (cfi < 1 || cfi > 3) return 0;
+  auto     v = ltehost::all_locations(h->dc.nof_cce[cfi - 1]);
+  uint32_t n = (uint32_t)std::min<size_t>(v.size(), max);
+  for (uint32_t i = 0; i < n; i++) ncce[i] = v[i].ncce, L[i] = v[i].L;
+  return n;
+}
+extern "C" uint64_t ltephy_launch_count(const ltephy_t* h) { return h->launches; }
+extern "C" int      ltephy_last_timing(ltephy_t* h, float ms[4])
+{
+  memcpy(ms, h->t_ms, sizeof(h->t_ms));
+  return LTEPHY_SUCCESS;
+}
+
+// ---------------------------------------------------------------------------------------- phase A
+static int phase_a_common(ltephy* h, const uint32_t* tti, uint32_t n)
+{
+  for (uint32_t i = 0; i < n; i++) {
+    memset(&h->h_info.p[i], 0, sizeof(DevSfInfo));
+    h->h_info.p[i].tti = tti[i];
+  }
+  CU(cudaMemcpyAsync(h->d_info.p, h->h_info.p, n * sizeof(DevSfInfo), cudaMemcpyHostToDevice, h->stream));
+  launch_frontend(h->dc, h->d_iq.p, h->d_sym.p, h->d_ce.p, h->d_llr.p, h->d_info.p, n, h->stream, &h->launches);
+  launch_viterbi(h->dc, h->d_llr.p, h->d_info.p, h->d_cands.p, n, h->stream, &h->launches);
+  CU(cudaEventRecord(h->ev[1], h->stream));
+  CU(cudaGetLastError());
+  h->n_cur = n;
+  return LTEPHY_SUCCESS;
+}
+extern "C" int ltephy_submit_iq(ltephy_t* h, const float* iq, const uint32_t* tti, uint32_t n)
+{
+  if (!h || !iq || !tti || n == 0 || n > h->cfg.max_subframes) return fail(LTEPHY_ERROR_INVALID_INPUTS, "submit_iq: bad arguments");
+  CU(cudaSetDevice(h->cfg.device));
+  CU(cudaEventRecord(h->ev[0], h->stream));
+  CU(cudaMemcpyAsync(h->d_iq.p, iq, (size_t)n * h->dc.nof_rx * h->dc.sf_len * sizeof(float2), cudaMemcpyHostToDevice, h->stream));
+  return phase_a_common(h, tti, n);
+}
+extern "C" int ltephy_submit_iq_device(ltephy_t* h, const void* iq_dev, const uint32_t* tti, uint32_t n)
+{
+  if (!h || !iq_dev || !tti || n == 0 || n > h->cfg.max_subframes) return fail(LTEPHY_ERROR_INVALID_INPUTS, "submit_iq_device: bad arguments");
+  CU(cudaSetDevice(h->cfg.device));
+  CU(cudaEventRecord(h->ev[0], h->stream));
+  if (iq_dev != h->d_iq.p)
+    CU(cudaMemcpyAsync(h->d_iq.p, iq_dev, (size_t)n * h->dc.nof_rx * h->dc.sf_len * sizeof(float2), cudaMemcpyDeviceToDevice, h->stream));
+  return phase_a_common(h, tti, n);
+}
+extern "C" int ltephy_get_phase_a(ltephy_t* h, ltephy_sf_info_t* info, ltephy_cand_t* cands)
+{
+  if (!h || !h->n_cur) return fail(LTEPHY_ERROR_INVALID_INPUTS, "get_phase_a: nothing submitted");
+  const uint32_t n = h->n_cur;
+  CU(cudaMemcpyAsync(h->h_info.p, h->d_info.p, n * sizeof(DevSfInfo), cudaMemcpyDeviceToHost, h->stream));
+  if (cands)
+    CU(cudaMemcpyAsync(cands, h->d_cands.p, (size_t)n * LTEPHY_MAX_LOC * LTEPHY_MAX_SIZES * sizeof(ltephy_cand_t), cudaMemcpyDeviceToHost,
+                       h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  cudaEventElapsedTime(&h->t_ms[0], h->ev[0], h->ev[1]);
+  const float npa = (float)(h->dc.nof_ports * h->dc.nof_rx);
+  for (uint32_t i = 0; i < n; i++) {
+    DevSfInfo& s  = h->h_info.p[i];
+    float      ns = 0.0f, ps = 0.0f;
+    for (uint32_t p = 0; p < h->dc.nof_ports; p++)
+      for (uint32_t a = 0; a < h->dc.nof_rx; a++) {
+        ns = ns + s.noise[p][a];
+        ps = ps + s.rsrp[p][a];
+      }
+    s.noise_avg = ns / npa;
+    s.rsrp_avg  = ps / npa;
+    s.snr_db    = 10.0f * log10f(s.rsrp_avg / s.noise_avg);
+    s.cfo       = atan2f(s.cfo_im, s.cfo_re) / (2.0f * (float)M_PI * 7.5f);
+    if (info) memcpy(&info[i], &s, sizeof(s));
+  }
+  return LTEPHY_SUCCESS;
+}
+
+// ---------------------------------------------------------------------------------------- phase B
+static int rm_table_for(ltephy* h, uint32_t K, uint32_t F, uint32_t rv, uint32_t& off, uint32_t& nn)
+{
+  auto key = std::make_tuple(K, F, rv);
+  auto it  = h->rm_cache.find(key);
+  if (it != h->rm_cache.end()) {
+    off = it->second.first, nn = it->second.second;
+    return 0;
+  }
+  auto t = ltehost::rm_turbo_table(K, F, rv);
+  if (h->rm_used + t.first.size() > h->d_rm.cap) { // cache full: start over (tables already queued stay valid until the stream drains)
+    cudaStreamSynchronize(h->stream);
+    h->rm_cache.clear();
+    h->rm_used = 0;
+  }
+  off = (uint32_t)h->rm_used, nn = t.nn;
+  if (cudaMemcpyAsync(h->d_rm.p + off, t.first.data(), t.first.size() * 4, cudaMemcpyHostToDevice, h->stream) != cudaSuccess) return -1;
+  cudaStreamSynchronize(h->stream); // source vector dies at scope exit
+  h->rm_used += t.first.size();
+  h->rm_cache[key] = {off, nn};
+  return 0;
+}
+static int pi_table_for(ltephy* h, uint32_t K, uint32_t& off)
+{
+  auto it = h->pi_cache.find(K);
+  if (it != h->pi_cache.end()) {
+    off = it->second;
+    return 0;
+  }
+  uint32_t f1, f2;
+  if (!ltehost::qpp_params(K, f1, f2)) return -1;
+  const uint32_t        NW = (K + 31) / 32;
+  std::vector<uint16_t> t((size_t)32 * NW, 0);
+  for (uint64_t i = 0; i < K; i++) t[(i & 31) * NW + (i >> 5)] = (uint16_t)((f1 * i + f2 * i * i) % K);
+  if (h->pi_used + t.size() > h->d_pi.cap) return -1;
+  off = (uint32_t)h->pi_used;
+  if (cudaMemcpyAsync(h->d_pi.p + off, t.data(), t.size() * 2, cudaMemcpyHostToDevice, h->stream) != cudaSuccess) return -1;
+  cudaStreamSynchronize(h->stream);
+  h->pi_used += t.size();
+  h->pi_cache[K] = off;
+  return 0;
+}
+
+static int build_jobs(ltephy* h, const ltephy_grant_t* gin, uint32_t n, size_t& seq_words, size_t& turbo_words, uint32_t& max_scr_words)
+{
+  const DevCell& c = h->dc;
+  const uint32_t N = c.nof_prb;
+  h->grants.clear(), h->cbs.clear(), h->pairs.clear(), h->tbs.clear(), h->pair_pi_off.clear();
+  h->tb_slot.assign((size_t)n * 2, 0xFFFFFFFFu);
+  h->pllr_elems = 0, h->payload_bytes = 0;
+  seq_words = 0, turbo_words = 0, max_scr_words = 0;
+  std::map<uint32_t, uint32_t> open_pair; // K -> pair index with a free half
+  for (uint32_t gi = 0; gi < n; gi++) {
+    const ltephy_grant_t& g = gin[gi];
+    if (g.sf >= h->n_cur) return fail(LTEPHY_ERROR_INVALID_INPUTS, "grant %u: subframe %u outside the batch", gi, g.sf);
+    DevGrant d{};
+    d.sf = g.sf, d.sf_idx = h->h_info.p[g.sf].tti % 10, d.cfi = h->h_info.p[g.sf].cfi, d.rnti = g.rnti, d.tx_scheme = g.tx_scheme;
+    if (d.cfi < 1 || d.cfi > 3) return fail(LTEPHY_ERROR_INVALID_INPUTS, "grant %u: subframe has no CFI (phase A not fetched?)", gi);
+    memcpy(d.prb_mask, g.prb_mask, sizeof(d.prb_mask));
+    const uint32_t cls = d.sf_idx == 0 ? 0 : d.sf_idx == 5 ? 1 : 2;
+    const uint8_t* cnt = &h->re_cnt[((size_t)(cls * 3 + d.cfi - 1) * 14) * N];
+    uint32_t       acc = 0;
+    for (uint32_t l = 0; l < 14; l++) {
+      d.re_off[l] = acc;
+      const uint32_t* m = d.prb_mask[l / 7];
+      for (uint32_t prb = 0; prb < N; prb++)
+        if ((m[prb >> 5] >> (prb & 31)) & 1u) acc += cnt[l * N + prb];
+    }
+    d.re_off[14] = acc;
+    d.nof_re     = acc;
+    if (acc != g.nof_re) return fail(LTEPHY_ERROR_INVALID_INPUTS, "grant %u: nof_re %u does not match the PRB mask (%u)", gi, g.nof_re, acc);
+    const bool two_cw = g.tx_scheme == LTEPHY_TX_CDD || (g.tx_scheme == LTEPHY_TX_SPATIALMUX && g.nof_tb == 2);
+    if (g.tx_scheme == LTEPHY_TX_SPATIALMUX) return fail(LTEPHY_ERROR_INVALID_INPUTS, "grant %u: spatial multiplexing not implemented yet", gi);
+    if (g.tx_scheme == LTEPHY_TX_CDD && !(c.nof_ports == 2 && c.nof_rx == 2)) return fail(LTEPHY_ERROR_INVALID_INPUTS, "grant %u: CDD needs 2x2", gi);
+    if (g.tx_scheme == LTEPHY_TX_DIVERSITY && c.nof_ports != 2) return fail(LTEPHY_ERROR_INVALID_INPUTS, "grant %u: tx diversity needs 2 ports", gi);
+    uint32_t cw = 0;
+    for (int t = 0; t < 2; t++) {
+      if (!g.tb[t].enabled) continue;
+      if (cw >= (two_cw ? 2u : 1u)) return fail(LTEPHY_ERROR_INVALID_INPUTS, "grant %u: too many transport blocks for the tx scheme", gi);
+      const uint32_t qm = g.tb[t].qm, G = acc * qm;
+      if (qm != 2 && qm != 4 && qm != 6 && qm != 8) return fail(LTEPHY_ERROR_INVALID_INPUTS, "grant %u: bad modulation order", gi);
+      d.qm[cw]      = qm;
+      d.llr_off[cw] = (uint32_t)h->pllr_elems;
+      d.scr_off[cw] = (uint32_t)seq_words;
+      const uint32_t w = (G + 31) / 32;
+      if (w > h->gold_words) return fail(LTEPHY_ERROR, "grant %u: codeword longer than the scrambling basis", gi);
+      max_scr_words = std::max(max_scr_words, w);
+      seq_words += w;
+      h->pllr_elems += (G + 7) & ~7u;
+      if (g.tb[t].tbs > 0) {
+        const uint32_t tbs = (uint32_t)g.tb[t].tbs;
+        auto           sit = h->segm_cache.find(tbs);
+        if (sit == h->segm_cache.end()) {
+          ltehost::Segm s;
+          if (!ltehost::cb_segmentation(tbs, s)) return fail(LTEPHY_ERROR_INVALID_INPUTS, "grant %u: invalid TBS %u", gi, tbs);
+          sit = h->segm_cache.emplace(tbs, s).first;
+        }
+        const ltehost::Segm& s  = sit->second;
+        const uint32_t       NL = g.tx_scheme == LTEPHY_TX_DIVERSITY ? 2 : 1;
+        DevTb                tb{};
+        tb.byte_off = (uint32_t)h->payload_bytes, tb.nbytes = tbs / 8, tb.cb_first = (uint32_t)h->cbs.size(), tb.ncb = s.C;
+        h->payload_bytes += (tb.nbytes + 3 + 3) & ~3u;
+        uint32_t rp = d.llr_off[cw], wbit = 0;
+        for (uint32_t r = 0; r < s.C; r++) {
+          DevCb cb{};
+          cb.K = s.K(r), cb.F = r == 0 ? s.F : 0, cb.E = ltehost::rm_turbo_E(G, s.C, r, qm, NL);
+          cb.llr_off = rp;
+          rp += cb.E;
+          cb.shift = qm == 2 ? 0 : qm == 4 ? 1 : 2;
+          if (rm_table_for(h, cb.K, cb.F, g.tb[t].rv, cb.rm_tab, cb.rm_nn)) return fail(LTEPHY_ERROR, "rate-matching table upload failed");
+          // pair assignment
+          auto     op = open_pair.find(cb.K);
+          uint32_t pi;
+          if (op != open_pair.end()) {
+            pi = op->second;
+            open_pair.erase(op);
+            cb.half = 1;
+          } else {
+            DevPair p{};
+            p.K = cb.K, p.NW = (cb.K + 31) / 32;
+            ltehost::qpp_params(cb.K, p.f1, p.f2);
+            p.buf_off = (uint32_t)turbo_words;
+            turbo_words += (size_t)6 * 32 * p.NW + 16 + (size_t)4 * 8 * p.NW;
+            uint32_t po;
+            if (pi_table_for(h, cb.K, po)) return fail(LTEPHY_ERROR, "interleaver table upload failed");
+            pi = (uint32_t)h->pairs.size();
+            h->pairs.push_back(p);
+            h->pair_pi_off.push_back(po);
+            open_pair[cb.K] = pi;
+            cb.half         = 0;
+          }
+          cb.pair         = pi;
+          DevPair& p      = h->pairs[pi];
+          const uint32_t hh = cb.half;
+          p.ncb           = hh + 1;
+          p.crc_type[hh]  = s.C > 1 ? 2 : 1;
+          p.out_skip[hh]  = cb.F;
+          p.out_bits[hh]  = cb.K - cb.F - (s.C > 1 ? 24 : 0);
+          p.out_byte[hh]  = tb.byte_off + wbit / 8;
+          p.cb_index[hh]  = (uint32_t)h->cbs.size();
+          wbit += p.out_bits[hh];
+          h->cbs.push_back(cb);
+        }
+        h->tb_slot[(size_t)gi * 2 + t] = (uint32_t)h->tbs.size();
+        h->tbs.push_back(tb);
+      }
+      cw++;
+    }
+    d.ncw = cw;
+    h->grants.push_back(d);
+  }
+  return LTEPHY_SUCCESS;
+}
+
+static int run_turbo_stage(ltephy* h, uint32_t max_iter)
+{
+  // pairs are launched in buckets of equal CTA size so that small code blocks do not pay for 192 threads
+  std::vector<uint32_t> order(h->pairs.size());
+  for (uint32_t i = 0; i < order.size(); i++) order[i] = i;
+  // (pairs were appended in arbitrary K order: bucket by rounded thread count)
+  std::map<uint32_t, std::vector<uint32_t>> buckets;
+  for (uint32_t i = 0; i < h->pairs.size(); i++) buckets[((h->pairs[i].NW + 31) / 32) * 32].push_back(i);
+  std::vector<DevPair>  sorted;
+  std::vector<uint32_t> sorted_pi;
+  std::vector<std::pair<uint32_t, uint32_t>> ranges; // (threads, count)
+  std::vector<uint32_t> remap(h->pairs.size());
+  for (auto& b : buckets) {
+    ranges.push_back({b.first, (uint32_t)b.second.size()});
+    for (uint32_t i : b.second) {
+      remap[i] = (uint32_t)sorted.size();
+      sorted.push_back(h->pairs[i]);
+      sorted_pi.push_back(h->pair_pi_off[i]);
+    }
+  }
+  for (auto& cb : h->cbs) cb.pair = remap[cb.pair];
+  h->pairs.swap(sorted);
+  h->pair_pi_off.swap(sorted_pi);
+  if (h->d_pairs.reserve(h->pairs.size()) || h->d_pair_pi_off.reserve(h->pairs.size()) || h->d_cbs.reserve(h->cbs.size()))
+    return fail(LTEPHY_ERROR, "device allocation failed");
+  CU(cudaMemcpyAsync(h->d_pairs.p, h->pairs.data(), h->pairs.size() * sizeof(DevPair), cudaMemcpyHostToDevice, h->stream));
+  CU(cudaMemcpyAsync(h->d_pair_pi_off.p, h->pair_pi_off.data(), h->pairs.size() * 4, cudaMemcpyHostToDevice, h->stream));
+  CU(cudaMemcpyAsync(h->d_cbs.p, h->cbs.data(), h->cbs.size() * sizeof(DevCb), cudaMemcpyHostToDevice, h->stream));
+  launch_rm_turbo_rx(h->d_cbs.p, (uint32_t)h->cbs.size(), h->d_pairs.p, h->d_pllr.p, h->d_rm.p, h->d_turbo.p, h->stream, &h->launches);
+  CU(cudaEventRecord(h->ev[4], h->stream));
+  uint32_t first = 0;
+  for (auto& r : ranges) {
+    launch_turbo(h->d_pairs.p + first, r.second, r.first, h->d_turbo.p, h->d_pi.p, h->d_pair_pi_off.p + first, h->d_xpowA, h->d_xpowB,
+                 h->d_payload.p, h->d_cb_iters.p, h->d_cb_crc.p, max_iter, h->stream, &h->launches);
+    first += r.second;
+  }
+  CU(cudaEventRecord(h->ev[5], h->stream));
+  return LTEPHY_SUCCESS;
+}
+
+extern "C" int ltephy_submit_grants(ltephy_t* h, const ltephy_grant_t* gin, uint32_t n)
+{
+  if (!h || (!gin && n)) return fail(LTEPHY_ERROR_INVALID_INPUTS, "submit_grants: bad arguments");
+  CU(cudaSetDevice(h->cfg.device));
+  size_t   seq_words, turbo_words;
+  uint32_t max_scr_words;
+  int      r = build_jobs(h, gin, n, seq_words, turbo_words, max_scr_words);
+  if (r) return r;
+  if (h->d_grants.reserve(n + 1) || h->d_tbs.reserve(h->tbs.size() + 1) || h->d_seq.reserve(seq_words + 1) || h->d_pllr.reserve(h->pllr_elems + 8) ||
+      h->d_turbo.reserve(turbo_words + 1) || h->d_payload.reserve(h->payload_bytes + 4) || h->d_cb_iters.reserve(h->cbs.size() + 1) ||
+      h->d_cb_crc.reserve(h->cbs.size() + 1) || h->d_res.reserve(h->tbs.size() + 1) || h->h_res.reserve(h->tbs.size() + 1) ||
+      h->h_payload.reserve(h->payload_bytes + 4))
+    return fail(LTEPHY_ERROR, "device allocation failed");
+  CU(cudaEventRecord(h->ev[2], h->stream));
+  if (n) {
+    CU(cudaMemcpyAsync(h->d_grants.p, h->grants.data(), n * sizeof(DevGrant), cudaMemcpyHostToDevice, h->stream));
+    if (!h->tbs.empty()) CU(cudaMemcpyAsync(h->d_tbs.p, h->tbs.data(), h->tbs.size() * sizeof(DevTb), cudaMemcpyHostToDevice, h->stream));
+    if (turbo_words) CU(cudaMemsetAsync(h->d_turbo.p, 0, turbo_words * 4, h->stream));
+    launch_pdsch_front(h->dc, h->d_grants.p, n, max_scr_words, h->d_sym.p, h->d_ce.p, h->d_gold_x1, h->d_gold_basis, h->gold_words, h->d_seq.p,
+                       h->d_pllr.p, h->stream, &h->launches);
+    if (!h->cbs.empty()) {
+      r = run_turbo_stage(h, h->cfg.turbo_max_iter);
+      if (r) return r;
+      launch_tb_crc(h->d_tbs.p, (uint32_t)h->tbs.size(), h->d_payload.p, h->d_cb_crc.p, h->d_cb_iters.p, h->d_xpowA, h->d_res.p, h->stream,
+                    &h->launches);
+    }
+  }
+  CU(cudaEventRecord(h->ev[3], h->stream));
+  CU(cudaGetLastError());
+  return LTEPHY_SUCCESS;
+}
+
+extern "C" int ltephy_get_phase_b(ltephy_t* h, ltephy_tb_result_t* results, uint8_t* payload, size_t payload_cap)
+{
+  if (!h || !results) return fail(LTEPHY_ERROR_INVALID_INPUTS, "get_phase_b: bad arguments");
+  const size_t ntb = h->tbs.size();
+  if (ntb) {
+    CU(cudaMemcpyAsync(h->h_res.p, h->d_res.p, ntb * sizeof(ltephy_tb_result_t), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaMemcpyAsync(h->h_payload.p, h->d_payload.p, h->payload_bytes, cudaMemcpyDeviceToHost, h->stream));
+  }
+  CU(cudaStreamSynchronize(h->stream));
+  cudaEventElapsedTime(&h->t_ms[1], h->ev[2], h->ev[3]);
+  if (!h->cbs.empty()) cudaEventElapsedTime(&h->t_ms[2], h->ev[4], h->ev[5]);
+  size_t wp = 0;
+  for (size_t i = 0; i < h->tb_slot.size(); i++) {
+    ltephy_tb_result_t o{};
+    if (h->tb_slot[i] != 0xFFFFFFFFu) {
+      const DevTb& tb = h->tbs[h->tb_slot[i]];
+      o               = h->h_res.p[h->tb_slot[i]];
+      o.payload_off   = (uint32_t)wp;
+      o.payload_len   = tb.nbytes;
+      if (payload) {
+        if (wp + tb.nbytes > payload_cap) return fail(LTEPHY_ERROR_INVALID_INPUTS, "payload buffer too small");
+        memcpy(payload + wp, h->h_payload.p + tb.byte_off, tb.nbytes);
+      }
+      wp += tb.nbytes;
+    }
+    results[i] = o;
+  }
+  return LTEPHY_SUCCESS;
+}
+
+// ---------------------------------------------------------------------------------------- stand-alone kernels
+extern "C" int ltephy_dci_sweep(ltephy_t* h, const float* llr, const uint32_t* cfi, uint32_t n, ltephy_cand_t* cands)
+{
+  if (!h || !llr || !cfi || !cands || n == 0 || n > h->cfg.max_subframes) return fail(LTEPHY_ERROR_INVALID_INPUTS, "dci_sweep: bad arguments");
+  CU(cudaSetDevice(h->cfg.device));
+  for (uint32_t i = 0; i < n; i++) {
+    DevSfInfo& s = h->h_info.p[i];
+    memset(&s, 0, sizeof(s));
+    if (cfi[i] < 1 || cfi[i] > 3) return fail(LTEPHY_ERROR_INVALID_INPUTS, "dci_sweep: bad cfi");
+    s.cfi = cfi[i], s.nof_cce = h->dc.nof_cce[cfi[i] - 1], s.nof_locations = h->dc.nloc[cfi[i] - 1];
+    for (auto& p : s.cce_power) p = 1.0f;
+  }
+  CU(cudaMemcpyAsync(h->d_info.p, h->h_info.p, n * sizeof(DevSfInfo), cudaMemcpyHostToDevice, h->stream));
+  CU(cudaMemcpyAsync(h->d_llr.p, llr, (size_t)n * LLR_STRIDE * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+  CU(cudaEventRecord(h->ev[0], h->stream));
+  launch_viterbi(h->dc, h->d_llr.p, h->d_info.p, h->d_cands.p, n, h->stream, &h->launches);
+  CU(cudaEventRecord(h->ev[1], h->stream));
+  CU(cudaMemcpyAsync(cands, h->d_cands.p, (size_t)n * LTEPHY_MAX_LOC * LTEPHY_MAX_SIZES * sizeof(ltephy_cand_t), cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  CU(cudaGetLastError());
+  cudaEventElapsedTime(&h->t_ms[3], h->ev[0], h->ev[1]);
+  return LTEPHY_SUCCESS;
+}
+
+extern "C" int ltephy_turbo_batch(ltephy_t* h, const int16_t* d, uint32_t K, uint32_t ncb, uint32_t max_iter, int crc_type, uint8_t* bits,
+                                  uint8_t* iters, uint8_t* crc_ok)
+{
+  if (!h || !d || !bits || ncb == 0) return fail(LTEPHY_ERROR_INVALID_INPUTS, "turbo_batch: bad arguments");
+  uint32_t f1, f2;
+  if (!ltehost::qpp_params(K, f1, f2)) return fail(LTEPHY_ERROR_INVALID_INPUTS, "turbo_batch: K=%u is not a turbo block size", K);
+  CU(cudaSetDevice(h->cfg.device));
+  const uint32_t NW = (K + 31) / 32, D = K + 4, npairs = (ncb + 1) / 2;
+  const size_t   pw = (size_t)6 * 32 * NW + 16 + (size_t)4 * 8 * NW; // words per pair
+  h->pairs.clear(), h->pair_pi_off.clear(), h->cbs.clear(), h->tbs.clear();
+  uint32_t po;
+  if (pi_table_for(h, K, po)) return fail(LTEPHY_ERROR, "interleaver table upload failed");
+  std::vector<uint32_t> pool(pw * npairs, 0u);
+  const uint32_t        out_bytes = K / 8;
+  for (uint32_t p = 0; p < npairs; p++) {
+    DevPair pr{};
+    pr.K = K, pr.NW = NW, pr.f1 = f1, pr.f2 = f2, pr.buf_off = (uint32_t)(pw * p), pr.ncb = (2 * p + 1 < ncb) ? 2 : 1;
+    for (uint32_t hh = 0; hh < pr.ncb; hh++) {
+      const uint32_t cbi = 2 * p + hh;
+      pr.crc_type[hh] = (uint32_t)crc_type, pr.out_skip[hh] = 0, pr.out_bits[hh] = K, pr.out_byte[hh] = cbi * out_bytes, pr.cb_index[hh] = cbi;
+      short*         buf = reinterpret_cast<short*>(pool.data() + pr.buf_off);
+      const int16_t* src = d + (size_t)cbi * 3 * D;
+      for (uint32_t s = 0; s < 3; s++)
+        for (uint32_t i = 0; i < D; i++) {
+          const uint32_t word = i < K ? s * 32 * NW + (i & 31u) * NW + (i >> 5) : 5 * 32 * NW + s * 4 + (i - K);
+          buf[2 * word + hh]  = src[s * D + i];
+        }
+    }
+    h->pairs.push_back(pr);
+    h->pair_pi_off.push_back(po);
+  }
+  if (h->d_turbo.reserve(pool.size()) || h->d_pairs.reserve(npairs) || h->d_pair_pi_off.reserve(npairs) || h->d_payload.reserve((size_t)ncb * out_bytes) ||
+      h->d_cb_iters.reserve(ncb) || h->d_cb_crc.reserve(ncb))
+    return fail(LTEPHY_ERROR, "device allocation failed");
+  CU(cudaMemcpyAsync(h->d_turbo.p, pool.data(), pool.size() * 4, cudaMemcpyHostToDevice, h->stream));
+  CU(cudaMemcpyAsync(h->d_pairs.p, h->pairs.data(), npairs * sizeof(DevPair), cudaMemcpyHostToDevice, h->stream));
+  CU(cudaMemcpyAsync(h->d_pair_pi_off.p, h->pair_pi_off.data(), npairs * 4, cudaMemcpyHostToDevice, h->stream));
+  CU(cudaEventRecord(h->ev[4], h->stream));
+  launch_turbo(h->d_pairs.p, npairs, NW, h->d_turbo.p, h->d_pi.p, h->d_pair_pi_off.p, h->d_xpowA, h->d_xpowB, h->d_payload.p, h->d_cb_iters.p,
+               h->d_cb_crc.p, max_iter ? max_iter : 1, h->stream, &h->launches);
+  CU(cudaEventRecord(h->ev[5], h->stream));
+  std::vector<uint8_t> packed((size_t)ncb * out_bytes), it(ncb), ok(ncb);
+  CU(cudaMemcpyAsync(packed.data(), h->d_payload.p, packed.size(), cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaMemcpyAsync(it.data(), h->d_cb_iters.p, ncb, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaMemcpyAsync(ok.data(), h->d_cb_crc.p, ncb, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  CU(cudaGetLastError());
+  cudaEventElapsedTime(&h->t_ms[2], h->ev[4], h->ev[5]);
+  for (size_t i = 0; i < (size_t)ncb * K; i++) bits[i] = (packed[i >> 3] >> (7 - (i & 7))) & 1;
+  if (iters) memcpy(iters, it.data(), ncb);
+  if (crc_ok) memcpy(crc_ok, ok.data(), ncb);
+  return LTEPHY_SUCCESS;
+}
+
+extern "C" int ltephy_tap(ltephy_t* h, int what, void* dst, size_t bytes)
+{
+  if (!h || !dst) return fail(LTEPHY_ERROR_INVALID_INPUTS, "tap: bad arguments");
+  const void* src = nullptr;
+  size_t      avail = 0;
+  const size_t g = (size_t)14 * h->dc.nsc, n = h->n_cur;
+  switch (what) {
+    case LTEPHY_TAP_SYM: src = h->d_sym.p, avail = n * h->dc.nof_rx * g * sizeof(float2); break;
+    case LTEPHY_TAP_CE: src = h->d_ce.p, avail = n * h->dc.nof_ports * h->dc.nof_rx * g * sizeof(float2); break;
+    case LTEPHY_TAP_LLR: src = h->d_llr.p, avail = n * LLR_STRIDE * sizeof(float); break;
+    case LTEPHY_TAP_PDSCH_LLR: src = h->d_pllr.p, avail = h->pllr_elems * sizeof(short); break;
+    case LTEPHY_TAP_TURBO_IN: src = h->d_turbo.p, avail = h->d_turbo.cap * 4; break;
+    default: return fail(LTEPHY_ERROR_INVALID_INPUTS, "tap: unknown buffer");
+  }
+  if (bytes > avail) return fail(LTEPHY_ERROR_INVALID_INPUTS, "tap: %zu bytes requested, %zu available", bytes, avail);
+  CU(cudaStreamSynchronize(h->stream));
+  CU(cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost));
+  return LTEPHY_SUCCESS;
+}

@@ -1,0 +1,772 @@
+/*
+ * lte_oracle.c -- CPU ORACLE (test infrastructure, parity unpinned; see lte_oracle.h header).
+ * Build with -ffp-contract=off: every float expression is evaluated exactly as written.
+ */
+#include "lte_oracle.h"
+#include "../include/lte_tables.h"
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+#define NPILSYM 4
+static const uint32_t PIL_L[NPILSYM] = {0, 4, 7, 11};
+
+struct lteo {
+  lte_cell_t cell;
+  lte_regs_t regs;
+  uint32_t   fft, nsc, sf_len, log2n;
+  float *    tw_re, *tw_im; /* tw[k] = exp(-2 pi i k / N), k < N/2, rounded from double */
+  uint16_t*  bitrev;
+  uint32_t   sym_off[14];
+  /* CRS pilots [sf_idx 10][port 2][pilsym 4][2*nof_prb] */
+  cf_t*   crs;
+  float   filt[5];
+  float   noise_corr;                   /* 1 - 2 f_c + sum f^2 */
+  float   interp_c[17];                 /* (float)j / 6.0f for j = -5..11 */
+  uint8_t* pdcch_scr[10];               /* PDCCH scrambling bits per subframe */
+  uint8_t  pcfich_scr[10][32];
+};
+
+/* ---------------------------------------------------------------- deterministic reduction */
+float lteo_det_sum(const float* x, uint32_t n)
+{
+  float p[32];
+  for (uint32_t j = 0; j < 32; j++) {
+    float a = 0.0f;
+    for (uint32_t i = j; i < n; i += 32) a = a + x[i];
+    p[j] = a;
+  }
+  for (uint32_t off = 16; off >= 1; off >>= 1)
+    for (uint32_t j = 0; j < off; j++) p[j] = p[j] + p[j + off];
+  return p[0];
+}
+
+/* ---------------------------------------------------------------- create */
+lteo_t* lteo_create(const lte_cell_t* cell)
+{
+  lteo_t* q = (lteo_t*)calloc(1, sizeof(*q));
+  q->cell   = *cell;
+  if (lte_regs_init(&q->regs, cell)) {
+    free(q);
+    return NULL;
+  }
+  q->fft    = lte_fft_size(cell->nof_prb);
+  q->nsc    = 12 * cell->nof_prb;
+  q->sf_len = lte_sf_len(cell->nof_prb);
+  for (q->log2n = 0; (1u << q->log2n) < q->fft; q->log2n++) {
+  }
+  q->tw_re  = (float*)malloc(sizeof(float) * q->fft / 2);
+  q->tw_im  = (float*)malloc(sizeof(float) * q->fft / 2);
+  q->bitrev = (uint16_t*)malloc(sizeof(uint16_t) * q->fft);
+  for (uint32_t k = 0; k < q->fft / 2; k++) {
+    double a    = -2.0 * M_PI * (double)k / (double)q->fft;
+    q->tw_re[k] = (float)cos(a);
+    q->tw_im[k] = (float)sin(a);
+  }
+  for (uint32_t i = 0; i < q->fft; i++) {
+    uint32_t r = 0;
+    for (uint32_t b = 0; b < q->log2n; b++)
+      if (i & (1u << b)) r |= 1u << (q->log2n - 1 - b);
+    q->bitrev[i] = (uint16_t)r;
+  }
+  uint32_t pos = 0;
+  for (uint32_t l = 0; l < 14; l++) {
+    pos += lte_cp_len(q->fft, l % 7);
+    q->sym_off[l] = pos;
+    pos += q->fft;
+  }
+  q->crs = (cf_t*)malloc(sizeof(cf_t) * 10 * 2 * NPILSYM * 2 * cell->nof_prb);
+  for (uint32_t sf = 0; sf < 10; sf++)
+    for (uint32_t p = 0; p < 2; p++)
+      for (uint32_t li = 0; li < NPILSYM; li++)
+        lte_crs(cell, p, 2 * sf + PIL_L[li] / 7, PIL_L[li] % 7, &q->crs[((sf * 2 + p) * NPILSYM + li) * 2 * cell->nof_prb]);
+  /* gaussian smoothing filter, order 4 / sigma 1: chest cfg filter_coef {4,1}, src/src/SubframeWorker.cc:379-389 */
+  {
+    float s = 0.0f;
+    for (int i = 0; i < 5; i++) {
+      q->filt[i] = (float)exp(-(double)((i - 2) * (i - 2)) / 2.0);
+      s          = s + q->filt[i];
+    }
+    float s2 = 0.0f;
+    for (int i = 0; i < 5; i++) {
+      q->filt[i] = q->filt[i] / s;
+      s2         = s2 + q->filt[i] * q->filt[i];
+    }
+    q->noise_corr = (1.0f - 2.0f * q->filt[2]) + s2;
+  }
+  for (int j = -5; j <= 11; j++) q->interp_c[j + 5] = (float)j / 6.0f;
+  for (uint32_t sf = 0; sf < 10; sf++) {
+    q->pdcch_scr[sf] = (uint8_t*)malloc(LTE_MAX_CCE * 72);
+    lte_gold_bits((sf << 9) + cell->cell_id, q->pdcch_scr[sf], LTE_MAX_CCE * 72);
+    lte_gold_bits((sf + 1) * (2 * cell->cell_id + 1) * 512u + cell->cell_id, q->pcfich_scr[sf], 32);
+  }
+  return q;
+}
+void lteo_destroy(lteo_t* q)
+{
+  if (!q) return;
+  free(q->tw_re), free(q->tw_im), free(q->bitrev), free(q->crs);
+  for (int i = 0; i < 10; i++) free(q->pdcch_scr[i]);
+  free(q);
+}
+uint32_t lteo_nof_cce(lteo_t* q, uint32_t cfi) { return (cfi >= 1 && cfi <= 3) ? q->regs.nof_cce[cfi - 1] : 0; }
+
+/* ---------------------------------------------------------------- K1: OFDM receive
+ * restates srsran_ofdm_rx_sf as reached from srsran_ue_dl_decode_fft_estimate (DCISearch.cc:562):
+ * CP removed, forward DFT without scaling, guard bands and DC dropped.
+ * FFT = iterative radix-2 decimation-in-time, twiddles from the rounded table. */
+static void fft_fwd(const lteo_t* q, const cf_t* in, float* re, float* im)
+{
+  uint32_t n = q->fft;
+  for (uint32_t i = 0; i < n; i++) {
+    re[q->bitrev[i]] = in[i].re;
+    im[q->bitrev[i]] = in[i].im;
+  }
+  for (uint32_t s = 1; s <= q->log2n; s++) {
+    uint32_t m = 1u << s, h = m >> 1, step = n / m;
+    for (uint32_t j = 0; j < n; j += m)
+      for (uint32_t k = 0; k < h; k++) {
+        float wr = q->tw_re[k * step], wi = q->tw_im[k * step];
+        float br = re[j + k + h], bi = im[j + k + h];
+        float tr = wr * br - wi * bi;
+        float ti = wr * bi + wi * br;
+        float ar = re[j + k], ai = im[j + k];
+        re[j + k]     = ar + tr;
+        im[j + k]     = ai + ti;
+        re[j + k + h] = ar - tr;
+        im[j + k + h] = ai - ti;
+      }
+  }
+}
+void lteo_ofdm_rx(lteo_t* q, const cf_t* iq, cf_t* sym)
+{
+  float*   re = (float*)malloc(sizeof(float) * q->fft);
+  float*   im = (float*)malloc(sizeof(float) * q->fft);
+  uint32_t h  = q->nsc / 2;
+  for (uint32_t l = 0; l < 14; l++) {
+    fft_fwd(q, iq + q->sym_off[l], re, im);
+    for (uint32_t k = 0; k < q->nsc; k++) {
+      uint32_t bin        = (k < h) ? q->fft - h + k : k - h + 1;
+      sym[l * q->nsc + k] = (cf_t){re[bin], im[bin]};
+    }
+  }
+  free(re);
+  free(im);
+}
+
+/* ---------------------------------------------------------------- K2: channel estimation
+ * restates srsran_chest_dl_estimate_cfg with the reference's configuration
+ * (src/src/SubframeWorker.cc:376-400): LS at the CRS, gaussian frequency smoothing (edge taps
+ * renormalised), noise from LS - smoothed (NOISE_ALG_REFS), linear interpolation in frequency then
+ * time (ESTIMATOR_ALG_INTERPOLATE). */
+void lteo_chest(lteo_t* q, uint32_t sf_idx, const cf_t* const* sym, cf_t* const* ce, lteo_chest_res_t* res)
+{
+  const uint32_t N = q->cell.nof_prb, np = 2 * N, nsc = q->nsc;
+  cf_t*          ls  = (cf_t*)malloc(sizeof(cf_t) * NPILSYM * np);
+  cf_t*          sm  = (cf_t*)malloc(sizeof(cf_t) * NPILSYM * np);
+  cf_t*          fi  = (cf_t*)malloc(sizeof(cf_t) * NPILSYM * nsc);
+  float*         tmp = (float*)malloc(sizeof(float) * np);
+  memset(res, 0, sizeof(*res));
+  for (uint32_t p = 0; p < q->cell.nof_ports; p++)
+    for (uint32_t a = 0; a < q->cell.nof_rx; a++) {
+      float nsum = 0.0f, psum = 0.0f;
+      for (uint32_t li = 0; li < NPILSYM; li++) {
+        uint32_t    l = PIL_L[li], off = lte_crs_offset(&q->cell, p, l % 7);
+        const cf_t* pil = &q->crs[((sf_idx * 2 + p) * NPILSYM + li) * np];
+        for (uint32_t m = 0; m < np; m++) {
+          cf_t y  = sym[a][l * nsc + 6 * m + off];
+          cf_t pl = pil[m];
+          ls[li * np + m].re = y.re * pl.re + y.im * pl.im;
+          ls[li * np + m].im = y.im * pl.re - y.re * pl.im;
+        }
+        for (uint32_t m = 0; m < np; m++) {
+          float ar = 0.0f, ai = 0.0f, ws = 0.0f;
+          for (int j = 0; j < 5; j++) {
+            int mm = (int)m + j - 2;
+            if (mm < 0 || mm >= (int)np) continue;
+            ar = ar + q->filt[j] * ls[li * np + mm].re;
+            ai = ai + q->filt[j] * ls[li * np + mm].im;
+            ws = ws + q->filt[j];
+          }
+          sm[li * np + m].re = ar / ws;
+          sm[li * np + m].im = ai / ws;
+        }
+        for (uint32_t m = 0; m < np; m++) {
+          float dr = ls[li * np + m].re - sm[li * np + m].re, di = ls[li * np + m].im - sm[li * np + m].im;
+          tmp[m]   = dr * dr + di * di;
+        }
+        nsum = nsum + lteo_det_sum(tmp, np);
+        for (uint32_t m = 0; m < np; m++) tmp[m] = sm[li * np + m].re * sm[li * np + m].re + sm[li * np + m].im * sm[li * np + m].im;
+        psum = psum + lteo_det_sum(tmp, np);
+        /* frequency interpolation */
+        for (uint32_t k = 0; k < nsc; k++) {
+          int m = ((int)k - (int)off) / 6;
+          if ((int)k < (int)off) m = 0;
+          if (m > (int)np - 2) m = (int)np - 2;
+          int   j = (int)k - (6 * m + (int)off);
+          float c = q->interp_c[j + 5];
+          cf_t  A = sm[li * np + m], B = sm[li * np + m + 1];
+          fi[li * nsc + k].re = A.re + (B.re - A.re) * c;
+          fi[li * nsc + k].im = A.im + (B.im - A.im) * c;
+        }
+      }
+      float cnt                = (float)(NPILSYM * np);
+      res->noise[p][a]         = (nsum / cnt) / q->noise_corr;
+      res->rsrp[p][a]          = psum / cnt;
+      if (p == 0 && a == 0) {
+        for (uint32_t m = 0; m < np; m++) tmp[m] = ls[0 * np + m].re * ls[2 * np + m].re + ls[0 * np + m].im * ls[2 * np + m].im;
+        res->cfo_re = lteo_det_sum(tmp, np);
+        for (uint32_t m = 0; m < np; m++) tmp[m] = ls[0 * np + m].re * ls[2 * np + m].im - ls[0 * np + m].im * ls[2 * np + m].re;
+        res->cfo_im = lteo_det_sum(tmp, np);
+      }
+      /* time interpolation */
+      cf_t* out = ce[p * q->cell.nof_rx + a];
+      for (uint32_t l = 0; l < 14; l++) {
+        uint32_t ia, ib;
+        float    t;
+        if (l < 4)
+          ia = 0, ib = 1, t = (float)l / 4.0f;
+        else if (l < 7)
+          ia = 1, ib = 2, t = (float)(l - 4) / 3.0f;
+        else if (l < 11)
+          ia = 2, ib = 3, t = (float)(l - 7) / 4.0f;
+        else
+          ia = 2, ib = 3, t = (float)(l - 11) / 4.0f;
+        for (uint32_t k = 0; k < nsc; k++) {
+          cf_t A = fi[ia * nsc + k], B = fi[ib * nsc + k];
+          if (l < 11) {
+            out[l * nsc + k].re = A.re + (B.re - A.re) * t;
+            out[l * nsc + k].im = A.im + (B.im - A.im) * t;
+          } else {
+            out[l * nsc + k].re = B.re + (B.re - A.re) * t;
+            out[l * nsc + k].im = B.im + (B.im - A.im) * t;
+          }
+        }
+      }
+    }
+  float ns = 0.0f, ps = 0.0f;
+  for (uint32_t p = 0; p < q->cell.nof_ports; p++)
+    for (uint32_t a = 0; a < q->cell.nof_rx; a++) {
+      ns = ns + res->noise[p][a];
+      ps = ps + res->rsrp[p][a];
+    }
+  float npa      = (float)(q->cell.nof_ports * q->cell.nof_rx);
+  res->noise_avg = ns / npa;
+  res->rsrp_avg  = ps / npa;
+  res->snr_db    = 10.0f * log10f(res->rsrp_avg / res->noise_avg);
+  res->cfo       = atan2f(res->cfo_im, res->cfo_re) / (2.0f * (float)M_PI * 7.5f);
+  free(ls), free(sm), free(fi), free(tmp);
+}
+
+void lteo_rb_power(lteo_t* q, const cf_t* sym0, float* pwr)
+{
+  float t[14 * 12];
+  for (uint32_t prb = 0; prb < q->cell.nof_prb; prb++) {
+    for (uint32_t l = 0; l < 14; l++)
+      for (uint32_t k = 0; k < 12; k++) {
+        cf_t v        = sym0[l * q->nsc + 12 * prb + k];
+        t[l * 12 + k] = v.re * v.re + v.im * v.im;
+      }
+    pwr[prb] = lteo_det_sum(t, 168) / 168.0f;
+  }
+}
+
+/* ---------------------------------------------------------------- equalisers (ZF; decoder_type 0) */
+static cf_t eq_port0(const lteo_t* q, const cf_t* const* sym, const cf_t* const* ce, uint32_t idx)
+{
+  float nr = 0.0f, ni = 0.0f, den = 0.0f;
+  for (uint32_t a = 0; a < q->cell.nof_rx; a++) {
+    cf_t y = sym[a][idx], h = ce[a][idx];
+    nr  = nr + (y.re * h.re + y.im * h.im);
+    ni  = ni + (y.im * h.re - y.re * h.im);
+    den = den + (h.re * h.re + h.im * h.im);
+  }
+  return (cf_t){nr / den, ni / den};
+}
+/* SFBC pair at grid indices i0, i1 -> x0, x1 (36.211 6.3.4.3 inverted) */
+static void eq_sfbc(const lteo_t* q, const cf_t* const* sym, const cf_t* const* ce, uint32_t i0, uint32_t i1, cf_t* x0, cf_t* x1)
+{
+  const uint32_t A  = q->cell.nof_rx;
+  float          n0r = 0.0f, n0i = 0.0f, n1r = 0.0f, n1i = 0.0f, d0 = 0.0f, d1 = 0.0f;
+  for (uint32_t a = 0; a < A; a++) {
+    cf_t r0 = sym[a][i0], r1 = sym[a][i1];
+    cf_t h00 = ce[0 * A + a][i0], h01 = ce[0 * A + a][i1]; /* port 0 at RE0 / RE1 */
+    cf_t h10 = ce[1 * A + a][i0], h11 = ce[1 * A + a][i1]; /* port 1 */
+    /* x0 += conj(h00) r0 + h11 conj(r1) */
+    n0r = n0r + ((h00.re * r0.re + h00.im * r0.im) + (h11.re * r1.re + h11.im * r1.im));
+    n0i = n0i + ((h00.re * r0.im - h00.im * r0.re) + (h11.im * r1.re - h11.re * r1.im));
+    /* x1 += conj(h01) r1 - h10 conj(r0) */
+    n1r = n1r + ((h01.re * r1.re + h01.im * r1.im) - (h10.re * r0.re + h10.im * r0.im));
+    n1i = n1i + ((h01.re * r1.im - h01.im * r1.re) - (h10.im * r0.re - h10.re * r0.im));
+    d0  = d0 + ((h00.re * h00.re + h00.im * h00.im) + (h11.re * h11.re + h11.im * h11.im));
+    d1  = d1 + ((h01.re * h01.re + h01.im * h01.im) + (h10.re * h10.re + h10.im * h10.im));
+  }
+  const float s2 = 1.41421354f;
+  x0->re = (n0r / d0) * s2;
+  x0->im = (n0i / d0) * s2;
+  x1->re = (n1r / d1) * s2;
+  x1->im = (n1i / d1) * s2;
+}
+/* 2x2 large-delay CDD zero forcing: r = H (1/2)[[1,1],[s,-s]] x */
+static void eq_cdd(const lteo_t* q, const cf_t* const* sym, const cf_t* const* ce, uint32_t idx, int odd, cf_t* x0, cf_t* x1)
+{
+  (void)q;
+  cf_t  r0 = sym[0][idx], r1 = sym[1][idx];
+  cf_t  h00 = ce[0][idx], h10 = ce[1][idx]; /* port0: ant0, ant1 */
+  cf_t  h01 = ce[2][idx], h11 = ce[3][idx]; /* port1: ant0, ant1 */
+  float s = odd ? -1.0f : 1.0f;
+  /* E = 2 Heff = [[h00 + s h01, h00 - s h01],[h10 + s h11, h10 - s h11]] */
+  cf_t e00 = {h00.re + s * h01.re, h00.im + s * h01.im}, e01 = {h00.re - s * h01.re, h00.im - s * h01.im};
+  cf_t e10 = {h10.re + s * h11.re, h10.im + s * h11.im}, e11 = {h10.re - s * h11.re, h10.im - s * h11.im};
+  cf_t det = {(e00.re * e11.re - e00.im * e11.im) - (e01.re * e10.re - e01.im * e10.im),
+              (e00.re * e11.im + e00.im * e11.re) - (e01.re * e10.im + e01.im * e10.re)};
+  cf_t a0  = {(e11.re * r0.re - e11.im * r0.im) - (e01.re * r1.re - e01.im * r1.im),
+              (e11.re * r0.im + e11.im * r0.re) - (e01.re * r1.im + e01.im * r1.re)};
+  cf_t a1  = {(e00.re * r1.re - e00.im * r1.im) - (e10.re * r0.re - e10.im * r0.im),
+              (e00.re * r1.im + e00.im * r1.re) - (e10.re * r0.im + e10.im * r0.re)};
+  float dd = det.re * det.re + det.im * det.im;
+  /* x = 2 a conj(det) / |det|^2 */
+  x0->re = ((a0.re * det.re + a0.im * det.im) / dd) * 2.0f;
+  x0->im = ((a0.im * det.re - a0.re * det.im) / dd) * 2.0f;
+  x1->re = ((a1.re * det.re + a1.im * det.im) / dd) * 2.0f;
+  x1->im = ((a1.im * det.re - a1.re * det.im) / dd) * 2.0f;
+}
+
+/* equalise n control-channel REs given by grid indices (n multiple of 2 for 2 ports) */
+static void eq_ctrl(const lteo_t* q, const cf_t* const* sym, const cf_t* const* ce, const uint32_t* idx, uint32_t n, cf_t* d)
+{
+  if (q->cell.nof_ports == 1) {
+    for (uint32_t i = 0; i < n; i++) d[i] = eq_port0(q, sym, ce, idx[i]);
+  } else {
+    for (uint32_t i = 0; i + 1 < n; i += 2) eq_sfbc(q, sym, ce, idx[i], idx[i + 1], &d[i], &d[i + 1]);
+  }
+}
+
+/* ---------------------------------------------------------------- K3: PCFICH (srsran_pcfich_decode) */
+uint32_t lteo_pcfich_decode(lteo_t* q, uint32_t sf_idx, const cf_t* const* sym, const cf_t* const* ce, float* corr)
+{
+  uint32_t idx[16];
+  cf_t     d[16];
+  float    llr[32];
+  for (int i = 0; i < 4; i++)
+    for (int j = 0; j < 4; j++) idx[4 * i + j] = q->regs.regs[q->regs.pcfich_reg[i]].k[j]; /* symbol 0 */
+  eq_ctrl(q, sym, ce, idx, 16, d);
+  const float ms2 = -1.41421354f;
+  for (int i = 0; i < 16; i++) {
+    llr[2 * i]     = d[i].re * ms2;
+    llr[2 * i + 1] = d[i].im * ms2;
+  }
+  for (int i = 0; i < 32; i++)
+    if (q->pcfich_scr[sf_idx][i]) llr[i] = -llr[i];
+  uint32_t best = 0;
+  for (uint32_t c = 0; c < 3; c++) {
+    float acc = 0.0f;
+    for (int i = 0; i < 32; i++) acc = acc + (lte_cfi_codeword[c][i] ? llr[i] : -llr[i]);
+    corr[c] = acc;
+    if (acc > corr[best]) best = c;
+  }
+  return best + 1;
+}
+
+/* ---------------------------------------------------------------- K4: PDCCH LLRs (srsran_pdcch_extract_llr) */
+uint32_t lteo_pdcch_extract_llr(lteo_t* q, uint32_t sf_idx, uint32_t cfi, const cf_t* const* sym, const cf_t* const* ce, float* llr)
+{
+  uint32_t    nof_cce = q->regs.nof_cce[cfi - 1], nq = nof_cce * 9;
+  const float ms2     = -1.41421354f;
+  for (uint32_t qq = 0; qq < nq; qq++) {
+    const lte_reg_t* rg = &q->regs.regs[q->regs.pdcch_map[cfi - 1][qq]];
+    uint32_t         idx[4];
+    cf_t             d[4];
+    for (int j = 0; j < 4; j++) idx[j] = rg->l * q->nsc + rg->k[j];
+    eq_ctrl(q, sym, ce, idx, 4, d);
+    for (int j = 0; j < 4; j++) {
+      float a = d[j].re * ms2, b = d[j].im * ms2;
+      llr[8 * qq + 2 * j]     = q->pdcch_scr[sf_idx][8 * qq + 2 * j] ? -a : a;
+      llr[8 * qq + 2 * j + 1] = q->pdcch_scr[sf_idx][8 * qq + 2 * j + 1] ? -b : b;
+    }
+  }
+  return nof_cce;
+}
+void lteo_cce_power(const float* llr, uint32_t nof_cce, float* pwr)
+{
+  for (uint32_t c = 0; c < nof_cce; c++) {
+    double m = 0;
+    for (int i = 0; i < 72; i++) m += fabsf(llr[c * 72 + i]);
+    pwr[c] = (float)(m / 72);
+  }
+}
+
+/* ---------------------------------------------------------------- K5: DCI decode
+ * restates srsran_pdcch_dci_decode (falcon_pdcch.c:142 -> rm_conv_rx + viterbi_decode_f + crc):
+ * accumulate-dematch, quantise to uint8 with gain 32/max (falcon_pdcch.c:432 mirrors the constants),
+ * K=7 r=1/3 tail-biting Viterbi run over 3 copies keeping the middle one, CRC16 remainder XOR. */
+int lteo_dci_decode(const float* e, uint32_t E, uint32_t nof_bits, uint8_t* bits, uint16_t* crc_rem)
+{
+  const uint32_t K = nof_bits + 16, n3 = 3 * K;
+  uint16_t       tab[3 * (LTE_DCI_MAX_BITS + 16)];
+  float          rm[3 * (LTE_DCI_MAX_BITS + 16)];
+  int            r[3 * (LTE_DCI_MAX_BITS + 16)];
+  lte_rm_conv_table(K, tab);
+  for (uint32_t i = 0; i < n3; i++) rm[i] = 0.0f;
+  for (uint32_t k = 0; k < E; k++) rm[tab[k % n3]] = rm[tab[k % n3]] + e[k];
+  float mx = 0.0f;
+  for (uint32_t i = 0; i < n3; i++)
+    if (fabsf(rm[i]) > mx) mx = fabsf(rm[i]);
+  if (!(mx > 0.0f)) return -1;
+  float gain = 32.0f / mx;
+  for (uint32_t i = 0; i < n3; i++) {
+    float v = rm[i] * gain + 127.5f;
+    if (v < 0.0f) v = 0.0f;
+    if (v > 255.0f) v = 255.0f;
+    int qv = (int)v;
+    r[i]   = 2 * qv - 255;
+  }
+  /* outputs for (state, input): state bit j = c_{k-1-j} */
+  static int8_t sgn[64][2][3];
+  static int    init = 0;
+  if (!init) {
+    for (int s = 0; s < 64; s++)
+      for (int c = 0; c < 2; c++) {
+#define T(j) ((s >> ((j)-1)) & 1)
+        int o0 = c ^ T(2) ^ T(3) ^ T(5) ^ T(6), o1 = c ^ T(1) ^ T(2) ^ T(3) ^ T(6), o2 = c ^ T(1) ^ T(2) ^ T(4) ^ T(6);
+#undef T
+        sgn[s][c][0] = o0 ? 1 : -1, sgn[s][c][1] = o1 ? 1 : -1, sgn[s][c][2] = o2 ? 1 : -1;
+      }
+    init = 1;
+  }
+  const uint32_t T3 = 3 * K;
+  int            pm[64], nm[64];
+  uint64_t*      dec = (uint64_t*)malloc(sizeof(uint64_t) * T3);
+  memset(pm, 0, sizeof(pm));
+  for (uint32_t t = 0; t < T3; t++) {
+    uint32_t k  = t % K;
+    int      r0 = r[k], r1 = r[K + k], r2 = r[2 * K + k];
+    uint64_t dw = 0;
+    for (int sn = 0; sn < 64; sn++) {
+      int c = sn & 1, p0 = sn >> 1, p1 = (sn >> 1) | 32;
+      int m0 = pm[p0] + sgn[p0][c][0] * r0 + sgn[p0][c][1] * r1 + sgn[p0][c][2] * r2;
+      int m1 = pm[p1] + sgn[p1][c][0] * r0 + sgn[p1][c][1] * r1 + sgn[p1][c][2] * r2;
+      if (m1 > m0) {
+        nm[sn] = m1;
+        dw |= 1ull << sn;
+      } else
+        nm[sn] = m0;
+    }
+    memcpy(pm, nm, sizeof(pm));
+    dec[t] = dw;
+  }
+  int best = 0;
+  for (int s = 1; s < 64; s++)
+    if (pm[s] > pm[best]) best = s;
+  uint8_t data[LTE_DCI_MAX_BITS + 16];
+  int     st = best;
+  for (int t = (int)T3 - 1; t >= (int)K; t--) {
+    if (t < (int)(2 * K)) data[t - K] = (uint8_t)(st & 1);
+    st = (st >> 1) | ((int)((dec[t] >> st) & 1) << 5);
+  }
+  free(dec);
+  memcpy(bits, data, nof_bits);
+  uint32_t p = 0;
+  for (uint32_t i = 0; i < 16; i++) p = (p << 1) | data[nof_bits + i];
+  *crc_rem = (uint16_t)(p ^ lte_crc(LTE_CRC16, 16, data, nof_bits));
+  return 0;
+}
+
+/* ---------------------------------------------------------------- K6: PDSCH symbols -> int16 LLRs
+ * restates the front half of srsran_pdsch_decode (DL_Sniffer_PDSCH.cc:997): srsran_predecoding_type,
+ * layer demapping, srsran_demod_soft_demodulate_s, descrambling. */
+static int16_t f2s(float v)
+{
+  if (v > 32767.0f) v = 32767.0f;
+  if (v < -32767.0f) v = -32767.0f;
+  return (int16_t)v; /* truncation toward zero, as the C cast in the int16 demodulator */
+}
+static void demod_s(cf_t x, uint32_t Qm, int16_t* z)
+{
+  switch (Qm) {
+    case 2:
+      z[0] = (int16_t)-f2s(x.re * 141.421356f);
+      z[1] = (int16_t)-f2s(x.im * 141.421356f);
+      break;
+    case 4: {
+      int16_t yr = f2s(x.re * 400.0f), yi = f2s(x.im * 400.0f);
+      z[0] = (int16_t)-yr, z[1] = (int16_t)-yi;
+      z[2] = (int16_t)(abs(yr) - 252), z[3] = (int16_t)(abs(yi) - 252);
+    } break;
+    case 6: {
+      int16_t yr = f2s(x.re * 700.0f), yi = f2s(x.im * 700.0f);
+      z[0] = (int16_t)-yr, z[1] = (int16_t)-yi;
+      z[2] = (int16_t)(abs(yr) - 432), z[3] = (int16_t)(abs(yi) - 432);
+      z[4] = (int16_t)(abs(z[2]) - 216), z[5] = (int16_t)(abs(z[3]) - 216);
+    } break;
+    default: {
+      int16_t yr = f2s(x.re * 1000.0f), yi = f2s(x.im * 1000.0f);
+      z[0] = (int16_t)-yr, z[1] = (int16_t)-yi;
+      z[2] = (int16_t)(abs(yr) - 613), z[3] = (int16_t)(abs(yi) - 613);
+      z[4] = (int16_t)(abs(z[2]) - 306), z[5] = (int16_t)(abs(z[3]) - 306);
+      z[6] = (int16_t)(abs(z[4]) - 153), z[7] = (int16_t)(abs(z[5]) - 153);
+    } break;
+  }
+}
+int lteo_pdsch_llr(lteo_t* q, uint32_t sf_idx, uint32_t cfi, uint16_t rnti, const lte_dl_grant_t* g, const cf_t* const* sym,
+                   const cf_t* const* ce, int16_t* const* llr, cf_t* const* eq_out)
+{
+  const uint32_t N = q->cell.nof_prb, nsc = q->nsc;
+  uint32_t*      idx = (uint32_t*)malloc(sizeof(uint32_t) * (g->nof_re + 16));
+  uint16_t       kk[12];
+  uint32_t       n = 0;
+  for (uint32_t l = 0; l < 14; l++)
+    for (uint32_t prb = 0; prb < N; prb++)
+      if (g->prb_mask[l / 7][prb]) {
+        uint32_t c = lte_pdsch_re_in_prb(&q->cell, sf_idx, cfi, l, prb, kk);
+        for (uint32_t i = 0; i < c; i++) idx[n++] = l * nsc + kk[i];
+      }
+  if (n != g->nof_re) {
+    free(idx);
+    return -1;
+  }
+  cf_t* x[2] = {(cf_t*)malloc(sizeof(cf_t) * (n + 2)), (cf_t*)malloc(sizeof(cf_t) * (n + 2))};
+  uint32_t ncw = 0, qm[2] = {0, 0};
+  for (int t = 0; t < 2; t++)
+    if (g->tb[t].enabled) qm[ncw++] = g->tb[t].qm;
+  if (g->tx_scheme == LTE_TX_PORT0) {
+    for (uint32_t i = 0; i < n; i++) x[0][i] = eq_port0(q, sym, ce, idx[i]);
+  } else if (g->tx_scheme == LTE_TX_DIVERSITY) {
+    for (uint32_t i = 0; i + 1 < n; i += 2) eq_sfbc(q, sym, ce, idx[i], idx[i + 1], &x[0][i], &x[0][i + 1]);
+  } else if (g->tx_scheme == LTE_TX_CDD && q->cell.nof_rx == 2 && q->cell.nof_ports == 2) {
+    for (uint32_t i = 0; i < n; i++) eq_cdd(q, sym, ce, idx[i], (int)(i & 1), &x[0][i], &x[1][i]);
+  } else {
+    free(idx), free(x[0]), free(x[1]);
+    return -2; /* spatial multiplexing (TM4): next round */
+  }
+  static __thread uint8_t scr[110 * 12 * 14 * 8];
+  for (uint32_t cw = 0; cw < ncw; cw++) {
+    uint32_t G = n * qm[cw];
+    lte_gold_bits(((uint32_t)rnti << 14) + (cw << 13) + (sf_idx << 9) + q->cell.cell_id, scr, G);
+    for (uint32_t i = 0; i < n; i++) demod_s(x[cw][i], qm[cw], &llr[cw][i * qm[cw]]);
+    for (uint32_t i = 0; i < G; i++)
+      if (scr[i]) llr[cw][i] = (int16_t)-llr[cw][i];
+    if (eq_out && eq_out[cw]) memcpy(eq_out[cw], x[cw], sizeof(cf_t) * n);
+  }
+  free(idx), free(x[0]), free(x[1]);
+  return 0;
+}
+
+/* ---------------------------------------------------------------- K7: turbo rate de-matching
+ * restates srsran_rm_turbo_rx_lut: saturating int16 accumulation into the circular buffer
+ * (N_cb = K_w), then de-interleave to the three streams; turbo input conditioning
+ * v = clamp(w >> sh(Qm), +-255), sh = {QPSK 0, 16QAM 1, 64QAM 2, 256QAM 2}. */
+static int sat16(int v) { return v > 32767 ? 32767 : v < -32768 ? -32768 : v; }
+void       lteo_rm_turbo_rx(const int16_t* e, uint32_t E, uint32_t K, uint32_t F, uint32_t rv, uint32_t Qm, int16_t* d)
+{
+  static __thread uint32_t tab[3 * 6176];
+  static __thread int16_t  w[3 * 6176];
+  static __thread uint32_t order[3 * 6176];
+  uint32_t                 Kpi = lte_rm_turbo_table(K, tab), Kw = 3 * Kpi, D = K + 4;
+  /* list of transmittable circular-buffer positions in order starting from k0 */
+  uint32_t nn = 0, k0 = lte_rm_turbo_k0(K, rv);
+  for (uint32_t j = 0; j < Kw; j++) {
+    uint32_t pos = (k0 + j) % Kw, t = tab[pos];
+    if (t == 0xFFFFFFFFu) continue;
+    if (t / D < 2 && t % D < F) continue;
+    order[nn++] = t;
+  }
+  memset(w, 0, sizeof(int16_t) * 3 * D);
+  for (uint32_t k = 0; k < E; k++) {
+    uint32_t t = order[k % nn];
+    w[t]       = (int16_t)sat16((int)w[t] + (int)e[k]);
+  }
+  int sh = Qm == 2 ? 0 : Qm == 4 ? 1 : 2;
+  for (uint32_t i = 0; i < 3 * D; i++) {
+    int v = w[i] >> sh;
+    d[i]  = (int16_t)(v > 255 ? 255 : v < -255 ? -255 : v);
+  }
+  for (uint32_t i = 0; i < F; i++) d[i] = -255, d[D + i] = -255; /* filler bits are known zeros */
+}
+
+/* ---------------------------------------------------------------- K8: turbo decoder
+ * restates srsran_tdec_* behaviour (max-log-MAP, int16 LLRs, CRC early stop, do-while so at least
+ * one iteration) as a windowed decoder: windows of 32 trellis steps, boundary state metrics carried
+ * over from the previous iteration (next-iteration initialisation), extrinsic scaled by 3/8 of the
+ * doubled-metric difference (= 0.75 of the true extrinsic) and clamped to +-511. */
+#define TD_WL 32
+#define TD_NINF (-8192)
+static const uint8_t TD_NEXT[8][2] = {{0, 4}, {4, 0}, {5, 1}, {1, 5}, {2, 6}, {6, 2}, {7, 3}, {3, 7}};
+static const uint8_t TD_PAR[8][2]  = {{0, 1}, {0, 1}, {1, 0}, {1, 0}, {1, 0}, {1, 0}, {0, 1}, {0, 1}};
+/* state s = 4 r1 + 2 r2 + r3;  a = u^r2^r3;  z = a^r1^r3;  next = 4a + 2 r1 + r2 */
+
+typedef struct {
+  int A[(6144 / TD_WL) + 1][8], B[(6144 / TD_WL) + 1][8];
+} td_bound_t;
+
+static void siso(const int* sys, const int* par, const int* apr, uint32_t K, const int tx[3], const int tz[3], td_bound_t* bd,
+                 int* ext, int* llr2x)
+{
+  uint32_t NW = (K + TD_WL - 1) / TD_WL;
+  static __thread td_bound_t nb;
+  /* beta at K from the tail: beta_{K+3} = state 0 */
+  int bt[8], bn[8];
+  for (int s = 0; s < 8; s++) bt[s] = s ? TD_NINF : 0;
+  for (int k = 2; k >= 0; k--) {
+    for (int s = 0; s < 8; s++) {
+      int best = -(1 << 30);
+      for (int u = 0; u < 2; u++) {
+        int g = (u ? tx[k] : -tx[k]) + (TD_PAR[s][u] ? tz[k] : -tz[k]);
+        int v = bt[TD_NEXT[s][u]] + g;
+        if (v > best) best = v;
+      }
+      bn[s] = best;
+    }
+    memcpy(bt, bn, sizeof(bt));
+  }
+  for (int s = 7; s >= 0; s--) bt[s] -= bt[0];
+  for (uint32_t w = 0; w < NW; w++) {
+    uint32_t k0 = w * TD_WL, k1 = k0 + TD_WL < K ? k0 + TD_WL : K;
+    int      al[TD_WL + 1][8], be[8], t[8];
+    if (w == 0)
+      for (int s = 0; s < 8; s++) al[0][s] = s ? TD_NINF : 0;
+    else
+      memcpy(al[0], bd->A[w], sizeof(int) * 8);
+    for (uint32_t k = k0; k < k1; k++) {
+      int xa = sys[k] + apr[k], p = par[k];
+      int* a = al[k - k0];
+      for (int s = 0; s < 8; s++) t[s] = -(1 << 30);
+      for (int s = 0; s < 8; s++)
+        for (int u = 0; u < 2; u++) {
+          int g = (u ? xa : -xa) + (TD_PAR[s][u] ? p : -p);
+          int v = a[s] + g, n = TD_NEXT[s][u];
+          if (v > t[n]) t[n] = v;
+        }
+      memcpy(al[k - k0 + 1], t, sizeof(t));
+    }
+    for (int s = 7; s >= 0; s--) nb.A[w + 1][s] = al[k1 - k0][s] - al[k1 - k0][0];
+    if (w == NW - 1)
+      memcpy(be, bt, sizeof(be));
+    else
+      memcpy(be, bd->B[w], sizeof(be));
+    for (int k = (int)k1 - 1; k >= (int)k0; k--) {
+      int  xa = sys[k] + apr[k], p = par[k];
+      int* a  = al[k - (int)k0];
+      int  m1 = -(1 << 30), m0 = -(1 << 30);
+      for (int s = 0; s < 8; s++) {
+        int best = -(1 << 30);
+        for (int u = 0; u < 2; u++) {
+          int g = (u ? xa : -xa) + (TD_PAR[s][u] ? p : -p);
+          int v = be[TD_NEXT[s][u]] + g;
+          if (v > best) best = v;
+          int tot = a[s] + v;
+          if (u) {
+            if (tot > m1) m1 = tot;
+          } else if (tot > m0)
+            m0 = tot;
+        }
+        t[s] = best;
+      }
+      memcpy(be, t, sizeof(be));
+      int L     = m1 - m0;
+      llr2x[k]  = L;
+      int e     = (3 * (L - 2 * xa)) >> 3;
+      ext[k]    = e > 511 ? 511 : e < -511 ? -511 : e;
+    }
+    if (w > 0)
+      for (int s = 7; s >= 0; s--) nb.B[w - 1][s] = be[s] - be[0];
+  }
+  for (uint32_t w = 1; w < NW; w++) memcpy(bd->A[w], nb.A[w], sizeof(int) * 8);
+  for (uint32_t w = 0; w + 1 < NW; w++) memcpy(bd->B[w], nb.B[w], sizeof(int) * 8);
+}
+
+uint32_t lteo_turbo_decode(const int16_t* d, uint32_t K, uint32_t max_iter, int crc_type, uint8_t* bits, int* crc_ok)
+{
+  static __thread int        sys[6144], p1[6144], p2[6144], sysi[6144], apr1[6144], apr2[6144], ext[6144], l2[6144];
+  static __thread uint16_t   pi[6144];
+  static __thread td_bound_t b1, b2;
+  uint32_t                   D = K + 4;
+  lte_qpp(K, pi);
+  for (uint32_t k = 0; k < K; k++) {
+    sys[k] = d[k], p1[k] = d[D + k], p2[k] = d[2 * D + k];
+    apr1[k] = 0;
+  }
+  for (uint32_t i = 0; i < K; i++) sysi[i] = sys[pi[i]];
+  /* tails: d0 = xK, zK+1, x'K, z'K+1 ; d1 = zK, xK+2, z'K, x'K+2 ; d2 = xK+1, zK+2, x'K+1, z'K+2 */
+  int tx1[3] = {d[K], d[2 * D + K], d[D + K + 1]}, tz1[3] = {d[D + K], d[K + 1], d[2 * D + K + 1]};
+  int tx2[3] = {d[K + 2], d[2 * D + K + 2], d[D + K + 3]}, tz2[3] = {d[D + K + 2], d[K + 3], d[2 * D + K + 3]};
+  memset(&b1, 0, sizeof(b1));
+  memset(&b2, 0, sizeof(b2));
+  if (max_iter < 1) max_iter = 1;
+  uint32_t it = 0;
+  *crc_ok     = 0;
+  while (it < max_iter) {
+    siso(sys, p1, apr1, K, tx1, tz1, &b1, ext, l2);
+    for (uint32_t i = 0; i < K; i++) apr2[i] = ext[pi[i]];
+    siso(sysi, p2, apr2, K, tx2, tz2, &b2, ext, l2);
+    for (uint32_t i = 0; i < K; i++) {
+      apr1[pi[i]] = ext[i];
+      bits[pi[i]] = l2[i] > 0;
+    }
+    it++;
+    if (crc_type) {
+      uint32_t poly = crc_type == 1 ? LTE_CRC24A : LTE_CRC24B, c = lte_crc(poly, 24, bits, K - 24), r = 0;
+      for (uint32_t i = 0; i < 24; i++) r = (r << 1) | bits[K - 24 + i];
+      if (c == r) {
+        *crc_ok = 1;
+        break;
+      }
+    }
+  }
+  return it;
+}
+
+int lteo_dlsch_decode(const int16_t* e, uint32_t G, uint32_t tbs, uint32_t rv, uint32_t Qm, uint32_t NL, uint32_t max_iter,
+                      int early_stop, uint8_t* payload, uint32_t* iters_out)
+{
+  lte_cbsegm_t s;
+  if (lte_cbsegm(&s, tbs)) return -1;
+  static __thread int16_t d[3 * 6148];
+  static __thread uint8_t cb[6144];
+  uint8_t*                tb = (uint8_t*)malloc(tbs + 24 + 64);
+  uint32_t                rp = 0, wp = 0;
+  int                     all_cb_ok = 1;
+  for (uint32_t r = 0; r < s.C; r++) {
+    uint32_t K = lte_cb_K(&s, r), F = (r == 0) ? s.F : 0, E = lte_rm_turbo_E(G, s.C, r, Qm, NL);
+    lteo_rm_turbo_rx(e + rp, E, K, F, rv, Qm, d);
+    rp += E;
+    int      ok = 0;
+    uint32_t it = lteo_turbo_decode(d, K, max_iter, early_stop ? (s.C > 1 ? 2 : 1) : 0, cb, &ok);
+    if (!early_stop && s.C > 1) {
+      uint32_t c = lte_crc(LTE_CRC24B, 24, cb, K - 24), rr = 0;
+      for (uint32_t i = 0; i < 24; i++) rr = (rr << 1) | cb[K - 24 + i];
+      ok = (c == rr);
+    }
+    if (s.C > 1 && !ok) all_cb_ok = 0;
+    if (iters_out) iters_out[r] = it;
+    uint32_t nd = K - F - (s.C > 1 ? 24 : 0);
+    memcpy(tb + wp, cb + F, nd);
+    wp += nd;
+  }
+  uint32_t c = lte_crc(LTE_CRC24A, 24, tb, tbs), rr = 0;
+  for (uint32_t i = 0; i < 24; i++) rr = (rr << 1) | tb[tbs + i];
+  lte_bits_pack(tb, tbs, payload);
+  free(tb);
+  return (c == rr && all_cb_ok) ? 1 : 0;
+}
+
+int lteo_pdsch_decode(lteo_t* q, uint32_t sf_idx, uint32_t cfi, uint16_t rnti, const lte_dl_grant_t* g, const cf_t* const* sym,
+                      const cf_t* const* ce, uint32_t max_iter, uint8_t* const* payload, int* crc_ok)
+{
+  int16_t* llr[2] = {(int16_t*)malloc(sizeof(int16_t) * (g->nof_re * 8 + 16)), (int16_t*)malloc(sizeof(int16_t) * (g->nof_re * 8 + 16))};
+  int      ret    = lteo_pdsch_llr(q, sf_idx, cfi, rnti, g, sym, ce, llr, NULL);
+  if (ret == 0) {
+    uint32_t cw = 0;
+    for (int t = 0; t < 2; t++) {
+      crc_ok[t] = 0;
+      if (!g->tb[t].enabled) continue;
+      uint32_t NL = g->tx_scheme == LTE_TX_DIVERSITY ? 2 : 1;
+      if (g->tb[t].tbs > 0)
+        crc_ok[t] = lteo_dlsch_decode(llr[cw], g->tb[t].nof_bits, (uint32_t)g->tb[t].tbs, g->tb[t].rv, g->tb[t].qm, NL, max_iter, 1,
+                                      payload[t], NULL);
+      cw++;
+    }
+  }
+  free(llr[0]), free(llr[1]);
+  return ret;
+}

@@ -1,0 +1,208 @@
+/*
+ * lte_common.h -- LTE (36.211/212/213) primitives shared by the synthetic eNB (sim/) and the
+ * CPU oracle (oracle/).  TEST INFRASTRUCTURE: nothing under ltesniffer_b200/ links this.
+ *
+ * The reference delegates all of this to srsRAN (absent from /root/reference, see SURVEY.md
+ * section 8c); each function names the reference call site whose behaviour it restates.
+ */
+#ifndef LTE_COMMON_H
+#define LTE_COMMON_H
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct {
+  float re, im;
+} cf_t;
+
+#define LTE_MAX_PRB 110
+#define LTE_NRE 12
+#define LTE_NSYMB_SF 14 /* normal CP only (file mode assumes normal CP: src/src/LTESniffer_Core.cc:242-247) */
+#define LTE_MAX_PORTS 2
+#define LTE_MAX_ANT 2
+#define LTE_MAX_CCE 88
+#define LTE_DCI_MAX_BITS 64
+
+typedef struct {
+  uint32_t nof_prb;   /* 6,15,25,50,75,100 */
+  uint32_t nof_ports; /* 1 or 2 CRS ports */
+  uint32_t cell_id;   /* PCI 0..503 */
+  uint32_t nof_rx;    /* rx antennas 1 or 2 */
+} lte_cell_t;
+
+/* numerology */
+uint32_t lte_fft_size(uint32_t nof_prb);
+uint32_t lte_cp_len(uint32_t fft, uint32_t symbol_in_slot);
+uint32_t lte_sf_len(uint32_t nof_prb);
+
+/* ---- sequences / CRC ---- */
+void     lte_gold_bits(uint32_t c_init, uint8_t* c, uint32_t len);               /* 36.211 7.2 */
+uint32_t lte_crc(uint32_t poly, uint32_t order, const uint8_t* bits, uint32_t n); /* bitwise, zero init */
+#define LTE_CRC24A 0x1864CFBu
+#define LTE_CRC24B 0x1800063u
+#define LTE_CRC16 0x11021u
+#define LTE_CRC8 0x19Bu
+void lte_bits_pack(const uint8_t* bits, uint32_t nbits, uint8_t* bytes); /* MSB first */
+void lte_bits_unpack(const uint8_t* bytes, uint32_t nbits, uint8_t* bits);
+
+/* ---- CRS (36.211 6.10.1) ---- */
+/* fills pilot value r_{l,ns}(m') for m = 0..2*nof_prb-1; returns subcarrier offset (v+v_shift)%6 */
+uint32_t lte_crs(const lte_cell_t* c, uint32_t port, uint32_t ns, uint32_t l, cf_t* pilots);
+uint32_t lte_crs_offset(const lte_cell_t* c, uint32_t port, uint32_t l_in_slot);
+
+/* ---- control region REG geometry (36.211 6.2.4, 6.7.4, 6.9.3, 6.8.5) ---- */
+typedef struct {
+  uint16_t k0; /* lowest subcarrier of the REG */
+  uint8_t  l;  /* OFDM symbol */
+  uint8_t  kind; /* 0 = free for PDCCH, 1 = PCFICH, 2 = PHICH */
+  uint16_t k[4]; /* the 4 data REs of the REG (CRS slots skipped) */
+} lte_reg_t;
+
+typedef struct {
+  lte_cell_t cell;
+  uint32_t   nof_regs_sym[3]; /* REGs in symbol 0,1,2 */
+  lte_reg_t  regs[3 * 3 * LTE_MAX_PRB];
+  uint32_t   nof_regs_total;
+  uint32_t   pcfich_reg[4]; /* indices into regs[] */
+  uint32_t   nof_phich_groups;
+  uint32_t   phich_reg[3 * 16];
+  /* per CFI: */
+  uint32_t nof_pdcch_regs[3]; /* (N_reg/9)*9 */
+  uint32_t nof_cce[3];
+  /* pdcch_map[cfi-1][q] = index into regs[] of the REG carrying quadruplet q of the CCE stream
+   * (interleaver + cyclic shift applied; restates srsRAN regs_pdcch_init behaviour used by
+   *  srsran_pdcch_extract_llr at src/src/DCISearch.cc:562) */
+  uint16_t pdcch_map[3][3 * 3 * LTE_MAX_PRB];
+} lte_regs_t;
+
+int lte_regs_init(lte_regs_t* r, const lte_cell_t* cell);
+
+/* ---- convolutional code (36.212 5.1.3.1 / 5.1.4.2) ---- */
+void lte_conv_encode(const uint8_t* in, uint32_t K, uint8_t* out /* 3K, stream-major d0|d1|d2 */);
+/* w-index table: for circular-buffer position j (NULLs removed, 0..3K-1) gives index into the
+ * stream-major coded array (s*K + k). */
+void lte_rm_conv_table(uint32_t K, uint16_t* tab /* 3K */);
+void lte_rm_conv_tx(const uint8_t* d, uint32_t K, uint8_t* e, uint32_t E);
+
+/* ---- turbo code (36.212 5.1.3.2 / 5.1.4.1) ---- */
+typedef struct {
+  uint32_t tbs, C, Kp, Km, Cp, Cm, F;
+} lte_cbsegm_t;
+int      lte_cbsegm(lte_cbsegm_t* s, uint32_t tbs);
+uint32_t lte_cb_K(const lte_cbsegm_t* s, uint32_t r); /* first Cm blocks use Km */
+void     lte_qpp(uint32_t K, uint16_t* pi);           /* pi[i] = (f1 i + f2 i^2) mod K */
+/* encode one code block: in[K] -> d0,d1,d2 each K+4 */
+void lte_turbo_encode(const uint8_t* in, uint32_t K, uint8_t* d0, uint8_t* d1, uint8_t* d2);
+/* circular-buffer map: for w position j in [0,3*Kpi) returns index into stream-major (s*(K+4)+k)
+ * or 0xFFFFFFFF for a <NULL> dummy.  Kpi = 32*ceil((K+4)/32). */
+uint32_t lte_rm_turbo_table(uint32_t K, uint32_t* tab /* 3*Kpi */);
+uint32_t lte_rm_turbo_k0(uint32_t K, uint32_t rv);
+/* rate-match one code block: d (stream-major, 3*(K+4)), F filler bits at the start of d0/d1 are
+ * treated as <NULL>; writes E bits */
+void lte_rm_turbo_tx(const uint8_t* d, uint32_t K, uint32_t F, uint32_t rv, uint8_t* e, uint32_t E);
+/* E_r for code block r (36.212 5.1.4.1.2) */
+uint32_t lte_rm_turbo_E(uint32_t G, uint32_t C, uint32_t r, uint32_t Qm, uint32_t NL);
+
+/* ---- modulation (36.211 7.1) ---- */
+void lte_modulate(const uint8_t* bits, uint32_t nsym, uint32_t Qm, cf_t* out);
+
+/* ---- DCI (36.212 5.3.3) ---- */
+typedef enum {
+  LTE_DCI_FORMAT0 = 0,
+  LTE_DCI_FORMAT1,
+  LTE_DCI_FORMAT1A,
+  LTE_DCI_FORMAT1B,
+  LTE_DCI_FORMAT1C,
+  LTE_DCI_FORMAT1D,
+  LTE_DCI_FORMAT2,
+  LTE_DCI_FORMAT2A,
+  LTE_DCI_FORMAT2B,
+  LTE_DCI_NOF_FORMATS
+} lte_dci_format_t; /* same order as the reference's list, src/src/DCISearch.cc:84-95 */
+
+uint32_t lte_dci_sizeof(const lte_cell_t* c, lte_dci_format_t f); /* restates srsran_dci_format_sizeof (falcon_pdcch.c:133) */
+
+typedef struct {
+  uint16_t rnti;
+  uint8_t  format;
+  /* resource allocation */
+  uint8_t  alloc_type;  /* 0,1,2 */
+  uint32_t rbg_bitmask; /* type0 */
+  uint32_t t1_vrb_bitmask, t1_subset, t1_shift;
+  uint32_t riv;         /* type2 */
+  uint8_t  t2_dist;     /* 1 = distributed VRB */
+  uint8_t  t2_ngap2;    /* gap selection */
+  uint8_t  n_prb1a;     /* 2 or 3 (SI/P/RA-RNTI 1A TBS column) */
+  /* TBs */
+  uint8_t  mcs[2], rv[2], ndi[2];
+  uint8_t  tb_en[2];
+  uint8_t  tb_cw_swap;
+  uint8_t  pinfo;
+  uint8_t  pid, tpc;
+  /* format 0 */
+  uint8_t  hop, n_dmrs, cqi_req;
+} lte_dci_t;
+
+int lte_dci_pack(const lte_cell_t* c, const lte_dci_t* d, uint8_t* bits, uint32_t* nbits);
+int lte_dci_unpack(const lte_cell_t* c, lte_dci_format_t f, uint16_t rnti, const uint8_t* bits, uint32_t nbits, lte_dci_t* d);
+
+/* ---- DL grant (36.213 7.1.6 / 7.1.7) ---- */
+typedef enum { LTE_TX_PORT0 = 0, LTE_TX_DIVERSITY, LTE_TX_CDD, LTE_TX_SPATIALMUX } lte_txscheme_t;
+typedef struct {
+  uint8_t  prb_mask[2][LTE_MAX_PRB]; /* per slot */
+  uint32_t nof_prb;
+  uint32_t nof_tb;
+  struct {
+    uint8_t  enabled;
+    uint8_t  qm;     /* 2,4,6,8 */
+    uint8_t  rv;
+    uint8_t  mcs;
+    int32_t  tbs;
+    uint32_t nof_bits; /* G */
+  } tb[2];
+  uint32_t nof_re;
+  uint8_t  tx_scheme;
+  uint8_t  nof_layers;
+  uint8_t  pmi;
+} lte_dl_grant_t;
+
+#define LTE_SIRNTI 0xFFFF
+#define LTE_PRNTI 0xFFFE
+#define LTE_RARNTI_START 0x0001
+#define LTE_RARNTI_END 0x000A
+#define LTE_CRNTI_START 0x000B
+#define LTE_CRNTI_END 0xFFF3
+#define LTE_RNTI_ISUSER(r) ((r) >= LTE_CRNTI_START && (r) <= LTE_CRNTI_END)
+
+/* restates dl_sniffer_ra_dl_dci_to_grant (lib/src/phy/falcon_phch/dl_sniffer_pdsch.c:95-132) +
+ * dl_sniffer_config_mimo (:255-276); returns 0 ok, <0 error */
+int lte_dl_dci_to_grant(const lte_cell_t* c, uint32_t sf_idx, uint32_t cfi, int use_alt_table, const lte_dci_t* d, lte_dl_grant_t* g);
+int lte_tbs_from_idx(int itbs, uint32_t nprb);
+/* which REs of symbol l in PRB prb are PDSCH data for this cell/subframe; returns count, fills k[] (abs subcarrier) */
+uint32_t lte_pdsch_re_in_prb(const lte_cell_t* c, uint32_t sf_idx, uint32_t cfi, uint32_t l, uint32_t prb, uint16_t* k);
+
+/* ---- PDCCH search spaces (36.213 9.1.1) ---- */
+uint32_t lte_pdcch_ue_locations(uint32_t nof_cce, uint32_t sf_idx, uint16_t rnti, uint16_t* ncce, uint8_t* L, uint32_t max);
+uint32_t lte_pdcch_common_locations(uint32_t nof_cce, uint16_t* ncce, uint8_t* L, uint32_t max);
+/* restates srsran_pdcch_validate_location (lib/src/phy/falcon_phch/falcon_pdcch.c:223-250) */
+uint32_t lte_pdcch_validate_location(uint32_t nof_cce, uint32_t ncce, uint32_t L, uint32_t sf_idx, uint16_t rnti);
+
+/* ---- PCFICH (36.212 5.3.4) ---- */
+extern const uint8_t lte_cfi_codeword[3][32];
+
+/* ---- deterministic RNG (splitmix/xoshiro) so sim + tests are reproducible ---- */
+typedef struct {
+  uint64_t s[4];
+} lte_rng_t;
+void     lte_rng_seed(lte_rng_t* r, uint64_t seed);
+uint64_t lte_rng_u64(lte_rng_t* r);
+double   lte_rng_uniform(lte_rng_t* r);
+double   lte_rng_gauss(lte_rng_t* r);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

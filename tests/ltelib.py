@@ -1,0 +1,273 @@
+"""ctypes bindings for the TEST infrastructure: sim/libltesim.so (synthetic eNB) and
+oracle/liblteoracle.so (CPU oracle).  Imported only by tests/, bench.py's cpu_baseline /
+--impl reference legs and __graft_entry__.smoke()."""
+import ctypes as C
+import os
+import subprocess
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+MAX_PRB = 110
+DCI_MAX_BITS = 64
+SIM_MAX_DCI = 32
+
+
+class Cell(C.Structure):
+    _fields_ = [("nof_prb", C.c_uint32), ("nof_ports", C.c_uint32), ("cell_id", C.c_uint32), ("nof_rx", C.c_uint32)]
+
+
+class SimCfg(C.Structure):
+    _fields_ = [("cell", Cell), ("seed", C.c_uint64), ("cfi", C.c_uint32), ("nof_ues", C.c_uint32),
+                ("dl_min", C.c_uint32), ("dl_max", C.c_uint32), ("ul_min", C.c_uint32), ("ul_max", C.c_uint32),
+                ("tm", C.c_uint32), ("mcs_min", C.c_uint32), ("mcs_max", C.c_uint32), ("si_period", C.c_uint32),
+                ("snr_db", C.c_float), ("chan_delay", C.c_uint32), ("fixed_L", C.c_uint32), ("full_band", C.c_uint32),
+                ("alt_table", C.c_uint32), ("reserved", C.c_uint32 * 7)]
+
+
+class DciTruth(C.Structure):
+    _fields_ = [("rnti", C.c_uint16), ("format", C.c_uint8), ("L", C.c_uint8), ("ncce", C.c_uint16), ("nbits", C.c_uint16),
+                ("bits", C.c_uint8 * DCI_MAX_BITS), ("nof_tb", C.c_uint8), ("tx_scheme", C.c_uint8),
+                ("qm", C.c_uint8 * 2), ("rv", C.c_uint8 * 2), ("mcs", C.c_uint8 * 2), ("tbs", C.c_int32 * 2),
+                ("payload_off", C.c_uint32 * 2), ("nof_prb", C.c_uint32), ("nof_re", C.c_uint32)]
+
+
+class SimTruth(C.Structure):
+    _fields_ = [("tti", C.c_uint32), ("cfi", C.c_uint32), ("nof_dci", C.c_uint32), ("dci", DciTruth * SIM_MAX_DCI),
+                ("payload_len", C.c_uint32)]
+
+
+class Dci(C.Structure):
+    _fields_ = [("rnti", C.c_uint16), ("format", C.c_uint8), ("alloc_type", C.c_uint8), ("rbg_bitmask", C.c_uint32),
+                ("t1_vrb_bitmask", C.c_uint32), ("t1_subset", C.c_uint32), ("t1_shift", C.c_uint32), ("riv", C.c_uint32),
+                ("t2_dist", C.c_uint8), ("t2_ngap2", C.c_uint8), ("n_prb1a", C.c_uint8),
+                ("mcs", C.c_uint8 * 2), ("rv", C.c_uint8 * 2), ("ndi", C.c_uint8 * 2), ("tb_en", C.c_uint8 * 2),
+                ("tb_cw_swap", C.c_uint8), ("pinfo", C.c_uint8), ("pid", C.c_uint8), ("tpc", C.c_uint8),
+                ("hop", C.c_uint8), ("n_dmrs", C.c_uint8), ("cqi_req", C.c_uint8)]
+
+
+class GrantTb(C.Structure):
+    _fields_ = [("enabled", C.c_uint8), ("qm", C.c_uint8), ("rv", C.c_uint8), ("mcs", C.c_uint8), ("tbs", C.c_int32),
+                ("nof_bits", C.c_uint32)]
+
+
+class DlGrant(C.Structure):
+    _fields_ = [("prb_mask", (C.c_uint8 * MAX_PRB) * 2), ("nof_prb", C.c_uint32), ("nof_tb", C.c_uint32), ("tb", GrantTb * 2),
+                ("nof_re", C.c_uint32), ("tx_scheme", C.c_uint8), ("nof_layers", C.c_uint8), ("pmi", C.c_uint8)]
+
+
+class ChestRes(C.Structure):
+    _fields_ = [("noise", (C.c_float * 2) * 2), ("rsrp", (C.c_float * 2) * 2), ("noise_avg", C.c_float), ("rsrp_avg", C.c_float),
+                ("cfo_re", C.c_float), ("cfo_im", C.c_float), ("snr_db", C.c_float), ("cfo", C.c_float)]
+
+
+FORMATS = ["0", "1", "1A", "1B", "1C", "1D", "2", "2A", "2B"]
+_built = False
+
+
+def build_infra():
+    """make sim/libltesim.so and oracle/liblteoracle.so if missing or stale."""
+    global _built
+    if _built:
+        return
+    subprocess.run(["make", "-s", "-C", ROOT, "all"], check=True)
+    _built = True
+
+
+_sim = None
+_ora = None
+
+
+def sim():
+    global _sim
+    if _sim is None:
+        build_infra()
+        L = C.CDLL(os.path.join(ROOT, "sim", "libltesim.so"))
+        L.lte_sim_create.restype = C.c_void_p
+        L.lte_sim_create.argtypes = [C.POINTER(SimCfg)]
+        L.lte_sim_destroy.argtypes = [C.c_void_p]
+        L.lte_sim_subframe.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.POINTER(SimTruth), C.c_void_p, C.c_uint32]
+        L.lte_sim_rntis.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32]
+        L.lte_sim_pdcch_encode.argtypes = [C.c_void_p, C.c_uint32, C.c_uint16, C.c_uint32, C.c_void_p]
+        L.lte_sim_dlsch_encode.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p]
+        L.lte_dci_sizeof.argtypes = [C.POINTER(Cell), C.c_int]
+        L.lte_dci_sizeof.restype = C.c_uint32
+        L.lte_dci_unpack.argtypes = [C.POINTER(Cell), C.c_int, C.c_uint16, C.c_void_p, C.c_uint32, C.POINTER(Dci)]
+        L.lte_dci_pack.argtypes = [C.POINTER(Cell), C.POINTER(Dci), C.c_void_p, C.POINTER(C.c_uint32)]
+        L.lte_dl_dci_to_grant.argtypes = [C.POINTER(Cell), C.c_uint32, C.c_uint32, C.c_int, C.POINTER(Dci), C.POINTER(DlGrant)]
+        L.lte_pdcch_validate_location.argtypes = [C.c_uint32] * 4 + [C.c_uint16]
+        L.lte_pdcch_validate_location.restype = C.c_uint32
+        L.lte_sf_len.argtypes = [C.c_uint32]
+        L.lte_sf_len.restype = C.c_uint32
+        L.lte_gold_bits.argtypes = [C.c_uint32, C.c_void_p, C.c_uint32]
+        L.lte_crc.argtypes = [C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint32]
+        L.lte_crc.restype = C.c_uint32
+        L.lte_tbs_from_idx.argtypes = [C.c_int, C.c_uint32]
+        L.lte_rm_turbo_E.argtypes = [C.c_uint32] * 5
+        L.lte_rm_turbo_E.restype = C.c_uint32
+        _sim = L
+    return _sim
+
+
+def oracle():
+    global _ora
+    if _ora is None:
+        build_infra()
+        L = C.CDLL(os.path.join(ROOT, "oracle", "liblteoracle.so"))
+        P = C.c_void_p
+        L.lteo_create.restype = P
+        L.lteo_create.argtypes = [C.POINTER(Cell)]
+        L.lteo_destroy.argtypes = [P]
+        L.lteo_nof_cce.argtypes = [P, C.c_uint32]
+        L.lteo_nof_cce.restype = C.c_uint32
+        L.lteo_det_sum.argtypes = [P, C.c_uint32]
+        L.lteo_det_sum.restype = C.c_float
+        L.lteo_ofdm_rx.argtypes = [P, P, P]
+        L.lteo_chest.argtypes = [P, C.c_uint32, P, P, C.POINTER(ChestRes)]
+        L.lteo_rb_power.argtypes = [P, P, P]
+        L.lteo_pcfich_decode.argtypes = [P, C.c_uint32, P, P, P]
+        L.lteo_pcfich_decode.restype = C.c_uint32
+        L.lteo_pdcch_extract_llr.argtypes = [P, C.c_uint32, C.c_uint32, P, P, P]
+        L.lteo_pdcch_extract_llr.restype = C.c_uint32
+        L.lteo_cce_power.argtypes = [P, C.c_uint32, P]
+        L.lteo_dci_decode.argtypes = [P, C.c_uint32, C.c_uint32, P, P]
+        L.lteo_pdsch_llr.argtypes = [P, C.c_uint32, C.c_uint32, C.c_uint16, C.POINTER(DlGrant), P, P, P, P]
+        L.lteo_dlsch_decode.argtypes = [P, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, P, P]
+        L.lteo_rm_turbo_rx.argtypes = [P, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, P]
+        L.lteo_turbo_decode.argtypes = [P, C.c_uint32, C.c_uint32, C.c_int, P, P]
+        L.lteo_turbo_decode.restype = C.c_uint32
+        L.lteo_pdsch_decode.argtypes = [P, C.c_uint32, C.c_uint32, C.c_uint16, C.POINTER(DlGrant), P, P, C.c_uint32, P, P]
+        _ora = L
+    return _ora
+
+
+def ptr(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def ptr_array(arrs):
+    """void*[] from a list of numpy arrays."""
+    t = (C.c_void_p * len(arrs))(*[a.ctypes.data for a in arrs])
+    return t
+
+
+class Sim:
+    def __init__(self, **kw):
+        cell = kw.pop("cell")
+        cfg = SimCfg()
+        cfg.cell = cell
+        d = dict(seed=1, cfi=2, nof_ues=1, dl_min=1, dl_max=1, ul_min=0, ul_max=0, tm=1, mcs_min=5, mcs_max=5, si_period=0,
+                 snr_db=30.0, chan_delay=0, fixed_L=0xFF, full_band=0, alt_table=0)
+        d.update(kw)
+        for k, v in d.items():
+            setattr(cfg, k, v)
+        self.cfg = cfg
+        self.cell = cell
+        self.h = sim().lte_sim_create(C.byref(cfg))
+        assert self.h, "lte_sim_create failed"
+        self.sf_len = sim().lte_sf_len(cell.nof_prb)
+
+    def rntis(self):
+        out = np.zeros(self.cfg.nof_ues, np.uint16)
+        sim().lte_sim_rntis(self.h, ptr(out), len(out))
+        return out
+
+    def subframe(self, tti):
+        iq = np.zeros((self.cell.nof_rx, self.sf_len), np.complex64)
+        tr = SimTruth()
+        pl = np.zeros(1 << 17, np.uint8)
+        r = sim().lte_sim_subframe(self.h, tti, ptr(iq), C.byref(tr), ptr(pl), len(pl))
+        assert r == 0, r
+        return iq, tr, pl[:tr.payload_len].copy()
+
+    def __del__(self):
+        try:
+            sim().lte_sim_destroy(self.h)
+        except Exception:
+            pass
+
+
+class Oracle:
+    """Thin OO wrapper over the oracle stages for one cell."""
+
+    def __init__(self, cell):
+        self.cell = cell
+        self.L = oracle()
+        self.h = self.L.lteo_create(C.byref(cell))
+        assert self.h
+        self.nsc = 12 * cell.nof_prb
+
+    def __del__(self):
+        try:
+            self.L.lteo_destroy(self.h)
+        except Exception:
+            pass
+
+    def ofdm(self, iq):
+        """iq [ant][sf_len] -> sym [ant][14*nsc]"""
+        sym = np.zeros((self.cell.nof_rx, 14 * self.nsc), np.complex64)
+        for a in range(self.cell.nof_rx):
+            self.L.lteo_ofdm_rx(self.h, ptr(np.ascontiguousarray(iq[a])), ptr(sym[a]))
+        return sym
+
+    def chest(self, sf_idx, sym):
+        npa = self.cell.nof_ports * self.cell.nof_rx
+        ce = np.zeros((npa, 14 * self.nsc), np.complex64)
+        res = ChestRes()
+        self.L.lteo_chest(self.h, sf_idx, ptr_array([sym[a] for a in range(self.cell.nof_rx)]),
+                          ptr_array([ce[i] for i in range(npa)]), C.byref(res))
+        return ce, res
+
+    def _pp(self, sym, ce):
+        return (ptr_array([sym[a] for a in range(sym.shape[0])]), ptr_array([ce[i] for i in range(ce.shape[0])]))
+
+    def pcfich(self, sf_idx, sym, ce):
+        corr = np.zeros(3, np.float32)
+        s, c = self._pp(sym, ce)
+        cfi = self.L.lteo_pcfich_decode(self.h, sf_idx, s, c, ptr(corr))
+        return cfi, corr
+
+    def pdcch_llr(self, sf_idx, cfi, sym, ce):
+        n = self.L.lteo_nof_cce(self.h, cfi)
+        llr = np.zeros(n * 72, np.float32)
+        s, c = self._pp(sym, ce)
+        self.L.lteo_pdcch_extract_llr(self.h, sf_idx, cfi, s, c, ptr(llr))
+        return llr
+
+    def rb_power(self, sym0):
+        p = np.zeros(self.cell.nof_prb, np.float32)
+        self.L.lteo_rb_power(self.h, ptr(np.ascontiguousarray(sym0)), ptr(p))
+        return p
+
+    def dci_decode(self, e, nof_bits):
+        e = np.ascontiguousarray(e, np.float32)
+        bits = np.zeros(DCI_MAX_BITS, np.uint8)
+        crc = C.c_uint16(0)
+        r = self.L.lteo_dci_decode(ptr(e), len(e), nof_bits, ptr(bits), C.byref(crc))
+        return r, bits[:nof_bits].copy(), crc.value
+
+    def pdsch_llr(self, sf_idx, cfi, rnti, grant, sym, ce):
+        n = grant.nof_re
+        llr = [np.zeros(n * 8 + 16, np.int16) for _ in range(2)]
+        eq = [np.zeros(n + 2, np.complex64) for _ in range(2)]
+        s, c = self._pp(sym, ce)
+        r = self.L.lteo_pdsch_llr(self.h, sf_idx, cfi, rnti, C.byref(grant), s, c, ptr_array(llr), ptr_array(eq))
+        return r, llr, eq
+
+    def pdsch_decode(self, sf_idx, cfi, rnti, grant, sym, ce, max_iter=8):
+        pl = [np.zeros(16000, np.uint8) for _ in range(2)]
+        ok = (C.c_int * 2)(0, 0)
+        s, c = self._pp(sym, ce)
+        r = self.L.lteo_pdsch_decode(self.h, sf_idx, cfi, rnti, C.byref(grant), s, c, max_iter, ptr_array(pl), ok)
+        return r, pl, [ok[0], ok[1]]
+
+
+def unpack_and_grant(cell, fmt, rnti, bits, sf_idx, cfi, alt=0):
+    d = Dci()
+    b = np.ascontiguousarray(bits, np.uint8)
+    r = sim().lte_dci_unpack(C.byref(cell), fmt, rnti, ptr(b), len(b), C.byref(d))
+    if r:
+        return r, d, None
+    g = DlGrant()
+    r = sim().lte_dl_dci_to_grant(C.byref(cell), sf_idx, cfi, alt, C.byref(d), C.byref(g))
+    return r, d, g
