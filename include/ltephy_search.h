@@ -1,0 +1,101 @@
+/*
+ * ltephy_search.h -- host half of the drop-in path (C-ABI, no GPU types): FALCON's blind-search
+ * acceptance walk over the GPU candidate table, RNTI history, DCI -> PDSCH grant, and the one-call
+ * batched pipeline.  Replaces, for this path:
+ *   DCISearch::search / recursive_blind_dci_search / inspect_dci_location_recursively
+ *                                       (reference src/src/DCISearch.cc:102-578)
+ *   RNTIManager (lib/src/util/RNTIManager.cc) -- a faithful restatement kept private to the search
+ *       object; a deployment that keeps the reference's own RNTIManager can instead run
+ *       DCISearch.cc unchanged on top of the tier-2 shim
+ *   DCIMetaFormats::update_formats      (src/src/MetaFormats.cc:41-89)
+ *   srsran_pdcch_validate_location      (lib/src/phy/falcon_phch/falcon_pdcch.c:223-250)
+ *   srsran_dci_msg_to_trace_timestamp -> dl_sniffer_ra_dl_dci_to_grant + dl_sniffer_config_mimo
+ *                                       (falcon_dci.c:148-352, dl_sniffer_pdsch.c:14-276)
+ *   SubframeWorker::work                (src/src/SubframeWorker.cc:142-207) == ltephy_decode_subframes
+ */
+#ifndef LTEPHY_SEARCH_H
+#define LTEPHY_SEARCH_H
+#include "ltephy_b200.h"
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct ltephy_search ltephy_search_t;
+
+/* DCIBlindSearchStats, src/include/PhyCommon.h:11-25 */
+typedef struct {
+  uint32_t nof_decoded_locations, nof_cce, nof_missed_cce, nof_subframes, nof_subframe_collisions_dw, nof_subframe_collisions_up,
+      nof_locations;
+} ltephy_search_stats_t;
+
+/* unpacked DCI fields (subset of srsran_dci_dl_t the grant conversion needs) */
+typedef struct {
+  uint16_t rnti;
+  uint8_t  format, alloc_type;
+  uint8_t  mcs[2], rv[2], ndi[2];
+  uint8_t  harq_pid, tpc, tb_cw_swap, pinfo;
+  uint32_t nof_prb;
+} ltephy_dci_fields_t;
+
+#define LTEPHY_MIMO_NOT_SUPPORT -10 /* DL_SNIFFER_MIMO_NOT_SUPPORT */
+#define LTEPHY_MIMO_PMI_WRONG -11   /* DL_SNIFFER_PMI_WRONG */
+#define LTEPHY_MIMO_LAYER_WRONG -12 /* DL_SNIFFER_LAYER_WRONG */
+#define LTEPHY_SEQ_NONE (~0ull)
+
+/* activation reasons: rnti_manager_activation_reason_t, lib/include/falcon/util/rnti_manager_c.h */
+enum { LTEPHY_ACT_UNSET = 0, LTEPHY_ACT_EVERGREEN, LTEPHY_ACT_RAR, LTEPHY_ACT_SHORTCUT, LTEPHY_ACT_HISTOGRAM, LTEPHY_ACT_OTHER };
+
+/* geometry helper used by the search (implemented next to the PHY handle) */
+void ltephy_cell_of(const ltephy_t* h, uint32_t* nof_prb, uint32_t* nof_ports, uint32_t* cell_id, uint32_t* nof_rx);
+
+/* histogram_threshold: DEFAULT_RNTI_HISTOGRAM_THRESHOLD = 5 (src/include/Settings.h:57).  The evergreen
+ * (RA-RNTI, P/SI-RNTI for formats 1A and 1C) and forbidden (RNTI 0) ranges are seeded as
+ * LTESniffer_Core.cc:398-417 does after the MIB. */
+ltephy_search_t* ltephy_search_create(const ltephy_t* h, uint32_t histogram_threshold);
+/* same without a GPU handle (host-only use: unit tests, or a search running beside a remote PHY) */
+ltephy_search_t* ltephy_search_create_cell(uint32_t nof_prb, uint32_t nof_ports, uint32_t cell_id, uint32_t nof_rx, uint32_t histogram_threshold);
+void             ltephy_search_destroy(ltephy_search_t* s);
+/* shortcut discovery on/off (DCISearch::setShortcutDiscovery), -m skip_secondary_meta_formats,
+ * dci_format_split_update_interval_ms (0 = never re-split) */
+void ltephy_search_config(ltephy_search_t* s, int shortcut, int skip_secondary, uint32_t update_interval);
+void ltephy_search_add_evergreen(ltephy_search_t* s, uint16_t rnti_start, uint16_t rnti_end, uint32_t format_idx);
+void ltephy_search_add_forbidden(ltephy_search_t* s, uint16_t rnti_start, uint16_t rnti_end, uint32_t format_idx);
+/* rntiManager.activateAndRefresh, e.g. for T-CRNTIs found in a RAR (src/src/DL_Sniffer_PDSCH.cc:659,794) */
+void ltephy_search_activate(ltephy_search_t* s, uint16_t rnti, uint32_t format_idx, int reason);
+
+/* One subframe (must be called in subframe order).  cands: [LTEPHY_MAX_LOC][LTEPHY_MAX_SIZES] of this
+ * subframe.  Writes the accepted DCIs in the order DCICollection::addCandidate would receive them. */
+int ltephy_search_subframe(ltephy_search_t* s, const ltephy_sf_info_t* info, const ltephy_cand_t* cands, uint32_t sf_in_batch, ltephy_dci_t* out,
+                           uint32_t max_out, uint32_t* n_out);
+void ltephy_search_get_stats(const ltephy_search_t* s, ltephy_search_stats_t* st);
+uint32_t ltephy_search_validate_location(uint32_t nof_cce, uint32_t ncce, uint32_t L, uint32_t sf_idx, uint16_t rnti);
+
+/* RNTI-history taps (same semantics as the reference's rnti_manager_* C wrappers) */
+int      ltephy_search_rnti_validate_and_refresh(ltephy_search_t* s, uint16_t rnti, uint32_t format_idx);
+void     ltephy_search_rnti_add_candidate(ltephy_search_t* s, uint16_t rnti, uint32_t format_idx);
+void     ltephy_search_rnti_step_time(ltephy_search_t* s);
+uint32_t ltephy_search_rnti_frequency(const ltephy_search_t* s, uint16_t rnti, uint32_t format_idx);
+uint32_t ltephy_search_rnti_assoc_format(const ltephy_search_t* s, uint16_t rnti);
+int      ltephy_search_rnti_reason(const ltephy_search_t* s, uint16_t rnti);
+int      ltephy_search_rnti_is_forbidden(const ltephy_search_t* s, uint16_t rnti, uint32_t format_idx);
+int      ltephy_search_rnti_is_evergreen(const ltephy_search_t* s, uint16_t rnti, uint32_t format_idx);
+
+/* DCI bits -> grant.  use_256qam_table: 0 = 36.213 Table 7.1.7.1-1, 1 = Table 7.1.7.1-1A.
+ * Returns 0, LTEPHY_ERROR (unpack / allocation / TBS failure: the reference zeroes the RNTI,
+ * falcon_dci.c:286-305) or LTEPHY_MIMO_*. */
+int ltephy_dci_to_grant(const ltephy_search_t* s, const ltephy_dci_t* dci, uint32_t sf_idx, uint32_t cfi, int use_256qam_table, ltephy_grant_t* grant,
+                        ltephy_dci_fields_t* fields);
+
+/* Whole batch: IQ in host memory -> accepted DCIs + transport blocks.  seq orders concurrent calls on
+ * different PHY handles that share one search object (the search runs strictly in seq order, starting
+ * at 0); pass LTEPHY_SEQ_NONE for a single pipeline.
+ *   info[n], cand_scratch[n*LTEPHY_MAX_LOC*LTEPHY_MAX_SIZES] (caller-owned, pinned if possible),
+ *   dcis[max_dcis], tbs[2*max_dcis] (tbs[2*i+t] belongs to dcis[i]), payload. */
+int ltephy_decode_subframes(ltephy_t* h, ltephy_search_t* s, const float* iq, const uint32_t* tti, uint32_t n, uint64_t seq, ltephy_sf_info_t* info,
+                            ltephy_cand_t* cand_scratch, ltephy_dci_t* dcis, uint32_t max_dcis, uint32_t* n_dcis, ltephy_tb_result_t* tbs,
+                            uint8_t* payload, size_t payload_cap);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

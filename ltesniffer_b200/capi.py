@@ -205,3 +205,129 @@ def cand_bits(c, nbits):
     """uint64 payload -> array of nbits bits (bit i at position 63-i)."""
     v = int(c)
     return np.array([(v >> (63 - i)) & 1 for i in range(nbits)], np.uint8)
+
+
+# ------------------------------------------------------------------------------------------------
+# host search / grant conversion / one-call pipeline (include/ltephy_search.h)
+class DciOut(C.Structure):
+    _fields_ = [("sf", C.c_uint32), ("rnti", C.c_uint16), ("format", C.c_uint8), ("L", C.c_uint8), ("ncce", C.c_uint16),
+                ("nof_bits", C.c_uint16), ("bits", C.c_uint64), ("histogram_value", C.c_uint32)]
+
+
+class SearchStats(C.Structure):
+    _fields_ = [("nof_decoded_locations", C.c_uint32), ("nof_cce", C.c_uint32), ("nof_missed_cce", C.c_uint32), ("nof_subframes", C.c_uint32),
+                ("nof_subframe_collisions_dw", C.c_uint32), ("nof_subframe_collisions_up", C.c_uint32), ("nof_locations", C.c_uint32)]
+
+
+class DciFields(C.Structure):
+    _fields_ = [("rnti", C.c_uint16), ("format", C.c_uint8), ("alloc_type", C.c_uint8), ("mcs", C.c_uint8 * 2), ("rv", C.c_uint8 * 2),
+                ("ndi", C.c_uint8 * 2), ("harq_pid", C.c_uint8), ("tpc", C.c_uint8), ("tb_cw_swap", C.c_uint8), ("pinfo", C.c_uint8),
+                ("nof_prb", C.c_uint32)]
+
+
+DCI_DTYPE = np.dtype({"names": ["sf", "rnti", "format", "L", "ncce", "nof_bits", "bits", "histogram_value"],
+                      "formats": ["<u4", "<u2", "u1", "u1", "<u2", "<u2", "<u8", "<u4"],
+                      "offsets": [DciOut.sf.offset, DciOut.rnti.offset, DciOut.format.offset, DciOut.L.offset, DciOut.ncce.offset,
+                                  DciOut.nof_bits.offset, DciOut.bits.offset, DciOut.histogram_value.offset],
+                      "itemsize": C.sizeof(DciOut)})
+assert DCI_DTYPE.itemsize == C.sizeof(DciOut)
+SEQ_NONE = (1 << 64) - 1
+
+
+def _bind_search(L):
+    if getattr(L, "_search_bound", False):
+        return
+    P = C.c_void_p
+    L.ltephy_search_create.argtypes = [P, C.c_uint32]
+    L.ltephy_search_create.restype = P
+    L.ltephy_search_create_cell.argtypes = [C.c_uint32] * 5
+    L.ltephy_search_create_cell.restype = P
+    L.ltephy_search_destroy.argtypes = [P]
+    L.ltephy_search_config.argtypes = [P, C.c_int, C.c_int, C.c_uint32]
+    L.ltephy_search_add_evergreen.argtypes = [P, C.c_uint16, C.c_uint16, C.c_uint32]
+    L.ltephy_search_add_forbidden.argtypes = [P, C.c_uint16, C.c_uint16, C.c_uint32]
+    L.ltephy_search_activate.argtypes = [P, C.c_uint16, C.c_uint32, C.c_int]
+    L.ltephy_search_subframe.argtypes = [P, P, P, C.c_uint32, P, C.c_uint32, P]
+    L.ltephy_search_get_stats.argtypes = [P, P]
+    L.ltephy_search_validate_location.argtypes = [C.c_uint32] * 4 + [C.c_uint16]
+    L.ltephy_search_validate_location.restype = C.c_uint32
+    L.ltephy_search_rnti_validate_and_refresh.argtypes = [P, C.c_uint16, C.c_uint32]
+    L.ltephy_search_rnti_add_candidate.argtypes = [P, C.c_uint16, C.c_uint32]
+    L.ltephy_search_rnti_step_time.argtypes = [P]
+    for f in ("ltephy_search_rnti_frequency", "ltephy_search_rnti_is_forbidden", "ltephy_search_rnti_is_evergreen"):
+        getattr(L, f).argtypes = [P, C.c_uint16, C.c_uint32]
+        getattr(L, f).restype = C.c_uint32
+    L.ltephy_search_rnti_assoc_format.argtypes = [P, C.c_uint16]
+    L.ltephy_search_rnti_assoc_format.restype = C.c_uint32
+    L.ltephy_search_rnti_reason.argtypes = [P, C.c_uint16]
+    L.ltephy_dci_to_grant.argtypes = [P, P, C.c_uint32, C.c_uint32, C.c_int, P, P]
+    L.ltephy_decode_subframes.argtypes = [P, P, P, P, C.c_uint32, C.c_uint64, P, P, P, C.c_uint32, P, P, P, C.c_size_t]
+    L._search_bound = True
+
+
+class Search:
+    """FALCON acceptance walk + RNTI history (host only; usable without a GPU)."""
+
+    def __init__(self, nof_prb, nof_ports, cell_id, nof_rx, threshold=5):
+        self.L = load_library()
+        _bind_search(self.L)
+        self.h = self.L.ltephy_search_create_cell(nof_prb, nof_ports, cell_id, nof_rx, threshold)
+        if not self.h:
+            raise RuntimeError("ltephy_search_create_cell failed")
+
+    def close(self):
+        if self.h:
+            self.L.ltephy_search_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def config(self, shortcut=1, skip_secondary=0, update_interval=500):
+        self.L.ltephy_search_config(self.h, shortcut, skip_secondary, update_interval)
+
+    def subframe(self, info, cands, sf_in_batch=0, max_out=64):
+        """info: SfInfo, cands: CAND_DTYPE array [MAX_LOC][MAX_SIZES] -> accepted DCIs (structured array)"""
+        out = np.zeros(max_out, DCI_DTYPE)
+        n = C.c_uint32(0)
+        cands = np.ascontiguousarray(cands)
+        r = self.L.ltephy_search_subframe(self.h, C.byref(info), _p(cands), sf_in_batch, _p(out), max_out, C.byref(n))
+        if r < 0:
+            raise RuntimeError("ltephy_search_subframe failed (%d)" % r)
+        return out[:n.value].copy()
+
+    def stats(self):
+        st = SearchStats()
+        self.L.ltephy_search_get_stats(self.h, C.byref(st))
+        return st
+
+    def dci_to_grant(self, dci_row, sf_idx, cfi, use_256qam=0):
+        d = DciOut(sf=int(dci_row["sf"]), rnti=int(dci_row["rnti"]), format=int(dci_row["format"]), L=int(dci_row["L"]), ncce=int(dci_row["ncce"]),
+                   nof_bits=int(dci_row["nof_bits"]), bits=int(dci_row["bits"]), histogram_value=int(dci_row["histogram_value"]))
+        g = Grant()
+        f = DciFields()
+        r = self.L.ltephy_dci_to_grant(self.h, C.byref(d), sf_idx, cfi, use_256qam, C.byref(g), C.byref(f))
+        return r, g, f
+
+
+def decode_subframes(phy, search, iq, tti, seq=SEQ_NONE, max_dcis=None, scratch=None):
+    """One call through the reference-facing pipeline: host IQ -> (info, dcis, tb results, payload)."""
+    L = phy.L
+    _bind_search(L)
+    iq = np.ascontiguousarray(iq, np.complex64)
+    tti = np.ascontiguousarray(tti, np.uint32)
+    n = len(tti)
+    max_dcis = max_dcis or 32 * n
+    if scratch is None:
+        scratch = dict(info=(SfInfo * n)(), cands=np.zeros((n, MAX_LOC, MAX_SIZES), CAND_DTYPE), dcis=np.zeros(max_dcis, DCI_DTYPE),
+                       tbs=(TbResult * (2 * max_dcis))(), payload=np.zeros(max_dcis * 2 * 2048 + n * 40000, np.uint8))
+    nd = C.c_uint32(0)
+    r = L.ltephy_decode_subframes(phy.h, search.h, _p(iq), _p(tti), n, seq, scratch["info"], _p(scratch["cands"]), _p(scratch["dcis"]), max_dcis,
+                                  C.byref(nd), scratch["tbs"], _p(scratch["payload"]), scratch["payload"].nbytes)
+    if r != 0:
+        raise RuntimeError("ltephy_decode_subframes failed (%d): %s" % (r, L.ltephy_last_error().decode()))
+    phy.n = n
+    return scratch["info"], scratch["dcis"][:nd.value], scratch["tbs"], scratch["payload"]

@@ -1,0 +1,759 @@
+// host_search.cpp -- host (C++17) half of the drop-in path: replays FALCON's recursive blind DCI search
+// over the candidate table produced by the Viterbi kernel, in subframe order, with a restatement of the
+// reference's RNTI history, and converts accepted DL DCIs into PDSCH grants.
+//   reference: src/src/DCISearch.cc:102-578 (inspect_dci_location_recursively, recursive_blind_dci_search,
+//   search), lib/src/util/RNTIManager.cc + Histogram.cc, src/src/MetaFormats.cc:41-89,
+//   lib/src/phy/falcon_phch/falcon_pdcch.c:183-250 (search-space validation), falcon_dci.c:148-352 and
+//   dl_sniffer_pdsch.c:14-276 (DCI -> grant).  Integer control flow only: the GPU never sees this state.
+#include "../../include/ltephy_b200.h"
+#include "../../include/ltephy_search.h"
+#include "../../include/lte_tables.h"
+#include "lte_host.hpp"
+#include <algorithm>
+#include <condition_variable>
+#include <cstring>
+#include <mutex>
+#include <vector>
+
+namespace {
+
+constexpr int      NF            = LTEPHY_NOF_FORMATS;
+constexpr uint32_t HIST_DEPTH    = 200 * (304 / 5); // RNTI_HISTORY_DEPTH, RNTIManager.h:47-49
+constexpr uint32_t PER_SF        = 304 / 5;         // RNTI_PER_SUBFRAME
+constexpr uint32_t LIFETIME      = 10000;           // RRC_INACTIVITY_TIMER_MS
+constexpr uint16_t RARNTI_START = 0x0001, RARNTI_END = 0x000A, CRNTI_START = 0x000B, CRNTI_END = 0xFFF3, MRNTI = 0xFFFD, PRNTI = 0xFFFE;
+enum { ACT_UNSET = 0, ACT_EVERGREEN, ACT_RAR, ACT_SHORTCUT, ACT_HISTOGRAM, ACT_OTHER };
+
+// ---------------------------------------------------------------------------------------------------
+// RNTI history: same observable behaviour as RNTIManager (per-format 200 ms sliding histogram padded to
+// 60 entries per subframe, active set with 10 s expiry, evergreen / forbidden intervals).
+struct RntiManager {
+  struct Hist {
+    std::vector<uint16_t> ring  = std::vector<uint16_t>(HIST_DEPTH, 0);
+    std::vector<uint16_t> count = std::vector<uint16_t>(65536, 0);
+    uint32_t              cur   = 0;
+    bool                  ready = false;
+    inline void           add(uint16_t v)
+    {
+      if (ready) count[ring[cur]]--;
+      ring[cur] = v;
+      count[v]++;
+      if (++cur == HIST_DEPTH) ready = true, cur = 0;
+    }
+  };
+  struct Interval {
+    uint16_t a, b;
+  };
+  Hist                  hist[NF];
+  std::vector<Interval> evergreen[NF], forbidden[NF];
+  std::vector<uint8_t>  active  = std::vector<uint8_t>(65536, 0);
+  std::vector<uint8_t>  reason  = std::vector<uint8_t>(65536, 0);
+  std::vector<uint32_t> last_seen = std::vector<uint32_t>(65536, 0);
+  std::vector<uint32_t> assoc   = std::vector<uint32_t>(65536, 0);
+  uint32_t              timestamp = 0, threshold = 5;
+  int32_t               remaining[NF];
+  RntiManager() { std::fill(remaining, remaining + NF, (int32_t)PER_SF); }
+
+  bool is_evergreen(uint16_t r, uint32_t f) const
+  {
+    for (auto& i : evergreen[f])
+      if (r >= i.a && r <= i.b) return true;
+    return false;
+  }
+  bool is_forbidden(uint16_t r, uint32_t f) const
+  {
+    for (auto& i : forbidden[f])
+      if (r >= i.a && r <= i.b) return true;
+    return false;
+  }
+  uint32_t freq(uint16_t r, uint32_t f) const { return hist[f].count[r]; }
+  void     add_candidate(uint16_t r, uint32_t f)
+  {
+    hist[f].add(r);
+    remaining[f]--;
+  }
+  void activate(uint16_t r, uint8_t why)
+  {
+    if (!active[r]) active[r] = 1, reason[r] = why;
+  }
+  void deactivate(uint16_t r)
+  {
+    if (active[r]) active[r] = 0, assoc[r] = 0, reason[r] = ACT_UNSET;
+  }
+  bool expired(uint16_t r) const { return !(active[r] && timestamp - last_seen[r] < LIFETIME); }
+  bool validate(uint16_t r, uint32_t f)
+  {
+    if (is_evergreen(r, f)) return true;
+    if (is_forbidden(r, f)) return false;
+    if (active[r]) {
+      if (!expired(r)) return true;
+      deactivate(r);
+    }
+    // validateByHistogram
+    uint32_t likely = 0, maxf = 0;
+    for (uint32_t i = 1; i < NF; i++)
+      if (hist[i].count[r] > maxf) maxf = hist[i].count[r], likely = i;
+    if (f != 0 && f != likely) return false;
+    const uint32_t ul = hist[0].count[r], dl = likely ? hist[likely].count[r] : 0;
+    if (ul + dl > threshold) {
+      activate(r, ACT_HISTOGRAM);
+      assoc[r] = dl > threshold ? likely : 0;
+      return true;
+    }
+    return false;
+  }
+  bool validate_and_refresh(uint16_t r, uint32_t f)
+  {
+    const bool ok = validate(r, f);
+    if (ok) last_seen[r] = timestamp;
+    return ok;
+  }
+  void activate_and_refresh(uint16_t r, uint32_t f, uint8_t why)
+  {
+    activate(r, why);
+    last_seen[r] = timestamp;
+    assoc[r]     = f;
+  }
+  void step_time()
+  {
+    for (int i = 0; i < NF; i++) {
+      for (int32_t k = 0; k < remaining[i]; k++) hist[i].add(0);
+      remaining[i] = (int32_t)PER_SF;
+    }
+    timestamp++;
+  }
+};
+
+// 36.213 9.1.1 search-space membership in O(1); equals srsran_pdcch_validate_location (falcon_pdcch.c:223-250)
+inline bool in_ue_space(uint32_t nof_cce, uint32_t ncce, uint32_t l, uint32_t Yk)
+{
+  static const uint32_t M[4] = {6, 6, 2, 2};
+  const uint32_t        L = 1u << l;
+  if (nof_cce < L || (ncce & (L - 1))) return false;
+  const uint32_t n = nof_cce / L, q = ncce / L;
+  if (q >= n) return false;
+  return (q + n - Yk % n) % n < M[l];
+}
+inline bool in_common_space(uint32_t nof_cce, uint32_t ncce, uint32_t l)
+{
+  if (l < 2) return false;
+  const uint32_t L = 1u << l;
+  if (nof_cce < L || (ncce & (L - 1))) return false;
+  const uint32_t lim = std::min<uint32_t>(nof_cce, 16) / L, q = ncce / L;
+  return q < lim && q < nof_cce / L;
+}
+uint32_t validate_location(uint32_t nof_cce, uint32_t ncce, uint32_t l, uint32_t sf_idx, uint16_t rnti)
+{
+  bool ue = false, common = false;
+  if (rnti >= RARNTI_START && rnti <= RARNTI_END)
+    common = true;
+  else if (rnti >= CRNTI_START && rnti <= CRNTI_END)
+    ue = common = true;
+  else if (rnti >= MRNTI)
+    common = true;
+  else
+    return 0;
+  uint32_t Yk = rnti;
+  if (ue)
+    for (uint32_t m = 0; m < sf_idx + 1; m++) Yk = (39827u * Yk) % 65537u;
+  const bool valid = (ue && in_ue_space(nof_cce, ncce, l, Yk)) || (common && in_common_space(nof_cce, ncce, l));
+  if (!valid) return 0;
+  const bool amb = l > 0 && ((ue && in_ue_space(nof_cce, ncce, l - 1, Yk)) || (common && in_common_space(nof_cce, ncce, l - 1)));
+  return amb ? 1 : 2;
+}
+
+struct Cand {
+  uint64_t bits   = 0;
+  uint16_t rnti   = 0;
+  uint8_t  format = 0; // decoded format
+  uint8_t  ssm    = 0;
+  uint16_t nof_bits = 0;
+};
+struct Loc {
+  uint8_t L;
+  uint8_t ncce;
+  bool    used, occupied, checked, sufficient_power;
+};
+struct Meta {
+  uint8_t  format;
+  uint32_t hits;
+};
+struct TempDci0 {
+  uint16_t rnti;
+  uint8_t  L, format;
+  uint16_t ncce;
+  Cand     cand;
+};
+
+} // namespace
+
+struct ltephy_search {
+  ltehost::Cell      cell;
+  ltehost::SizeTable st;
+  uint32_t           nof_cce[3]{};
+  RntiManager        rm;
+  Meta               all[NF];
+  uint8_t            primary[NF], secondary[NF];
+  uint32_t           n_primary = 0, n_secondary = 0;
+  double             split_ratio     = 0.99;
+  bool               skip_secondary  = false, shortcut = true;
+  uint32_t           update_interval = 500, sf_cnt = 0;
+  ltephy_search_stats_t stats{};
+  // per-subframe scratch
+  const ltephy_cand_t* T = nullptr;
+  uint32_t             sf_idx = 0, ncce_sf = 0, sf_batch = 0;
+  Loc                  loc[LTEPHY_MAX_LOC];
+  int16_t              loc_of[4][LTEPHY_MAX_CCE]; // [L][ncce] -> location index or -1
+  std::vector<TempDci0> temp_dci0;
+  ltephy_dci_t*        out = nullptr;
+  uint32_t             out_cap = 0, out_n = 0;
+  // batch ordering for concurrent pipelines
+  std::mutex              mtx;
+  std::condition_variable cv;
+  uint64_t                next_seq = 0;
+
+  void update_formats()
+  {
+    uint8_t sorted[NF];
+    double  total = 0;
+    for (int i = 0; i < NF; i++) sorted[i] = (uint8_t)i, total += all[i].hits;
+    for (int i = 0; i < NF - 1; i++) {
+      int mx = i;
+      for (int j = mx; j < NF; j++)
+        if (all[sorted[j]].hits > all[sorted[mx]].hits) mx = j;
+      std::swap(sorted[i], sorted[mx]);
+    }
+    const double thr = total * split_ratio;
+    double       cum = 0;
+    n_primary = n_secondary = 0;
+    for (int i = 0; i < NF; i++) {
+      if (cum <= thr)
+        primary[n_primary++] = sorted[i];
+      else
+        secondary[n_secondary++] = sorted[i];
+      cum += all[sorted[i]].hits;
+      all[sorted[i]].hits = 0;
+    }
+  }
+  inline void fetch(uint32_t li, uint32_t format, Cand& c) const
+  {
+    const ltephy_cand_t& t = T[(size_t)li * LTEPHY_MAX_SIZES + st.index_of[format]];
+    c                      = Cand{};
+    c.nof_bits             = (uint16_t)st.sizes[st.index_of[format]];
+    if (!t.valid) return; // all-zero LLRs: the reference leaves the calloc'ed candidate untouched
+    c.bits = t.bits, c.rnti = t.rnti;
+    if (format == ltehost::F0 || format == ltehost::F1A)
+      c.format = (t.bits >> 63) ? ltehost::F1A : ltehost::F0;
+    else
+      c.format = (uint8_t)format;
+  }
+  void emit(const Cand& c, uint32_t L, uint32_t ncce, uint32_t histval)
+  {
+    if (out_n < out_cap) {
+      ltephy_dci_t& o = out[out_n];
+      o.sf = sf_batch, o.rnti = c.rnti, o.format = c.format, o.L = (uint8_t)L, o.ncce = (uint16_t)ncce, o.nof_bits = c.nof_bits, o.bits = c.bits;
+      o.histogram_value = histval;
+    }
+    out_n++;
+  }
+  int inspect(uint32_t ncce, uint32_t L, uint32_t max_depth, const uint8_t* mf, uint32_t nf, bool discovery, const Cand* parent)
+  {
+    const int li = loc_of[L][ncce];
+    if (li < 0) return 0;
+    Loc& lc = loc[li];
+    if (lc.occupied || lc.checked || !lc.sufficient_power) return 0;
+    Cand     cand[NF];
+    int      best = -1;
+    uint32_t best_val = 0, n_above = 0;
+    for (uint32_t f = 0; f < nf; f++) {
+      const uint32_t fmt = mf[f];
+      fetch((uint32_t)li, fmt, cand[f]);
+      stats.nof_decoded_locations++;
+      if (rm.reason[cand[f].rnti] == ACT_RAR && cand[f].format == 0) {
+        bool add = true;
+        for (auto& m : temp_dci0)
+          if (m.format == cand[f].format && m.rnti == cand[f].rnti && m.ncce == ncce) add = false;
+        if (add) temp_dci0.push_back({cand[f].rnti, (uint8_t)L, cand[f].format, (uint16_t)ncce, cand[f]});
+      }
+      if (fmt != cand[f].format) {
+        cand[f].rnti = 0;
+        continue;
+      }
+      const uint16_t r = cand[f].rnti;
+      if (fmt == ltehost::F1C && r > RARNTI_END && r < PRNTI) {
+        cand[f].rnti = 0;
+        continue;
+      }
+      if (r > RARNTI_START && r < RARNTI_END && fmt != ltehost::F1A && fmt != ltehost::F1C) {
+        cand[f].rnti = 0;
+        continue;
+      }
+      if (shortcut && discovery && parent && parent[f].rnti == r && !rm.is_forbidden(r, fmt)) return -((int)f + 1);
+      cand[f].ssm = (uint8_t)validate_location(ncce_sf, ncce, L, sf_idx, r);
+      if (cand[f].ssm == 0) {
+        cand[f].rnti = 0;
+        continue;
+      }
+      if (rm.validate_and_refresh(r, fmt)) {
+        n_above++;
+        best     = (int)f;
+        best_val = rm.freq(r, fmt);
+      }
+    }
+    if (n_above > 1) {
+      best = -1;
+      uint32_t hmax = 0;
+      for (uint32_t f = 0; f < nf; f++)
+        if (cand[f].rnti != 0) {
+          const uint32_t h = rm.freq(cand[f].rnti, mf[f]);
+          if (h > hmax) hmax = h, best = (int)f, best_val = h;
+        }
+      if (best < 0) n_above = 0;
+    }
+    lc.checked = true;
+    int disamb = 0;
+    if (n_above > 0 && cand[best].ssm == 1) {
+      if (L > 0 && max_depth > 0) disamb = inspect(ncce + (1u << (L - 1)), L - 1, max_depth - 1, mf, nf, false, nullptr);
+    } else if (n_above == 0) {
+      int rr = 0;
+      if (L > 0 && max_depth > 0) {
+        rr += inspect(ncce, L - 1, max_depth - 1, mf, nf, discovery, cand);
+        if (rr < 0) {
+          best     = -rr - 1;
+          best_val = rm.freq(cand[best].rnti, mf[best]);
+          n_above  = 1;
+          if (cand[best].ssm == 1) disamb = inspect(ncce + (1u << (L - 1)), L - 1, std::min<uint32_t>(max_depth, 99) - 1, mf, nf, false, nullptr);
+          rm.activate_and_refresh(cand[best].rnti, mf[best], ACT_SHORTCUT);
+        } else
+          rr += inspect(ncce + (1u << (L - 1)), L - 1, max_depth - 1, mf, nf, discovery, nullptr);
+      }
+      if (rr == 0) {
+        if (discovery)
+          for (uint32_t f = 0; f < nf; f++)
+            if (cand[f].rnti != 0) rm.add_candidate(cand[f].rnti, mf[f]);
+        return 0;
+      }
+      if (rr > 0) return rr;
+    }
+    if (n_above > 0) {
+      lc.used = true;
+      for (uint32_t c = ncce; c < ncce + (1u << L); c++)
+        for (int a = 0; a < 4; a++) {
+          const int j = loc_of[a][c & ~((1u << a) - 1)];
+          if (j >= 0) loc[j].occupied = loc[j].checked = true;
+        }
+      rm.add_candidate(cand[best].rnti, mf[best]);
+      all[mf[best]].hits++;
+      const uint32_t L_dis = disamb > 0 ? L - 1 : L;
+      const Cand&    b     = cand[best];
+      if (b.rnti != 0) {
+        bool add = true;
+        if (b.format == 0)
+          for (auto& m : temp_dci0)
+            if (m.format == b.format && m.rnti == b.rnti && m.ncce == ncce) add = false;
+        if (add) emit(b, L_dis, ncce, best_val);
+        for (auto& m : temp_dci0) emit(m.cand, m.L, m.ncce, rm.freq(m.rnti, m.format));
+        temp_dci0.clear();
+      }
+      return 1 + disamb;
+    }
+    return 0;
+  }
+  int search_subframe(const ltephy_sf_info_t& info, const ltephy_cand_t* table, uint32_t sf_in_batch, ltephy_dci_t* o, uint32_t cap, uint32_t* n)
+  {
+    if (update_interval && (sf_cnt % update_interval) == 0) update_formats();
+    sf_cnt++;
+    out = o, out_cap = cap, out_n = 0, sf_batch = sf_in_batch, T = table;
+    int ret = LTEPHY_ERROR;
+    if (info.snr_db > 6.0f && info.cfi >= 1 && info.cfi <= 3) {
+      temp_dci0.clear();
+      sf_idx  = info.tti % 10;
+      ncce_sf = nof_cce[info.cfi - 1];
+      stats.nof_cce += ncce_sf;
+      memset(loc_of, 0xFF, sizeof(loc_of));
+      const uint32_t lim = std::min<uint32_t>(ncce_sf, LTEPHY_SEARCH_MAX_CCE);
+      uint32_t       k   = 0;
+      for (int l = 3; l >= 0; l--) {
+        const uint32_t Lc = 1u << l;
+        for (uint32_t i = 0; i < lim / Lc && k < LTEPHY_MAX_LOC; i++) {
+          loc[k]                 = {(uint8_t)l, (uint8_t)(Lc * i), false, false, false, true};
+          loc_of[l][Lc * i]      = (int16_t)k;
+          k++;
+        }
+      }
+      stats.nof_locations += k;
+      for (uint32_t c = 0; c < lim; c++)
+        if (info.cce_power[c] < 0.7f)
+          for (int a = 0; a < 4; a++) {
+            const int j = loc_of[a][c & ~((1u << a) - 1)];
+            if (j >= 0) loc[j].sufficient_power = false;
+          }
+      ret = 0;
+      for (uint32_t i = 0; i < k; i++) ret += inspect(loc[i].ncce, loc[i].L, 99, primary, n_primary, true, nullptr);
+      if (!skip_secondary) {
+        for (uint32_t i = 0; i < k; i++) loc[i].checked = false;
+        for (uint32_t i = 0; i < k; i++) ret += inspect(loc[i].ncce, loc[i].L, 99, secondary, n_secondary, true, nullptr);
+      }
+      uint32_t missed = 0;
+      for (uint32_t c = 0; c < lim; c++) {
+        if (info.cce_power[c] < 0.7f) continue;
+        bool m = true;
+        for (int a = 0; a < 4 && m; a++) {
+          const int j = loc_of[a][c & ~((1u << a) - 1)];
+          if (j >= 0 && loc[j].used) m = false;
+        }
+        missed += m;
+      }
+      stats.nof_missed_cce += missed;
+      rm.step_time();
+    }
+    stats.nof_subframes++;
+    if (n) *n = out_n;
+    return out_n > cap ? LTEPHY_ERROR_INVALID_INPUTS : (ret < 0 ? 0 : ret);
+  }
+};
+
+// ===================================================================================================
+// DCI -> grant (a10).  srsran_dci_msg_unpack_pdsch + dl_sniffer_ra_dl_dci_to_grant + dl_sniffer_config_mimo.
+namespace {
+struct Bits {
+  uint64_t v;
+  uint32_t pos = 0;
+  uint32_t get(uint32_t n)
+  {
+    uint32_t r = n ? (uint32_t)((v << pos) >> (64 - n)) : 0;
+    pos += n;
+    return r;
+  }
+};
+uint32_t clog2(uint32_t v)
+{
+  uint32_t n = 0;
+  while ((1u << n) < v) n++;
+  return n;
+}
+uint32_t rbg_size(uint32_t n) { return n <= 10 ? 1 : n <= 26 ? 2 : n <= 63 ? 3 : 4; }
+uint32_t gap1(uint32_t n) { return n <= 10 ? (n + 1) / 2 : n == 11 ? 4 : n <= 19 ? 8 : n <= 26 ? 12 : n <= 44 ? 18 : n <= 63 ? 27 : n <= 79 ? 32 : 48; }
+uint32_t gap2(uint32_t n) { return n < 50 ? 0 : n <= 63 ? 9 : 16; }
+uint32_t nvrb(uint32_t n, bool g2)
+{
+  if (!g2) {
+    uint32_t g = gap1(n);
+    return 2 * std::min(g, n - g);
+  }
+  uint32_t g = gap2(n);
+  return g ? (n / (2 * g)) * 2 * g : 0;
+}
+void riv_decode(uint32_t riv, uint32_t N, uint32_t& L, uint32_t& S)
+{
+  L = riv / N + 1, S = riv % N;
+  if (L + S > N) L = N - L + 2, S = N - 1 - S;
+}
+void dvrb(uint32_t N, bool g2, uint32_t v, uint32_t& p0, uint32_t& p1)
+{
+  const uint32_t P = rbg_size(N), Ng = g2 ? gap2(N) : gap1(N), Nt = g2 ? 2 * Ng : nvrb(N, false);
+  const uint32_t Nrow = ((Nt + 4 * P - 1) / (4 * P)) * P, Nnull = 4 * Nrow - Nt, nt = v % Nt, blk = v / Nt;
+  const int      a = (int)(2 * Nrow * (nt % 2) + nt / 2 + Nt * blk), b = (int)(Nrow * (nt % 4) + nt / 4 + Nt * blk);
+  int            e;
+  if (Nnull && nt >= Nt - Nnull && (nt & 1))
+    e = a - (int)Nrow;
+  else if (Nnull && nt >= Nt - Nnull)
+    e = a - (int)Nrow + (int)Nnull / 2;
+  else if (Nnull && (nt % 4) >= 2)
+    e = b - (int)Nnull / 2;
+  else
+    e = b;
+  const uint32_t ee = (uint32_t)e, oo = (ee + Nt / 2) % Nt + Nt * blk;
+  p0 = (ee % Nt) < Nt / 2 ? ee : ee + Ng - Nt / 2;
+  p1 = (oo % Nt) < Nt / 2 ? oo : oo + Ng - Nt / 2;
+}
+inline void set_prb(ltephy_grant_t& g, int slot, uint32_t prb) { g.prb_mask[slot][prb >> 5] |= 1u << (prb & 31); }
+inline bool user_rnti(uint16_t r) { return r >= CRNTI_START && r <= CRNTI_END; }
+} // namespace
+
+extern "C" {
+
+int ltephy_dci_to_grant(const ltephy_search_t* s, const ltephy_dci_t* d, uint32_t sf_idx, uint32_t cfi, int use_256qam_table, ltephy_grant_t* g,
+                        ltephy_dci_fields_t* fields)
+{
+  if (!s || !d || !g || cfi < 1 || cfi > 3 || sf_idx > 9) return LTEPHY_ERROR_INVALID_INPUTS;
+  const ltehost::Cell& c = s->cell;
+  const uint32_t       N = c.nof_prb, P = rbg_size(N), nrbg = (N + P - 1) / P, hdr = N > 10, rivb = clog2(N * (N + 1) / 2);
+  memset(g, 0, sizeof(*g));
+  ltephy_dci_fields_t f{};
+  Bits                b{d->bits};
+  f.format = d->format, f.rnti = d->rnti;
+  uint32_t alloc = 0, rbg_mask = 0, t1_subset = 0, t1_shift = 0, t1_mask = 0, riv = 0;
+  bool     dist = false, ngap2 = false;
+  uint32_t n_prb1a = 2;
+  bool     tb_en[2] = {false, false};
+  switch (d->format) {
+    case ltehost::F1A:
+      if (b.get(1) != 1) return LTEPHY_ERROR;
+      alloc = 2;
+      dist  = b.get(1);
+      if (dist && N >= 50) {
+        ngap2 = b.get(1);
+        riv   = b.get(rivb - 1);
+      } else
+        riv = b.get(rivb);
+      f.mcs[0] = (uint8_t)b.get(5), f.harq_pid = (uint8_t)b.get(3), f.ndi[0] = (uint8_t)b.get(1), f.rv[0] = (uint8_t)b.get(2);
+      {
+        const uint32_t t = b.get(2);
+        if (user_rnti(d->rnti))
+          f.tpc = (uint8_t)t;
+        else
+          n_prb1a = (t & 1) ? 3 : 2;
+      }
+      tb_en[0] = true;
+      break;
+    case ltehost::F1C:
+      alloc = 2, dist = true;
+      if (N >= 50) ngap2 = b.get(1);
+      {
+        const uint32_t nv = nvrb(N, false) / (N < 50 ? 2 : 4);
+        riv               = b.get(clog2(nv * (nv + 1) / 2));
+      }
+      f.mcs[0] = (uint8_t)b.get(5);
+      tb_en[0] = true;
+      break;
+    case ltehost::F1:
+    case ltehost::F2:
+    case ltehost::F2A:
+      alloc = hdr ? b.get(1) : 0;
+      if (alloc == 0)
+        rbg_mask = b.get(nrbg);
+      else {
+        const uint32_t sb = clog2(P);
+        t1_subset = b.get(sb), t1_shift = b.get(1), t1_mask = b.get(nrbg - sb - 1);
+      }
+      if (d->format == ltehost::F1) {
+        f.mcs[0] = (uint8_t)b.get(5), f.harq_pid = (uint8_t)b.get(3), f.ndi[0] = (uint8_t)b.get(1), f.rv[0] = (uint8_t)b.get(2), f.tpc = (uint8_t)b.get(2);
+        tb_en[0] = true;
+      } else {
+        f.tpc = (uint8_t)b.get(2), f.harq_pid = (uint8_t)b.get(3), f.tb_cw_swap = (uint8_t)b.get(1);
+        for (int i = 0; i < 2; i++) {
+          f.mcs[i] = (uint8_t)b.get(5), f.ndi[i] = (uint8_t)b.get(1), f.rv[i] = (uint8_t)b.get(2);
+          tb_en[i] = !(f.mcs[i] == 0 && f.rv[i] == 1);
+        }
+        if (d->format == ltehost::F2) f.pinfo = (uint8_t)b.get(c.nof_ports == 2 ? 3 : c.nof_ports == 4 ? 6 : 0);
+        if (d->format == ltehost::F2A && c.nof_ports == 4) f.pinfo = (uint8_t)b.get(2);
+      }
+      break;
+    default: return LTEPHY_ERROR; // format 0 is an uplink grant; 1B/1D/2B are rejected by dl_sniffer_config_mimo_type
+  }
+  f.alloc_type = (uint8_t)alloc;
+  // ---- PRB allocation (srsran_ra_dl_grant_to_grant_prb_allocation) ----
+  uint32_t nof_prb = 0;
+  if (alloc == 0) {
+    for (uint32_t i = 0; i < nrbg; i++)
+      if (rbg_mask & (1u << (nrbg - 1 - i)))
+        for (uint32_t j = i * P; j < (i + 1) * P && j < N; j++) set_prb(*g, 0, j), set_prb(*g, 1, j), nof_prb++;
+  } else if (alloc == 1) {
+    const uint32_t sb = clog2(P), nb = nrbg - sb - 1, q = (N - 1) / (P * P), pm = ((N - 1) / P) % P;
+    const uint32_t nsub  = t1_subset < pm ? q * P + P : t1_subset == pm ? q * P + (N - 1) % P + 1 : q * P;
+    const uint32_t shift = t1_shift ? nsub - nb : 0;
+    for (uint32_t i = 0; i < nb; i++)
+      if (t1_mask & (1u << (nb - 1 - i))) {
+        const uint32_t v = ((i + shift) / P) * P * P + t1_subset * P + (i + shift) % P;
+        if (v >= N) return LTEPHY_ERROR;
+        set_prb(*g, 0, v), set_prb(*g, 1, v), nof_prb++;
+      }
+  } else {
+    uint32_t L, S;
+    if (d->format == ltehost::F1C) {
+      const uint32_t step = N < 50 ? 2 : 4;
+      riv_decode(riv, nvrb(N, ngap2) / step, L, S);
+      L *= step, S *= step;
+    } else if (dist)
+      riv_decode(riv, nvrb(N, ngap2), L, S);
+    else
+      riv_decode(riv, N, L, S);
+    {
+      const uint32_t lim = dist ? nvrb(N, ngap2) : N; // an out-of-range RIV decodes to nonsense: reject it
+      if (L < 1 || L > lim || S >= lim || S + L > lim) return LTEPHY_ERROR;
+    }
+    if (!dist) {
+      for (uint32_t j = S; j < S + L; j++) set_prb(*g, 0, j), set_prb(*g, 1, j);
+    } else {
+      for (uint32_t v = S; v < S + L; v++) {
+        uint32_t p0, p1;
+        dvrb(N, ngap2, v, p0, p1);
+        if (p0 >= N || p1 >= N) return LTEPHY_ERROR;
+        set_prb(*g, 0, p0), set_prb(*g, 1, p1);
+      }
+    }
+    nof_prb = L;
+  }
+  if (!nof_prb) return LTEPHY_ERROR;
+  f.nof_prb = nof_prb;
+  // ---- transport blocks (dl_sniffer_compute_tb, dl_sniffer_pdsch.c:14-92) ----
+  bool alt = use_256qam_table != 0;
+  if (d->format == ltehost::F1A || !user_rnti(d->rnti)) alt = false;
+  for (int i = 0; i < 2; i++) {
+    g->tb[i].rv = f.rv[i];
+    if ((tb_en[i] && d->format >= ltehost::F2) || (d->format < ltehost::F2 && i == 0)) g->tb[i].enabled = 1, g->nof_tb++;
+  }
+  if (!user_rnti(d->rnti)) {
+    int tbs;
+    if (d->format == ltehost::F1A)
+      tbs = f.mcs[0] < LTE_TBS_NOF_ITBS ? lte_tbs_table[f.mcs[0]][n_prb1a - 1] : -1;
+    else if (d->format == ltehost::F1C)
+      tbs = lte_tbs_format1c[f.mcs[0] & 31];
+    else
+      return LTEPHY_ERROR;
+    if (tbs < 0) return LTEPHY_ERROR;
+    g->tb[0].qm = 2, g->tb[0].tbs = tbs;
+  } else {
+    for (int i = 0; i < 2; i++) {
+      if (!g->tb[i].enabled) continue;
+      const int itbs = alt ? lte_dl_mcs_itbs_alt[f.mcs[i]] : lte_dl_mcs_itbs[f.mcs[i]];
+      g->tb[i].qm    = (uint8_t)(alt ? lte_dl_mcs_qm_alt[f.mcs[i]] : lte_dl_mcs_qm[f.mcs[i]]);
+      g->tb[i].tbs   = itbs >= 0 ? lte_tbs_table[itbs][nof_prb - 1] : 0;
+    }
+  }
+  // ---- nof_re (srsran_ra_dl_compute_nof_re) ----
+  uint16_t kk[12];
+  for (uint32_t l = 0; l < 14; l++)
+    for (uint32_t prb = 0; prb < N; prb++)
+      if ((g->prb_mask[l / 7][prb >> 5] >> (prb & 31)) & 1u) g->nof_re += ltehost::pdsch_re_in_prb(c, sf_idx, cfi, l, prb, kk);
+  if (d->format == ltehost::F1C && (d->rnti <= RARNTI_END || d->rnti == PRNTI))
+    for (int i = 0; i < 2; i++) g->tb[i].rv = 0;
+  // ---- MIMO (dl_sniffer_config_mimo, dl_sniffer_pdsch.c:134-276) ----
+  switch (d->format) {
+    case ltehost::F2: g->tx_scheme = (g->nof_tb == 1 && f.pinfo == 0) ? LTEPHY_TX_DIVERSITY : LTEPHY_TX_SPATIALMUX; break;
+    case ltehost::F2A: g->tx_scheme = (g->nof_tb == 1 && f.pinfo == 0) ? LTEPHY_TX_DIVERSITY : LTEPHY_TX_CDD; break;
+    default: g->tx_scheme = c.nof_ports == 1 ? LTEPHY_TX_PORT0 : LTEPHY_TX_DIVERSITY; break;
+  }
+  if (g->tx_scheme == LTEPHY_TX_SPATIALMUX) {
+    if (g->nof_tb == 1) {
+      if (!(f.pinfo > 0 && f.pinfo < 5)) return LTEPHY_MIMO_PMI_WRONG;
+    } else if (f.pinfo >= 2)
+      return LTEPHY_MIMO_PMI_WRONG;
+  }
+  if ((g->tx_scheme == LTEPHY_TX_PORT0 || g->tx_scheme == LTEPHY_TX_DIVERSITY) && g->nof_tb != 1) return LTEPHY_MIMO_LAYER_WRONG;
+  if (g->tx_scheme == LTEPHY_TX_CDD && g->nof_tb != 2) return LTEPHY_MIMO_LAYER_WRONG;
+  g->rnti = d->rnti, g->sf = d->sf;
+  if (fields) *fields = f;
+  return LTEPHY_SUCCESS;
+}
+
+// ===================================================================================================
+ltephy_search_t* ltephy_search_create_cell(uint32_t nof_prb, uint32_t nof_ports, uint32_t cell_id, uint32_t nof_rx, uint32_t histogram_threshold)
+{
+  ltehost::CtrlMap cm;
+  ltehost::Cell    cell{nof_prb, nof_ports, cell_id, nof_rx};
+  if (!ltehost::build_ctrl_map(cell, cm)) return nullptr;
+  ltephy_search* s = new ltephy_search();
+  s->cell          = cell;
+  s->st = ltehost::dci_size_table(s->cell);
+  for (uint32_t cfi = 1; cfi <= 3; cfi++) s->nof_cce[cfi - 1] = cm.nof_cce[cfi - 1];
+  s->rm.threshold = histogram_threshold;
+  for (int i = 0; i < NF; i++) s->all[i] = {(uint8_t)i, 0};
+  s->update_formats();
+  // evergreen / forbidden ranges exactly as LTESniffer_Core.cc:398-417 seeds them after the MIB
+  for (int f : {(int)ltehost::F1A, (int)ltehost::F1C}) {
+    s->rm.evergreen[f].push_back({RARNTI_START, RARNTI_END});
+    s->rm.evergreen[f].push_back({PRNTI, 0xFFFF});
+  }
+  for (int f = 0; f < NF; f++) s->rm.forbidden[f].push_back({0, 0});
+  return s;
+}
+ltephy_search_t* ltephy_search_create(const ltephy_t* h, uint32_t histogram_threshold)
+{
+  if (!h) return nullptr;
+  uint32_t a, b, c, d;
+  ltephy_cell_of(h, &a, &b, &c, &d);
+  return ltephy_search_create_cell(a, b, c, d, histogram_threshold);
+}
+void ltephy_search_destroy(ltephy_search_t* s) { delete s; }
+void ltephy_search_config(ltephy_search_t* s, int shortcut, int skip_secondary, uint32_t update_interval)
+{
+  s->shortcut = shortcut != 0, s->skip_secondary = skip_secondary != 0, s->update_interval = update_interval;
+}
+void ltephy_search_add_evergreen(ltephy_search_t* s, uint16_t a, uint16_t b, uint32_t f)
+{
+  if (f < NF) s->rm.evergreen[f].push_back({a, b});
+}
+void ltephy_search_add_forbidden(ltephy_search_t* s, uint16_t a, uint16_t b, uint32_t f)
+{
+  if (f < NF) s->rm.forbidden[f].push_back({a, b});
+}
+void ltephy_search_activate(ltephy_search_t* s, uint16_t rnti, uint32_t format_idx, int reason) { s->rm.activate_and_refresh(rnti, format_idx, (uint8_t)reason); }
+int  ltephy_search_subframe(ltephy_search_t* s, const ltephy_sf_info_t* info, const ltephy_cand_t* cands, uint32_t sf_in_batch, ltephy_dci_t* out,
+                            uint32_t max_out, uint32_t* n_out)
+{
+  if (!s || !info || !cands) return LTEPHY_ERROR_INVALID_INPUTS;
+  return s->search_subframe(*info, cands, sf_in_batch, out, max_out, n_out);
+}
+void ltephy_search_get_stats(const ltephy_search_t* s, ltephy_search_stats_t* st) { *st = s->stats; }
+uint32_t ltephy_search_validate_location(uint32_t nof_cce, uint32_t ncce, uint32_t L, uint32_t sf_idx, uint16_t rnti)
+{
+  return validate_location(nof_cce, ncce, L, sf_idx, rnti);
+}
+// thin test hooks onto the RNTI history (parity with the reference's rnti_manager_* C wrappers)
+int      ltephy_search_rnti_validate_and_refresh(ltephy_search_t* s, uint16_t r, uint32_t f) { return s->rm.validate_and_refresh(r, f); }
+void     ltephy_search_rnti_add_candidate(ltephy_search_t* s, uint16_t r, uint32_t f) { s->rm.add_candidate(r, f); }
+void     ltephy_search_rnti_step_time(ltephy_search_t* s) { s->rm.step_time(); }
+uint32_t ltephy_search_rnti_frequency(const ltephy_search_t* s, uint16_t r, uint32_t f) { return s->rm.freq(r, f); }
+uint32_t ltephy_search_rnti_assoc_format(const ltephy_search_t* s, uint16_t r) { return s->rm.assoc[r]; }
+int      ltephy_search_rnti_reason(const ltephy_search_t* s, uint16_t r) { return s->rm.reason[r]; }
+int      ltephy_search_rnti_is_forbidden(const ltephy_search_t* s, uint16_t r, uint32_t f) { return s->rm.is_forbidden(r, f); }
+int      ltephy_search_rnti_is_evergreen(const ltephy_search_t* s, uint16_t r, uint32_t f) { return s->rm.is_evergreen(r, f); }
+
+// ===================================================================================================
+// One call = what SubframeWorker::work does for every subframe of the batch (src/src/SubframeWorker.cc:142-207):
+// phase A on the GPU, FALCON search on the host in subframe order, phase B on the GPU for the DL grants.
+int ltephy_decode_subframes(ltephy_t* h, ltephy_search_t* s, const float* iq, const uint32_t* tti, uint32_t n, uint64_t seq, ltephy_sf_info_t* info,
+                            ltephy_cand_t* cand_scratch, ltephy_dci_t* dcis, uint32_t max_dcis, uint32_t* n_dcis, ltephy_tb_result_t* tbs,
+                            uint8_t* payload, size_t payload_cap)
+{
+  if (!h || !s || !iq || !tti || !info || !cand_scratch || !dcis || !n_dcis || !tbs) return LTEPHY_ERROR_INVALID_INPUTS;
+  int r = ltephy_submit_iq(h, iq, tti, n);
+  if (r) return r;
+  r = ltephy_get_phase_a(h, info, cand_scratch);
+  if (r) return r;
+  uint32_t                    nd = 0;
+  std::vector<ltephy_grant_t> grants;
+  std::vector<uint32_t>       grant_dci;
+  {
+    std::unique_lock<std::mutex> lk(s->mtx);
+    s->cv.wait(lk, [&] { return s->next_seq == seq || seq == LTEPHY_SEQ_NONE; });
+    for (uint32_t i = 0; i < n; i++) {
+      uint32_t k = 0;
+      r          = s->search_subframe(info[i], cand_scratch + (size_t)i * LTEPHY_MAX_LOC * LTEPHY_MAX_SIZES, i, dcis + nd, max_dcis - nd, &k);
+      if (r < 0) break;
+      nd += std::min(k, max_dcis - nd);
+    }
+    if (seq != LTEPHY_SEQ_NONE) s->next_seq = seq + 1;
+    lk.unlock();
+    s->cv.notify_all();
+  }
+  if (r < 0) return r;
+  *n_dcis = nd;
+  grants.reserve(nd);
+  for (uint32_t i = 0; i < nd; i++) {
+    tbs[2 * i] = tbs[2 * i + 1] = ltephy_tb_result_t{};
+    const ltephy_dci_t& d       = dcis[i];
+    if (d.format == ltehost::F0 || d.rnti == 0) continue;
+    ltephy_grant_t g;
+    if (ltephy_dci_to_grant(s, &d, info[d.sf].tti % 10, info[d.sf].cfi, 0, &g, nullptr) != LTEPHY_SUCCESS) continue;
+    // skip rule of decode_dl_mode (src/src/DL_Sniffer_PDSCH.cc:887-889)
+    if (!(g.tb[0].tbs > 0 && !(s->cell.nof_rx == 1 && g.nof_tb == 2))) continue;
+    if (g.tx_scheme == LTEPHY_TX_SPATIALMUX) continue; // not implemented yet
+    grants.push_back(g);
+    grant_dci.push_back(i);
+  }
+  r = ltephy_submit_grants(h, grants.data(), (uint32_t)grants.size());
+  if (r) return r;
+  std::vector<ltephy_tb_result_t> res(2 * grants.size() + 2);
+  r = ltephy_get_phase_b(h, res.data(), payload, payload_cap);
+  if (r) return r;
+  for (size_t gi = 0; gi < grants.size(); gi++) {
+    tbs[2 * grant_dci[gi]]     = res[2 * gi];
+    tbs[2 * grant_dci[gi] + 1] = res[2 * gi + 1];
+  }
+  return LTEPHY_SUCCESS;
+}
+
+} // extern "C"

@@ -2,6 +2,7 @@
 // caches, job construction for phase A / phase B and kernel launches on one CUDA stream.
 // There is no CPU fallback: creation fails when no CUDA device can be used.
 #include "../../include/ltephy_b200.h"
+#include "../../include/ltephy_search.h"
 #include "dev_common.cuh"
 #include "lte_host.hpp"
 #include <cmath>
@@ -314,6 +315,10 @@ extern "C" uint32_t ltephy_locations(const ltephy_t* h, uint32_t cfi, uint16_t* 
   uint32_t n = (uint32_t)std::min<size_t>(v.size(), max);
   for (uint32_t i = 0; i < n; i++) ncce[i] = v[i].ncce, L[i] = v[i].L;
   return n;
+}
+extern "C" void ltephy_cell_of(const ltephy_t* h, uint32_t* a, uint32_t* b, uint32_t* c, uint32_t* d)
+{
+  *a = h->cell.nof_prb, *b = h->cell.nof_ports, *c = h->cell.cell_id, *d = h->cell.nof_rx;
 }
 extern "C" uint64_t ltephy_launch_count(const ltephy_t* h) { return h->launches; }
 extern "C" int      ltephy_last_timing(ltephy_t* h, float ms[4])

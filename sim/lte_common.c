@@ -667,11 +667,13 @@ static int ra_to_prb_mask(const lte_cell_t* c, const lte_dci_t* d, lte_dl_grant_
       riv_decode(d->riv, nvrb_gap(N, d->t2_ngap2), &L, &S);
     } else
       riv_decode(d->riv, N, &L, &S);
+    {
+      uint32_t lim = d->t2_dist ? nvrb_gap(N, d->t2_ngap2) : N; /* an out-of-range RIV decodes to nonsense: reject it */
+      if (L < 1 || L > lim || S >= lim || S + L > lim) return -1;
+    }
     if (!d->t2_dist) {
-      if (S + L > N) return -1;
       for (uint32_t j = S; j < S + L; j++) g->prb_mask[0][j] = g->prb_mask[1][j] = 1;
     } else {
-      if (S + L > nvrb_gap(N, d->t2_ngap2)) return -1;
       for (uint32_t v = S; v < S + L; v++) {
         uint32_t p0, p1;
         dvrb_to_prb(N, d->t2_ngap2, v, &p0, &p1);

@@ -271,3 +271,100 @@ def unpack_and_grant(cell, fmt, rnti, bits, sf_idx, cfi, alt=0):
     g = DlGrant()
     r = sim().lte_dl_dci_to_grant(C.byref(cell), sf_idx, cfi, alt, C.byref(d), C.byref(g))
     return r, d, g
+
+
+# ------------------------------------------------------------------------------------------------
+# oracle/_ref: the reference's own RNTIManager + the oracle walk that uses it
+class WalkDci(C.Structure):
+    _fields_ = [("rnti", C.c_uint16), ("format", C.c_uint8), ("L", C.c_uint8), ("ncce", C.c_uint16), ("nof_bits", C.c_uint16),
+                ("bits", C.c_uint8 * DCI_MAX_BITS), ("histval", C.c_uint32)]
+
+
+class WalkStats(C.Structure):
+    _fields_ = [("nof_decoded_locations", C.c_uint32), ("nof_cce", C.c_uint32), ("nof_missed_cce", C.c_uint32), ("nof_subframes", C.c_uint32),
+                ("nof_locations", C.c_uint32)]
+
+
+_walk = None
+_rm = None
+
+
+def build_ref():
+    if os.path.isdir("/root/reference"):
+        subprocess.run(["bash", os.path.join(ROOT, "oracle", "build_ref.sh")], check=True, stdout=subprocess.DEVNULL)
+
+
+def ref_available():
+    return os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libfalcon_walk.so"))
+
+
+def walklib():
+    global _walk
+    if _walk is None:
+        build_infra()
+        build_ref()
+        C.CDLL(os.path.join(ROOT, "oracle", "liblteoracle.so"), mode=C.RTLD_GLOBAL)
+        L = C.CDLL(os.path.join(ROOT, "oracle", "_ref", "libfalcon_walk.so"))
+        P = C.c_void_p
+        L.lteo_walk_create.argtypes = [C.POINTER(Cell), C.c_uint32]
+        L.lteo_walk_create.restype = P
+        L.lteo_walk_destroy.argtypes = [P]
+        L.lteo_walk_config.argtypes = [P, C.c_int, C.c_int, C.c_uint32]
+        L.lteo_walk_subframe.argtypes = [P, C.c_uint32, C.c_uint32, C.c_uint32, P, C.c_float, P, C.c_uint32, P]
+        L.lteo_walk_stats.argtypes = [P, P]
+        L.lteo_walk_activate.argtypes = [P, C.c_uint16, C.c_uint32, C.c_int]
+        _walk = L
+    return _walk
+
+
+def rntimgr_ref():
+    """the reference's RNTIManager through its own C wrappers (lib/include/falcon/util/rnti_manager_c.h)"""
+    global _rm
+    if _rm is None:
+        build_ref()
+        L = C.CDLL(os.path.join(ROOT, "oracle", "_ref", "librntimgr_ref.so"))
+        P = C.c_void_p
+        L.rnti_manager_create.argtypes = [C.c_uint32] * 3
+        L.rnti_manager_create.restype = P
+        L.rnti_manager_free.argtypes = [P]
+        for f in ("rnti_manager_add_evergreen", "rnti_manager_add_forbidden"):
+            getattr(L, f).argtypes = [P, C.c_uint16, C.c_uint16, C.c_uint32]
+        L.rnti_manager_add_candidate.argtypes = [P, C.c_uint16, C.c_uint32]
+        for f in ("rnti_manager_validate_and_refresh", "rnti_manager_is_evergreen", "rnti_manager_is_forbidden"):
+            getattr(L, f).argtypes = [P, C.c_uint16, C.c_uint32]
+        L.rnti_manager_activate_and_refresh.argtypes = [P, C.c_uint16, C.c_uint32, C.c_int]
+        L.rnti_manager_step_time.argtypes = [P]
+        L.rnti_manager_getFrequency.argtypes = [P, C.c_uint16, C.c_uint32]
+        L.rnti_manager_getFrequency.restype = C.c_uint32
+        L.rnti_manager_get_associated_format_idx.argtypes = [P, C.c_uint16]
+        L.rnti_manager_get_associated_format_idx.restype = C.c_uint32
+        L.rnti_manager_get_activation_reason.argtypes = [P, C.c_uint16]
+        _rm = L
+    return _rm
+
+
+class OracleWalk:
+    def __init__(self, cell, threshold=5):
+        self.L = walklib()
+        self.h = self.L.lteo_walk_create(C.byref(cell), threshold)
+
+    def config(self, shortcut=1, skip_secondary=0, update_interval=500):
+        self.L.lteo_walk_config(self.h, shortcut, skip_secondary, update_interval)
+
+    def subframe(self, sf_idx, cfi, nof_cce, llr, snr_db):
+        out = (WalkDci * 64)()
+        n = C.c_uint32(0)
+        llr = np.ascontiguousarray(llr, np.float32)
+        self.L.lteo_walk_subframe(self.h, sf_idx, cfi, nof_cce, ptr(llr), snr_db, out, 64, C.byref(n))
+        return [out[i] for i in range(n.value)]
+
+    def stats(self):
+        s = WalkStats()
+        self.L.lteo_walk_stats(self.h, C.byref(s))
+        return s
+
+    def __del__(self):
+        try:
+            self.L.lteo_walk_destroy(self.h)
+        except Exception:
+            pass

@@ -1,0 +1,107 @@
+"""CPU tests of the test infrastructure itself: synthetic eNB -> oracle receiver loop (ground truth is
+CRC-self-validating), DCI size known answers, segmentation/rate-matching properties."""
+import ctypes as C
+import numpy as np
+import pytest
+import ltelib
+from ltelib import Cell, Sim, Oracle, FORMATS
+
+
+def test_dci_sizes_known_answers(infra):
+    S = infra.sim()
+    c = Cell(100, 2, 0, 1)   # 0/1A 28, 1 39, 1B 30, 1C 15, 1D 30, 2 51, 2A 48
+    assert [S.lte_dci_sizeof(C.byref(c), f) for f in range(9)] == [28, 39, 28, 30, 15, 30, 51, 48, 48]
+    c = Cell(50, 2, 0, 1)
+    assert [S.lte_dci_sizeof(C.byref(c), f) for f in (0, 1, 2, 4, 6, 7)] == [27, 31, 27, 13, 43, 41]
+    c = Cell(25, 1, 0, 1)
+    assert [S.lte_dci_sizeof(C.byref(c), f) for f in (0, 1, 2, 4)] == [25, 27, 25, 12]
+
+
+def test_control_region_sizes(infra):
+    o = Oracle(Cell(100, 2, 1, 1))
+    assert [infra.oracle().lteo_nof_cce(o.h, cfi) for cfi in (1, 2, 3)] == [20, 54, 87]
+
+
+@pytest.mark.parametrize("tbs,rv,qm", [(40, 0, 2), (2216, 0, 4), (6200, 2, 6), (36696, 0, 6), (75376, 0, 6), (75376, 1, 6), (97896, 0, 8)])
+def test_dlsch_encode_decode_roundtrip(infra, tbs, rv, qm):
+    """encode -> (noise free) soft bits -> rate-dematch + turbo -> CRC ok and identical bytes"""
+    S, O = infra.sim(), infra.oracle()
+    rng = np.random.default_rng(tbs + rv)
+    pl = rng.integers(0, 256, tbs // 8).astype(np.uint8)
+    G = int((tbs + 24) * (1.6 if rv == 0 else 2.4)) // (2 * qm) * 2 * qm
+    e = np.zeros(G, np.uint8)
+    assert S.lte_sim_dlsch_encode(ltelib.ptr(pl), tbs, rv, G, qm, 1, ltelib.ptr(e)) == 0
+    llr = ((2 * e.astype(np.int16) - 1) * 120).astype(np.int16)
+    out = np.zeros(tbs // 8 + 8, np.uint8)
+    it = np.zeros(32, np.uint32)
+    assert O.lteo_dlsch_decode(ltelib.ptr(llr), G, tbs, rv, qm, 1, 4, 1, ltelib.ptr(out), ltelib.ptr(it)) == 1
+    assert np.array_equal(out[:tbs // 8], pl)
+    # erase 15 % of the soft bits: still decodable (encode -> erase -> decode property)
+    llr2 = llr.copy()
+    llr2[rng.random(G) < 0.15] = 0
+    assert O.lteo_dlsch_decode(ltelib.ptr(llr2), G, tbs, rv, qm, 1, 8, 1, ltelib.ptr(out), ltelib.ptr(it)) == 1
+    assert np.array_equal(out[:tbs // 8], pl)
+
+
+def test_pdcch_encode_decode_all_formats(infra):
+    S = infra.sim()
+    cell = Cell(100, 2, 5, 1)
+    o = Oracle(cell)
+    rng = np.random.default_rng(1)
+    for f in range(9):
+        nb = S.lte_dci_sizeof(C.byref(cell), f)
+        for L in range(4):
+            if 3 * (nb + 16) > (72 << L) * 3:
+                continue
+            b = rng.integers(0, 2, nb).astype(np.uint8)
+            rnti = int(rng.integers(1, 65535))
+            e = np.zeros(72 << L, np.uint8)
+            S.lte_sim_pdcch_encode(ltelib.ptr(b), nb, rnti, L, ltelib.ptr(e))
+            llr = (2.0 * e - 1.0 + 0.25 * rng.standard_normal(72 << L)).astype(np.float32)
+            if nb + 16 > 0.9 * (72 << L):
+                continue
+            r, bits, crc = o.dci_decode(llr, nb)
+            assert r == 0 and crc == rnti and np.array_equal(bits, b), (FORMATS[f], L)
+    # all-zero input is not decoded (falcon_pdcch.c:141: mean > 0)
+    assert o.dci_decode(np.zeros(72, np.float32), 28)[0] == -1
+
+
+CAPS = {
+    "cfg1_10sf_1rnti_tm1_qpsk": (Cell(100, 1, 1, 1), 10, dict(seed=1, cfi=2, nof_ues=1, tm=1, mcs_min=5, mcs_max=5, snr_db=30.0, fixed_L=2, si_period=5)),
+    "tm3_2x2_64qam": (Cell(100, 2, 7, 2), 2, dict(seed=2, cfi=3, nof_ues=150, dl_min=8, dl_max=12, tm=3, mcs_min=17, mcs_max=24, snr_db=28.0, full_band=1)),
+    "mix_50prb_delay": (Cell(50, 2, 301, 2), 3, dict(seed=3, cfi=3, nof_ues=20, dl_min=3, dl_max=5, ul_min=1, ul_max=2, tm=13, mcs_min=0, mcs_max=20, snr_db=22.0, chan_delay=6)),
+    "sf0_sf5_sync_re_exclusion_25prb": (Cell(25, 2, 77, 1), 6, dict(seed=4, cfi=2, nof_ues=3, dl_min=1, dl_max=2, tm=1, mcs_min=4, mcs_max=10, snr_db=26.0, full_band=1)),
+}
+
+
+@pytest.mark.parametrize("name", list(CAPS))
+def test_sim_to_oracle_ground_truth(infra, name):
+    """every transmitted DCI and transport block is recovered by the oracle receiver"""
+    cell, n, kw = CAPS[name]
+    s, o = Sim(cell=cell, **kw), Oracle(cell)
+    ndci = ntb = 0
+    for tti in range(n):
+        iq, tr, pl = s.subframe(tti)
+        sym = o.ofdm(iq)
+        ce, res = o.chest(tti % 10, sym)
+        cfi, _ = o.pcfich(tti % 10, sym, ce)
+        assert cfi == tr.cfi
+        assert abs(res.snr_db - kw["snr_db"]) < 6.0
+        llr = o.pdcch_llr(tti % 10, cfi, sym, ce)
+        for i in range(tr.nof_dci):
+            d = tr.dci[i]
+            r, bits, crc = o.dci_decode(llr[72 * d.ncce:72 * d.ncce + (72 << d.L)], d.nbits)
+            assert r == 0 and crc == d.rnti and np.array_equal(bits, np.frombuffer(bytes(d.bits), np.uint8)[:d.nbits])
+            ndci += 1
+            if d.nof_tb == 0:
+                continue
+            r, dd, g = ltelib.unpack_and_grant(cell, d.format, crc, bits, tti % 10, cfi)
+            assert r == 0 and g.nof_re == d.nof_re
+            r, pay, ok = o.pdsch_decode(tti % 10, cfi, crc, g, sym, ce, 8)
+            assert r == 0
+            for t in range(2):
+                if g.tb[t].enabled:
+                    nby = g.tb[t].tbs // 8
+                    assert ok[t] and np.array_equal(pay[t][:nby], pl[d.payload_off[t]:d.payload_off[t] + nby]), (name, tti, hex(d.rnti), t)
+                    ntb += 1
+    assert ndci >= n and ntb >= 1

@@ -1,0 +1,151 @@
+"""Host search (product, table-driven) against the oracle walk (lazy decodes + the reference's own
+RNTIManager) on the same captures; search-space validation and DCI->grant against the oracle's versions."""
+import ctypes as C
+import numpy as np
+import pytest
+import ltelib
+from ltelib import Cell, Sim, Oracle, OracleWalk, FORMATS
+from ltesniffer_b200 import capi
+
+needs_ref = pytest.mark.skipif(not (ltelib.ref_available() or __import__("os").path.isdir("/root/reference")), reason="oracle/_ref not built")
+
+
+def oracle_table(o, phy_sizes, nc, Ls, llr):
+    """the candidate table exactly as the Viterbi kernel defines it, built with the CPU oracle"""
+    sizes, sidx = phy_sizes
+    T = np.zeros((capi.MAX_LOC, capi.MAX_SIZES), capi.CAND_DTYPE)
+    distinct = {sidx[f]: sizes[f] for f in range(9)}
+    for li in range(len(nc)):
+        e = llr[72 * int(nc[li]):72 * int(nc[li]) + (72 << int(Ls[li]))]
+        for si, nb in distinct.items():
+            r, bits, crc = o.dci_decode(e, nb)
+            if r == 0:
+                v = 0
+                for i, b in enumerate(bits):
+                    v |= int(b) << (63 - i)
+                T[li, si] = (v, crc, 1, [0] * 5)
+    return T
+
+
+def host_geometry(cell):
+    """sizes / size index / locations from the sim's DCI size function (no GPU needed)"""
+    S = ltelib.sim()
+    sizes = [S.lte_dci_sizeof(C.byref(cell), f) for f in range(9)]
+    order = []
+    for s in sizes:
+        if s not in order:
+            order.append(s)
+    return sizes, [order.index(s) for s in sizes]
+
+
+def locations(nof_cce):
+    nc, Ls = [], []
+    lim = min(nof_cce, 84)
+    for l in (3, 2, 1, 0):
+        for i in range(lim // (1 << l)):
+            nc.append((1 << l) * i)
+            Ls.append(l)
+    return np.array(nc), np.array(Ls)
+
+
+def test_validate_location_matches_list_based_version(infra):
+    S, L = infra.sim(), capi.load_library()
+    capi._bind_search(L)
+    rng = np.random.default_rng(0)
+    for nof_cce in (20, 25, 54, 87, 41, 8, 3):
+        for _ in range(4000):
+            rnti = int(rng.choice([rng.integers(0, 65536), rng.integers(0, 12), rng.integers(0xFFF0, 0x10000)]))
+            l = int(rng.integers(0, 4))
+            ncce = int(rng.integers(0, max(1, nof_cce))) // (1 << l) * (1 << l)
+            sf = int(rng.integers(0, 10))
+            assert L.ltephy_search_validate_location(nof_cce, ncce, l, sf, rnti) == S.lte_pdcch_validate_location(nof_cce, ncce, l, sf, rnti), (nof_cce, ncce, l, sf, rnti)
+
+
+@needs_ref
+@pytest.mark.parametrize("name,cell,n,kw", [
+    ("tm1_shortcut", Cell(100, 1, 1, 1), 30, dict(seed=1, cfi=2, nof_ues=2, dl_min=1, dl_max=2, tm=1, mcs_min=5, mcs_max=5, snr_db=30.0, fixed_L=2, si_period=5)),
+    ("busy_tm3", Cell(50, 2, 7, 2), 60, dict(seed=2, cfi=3, nof_ues=12, dl_min=3, dl_max=5, ul_min=1, ul_max=2, tm=13, mcs_min=3, mcs_max=12, snr_db=26.0)),
+    ("low_snr_gate", Cell(25, 1, 9, 1), 6, dict(seed=3, cfi=2, nof_ues=2, dl_min=1, dl_max=1, tm=1, mcs_min=2, mcs_max=2, snr_db=3.0)),
+])
+def test_search_matches_oracle_walk(infra, name, cell, n, kw):
+    s, o = Sim(cell=cell, **kw), Oracle(cell)
+    walk = OracleWalk(cell)
+    srch = capi.Search(cell.nof_prb, cell.nof_ports, cell.cell_id, cell.nof_rx)
+    walk.config(1, 0, 10)
+    srch.config(1, 0, 10)
+    geo = host_geometry(cell)
+    found = set()
+    sent = set()
+    total = 0
+    for tti in range(n):
+        iq, tr, pl = s.subframe(tti)
+        sym = o.ofdm(iq)
+        ce, res = o.chest(tti % 10, sym)
+        cfi, corr = o.pcfich(tti % 10, sym, ce)
+        llr = o.pdcch_llr(tti % 10, cfi, sym, ce)
+        ncce = len(llr) // 72
+        ref = walk.subframe(tti % 10, cfi, ncce, llr, res.snr_db)
+        info = capi.SfInfo()
+        info.tti, info.cfi, info.nof_cce, info.snr_db = tti, cfi, ncce, res.snr_db
+        pw = np.zeros(ncce, np.float32)
+        ltelib.oracle().lteo_cce_power(ltelib.ptr(llr), ncce, ltelib.ptr(pw))
+        for i in range(ncce):
+            info.cce_power[i] = pw[i]
+        nc, Ls = locations(ncce)
+        T = oracle_table(o, geo, nc, Ls, llr) if res.snr_db > 6.0 else np.zeros((capi.MAX_LOC, capi.MAX_SIZES), capi.CAND_DTYPE)
+        got = srch.subframe(info, T)
+        assert len(got) == len(ref), (name, tti, len(got), len(ref))
+        for a, b in zip(got, ref):
+            assert (int(a["rnti"]), int(a["format"]), int(a["L"]), int(a["ncce"]), int(a["nof_bits"]), int(a["histogram_value"])) == \
+                   (b.rnti, b.format, b.L, b.ncce, b.nof_bits, b.histval), (name, tti)
+            assert np.array_equal(capi.cand_bits(a["bits"], b.nof_bits), np.frombuffer(bytes(b.bits), np.uint8)[:b.nof_bits])
+            found.add((tti, int(a["rnti"]), int(a["ncce"])))
+        total += len(got)
+        for i in range(tr.nof_dci):
+            sent.add((tti, tr.dci[i].rnti, tr.dci[i].ncce))
+    ws, ps = walk.stats(), srch.stats()
+    assert (ws.nof_decoded_locations, ws.nof_cce, ws.nof_missed_cce, ws.nof_subframes, ws.nof_locations) == \
+           (ps.nof_decoded_locations, ps.nof_cce, ps.nof_missed_cce, ps.nof_subframes, ps.nof_locations)
+    if name == "low_snr_gate":
+        assert total == 0
+    else:
+        late = {x for x in sent if x[0] >= n // 2}
+        assert len(late & found) >= 0.9 * len(late), "search finds %d of %d transmitted DCIs in the second half" % (len(late & found), len(late))
+
+
+def test_dci_to_grant_matches_oracle(infra):
+    """random valid DCIs of every decodable DL format: product ltephy_dci_to_grant == oracle lte_dl_dci_to_grant"""
+    S = infra.sim()
+    rng = np.random.default_rng(5)
+    ncheck = 0
+    for cell in (Cell(100, 2, 3, 2), Cell(50, 1, 9, 1), Cell(25, 2, 100, 2), Cell(75, 2, 5, 2)):
+        srch = capi.Search(cell.nof_prb, cell.nof_ports, cell.cell_id, cell.nof_rx)
+        for _ in range(1500):
+            f = int(rng.choice([1, 2, 4, 6, 7]))
+            nb = S.lte_dci_sizeof(C.byref(cell), f)
+            bits = rng.integers(0, 2, nb).astype(np.uint8)
+            if f == 2:
+                bits[0] = 1
+            rnti = int(rng.choice([rng.integers(11, 0xFFF3), 0xFFFF, 0xFFFE, rng.integers(1, 11)]))
+            sf_idx, cfi, alt = int(rng.integers(0, 10)), int(rng.integers(1, 4)), int(rng.integers(0, 2))
+            r0, d, g = ltelib.unpack_and_grant(cell, f, rnti, bits, sf_idx, cfi, alt)
+            v = 0
+            for i, b in enumerate(bits):
+                v |= int(b) << (63 - i)
+            row = np.zeros(1, capi.DCI_DTYPE)[0]
+            row["rnti"], row["format"], row["nof_bits"], row["bits"] = rnti, f, nb, v
+            r1, pg, fl = srch.dci_to_grant(row, sf_idx, cfi, alt)
+            assert (r0 == 0) == (r1 == 0), (cell.nof_prb, FORMATS[f], r0, r1, hex(rnti))
+            if r0 != 0:
+                continue
+            ncheck += 1
+            assert (pg.nof_re, pg.tx_scheme, pg.nof_tb) == (g.nof_re, g.tx_scheme, g.nof_tb)
+            for t in range(2):
+                assert (pg.tb[t].enabled, pg.tb[t].tbs if g.tb[t].enabled else 0, pg.tb[t].qm if g.tb[t].enabled else 0) == \
+                       (g.tb[t].enabled, g.tb[t].tbs if g.tb[t].enabled else 0, g.tb[t].qm if g.tb[t].enabled else 0)
+                if g.tb[t].enabled:
+                    assert pg.tb[t].rv == g.tb[t].rv
+            for sl in range(2):
+                for prb in range(cell.nof_prb):
+                    assert ((pg.prb_mask[sl][prb >> 5] >> (prb & 31)) & 1) == g.prb_mask[sl][prb]
+    assert ncheck > 2000

@@ -1,0 +1,40 @@
+"""3GPP table checks (CPU): structural validation of include/lte_tables.h plus the anchors that exist in
+the reference tree (row 32A, format-1C TBS table)."""
+import os
+import re
+import sys
+import numpy as np
+import pytest
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+import check_tables  # noqa: E402
+
+REF = "/root/reference"
+
+
+def test_tables_structurally_valid():
+    assert check_tables.check() == []
+
+
+def test_known_answers():
+    f1, f2, tbs, f1c = check_tables.load()
+    T = np.array(tbs).reshape(34, 110)
+    assert T[26, 99] == 75376 and T[33, 99] == 97896 and T[0, 0] == 16 and T[26, 0] == 712
+    assert check_tables.segm(75376)[:2] == (13, 5824) and check_tables.segm(97896)[:2] == (16, 6144) and check_tables.segm(36696)[:2] == (6, 6144)
+    assert (f1[0], f2[0]) == (3, 10) and (f1[187], f2[187]) == (263, 480)                      # K = 40, K = 6144
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="reference tree not mounted (GPU box)")
+def test_anchors_in_reference_tree():
+    _, _, tbs, f1c = check_tables.load()
+    T = np.array(tbs).reshape(34, 110)
+    src = open(os.path.join(REF, "lib/src/phy/falcon_phch/dl_sniffer_pdsch.c")).read()
+    m = re.search(r"dl_sniffer_tbs_format1c_table\[32\]\s*=\s*\{(.*?)\};", src, re.S)
+    assert [int(x) for x in re.findall(r"\d+", m.group(1))] == f1c
+    src = open(os.path.join(REF, "lib/src/phy/falcon_phch/ul_sniffer_pusch.c")).read()
+    m = re.search(r"tbs_table_32A\[110\]\s*=\s*(?:/\*.*?\*/)?\s*\{(.*?)\};", src, re.S)
+    row32a = np.array([int(x) for x in re.findall(r"\d+", m.group(1))])
+    assert len(row32a) == 110
+    # 32A lies between rows 32 and 33 of Table 7.1.7.2.1-1 and only uses transport block sizes of the table
+    assert np.all(row32a >= T[31]) and np.all(row32a[:100] <= T[33][:100])   # (32A keeps growing to 101840 above 100 PRB)
+    assert set(row32a.tolist()) <= set(T.ravel().tolist()) | {101840}
