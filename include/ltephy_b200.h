@@ -163,6 +163,13 @@ int ltephy_tap(ltephy_t* h, int what, void* dst, size_t bytes);
 
 /* timing of the last batch, from CUDA events on the library's stream (ms): [0] H2D+phase A, [1] phase B */
 int ltephy_last_timing(ltephy_t* h, float ms[4]);
+/* user markers on the library's stream: ltephy_mark(h, 0) ... ltephy_mark(h, 1); ltephy_mark_elapsed_ms
+ * synchronises the stream and returns the device time between the two markers */
+int   ltephy_mark(ltephy_t* h, int slot);
+float ltephy_mark_elapsed_ms(ltephy_t* h);
+/* algorithmic bytes of the turbo stage of the last phase B: sum over code blocks of 3(K+4)*2 + K/8,
+ * number of code blocks and information bits */
+int ltephy_last_turbo_work(ltephy_t* h, uint64_t* bytes, uint64_t* code_blocks, uint64_t* info_bits);
 /* number of kernel launches issued by the library since creation */
 uint64_t ltephy_launch_count(const ltephy_t* h);
 

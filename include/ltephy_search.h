@@ -95,6 +95,22 @@ int ltephy_decode_subframes(ltephy_t* h, ltephy_search_t* s, const float* iq, co
                             ltephy_cand_t* cand_scratch, ltephy_dci_t* dcis, uint32_t max_dcis, uint32_t* n_dcis, ltephy_tb_result_t* tbs,
                             uint8_t* payload, size_t payload_cap);
 
+/* same, with the IQ samples already resident in device memory (kernel-side throughput measurements) */
+int ltephy_decode_subframes_device(ltephy_t* h, ltephy_search_t* s, const void* iq_dev, const uint32_t* tti, uint32_t n, uint64_t seq,
+                                   ltephy_sf_info_t* info, ltephy_cand_t* cand_scratch, ltephy_dci_t* dcis, uint32_t max_dcis, uint32_t* n_dcis,
+                                   ltephy_tb_result_t* tbs, uint8_t* payload, size_t payload_cap);
+
+/* host wall time of the phases of the last decode call (ms): submit A, wait+fetch A, search, grants, submit B, wait+fetch B */
+void ltephy_last_host_timing(double* ms8);
+
+/* building blocks of the call above, exposed for sharded (multi-GPU) operation: every rank runs phase A on
+ * its subframes, candidate tables are all-gathered, each rank replays the walk over ALL subframes in order
+ * and keeps the grants of the subframes it owns (sf % mod == rem; grant.sf becomes sf / mod). */
+int ltephy_search_batch(ltephy_search_t* s, const ltephy_sf_info_t* info, const ltephy_cand_t* cands, uint32_t n, ltephy_dci_t* dcis, uint32_t max_dcis,
+                        uint32_t* n_dcis);
+int ltephy_grants_from_dcis(const ltephy_search_t* s, const ltephy_sf_info_t* info, const ltephy_dci_t* dcis, uint32_t nd, uint32_t mod, uint32_t rem,
+                            ltephy_grant_t* grants, uint32_t* grant_dci, uint32_t max_grants, uint32_t* n_grants);
+
 #ifdef __cplusplus
 }
 #endif

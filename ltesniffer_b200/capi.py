@@ -82,6 +82,10 @@ def load_library(build_if_missing=True):
     L.ltephy_turbo_batch.argtypes = [P, P, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, P, P, P]
     L.ltephy_tap.argtypes = [P, C.c_int, P, C.c_size_t]
     L.ltephy_last_timing.argtypes = [P, P]
+    L.ltephy_mark.argtypes = [P, C.c_int]
+    L.ltephy_mark_elapsed_ms.argtypes = [P]
+    L.ltephy_mark_elapsed_ms.restype = C.c_float
+    L.ltephy_last_turbo_work.argtypes = [P, P, P, P]
     L.ltephy_launch_count.argtypes = [P]
     L.ltephy_launch_count.restype = C.c_uint64
     _lib = L
@@ -197,6 +201,17 @@ class LtePhy:
         self.L.ltephy_last_timing(self.h, t)
         return list(t)
 
+    def mark(self, slot):
+        self._chk(self.L.ltephy_mark(self.h, slot), "mark")
+
+    def mark_elapsed_ms(self):
+        return float(self.L.ltephy_mark_elapsed_ms(self.h))
+
+    def turbo_work(self):
+        b, c, i = C.c_uint64(0), C.c_uint64(0), C.c_uint64(0)
+        self.L.ltephy_last_turbo_work(self.h, C.byref(b), C.byref(c), C.byref(i))
+        return b.value, c.value, i.value
+
     def launch_count(self):
         return int(self.L.ltephy_launch_count(self.h))
 
@@ -262,6 +277,9 @@ def _bind_search(L):
     L.ltephy_search_rnti_reason.argtypes = [P, C.c_uint16]
     L.ltephy_dci_to_grant.argtypes = [P, P, C.c_uint32, C.c_uint32, C.c_int, P, P]
     L.ltephy_decode_subframes.argtypes = [P, P, P, P, C.c_uint32, C.c_uint64, P, P, P, C.c_uint32, P, P, P, C.c_size_t]
+    L.ltephy_decode_subframes_device.argtypes = [P, P, P, P, C.c_uint32, C.c_uint64, P, P, P, C.c_uint32, P, P, P, C.c_size_t]
+    L.ltephy_search_batch.argtypes = [P, P, P, C.c_uint32, P, C.c_uint32, P]
+    L.ltephy_grants_from_dcis.argtypes = [P, P, P, C.c_uint32, C.c_uint32, C.c_uint32, P, P, C.c_uint32, P]
     L._search_bound = True
 
 

@@ -10,6 +10,7 @@
 #include "../../include/lte_tables.h"
 #include "lte_host.hpp"
 #include <algorithm>
+#include <chrono>
 #include <condition_variable>
 #include <cstring>
 #include <mutex>
@@ -191,6 +192,7 @@ struct ltephy_search {
   ltehost::Cell      cell;
   ltehost::SizeTable st;
   uint32_t           nof_cce[3]{};
+  std::vector<uint16_t> re_slot; // [3 sf class][3 cfi][2 slots][nof_prb]: data REs of a PRB in a slot
   RntiManager        rm;
   Meta               all[NF];
   uint8_t            primary[NF], secondary[NF];
@@ -613,10 +615,19 @@ int ltephy_dci_to_grant(const ltephy_search_t* s, const ltephy_dci_t* d, uint32_
     }
   }
   // ---- nof_re (srsran_ra_dl_compute_nof_re) ----
-  uint16_t kk[12];
-  for (uint32_t l = 0; l < 14; l++)
-    for (uint32_t prb = 0; prb < N; prb++)
-      if ((g->prb_mask[l / 7][prb >> 5] >> (prb & 31)) & 1u) g->nof_re += ltehost::pdsch_re_in_prb(c, sf_idx, cfi, l, prb, kk);
+  {
+    const uint32_t  cls = sf_idx == 0 ? 0 : sf_idx == 5 ? 1 : 2;
+    const uint16_t* cnt = &s->re_slot[((size_t)cls * 3 + cfi - 1) * 2 * N];
+    for (uint32_t sl = 0; sl < 2; sl++)
+      for (uint32_t w = 0; w < 4; w++) {
+        uint32_t m = g->prb_mask[sl][w];
+        while (m) {
+          const uint32_t b = (uint32_t)__builtin_ctz(m);
+          m &= m - 1;
+          g->nof_re += cnt[sl * N + 32 * w + b];
+        }
+      }
+  }
   if (d->format == ltehost::F1C && (d->rnti <= RARNTI_END || d->rnti == PRNTI))
     for (int i = 0; i < 2; i++) g->tb[i].rv = 0;
   // ---- MIMO (dl_sniffer_config_mimo, dl_sniffer_pdsch.c:134-276) ----
@@ -648,6 +659,16 @@ ltephy_search_t* ltephy_search_create_cell(uint32_t nof_prb, uint32_t nof_ports,
   s->cell          = cell;
   s->st = ltehost::dci_size_table(s->cell);
   for (uint32_t cfi = 1; cfi <= 3; cfi++) s->nof_cce[cfi - 1] = cm.nof_cce[cfi - 1];
+  {
+    const uint32_t cls_sf[3] = {0, 5, 1};
+    uint16_t       kk[12];
+    s->re_slot.assign((size_t)3 * 3 * 2 * nof_prb, 0);
+    for (uint32_t cls = 0; cls < 3; cls++)
+      for (uint32_t cfi = 1; cfi <= 3; cfi++)
+        for (uint32_t l = 0; l < 14; l++)
+          for (uint32_t prb = 0; prb < nof_prb; prb++)
+            s->re_slot[(((size_t)cls * 3 + cfi - 1) * 2 + l / 7) * nof_prb + prb] += (uint16_t)ltehost::pdsch_re_in_prb(cell, cls_sf[cls], cfi, l, prb, kk);
+  }
   s->rm.threshold = histogram_threshold;
   for (int i = 0; i < NF; i++) s->all[i] = {(uint8_t)i, 0};
   s->update_formats();
@@ -702,58 +723,107 @@ int      ltephy_search_rnti_is_forbidden(const ltephy_search_t* s, uint16_t r, u
 int      ltephy_search_rnti_is_evergreen(const ltephy_search_t* s, uint16_t r, uint32_t f) { return s->rm.is_evergreen(r, f); }
 
 // ===================================================================================================
+// Batch helpers.  ltephy_search_batch: FALCON walk over n subframes in order (dci.sf = index in the batch).
+int ltephy_search_batch(ltephy_search_t* s, const ltephy_sf_info_t* info, const ltephy_cand_t* cands, uint32_t n, ltephy_dci_t* dcis, uint32_t max_dcis,
+                        uint32_t* n_dcis)
+{
+  if (!s || !info || !cands || !dcis || !n_dcis) return LTEPHY_ERROR_INVALID_INPUTS;
+  uint32_t nd = 0;
+  for (uint32_t i = 0; i < n; i++) {
+    uint32_t k = 0;
+    int      r = s->search_subframe(info[i], cands + (size_t)i * LTEPHY_MAX_LOC * LTEPHY_MAX_SIZES, i, dcis + nd, max_dcis - nd, &k);
+    if (r < 0) return r;
+    nd += std::min(k, max_dcis - nd);
+  }
+  *n_dcis = nd;
+  return LTEPHY_SUCCESS;
+}
+// Accepted DL DCIs -> PDSCH grants, applying decode_dl_mode's skip rule (src/src/DL_Sniffer_PDSCH.cc:887-889).
+// Only subframes with sf % mod == rem are taken (multi-GPU sharding); grant.sf = sf / mod (local index).
+int ltephy_grants_from_dcis(const ltephy_search_t* s, const ltephy_sf_info_t* info, const ltephy_dci_t* dcis, uint32_t nd, uint32_t mod, uint32_t rem,
+                            ltephy_grant_t* grants, uint32_t* grant_dci, uint32_t max_grants, uint32_t* n_grants)
+{
+  if (!s || !info || !dcis || !grants || !grant_dci || !n_grants || mod == 0) return LTEPHY_ERROR_INVALID_INPUTS;
+  uint32_t ng = 0;
+  for (uint32_t i = 0; i < nd; i++) {
+    const ltephy_dci_t& d = dcis[i];
+    if (d.sf % mod != rem || d.format == ltehost::F0 || d.rnti == 0) continue;
+    ltephy_grant_t g;
+    if (ltephy_dci_to_grant(s, &d, info[d.sf].tti % 10, info[d.sf].cfi, 0, &g, nullptr) != LTEPHY_SUCCESS) continue;
+    if (!(g.tb[0].tbs > 0 && !(s->cell.nof_rx == 1 && g.nof_tb == 2))) continue;
+    if (g.tx_scheme == LTEPHY_TX_SPATIALMUX) continue; // TM4 codebook precoding: next round
+    if (ng >= max_grants) return LTEPHY_ERROR_INVALID_INPUTS;
+    g.sf          = d.sf / mod;
+    grants[ng]    = g;
+    grant_dci[ng] = i;
+    ng++;
+  }
+  *n_grants = ng;
+  return LTEPHY_SUCCESS;
+}
+
 // One call = what SubframeWorker::work does for every subframe of the batch (src/src/SubframeWorker.cc:142-207):
 // phase A on the GPU, FALCON search on the host in subframe order, phase B on the GPU for the DL grants.
-int ltephy_decode_subframes(ltephy_t* h, ltephy_search_t* s, const float* iq, const uint32_t* tti, uint32_t n, uint64_t seq, ltephy_sf_info_t* info,
-                            ltephy_cand_t* cand_scratch, ltephy_dci_t* dcis, uint32_t max_dcis, uint32_t* n_dcis, ltephy_tb_result_t* tbs,
-                            uint8_t* payload, size_t payload_cap)
+static double g_host_ms[8];
+static inline double now_ms() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+void ltephy_last_host_timing(double* ms8) { memcpy(ms8, g_host_ms, sizeof(g_host_ms)); }
+
+static int decode_common(ltephy_t* h, ltephy_search_t* s, const void* iq, bool iq_on_device, const uint32_t* tti, uint32_t n, uint64_t seq,
+                         ltephy_sf_info_t* info, ltephy_cand_t* cand_scratch, ltephy_dci_t* dcis, uint32_t max_dcis, uint32_t* n_dcis,
+                         ltephy_tb_result_t* tbs, uint8_t* payload, size_t payload_cap)
 {
   if (!h || !s || !iq || !tti || !info || !cand_scratch || !dcis || !n_dcis || !tbs) return LTEPHY_ERROR_INVALID_INPUTS;
-  int r = ltephy_submit_iq(h, iq, tti, n);
+  double t0 = now_ms();
+  int r = iq_on_device ? ltephy_submit_iq_device(h, iq, tti, n) : ltephy_submit_iq(h, (const float*)iq, tti, n);
   if (r) return r;
+  double t1 = now_ms();
   r = ltephy_get_phase_a(h, info, cand_scratch);
   if (r) return r;
-  uint32_t                    nd = 0;
-  std::vector<ltephy_grant_t> grants;
-  std::vector<uint32_t>       grant_dci;
+  double t2 = now_ms();
+  uint32_t nd = 0;
   {
     std::unique_lock<std::mutex> lk(s->mtx);
     s->cv.wait(lk, [&] { return s->next_seq == seq || seq == LTEPHY_SEQ_NONE; });
-    for (uint32_t i = 0; i < n; i++) {
-      uint32_t k = 0;
-      r          = s->search_subframe(info[i], cand_scratch + (size_t)i * LTEPHY_MAX_LOC * LTEPHY_MAX_SIZES, i, dcis + nd, max_dcis - nd, &k);
-      if (r < 0) break;
-      nd += std::min(k, max_dcis - nd);
-    }
+    r = ltephy_search_batch(s, info, cand_scratch, n, dcis, max_dcis, &nd);
     if (seq != LTEPHY_SEQ_NONE) s->next_seq = seq + 1;
     lk.unlock();
     s->cv.notify_all();
   }
   if (r < 0) return r;
+  double t3 = now_ms();
   *n_dcis = nd;
-  grants.reserve(nd);
-  for (uint32_t i = 0; i < nd; i++) {
-    tbs[2 * i] = tbs[2 * i + 1] = ltephy_tb_result_t{};
-    const ltephy_dci_t& d       = dcis[i];
-    if (d.format == ltehost::F0 || d.rnti == 0) continue;
-    ltephy_grant_t g;
-    if (ltephy_dci_to_grant(s, &d, info[d.sf].tti % 10, info[d.sf].cfi, 0, &g, nullptr) != LTEPHY_SUCCESS) continue;
-    // skip rule of decode_dl_mode (src/src/DL_Sniffer_PDSCH.cc:887-889)
-    if (!(g.tb[0].tbs > 0 && !(s->cell.nof_rx == 1 && g.nof_tb == 2))) continue;
-    if (g.tx_scheme == LTEPHY_TX_SPATIALMUX) continue; // not implemented yet
-    grants.push_back(g);
-    grant_dci.push_back(i);
-  }
-  r = ltephy_submit_grants(h, grants.data(), (uint32_t)grants.size());
+  std::vector<ltephy_grant_t> grants(nd + 1);
+  std::vector<uint32_t>       grant_dci(nd + 1);
+  uint32_t                    ng = 0;
+  r = ltephy_grants_from_dcis(s, info, dcis, nd, 1, 0, grants.data(), grant_dci.data(), nd + 1, &ng);
   if (r) return r;
-  std::vector<ltephy_tb_result_t> res(2 * grants.size() + 2);
+  double t4 = now_ms();
+  for (uint32_t i = 0; i < 2 * nd; i++) tbs[i] = ltephy_tb_result_t{};
+  r = ltephy_submit_grants(h, grants.data(), ng);
+  if (r) return r;
+  double t5 = now_ms();
+  std::vector<ltephy_tb_result_t> res(2 * (size_t)ng + 2);
   r = ltephy_get_phase_b(h, res.data(), payload, payload_cap);
   if (r) return r;
-  for (size_t gi = 0; gi < grants.size(); gi++) {
+  double t6 = now_ms();
+  g_host_ms[0] = t1 - t0, g_host_ms[1] = t2 - t1, g_host_ms[2] = t3 - t2, g_host_ms[3] = t4 - t3, g_host_ms[4] = t5 - t4, g_host_ms[5] = t6 - t5;
+  for (uint32_t gi = 0; gi < ng; gi++) {
     tbs[2 * grant_dci[gi]]     = res[2 * gi];
     tbs[2 * grant_dci[gi] + 1] = res[2 * gi + 1];
   }
   return LTEPHY_SUCCESS;
+}
+int ltephy_decode_subframes(ltephy_t* h, ltephy_search_t* s, const float* iq, const uint32_t* tti, uint32_t n, uint64_t seq, ltephy_sf_info_t* info,
+                            ltephy_cand_t* cand_scratch, ltephy_dci_t* dcis, uint32_t max_dcis, uint32_t* n_dcis, ltephy_tb_result_t* tbs,
+                            uint8_t* payload, size_t payload_cap)
+{
+  return decode_common(h, s, iq, false, tti, n, seq, info, cand_scratch, dcis, max_dcis, n_dcis, tbs, payload, payload_cap);
+}
+int ltephy_decode_subframes_device(ltephy_t* h, ltephy_search_t* s, const void* iq_dev, const uint32_t* tti, uint32_t n, uint64_t seq,
+                                   ltephy_sf_info_t* info, ltephy_cand_t* cand_scratch, ltephy_dci_t* dcis, uint32_t max_dcis, uint32_t* n_dcis,
+                                   ltephy_tb_result_t* tbs, uint8_t* payload, size_t payload_cap)
+{
+  return decode_common(h, s, iq_dev, true, tti, n, seq, info, cand_scratch, dcis, max_dcis, n_dcis, tbs, payload, payload_cap);
 }
 
 } // extern "C"

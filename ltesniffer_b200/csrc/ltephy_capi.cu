@@ -5,6 +5,7 @@
 #include "../../include/ltephy_search.h"
 #include "dev_common.cuh"
 #include "lte_host.hpp"
+#include "../../include/lte_tables.h"
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -100,7 +101,7 @@ struct ltephy {
   ltehost::SizeTable st;
   DevCell            dc{};
   cudaStream_t       stream = nullptr;
-  cudaEvent_t        ev[6]{};
+  cudaEvent_t        ev[6]{}, mark[2]{};
   std::vector<void*> tables; // device tables freed at destroy
   uint64_t           launches = 0;
 
@@ -136,6 +137,10 @@ struct ltephy {
   uint32_t *                 d_gold_x1 = nullptr, *d_gold_basis = nullptr, gold_words = 0;
   uint32_t *                 d_xpowA = nullptr, *d_xpowB = nullptr;
   std::map<std::tuple<uint32_t, uint32_t, uint32_t>, std::pair<uint32_t, uint32_t>> rm_cache; // (K,F,rv) -> (offset, nn)
+  int64_t  rm_fast[188][4];   // F == 0 fast path: offset or -1
+  uint32_t rm_fast_nn[188][4];
+  int64_t  pi_fast[188];
+  std::vector<ltehost::Segm> segm_fast; // index tbs/8, C == 0 means "not computed"
   size_t                                                                            rm_used = 0;
   std::map<uint32_t, uint32_t>                                                      pi_cache; // K -> offset
   size_t                                                                            pi_used = 0;
@@ -174,8 +179,12 @@ extern "C" int ltephy_create(const ltephy_cfg_t* cfg, ltephy_t** out)
     return fail(LTEPHY_ERROR_INVALID_INPUTS, "control region map failed");
   }
   h->st = ltehost::dci_size_table(h->cell);
+  memset(h->rm_fast, 0xFF, sizeof(h->rm_fast));
+  memset(h->pi_fast, 0xFF, sizeof(h->pi_fast));
+  h->segm_fast.assign(110000 / 8, ltehost::Segm{});
   CU(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
   for (auto& e : h->ev) CU(cudaEventCreate(&e));
+  for (auto& e : h->mark) CU(cudaEventCreate(&e));
 
   DevCell& c = h->dc;
   c.nof_prb = cfg->nof_prb, c.nof_ports = cfg->nof_ports, c.cell_id = cfg->cell_id, c.nof_rx = cfg->nof_rx;
@@ -320,6 +329,29 @@ extern "C" void ltephy_cell_of(const ltephy_t* h, uint32_t* a, uint32_t* b, uint
 {
   *a = h->cell.nof_prb, *b = h->cell.nof_ports, *c = h->cell.cell_id, *d = h->cell.nof_rx;
 }
+extern "C" int ltephy_mark(ltephy_t* h, int slot)
+{
+  if (!h || slot < 0 || slot > 1) return LTEPHY_ERROR_INVALID_INPUTS;
+  CU(cudaEventRecord(h->mark[slot], h->stream));
+  return LTEPHY_SUCCESS;
+}
+extern "C" float ltephy_mark_elapsed_ms(ltephy_t* h)
+{
+  float ms = -1.0f;
+  if (cudaEventSynchronize(h->mark[1]) != cudaSuccess) return -1.0f;
+  cudaEventElapsedTime(&ms, h->mark[0], h->mark[1]);
+  return ms;
+}
+extern "C" int ltephy_last_turbo_work(ltephy_t* h, uint64_t* bytes, uint64_t* code_blocks, uint64_t* info_bits)
+{
+  uint64_t b = 0, ib = 0;
+  for (auto& cb : h->cbs) b += 3ull * (cb.K + 4) * 2 + cb.K / 8;
+  for (auto& tb : h->tbs) ib += 8ull * tb.nbytes;
+  if (bytes) *bytes = b;
+  if (code_blocks) *code_blocks = h->cbs.size();
+  if (info_bits) *info_bits = ib;
+  return LTEPHY_SUCCESS;
+}
 extern "C" uint64_t ltephy_launch_count(const ltephy_t* h) { return h->launches; }
 extern "C" int      ltephy_last_timing(ltephy_t* h, float ms[4])
 {
@@ -328,14 +360,14 @@ extern "C" int      ltephy_last_timing(ltephy_t* h, float ms[4])
 }
 
 // ---------------------------------------------------------------------------------------- phase A
-static int phase_a_common(ltephy* h, const uint32_t* tti, uint32_t n)
+static int phase_a_common(ltephy* h, const float2* iq_dev, const uint32_t* tti, uint32_t n)
 {
   for (uint32_t i = 0; i < n; i++) {
     memset(&h->h_info.p[i], 0, sizeof(DevSfInfo));
     h->h_info.p[i].tti = tti[i];
   }
   CU(cudaMemcpyAsync(h->d_info.p, h->h_info.p, n * sizeof(DevSfInfo), cudaMemcpyHostToDevice, h->stream));
-  launch_frontend(h->dc, h->d_iq.p, h->d_sym.p, h->d_ce.p, h->d_llr.p, h->d_info.p, n, h->stream, &h->launches);
+  launch_frontend(h->dc, iq_dev, h->d_sym.p, h->d_ce.p, h->d_llr.p, h->d_info.p, n, h->stream, &h->launches);
   launch_viterbi(h->dc, h->d_llr.p, h->d_info.p, h->d_cands.p, n, h->stream, &h->launches);
   CU(cudaEventRecord(h->ev[1], h->stream));
   CU(cudaGetLastError());
@@ -348,16 +380,14 @@ extern "C" int ltephy_submit_iq(ltephy_t* h, const float* iq, const uint32_t* tt
   CU(cudaSetDevice(h->cfg.device));
   CU(cudaEventRecord(h->ev[0], h->stream));
   CU(cudaMemcpyAsync(h->d_iq.p, iq, (size_t)n * h->dc.nof_rx * h->dc.sf_len * sizeof(float2), cudaMemcpyHostToDevice, h->stream));
-  return phase_a_common(h, tti, n);
+  return phase_a_common(h, h->d_iq.p, tti, n);
 }
 extern "C" int ltephy_submit_iq_device(ltephy_t* h, const void* iq_dev, const uint32_t* tti, uint32_t n)
 {
   if (!h || !iq_dev || !tti || n == 0 || n > h->cfg.max_subframes) return fail(LTEPHY_ERROR_INVALID_INPUTS, "submit_iq_device: bad arguments");
   CU(cudaSetDevice(h->cfg.device));
   CU(cudaEventRecord(h->ev[0], h->stream));
-  if (iq_dev != h->d_iq.p)
-    CU(cudaMemcpyAsync(h->d_iq.p, iq_dev, (size_t)n * h->dc.nof_rx * h->dc.sf_len * sizeof(float2), cudaMemcpyDeviceToDevice, h->stream));
-  return phase_a_common(h, tti, n);
+  return phase_a_common(h, reinterpret_cast<const float2*>(iq_dev), tti, n); // read in place: the caller keeps the buffer alive until phase A is fetched
 }
 extern "C" int ltephy_get_phase_a(ltephy_t* h, ltephy_sf_info_t* info, ltephy_cand_t* cands)
 {
@@ -390,6 +420,11 @@ extern "C" int ltephy_get_phase_a(ltephy_t* h, ltephy_sf_info_t* info, ltephy_ca
 // ---------------------------------------------------------------------------------------- phase B
 static int rm_table_for(ltephy* h, uint32_t K, uint32_t F, uint32_t rv, uint32_t& off, uint32_t& nn)
 {
+  const int ki = lte_qpp_index_ge(K);
+  if (F == 0 && rv < 4 && ki >= 0 && h->rm_fast[ki][rv] >= 0) {
+    off = (uint32_t)h->rm_fast[ki][rv], nn = h->rm_fast_nn[ki][rv];
+    return 0;
+  }
   auto key = std::make_tuple(K, F, rv);
   auto it  = h->rm_cache.find(key);
   if (it != h->rm_cache.end()) {
@@ -400,6 +435,7 @@ static int rm_table_for(ltephy* h, uint32_t K, uint32_t F, uint32_t rv, uint32_t
   if (h->rm_used + t.first.size() > h->d_rm.cap) { // cache full: start over (tables already queued stay valid until the stream drains)
     cudaStreamSynchronize(h->stream);
     h->rm_cache.clear();
+    memset(h->rm_fast, 0xFF, sizeof(h->rm_fast));
     h->rm_used = 0;
   }
   off = (uint32_t)h->rm_used, nn = t.nn;
@@ -407,10 +443,16 @@ static int rm_table_for(ltephy* h, uint32_t K, uint32_t F, uint32_t rv, uint32_t
   cudaStreamSynchronize(h->stream); // source vector dies at scope exit
   h->rm_used += t.first.size();
   h->rm_cache[key] = {off, nn};
+  if (F == 0 && rv < 4 && ki >= 0) h->rm_fast[ki][rv] = off, h->rm_fast_nn[ki][rv] = nn;
   return 0;
 }
 static int pi_table_for(ltephy* h, uint32_t K, uint32_t& off)
 {
+  const int ki = lte_qpp_index_ge(K);
+  if (ki >= 0 && h->pi_fast[ki] >= 0) {
+    off = (uint32_t)h->pi_fast[ki];
+    return 0;
+  }
   auto it = h->pi_cache.find(K);
   if (it != h->pi_cache.end()) {
     off = it->second;
@@ -427,6 +469,7 @@ static int pi_table_for(ltephy* h, uint32_t K, uint32_t& off)
   cudaStreamSynchronize(h->stream);
   h->pi_used += t.size();
   h->pi_cache[K] = off;
+  if (ki >= 0) h->pi_fast[ki] = off;
   return 0;
 }
 
@@ -438,7 +481,9 @@ static int build_jobs(ltephy* h, const ltephy_grant_t* gin, uint32_t n, size_t& 
   h->tb_slot.assign((size_t)n * 2, 0xFFFFFFFFu);
   h->pllr_elems = 0, h->payload_bytes = 0;
   seq_words = 0, turbo_words = 0, max_scr_words = 0;
-  std::map<uint32_t, uint32_t> open_pair; // K -> pair index with a free half
+  int32_t open_pair[188]; // qpp index of K -> pair index with a free half, or -1
+  memset(open_pair, 0xFF, sizeof(open_pair));
+  h->grants.reserve(n), h->cbs.reserve((size_t)n * 4), h->pairs.reserve((size_t)n * 2), h->tbs.reserve((size_t)n * 2), h->pair_pi_off.reserve((size_t)n * 2);
   for (uint32_t gi = 0; gi < n; gi++) {
     const ltephy_grant_t& g = gin[gi];
     if (g.sf >= h->n_cur) return fail(LTEPHY_ERROR_INVALID_INPUTS, "grant %u: subframe %u outside the batch", gi, g.sf);
@@ -449,11 +494,22 @@ static int build_jobs(ltephy* h, const ltephy_grant_t* gin, uint32_t n, size_t& 
     const uint32_t cls = d.sf_idx == 0 ? 0 : d.sf_idx == 5 ? 1 : 2;
     const uint8_t* cnt = &h->re_cnt[((size_t)(cls * 3 + d.cfi - 1) * 14) * N];
     uint32_t       acc = 0;
+    uint8_t        plist[2][LTEPHY_MAX_PRB];
+    uint32_t       pn[2] = {0, 0};
+    for (uint32_t sl = 0; sl < 2; sl++)
+      for (uint32_t w = 0; w < 4; w++) {
+        uint32_t m = d.prb_mask[sl][w];
+        while (m) {
+          const uint32_t b = (uint32_t)__builtin_ctz(m);
+          m &= m - 1;
+          if (32 * w + b < N) plist[sl][pn[sl]++] = (uint8_t)(32 * w + b);
+        }
+      }
     for (uint32_t l = 0; l < 14; l++) {
       d.re_off[l] = acc;
-      const uint32_t* m = d.prb_mask[l / 7];
-      for (uint32_t prb = 0; prb < N; prb++)
-        if ((m[prb >> 5] >> (prb & 31)) & 1u) acc += cnt[l * N + prb];
+      const uint8_t* pl = plist[l / 7];
+      const uint8_t* cl = cnt + l * N;
+      for (uint32_t i = 0; i < pn[l / 7]; i++) acc += cl[pl[i]];
     }
     d.re_off[14] = acc;
     d.nof_re     = acc;
@@ -478,13 +534,10 @@ static int build_jobs(ltephy* h, const ltephy_grant_t* gin, uint32_t n, size_t& 
       h->pllr_elems += (G + 7) & ~7u;
       if (g.tb[t].tbs > 0) {
         const uint32_t tbs = (uint32_t)g.tb[t].tbs;
-        auto           sit = h->segm_cache.find(tbs);
-        if (sit == h->segm_cache.end()) {
-          ltehost::Segm s;
-          if (!ltehost::cb_segmentation(tbs, s)) return fail(LTEPHY_ERROR_INVALID_INPUTS, "grant %u: invalid TBS %u", gi, tbs);
-          sit = h->segm_cache.emplace(tbs, s).first;
-        }
-        const ltehost::Segm& s  = sit->second;
+        if (tbs / 8 >= h->segm_fast.size() || (tbs & 7)) return fail(LTEPHY_ERROR_INVALID_INPUTS, "grant %u: invalid TBS %u", gi, tbs);
+        if (h->segm_fast[tbs / 8].C == 0 && !ltehost::cb_segmentation(tbs, h->segm_fast[tbs / 8]))
+          return fail(LTEPHY_ERROR_INVALID_INPUTS, "grant %u: invalid TBS %u", gi, tbs);
+        const ltehost::Segm& s  = h->segm_fast[tbs / 8];
         const uint32_t       NL = g.tx_scheme == LTEPHY_TX_DIVERSITY ? 2 : 1;
         DevTb                tb{};
         tb.byte_off = (uint32_t)h->payload_bytes, tb.nbytes = tbs / 8, tb.cb_first = (uint32_t)h->cbs.size(), tb.ncb = s.C;
@@ -498,12 +551,12 @@ static int build_jobs(ltephy* h, const ltephy_grant_t* gin, uint32_t n, size_t& 
           cb.shift = qm == 2 ? 0 : qm == 4 ? 1 : 2;
           if (rm_table_for(h, cb.K, cb.F, g.tb[t].rv, cb.rm_tab, cb.rm_nn)) return fail(LTEPHY_ERROR, "rate-matching table upload failed");
           // pair assignment
-          auto     op = open_pair.find(cb.K);
-          uint32_t pi;
-          if (op != open_pair.end()) {
-            pi = op->second;
-            open_pair.erase(op);
-            cb.half = 1;
+          const int kq = lte_qpp_index_ge(cb.K);
+          uint32_t  pi;
+          if (open_pair[kq] >= 0) {
+            pi            = (uint32_t)open_pair[kq];
+            open_pair[kq] = -1;
+            cb.half       = 1;
           } else {
             DevPair p{};
             p.K = cb.K, p.NW = (cb.K + 31) / 32;
@@ -515,8 +568,8 @@ static int build_jobs(ltephy* h, const ltephy_grant_t* gin, uint32_t n, size_t& 
             pi = (uint32_t)h->pairs.size();
             h->pairs.push_back(p);
             h->pair_pi_off.push_back(po);
-            open_pair[cb.K] = pi;
-            cb.half         = 0;
+            open_pair[kq] = (int32_t)pi;
+            cb.half       = 0;
           }
           cb.pair         = pi;
           DevPair& p      = h->pairs[pi];

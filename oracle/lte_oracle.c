@@ -770,3 +770,22 @@ int lteo_pdsch_decode(lteo_t* q, uint32_t sf_idx, uint32_t cfi, uint16_t rnti, c
   free(llr[0]), free(llr[1]);
   return ret;
 }
+
+/* ---------------------------------------------------------------- whole phase A for one subframe (convenience for the
+ * CPU baseline and the end-to-end tests): OFDM rx, channel estimate, PCFICH, PDCCH LLRs. sym/ce are caller buffers. */
+int lteo_phase_a(lteo_t* q, const cf_t* iq, uint32_t sf_idx, cf_t* sym /* [nof_rx][14*nsc] */, cf_t* ce /* [ports*rx][14*nsc] */,
+                 float* llr /* [88*72] */, lteo_chest_res_t* res, uint32_t* cfi_out)
+{
+  const uint32_t g = 14 * q->nsc;
+  const cf_t*    symp[LTE_MAX_ANT];
+  cf_t*          cep[LTE_MAX_PORTS * LTE_MAX_ANT];
+  for (uint32_t a = 0; a < q->cell.nof_rx; a++) {
+    lteo_ofdm_rx(q, iq + (size_t)a * q->sf_len, sym + (size_t)a * g);
+    symp[a] = sym + (size_t)a * g;
+  }
+  for (uint32_t i = 0; i < q->cell.nof_ports * q->cell.nof_rx; i++) cep[i] = ce + (size_t)i * g;
+  lteo_chest(q, sf_idx, symp, cep, res);
+  float corr[3];
+  *cfi_out = lteo_pcfich_decode(q, sf_idx, symp, (const cf_t* const*)cep, corr);
+  return (int)lteo_pdcch_extract_llr(q, sf_idx, *cfi_out, symp, (const cf_t* const*)cep, llr);
+}

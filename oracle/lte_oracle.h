@@ -74,6 +74,9 @@ uint32_t lteo_turbo_decode(const int16_t* d, uint32_t K, uint32_t max_iter, int 
 int lteo_pdsch_decode(lteo_t* q, uint32_t sf_idx, uint32_t cfi, uint16_t rnti, const lte_dl_grant_t* g, const cf_t* const* sym,
                       const cf_t* const* ce, uint32_t max_iter, uint8_t* const* payload, int* crc_ok);
 
+/* whole phase A of one subframe (OFDM rx, chest, PCFICH, PDCCH LLR); returns nof_cce */
+int lteo_phase_a(lteo_t* q, const cf_t* iq, uint32_t sf_idx, cf_t* sym, cf_t* ce, float* llr, lteo_chest_res_t* res, uint32_t* cfi_out);
+
 #ifdef __cplusplus
 }
 #endif

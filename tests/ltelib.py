@@ -368,3 +368,38 @@ class OracleWalk:
             self.L.lteo_walk_destroy(self.h)
         except Exception:
             pass
+
+
+def oracle_pipeline(cell, iq, tti, walk=None, max_iter=8, want_tb=True):
+    """The whole reference-shaped CPU path on a capture: phase A, FALCON walk (reference RNTIManager),
+    DCI->grant (64QAM table), PDSCH decode.  Returns per-subframe list of (walk dcis, [(grant, payloads, crc)])."""
+    O = oracle()
+    O.lteo_phase_a.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(ChestRes), C.POINTER(C.c_uint32)]
+    o = Oracle(cell)
+    walk = walk or OracleWalk(cell)
+    g = 14 * 12 * cell.nof_prb
+    out = []
+    for i in range(len(tti)):
+        sym = np.zeros((cell.nof_rx, g), np.complex64)
+        ce = np.zeros((cell.nof_ports * cell.nof_rx, g), np.complex64)
+        llr = np.zeros(88 * 72, np.float32)
+        res = ChestRes()
+        cfi = C.c_uint32(0)
+        sf_idx = int(tti[i]) % 10
+        ncce = O.lteo_phase_a(o.h, ptr(np.ascontiguousarray(iq[i])), sf_idx, ptr(sym), ptr(ce), ptr(llr), C.byref(res), C.byref(cfi))
+        dcis = walk.subframe(sf_idx, cfi.value, ncce, llr[:72 * ncce], res.snr_db)
+        tbs = []
+        if want_tb:
+            for d in dcis:
+                if d.format == 0 or d.rnti == 0:
+                    tbs.append(None)
+                    continue
+                bits = np.frombuffer(bytes(d.bits), np.uint8)[:d.nof_bits]
+                r, dd, gr = unpack_and_grant(cell, d.format, d.rnti, bits, sf_idx, cfi.value, 0)
+                if r != 0 or not (gr.tb[0].tbs > 0 and not (cell.nof_rx == 1 and gr.nof_tb == 2)) or gr.tx_scheme == 3:
+                    tbs.append(None)
+                    continue
+                r, pl, ok = o.pdsch_decode(sf_idx, cfi.value, d.rnti, gr, sym, ce, max_iter)
+                tbs.append((gr, pl, ok))
+        out.append((dcis, tbs, res.snr_db, cfi.value))
+    return out
