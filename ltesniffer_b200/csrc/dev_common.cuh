@@ -26,6 +26,7 @@ struct DevCell {
   const uint32_t* pdcch_scr;      // [10][pdcch_scr_words]
   const uint16_t* conv_tab[LTEPHY_MAX_SIZES]; // [3K] circular position -> stream-major index
   const uint16_t* loc_tab[3];     // [nloc] ncce | (L << 8)
+  const uint16_t* re_mask;        // [3 sf class][3 cfi][14][nof_prb]: 12-bit mask of PDSCH data REs of the PRB in the symbol
 };
 
 // per-subframe device record (layout mirrors the leading part of ltephy_sf_info_t)
@@ -57,6 +58,9 @@ struct DevGrant {          // one PDSCH grant
   uint32_t prb_mask[2][4];
   uint32_t nof_re;
   uint32_t re_off[15];     // prefix sum of data REs per OFDM symbol
+  uint32_t cls;            // subframe class for the RE masks: 0 = sf 0, 1 = sf 5, 2 = other
+  uint32_t np[2];          // allocated PRBs per slot
+  uint8_t  plist[2][112];  // allocated PRB indices per slot, ascending
   uint32_t qm[2];
   uint32_t llr_off[2];     // offset (int16 elements) of codeword LLRs in the LLR pool
   uint32_t scr_off[2];     // offset (words) of the scrambling sequence in the sequence pool
@@ -66,7 +70,7 @@ struct DevCb {             // one code block
   uint32_t llr_off;        // first soft bit of this code block in the LLR pool
   uint32_t E;              // soft bits received
   uint32_t K, F;
-  uint32_t rm_tab;         // offset into the rate-matching table pool (uint32 first[3*(K+4)])
+  uint32_t rm_tab;         // offset into the rate-matching table pool: order[k] = word of the pair buffer hit by soft bit k
   uint32_t rm_nn;
   uint32_t shift;          // conditioning shift from Qm
   uint32_t pair, half;     // turbo job and 16-bit lane it occupies

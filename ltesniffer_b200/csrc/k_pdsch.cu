@@ -25,25 +25,6 @@ __global__ void __launch_bounds__(256) scr_seq_kernel(const DevGrant* __restrict
   seq_pool[g.scr_off[cw] + wi] = v;
 }
 
-// ---- data REs of one PRB in one symbol (same rule as srsran_ra_dl_compute_nof_re / pdsch RE mapping)
-__device__ __forceinline__ uint32_t re_in_prb(const DevCell& c, uint32_t sf_idx, uint32_t cfi, uint32_t l, uint32_t prb, uint16_t* kk)
-{
-  if (l < (c.nof_prb <= 10 ? cfi + 1 : cfi)) return 0;
-  const uint32_t lo = 6 * c.nof_prb - 36, hi = lo + 72;
-  const bool     crs = (l % 7 == 0) || (l % 7 == 4);
-  uint32_t       n = 0;
-  for (uint32_t k = 12 * prb; k < 12 * prb + 12; k++) {
-    if (crs && (c.nof_ports == 1 ? (k % 6 == c.crs_off[0][(l % 7) ? 1 : 0]) : (k % 3 == c.cell_id % 3))) continue;
-    if (k >= lo && k < hi) {
-      if ((sf_idx == 0 || sf_idx == 5) && (l == 5 || l == 6)) continue;
-      if (sf_idx == 0 && l >= 7 && l <= 10) continue;
-    }
-    if (kk) kk[n] = (uint16_t)k;
-    n++;
-  }
-  return n;
-}
-
 __device__ __forceinline__ short f2s(float v)
 {
   v = fminf(fmaxf(v, -32767.0f), 32767.0f);
@@ -72,95 +53,121 @@ __device__ __forceinline__ void demod_s(float2 x, uint32_t qm, short* z)
     z[6] = (short)(iabs(z[4]) - 153), z[7] = (short)(iabs(z[5]) - 153);
   }
 }
+// soft-demodulate one equalised symbol, descramble with Qm bits taken from a 64-bit window of the sequence, store
 __device__ __forceinline__ void emit(const DevGrant& g, uint32_t cw, uint32_t gi, float2 x, const uint32_t* __restrict__ seq_pool,
                                      short* __restrict__ llr_pool)
 {
   const uint32_t qm = g.qm[cw];
   short          z[8];
   demod_s(x, qm, z);
-  const uint32_t* seq = seq_pool + g.scr_off[cw];
-  short*          out = llr_pool + g.llr_off[cw] + (size_t)gi * qm;
-  const uint32_t  b0  = gi * qm;
-  for (uint32_t i = 0; i < qm; i++) {
-    const uint32_t b = b0 + i, s = (seq[b >> 5] >> (b & 31)) & 1u;
-    out[i]           = s ? (short)-z[i] : z[i];
+  const uint32_t*    seq = seq_pool + g.scr_off[cw];
+  const uint32_t     b0  = gi * qm, w0 = b0 >> 5;
+  const unsigned long long win = ((unsigned long long)seq[w0] | ((unsigned long long)seq[w0 + 1] << 32)) >> (b0 & 31u);
+  uint32_t*          out = reinterpret_cast<uint32_t*>(llr_pool + g.llr_off[cw] + (size_t)gi * qm); // Qm even, offsets 8-aligned
+#pragma unroll
+  for (uint32_t i = 0; i < 8; i += 2) {
+    if (i >= qm) break;
+    const int a = ((win >> i) & 1ull) ? -(int)z[i] : (int)z[i], b = ((win >> (i + 1)) & 1ull) ? -(int)z[i + 1] : (int)z[i + 1];
+    out[i >> 1] = ((uint32_t)a & 0xFFFFu) | ((uint32_t)b << 16);
   }
 }
 
-// one CTA per (OFDM symbol, grant)
+// One CTA per grant.  Work items are (OFDM symbol, allocated PRB, subcarrier) slots; the 12-bit data-RE
+// mask of the PRB gives the rank of the RE inside the grant (36.211 6.3.5 mapping order: k first, then l).
 __global__ void __launch_bounds__(256) pdsch_demod_kernel(const __grid_constant__ DevCell c, const DevGrant* __restrict__ grants,
                                                           const float2* __restrict__ sym, const float2* __restrict__ ce,
                                                           const uint32_t* __restrict__ seq_pool, short* __restrict__ llr_pool)
 {
-  __shared__ uint16_t klist[12 * LTEPHY_MAX_PRB];
-  __shared__ uint16_t pref[LTEPHY_MAX_PRB + 1];
-  const DevGrant&    g = grants[blockIdx.y];
-  const uint32_t     l = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
-  const uint32_t     nre = g.re_off[l + 1] - g.re_off[l];
-  if (nre == 0) return;
-  const uint32_t slot = l / 7;
-  if (tid == 0) {
-    uint32_t acc = 0;
-    for (uint32_t prb = 0; prb < c.nof_prb; prb++) {
-      pref[prb] = (uint16_t)acc;
-      if ((g.prb_mask[slot][prb >> 5] >> (prb & 31)) & 1u) acc += re_in_prb(c, g.sf_idx, g.cfi, l, prb, nullptr);
+  __shared__ uint16_t pref[14][LTEPHY_MAX_PRB + 2];
+  __shared__ DevGrant gs;
+  const uint32_t tid = threadIdx.x, nt = blockDim.x, N = c.nof_prb;
+  for (uint32_t i = tid; i < sizeof(DevGrant) / 4; i += nt) reinterpret_cast<uint32_t*>(&gs)[i] = reinterpret_cast<const uint32_t*>(&grants[blockIdx.x])[i];
+  __syncthreads();
+  const DevGrant& g    = gs;
+  const uint16_t* mask = c.re_mask + ((size_t)(g.cls * 3 + g.cfi - 1) * 14) * N;
+  if (tid < 14) {
+    const uint32_t l = tid, sl = l / 7, np = g.np[sl];
+    uint32_t       acc = 0;
+    for (uint32_t j = 0; j < np; j++) {
+      pref[l][j] = (uint16_t)acc;
+      acc += __popc(mask[l * N + g.plist[sl][j]]);
     }
-    pref[c.nof_prb] = (uint16_t)acc;
+    pref[l][np] = (uint16_t)acc;
   }
   __syncthreads();
-  for (uint32_t prb = tid; prb < c.nof_prb; prb += nt)
-    if (pref[prb + 1] > pref[prb]) re_in_prb(c, g.sf_idx, g.cfi, l, prb, &klist[pref[prb]]);
-  __syncthreads();
-  const SfView   v    = make_view(c, sym, ce, g.sf);
-  const uint32_t base = g.re_off[l];
-  if (g.tx_scheme == LTEPHY_TX_PORT0) {
-    for (uint32_t i = tid; i < nre; i += nt) emit(g, 0, base + i, eq_port0(c, v, l * c.nsc + klist[i]), seq_pool, llr_pool);
-  } else if (g.tx_scheme == LTEPHY_TX_DIVERSITY) {
-    for (uint32_t i = 2 * tid; i + 1 < nre; i += 2 * nt) {
+  const SfView   v  = make_view(c, sym, ce, g.sf);
+  const uint32_t n0 = 7 * 12 * g.np[0], n1 = 7 * 12 * g.np[1];
+  for (uint32_t it = tid; it < n0 + n1; it += nt) {
+    uint32_t sl, rem;
+    if (it < n0)
+      sl = 0, rem = it;
+    else
+      sl = 1, rem = it - n0;
+    const uint32_t per = 12 * g.np[sl], l = 7 * sl + rem / per, q = rem % per, j = q / 12, kk = q % 12;
+    const uint32_t prb = g.plist[sl][j], m = mask[l * N + prb];
+    if (!((m >> kk) & 1u)) continue;
+    const uint32_t r = pref[l][j] + __popc(m & ((1u << kk) - 1u)), gi = g.re_off[l] + r, idx = l * c.nsc + 12 * prb + kk;
+    if (g.tx_scheme == LTEPHY_TX_PORT0) {
+      emit(g, 0, gi, eq_port0(c, v, idx), seq_pool, llr_pool);
+    } else if (g.tx_scheme == LTEPHY_TX_DIVERSITY) {
+      if (gi & 1u) continue; // handled together with its even partner
+      const uint32_t rest = m >> (kk + 1);
+      uint32_t       idx2;
+      if (rest)
+        idx2 = idx + 1 + (uint32_t)(__ffs(rest) - 1);
+      else { // partner is the first data RE of the next allocated PRB (never happens for even per-PRB counts)
+        const uint32_t prb2 = g.plist[sl][j + 1], m2 = mask[l * N + prb2];
+        idx2 = l * c.nsc + 12 * prb2 + (uint32_t)(__ffs(m2) - 1);
+      }
       float2 x0, x1;
-      eq_sfbc(c, v, l * c.nsc + klist[i], l * c.nsc + klist[i + 1], x0, x1);
-      emit(g, 0, base + i, x0, seq_pool, llr_pool);
-      emit(g, 0, base + i + 1, x1, seq_pool, llr_pool);
-    }
-  } else if (g.tx_scheme == LTEPHY_TX_CDD) {
-    for (uint32_t i = tid; i < nre; i += nt) {
+      eq_sfbc(c, v, idx, idx2, x0, x1);
+      emit(g, 0, gi, x0, seq_pool, llr_pool);
+      emit(g, 0, gi + 1, x1, seq_pool, llr_pool);
+    } else if (g.tx_scheme == LTEPHY_TX_CDD) {
       float2 x0, x1;
-      eq_cdd(v, l * c.nsc + klist[i], ((base + i) & 1u) != 0, x0, x1);
-      emit(g, 0, base + i, x0, seq_pool, llr_pool);
-      emit(g, 1, base + i, x1, seq_pool, llr_pool);
+      eq_cdd(v, idx, (gi & 1u) != 0, x0, x1);
+      emit(g, 0, gi, x0, seq_pool, llr_pool);
+      emit(g, 1, gi, x1, seq_pool, llr_pool);
     }
   }
 }
 
-// ---- K7: one CTA per code block.  For every stream position: saturating sum of the soft bits that
-// land on it (first, first+nn, ...), conditioning shift/clamp, store into the turbo stream buffers
-// (window-transposed, two code blocks interleaved as int16x2).
+// ---- K7: one CTA per code block, iterating in RECEIVED order: soft bit k (and its repeats k+nn, ...) lands on
+// pair-buffer word order[k]; reads of e are coalesced, writes follow the runs of the sub-block interleaver
+// (consecutive k -> consecutive words of the window-transposed stream).  Unreceived positions are zeroed here,
+// so the stream buffers need no memset.
 __device__ __forceinline__ int sat16(int v) { return v > 32767 ? 32767 : (v < -32768 ? -32768 : v); }
 
 __global__ void __launch_bounds__(256) rm_turbo_rx_kernel(const DevCb* __restrict__ cbs, const DevPair* __restrict__ pairs,
                                                           const short* __restrict__ llr_pool, const uint32_t* __restrict__ rm_pool,
                                                           uint32_t* __restrict__ turbo_pool)
 {
-  const DevCb&    cb = cbs[blockIdx.x];
+  const DevCb     cb = cbs[blockIdx.x];
   const DevPair&  pr = pairs[cb.pair];
-  const uint32_t  K = cb.K, D = K + 4, NW = pr.NW;
+  const uint32_t  NW = pr.NW;
+  const bool      alone = pr.ncb == 1;
   const short*    e   = llr_pool + cb.llr_off;
-  const uint32_t* tab = rm_pool + cb.rm_tab;
-  short*          buf = reinterpret_cast<short*>(turbo_pool + pr.buf_off);
-  for (uint32_t t = threadIdx.x; t < 3 * D; t += blockDim.x) {
-    const uint32_t s = t / D, i = t % D, first = tab[t];
-    int            acc = 0;
-    if (first != 0xFFFFFFFFu)
-      for (uint32_t k = first; k < cb.E; k += cb.rm_nn) acc = sat16(acc + (int)e[k]);
+  const uint32_t* ord = rm_pool + cb.rm_tab;
+  uint32_t*       bw  = turbo_pool + pr.buf_off;
+  short*          bh  = reinterpret_cast<short*>(bw);
+  for (uint32_t k = threadIdx.x; k < cb.rm_nn; k += blockDim.x) {
+    int acc = 0;
+    for (uint32_t kk = k; kk < cb.E; kk += cb.rm_nn) acc = sat16(acc + (int)e[kk]);
     int v = acc >> cb.shift;
     v     = v > 255 ? 255 : (v < -255 ? -255 : v);
-    if (s < 2 && i < cb.F) v = -255;
-    uint32_t word; // word index inside the pair buffer
-    if (i < K)
-      word = s * 32 * NW + (i & 31u) * NW + (i >> 5);
+    const uint32_t w = ord[k];
+    if (alone)
+      bw[w] = (uint32_t)v & 0xFFFFu;
     else
-      word = 5 * 32 * NW + s * 4 + (i - K);
-    buf[2 * word + cb.half] = (short)v;
+      bh[2 * w + cb.half] = (short)v;
+  }
+  // filler bits are known zeros: strong "0" in the systematic and first parity streams
+  for (uint32_t i = threadIdx.x; i < 2 * cb.F; i += blockDim.x) {
+    const uint32_t st = i / cb.F, ii = i % cb.F, w = st * 32 * NW + (ii & 31u) * NW + (ii >> 5);
+    if (alone)
+      bw[w] = (uint32_t)(-255) & 0xFFFFu;
+    else
+      bh[2 * w + cb.half] = (short)-255;
   }
 }
 
@@ -170,7 +177,7 @@ extern "C" void launch_pdsch_front(const DevCell& c, const DevGrant* grants, uin
 {
   if (!ngrants) return;
   scr_seq_kernel<<<dim3((max_words + 255) / 256, 2 * ngrants), 256, 0, st>>>(grants, gold_x1, gold_basis, basis_words, c.cell_id, seq_pool);
-  pdsch_demod_kernel<<<dim3(14, ngrants), 256, 0, st>>>(c, grants, sym, ce, seq_pool, llr_pool);
+  pdsch_demod_kernel<<<ngrants, 256, 0, st>>>(c, grants, sym, ce, seq_pool, llr_pool);
   *launches += 2;
 }
 extern "C" void launch_rm_turbo_rx(const DevCb* cbs, uint32_t ncb, const DevPair* pairs, const short* llr_pool, const uint32_t* rm_pool,

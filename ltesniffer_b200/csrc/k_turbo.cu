@@ -79,10 +79,14 @@ struct TurboView {
   uint32_t  K, NW;
 };
 
+#define TD_SUB 8 // alpha is kept in shared memory for TD_SUB steps at a time
+
 // one SISO pass for window w.  IL = second constituent decoder (interleaved order).
+// Shared memory per thread: g_s[32] (branch metrics g0 = xa+p, g1 = xa-p, staged once per pass with all the
+// global loads in flight together), pos_s[32] (where the extrinsic goes), alpha_s[TD_SUB][2] (uint4).
 template <bool IL>
-__device__ __forceinline__ void siso_pass(const TurboView& tv, uint4* alpha_s, uint32_t* bits_s, uint32_t w, uint32_t nthreads, bool active,
-                                          const uint32_t* btail)
+__device__ __forceinline__ void siso_pass(const TurboView& tv, uint4* alpha_s, uint2* g_s, uint16_t* pos_s, uint32_t* bits_s, uint32_t w,
+                                          uint32_t nthreads, bool active, const uint32_t* btail, bool first_iter)
 {
   const uint32_t  K = tv.K, NW = tv.NW, tid = threadIdx.x;
   const uint32_t  k0 = w * TD_WL, len = active ? min((uint32_t)TD_WL, K - k0) : 0;
@@ -99,66 +103,81 @@ __device__ __forceinline__ void siso_pass(const TurboView& tv, uint4* alpha_s, u
       a0.s[s] = (w == 0) ? (s ? pk2(TD_NINF, TD_NINF) : 0u) : A[(size_t)w * 8 + s];
       b.s[s]  = (w == NW - 1) ? btail[s] : B[(size_t)w * 8 + s];
     }
-  }
-  __syncthreads(); // every window has read its boundaries before anybody overwrites them
-
-  auto load = [&](uint32_t j, uint32_t& xa, uint32_t& p, uint32_t& pos) {
-    if (!IL) {
-      pos = j * NW + w;
-      xa  = vadd(tv.sysT[pos], apr[pos]);
-    } else {
-      const uint32_t pi = tv.piT[j * NW + w];
-      pos               = (pi & 31u) * NW + (pi >> 5);
-      xa                = vadd(tv.sysT[pos], apr[pos]);
+    // ---- stage the window: every load of the pass is issued here, independent of the recursions ----
+#pragma unroll 8
+    for (uint32_t j = 0; j < len; j++) {
+      uint32_t pos;
+      if (!IL)
+        pos = j * NW + w;
+      else {
+        const uint32_t pi = tv.piT[j * NW + w];
+        pos               = (pi & 31u) * NW + (pi >> 5);
+      }
+      const uint32_t sy = tv.sysT[pos], ap = (!IL && first_iter) ? 0u : apr[pos], p = par[j * NW + w];
+      const uint32_t xa = vadd(sy, ap);
+      g_s[j * nthreads + tid]   = make_uint2(vadd(xa, p), vadd(xa, vneg(p)));
+      pos_s[j * nthreads + tid] = (uint16_t)pos;
     }
-    p = par[j * NW + w];
-  };
+  }
+  __syncthreads(); // every window has read its boundaries (and inputs) before anybody overwrites them
 
   if (active) {
-    // ---- forward over the whole window (no storage) to get alpha at TD_HALF and at the end --------
-    St8 a = a0, amid = a0;
-    for (uint32_t j = 0; j < len; j++) {
-      if (j == TD_HALF) amid = a;
-      uint32_t xa, p, pos;
-      load(j, xa, p, pos);
-      const uint32_t g0 = vadd(xa, p), g1 = vadd(xa, vneg(p));
-      alpha_step(a, g0, g1, vneg(g0), vneg(g1));
-      if ((j & 3u) == 3u) norm8(a);
+    // ---- forward over the whole window, remembering alpha at every TD_SUB-th step -------------------
+    St8 a = a0, ck[TD_WL / TD_SUB - 1];
+#pragma unroll
+    for (uint32_t j = 0; j < TD_WL; j++) {
+      if (j < len) {
+        if (j > 0 && (j % TD_SUB) == 0) ck[j / TD_SUB - 1] = a;
+        const uint2 g = g_s[j * nthreads + tid];
+        alpha_step(a, g.x, g.y, vneg(g.x), vneg(g.y));
+        if ((j & 3u) == 3u) norm8(a);
+      }
     }
     norm8(a);
     if (w + 1 < NW) {
 #pragma unroll
       for (int s = 0; s < 8; s++) A[(size_t)(w + 1) * 8 + s] = a.s[s];
     }
-    // ---- two half windows: forward with storage, then backward with LLR/extrinsic -----------------
-    for (int hw = (len > TD_HALF ? 1 : 0); hw >= 0; hw--) {
-      const uint32_t j0 = hw ? TD_HALF : 0, j1 = hw ? len : min(len, (uint32_t)TD_HALF);
-      St8            af = hw ? amid : a0;
-      for (uint32_t j = j0; j < j1; j++) {
-        alpha_s[((j - j0) * 2 + 0) * nthreads + tid] = make_uint4(af.s[0], af.s[1], af.s[2], af.s[3]);
-        alpha_s[((j - j0) * 2 + 1) * nthreads + tid] = make_uint4(af.s[4], af.s[5], af.s[6], af.s[7]);
-        uint32_t xa, p, pos;
-        load(j, xa, p, pos);
-        const uint32_t g0 = vadd(xa, p), g1 = vadd(xa, vneg(p));
-        alpha_step(af, g0, g1, vneg(g0), vneg(g1));
-        if ((j & 3u) == 3u) norm8(af);
-      }
-      for (int j = (int)j1 - 1; j >= (int)j0; j--) {
-        uint32_t xa, p, pos;
-        load((uint32_t)j, xa, p, pos);
-        const uint32_t g0 = vadd(xa, p), g1 = vadd(xa, vneg(p));
-        const uint4    u0 = alpha_s[((j - j0) * 2 + 0) * nthreads + tid], u1 = alpha_s[((j - j0) * 2 + 1) * nthreads + tid];
-        St8            al;
-        al.s[0] = u0.x, al.s[1] = u0.y, al.s[2] = u0.z, al.s[3] = u0.w, al.s[4] = u1.x, al.s[5] = u1.y, al.s[6] = u1.z, al.s[7] = u1.w;
-        uint32_t m1, m0;
-        beta_llr_step(b, al, g0, g1, vneg(g0), vneg(g1), m1, m0);
-        if ((j & 3) == 0) norm8(b);
-        const int Ll = lo_s(m1) - lo_s(m0), Lh = hi_s(m1) - hi_s(m0);
-        out[pos]     = pk2(ext_of(Ll, lo_s(xa)), ext_of(Lh, hi_s(xa)));
-        if (IL) {
-          const uint32_t pi = tv.piT[(uint32_t)j * NW + w]; // natural bit index
-          if (Ll > 0) atomicOr(&bits_s[pi >> 5], 0x80000000u >> (pi & 31u));
-          if (Lh > 0) atomicOr(&bits_s[(TD_WL * 6) + (pi >> 5)], 0x80000000u >> (pi & 31u));
+    // ---- sub-windows, last first: forward with storage, then backward with LLR / extrinsic ----------
+#pragma unroll
+    for (int sw = TD_WL / TD_SUB - 1; sw >= 0; sw--) {
+      const uint32_t j0 = (uint32_t)sw * TD_SUB;
+      if (j0 < len) {
+        const uint32_t j1 = min(len, j0 + TD_SUB);
+        St8            af = sw ? ck[sw ? sw - 1 : 0] : a0;
+#pragma unroll
+        for (uint32_t jj = 0; jj < TD_SUB; jj++) {
+          const uint32_t j = j0 + jj;
+          if (j < j1) {
+            alpha_s[(jj * 2 + 0) * nthreads + tid] = make_uint4(af.s[0], af.s[1], af.s[2], af.s[3]);
+            alpha_s[(jj * 2 + 1) * nthreads + tid] = make_uint4(af.s[4], af.s[5], af.s[6], af.s[7]);
+            const uint2 g = g_s[j * nthreads + tid];
+            alpha_step(af, g.x, g.y, vneg(g.x), vneg(g.y));
+            if ((j & 3u) == 3u) norm8(af);
+          }
+        }
+#pragma unroll
+        for (int jj = TD_SUB - 1; jj >= 0; jj--) {
+          const uint32_t j = j0 + (uint32_t)jj;
+          if (j < j1) {
+            const uint2 g  = g_s[j * nthreads + tid];
+            const uint4 u0 = alpha_s[(jj * 2 + 0) * nthreads + tid], u1 = alpha_s[(jj * 2 + 1) * nthreads + tid];
+            St8         al;
+            al.s[0] = u0.x, al.s[1] = u0.y, al.s[2] = u0.z, al.s[3] = u0.w, al.s[4] = u1.x, al.s[5] = u1.y, al.s[6] = u1.z, al.s[7] = u1.w;
+            uint32_t m1, m0;
+            beta_llr_step(b, al, g.x, g.y, vneg(g.x), vneg(g.y), m1, m0);
+            if ((j & 3u) == 0u) norm8(b);
+            // xa = (g0 + g1) / 2 exactly, per half
+            const int xal = (lo_s(g.x) + lo_s(g.y)) >> 1, xah = (hi_s(g.x) + hi_s(g.y)) >> 1;
+            const int Ll = lo_s(m1) - lo_s(m0), Lh = hi_s(m1) - hi_s(m0);
+            out[pos_s[j * nthreads + tid]] = pk2(ext_of(Ll, xal), ext_of(Lh, xah));
+            if (IL) {
+              const uint32_t ps = pos_s[j * nthreads + tid];
+              const uint32_t pi = (ps % NW) * 32u + ps / NW; // natural bit index back from the transposed position
+              if (Ll > 0) atomicOr(&bits_s[pi >> 5], 0x80000000u >> (pi & 31u));
+              if (Lh > 0) atomicOr(&bits_s[(TD_WL * 6) + (pi >> 5)], 0x80000000u >> (pi & 31u));
+            }
+          }
         }
       }
     }
@@ -193,13 +212,15 @@ __device__ __forceinline__ uint32_t gf_mod24(uint32_t v, uint32_t nbits, uint32_
   return r;
 }
 
-__global__ void __launch_bounds__(192) turbo_kernel(const DevPair* __restrict__ pairs, uint32_t* __restrict__ pool, const uint16_t* __restrict__ pi_pool,
+__global__ void __launch_bounds__(192, 2) turbo_kernel(const DevPair* __restrict__ pairs, uint32_t* __restrict__ pool, const uint16_t* __restrict__ pi_pool,
                                                     const uint32_t* __restrict__ pi_off, const uint32_t* __restrict__ xpowA,
                                                     const uint32_t* __restrict__ xpowB, uint8_t* __restrict__ payload, uint8_t* __restrict__ cb_iters,
                                                     uint8_t* __restrict__ cb_crc, uint32_t max_iter)
 {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  uint4*             alpha_s = reinterpret_cast<uint4*>(smem_raw); // [TD_HALF][2][nthreads]
+  uint4*             alpha_s = reinterpret_cast<uint4*>(smem_raw);                               // [TD_SUB][2][nthreads]
+  uint2*             g_s     = reinterpret_cast<uint2*>(alpha_s + TD_SUB * 2 * blockDim.x);       // [TD_WL][nthreads]
+  uint16_t*          pos_s   = reinterpret_cast<uint16_t*>(g_s + TD_WL * blockDim.x);             // [TD_WL][nthreads]
   __shared__ uint32_t bits_s[2 * TD_WL * 6];                       // 2 x 6144 bits
   __shared__ uint32_t btail[2][8];
   __shared__ uint32_t red_s[8];
@@ -219,7 +240,7 @@ __global__ void __launch_bounds__(192) turbo_kernel(const DevPair* __restrict__ 
   tv.piT   = pi_pool + pi_off[blockIdx.x];
   tv.K = K, tv.NW = NW;
 
-  // boundary metrics start "unknown" (all zero); apr starts at zero (buffers are cleared by the host)
+  // boundary metrics start "unknown" (all zero); the a-priori input of the very first half iteration is zero
   for (uint32_t i = tid; i < 4 * NW * 8; i += nthreads) tv.bnd[i] = 0u;
   if (tid < 2) done_s[tid] = (tid < P.ncb) ? 0u : 1u;
   if (tid == 0) {
@@ -266,8 +287,8 @@ __global__ void __launch_bounds__(192) turbo_kernel(const DevPair* __restrict__ 
   uint32_t it = 0;
   while (it < max_iter) {
     for (uint32_t i = tid; i < 2 * TD_WL * 6; i += nthreads) bits_s[i] = 0u;
-    siso_pass<false>(tv, alpha_s, bits_s, tid, nthreads, active, btail[0]);
-    siso_pass<true>(tv, alpha_s, bits_s, tid, nthreads, active, btail[1]);
+    siso_pass<false>(tv, alpha_s, g_s, pos_s, bits_s, tid, nthreads, active, btail[0], it == 0);
+    siso_pass<true>(tv, alpha_s, g_s, pos_s, bits_s, tid, nthreads, active, btail[1], false);
     it++;
     // ---- CRC over the K decided bits of each code block -------------------------------------------
     bool all_done = true;
@@ -359,7 +380,7 @@ extern "C" void launch_turbo(const DevPair* pairs, uint32_t npairs, uint32_t max
   if (!npairs) return;
   uint32_t nthreads = ((max_threads + 31) / 32) * 32;
   if (nthreads < 32) nthreads = 32;
-  const size_t smem = (size_t)TD_HALF * 2 * nthreads * sizeof(uint4);
+  const size_t smem = (size_t)nthreads * (TD_SUB * 2 * sizeof(uint4) + TD_WL * sizeof(uint2) + TD_WL * sizeof(uint16_t));
   static bool  attr_set = false;
   if (!attr_set) {
     cudaFuncSetAttribute(turbo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024);

@@ -317,14 +317,15 @@ RmTurboTable rm_turbo_table(uint32_t K, uint32_t F, uint32_t rv)
     if (y2 >= ND) w[Kpi + 2 * k + 1] = 2 * D + y2 - ND;
   }
   RmTurboTable t;
-  t.first.assign(3 * D, 0xFFFFFFFFu);
+  t.order.reserve(Kw);
   const uint32_t k0 = R * (2 * ((Kw + 8 * R - 1) / (8 * R)) * rv + 2);
   for (uint32_t j = 0; j < Kw; j++) {
     uint32_t s = w[(k0 + j) % Kw];
     if (s == 0xFFFFFFFFu) continue;
     if (s / D < 2 && s % D < F) continue; // filler bits are <NULL> in d0/d1
-    t.first[s] = t.nn++;
+    t.order.push_back(s);
   }
+  t.nn = (uint32_t)t.order.size();
   return t;
 }
 

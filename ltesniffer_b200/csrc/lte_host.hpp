@@ -73,11 +73,11 @@ struct Segm {
 bool     cb_segmentation(uint32_t tbs, Segm& s);
 bool     qpp_params(uint32_t K, uint32_t& f1, uint32_t& f2);
 uint32_t rm_turbo_E(uint32_t G, uint32_t C, uint32_t r, uint32_t Qm, uint32_t NL);
-// For every stream position t in [0, 3*(K+4)): index of the first received soft bit that lands on it
-// (0xFFFFFFFF if punctured / <NULL>), and nn = number of transmittable positions (the repeat period).
+// order[k], k in [0, nn): the stream position (s*(K+4)+i) that receives soft bit k, k+nn, k+2nn, ...
+// nn = number of transmittable circular-buffer positions (the repeat period).
 struct RmTurboTable {
   uint32_t              nn = 0;
-  std::vector<uint32_t> first; // [3*(K+4)]
+  std::vector<uint32_t> order; // [nn]
 };
 RmTurboTable rm_turbo_table(uint32_t K, uint32_t F, uint32_t rv);
 

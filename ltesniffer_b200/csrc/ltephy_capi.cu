@@ -274,16 +274,22 @@ extern "C" int ltephy_create(const ltephy_cfg_t* cfg, ltephy_t** out)
     h->d_xpowA = upload(h, xa.data(), xa.size());
     h->d_xpowB = upload(h, xb.data(), xb.size());
   }
-  { // data-RE count per (subframe class, cfi, symbol, prb)
+  { // data-RE count and 12-bit mask per (subframe class, cfi, symbol, prb)
     const uint32_t N = c.nof_prb;
     h->re_cnt.resize((size_t)3 * 3 * 14 * N);
-    const uint32_t cls_sf[3] = {0, 5, 1};
-    uint16_t       kk[12];
+    std::vector<uint16_t> masks((size_t)3 * 3 * 14 * N, 0);
+    const uint32_t        cls_sf[3] = {0, 5, 1};
+    uint16_t              kk[12];
     for (uint32_t cls = 0; cls < 3; cls++)
       for (uint32_t cfi = 1; cfi <= 3; cfi++)
         for (uint32_t l = 0; l < 14; l++)
-          for (uint32_t prb = 0; prb < N; prb++)
-            h->re_cnt[((cls * 3 + (cfi - 1)) * 14 + l) * N + prb] = (uint8_t)ltehost::pdsch_re_in_prb(h->cell, cls_sf[cls], cfi, l, prb, kk);
+          for (uint32_t prb = 0; prb < N; prb++) {
+            const size_t   idx = ((cls * 3 + (cfi - 1)) * 14 + l) * N + prb;
+            const uint32_t n   = ltehost::pdsch_re_in_prb(h->cell, cls_sf[cls], cfi, l, prb, kk);
+            h->re_cnt[idx]     = (uint8_t)n;
+            for (uint32_t i = 0; i < n; i++) masks[idx] |= (uint16_t)(1u << (kk[i] - 12 * prb));
+          }
+    c.re_mask = upload(h, masks.data(), masks.size());
   }
   const size_t S = cfg->max_subframes, g = (size_t)14 * c.nsc;
   if (h->d_iq.reserve(S * c.nof_rx * c.sf_len) || h->d_sym.reserve(S * c.nof_rx * g) || h->d_ce.reserve(S * c.nof_ports * c.nof_rx * g) ||
@@ -432,16 +438,23 @@ static int rm_table_for(ltephy* h, uint32_t K, uint32_t F, uint32_t rv, uint32_t
     return 0;
   }
   auto t = ltehost::rm_turbo_table(K, F, rv);
-  if (h->rm_used + t.first.size() > h->d_rm.cap) { // cache full: start over (tables already queued stay valid until the stream drains)
+  { // stream position -> word index inside the pair buffer (window-transposed streams, then the 12 tail words)
+    const uint32_t D = K + 4, NW = (K + 31) / 32;
+    for (auto& v : t.order) {
+      const uint32_t st = v / D, i = v % D;
+      v = i < K ? st * 32 * NW + (i & 31u) * NW + (i >> 5) : 5 * 32 * NW + st * 4 + (i - K);
+    }
+  }
+  if (h->rm_used + t.order.size() > h->d_rm.cap) { // cache full: start over (tables already queued stay valid until the stream drains)
     cudaStreamSynchronize(h->stream);
     h->rm_cache.clear();
     memset(h->rm_fast, 0xFF, sizeof(h->rm_fast));
     h->rm_used = 0;
   }
   off = (uint32_t)h->rm_used, nn = t.nn;
-  if (cudaMemcpyAsync(h->d_rm.p + off, t.first.data(), t.first.size() * 4, cudaMemcpyHostToDevice, h->stream) != cudaSuccess) return -1;
+  if (cudaMemcpyAsync(h->d_rm.p + off, t.order.data(), t.order.size() * 4, cudaMemcpyHostToDevice, h->stream) != cudaSuccess) return -1;
   cudaStreamSynchronize(h->stream); // source vector dies at scope exit
-  h->rm_used += t.first.size();
+  h->rm_used += t.order.size();
   h->rm_cache[key] = {off, nn};
   if (F == 0 && rv < 4 && ki >= 0) h->rm_fast[ki][rv] = off, h->rm_fast_nn[ki][rv] = nn;
   return 0;
@@ -511,6 +524,9 @@ static int build_jobs(ltephy* h, const ltephy_grant_t* gin, uint32_t n, size_t& 
       const uint8_t* cl = cnt + l * N;
       for (uint32_t i = 0; i < pn[l / 7]; i++) acc += cl[pl[i]];
     }
+    d.cls = cls, d.np[0] = pn[0], d.np[1] = pn[1];
+    memcpy(d.plist[0], plist[0], pn[0]);
+    memcpy(d.plist[1], plist[1], pn[1]);
     d.re_off[14] = acc;
     d.nof_re     = acc;
     if (acc != g.nof_re) return fail(LTEPHY_ERROR_INVALID_INPUTS, "grant %u: nof_re %u does not match the PRB mask (%u)", gi, g.nof_re, acc);
@@ -530,7 +546,7 @@ static int build_jobs(ltephy* h, const ltephy_grant_t* gin, uint32_t n, size_t& 
       const uint32_t w = (G + 31) / 32;
       if (w > h->gold_words) return fail(LTEPHY_ERROR, "grant %u: codeword longer than the scrambling basis", gi);
       max_scr_words = std::max(max_scr_words, w);
-      seq_words += w;
+      seq_words += w + 1; // +1: the demapper reads a 64-bit window
       h->pllr_elems += (G + 7) & ~7u;
       if (g.tb[t].tbs > 0) {
         const uint32_t tbs = (uint32_t)g.tb[t].tbs;
@@ -651,7 +667,6 @@ extern "C" int ltephy_submit_grants(ltephy_t* h, const ltephy_grant_t* gin, uint
   if (n) {
     CU(cudaMemcpyAsync(h->d_grants.p, h->grants.data(), n * sizeof(DevGrant), cudaMemcpyHostToDevice, h->stream));
     if (!h->tbs.empty()) CU(cudaMemcpyAsync(h->d_tbs.p, h->tbs.data(), h->tbs.size() * sizeof(DevTb), cudaMemcpyHostToDevice, h->stream));
-    if (turbo_words) CU(cudaMemsetAsync(h->d_turbo.p, 0, turbo_words * 4, h->stream));
     launch_pdsch_front(h->dc, h->d_grants.p, n, max_scr_words, h->d_sym.p, h->d_ce.p, h->d_gold_x1, h->d_gold_basis, h->gold_words, h->d_seq.p,
                        h->d_pllr.p, h->stream, &h->launches);
     if (!h->cbs.empty()) {
