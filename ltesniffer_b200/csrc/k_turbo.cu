@@ -80,16 +80,18 @@ struct TurboView {
 };
 
 #define TD_SUB 8 // alpha is kept in shared memory for TD_SUB steps at a time
+#define TD_NSUB (TD_WL / TD_SUB)
 
-// one SISO pass for window w.  IL = second constituent decoder (interleaved order).
+// one SISO pass for window w.  IL = second constituent decoder (interleaved order); NT = threads per CTA
+// (compile time, so every shared-memory access is base + immediate); FULL = every window has 32 steps.
 // Shared memory per thread: g_s[32] (branch metrics g0 = xa+p, g1 = xa-p, staged once per pass with all the
 // global loads in flight together), pos_s[32] (where the extrinsic goes), alpha_s[TD_SUB][2] (uint4).
-template <bool IL>
-__device__ __forceinline__ void siso_pass(const TurboView& tv, uint4* alpha_s, uint2* g_s, uint16_t* pos_s, uint32_t* bits_s, uint32_t w,
-                                          uint32_t nthreads, bool active, const uint32_t* btail, bool first_iter)
+template <bool IL, int NT, bool FULL>
+__device__ __forceinline__ void siso_pass(const TurboView& tv, uint4* __restrict__ alpha_t, uint2* __restrict__ g_t, uint16_t* __restrict__ pos_t,
+                                          uint32_t* bits_s, uint32_t w, bool active, const uint32_t* btail, bool first_iter)
 {
-  const uint32_t  K = tv.K, NW = tv.NW, tid = threadIdx.x;
-  const uint32_t  k0 = w * TD_WL, len = active ? min((uint32_t)TD_WL, K - k0) : 0;
+  const uint32_t  K = tv.K, NW = tv.NW;
+  const uint32_t  len = FULL ? (uint32_t)TD_WL : (active ? min((uint32_t)TD_WL, K - w * TD_WL) : 0u);
   uint32_t*       A  = tv.bnd + (size_t)(IL ? 2 : 0) * NW * 8;
   uint32_t*       B  = A + (size_t)NW * 8;
   const uint32_t* par = IL ? tv.p2T : tv.p1T;
@@ -105,32 +107,38 @@ __device__ __forceinline__ void siso_pass(const TurboView& tv, uint4* alpha_s, u
     }
     // ---- stage the window: every load of the pass is issued here, independent of the recursions ----
 #pragma unroll 8
-    for (uint32_t j = 0; j < len; j++) {
-      uint32_t pos;
-      if (!IL)
-        pos = j * NW + w;
-      else {
-        const uint32_t pi = tv.piT[j * NW + w];
-        pos               = (pi & 31u) * NW + (pi >> 5);
+    for (uint32_t j = 0; j < TD_WL; j++) {
+      if (FULL || j < len) {
+        uint32_t pos;
+        if (!IL)
+          pos = j * NW + w;
+        else {
+          const uint32_t pi = tv.piT[j * NW + w];
+          pos               = (pi & 31u) * NW + (pi >> 5);
+        }
+        const uint32_t sy = tv.sysT[pos], ap = (!IL && first_iter) ? 0u : apr[pos], p = par[j * NW + w];
+        const uint32_t xa = vadd(sy, ap);
+        g_t[j * NT]       = make_uint2(vadd(xa, p), vadd(xa, vneg(p)));
+        pos_t[j * NT]     = (uint16_t)pos;
       }
-      const uint32_t sy = tv.sysT[pos], ap = (!IL && first_iter) ? 0u : apr[pos], p = par[j * NW + w];
-      const uint32_t xa = vadd(sy, ap);
-      g_s[j * nthreads + tid]   = make_uint2(vadd(xa, p), vadd(xa, vneg(p)));
-      pos_s[j * nthreads + tid] = (uint16_t)pos;
     }
   }
   __syncthreads(); // every window has read its boundaries (and inputs) before anybody overwrites them
 
   if (active) {
-    // ---- forward over the whole window, remembering alpha at every TD_SUB-th step -------------------
-    St8 a = a0, ck[TD_WL / TD_SUB - 1];
+    // ---- forward over the whole window, remembering alpha at the start of every sub-window ----------
+    St8 a = a0, ck[TD_NSUB];
+#pragma unroll 1
+    for (uint32_t sw = 0; sw < TD_NSUB; sw++) {
+      ck[sw] = a;
 #pragma unroll
-    for (uint32_t j = 0; j < TD_WL; j++) {
-      if (j < len) {
-        if (j > 0 && (j % TD_SUB) == 0) ck[j / TD_SUB - 1] = a;
-        const uint2 g = g_s[j * nthreads + tid];
-        alpha_step(a, g.x, g.y, vneg(g.x), vneg(g.y));
-        if ((j & 3u) == 3u) norm8(a);
+      for (uint32_t jj = 0; jj < TD_SUB; jj++) {
+        const uint32_t j = sw * TD_SUB + jj;
+        if (FULL || j < len) {
+          const uint2 g = g_t[j * NT];
+          alpha_step(a, g.x, g.y, vneg(g.x), vneg(g.y));
+          if ((jj & 3u) == 3u) norm8(a);
+        }
       }
     }
     norm8(a);
@@ -139,44 +147,44 @@ __device__ __forceinline__ void siso_pass(const TurboView& tv, uint4* alpha_s, u
       for (int s = 0; s < 8; s++) A[(size_t)(w + 1) * 8 + s] = a.s[s];
     }
     // ---- sub-windows, last first: forward with storage, then backward with LLR / extrinsic ----------
-#pragma unroll
-    for (int sw = TD_WL / TD_SUB - 1; sw >= 0; sw--) {
+#pragma unroll 1
+    for (int sw = TD_NSUB - 1; sw >= 0; sw--) {
       const uint32_t j0 = (uint32_t)sw * TD_SUB;
-      if (j0 < len) {
-        const uint32_t j1 = min(len, j0 + TD_SUB);
-        St8            af = sw ? ck[sw ? sw - 1 : 0] : a0;
+      if (!FULL && j0 >= len) continue;
+      St8 af = ck[sw];
 #pragma unroll
-        for (uint32_t jj = 0; jj < TD_SUB; jj++) {
-          const uint32_t j = j0 + jj;
-          if (j < j1) {
-            alpha_s[(jj * 2 + 0) * nthreads + tid] = make_uint4(af.s[0], af.s[1], af.s[2], af.s[3]);
-            alpha_s[(jj * 2 + 1) * nthreads + tid] = make_uint4(af.s[4], af.s[5], af.s[6], af.s[7]);
-            const uint2 g = g_s[j * nthreads + tid];
+      for (uint32_t jj = 0; jj < TD_SUB; jj++) {
+        const uint32_t j = j0 + jj;
+        if (FULL || j < len) {
+          alpha_t[(jj * 2 + 0) * NT] = make_uint4(af.s[0], af.s[1], af.s[2], af.s[3]);
+          alpha_t[(jj * 2 + 1) * NT] = make_uint4(af.s[4], af.s[5], af.s[6], af.s[7]);
+          if (jj + 1 < TD_SUB) {
+            const uint2 g = g_t[j * NT];
             alpha_step(af, g.x, g.y, vneg(g.x), vneg(g.y));
-            if ((j & 3u) == 3u) norm8(af);
+            if ((jj & 3u) == 3u) norm8(af);
           }
         }
-#pragma unroll
-        for (int jj = TD_SUB - 1; jj >= 0; jj--) {
-          const uint32_t j = j0 + (uint32_t)jj;
-          if (j < j1) {
-            const uint2 g  = g_s[j * nthreads + tid];
-            const uint4 u0 = alpha_s[(jj * 2 + 0) * nthreads + tid], u1 = alpha_s[(jj * 2 + 1) * nthreads + tid];
-            St8         al;
-            al.s[0] = u0.x, al.s[1] = u0.y, al.s[2] = u0.z, al.s[3] = u0.w, al.s[4] = u1.x, al.s[5] = u1.y, al.s[6] = u1.z, al.s[7] = u1.w;
-            uint32_t m1, m0;
-            beta_llr_step(b, al, g.x, g.y, vneg(g.x), vneg(g.y), m1, m0);
-            if ((j & 3u) == 0u) norm8(b);
-            // xa = (g0 + g1) / 2 exactly, per half
-            const int xal = (lo_s(g.x) + lo_s(g.y)) >> 1, xah = (hi_s(g.x) + hi_s(g.y)) >> 1;
-            const int Ll = lo_s(m1) - lo_s(m0), Lh = hi_s(m1) - hi_s(m0);
-            out[pos_s[j * nthreads + tid]] = pk2(ext_of(Ll, xal), ext_of(Lh, xah));
-            if (IL) {
-              const uint32_t ps = pos_s[j * nthreads + tid];
-              const uint32_t pi = (ps % NW) * 32u + ps / NW; // natural bit index back from the transposed position
-              if (Ll > 0) atomicOr(&bits_s[pi >> 5], 0x80000000u >> (pi & 31u));
-              if (Lh > 0) atomicOr(&bits_s[(TD_WL * 6) + (pi >> 5)], 0x80000000u >> (pi & 31u));
-            }
+      }
+#pragma unroll 4
+      for (int jj = TD_SUB - 1; jj >= 0; jj--) {
+        const uint32_t j = j0 + (uint32_t)jj;
+        if (FULL || j < len) {
+          const uint2 g  = g_t[j * NT];
+          const uint4 u0 = alpha_t[(jj * 2 + 0) * NT], u1 = alpha_t[(jj * 2 + 1) * NT];
+          St8         al;
+          al.s[0] = u0.x, al.s[1] = u0.y, al.s[2] = u0.z, al.s[3] = u0.w, al.s[4] = u1.x, al.s[5] = u1.y, al.s[6] = u1.z, al.s[7] = u1.w;
+          uint32_t m1, m0;
+          beta_llr_step(b, al, g.x, g.y, vneg(g.x), vneg(g.y), m1, m0);
+          if ((jj & 3) == 0) norm8(b);
+          // xa = (g0 + g1) / 2 exactly, per half
+          const int      xal = (lo_s(g.x) + lo_s(g.y)) >> 1, xah = (hi_s(g.x) + hi_s(g.y)) >> 1;
+          const int      Ll = lo_s(m1) - lo_s(m0), Lh = hi_s(m1) - hi_s(m0);
+          const uint32_t ps = pos_t[j * NT];
+          out[ps]           = pk2(ext_of(Ll, xal), ext_of(Lh, xah));
+          if (IL) {
+            const uint32_t pi = (ps % NW) * 32u + ps / NW; // natural bit index back from the transposed position
+            if (Ll > 0) atomicOr(&bits_s[pi >> 5], 0x80000000u >> (pi & 31u));
+            if (Lh > 0) atomicOr(&bits_s[(TD_WL * 6) + (pi >> 5)], 0x80000000u >> (pi & 31u));
           }
         }
       }
@@ -212,22 +220,23 @@ __device__ __forceinline__ uint32_t gf_mod24(uint32_t v, uint32_t nbits, uint32_
   return r;
 }
 
-__global__ void __launch_bounds__(192, 2) turbo_kernel(const DevPair* __restrict__ pairs, uint32_t* __restrict__ pool, const uint16_t* __restrict__ pi_pool,
+template <int NT, bool FULL>
+__global__ void __launch_bounds__(NT, (NT > 128 ? 2 : (NT > 64 ? 3 : 6))) turbo_kernel(const DevPair* __restrict__ pairs, uint32_t* __restrict__ pool, const uint16_t* __restrict__ pi_pool,
                                                     const uint32_t* __restrict__ pi_off, const uint32_t* __restrict__ xpowA,
                                                     const uint32_t* __restrict__ xpowB, uint8_t* __restrict__ payload, uint8_t* __restrict__ cb_iters,
                                                     uint8_t* __restrict__ cb_crc, uint32_t max_iter)
 {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  uint4*             alpha_s = reinterpret_cast<uint4*>(smem_raw);                               // [TD_SUB][2][nthreads]
-  uint2*             g_s     = reinterpret_cast<uint2*>(alpha_s + TD_SUB * 2 * blockDim.x);       // [TD_WL][nthreads]
-  uint16_t*          pos_s   = reinterpret_cast<uint16_t*>(g_s + TD_WL * blockDim.x);             // [TD_WL][nthreads]
+  uint4*             alpha_t = reinterpret_cast<uint4*>(smem_raw) + threadIdx.x;                          // [TD_SUB][2][NT]
+  uint2*             g_t     = reinterpret_cast<uint2*>(reinterpret_cast<uint4*>(smem_raw) + TD_SUB * 2 * NT) + threadIdx.x; // [TD_WL][NT]
+  uint16_t*          pos_t   = reinterpret_cast<uint16_t*>(reinterpret_cast<uint2*>(reinterpret_cast<uint4*>(smem_raw) + TD_SUB * 2 * NT) + TD_WL * NT) + threadIdx.x;
   __shared__ uint32_t bits_s[2 * TD_WL * 6];                       // 2 x 6144 bits
   __shared__ uint32_t btail[2][8];
   __shared__ uint32_t red_s[8];
   __shared__ uint32_t done_s[2];
 
   const DevPair  P = pairs[blockIdx.x];
-  const uint32_t K = P.K, NW = P.NW, tid = threadIdx.x, nthreads = blockDim.x;
+  const uint32_t K = P.K, NW = P.NW, tid = threadIdx.x, nthreads = NT;
   const bool     active = tid < NW;
   TurboView      tv;
   tv.sysT  = pool + P.buf_off;
@@ -287,8 +296,8 @@ __global__ void __launch_bounds__(192, 2) turbo_kernel(const DevPair* __restrict
   uint32_t it = 0;
   while (it < max_iter) {
     for (uint32_t i = tid; i < 2 * TD_WL * 6; i += nthreads) bits_s[i] = 0u;
-    siso_pass<false>(tv, alpha_s, g_s, pos_s, bits_s, tid, nthreads, active, btail[0], it == 0);
-    siso_pass<true>(tv, alpha_s, g_s, pos_s, bits_s, tid, nthreads, active, btail[1], false);
+    siso_pass<false, NT, FULL>(tv, alpha_t, g_t, pos_t, bits_s, tid, active, btail[0], it == 0);
+    siso_pass<true, NT, FULL>(tv, alpha_t, g_t, pos_t, bits_s, tid, active, btail[1], false);
     it++;
     // ---- CRC over the K decided bits of each code block -------------------------------------------
     bool all_done = true;
@@ -373,20 +382,41 @@ __global__ void __launch_bounds__(256) tb_crc_kernel(const DevTb* __restrict__ t
   }
 }
 
-extern "C" void launch_turbo(const DevPair* pairs, uint32_t npairs, uint32_t max_threads, uint32_t* pool, const uint16_t* pi_pool,
+template <int NT, bool FULL>
+static void launch_turbo_t(const DevPair* pairs, uint32_t npairs, uint32_t* pool, const uint16_t* pi_pool, const uint32_t* pi_off, const uint32_t* xpowA,
+                           const uint32_t* xpowB, uint8_t* payload, uint8_t* cb_iters, uint8_t* cb_crc, uint32_t max_iter, cudaStream_t st)
+{
+  const size_t smem = (size_t)NT * (TD_SUB * 2 * sizeof(uint4) + TD_WL * sizeof(uint2) + TD_WL * sizeof(uint16_t));
+  static bool  attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(turbo_kernel<NT, FULL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    attr_set = true;
+  }
+  turbo_kernel<NT, FULL><<<npairs, NT, smem, st>>>(pairs, pool, pi_pool, pi_off, xpowA, xpowB, payload, cb_iters, cb_crc, max_iter);
+}
+// all pairs of one launch share the CTA size class `max_threads` (32..192) and `full` (every K a multiple of 32)
+extern "C" void launch_turbo(const DevPair* pairs, uint32_t npairs, uint32_t max_threads, int full, uint32_t* pool, const uint16_t* pi_pool,
                              const uint32_t* pi_off, const uint32_t* xpowA, const uint32_t* xpowB, uint8_t* payload, uint8_t* cb_iters,
                              uint8_t* cb_crc, uint32_t max_iter, cudaStream_t st, uint64_t* launches)
 {
   if (!npairs) return;
-  uint32_t nthreads = ((max_threads + 31) / 32) * 32;
-  if (nthreads < 32) nthreads = 32;
-  const size_t smem = (size_t)nthreads * (TD_SUB * 2 * sizeof(uint4) + TD_WL * sizeof(uint2) + TD_WL * sizeof(uint16_t));
-  static bool  attr_set = false;
-  if (!attr_set) {
-    cudaFuncSetAttribute(turbo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024);
-    attr_set = true;
+  const uint32_t nt = ((max_threads + 31) / 32) * 32;
+#define TURBO_CASE(N)                                                                                                              \
+  case N:                                                                                                                          \
+    if (full)                                                                                                                      \
+      launch_turbo_t<N, true>(pairs, npairs, pool, pi_pool, pi_off, xpowA, xpowB, payload, cb_iters, cb_crc, max_iter, st);        \
+    else                                                                                                                           \
+      launch_turbo_t<N, false>(pairs, npairs, pool, pi_pool, pi_off, xpowA, xpowB, payload, cb_iters, cb_crc, max_iter, st);       \
+    break;
+  switch (nt) {
+    TURBO_CASE(32)
+    TURBO_CASE(64)
+    TURBO_CASE(96)
+    TURBO_CASE(128)
+    TURBO_CASE(160)
+    default: TURBO_CASE(192)
   }
-  turbo_kernel<<<npairs, nthreads, smem, st>>>(pairs, pool, pi_pool, pi_off, xpowA, xpowB, payload, cb_iters, cb_crc, max_iter);
+#undef TURBO_CASE
   *launches += 1;
 }
 extern "C" void launch_tb_crc(const DevTb* tbs, uint32_t ntb, const uint8_t* payload, const uint8_t* cb_crc, const uint8_t* cb_iters,

@@ -21,8 +21,8 @@ void launch_viterbi(const DevCell&, const float*, const DevSfInfo*, ltephy_cand_
 void launch_pdsch_front(const DevCell&, const DevGrant*, uint32_t, uint32_t, const float2*, const float2*, const uint32_t*, const uint32_t*, uint32_t,
                         uint32_t*, short*, cudaStream_t, uint64_t*);
 void launch_rm_turbo_rx(const DevCb*, uint32_t, const DevPair*, const short*, const uint32_t*, uint32_t*, cudaStream_t, uint64_t*);
-void launch_turbo(const DevPair*, uint32_t, uint32_t, uint32_t*, const uint16_t*, const uint32_t*, const uint32_t*, const uint32_t*, uint8_t*, uint8_t*,
-                  uint8_t*, uint32_t, cudaStream_t, uint64_t*);
+void launch_turbo(const DevPair*, uint32_t, uint32_t, int, uint32_t*, const uint16_t*, const uint32_t*, const uint32_t*, const uint32_t*, uint8_t*,
+                  uint8_t*, uint8_t*, uint32_t, cudaStream_t, uint64_t*);
 void launch_tb_crc(const DevTb*, uint32_t, const uint8_t*, const uint8_t*, const uint8_t*, const uint32_t*, ltephy_tb_result_t*, cudaStream_t,
                    uint64_t*);
 }
@@ -616,8 +616,8 @@ static int run_turbo_stage(ltephy* h, uint32_t max_iter)
   std::vector<uint32_t> order(h->pairs.size());
   for (uint32_t i = 0; i < order.size(); i++) order[i] = i;
   // (pairs were appended in arbitrary K order: bucket by rounded thread count)
-  std::map<uint32_t, std::vector<uint32_t>> buckets;
-  for (uint32_t i = 0; i < h->pairs.size(); i++) buckets[((h->pairs[i].NW + 31) / 32) * 32].push_back(i);
+  std::map<uint32_t, std::vector<uint32_t>> buckets; // key = 2 * threads + (ragged last window)
+  for (uint32_t i = 0; i < h->pairs.size(); i++) buckets[2 * (((h->pairs[i].NW + 31) / 32) * 32) + ((h->pairs[i].K & 31u) ? 1 : 0)].push_back(i);
   std::vector<DevPair>  sorted;
   std::vector<uint32_t> sorted_pi;
   std::vector<std::pair<uint32_t, uint32_t>> ranges; // (threads, count)
@@ -642,8 +642,8 @@ static int run_turbo_stage(ltephy* h, uint32_t max_iter)
   CU(cudaEventRecord(h->ev[4], h->stream));
   uint32_t first = 0;
   for (auto& r : ranges) {
-    launch_turbo(h->d_pairs.p + first, r.second, r.first, h->d_turbo.p, h->d_pi.p, h->d_pair_pi_off.p + first, h->d_xpowA, h->d_xpowB,
-                 h->d_payload.p, h->d_cb_iters.p, h->d_cb_crc.p, max_iter, h->stream, &h->launches);
+    launch_turbo(h->d_pairs.p + first, r.second, r.first / 2, (r.first & 1u) == 0, h->d_turbo.p, h->d_pi.p, h->d_pair_pi_off.p + first, h->d_xpowA,
+                 h->d_xpowB, h->d_payload.p, h->d_cb_iters.p, h->d_cb_crc.p, max_iter, h->stream, &h->launches);
     first += r.second;
   }
   CU(cudaEventRecord(h->ev[5], h->stream));
@@ -773,8 +773,8 @@ extern "C" int ltephy_turbo_batch(ltephy_t* h, const int16_t* d, uint32_t K, uin
   CU(cudaMemcpyAsync(h->d_pairs.p, h->pairs.data(), npairs * sizeof(DevPair), cudaMemcpyHostToDevice, h->stream));
   CU(cudaMemcpyAsync(h->d_pair_pi_off.p, h->pair_pi_off.data(), npairs * 4, cudaMemcpyHostToDevice, h->stream));
   CU(cudaEventRecord(h->ev[4], h->stream));
-  launch_turbo(h->d_pairs.p, npairs, NW, h->d_turbo.p, h->d_pi.p, h->d_pair_pi_off.p, h->d_xpowA, h->d_xpowB, h->d_payload.p, h->d_cb_iters.p,
-               h->d_cb_crc.p, max_iter ? max_iter : 1, h->stream, &h->launches);
+  launch_turbo(h->d_pairs.p, npairs, NW, (K & 31u) == 0, h->d_turbo.p, h->d_pi.p, h->d_pair_pi_off.p, h->d_xpowA, h->d_xpowB, h->d_payload.p,
+               h->d_cb_iters.p, h->d_cb_crc.p, max_iter ? max_iter : 1, h->stream, &h->launches);
   CU(cudaEventRecord(h->ev[5], h->stream));
   std::vector<uint8_t> packed((size_t)ncb * out_bytes), it(ncb), ok(ncb);
   CU(cudaMemcpyAsync(packed.data(), h->d_payload.p, packed.size(), cudaMemcpyDeviceToHost, h->stream));
