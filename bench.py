@@ -212,7 +212,7 @@ def main():
     tti = (np.arange(B, dtype=np.uint32) * world + rank).astype(np.uint32)
     tti_local = (np.arange(B, dtype=np.uint32) % len(iq_u)).astype(np.uint32)  # the tti each subframe was generated for
 
-    T = 1 if world > 1 else max(1, args.pipelines)
+    T = 3 if world > 1 else max(1, args.pipelines)
     phys = [capi.LtePhy(cell.nof_prb, cell.nof_ports, cell.cell_id, cell.nof_rx, max_subframes=B, turbo_max_iter=8, device=local,
                         flags=capi.FLAG_SKIP_LOW_POWER) for _ in range(T)]
     phy = phys[0]
@@ -264,45 +264,53 @@ def main():
     def step_single(device_resident):
         run_steps(1, device_resident)
 
-    # ---- sharded step (N > 1): phase A local, all-gather of the candidate tables, walk over ALL subframes in
-    # global order on every rank, phase B for the owned subframes, one gather of the decoded TBs to rank 0.
+    # ---- sharded operation (N > 1): subframe g -> GPU g mod N.  Phase A local; candidate tables all-gathered and
+    # re-interleaved into global order; the walk is replayed over ALL subframes on every rank (its RNTI history is
+    # sequential by nature); phase B for the owned subframes; one gather of the decoded TBs to rank 0.
+    # Software pipeline over 3 handles in ONE thread (one communicator): A(k+1) and B(k-1) run while the host walks k.
     if world > 1:
-        info_all = (capi.SfInfo * (B * world))()
-        g_info = [torch.empty(B * C.sizeof(capi.SfInfo), dtype=torch.uint8, device="cuda") for _ in range(world)]
-        g_cand = [torch.empty(B * capi.MAX_LOC * capi.MAX_SIZES * 16, dtype=torch.uint8, device="cuda") for _ in range(world)]
-        cands_all = torch.empty((B * world, capi.MAX_LOC, capi.MAX_SIZES, 16), dtype=torch.uint8, pin_memory=True)
-        grants = (capi.Grant * (24 * B))()
-        grant_dci = np.zeros(24 * B, np.uint32)
-        ng = C.c_uint32(0)
-        res = (capi.TbResult * (2 * 24 * B))()
-        gather_sz = B * 16000
+        from ltesniffer_b200 import shard
+        gather_sz = B * 20000
         out_local = torch.zeros(gather_sz, dtype=torch.uint8, device="cuda")
         out_all = [torch.zeros(gather_sz, dtype=torch.uint8, device="cuda") for _ in range(world)] if rank == 0 else None
+        res = [(capi.TbResult * (2 * 24 * B))() for _ in range(T)]
+        ngr = [0] * T
+
+    def sh_submit_a(t, device_resident):
+        if device_resident:
+            phys[t]._chk(L.ltephy_submit_iq_device(phys[t].h, p(iq_dev), tti_c.ctypes.data_as(C.c_void_p), B), "submit_iq_device")
+        else:
+            phys[t]._chk(L.ltephy_submit_iq(phys[t].h, p(iq_pin), tti_c.ctypes.data_as(C.c_void_p), B), "submit_iq")
+        phys[t].n = B
+
+    def sh_finish_b(t):
+        phys[t]._chk(L.ltephy_get_phase_b(phys[t].h, res[t], p(scr[t].payload), scr[t].payload.numel()), "get_phase_b")
+        nby = sum(res[t][i].payload_len for i in range(2 * ngr[t]))
+        n = min(nby, gather_sz)
+        out_local[:n].copy_(scr[t].payload[:n], non_blocking=True)
+        dist.gather(out_local, out_all, dst=0)   # the single gather of decoded transport blocks
+
+    def run_sharded(nsteps, device_resident):
+        sh_submit_a(0, device_resident)
+        pending = None
+        for k in range(nsteps):
+            t = k % T
+            if k + 1 < nsteps:
+                sh_submit_a((k + 1) % T, device_resident)
+            S = scr[t]
+            phys[t]._chk(L.ltephy_get_phase_a(phys[t].h, S.info, p(S.cands)), "get_phase_a")
+            info_all, cands_all = shard.gather_tables(S.info, S.cands, world, "cuda")
+            d, grants, gidx, ng = shard.search_and_select(L, srch, info_all, cands_all, world, rank, max_dcis, 24 * B)
+            nd.value = len(d)
+            if pending is not None:
+                sh_finish_b(pending)
+            phys[t]._chk(L.ltephy_submit_grants(phys[t].h, grants, ng), "submit_grants")
+            ngr[t] = ng
+            pending = t
+        sh_finish_b(pending)
 
     def step_sharded(device_resident):
-        if device_resident:
-            phy._chk(L.ltephy_submit_iq_device(phy.h, p(iq_dev), tti_c.ctypes.data_as(C.c_void_p), B), "submit_iq_device")
-        else:
-            phy._chk(L.ltephy_submit_iq(phy.h, p(iq_pin), tti_c.ctypes.data_as(C.c_void_p), B), "submit_iq")
-        phy.n = B
-        phy._chk(L.ltephy_get_phase_a(phy.h, info, p(cands)), "get_phase_a")
-        li = torch.frombuffer(info, dtype=torch.uint8).cuda(non_blocking=True)
-        lc = cands.view(-1).cuda(non_blocking=True)
-        dist.all_gather(g_info, li)
-        dist.all_gather(g_cand, lc)
-        # interleave: global subframe g = i * world + r
-        ia = torch.stack(g_info).view(world, B, -1).transpose(0, 1).contiguous().cpu().numpy()
-        C.memmove(info_all, ia.ctypes.data, ia.nbytes)
-        cands_all.copy_(torch.stack(g_cand).view(world, B, capi.MAX_LOC, capi.MAX_SIZES, 16).transpose(0, 1).reshape(B * world, capi.MAX_LOC, capi.MAX_SIZES, 16))
-        torch.cuda.current_stream().synchronize()
-        phy._chk(L.ltephy_search_batch(srch.h, info_all, p(cands_all), B * world, dcis.ctypes.data_as(C.c_void_p), max_dcis, C.byref(nd)), "search_batch")
-        phy._chk(L.ltephy_grants_from_dcis(srch.h, info_all, dcis.ctypes.data_as(C.c_void_p), nd.value, world, rank, grants,
-                                           grant_dci.ctypes.data_as(C.c_void_p), 24 * B, C.byref(ng)), "grants_from_dcis")
-        phy._chk(L.ltephy_submit_grants(phy.h, grants, ng.value), "submit_grants")
-        phy._chk(L.ltephy_get_phase_b(phy.h, res, p(payload), payload.numel()), "get_phase_b")
-        nby = sum(res[i].payload_len for i in range(2 * ng.value))
-        out_local[:min(nby, gather_sz)].copy_(payload[:min(nby, gather_sz)], non_blocking=True)
-        dist.gather(out_local, out_all, dst=0)   # the single gather of decoded transport blocks
+        run_sharded(1, device_resident)
 
     step = step_sharded if world > 1 else step_single
 
@@ -315,7 +323,7 @@ def main():
     # ---------------- warm-up ----------------
     for _ in range(max(3, args.warmup)):
         if world > 1:
-            step(True)
+            run_sharded(T, True)
         else:
             run_steps(T, True)
     barrier()
@@ -330,8 +338,7 @@ def main():
         ph.mark(0)
     t0 = time.perf_counter()
     if world > 1:
-        for _ in range(args.steps):
-            step(True)
+        run_sharded(args.steps, True)
     else:
         run_steps(args.steps, True)
     for ph in phys:
@@ -356,15 +363,13 @@ def main():
     tbytes, ncb, info_bits = phy.turbo_work()
     # ---------------- e2e: host IQ through the C-ABI ----------------
     if world > 1:
-        for _ in range(2):
-            step(False)
+        run_sharded(T, False)
     else:
         run_steps(2 * T, False)
     barrier()
     t0 = time.perf_counter()
     if world > 1:
-        for _ in range(args.steps):
-            step(False)
+        run_sharded(args.steps, False)
     else:
         run_steps(args.steps, False)
     barrier()

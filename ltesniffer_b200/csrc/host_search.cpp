@@ -41,6 +41,29 @@ struct RntiManager {
       count[v]++;
       if (++cur == HIST_DEPTH) ready = true, cur = 0;
     }
+    // n consecutive add(0): the padding RNTIManager::stepTime appends every subframe (RNTIManager.cc:425-432)
+    inline void add_zeros(uint32_t n)
+    {
+      while (n) {
+        const uint32_t chunk = std::min(n, HIST_DEPTH - cur);
+        if (ready) {
+          uint32_t nz = 0;
+          for (uint32_t i = 0; i < chunk; i++) {
+            const uint16_t old = ring[cur + i];
+            if (old)
+              count[old]--;
+            else
+              nz++;
+          }
+          count[0] = (uint16_t)(count[0] + chunk - nz);
+        } else
+          count[0] = (uint16_t)(count[0] + chunk);
+        memset(&ring[cur], 0, chunk * sizeof(uint16_t));
+        cur += chunk;
+        n -= chunk;
+        if (cur == HIST_DEPTH) ready = true, cur = 0;
+      }
+    }
   };
   struct Interval {
     uint16_t a, b;
@@ -118,7 +141,7 @@ struct RntiManager {
   void step_time()
   {
     for (int i = 0; i < NF; i++) {
-      for (int32_t k = 0; k < remaining[i]; k++) hist[i].add(0);
+      if (remaining[i] > 0) hist[i].add_zeros((uint32_t)remaining[i]);
       remaining[i] = (int32_t)PER_SF;
     }
     timestamp++;

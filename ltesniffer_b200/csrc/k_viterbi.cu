@@ -15,9 +15,8 @@
 struct __align__(16) VitWarpSmem {
   float    rm[2][3 * VIT_KMAX]; // dematched soft bits, stream-major
   uint32_t R[3][VIT_KMAX];      // quantised symbols 2q-255, packed (cand0 lo, cand1 hi)
-  uint32_t S[VIT_KMAX][4];      // branch metrics for output patterns (1,o1,o2), packed
+  uint32_t S[VIT_KMAX][8];      // branch metrics for the 8 output sign patterns (o0 o1 o2), packed; S[k][p ^ 7] = -S[k][p]
   uint4    dec[2 * VIT_KMAX];   // survivor decisions of steps K..3K-1: {c0 even, c0 odd, c1 even, c1 odd}
-  uint32_t data[2][3];          // decoded K bits per candidate
 };
 
 __device__ __forceinline__ uint32_t pk(int lo, int hi) { return ((uint32_t)lo & 0xFFFFu) | ((uint32_t)hi << 16); }
@@ -85,57 +84,69 @@ __global__ void __launch_bounds__(VIT_WARPS * 32) dci_viterbi_kernel(const __gri
     }
     return;
   }
-  // branch-metric table: patterns (o0,o1,o2) = (1,0,0),(1,0,1),(1,1,0),(1,1,1); bm = sum (o ? +r : -r)
+  // branch-metric table for all 8 output patterns p = o0*4 + o1*2 + o2: bm = sum_i (o_i ? +r_i : -r_i)
   for (uint32_t k = lane; k < K; k += 32) {
     const uint32_t r0 = sm.R[0][k], r1 = sm.R[1][k], r2 = sm.R[2][k];
-    const uint32_t n1 = __vneg2(r1), n2 = __vneg2(r2);
-    sm.S[k][0] = __vadd2(__vadd2(r0, n1), n2);
-    sm.S[k][1] = __vadd2(__vadd2(r0, n1), r2);
-    sm.S[k][2] = __vadd2(__vadd2(r0, r1), n2);
-    sm.S[k][3] = __vadd2(__vadd2(r0, r1), r2);
+    const uint32_t n0 = __vneg2(r0), n1 = __vneg2(r1), n2 = __vneg2(r2);
+#pragma unroll
+    for (uint32_t pat = 0; pat < 8; pat++)
+      sm.S[k][pat] = __vadd2(__vadd2((pat & 4u) ? r0 : n0, (pat & 2u) ? r1 : n1), (pat & 1u) ? r2 : n2);
   }
   __syncwarp();
 
   // ---- per-lane constants: lane j owns old states j and j+32, produces new states 2j and 2j+1 ------
   // state bit i = c_{k-1-i}; outputs for (state j < 32, input 0): parity(j & mask); polys 133,171,165
   const uint32_t o0 = __popc(lane & 0x36u) & 1u, o1 = __popc(lane & 0x27u) & 1u, o2 = __popc(lane & 0x2Bu) & 1u;
-  const uint32_t sidx = o0 ? (o1 * 2 + o2) : ((o1 ^ 1u) * 2 + (o2 ^ 1u));
-  const bool     sneg = !o0; // m = bm(j, input 0) = o0 ? S[sidx] : -S[sidx]
-  const uint32_t odd  = lane & 1u, lo_half = lane < 16;
+  const uint32_t pat = o0 * 4 + o1 * 2 + o2; // m = bm(j, input 0) = S[k][pat], -m = S[k][pat ^ 7]
+  const uint32_t odd = lane & 1u, lo_half = lane < 16;
   const uint32_t src1 = odd ? 16 + (lane >> 1) : (lane >> 1);
   const uint32_t src2 = odd ? (lane >> 1) : 16 + (lane >> 1);
+  const uint32_t* Sp = &sm.S[0][pat];
+  const uint32_t* Sn = &sm.S[0][pat ^ 7u];
 
   uint32_t X0 = 0, X1 = 0; // packed path metrics of states j and j+32
-  for (uint32_t t = 0; t < n3; t++) {
-    const uint32_t k  = t < K ? t : (t < 2 * K ? t - K : t - 2 * K);
-    uint32_t       m  = sm.S[k][sidx];
-    uint32_t       mn = __vneg2(m);
-    if (sneg) {
-      const uint32_t tmp = m;
-      m = mn, mn = tmp;
-    }
+  // one trellis step; STORE: keep the survivor decisions of this step
+  auto step = [&](uint32_t k, uint4* dst, bool store) {
+    const uint32_t m = Sp[k * 8], mn = Sn[k * 8];
     // new 2j   (input 0): max(X0 + m, X1 - m) ; new 2j+1 (input 1): max(X0 - m, X1 + m); ties keep the j branch
     bool           p0h, p0l, p1h, p1l;
     const uint32_t N0 = __vibmax_s16x2(__vadd2(X0, m), __vadd2(X1, mn), &p0h, &p0l);
     const uint32_t N1 = __vibmax_s16x2(__vadd2(X0, mn), __vadd2(X1, m), &p1h, &p1l);
-    if (t >= K) {
+    if (store) {
       uint4 d;
       d.x = __ballot_sync(0xffffffffu, !p0l); // cand0, new state 2j   -> bit j
       d.y = __ballot_sync(0xffffffffu, !p1l); // cand0, new state 2j+1
       d.z = __ballot_sync(0xffffffffu, !p0h); // cand1
       d.w = __ballot_sync(0xffffffffu, !p1h);
-      if (lane == 0) sm.dec[t - K] = d;
+      if (lane == 0) *dst = d;
     }
     // re-distribute: lane j needs new[j], new[j+32]
     const uint32_t v1 = lo_half ? N0 : N1, v2 = lo_half ? N1 : N0;
     const uint32_t r1 = __shfl_sync(0xffffffffu, v1, src1), r2 = __shfl_sync(0xffffffffu, v2, src2);
     X0 = odd ? r2 : r1;
     X1 = odd ? r1 : r2;
-    if ((t % VIT_RENORM) == VIT_RENORM - 1) {
-      const uint32_t ref = __vneg2(__shfl_sync(0xffffffffu, X0, 0));
-      X0 = __vadd2(X0, ref);
-      X1 = __vadd2(X1, ref);
+  };
+  auto renorm = [&]() {
+    const uint32_t ref = __vneg2(__shfl_sync(0xffffffffu, X0, 0));
+    X0 = __vadd2(X0, ref);
+    X1 = __vadd2(X1, ref);
+  };
+  // three concatenated copies of the K-step frame; decisions are kept for copies 2 and 3
+  for (uint32_t pass = 0; pass < 3; pass++) {
+    uint4* dst = &sm.dec[(pass ? pass - 1 : 0) * K];
+    uint32_t k = 0;
+    for (; k + VIT_RENORM <= K; k += VIT_RENORM) {
+      if (pass == 0) {
+#pragma unroll
+        for (uint32_t u = 0; u < VIT_RENORM; u++) step(k + u, nullptr, false);
+      } else {
+#pragma unroll
+        for (uint32_t u = 0; u < VIT_RENORM; u++) step(k + u, dst + k + u, true);
+      }
+      renorm();
     }
+    for (; k < K; k++) step(k, dst + k, pass != 0);
+    renorm();
   }
   __syncwarp();
   // ---- best final state (lowest index on ties), per candidate ------------------------------------
@@ -153,29 +164,45 @@ __global__ void __launch_bounds__(VIT_WARPS * 32) dci_viterbi_kernel(const __gri
   }
   // ---- traceback (lanes 0,1: one candidate each), steps 3K-1 .. K, keep K..2K-1 --------------------
   if (lane < 2) {
-    const int cd = (int)lane;
-    uint32_t  st = (uint32_t)best_s[cd];
-    uint32_t  w[3] = {0, 0, 0};
-    for (int t = (int)n3 - 1; t >= (int)K; t--) {
-      if (t < (int)(2 * K)) {
-        const uint32_t i = (uint32_t)t - K; // data bit index
-        w[i >> 5] |= (st & 1u) << (31 - (i & 31));
-      }
-      const uint4    d    = sm.dec[t - (int)K];
-      const uint32_t word = cd ? ((st & 1u) ? d.w : d.z) : ((st & 1u) ? d.y : d.x);
+    const int       cd = (int)lane;
+    uint32_t        st = (uint32_t)best_s[cd];
+    const uint32_t* dw = reinterpret_cast<const uint32_t*>(sm.dec) + cd * 2; // word (t-K)*4 + cd*2 + (st&1)
+    auto back = [&](int idx) { // idx = t - K
+      const uint32_t word = dw[idx * 4 + (int)(st & 1u)];
       st                  = (st >> 1) | (((word >> (st >> 1)) & 1u) << 5);
+    };
+    for (int idx = 2 * (int)K - 1; idx >= (int)K; idx--) back(idx); // third copy: only gives traceback depth
+    // second copy: data bit i = idx (K-1 .. 0), bit i at position 31 - (i & 31) of word i >> 5
+    uint32_t w0 = 0, w1 = 0, w2 = 0;
+    int      idx = (int)K - 1;
+    for (; idx >= 64; idx--) {
+      w2 |= (st & 1u) << (31 - (idx & 31));
+      back(idx);
+    }
+    for (; idx >= 32; idx--) {
+      w1 |= (st & 1u) << (31 - (idx & 31));
+      back(idx);
+    }
+    for (; idx >= 0; idx--) {
+      w0 |= (st & 1u) << (31 - (idx & 31));
+      back(idx);
     }
     // CRC16 (poly 0x11021, zero init) over the first nb bits; RNTI = received parity ^ computed
-    uint32_t reg = 0;
+    const unsigned long long lo64 = ((unsigned long long)w0 << 32) | (unsigned long long)w1; // bits 0..63, bit i at 63 - i
+    uint32_t                 reg  = 0;
     for (uint32_t i = 0; i < nb + 16; i++) {
-      const uint32_t bit = i < nb ? (w[i >> 5] >> (31 - (i & 31))) & 1u : 0u;
+      const uint32_t bit = i < nb ? (uint32_t)((lo64 >> (63 - i)) & 1ull) : 0u;
       reg                = (reg << 1) | bit;
       if (reg & 0x10000u) reg ^= 0x11021u;
     }
+    // the 16 parity bits nb .. nb+15 (bit i of the frame: word i>>5)
     uint32_t par = 0;
-    for (uint32_t i = nb; i < nb + 16; i++) par = (par << 1) | ((w[i >> 5] >> (31 - (i & 31))) & 1u);
+    for (uint32_t i = nb; i < nb + 16; i++) {
+      const uint32_t wsel = (i >> 5) == 0 ? w0 : ((i >> 5) == 1 ? w1 : w2);
+      par                 = (par << 1) | ((wsel >> (31 - (i & 31))) & 1u);
+    }
     ltephy_cand_t o{};
-    uint64_t      bits = ((uint64_t)w[0] << 32) | (uint64_t)w[1];
+    unsigned long long bits = lo64;
     if (nb < 64) bits &= ~((~0ull) >> nb);
     o.bits  = bits;
     o.rnti  = (uint16_t)((par ^ reg) & 0xFFFFu);
