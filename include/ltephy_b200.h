@@ -86,6 +86,7 @@ typedef struct {
   uint8_t  nof_tb;
   uint32_t prb_mask[2][4];  /* per slot, bit (prb & 31) of word (prb >> 5) */
   uint32_t nof_re;          /* srsran_pdsch_grant_t.nof_re */
+  uint32_t pmi;             /* srsran_pdsch_grant_t.pmi (spatial multiplexing codebook index) */
   struct {
     int32_t tbs;            /* bits, <= 0 disables the TB */
     uint8_t qm;             /* 2,4,6,8 */
@@ -143,6 +144,32 @@ int ltephy_submit_grants(ltephy_t* h, const ltephy_grant_t* grants, uint32_t n);
 /* results[n][2]; payload receives the TB bytes back to back */
 int ltephy_get_phase_b(ltephy_t* h, ltephy_tb_result_t* results, uint8_t* payload, size_t payload_cap);
 
+/* ---- uplink: PUSCH (PUSCH_Decoder::decode / decode_run, src/src/UL_Sniffer_PUSCH.cc:250-263,389-392) ------------ */
+typedef struct {
+  uint32_t n_dmrs1;       /* cyclicShift of SIB2 (ULSchedule::set_config, src/src/ULSchedule.cc:140-158) */
+  uint32_t delta_ss;      /* groupAssignmentPUSCH */
+  uint32_t group_hopping; /* 0 (group / sequence hopping are not implemented yet) */
+  uint32_t seq_hopping;   /* 0 */
+} ltephy_ul_cfg_t;
+typedef struct {
+  uint32_t sf;            /* index of the UL subframe inside the submitted UL batch */
+  uint16_t rnti;
+  uint8_t  qm, rv;        /* srsran_pusch_grant_t.tb.mod / .rv */
+  uint32_t L_prb, n_prb;  /* contiguous allocation (no hopping); L_prb in the 2^a 3^b 5^c set, >= 3 */
+  uint32_t n_dmrs2;       /* 36.211 Table 5.5.2.1.1-1 value of the DCI-0 cyclic shift field */
+  int32_t  tbs;
+} ltephy_ul_grant_t;
+typedef struct {
+  float noise, rsrp;      /* srsran_chest_ul_res_t.noise_estimate, RSRP (linear) */
+  float snr_db;           /* .snr_db   (UL_Sniffer_PUSCH.cc:268) */
+  float ta_us;            /* .ta_us    (not estimated yet: 0) */
+} ltephy_ul_chest_t;
+int ltephy_set_ul_cfg(ltephy_t* h, const ltephy_ul_cfg_t* cfg);
+/* iq_ul: n * sf_len cf32 of the UL carrier (one antenna: the reference uses antenna buffer 1); host memory */
+int ltephy_submit_ul(ltephy_t* h, const float* iq_ul, const uint32_t* tti, uint32_t n, const ltephy_ul_grant_t* grants, uint32_t ngrants);
+/* results[ngrants], chest[ngrants]; payload receives the TB bytes back to back */
+int ltephy_get_ul(ltephy_t* h, ltephy_tb_result_t* results, ltephy_ul_chest_t* chest, uint8_t* payload, size_t payload_cap);
+
 /* ---- stand-alone batched kernels (BASELINE.json configs 3 and 4) --------------------------- */
 /* llr: n subframes x 72*LTEPHY_MAX_CCE float LLRs (host); cfi[n]; fills cands[n][MAX_LOC][MAX_SIZES] */
 int ltephy_dci_sweep(ltephy_t* h, const float* llr, const uint32_t* cfi, uint32_t n, ltephy_cand_t* cands);
@@ -157,7 +184,8 @@ enum {
   LTEPHY_TAP_CE  = 1, /* cf32 [n][port][rx][14][12*nof_prb]    q->chest_res.ce */
   LTEPHY_TAP_LLR = 2, /* f32  [n][72*LTEPHY_MAX_CCE]           q->pdcch.llr */
   LTEPHY_TAP_PDSCH_LLR = 3, /* int16, all codewords of the submitted grants back to back */
-  LTEPHY_TAP_TURBO_IN = 4   /* int16 conditioned streams (debug) */
+  LTEPHY_TAP_TURBO_IN = 4,  /* int16 conditioned streams (debug) */
+  LTEPHY_TAP_UL_SYM = 5     /* cf32 [n][14][12*nof_prb]  UL grid after srsran_enb_ul_fft */
 };
 int ltephy_tap(ltephy_t* h, int what, void* dst, size_t bytes);
 

@@ -86,6 +86,11 @@ int      ltephy_search_rnti_is_evergreen(const ltephy_search_t* s, uint16_t rnti
 int ltephy_dci_to_grant(const ltephy_search_t* s, const ltephy_dci_t* dci, uint32_t sf_idx, uint32_t cfi, int use_256qam_table, ltephy_grant_t* grant,
                         ltephy_dci_fields_t* fields);
 
+/* DCI format 0 -> PUSCH grant (srsran_ra_ul_dci_to_grant as used at falcon_dci.c:222, no hopping).
+ * enable_64qam: 0 caps the modulation at 16QAM (UE category without 64QAM), 1 uses Table 8.6.1-1 as is.
+ * Returns 0, or LTEPHY_ERROR for hopping / retransmission MCS / invalid RIV / L_prb outside the DFT set or < 3. */
+int ltephy_ul_dci_to_grant(const ltephy_search_t* s, const ltephy_dci_t* dci, int enable_64qam, ltephy_ul_grant_t* grant);
+
 /* Whole batch: IQ in host memory -> accepted DCIs + transport blocks.  seq orders concurrent calls on
  * different PHY handles that share one search object (the search runs strictly in seq order, starting
  * at 0); pass LTEPHY_SEQ_NONE for a single pipeline.

@@ -37,13 +37,27 @@ class GrantTb(C.Structure):
 
 class Grant(C.Structure):
     _fields_ = [("sf", C.c_uint32), ("rnti", C.c_uint16), ("tx_scheme", C.c_uint8), ("nof_tb", C.c_uint8),
-                ("prb_mask", (C.c_uint32 * 4) * 2), ("nof_re", C.c_uint32), ("tb", GrantTb * 2)]
+                ("prb_mask", (C.c_uint32 * 4) * 2), ("nof_re", C.c_uint32), ("pmi", C.c_uint32), ("tb", GrantTb * 2)]
 
 
 class TbResult(C.Structure):
     _fields_ = [("crc", C.c_uint8), ("avg_iters", C.c_uint8), ("nof_cb", C.c_uint16), ("payload_off", C.c_uint32), ("payload_len", C.c_uint32)]
 
 
+class UlCfg(C.Structure):
+    _fields_ = [("n_dmrs1", C.c_uint32), ("delta_ss", C.c_uint32), ("group_hopping", C.c_uint32), ("seq_hopping", C.c_uint32)]
+
+
+class UlGrant(C.Structure):
+    _fields_ = [("sf", C.c_uint32), ("rnti", C.c_uint16), ("qm", C.c_uint8), ("rv", C.c_uint8), ("L_prb", C.c_uint32), ("n_prb", C.c_uint32),
+                ("n_dmrs2", C.c_uint32), ("tbs", C.c_int32)]
+
+
+class UlChest(C.Structure):
+    _fields_ = [("noise", C.c_float), ("rsrp", C.c_float), ("snr_db", C.c_float), ("ta_us", C.c_float)]
+
+
+TAP_UL_SYM = 5
 CAND_DTYPE = np.dtype([("bits", "<u8"), ("rnti", "<u2"), ("valid", "u1"), ("pad", "u1", 5)])
 assert CAND_DTYPE.itemsize == C.sizeof(Cand) == 16
 
@@ -82,6 +96,9 @@ def load_library(build_if_missing=True):
     L.ltephy_turbo_batch.argtypes = [P, P, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, P, P, P]
     L.ltephy_tap.argtypes = [P, C.c_int, P, C.c_size_t]
     L.ltephy_last_timing.argtypes = [P, P]
+    L.ltephy_set_ul_cfg.argtypes = [P, C.POINTER(UlCfg)]
+    L.ltephy_submit_ul.argtypes = [P, P, P, C.c_uint32, P, C.c_uint32]
+    L.ltephy_get_ul.argtypes = [P, P, P, P, C.c_size_t]
     L.ltephy_mark.argtypes = [P, C.c_int]
     L.ltephy_mark_elapsed_ms.argtypes = [P]
     L.ltephy_mark_elapsed_ms.restype = C.c_float
@@ -175,6 +192,24 @@ class LtePhy:
         pl = np.zeros(cap, np.uint8)
         self._chk(self.L.ltephy_get_phase_b(self.h, res, _p(pl), cap), "get_phase_b")
         return res, pl
+
+    # ---- uplink
+    def set_ul_cfg(self, n_dmrs1=0, delta_ss=0):
+        cfg = UlCfg(n_dmrs1=n_dmrs1, delta_ss=delta_ss)
+        self._chk(self.L.ltephy_set_ul_cfg(self.h, C.byref(cfg)), "set_ul_cfg")
+
+    def decode_ul(self, iq_ul, tti, grants):
+        """iq_ul complex64 [n][sf_len]; grants: list of UlGrant -> (results, chest, payload)"""
+        iq_ul = np.ascontiguousarray(iq_ul, np.complex64)
+        tti = np.ascontiguousarray(tti, np.uint32)
+        arr = (UlGrant * max(1, len(grants)))(*grants)
+        self._chk(self.L.ltephy_submit_ul(self.h, _p(iq_ul), _p(tti), len(tti), arr, len(grants)), "submit_ul")
+        res = (TbResult * max(1, len(grants)))()
+        ch = (UlChest * max(1, len(grants)))()
+        pl = np.zeros(len(grants) * 10000 + 64, np.uint8)
+        self._chk(self.L.ltephy_get_ul(self.h, res, ch, _p(pl), pl.nbytes), "get_ul")
+        self.n_ul = len(tti)
+        return res, ch, pl
 
     # ---- stand-alone kernels
     def dci_sweep(self, llr, cfi):
@@ -276,6 +311,7 @@ def _bind_search(L):
     L.ltephy_search_rnti_assoc_format.restype = C.c_uint32
     L.ltephy_search_rnti_reason.argtypes = [P, C.c_uint16]
     L.ltephy_dci_to_grant.argtypes = [P, P, C.c_uint32, C.c_uint32, C.c_int, P, P]
+    L.ltephy_ul_dci_to_grant.argtypes = [P, P, C.c_int, P]
     L.ltephy_decode_subframes.argtypes = [P, P, P, P, C.c_uint32, C.c_uint64, P, P, P, C.c_uint32, P, P, P, C.c_size_t]
     L.ltephy_decode_subframes_device.argtypes = [P, P, P, P, C.c_uint32, C.c_uint64, P, P, P, C.c_uint32, P, P, P, C.c_size_t]
     L.ltephy_search_batch.argtypes = [P, P, P, C.c_uint32, P, C.c_uint32, P]

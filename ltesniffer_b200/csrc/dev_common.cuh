@@ -21,6 +21,7 @@ struct DevCell {
   uint16_t pcfich_idx[16];
   uint32_t pdcch_scr_words;       // words per subframe index
   const float2*   tw;             // [fft/2]
+  const float2*   ul_rot;         // [fft] exp(-j pi i / N)
   const float2*   crs;            // [10][2][4][2*nof_prb]
   const uint16_t* pdcch_idx[3];   // [nof_cce*9][4]
   const uint32_t* pdcch_scr;      // [10][pdcch_scr_words]
@@ -54,7 +55,7 @@ struct DevGrant {          // one PDSCH grant
   uint32_t sf_idx;         // tti % 10
   uint32_t cfi;
   uint32_t rnti;
-  uint32_t tx_scheme, ncw;
+  uint32_t tx_scheme, ncw, pmi;
   uint32_t prb_mask[2][4];
   uint32_t nof_re;
   uint32_t re_off[15];     // prefix sum of data REs per OFDM symbol

@@ -36,6 +36,46 @@ __device__ __forceinline__ void eq_sfbc(const DevCell& c, const SfView& v, uint3
   x0             = make_float2((n0r / d0) * s2, (n0i / d0) * s2);
   x1             = make_float2((n1r / d1) * s2, (n1i / d1) * s2);
 }
+// closed-loop spatial multiplexing, 2 CRS ports (36.211 Table 6.3.4.2.3-1): w = second precoder entry
+__device__ __forceinline__ float2 spmux_w(uint32_t nof_layers, uint32_t pmi)
+{
+  if (nof_layers == 1) return (pmi & 3u) == 0 ? make_float2(1.f, 0.f) : (pmi & 3u) == 1 ? make_float2(-1.f, 0.f) : (pmi & 3u) == 2 ? make_float2(0.f, 1.f) : make_float2(0.f, -1.f);
+  return (pmi & 1u) ? make_float2(0.f, 1.f) : make_float2(1.f, 0.f);
+}
+__device__ __forceinline__ float2 eq_spmux1(const DevCell& c, const SfView& v, uint32_t idx, float2 w)
+{
+  float nr = 0.0f, ni = 0.0f, den = 0.0f;
+  for (uint32_t a = 0; a < c.nof_rx; a++) {
+    const float2 y = v.y[a][idx], h0 = v.h[0][a][idx], h1 = v.h[1][a][idx];
+    const float2 e = make_float2(h0.x + (w.x * h1.x - w.y * h1.y), h0.y + (w.x * h1.y + w.y * h1.x));
+    nr  = nr + (e.x * y.x + e.y * y.y);
+    ni  = ni + (e.x * y.y - e.y * y.x);
+    den = den + (e.x * e.x + e.y * e.y);
+  }
+  const float s2 = 1.41421354f;
+  return make_float2((nr / den) * s2, (ni / den) * s2);
+}
+// x = 2 E^-1 r, E rows = rx antennas, columns = layers
+__device__ __forceinline__ void zf2x2(float2 e00, float2 e01, float2 e10, float2 e11, float2 r0, float2 r1, float2& x0, float2& x1)
+{
+  const float2 det = make_float2((e00.x * e11.x - e00.y * e11.y) - (e01.x * e10.x - e01.y * e10.y),
+                                 (e00.x * e11.y + e00.y * e11.x) - (e01.x * e10.y + e01.y * e10.x));
+  const float2 a0  = make_float2((e11.x * r0.x - e11.y * r0.y) - (e01.x * r1.x - e01.y * r1.y),
+                                 (e11.x * r0.y + e11.y * r0.x) - (e01.x * r1.y + e01.y * r1.x));
+  const float2 a1  = make_float2((e00.x * r1.x - e00.y * r1.y) - (e10.x * r0.x - e10.y * r0.y),
+                                 (e00.x * r1.y + e00.y * r1.x) - (e10.x * r0.y + e10.y * r0.x));
+  const float dd = det.x * det.x + det.y * det.y;
+  x0 = make_float2(((a0.x * det.x + a0.y * det.y) / dd) * 2.0f, ((a0.y * det.x - a0.x * det.y) / dd) * 2.0f);
+  x1 = make_float2(((a1.x * det.x + a1.y * det.y) / dd) * 2.0f, ((a1.y * det.x - a1.x * det.y) / dd) * 2.0f);
+}
+__device__ __forceinline__ void eq_spmux2(const SfView& v, uint32_t idx, float2 w, float2& x0, float2& x1)
+{
+  const float2 h00 = v.h[0][0][idx], h10 = v.h[0][1][idx], h01 = v.h[1][0][idx], h11 = v.h[1][1][idx];
+  const float2 w0 = make_float2(w.x * h01.x - w.y * h01.y, w.x * h01.y + w.y * h01.x);
+  const float2 w1 = make_float2(w.x * h11.x - w.y * h11.y, w.x * h11.y + w.y * h11.x);
+  zf2x2(make_float2(h00.x + w0.x, h00.y + w0.y), make_float2(h00.x - w0.x, h00.y - w0.y), make_float2(h10.x + w1.x, h10.y + w1.y),
+        make_float2(h10.x - w1.x, h10.y - w1.y), v.y[0][idx], v.y[1][idx], x0, x1);
+}
 __device__ __forceinline__ void eq_cdd(const SfView& v, uint32_t idx, bool odd, float2& x0, float2& x1)
 {
   const float2 r0 = v.y[0][idx], r1 = v.y[1][idx];

@@ -659,16 +659,53 @@ int ltephy_dci_to_grant(const ltephy_search_t* s, const ltephy_dci_t* d, uint32_
     case ltehost::F2A: g->tx_scheme = (g->nof_tb == 1 && f.pinfo == 0) ? LTEPHY_TX_DIVERSITY : LTEPHY_TX_CDD; break;
     default: g->tx_scheme = c.nof_ports == 1 ? LTEPHY_TX_PORT0 : LTEPHY_TX_DIVERSITY; break;
   }
-  if (g->tx_scheme == LTEPHY_TX_SPATIALMUX) {
+  if (g->tx_scheme == LTEPHY_TX_SPATIALMUX) { // dl_sniffer_config_mimo_pmi, dl_sniffer_pdsch.c:181-209
     if (g->nof_tb == 1) {
       if (!(f.pinfo > 0 && f.pinfo < 5)) return LTEPHY_MIMO_PMI_WRONG;
-    } else if (f.pinfo >= 2)
-      return LTEPHY_MIMO_PMI_WRONG;
+      g->pmi = f.pinfo - 1u;
+    } else {
+      if (f.pinfo >= 2) return LTEPHY_MIMO_PMI_WRONG;
+      g->pmi = f.pinfo % 2u;
+    }
   }
   if ((g->tx_scheme == LTEPHY_TX_PORT0 || g->tx_scheme == LTEPHY_TX_DIVERSITY) && g->nof_tb != 1) return LTEPHY_MIMO_LAYER_WRONG;
   if (g->tx_scheme == LTEPHY_TX_CDD && g->nof_tb != 2) return LTEPHY_MIMO_LAYER_WRONG;
   g->rnti = d->rnti, g->sf = d->sf;
   if (fields) *fields = f;
+  return LTEPHY_SUCCESS;
+}
+
+int ltephy_ul_dci_to_grant(const ltephy_search_t* s, const ltephy_dci_t* d, int enable_64qam, ltephy_ul_grant_t* g)
+{
+  static const uint8_t dmrs2_map[8] = {0, 6, 3, 4, 2, 8, 10, 9}; // 36.211 Table 5.5.2.1.1-1
+  if (!s || !d || !g || d->format != ltehost::F0) return LTEPHY_ERROR_INVALID_INPUTS;
+  const uint32_t N = s->cell.nof_prb, rivb = clog2(N * (N + 1) / 2);
+  Bits           b{d->bits};
+  if (b.get(1) != 0) return LTEPHY_ERROR;            // format 0/1A flag
+  if (b.get(1) != 0) return LTEPHY_ERROR;            // frequency hopping: not supported
+  const uint32_t riv = b.get(rivb), mcs = b.get(5);
+  b.get(1);                                          // ndi
+  b.get(2);                                          // tpc
+  const uint32_t cs = b.get(3);
+  uint32_t       L, S;
+  riv_decode(riv, N, L, S);
+  if (L < 3 || L > N || S >= N || S + L > N) return LTEPHY_ERROR;
+  uint32_t t = L;
+  while (t % 2 == 0) t /= 2;
+  while (t % 3 == 0) t /= 3;
+  while (t % 5 == 0) t /= 5;
+  if (t != 1) return LTEPHY_ERROR;                   // valid_prb_ul, src/src/UL_Sniffer_PUSCH.cc:3-10
+  memset(g, 0, sizeof(*g));
+  int itbs;
+  if (mcs <= 10)
+    g->qm = 2, itbs = (int)mcs;
+  else if (mcs <= 20)
+    g->qm = 4, itbs = (int)mcs - 1;
+  else if (mcs <= 28)
+    g->qm = enable_64qam ? 6 : 4, itbs = (int)mcs - 2;
+  else
+    return LTEPHY_ERROR;
+  g->sf = d->sf, g->rnti = d->rnti, g->rv = 0, g->L_prb = L, g->n_prb = S, g->n_dmrs2 = dmrs2_map[cs & 7], g->tbs = lte_tbs_table[itbs][L - 1];
   return LTEPHY_SUCCESS;
 }
 
@@ -774,7 +811,7 @@ int ltephy_grants_from_dcis(const ltephy_search_t* s, const ltephy_sf_info_t* in
     ltephy_grant_t g;
     if (ltephy_dci_to_grant(s, &d, info[d.sf].tti % 10, info[d.sf].cfi, 0, &g, nullptr) != LTEPHY_SUCCESS) continue;
     if (!(g.tb[0].tbs > 0 && !(s->cell.nof_rx == 1 && g.nof_tb == 2))) continue;
-    if (g.tx_scheme == LTEPHY_TX_SPATIALMUX) continue; // TM4 codebook precoding: next round
+    if (g.tx_scheme == LTEPHY_TX_SPATIALMUX && (s->cell.nof_ports != 2 || (g.nof_tb == 2 && s->cell.nof_rx != 2))) continue;
     if (ng >= max_grants) return LTEPHY_ERROR_INVALID_INPUTS;
     g.sf          = d.sf / mod;
     grants[ng]    = g;

@@ -44,6 +44,7 @@ __device__ __forceinline__ void fft_pass(float2* work, const float2* __restrict_
   }
 }
 
+template <bool UL>
 __global__ void __launch_bounds__(256) ofdm_rx_kernel(const __grid_constant__ DevCell c, const float2* __restrict__ iq, float2* __restrict__ sym)
 {
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -53,7 +54,8 @@ __global__ void __launch_bounds__(256) ofdm_rx_kernel(const __grid_constant__ De
   __shared__ __align__(8) unsigned long long mbar;
 
   const uint32_t l = blockIdx.x, a = blockIdx.y, sf = blockIdx.z, tid = threadIdx.x, nt = blockDim.x, n = c.fft;
-  const float2*  src = iq + ((size_t)sf * c.nof_rx + a) * c.sf_len + c.sym_off[l];
+  const uint32_t nant = UL ? 1u : c.nof_rx; // the UL carrier is decoded from one antenna (UL_Sniffer_PUSCH.cc:391-392)
+  const float2*  src = iq + ((size_t)sf * nant + a) * c.sf_len + c.sym_off[l];
   const bool     bulk_ok = ((reinterpret_cast<uintptr_t>(src) & 15u) == 0) && ((n * 8u) % 16u == 0);
 
   if (bulk_ok) {
@@ -83,7 +85,14 @@ __global__ void __launch_bounds__(256) ofdm_rx_kernel(const __grid_constant__ De
     for (uint32_t i = tid; i < n; i += nt) stage[i] = src[i];
   }
   __syncthreads();
-  for (uint32_t i = tid; i < n; i += nt) work[__brev(i) >> (32 - c.log2n)] = stage[i];
+  if (UL) { // remove the 7.5 kHz half-subcarrier shift: multiply by exp(-j pi i / N) (srsran_enb_ul_fft)
+    for (uint32_t i = tid; i < n; i += nt) {
+      const float2 v = stage[i], r = c.ul_rot[i];
+      work[__brev(i) >> (32 - c.log2n)] = make_float2(v.x * r.x - v.y * r.y, v.x * r.y + v.y * r.x);
+    }
+  } else {
+    for (uint32_t i = tid; i < n; i += nt) work[__brev(i) >> (32 - c.log2n)] = stage[i];
+  }
   __syncthreads();
   uint32_t s = 1;
   while (s + 2 <= c.log2n) {
@@ -100,9 +109,13 @@ __global__ void __launch_bounds__(256) ofdm_rx_kernel(const __grid_constant__ De
     fft_pass<1>(work, tw, n, s, tid, nt);
     __syncthreads();
   }
-  float2*        dst = sym + (((size_t)sf * c.nof_rx + a) * 14 + l) * c.nsc;
+  float2*        dst = sym + (((size_t)sf * nant + a) * 14 + l) * c.nsc;
   const uint32_t h   = c.nsc / 2;
-  for (uint32_t k = tid; k < c.nsc; k += nt) dst[k] = work[k < h ? n - h + k : k - h + 1];
+  if (UL) {
+    for (uint32_t k = tid; k < c.nsc; k += nt) dst[k] = work[(k + n - h) % n]; // no DC gap on the uplink
+  } else {
+    for (uint32_t k = tid; k < c.nsc; k += nt) dst[k] = work[k < h ? n - h + k : k - h + 1];
+  }
 }
 
 // =================================================================================================
@@ -318,10 +331,18 @@ extern "C" void launch_frontend(const DevCell& c, const float2* iq, float2* sym,
 {
   const uint32_t fft_threads = c.fft / 8 < 32 ? 32 : c.fft / 8;
   const size_t   smem_fft    = (size_t)c.fft * 8 * 2 + (size_t)c.fft * 4;
-  ofdm_rx_kernel<<<dim3(14, c.nof_rx, n), fft_threads, smem_fft, st>>>(c, iq, sym);
+  ofdm_rx_kernel<false><<<dim3(14, c.nof_rx, n), fft_threads, smem_fft, st>>>(c, iq, sym);
   const size_t smem_ch = (size_t)2 * NPILSYM * 2 * c.nof_prb * sizeof(float2);
   chest_kernel<<<dim3(c.nof_ports * c.nof_rx, n), 256, smem_ch, st>>>(c, sym, ce, info);
   rb_power_kernel<<<n, 128, 0, st>>>(c, sym, info);
   pdcch_llr_kernel<<<n, 256, 0, st>>>(c, sym, ce, llr, info);
   *launches += 4;
+}
+
+extern "C" void launch_ul_ofdm(const DevCell& c, const float2* iq, float2* sym, uint32_t n, cudaStream_t st, uint64_t* launches)
+{
+  const uint32_t fft_threads = c.fft / 8 < 32 ? 32 : c.fft / 8;
+  const size_t   smem_fft    = (size_t)c.fft * 8 * 2 + (size_t)c.fft * 4;
+  ofdm_rx_kernel<true><<<dim3(14, 1, n), fft_threads, smem_fft, st>>>(c, iq, sym);
+  *launches += 1;
 }

@@ -4,6 +4,7 @@
 #include "../../include/ltephy_b200.h"
 #include "../../include/ltephy_search.h"
 #include "dev_common.cuh"
+#include "dev_ul.cuh"
 #include "lte_host.hpp"
 #include "../../include/lte_tables.h"
 #include <cmath>
@@ -25,6 +26,9 @@ void launch_turbo(const DevPair*, uint32_t, uint32_t, int, uint32_t*, const uint
                   uint8_t*, uint8_t*, uint32_t, cudaStream_t, uint64_t*);
 void launch_tb_crc(const DevTb*, uint32_t, const uint8_t*, const uint8_t*, const uint8_t*, const uint32_t*, ltephy_tb_result_t*, cudaStream_t,
                    uint64_t*);
+void launch_ul_ofdm(const DevCell&, const float2*, float2*, uint32_t, cudaStream_t, uint64_t*);
+void launch_pusch(const DevCell&, const DevUlGrant*, uint32_t, uint32_t, uint32_t, const float2*, const float2*, const float2*, const uint32_t*,
+                  const uint32_t*, uint32_t, uint32_t*, short*, ltephy_ul_chest_t*, cudaStream_t, uint64_t*);
 }
 
 static thread_local std::string g_err;
@@ -141,6 +145,18 @@ struct ltephy {
   uint32_t rm_fast_nn[188][4];
   int64_t  pi_fast[188];
   std::vector<ltehost::Segm> segm_fast; // index tbs/8, C == 0 means "not computed"
+  // uplink
+  ltephy_ul_cfg_t            ulcfg{};
+  bool                       ulcfg_set = false;
+  uint32_t                   n_prs[20]{};
+  DevBuf<float2>             d_uliq, d_ulsym, d_ulpool; // d_ulpool: DMRS sequences and IDFT twiddles
+  DevBuf<DevUlGrant>         d_ulgrants;
+  DevBuf<ltephy_ul_chest_t>  d_ulchest;
+  PinBuf<ltephy_ul_chest_t>  h_ulchest;
+  std::vector<DevUlGrant>    ulgrants;
+  std::map<uint64_t, uint32_t> ul_tab_cache; // (kind, M, ncs) -> offset in d_ulpool
+  size_t                     ulpool_used = 0;
+  uint32_t                   n_ul = 0;
   size_t                                                                            rm_used = 0;
   std::map<uint32_t, uint32_t>                                                      pi_cache; // K -> offset
   size_t                                                                            pi_used = 0;
@@ -232,6 +248,12 @@ extern "C" int ltephy_create(const ltephy_cfg_t* cfg, ltephy_t** out)
       tw[k]    = make_float2((float)std::cos(a), (float)std::sin(a));
     }
     c.tw = upload(h, tw.data(), tw.size());
+    std::vector<float2> rot(c.fft);
+    for (uint32_t i = 0; i < c.fft; i++) {
+      double ph = M_PI * (double)i / (double)c.fft;
+      rot[i]    = make_float2((float)std::cos(ph), (float)-std::sin(ph));
+    }
+    c.ul_rot = upload(h, rot.data(), rot.size());
   }
   {
     auto crs = ltehost::crs_table(h->cell);
@@ -312,6 +334,7 @@ extern "C" void ltephy_destroy(ltephy_t* h)
   h->h_info.release(), h->d_grants.release(), h->d_cbs.release(), h->d_pairs.release(), h->d_tbs.release(), h->d_pair_pi_off.release();
   h->d_seq.release(), h->d_rm.release(), h->d_turbo.release(), h->d_pllr.release(), h->d_pi.release(), h->d_payload.release();
   h->d_cb_iters.release(), h->d_cb_crc.release(), h->d_res.release(), h->h_res.release(), h->h_payload.release();
+  h->d_uliq.release(), h->d_ulsym.release(), h->d_ulpool.release(), h->d_ulgrants.release(), h->d_ulchest.release(), h->h_ulchest.release();
   for (auto& e : h->ev)
     if (e) cudaEventDestroy(e);
   if (h->stream) cudaStreamDestroy(h->stream);
@@ -486,6 +509,61 @@ static int pi_table_for(ltephy* h, uint32_t K, uint32_t& off)
   return 0;
 }
 
+// transport block -> code blocks -> turbo pairs (shared by the PDSCH and PUSCH paths)
+static int add_transport_block(ltephy* h, uint32_t tbs, uint32_t G, uint32_t qm, uint32_t rv, uint32_t NL, uint32_t llr_off, int32_t* open_pair,
+                               size_t& turbo_words, uint32_t& tb_index)
+{
+  if (tbs / 8 >= h->segm_fast.size() || (tbs & 7)) return fail(LTEPHY_ERROR_INVALID_INPUTS, "invalid TBS %u", tbs);
+  if (h->segm_fast[tbs / 8].C == 0 && !ltehost::cb_segmentation(tbs, h->segm_fast[tbs / 8])) return fail(LTEPHY_ERROR_INVALID_INPUTS, "invalid TBS %u", tbs);
+  const ltehost::Segm& s = h->segm_fast[tbs / 8];
+  DevTb                tb{};
+  tb.byte_off = (uint32_t)h->payload_bytes, tb.nbytes = tbs / 8, tb.cb_first = (uint32_t)h->cbs.size(), tb.ncb = s.C;
+  h->payload_bytes += (tb.nbytes + 3 + 3) & ~3u;
+  uint32_t rp = llr_off, wbit = 0;
+  for (uint32_t r = 0; r < s.C; r++) {
+    DevCb cb{};
+    cb.K = s.K(r), cb.F = r == 0 ? s.F : 0, cb.E = ltehost::rm_turbo_E(G, s.C, r, qm, NL);
+    cb.llr_off = rp;
+    rp += cb.E;
+    cb.shift = qm == 2 ? 0 : qm == 4 ? 1 : 2;
+    if (rm_table_for(h, cb.K, cb.F, rv, cb.rm_tab, cb.rm_nn)) return fail(LTEPHY_ERROR, "rate-matching table upload failed");
+    const int kq = lte_qpp_index_ge(cb.K);
+    uint32_t  pi;
+    if (open_pair[kq] >= 0) {
+      pi            = (uint32_t)open_pair[kq];
+      open_pair[kq] = -1;
+      cb.half       = 1;
+    } else {
+      DevPair p{};
+      p.K = cb.K, p.NW = (cb.K + 31) / 32;
+      ltehost::qpp_params(cb.K, p.f1, p.f2);
+      p.buf_off = (uint32_t)turbo_words;
+      turbo_words += (size_t)6 * 32 * p.NW + 16 + (size_t)4 * 8 * p.NW;
+      uint32_t po;
+      if (pi_table_for(h, cb.K, po)) return fail(LTEPHY_ERROR, "interleaver table upload failed");
+      pi = (uint32_t)h->pairs.size();
+      h->pairs.push_back(p);
+      h->pair_pi_off.push_back(po);
+      open_pair[kq] = (int32_t)pi;
+      cb.half       = 0;
+    }
+    cb.pair           = pi;
+    DevPair&       p  = h->pairs[pi];
+    const uint32_t hh = cb.half;
+    p.ncb             = hh + 1;
+    p.crc_type[hh]    = s.C > 1 ? 2 : 1;
+    p.out_skip[hh]    = cb.F;
+    p.out_bits[hh]    = cb.K - cb.F - (s.C > 1 ? 24 : 0);
+    p.out_byte[hh]    = tb.byte_off + wbit / 8;
+    p.cb_index[hh]    = (uint32_t)h->cbs.size();
+    wbit += p.out_bits[hh];
+    h->cbs.push_back(cb);
+  }
+  tb_index = (uint32_t)h->tbs.size();
+  h->tbs.push_back(tb);
+  return LTEPHY_SUCCESS;
+}
+
 static int build_jobs(ltephy* h, const ltephy_grant_t* gin, uint32_t n, size_t& seq_words, size_t& turbo_words, uint32_t& max_scr_words)
 {
   const DevCell& c = h->dc;
@@ -531,7 +609,9 @@ static int build_jobs(ltephy* h, const ltephy_grant_t* gin, uint32_t n, size_t& 
     d.nof_re     = acc;
     if (acc != g.nof_re) return fail(LTEPHY_ERROR_INVALID_INPUTS, "grant %u: nof_re %u does not match the PRB mask (%u)", gi, g.nof_re, acc);
     const bool two_cw = g.tx_scheme == LTEPHY_TX_CDD || (g.tx_scheme == LTEPHY_TX_SPATIALMUX && g.nof_tb == 2);
-    if (g.tx_scheme == LTEPHY_TX_SPATIALMUX) return fail(LTEPHY_ERROR_INVALID_INPUTS, "grant %u: spatial multiplexing not implemented yet", gi);
+    if (g.tx_scheme == LTEPHY_TX_SPATIALMUX && (c.nof_ports != 2 || (g.nof_tb == 2 && c.nof_rx != 2) || g.pmi > 3 || (g.nof_tb == 2 && g.pmi > 1)))
+      return fail(LTEPHY_ERROR_INVALID_INPUTS, "grant %u: unsupported spatial multiplexing configuration", gi);
+    d.pmi = g.pmi;
     if (g.tx_scheme == LTEPHY_TX_CDD && !(c.nof_ports == 2 && c.nof_rx == 2)) return fail(LTEPHY_ERROR_INVALID_INPUTS, "grant %u: CDD needs 2x2", gi);
     if (g.tx_scheme == LTEPHY_TX_DIVERSITY && c.nof_ports != 2) return fail(LTEPHY_ERROR_INVALID_INPUTS, "grant %u: tx diversity needs 2 ports", gi);
     uint32_t cw = 0;
@@ -549,58 +629,10 @@ static int build_jobs(ltephy* h, const ltephy_grant_t* gin, uint32_t n, size_t& 
       seq_words += w + 1; // +1: the demapper reads a 64-bit window
       h->pllr_elems += (G + 7) & ~7u;
       if (g.tb[t].tbs > 0) {
-        const uint32_t tbs = (uint32_t)g.tb[t].tbs;
-        if (tbs / 8 >= h->segm_fast.size() || (tbs & 7)) return fail(LTEPHY_ERROR_INVALID_INPUTS, "grant %u: invalid TBS %u", gi, tbs);
-        if (h->segm_fast[tbs / 8].C == 0 && !ltehost::cb_segmentation(tbs, h->segm_fast[tbs / 8]))
-          return fail(LTEPHY_ERROR_INVALID_INPUTS, "grant %u: invalid TBS %u", gi, tbs);
-        const ltehost::Segm& s  = h->segm_fast[tbs / 8];
-        const uint32_t       NL = g.tx_scheme == LTEPHY_TX_DIVERSITY ? 2 : 1;
-        DevTb                tb{};
-        tb.byte_off = (uint32_t)h->payload_bytes, tb.nbytes = tbs / 8, tb.cb_first = (uint32_t)h->cbs.size(), tb.ncb = s.C;
-        h->payload_bytes += (tb.nbytes + 3 + 3) & ~3u;
-        uint32_t rp = d.llr_off[cw], wbit = 0;
-        for (uint32_t r = 0; r < s.C; r++) {
-          DevCb cb{};
-          cb.K = s.K(r), cb.F = r == 0 ? s.F : 0, cb.E = ltehost::rm_turbo_E(G, s.C, r, qm, NL);
-          cb.llr_off = rp;
-          rp += cb.E;
-          cb.shift = qm == 2 ? 0 : qm == 4 ? 1 : 2;
-          if (rm_table_for(h, cb.K, cb.F, g.tb[t].rv, cb.rm_tab, cb.rm_nn)) return fail(LTEPHY_ERROR, "rate-matching table upload failed");
-          // pair assignment
-          const int kq = lte_qpp_index_ge(cb.K);
-          uint32_t  pi;
-          if (open_pair[kq] >= 0) {
-            pi            = (uint32_t)open_pair[kq];
-            open_pair[kq] = -1;
-            cb.half       = 1;
-          } else {
-            DevPair p{};
-            p.K = cb.K, p.NW = (cb.K + 31) / 32;
-            ltehost::qpp_params(cb.K, p.f1, p.f2);
-            p.buf_off = (uint32_t)turbo_words;
-            turbo_words += (size_t)6 * 32 * p.NW + 16 + (size_t)4 * 8 * p.NW;
-            uint32_t po;
-            if (pi_table_for(h, cb.K, po)) return fail(LTEPHY_ERROR, "interleaver table upload failed");
-            pi = (uint32_t)h->pairs.size();
-            h->pairs.push_back(p);
-            h->pair_pi_off.push_back(po);
-            open_pair[kq] = (int32_t)pi;
-            cb.half       = 0;
-          }
-          cb.pair         = pi;
-          DevPair& p      = h->pairs[pi];
-          const uint32_t hh = cb.half;
-          p.ncb           = hh + 1;
-          p.crc_type[hh]  = s.C > 1 ? 2 : 1;
-          p.out_skip[hh]  = cb.F;
-          p.out_bits[hh]  = cb.K - cb.F - (s.C > 1 ? 24 : 0);
-          p.out_byte[hh]  = tb.byte_off + wbit / 8;
-          p.cb_index[hh]  = (uint32_t)h->cbs.size();
-          wbit += p.out_bits[hh];
-          h->cbs.push_back(cb);
-        }
-        h->tb_slot[(size_t)gi * 2 + t] = (uint32_t)h->tbs.size();
-        h->tbs.push_back(tb);
+        uint32_t tbi;
+        int r = add_transport_block(h, (uint32_t)g.tb[t].tbs, G, qm, g.tb[t].rv, g.tx_scheme == LTEPHY_TX_DIVERSITY ? 2 : 1, d.llr_off[cw], open_pair, turbo_words, tbi);
+        if (r) return r;
+        h->tb_slot[(size_t)gi * 2 + t] = tbi;
       }
       cw++;
     }
@@ -711,6 +743,179 @@ extern "C" int ltephy_get_phase_b(ltephy_t* h, ltephy_tb_result_t* results, uint
   return LTEPHY_SUCCESS;
 }
 
+
+// ---------------------------------------------------------------------------------------- uplink (PUSCH)
+extern "C" int ltephy_set_ul_cfg(ltephy_t* h, const ltephy_ul_cfg_t* cfg)
+{
+  if (!h || !cfg) return fail(LTEPHY_ERROR_INVALID_INPUTS, "set_ul_cfg: bad arguments");
+  if (cfg->group_hopping || cfg->seq_hopping) return fail(LTEPHY_ERROR_INVALID_INPUTS, "set_ul_cfg: group / sequence hopping not implemented");
+  h->ulcfg = *cfg, h->ulcfg_set = true;
+  const uint32_t fss = ((h->cell.cell_id % 30) + cfg->delta_ss) % 30;
+  auto           cw  = ltehost::gold_words((h->cell.cell_id / 30) * 32 + fss, 8 * 7 * 20 + 8);
+  for (uint32_t ns = 0; ns < 20; ns++) { // n_PRS(ns), 36.211 5.5.2.1.1
+    uint32_t v = 0;
+    for (uint32_t i = 0; i < 8; i++) {
+      const uint32_t b = 8 * 7 * ns + i;
+      v += ((cw[b >> 5] >> (b & 31)) & 1u) << i;
+    }
+    h->n_prs[ns] = v;
+  }
+  h->ul_tab_cache.clear();
+  h->ulpool_used = 0;
+  return LTEPHY_SUCCESS;
+}
+static uint32_t largest_prime_below(uint32_t n)
+{
+  for (uint32_t p = n - 1; p >= 2; p--) {
+    bool ok = true;
+    for (uint32_t d = 2; d * d <= p; d++)
+      if (p % d == 0) {
+        ok = false;
+        break;
+      }
+    if (ok) return p;
+  }
+  return 2;
+}
+// kind 0: DMRS r_{u,0}^{(alpha)} for (M, ncs); kind 1: IDFT twiddles for M
+static int ul_table_for(ltephy* h, uint32_t kind, uint32_t M, uint32_t ncs, uint32_t& off)
+{
+  const uint64_t key = ((uint64_t)kind << 40) | ((uint64_t)M << 8) | ncs;
+  auto           it  = h->ul_tab_cache.find(key);
+  if (it != h->ul_tab_cache.end()) {
+    off = it->second;
+    return 0;
+  }
+  std::vector<float2> t(M);
+  if (kind == 0) {
+    const uint32_t fss = ((h->cell.cell_id % 30) + h->ulcfg.delta_ss) % 30, Nzc = largest_prime_below(M);
+    const double   qb  = (double)Nzc * (fss + 1) / 31.0;
+    const uint32_t q   = (uint32_t)std::floor(qb + 0.5);
+    for (uint32_t n = 0; n < M; n++) {
+      const uint64_t m  = n % Nzc, tt = ((uint64_t)q * m * (m + 1)) % (2ull * Nzc);
+      const uint32_t a  = (ncs * n) % 12;
+      const double   ph = -M_PI * (double)tt / (double)Nzc + 2.0 * M_PI * (double)a / 12.0;
+      t[n]              = make_float2((float)std::cos(ph), (float)std::sin(ph));
+    }
+  } else {
+    for (uint32_t m = 0; m < M; m++) {
+      const double ph = 2.0 * M_PI * (double)m / (double)M;
+      t[m]            = make_float2((float)std::cos(ph), (float)std::sin(ph));
+    }
+  }
+  if (h->ulpool_used + M > h->d_ulpool.cap) return -1;
+  off = (uint32_t)h->ulpool_used;
+  if (cudaMemcpyAsync(h->d_ulpool.p + off, t.data(), M * sizeof(float2), cudaMemcpyHostToDevice, h->stream) != cudaSuccess) return -1;
+  cudaStreamSynchronize(h->stream);
+  h->ulpool_used += M;
+  h->ul_tab_cache[key] = off;
+  return 0;
+}
+
+extern "C" int ltephy_submit_ul(ltephy_t* h, const float* iq_ul, const uint32_t* tti, uint32_t n, const ltephy_ul_grant_t* gin, uint32_t ng)
+{
+  if (!h || !iq_ul || !tti || n == 0 || n > h->cfg.max_subframes || (!gin && ng)) return fail(LTEPHY_ERROR_INVALID_INPUTS, "submit_ul: bad arguments");
+  if (!h->ulcfg_set) return fail(LTEPHY_ERROR_INVALID_INPUTS, "submit_ul: ltephy_set_ul_cfg has not been called");
+  CU(cudaSetDevice(h->cfg.device));
+  const DevCell& c = h->dc;
+  if (h->d_uliq.reserve((size_t)h->cfg.max_subframes * c.sf_len) || h->d_ulsym.reserve((size_t)h->cfg.max_subframes * 14 * c.nsc) ||
+      h->d_ulpool.reserve((size_t)1 << 20))
+    return fail(LTEPHY_ERROR, "device allocation failed");
+  CU(cudaEventRecord(h->ev[2], h->stream));
+  CU(cudaMemcpyAsync(h->d_uliq.p, iq_ul, (size_t)n * c.sf_len * sizeof(float2), cudaMemcpyHostToDevice, h->stream));
+  launch_ul_ofdm(c, h->d_uliq.p, h->d_ulsym.p, n, h->stream, &h->launches);
+  h->n_ul = n;
+  // jobs
+  h->ulgrants.clear(), h->cbs.clear(), h->pairs.clear(), h->tbs.clear(), h->pair_pi_off.clear();
+  h->tb_slot.assign((size_t)ng, 0xFFFFFFFFu);
+  h->pllr_elems = 0, h->payload_bytes = 0;
+  size_t   seq_words = 0, turbo_words = 0;
+  uint32_t max_words = 0, max_M = 36;
+  int32_t  open_pair[188];
+  memset(open_pair, 0xFF, sizeof(open_pair));
+  for (uint32_t gi = 0; gi < ng; gi++) {
+    const ltephy_ul_grant_t& g = gin[gi];
+    if (g.sf >= n) return fail(LTEPHY_ERROR_INVALID_INPUTS, "UL grant %u: subframe outside the batch", gi);
+    const uint32_t M = 12 * g.L_prb;
+    if (g.L_prb < 3 || g.n_prb + g.L_prb > c.nof_prb || (g.qm != 2 && g.qm != 4 && g.qm != 6) || g.tbs <= 0)
+      return fail(LTEPHY_ERROR_INVALID_INPUTS, "UL grant %u: unsupported allocation / modulation", gi);
+    DevUlGrant d{};
+    d.sf = g.sf, d.sf_idx = tti[g.sf] % 10, d.rnti = g.rnti, d.M = M, d.k0 = 12 * g.n_prb, d.qm = g.qm;
+    for (uint32_t sl = 0; sl < 2; sl++) {
+      const uint32_t ncs = (h->ulcfg.n_dmrs1 + g.n_dmrs2 + h->n_prs[2 * d.sf_idx + sl]) % 12;
+      if (ul_table_for(h, 0, M, ncs, d.dmrs_off[sl])) return fail(LTEPHY_ERROR, "UL table upload failed");
+    }
+    if (ul_table_for(h, 1, M, 0, d.idft_off)) return fail(LTEPHY_ERROR, "UL table upload failed");
+    const uint32_t G = 12 * M * g.qm, w = (G + 31) / 32;
+    if (w > h->gold_words) return fail(LTEPHY_ERROR, "UL grant %u: codeword longer than the scrambling basis", gi);
+    d.llr_off = (uint32_t)h->pllr_elems, d.scr_off = (uint32_t)seq_words;
+    seq_words += w + 1;
+    h->pllr_elems += (G + 7) & ~7u;
+    max_words = std::max(max_words, w), max_M = std::max(max_M, M);
+    uint32_t tbi;
+    int      r = add_transport_block(h, (uint32_t)g.tbs, G, g.qm, g.rv, 1, d.llr_off, open_pair, turbo_words, tbi);
+    if (r) return r;
+    h->tb_slot[gi] = tbi;
+    h->ulgrants.push_back(d);
+  }
+  if (h->d_ulgrants.reserve(ng + 1) || h->d_ulchest.reserve(ng + 1) || h->h_ulchest.reserve(ng + 1) || h->d_tbs.reserve(h->tbs.size() + 1) ||
+      h->d_seq.reserve(seq_words + 1) || h->d_pllr.reserve(h->pllr_elems + 8) || h->d_turbo.reserve(turbo_words + 1) ||
+      h->d_payload.reserve(h->payload_bytes + 4) || h->d_cb_iters.reserve(h->cbs.size() + 1) || h->d_cb_crc.reserve(h->cbs.size() + 1) ||
+      h->d_res.reserve(h->tbs.size() + 1) || h->h_res.reserve(h->tbs.size() + 1) || h->h_payload.reserve(h->payload_bytes + 4))
+    return fail(LTEPHY_ERROR, "device allocation failed");
+  if (ng) {
+    CU(cudaMemcpyAsync(h->d_ulgrants.p, h->ulgrants.data(), ng * sizeof(DevUlGrant), cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemcpyAsync(h->d_tbs.p, h->tbs.data(), h->tbs.size() * sizeof(DevTb), cudaMemcpyHostToDevice, h->stream));
+    launch_pusch(c, h->d_ulgrants.p, ng, max_M, max_words, h->d_ulsym.p, h->d_ulpool.p, h->d_ulpool.p, h->d_gold_x1, h->d_gold_basis, h->gold_words,
+                 h->d_seq.p, h->d_pllr.p, h->d_ulchest.p, h->stream, &h->launches);
+    int r = run_turbo_stage(h, h->cfg.turbo_max_iter);
+    if (r) return r;
+    launch_tb_crc(h->d_tbs.p, (uint32_t)h->tbs.size(), h->d_payload.p, h->d_cb_crc.p, h->d_cb_iters.p, h->d_xpowA, h->d_res.p, h->stream, &h->launches);
+  }
+  CU(cudaEventRecord(h->ev[3], h->stream));
+  CU(cudaGetLastError());
+  return LTEPHY_SUCCESS;
+}
+
+extern "C" int ltephy_get_ul(ltephy_t* h, ltephy_tb_result_t* results, ltephy_ul_chest_t* chest, uint8_t* payload, size_t payload_cap)
+{
+  if (!h || !results) return fail(LTEPHY_ERROR_INVALID_INPUTS, "get_ul: bad arguments");
+  const size_t ng = h->ulgrants.size();
+  if (ng) CU(cudaMemcpyAsync(h->h_ulchest.p, h->d_ulchest.p, ng * sizeof(ltephy_ul_chest_t), cudaMemcpyDeviceToHost, h->stream));
+  // transport blocks come back through the shared phase-B path (one result per grant)
+  std::vector<ltephy_tb_result_t> res(ng + 1);
+  {
+    const size_t ntb = h->tbs.size();
+    if (ntb) {
+      CU(cudaMemcpyAsync(h->h_res.p, h->d_res.p, ntb * sizeof(ltephy_tb_result_t), cudaMemcpyDeviceToHost, h->stream));
+      CU(cudaMemcpyAsync(h->h_payload.p, h->d_payload.p, h->payload_bytes, cudaMemcpyDeviceToHost, h->stream));
+    }
+    CU(cudaStreamSynchronize(h->stream));
+  }
+  size_t wp = 0;
+  for (size_t i = 0; i < ng; i++) {
+    ltephy_tb_result_t o{};
+    if (h->tb_slot[i] != 0xFFFFFFFFu) {
+      const DevTb& tb = h->tbs[h->tb_slot[i]];
+      o               = h->h_res.p[h->tb_slot[i]];
+      o.payload_off   = (uint32_t)wp;
+      o.payload_len   = tb.nbytes;
+      if (payload) {
+        if (wp + tb.nbytes > payload_cap) return fail(LTEPHY_ERROR_INVALID_INPUTS, "payload buffer too small");
+        memcpy(payload + wp, h->h_payload.p + tb.byte_off, tb.nbytes);
+      }
+      wp += tb.nbytes;
+    }
+    results[i] = o;
+    if (chest) {
+      chest[i]        = h->h_ulchest.p[i];
+      chest[i].snr_db = 10.0f * log10f(chest[i].rsrp / chest[i].noise);
+      chest[i].ta_us  = 0.0f;
+    }
+  }
+  return LTEPHY_SUCCESS;
+}
+
 // ---------------------------------------------------------------------------------------- stand-alone kernels
 extern "C" int ltephy_dci_sweep(ltephy_t* h, const float* llr, const uint32_t* cfi, uint32_t n, ltephy_cand_t* cands)
 {
@@ -801,6 +1006,7 @@ extern "C" int ltephy_tap(ltephy_t* h, int what, void* dst, size_t bytes)
     case LTEPHY_TAP_LLR: src = h->d_llr.p, avail = n * LLR_STRIDE * sizeof(float); break;
     case LTEPHY_TAP_PDSCH_LLR: src = h->d_pllr.p, avail = h->pllr_elems * sizeof(short); break;
     case LTEPHY_TAP_TURBO_IN: src = h->d_turbo.p, avail = h->d_turbo.cap * 4; break;
+    case LTEPHY_TAP_UL_SYM: src = h->d_ulsym.p, avail = (size_t)h->n_ul * 14 * h->dc.nsc * sizeof(float2); break;
     default: return fail(LTEPHY_ERROR_INVALID_INPUTS, "tap: unknown buffer");
   }
   if (bytes > avail) return fail(LTEPHY_ERROR_INVALID_INPUTS, "tap: %zu bytes requested, %zu available", bytes, avail);

@@ -332,6 +332,56 @@ static void eq_cdd(const lteo_t* q, const cf_t* const* sym, const cf_t* const* c
   x1->im = ((a1.im * det.re - a1.re * det.im) / dd) * 2.0f;
 }
 
+/* closed-loop spatial multiplexing, 2 CRS ports (36.211 Table 6.3.4.2.3-1).  w = second precoder entry:
+ * 1 layer: W = (1/sqrt2)[1, w]^T, w in {1,-1,j,-j} (pmi 0..3); 2 layers: W = (1/2)[[1,1],[w,-w]], w in {1, j} (pmi 0,1) */
+static void spmux_w(uint32_t nof_layers, uint32_t pmi, float* wr, float* wi)
+{
+  static const float W1[4][2] = {{1, 0}, {-1, 0}, {0, 1}, {0, -1}};
+  static const float W2[2][2] = {{1, 0}, {0, 1}};
+  if (nof_layers == 1)
+    *wr = W1[pmi & 3][0], *wi = W1[pmi & 3][1];
+  else
+    *wr = W2[pmi & 1][0], *wi = W2[pmi & 1][1];
+}
+static cf_t eq_spmux1(const lteo_t* q, const cf_t* const* sym, const cf_t* const* ce, uint32_t idx, float wr, float wi)
+{
+  const uint32_t A = q->cell.nof_rx;
+  float          nr = 0.0f, ni = 0.0f, den = 0.0f;
+  for (uint32_t a = 0; a < A; a++) {
+    cf_t y = sym[a][idx], h0 = ce[0 * A + a][idx], h1 = ce[1 * A + a][idx];
+    cf_t e = {h0.re + (wr * h1.re - wi * h1.im), h0.im + (wr * h1.im + wi * h1.re)};
+    nr  = nr + (e.re * y.re + e.im * y.im);
+    ni  = ni + (e.re * y.im - e.im * y.re);
+    den = den + (e.re * e.re + e.im * e.im);
+  }
+  const float s2 = 1.41421354f;
+  return (cf_t){(nr / den) * s2, (ni / den) * s2};
+}
+/* x = 2 E^-1 r for E = [[e00, e01], [e10, e11]] (rows: rx antennas, columns: layers) */
+static void zf2x2(cf_t e00, cf_t e01, cf_t e10, cf_t e11, cf_t r0, cf_t r1, cf_t* x0, cf_t* x1)
+{
+  cf_t det = {(e00.re * e11.re - e00.im * e11.im) - (e01.re * e10.re - e01.im * e10.im),
+              (e00.re * e11.im + e00.im * e11.re) - (e01.re * e10.im + e01.im * e10.re)};
+  cf_t a0  = {(e11.re * r0.re - e11.im * r0.im) - (e01.re * r1.re - e01.im * r1.im),
+              (e11.re * r0.im + e11.im * r0.re) - (e01.re * r1.im + e01.im * r1.re)};
+  cf_t a1  = {(e00.re * r1.re - e00.im * r1.im) - (e10.re * r0.re - e10.im * r0.im),
+              (e00.re * r1.im + e00.im * r1.re) - (e10.re * r0.im + e10.im * r0.re)};
+  float dd = det.re * det.re + det.im * det.im;
+  x0->re = ((a0.re * det.re + a0.im * det.im) / dd) * 2.0f;
+  x0->im = ((a0.im * det.re - a0.re * det.im) / dd) * 2.0f;
+  x1->re = ((a1.re * det.re + a1.im * det.im) / dd) * 2.0f;
+  x1->im = ((a1.im * det.re - a1.re * det.im) / dd) * 2.0f;
+}
+static void eq_spmux2(const cf_t* const* sym, const cf_t* const* ce, uint32_t idx, float wr, float wi, cf_t* x0, cf_t* x1)
+{
+  cf_t h00 = ce[0][idx], h10 = ce[1][idx], h01 = ce[2][idx], h11 = ce[3][idx]; /* [port*2 + ant] */
+  cf_t w0 = {wr * h01.re - wi * h01.im, wr * h01.im + wi * h01.re}; /* w * h(ant0, port1) */
+  cf_t w1 = {wr * h11.re - wi * h11.im, wr * h11.im + wi * h11.re};
+  cf_t e00 = {h00.re + w0.re, h00.im + w0.im}, e01 = {h00.re - w0.re, h00.im - w0.im};
+  cf_t e10 = {h10.re + w1.re, h10.im + w1.im}, e11 = {h10.re - w1.re, h10.im - w1.im};
+  zf2x2(e00, e01, e10, e11, sym[0][idx], sym[1][idx], x0, x1);
+}
+
 /* equalise n control-channel REs given by grid indices (n multiple of 2 for 2 ports) */
 static void eq_ctrl(const lteo_t* q, const cf_t* const* sym, const cf_t* const* ce, const uint32_t* idx, uint32_t n, cf_t* d)
 {
@@ -535,9 +585,16 @@ int lteo_pdsch_llr(lteo_t* q, uint32_t sf_idx, uint32_t cfi, uint16_t rnti, cons
     for (uint32_t i = 0; i + 1 < n; i += 2) eq_sfbc(q, sym, ce, idx[i], idx[i + 1], &x[0][i], &x[0][i + 1]);
   } else if (g->tx_scheme == LTE_TX_CDD && q->cell.nof_rx == 2 && q->cell.nof_ports == 2) {
     for (uint32_t i = 0; i < n; i++) eq_cdd(q, sym, ce, idx[i], (int)(i & 1), &x[0][i], &x[1][i]);
+  } else if (g->tx_scheme == LTE_TX_SPATIALMUX && q->cell.nof_ports == 2 && (g->nof_layers == 1 || q->cell.nof_rx == 2)) {
+    float wr, wi;
+    spmux_w(g->nof_layers, g->pmi, &wr, &wi);
+    if (g->nof_layers == 1)
+      for (uint32_t i = 0; i < n; i++) x[0][i] = eq_spmux1(q, sym, ce, idx[i], wr, wi);
+    else
+      for (uint32_t i = 0; i < n; i++) eq_spmux2(sym, ce, idx[i], wr, wi, &x[0][i], &x[1][i]);
   } else {
     free(idx), free(x[0]), free(x[1]);
-    return -2; /* spatial multiplexing (TM4): next round */
+    return -2;
   }
   static __thread uint8_t scr[110 * 12 * 14 * 8];
   for (uint32_t cw = 0; cw < ncw; cw++) {
@@ -788,4 +845,122 @@ int lteo_phase_a(lteo_t* q, const cf_t* iq, uint32_t sf_idx, cf_t* sym /* [nof_r
   float corr[3];
   *cfi_out = lteo_pcfich_decode(q, sf_idx, symp, (const cf_t* const*)cep, corr);
   return (int)lteo_pdcch_extract_llr(q, sf_idx, *cfi_out, symp, (const cf_t* const*)cep, llr);
+}
+
+/* ================================================================== uplink (PUSCH) */
+void lteo_ul_ofdm(lteo_t* q, const cf_t* iq, cf_t* sym)
+{
+  const uint32_t N = q->fft, h = q->nsc / 2;
+  float*         re = (float*)malloc(sizeof(float) * N);
+  float*         im = (float*)malloc(sizeof(float) * N);
+  cf_t*          x  = (cf_t*)malloc(sizeof(cf_t) * N);
+  for (uint32_t l = 0; l < 14; l++) {
+    const cf_t* in = iq + q->sym_off[l];
+    for (uint32_t n = 0; n < N; n++) { /* multiply by exp(-j pi n / N) */
+      double ph = M_PI * (double)n / (double)N;
+      float  cr = (float)cos(ph), ci = (float)-sin(ph);
+      x[n].re   = in[n].re * cr - in[n].im * ci;
+      x[n].im   = in[n].re * ci + in[n].im * cr;
+    }
+    fft_fwd(q, x, re, im);
+    for (uint32_t kk = 0; kk < q->nsc; kk++) {
+      uint32_t bin          = (kk + N - h) % N;
+      sym[l * q->nsc + kk] = (cf_t){re[bin], im[bin]};
+    }
+  }
+  free(re), free(im), free(x);
+}
+
+int lteo_pusch_decode(lteo_t* q, const lte_ul_cfg_t* ucfg, uint32_t sf_idx, const lte_ul_grant_t* g, const cf_t* sym, uint32_t max_iter,
+                      uint8_t* payload, int* crc_ok, lteo_ul_chest_t* chest, int16_t* llr_out)
+{
+  static const uint32_t DATA_SYM[12] = {0, 1, 2, 4, 5, 6, 7, 8, 9, 11, 12, 13};
+  const uint32_t        M = 12 * g->L_prb, k0 = 12 * g->n_prb, nsc = q->nsc, Qm = g->qm, G = g->nof_bits;
+  if (M < 36 || k0 + M > nsc || G != 12 * M * Qm) return -1;
+  cf_t*  r   = (cf_t*)malloc(sizeof(cf_t) * M);
+  cf_t*  ls  = (cf_t*)malloc(sizeof(cf_t) * 2 * M);
+  cf_t*  sm  = (cf_t*)malloc(sizeof(cf_t) * 2 * M);
+  float* tmp = (float*)malloc(sizeof(float) * M);
+  /* smoothing taps (w, 1-2w, w), w = 0.3333 (srsRAN chest_ul default 3-tap filter), edges renormalised */
+  const float f[3] = {0.3333f, 1.0f - 2.0f * 0.3333f, 0.3333f};
+  const float ncorr = (1.0f - 2.0f * f[1]) + (f[0] * f[0] + f[1] * f[1] + f[2] * f[2]);
+  float       nsum = 0.0f, psum = 0.0f;
+  for (uint32_t sl = 0; sl < 2; sl++) {
+    if (lte_pusch_dmrs(&q->cell, ucfg, 2 * sf_idx + sl, g->n_dmrs2, M, r)) {
+      free(r), free(ls), free(sm), free(tmp);
+      return -2;
+    }
+    for (uint32_t n = 0; n < M; n++) {
+      cf_t y = sym[(7 * sl + 3) * nsc + k0 + n];
+      ls[sl * M + n].re = y.re * r[n].re + y.im * r[n].im;
+      ls[sl * M + n].im = y.im * r[n].re - y.re * r[n].im;
+    }
+    for (uint32_t n = 0; n < M; n++) {
+      float ar = 0.0f, ai = 0.0f, ws = 0.0f;
+      for (int j = 0; j < 3; j++) {
+        int nn = (int)n + j - 1;
+        if (nn < 0 || nn >= (int)M) continue;
+        ar = ar + f[j] * ls[sl * M + nn].re;
+        ai = ai + f[j] * ls[sl * M + nn].im;
+        ws = ws + f[j];
+      }
+      sm[sl * M + n].re = ar / ws;
+      sm[sl * M + n].im = ai / ws;
+    }
+    for (uint32_t n = 0; n < M; n++) {
+      float dr = ls[sl * M + n].re - sm[sl * M + n].re, di = ls[sl * M + n].im - sm[sl * M + n].im;
+      tmp[n]   = dr * dr + di * di;
+    }
+    nsum = nsum + lteo_det_sum(tmp, M);
+    for (uint32_t n = 0; n < M; n++) tmp[n] = sm[sl * M + n].re * sm[sl * M + n].re + sm[sl * M + n].im * sm[sl * M + n].im;
+    psum = psum + lteo_det_sum(tmp, M);
+  }
+  if (chest) {
+    chest->noise  = (nsum / (float)(2 * M)) / ncorr;
+    chest->rsrp   = psum / (float)(2 * M);
+    chest->snr_db = 10.0f * log10f(chest->rsrp / chest->noise);
+  }
+  /* IDFT twiddles W[m] = exp(+j 2 pi m / M) */
+  cf_t* W = (cf_t*)malloc(sizeof(cf_t) * M);
+  for (uint32_t m = 0; m < M; m++) {
+    double ph = 2.0 * M_PI * (double)m / (double)M;
+    W[m]      = (cf_t){(float)cos(ph), (float)sin(ph)};
+  }
+  const float scl = 1.0f / sqrtf((float)M);
+  cf_t*       x   = (cf_t*)malloc(sizeof(cf_t) * M);
+  int16_t*    e   = (int16_t*)malloc(sizeof(int16_t) * (G + 16));
+  uint8_t*    scr = (uint8_t*)malloc(G);
+  lte_gold_bits(((uint32_t)g->rnti << 14) + (sf_idx << 9) + q->cell.cell_id, scr, G);
+  for (uint32_t c = 0; c < 12; c++) {
+    const uint32_t l = DATA_SYM[c];
+    const float    t = (float)((int)l - 3) / 7.0f;
+    for (uint32_t n = 0; n < M; n++) {
+      cf_t A = sm[n], B = sm[M + n];
+      cf_t h = {A.re + (B.re - A.re) * t, A.im + (B.im - A.im) * t};
+      cf_t y = sym[l * nsc + k0 + n];
+      float den = h.re * h.re + h.im * h.im;
+      x[n].re   = (y.re * h.re + y.im * h.im) / den;
+      x[n].im   = (y.im * h.re - y.re * h.im) / den;
+    }
+    for (uint32_t k = 0; k < M; k++) {
+      float ar = 0.0f, ai = 0.0f;
+      for (uint32_t i = 0; i < M; i++) {
+        cf_t w = W[(uint32_t)(((uint64_t)i * k) % M)];
+        ar     = ar + (x[i].re * w.re - x[i].im * w.im);
+        ai     = ai + (x[i].re * w.im + x[i].im * w.re);
+      }
+      cf_t    z = {ar * scl, ai * scl};
+      int16_t v[8];
+      demod_s(z, Qm, v);
+      for (uint32_t b = 0; b < Qm; b++) {
+        uint32_t hb = (c * M + k) * Qm + b; /* position in the interleaved (transmitted) order */
+        int16_t  d  = scr[hb] ? (int16_t)-v[b] : v[b];
+        e[(k * 12 + c) * Qm + b] = d;       /* channel de-interleaver, 36.212 5.2.2.8 */
+      }
+    }
+  }
+  if (llr_out) memcpy(llr_out, e, sizeof(int16_t) * G);
+  *crc_ok = lteo_dlsch_decode(e, G, (uint32_t)g->tbs, g->rv, Qm, 1, max_iter, 1, payload, NULL);
+  free(r), free(ls), free(sm), free(tmp), free(W), free(x), free(e), free(scr);
+  return 0;
 }

@@ -81,3 +81,22 @@ int lteo_phase_a(lteo_t* q, const cf_t* iq, uint32_t sf_idx, cf_t* sym, cf_t* ce
 }
 #endif
 #endif
+
+/* ================================================================== uplink (PUSCH) -- ORACLE
+ * restates srsran_enb_ul_fft + srsran_chest_ul_estimate_pusch + srsran_pusch_decode as called from
+ * PUSCH_Decoder::decode / decode_run (src/src/UL_Sniffer_PUSCH.cc:250-263,389-392) for grants without UCI,
+ * without hopping, L_prb >= 3. */
+#ifdef __cplusplus
+extern "C" {
+#endif
+typedef struct {
+  float noise, rsrp, snr_db;
+} lteo_ul_chest_t;
+/* K1-UL: iq[sf_len] -> sym[14*nsc] with the 7.5 kHz shift removed */
+void lteo_ul_ofdm(lteo_t* q, const cf_t* iq, cf_t* sym);
+/* K9: one PUSCH grant; llr_out (optional) receives the nof_bits descrambled, de-interleaved int16 soft bits */
+int lteo_pusch_decode(lteo_t* q, const lte_ul_cfg_t* ucfg, uint32_t sf_idx, const lte_ul_grant_t* g, const cf_t* sym, uint32_t max_iter,
+                      uint8_t* payload, int* crc_ok, lteo_ul_chest_t* chest, int16_t* llr_out);
+#ifdef __cplusplus
+}
+#endif

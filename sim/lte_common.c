@@ -894,3 +894,76 @@ double lte_rng_gauss(lte_rng_t* r)
   if (u1 < 1e-300) u1 = 1e-300;
   return sqrt(-2.0 * log(u1)) * cos(2.0 * M_PI * u2);
 }
+
+/* ================================================================== uplink */
+int lte_ul_valid_prb(uint32_t L)
+{
+  if (L == 0) return 0;
+  while (L % 2 == 0) L /= 2;
+  while (L % 3 == 0) L /= 3;
+  while (L % 5 == 0) L /= 5;
+  return L == 1;
+}
+uint32_t lte_largest_prime_below(uint32_t n)
+{
+  for (uint32_t p = n - 1; p >= 2; p--) {
+    int ok = 1;
+    for (uint32_t d = 2; d * d <= p; d++)
+      if (p % d == 0) {
+        ok = 0;
+        break;
+      }
+    if (ok) return p;
+  }
+  return 2;
+}
+int lte_ul_dci_to_grant(const lte_cell_t* c, const lte_dci_t* d, int table, lte_ul_grant_t* g)
+{
+  static const uint8_t dmrs2_map[8] = {0, 6, 3, 4, 2, 8, 10, 9}; /* 36.211 Table 5.5.2.1.1-1 */
+  memset(g, 0, sizeof(*g));
+  if (d->format != LTE_DCI_FORMAT0 || d->hop) return -1;
+  uint32_t L, S;
+  riv_decode(d->riv, c->nof_prb, &L, &S);
+  if (L < 1 || L > c->nof_prb || S + L > c->nof_prb) return -1;
+  g->rnti = d->rnti, g->L_prb = L, g->n_prb = S, g->mcs = d->mcs[0], g->n_dmrs2 = dmrs2_map[d->n_dmrs & 7];
+  uint32_t m = d->mcs[0];
+  int      itbs;
+  if (m <= 10)
+    g->qm = 2, itbs = (int)m;
+  else if (m <= 20)
+    g->qm = 4, itbs = (int)m - 1;
+  else if (m <= 28)
+    g->qm = table ? 6 : 4, itbs = (int)m - 2;
+  else
+    return -2; /* retransmission MCS: needs the HARQ state the sniffer does not have */
+  g->rv  = 0;
+  g->tbs = lte_tbs_from_idx(itbs, L);
+  if (g->tbs <= 0) return -2;
+  g->nof_re   = 12 * L * 12; /* 12 data SC-FDMA symbols, no SRS */
+  g->nof_bits = g->nof_re * g->qm;
+  return 0;
+}
+int lte_pusch_dmrs(const lte_cell_t* c, const lte_ul_cfg_t* u, uint32_t ns, uint32_t n_dmrs2, uint32_t M, cf_t* r)
+{
+  if (M < 36 || u->group_hopping || u->seq_hopping) return -1;
+  uint32_t fss  = ((c->cell_id % 30) + u->delta_ss) % 30; /* f_ss^PUSCH; group hopping off -> u = f_ss */
+  uint32_t useq = fss;
+  /* n_PRS(ns), 36.211 5.5.2.1.1 */
+  uint8_t  cbits[8 * 7 * 20 + 8];
+  lte_gold_bits((c->cell_id / 30) * 32 + fss, cbits, 8 * 7 * 20 + 8);
+  uint32_t nprs = 0;
+  for (uint32_t i = 0; i < 8; i++) nprs += (uint32_t)cbits[8 * 7 * ns + i] << i;
+  uint32_t ncs = (u->n_dmrs1 + n_dmrs2 + nprs) % 12;
+  uint32_t Nzc = lte_largest_prime_below(M);
+  double   qb  = (double)Nzc * (useq + 1) / 31.0;
+  uint32_t q   = (uint32_t)floor(qb + 0.5); /* v = 0 */
+  for (uint32_t n = 0; n < M; n++) {
+    uint64_t m  = n % Nzc;
+    uint64_t t  = ((uint64_t)q * m * (m + 1)) % (2ull * Nzc);   /* phase = -pi t / Nzc */
+    uint32_t a  = (ncs * n) % 12;                               /* + 2 pi a / 12 */
+    double   ph = -M_PI * (double)t / (double)Nzc + 2.0 * M_PI * (double)a / 12.0;
+    r[n].re     = (float)cos(ph);
+    r[n].im     = (float)sin(ph);
+  }
+  return 0;
+}

@@ -206,3 +206,39 @@ double   lte_rng_gauss(lte_rng_t* r);
 }
 #endif
 #endif
+
+/* ================================================================== uplink (PUSCH), 36.211 5.x / 36.213 8 */
+#ifndef LTE_COMMON_UL_H
+#define LTE_COMMON_UL_H
+#ifdef __cplusplus
+extern "C" {
+#endif
+typedef struct {
+  uint32_t n_dmrs1;       /* cyclicShift (SIB2 -> ULSchedule::set_config, src/src/ULSchedule.cc:140-158) */
+  uint32_t delta_ss;      /* groupAssignmentPUSCH */
+  uint32_t group_hopping; /* must be 0 (disabled) in this round */
+  uint32_t seq_hopping;   /* must be 0 */
+} lte_ul_cfg_t;
+
+typedef struct {
+  uint16_t rnti;
+  uint32_t L_prb, n_prb; /* contiguous allocation, no hopping */
+  uint32_t mcs, qm, rv;
+  int32_t  tbs;
+  uint32_t n_dmrs2;      /* mapped from the 3-bit cyclic shift field of DCI format 0 */
+  uint32_t nof_re, nof_bits;
+} lte_ul_grant_t;
+
+/* L_prb must be 2^a 3^b 5^c (valid_prb_ul, src/src/UL_Sniffer_PUSCH.cc:3-10) */
+int lte_ul_valid_prb(uint32_t L_prb);
+/* restates srsran_ra_ul_dci_to_grant as used at falcon_dci.c:222; table: 0 = 16QAM cap (enable_64qam false), 1 = 64QAM.
+ * returns 0 ok */
+int lte_ul_dci_to_grant(const lte_cell_t* c, const lte_dci_t* d, int table, lte_ul_grant_t* g);
+/* DMRS for PUSCH (36.211 5.5.2.1) for slot ns: M_sc complex values; returns 0, or -1 if M_sc < 36 (the
+ * computer-generated 1- and 2-PRB base sequences are not implemented) */
+int lte_pusch_dmrs(const lte_cell_t* c, const lte_ul_cfg_t* u, uint32_t ns, uint32_t n_dmrs2, uint32_t M_sc, cf_t* r);
+uint32_t lte_largest_prime_below(uint32_t n);
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -287,7 +287,12 @@ int lte_sim_subframe(lte_sim_t* s, uint32_t tti, cf_t* iq, lte_sim_truth_t* trut
       kind       = r == 0 ? 1 : r == 1 ? 101 : r == 2 ? 3 : 103;
       if (cell->nof_ports == 1 && kind != 101) kind = 1;
     }
-    if (kind == 3 && cell->nof_ports != 2) kind = 1;
+    if (cfg->tm == 4) { /* closed-loop spatial multiplexing (DCI format 2): 2 codewords, or 1 codeword on 1 layer */
+      uint32_t r = (uint32_t)(lte_rng_u64(&rng) % 3);
+      kind       = r == 0 ? 104 : 4;
+    }
+    if ((kind == 3 || kind == 4 || kind == 104) && cell->nof_ports != 2) kind = 1;
+    if (kind == 4 && cell->nof_rx != 2) kind = 104;
     uint32_t rb0 = rbg_next, nr = chunk[i];
     rbg_next += nr;
     if (kind == 101) { /* 1A localized */
@@ -297,7 +302,9 @@ int lte_sim_subframe(lte_sim_t* s, uint32_t tti, cf_t* iq, lte_sim_truth_t* trut
       if (S + L > N) L = N - S;
       d->riv = (L - 1 <= N / 2) ? N * (L - 1) + S : N * (N - L + 1) + (N - 1 - S);
     } else {
-      d->format     = (kind == 1) ? LTE_DCI_FORMAT1 : LTE_DCI_FORMAT2A;
+      d->format     = (kind == 1) ? LTE_DCI_FORMAT1 : (kind == 4 || kind == 104) ? LTE_DCI_FORMAT2 : LTE_DCI_FORMAT2A;
+      if (kind == 4) d->pinfo = (uint8_t)(lte_rng_u64(&rng) % 2);
+      if (kind == 104) d->pinfo = (uint8_t)(1 + lte_rng_u64(&rng) % 4);
       d->alloc_type = 0;
       for (uint32_t r = rb0; r < rb0 + nr; r++) d->rbg_bitmask |= 1u << (nrbg - 1 - r);
     }
@@ -309,7 +316,7 @@ int lte_sim_subframe(lte_sim_t* s, uint32_t tti, cf_t* iq, lte_sim_truth_t* trut
       d->rv[t]  = 0;
     }
     d->tb_en[0] = 1;
-    d->tb_en[1] = (kind == 3);
+    d->tb_en[1] = (kind == 3 || kind == 4);
     if (kind == 101 && d->mcs[0] > 28) d->mcs[0] = 28;
   }
   for (uint32_t i = 0; i < n_ul && njobs < LTE_SIM_MAX_DCI; i++) {
@@ -441,6 +448,20 @@ int lte_sim_subframe(lte_sim_t* s, uint32_t tti, cf_t* iq, lte_sim_truth_t* trut
               pair_k = k;
             } else
               put_txdiv(s, pair_l, pair_k, l, k, s->dsym[0][isym - 1], s->dsym[0][isym]);
+          } else if (g.tx_scheme == LTE_TX_SPATIALMUX) { /* codebook precoding, 36.211 Table 6.3.4.2.3-1, 2 ports */
+            static const float W1[4][2] = {{1, 0}, {-1, 0}, {0, 1}, {0, -1}};
+            if (g.nof_layers == 1) {
+              cf_t        x = s->dsym[0][isym];
+              const float a = (float)M_SQRT1_2, wr = W1[g.pmi & 3][0], wi = W1[g.pmi & 3][1];
+              s->grid[0][l * nsc + k] = (cf_t){a * x.re, a * x.im};
+              s->grid[1][l * nsc + k] = (cf_t){a * (wr * x.re - wi * x.im), a * (wr * x.im + wi * x.re)};
+            } else {
+              cf_t        x0 = s->dsym[0][isym], x1 = s->dsym[1][isym];
+              const float wr = (g.pmi & 1) ? 0.0f : 1.0f, wi = (g.pmi & 1) ? 1.0f : 0.0f;
+              cf_t        dd = {x0.re - x1.re, x0.im - x1.im};
+              s->grid[0][l * nsc + k] = (cf_t){0.5f * (x0.re + x1.re), 0.5f * (x0.im + x1.im)};
+              s->grid[1][l * nsc + k] = (cf_t){0.5f * (wr * dd.re - wi * dd.im), 0.5f * (wr * dd.im + wi * dd.re)};
+            }
           } else { /* large-delay CDD, 2 layers, 2 ports: y = W D(i) U x */
             cf_t  x0 = s->dsym[0][isym], x1 = s->dsym[1][isym];
             float sg = (isym & 1) ? -1.0f : 1.0f;
@@ -511,6 +532,102 @@ int lte_sim_subframe(lte_sim_t* s, uint32_t tti, cf_t* iq, lte_sim_truth_t* trut
       }
       out[n] = (cf_t){(float)re, (float)im};
     }
+  }
+  return 0;
+}
+
+/* ================================================================== uplink: PUSCH transmitter */
+int lte_sim_ul_subframe(lte_sim_t* s, uint32_t tti, const lte_ul_cfg_t* ucfg, const lte_ul_grant_t* grants, uint32_t n, cf_t* iq, uint8_t* payload,
+                        uint32_t* payload_off, uint32_t payload_cap)
+{
+  const lte_cell_t* cell = &s->cfg.cell;
+  const uint32_t    sf_idx = tti % 10, nsc = s->nsc, N = s->fft;
+  lte_rng_t         rng;
+  lte_rng_seed(&rng, s->cfg.seed * 0x51ED27ull + 977ull * tti + 5);
+  cf_t* grid = s->grid[0];
+  memset(grid, 0, 14 * nsc * sizeof(cf_t));
+  uint32_t pl_off = 0;
+  static const uint32_t DATA_SYM[12] = {0, 1, 2, 4, 5, 6, 7, 8, 9, 11, 12, 13};
+  for (uint32_t gi = 0; gi < n; gi++) {
+    const lte_ul_grant_t* g = &grants[gi];
+    const uint32_t        M = 12 * g->L_prb, k0 = 12 * g->n_prb, G = g->nof_bits, Qm = g->qm, H = G / Qm;
+    if ((uint32_t)g->tbs / 8 + pl_off > payload_cap) return -1;
+    uint8_t* pl = payload + pl_off;
+    payload_off[gi] = pl_off;
+    for (uint32_t i = 0; i < (uint32_t)g->tbs / 8; i++) pl[i] = (uint8_t)lte_rng_u64(&rng);
+    pl_off += (uint32_t)g->tbs / 8;
+    uint8_t* e = s->ebits;
+    if (lte_sim_dlsch_encode(pl, (uint32_t)g->tbs, g->rv, G, Qm, 1, e)) return -2;
+    /* channel interleaver 36.212 5.2.2.8 (no UCI): R' x 12 matrix of Qm-bit groups, row-wise in, column-wise out */
+    uint8_t* h = s->tbbits;
+    for (uint32_t c = 0; c < 12; c++)
+      for (uint32_t r = 0; r < M; r++) memcpy(&h[(c * M + r) * Qm], &e[(r * 12 + c) * Qm], Qm);
+    uint8_t* sc = (uint8_t*)malloc(G);
+    lte_gold_bits(((uint32_t)g->rnti << 14) + (sf_idx << 9) + cell->cell_id, sc, G);
+    for (uint32_t i = 0; i < G; i++) h[i] ^= sc[i];
+    free(sc);
+    lte_modulate(h, H, Qm, s->dsym[0]);
+    /* transform precoding + mapping */
+    double* wr = (double*)malloc(sizeof(double) * M * 2);
+    for (uint32_t m = 0; m < M; m++) {
+      wr[2 * m]     = cos(2.0 * M_PI * m / M);
+      wr[2 * m + 1] = -sin(2.0 * M_PI * m / M);
+    }
+    double sc_dft = 1.0 / sqrt((double)M);
+    for (uint32_t c = 0; c < 12; c++) {
+      const cf_t* d = &s->dsym[0][c * M];
+      for (uint32_t k = 0; k < M; k++) {
+        double ar = 0, ai = 0;
+        for (uint32_t i = 0; i < M; i++) {
+          uint32_t t = (uint32_t)(((uint64_t)i * k) % M);
+          ar += d[i].re * wr[2 * t] - d[i].im * wr[2 * t + 1];
+          ai += d[i].re * wr[2 * t + 1] + d[i].im * wr[2 * t];
+        }
+        grid[DATA_SYM[c] * nsc + k0 + k] = (cf_t){(float)(ar * sc_dft), (float)(ai * sc_dft)};
+      }
+    }
+    free(wr);
+    cf_t* r = (cf_t*)malloc(sizeof(cf_t) * M);
+    for (uint32_t sl = 0; sl < 2; sl++) {
+      if (lte_pusch_dmrs(cell, ucfg, 2 * sf_idx + sl, g->n_dmrs2, M, r)) {
+        free(r);
+        return -3;
+      }
+      for (uint32_t k = 0; k < M; k++) grid[(7 * sl + 3) * nsc + k0 + k] = r[k];
+    }
+    free(r);
+  }
+  /* SC-FDMA modulation with the half-subcarrier shift (36.211 5.6) */
+  double scl = 1.0 / sqrt((double)N);
+  uint32_t pos = 0;
+  for (uint32_t l = 0; l < 14; l++) {
+    memset(s->fre, 0, N * sizeof(double));
+    memset(s->fim, 0, N * sizeof(double));
+    for (uint32_t kk = 0; kk < nsc; kk++) {
+      uint32_t bin = (kk + N - nsc / 2) % N;
+      s->fre[bin]  = grid[l * nsc + kk].re;
+      s->fim[bin]  = grid[l * nsc + kk].im;
+    }
+    fft_inplace(s->fre, s->fim, N, 1);
+    uint32_t cp = lte_cp_len(N, l % 7);
+    for (int nn = -(int)cp; nn < (int)N; nn++) {
+      uint32_t m  = (uint32_t)((nn + (int)N) % (int)N);
+      double   ph = M_PI * (double)nn / (double)N;
+      double   re = s->fre[m] * cos(ph) - s->fim[m] * sin(ph), im = s->fre[m] * sin(ph) + s->fim[m] * cos(ph);
+      s->td[0][pos++] = (cf_t){(float)(re * scl), (float)(im * scl)};
+    }
+  }
+  double sigma = pow(10.0, -s->cfg.snr_db / 20.0) * M_SQRT1_2;
+  float  hr = s->h_re[0][0], hi = s->h_im[0][0];
+  uint32_t dl = s->delay[0][0];
+  for (uint32_t i = 0; i < s->sf_len; i++) {
+    double re = sigma * lte_rng_gauss(&rng), im = sigma * lte_rng_gauss(&rng);
+    if (i >= dl) {
+      cf_t x = s->td[0][i - dl];
+      re += (double)hr * x.re - (double)hi * x.im;
+      im += (double)hr * x.im + (double)hi * x.re;
+    }
+    iq[i] = (cf_t){(float)re, (float)im};
   }
   return 0;
 }

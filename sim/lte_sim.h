@@ -71,3 +71,14 @@ int lte_sim_dlsch_encode(const uint8_t* payload, uint32_t tbs, uint32_t rv, uint
 }
 #endif
 #endif
+
+/* ---- uplink: one subframe of PUSCH from several UEs on one rx antenna (the reference decodes PUSCH from
+ * antenna buffer 1, src/src/UL_Sniffer_PUSCH.cc:391-392).  grants: already valid (lte_ul_dci_to_grant). */
+#ifdef __cplusplus
+extern "C" {
+#endif
+int lte_sim_ul_subframe(lte_sim_t* s, uint32_t tti, const lte_ul_cfg_t* ucfg, const lte_ul_grant_t* grants, uint32_t n, cf_t* iq /* [sf_len] */,
+                        uint8_t* payload, uint32_t* payload_off, uint32_t payload_cap);
+#ifdef __cplusplus
+}
+#endif

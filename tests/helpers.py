@@ -43,6 +43,7 @@ def to_phy_grant(sf, rnti, g):
     pg.tx_scheme = g.tx_scheme
     pg.nof_tb = g.nof_tb
     pg.nof_re = g.nof_re
+    pg.pmi = g.pmi
     for s in range(2):
         for prb in range(110):
             if g.prb_mask[s][prb]:

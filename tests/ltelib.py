@@ -403,3 +403,72 @@ def oracle_pipeline(cell, iq, tti, walk=None, max_iter=8, want_tb=True):
                 tbs.append((gr, pl, ok))
         out.append((dcis, tbs, res.snr_db, cfi.value))
     return out
+
+
+# ------------------------------------------------------------------------------------------------ uplink
+class UlCfg(C.Structure):
+    _fields_ = [("n_dmrs1", C.c_uint32), ("delta_ss", C.c_uint32), ("group_hopping", C.c_uint32), ("seq_hopping", C.c_uint32)]
+
+
+class UlGrant(C.Structure):
+    _fields_ = [("rnti", C.c_uint16), ("L_prb", C.c_uint32), ("n_prb", C.c_uint32), ("mcs", C.c_uint32), ("qm", C.c_uint32), ("rv", C.c_uint32),
+                ("tbs", C.c_int32), ("n_dmrs2", C.c_uint32), ("nof_re", C.c_uint32), ("nof_bits", C.c_uint32)]
+
+
+class UlChest(C.Structure):
+    _fields_ = [("noise", C.c_float), ("rsrp", C.c_float), ("snr_db", C.c_float)]
+
+
+def make_ul_grants(cell, rng, n, table=1, min_prb=3):
+    """n random non-overlapping valid UL grants (DCI format 0 fields -> lte_ul_dci_to_grant)"""
+    S = sim()
+    S.lte_ul_dci_to_grant.argtypes = [C.POINTER(Cell), C.POINTER(Dci), C.c_int, C.POINTER(UlGrant)]
+    S.lte_ul_valid_prb.argtypes = [C.c_uint32]
+    out, start = [], 0
+    N = cell.nof_prb
+    for i in range(n):
+        cand = [L for L in range(min_prb, max(min_prb + 1, (N - start) // max(1, (n - i)) + 1)) if S.lte_ul_valid_prb(L)]
+        if not cand or start + cand[0] > N:
+            break
+        L = int(rng.choice(cand))
+        d = Dci()
+        d.format, d.rnti, d.alloc_type = 0, int(rng.integers(0x100, 0xFFF0)), 2
+        d.riv = N * (L - 1) + start if (L - 1) <= N // 2 else N * (N - L + 1) + (N - 1 - start)
+        d.mcs[0] = int(rng.integers(2, 27))
+        d.n_dmrs = int(rng.integers(0, 8))
+        g = UlGrant()
+        r = S.lte_ul_dci_to_grant(C.byref(cell), C.byref(d), table, C.byref(g))
+        assert r == 0, r
+        out.append(g)
+        start += L
+    return out
+
+
+def sim_ul_subframe(simobj, tti, ucfg, grants):
+    S = sim()
+    S.lte_sim_ul_subframe.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(UlCfg), C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32]
+    iq = np.zeros(simobj.sf_len, np.complex64)
+    pl = np.zeros(1 << 16, np.uint8)
+    off = np.zeros(max(1, len(grants)), np.uint32)
+    arr = (UlGrant * max(1, len(grants)))(*grants)
+    r = S.lte_sim_ul_subframe(simobj.h, tti, C.byref(ucfg), arr, len(grants), ptr(iq), ptr(pl), ptr(off), len(pl))
+    assert r == 0, r
+    return iq, pl, off
+
+
+def oracle_ul(o, ucfg, tti, grants, iq, max_iter=8, want_llr=False):
+    O = oracle()
+    O.lteo_ul_ofdm.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    O.lteo_pusch_decode.argtypes = [C.c_void_p, C.POINTER(UlCfg), C.c_uint32, C.POINTER(UlGrant), C.c_void_p, C.c_uint32, C.c_void_p, C.POINTER(C.c_int),
+                                    C.POINTER(UlChest), C.c_void_p]
+    sym = np.zeros(14 * o.nsc, np.complex64)
+    O.lteo_ul_ofdm(o.h, ptr(np.ascontiguousarray(iq)), ptr(sym))
+    res = []
+    for g in grants:
+        pl = np.zeros(16000, np.uint8)
+        ok = C.c_int(0)
+        ch = UlChest()
+        llr = np.zeros(g.nof_bits + 16, np.int16) if want_llr else None
+        r = O.lteo_pusch_decode(o.h, C.byref(ucfg), tti % 10, C.byref(g), ptr(sym), max_iter, ptr(pl), C.byref(ok), C.byref(ch), ptr(llr) if want_llr else None)
+        res.append((r, pl, ok.value, ch, llr))
+    return sym, res

@@ -70,6 +70,7 @@ CAPS = {
     "cfg1_10sf_1rnti_tm1_qpsk": (Cell(100, 1, 1, 1), 10, dict(seed=1, cfi=2, nof_ues=1, tm=1, mcs_min=5, mcs_max=5, snr_db=30.0, fixed_L=2, si_period=5)),
     "tm3_2x2_64qam": (Cell(100, 2, 7, 2), 2, dict(seed=2, cfi=3, nof_ues=150, dl_min=8, dl_max=12, tm=3, mcs_min=17, mcs_max=24, snr_db=28.0, full_band=1)),
     "mix_50prb_delay": (Cell(50, 2, 301, 2), 3, dict(seed=3, cfi=3, nof_ues=20, dl_min=3, dl_max=5, ul_min=1, ul_max=2, tm=13, mcs_min=0, mcs_max=20, snr_db=22.0, chan_delay=6)),
+    "tm4_2x2_256qam_alt_table": (Cell(50, 2, 11, 2), 3, dict(seed=6, cfi=2, nof_ues=8, dl_min=2, dl_max=4, tm=4, mcs_min=4, mcs_max=22, snr_db=33.0, alt_table=1)),
     "sf0_sf5_sync_re_exclusion_25prb": (Cell(25, 2, 77, 1), 6, dict(seed=4, cfi=2, nof_ues=3, dl_min=1, dl_max=2, tm=1, mcs_min=4, mcs_max=10, snr_db=26.0, full_band=1)),
 }
 
@@ -95,7 +96,7 @@ def test_sim_to_oracle_ground_truth(infra, name):
             ndci += 1
             if d.nof_tb == 0:
                 continue
-            r, dd, g = ltelib.unpack_and_grant(cell, d.format, crc, bits, tti % 10, cfi)
+            r, dd, g = ltelib.unpack_and_grant(cell, d.format, crc, bits, tti % 10, cfi, kw.get("alt_table", 0))
             assert r == 0 and g.nof_re == d.nof_re
             r, pay, ok = o.pdsch_decode(tti % 10, cfi, crc, g, sym, ce, 8)
             assert r == 0

@@ -16,6 +16,7 @@ CASES = {
     "20MHz_1p1a": dict(cell=Cell(100, 1, 1, 1), n=3, kw=dict(seed=11, cfi=2, nof_ues=4, dl_min=1, dl_max=2, tm=1, mcs_min=3, mcs_max=9, snr_db=28.0, si_period=2)),
     "20MHz_2p2a_tm3": dict(cell=Cell(100, 2, 7, 2), n=3, kw=dict(seed=12, cfi=3, nof_ues=30, dl_min=6, dl_max=10, ul_min=1, ul_max=3, tm=3, mcs_min=10, mcs_max=24, snr_db=27.0, full_band=1, chan_delay=4)),
     "10MHz_2p2a_mix": dict(cell=Cell(50, 2, 301, 2), n=4, kw=dict(seed=13, cfi=3, nof_ues=12, dl_min=3, dl_max=5, ul_min=1, ul_max=2, tm=13, mcs_min=0, mcs_max=22, snr_db=24.0, chan_delay=6, tti0=4)),
+    "10MHz_tm4_256qam": dict(cell=Cell(50, 2, 11, 2), n=3, kw=dict(seed=15, cfi=2, nof_ues=8, dl_min=2, dl_max=4, tm=4, mcs_min=4, mcs_max=22, snr_db=33.0, alt_table=1)),
     "5MHz_2p1a": dict(cell=Cell(25, 2, 150, 1), n=3, kw=dict(seed=14, cfi=2, nof_ues=5, dl_min=1, dl_max=3, tm=1, mcs_min=2, mcs_max=12, snr_db=25.0, tti0=9)),
 }
 
@@ -30,7 +31,7 @@ def case(request, infra, phylib):
     phy = capi.LtePhy(cell.nof_prb, cell.nof_ports, cell.cell_id, cell.nof_rx, max_subframes=c["n"], turbo_max_iter=8)
     phy.submit_iq(iq, tti)
     info, cands = phy.get_phase_a()
-    yield dict(name=request.param, cell=cell, iq=iq, tti=tti, truths=truths, payloads=payloads, o=o, ref=ref, phy=phy, info=info, cands=cands, n=c["n"])
+    yield dict(name=request.param, alt=c["kw"].get("alt_table", 0), cell=cell, iq=iq, tti=tti, truths=truths, payloads=payloads, o=o, ref=ref, phy=phy, info=info, cands=cands, n=c["n"])
     phy.close()
 
 
@@ -107,7 +108,7 @@ def test_dci_table_bit_exact(case):
 
 def test_pdsch_llr_and_tb_bit_exact(case):
     cell, phy, o = case["cell"], case["phy"], case["o"]
-    tg = truth_grants(cell, case["truths"], case["tti"])
+    tg = truth_grants(cell, case["truths"], case["tti"], case["alt"])
     if not tg:
         pytest.skip("no DL grants in this capture")
     grants = [to_phy_grant(sf, d.rnti, g) for sf, d, g in tg]
