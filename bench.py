@@ -268,6 +268,8 @@ def main():
     # re-interleaved into global order; the walk is replayed over ALL subframes on every rank (its RNTI history is
     # sequential by nature); phase B for the owned subframes; one gather of the decoded TBs to rank 0.
     # Software pipeline over 3 handles in ONE thread (one communicator): A(k+1) and B(k-1) run while the host walks k.
+    TB_DTYPE = np.dtype({"names": ["crc", "avg_iters", "nof_cb", "payload_off", "payload_len"], "formats": ["u1", "u1", "<u2", "<u4", "<u4"],
+                         "offsets": [0, 1, 2, 4, 8], "itemsize": C.sizeof(capi.TbResult)})
     if world > 1:
         from ltesniffer_b200 import shard
         gather_sz = B * 20000
@@ -285,7 +287,7 @@ def main():
 
     def sh_finish_b(t):
         phys[t]._chk(L.ltephy_get_phase_b(phys[t].h, res[t], p(scr[t].payload), scr[t].payload.numel()), "get_phase_b")
-        nby = sum(res[t][i].payload_len for i in range(2 * ngr[t]))
+        nby = int(np.frombuffer(res[t], dtype=TB_DTYPE, count=2 * ngr[t])["payload_len"].sum()) if ngr[t] else 0
         n = min(nby, gather_sz)
         out_local[:n].copy_(scr[t].payload[:n], non_blocking=True)
         dist.gather(out_local, out_all, dst=0)   # the single gather of decoded transport blocks
@@ -358,8 +360,9 @@ def main():
     if world > 1:
         dist.all_reduce(t_val, op=dist.ReduceOp.MAX)
     dev_ms = float(t_val.item())
-    tb_ok = sum(tbs[i].crc for i in range(2 * nd.value)) if world == 1 else None
-    ntb = sum(1 for i in range(2 * nd.value) if tbs[i].payload_len) if world == 1 else None
+    tbv = np.frombuffer(tbs, dtype=TB_DTYPE, count=2 * nd.value) if world == 1 else None
+    tb_ok = int(tbv["crc"].sum()) if world == 1 else None
+    ntb = int((tbv["payload_len"] > 0).sum()) if world == 1 else None
     tbytes, ncb, info_bits = phy.turbo_work()
     # ---------------- e2e: host IQ through the C-ABI ----------------
     if world > 1:

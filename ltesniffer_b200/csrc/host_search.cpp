@@ -29,41 +29,44 @@ enum { ACT_UNSET = 0, ACT_EVERGREEN, ACT_RAR, ACT_SHORTCUT, ACT_HISTOGRAM, ACT_O
 // RNTI history: same observable behaviour as RNTIManager (per-format 200 ms sliding histogram padded to
 // 60 entries per subframe, active set with 10 s expiry, evergreen / forbidden intervals).
 struct RntiManager {
+  // Sliding histogram over the last HIST_DEPTH added entries (Histogram.cc).  Only non-zero RNTIs are stored,
+  // with the add-position they were written at, so the zero padding of stepTime costs O(1) plus the entries it
+  // expires; observable behaviour (getFrequency of any value, including 0) is unchanged.
   struct Hist {
-    std::vector<uint16_t> ring  = std::vector<uint16_t>(HIST_DEPTH, 0);
+    struct Ent {
+      uint64_t pos;
+      uint16_t rnti;
+    };
+    std::vector<Ent>      q     = std::vector<Ent>(HIST_DEPTH); // circular FIFO of the non-zero entries in the window
     std::vector<uint16_t> count = std::vector<uint16_t>(65536, 0);
-    uint32_t              cur   = 0;
-    bool                  ready = false;
-    inline void           add(uint16_t v)
+    uint32_t              head = 0, size = 0;
+    uint64_t              pos  = 0; // number of adds so far
+    inline void           expire()
     {
-      if (ready) count[ring[cur]]--;
-      ring[cur] = v;
-      count[v]++;
-      if (++cur == HIST_DEPTH) ready = true, cur = 0;
-    }
-    // n consecutive add(0): the padding RNTIManager::stepTime appends every subframe (RNTIManager.cc:425-432)
-    inline void add_zeros(uint32_t n)
-    {
-      while (n) {
-        const uint32_t chunk = std::min(n, HIST_DEPTH - cur);
-        if (ready) {
-          uint32_t nz = 0;
-          for (uint32_t i = 0; i < chunk; i++) {
-            const uint16_t old = ring[cur + i];
-            if (old)
-              count[old]--;
-            else
-              nz++;
-          }
-          count[0] = (uint16_t)(count[0] + chunk - nz);
-        } else
-          count[0] = (uint16_t)(count[0] + chunk);
-        memset(&ring[cur], 0, chunk * sizeof(uint16_t));
-        cur += chunk;
-        n -= chunk;
-        if (cur == HIST_DEPTH) ready = true, cur = 0;
+      while (size && q[head].pos + HIST_DEPTH <= pos - 1) {
+        count[q[head].rnti]--;
+        head = head + 1 == HIST_DEPTH ? 0 : head + 1;
+        size--;
       }
     }
+    inline void add(uint16_t v)
+    {
+      pos++;
+      expire();
+      if (v) {
+        uint32_t tail = head + size;
+        if (tail >= HIST_DEPTH) tail -= HIST_DEPTH;
+        q[tail] = {pos - 1, v};
+        size++;
+        count[v]++;
+      }
+    }
+    inline void add_zeros(uint32_t n)
+    {
+      pos += n;
+      expire();
+    }
+    inline uint32_t freq(uint16_t v) const { return v ? count[v] : (uint32_t)(std::min<uint64_t>(pos, HIST_DEPTH) - size); }
   };
   struct Interval {
     uint16_t a, b;
@@ -90,7 +93,7 @@ struct RntiManager {
       if (r >= i.a && r <= i.b) return true;
     return false;
   }
-  uint32_t freq(uint16_t r, uint32_t f) const { return hist[f].count[r]; }
+  uint32_t freq(uint16_t r, uint32_t f) const { return hist[f].freq(r); }
   void     add_candidate(uint16_t r, uint32_t f)
   {
     hist[f].add(r);
@@ -116,9 +119,9 @@ struct RntiManager {
     // validateByHistogram
     uint32_t likely = 0, maxf = 0;
     for (uint32_t i = 1; i < NF; i++)
-      if (hist[i].count[r] > maxf) maxf = hist[i].count[r], likely = i;
+      if (hist[i].freq(r) > maxf) maxf = hist[i].freq(r), likely = i;
     if (f != 0 && f != likely) return false;
-    const uint32_t ul = hist[0].count[r], dl = likely ? hist[likely].count[r] : 0;
+    const uint32_t ul = hist[0].freq(r), dl = likely ? hist[likely].freq(r) : 0;
     if (ul + dl > threshold) {
       activate(r, ACT_HISTOGRAM);
       assoc[r] = dl > threshold ? likely : 0;
@@ -229,6 +232,11 @@ struct ltephy_search {
   uint32_t             sf_idx = 0, ncce_sf = 0, sf_batch = 0;
   Loc                  loc[LTEPHY_MAX_LOC];
   int16_t              loc_of[4][LTEPHY_MAX_CCE]; // [L][ncce] -> location index or -1
+  struct LocTemplate {
+    uint32_t n = 0;
+    Loc      loc[LTEPHY_MAX_LOC];
+    int16_t  loc_of[4][LTEPHY_MAX_CCE];
+  } tmpl[3];
   std::vector<TempDci0> temp_dci0;
   ltephy_dci_t*        out = nullptr;
   uint32_t             out_cap = 0, out_n = 0;
@@ -395,17 +403,11 @@ struct ltephy_search {
       sf_idx  = info.tti % 10;
       ncce_sf = nof_cce[info.cfi - 1];
       stats.nof_cce += ncce_sf;
-      memset(loc_of, 0xFF, sizeof(loc_of));
-      const uint32_t lim = std::min<uint32_t>(ncce_sf, LTEPHY_SEARCH_MAX_CCE);
-      uint32_t       k   = 0;
-      for (int l = 3; l >= 0; l--) {
-        const uint32_t Lc = 1u << l;
-        for (uint32_t i = 0; i < lim / Lc && k < LTEPHY_MAX_LOC; i++) {
-          loc[k]                 = {(uint8_t)l, (uint8_t)(Lc * i), false, false, false, true};
-          loc_of[l][Lc * i]      = (int16_t)k;
-          k++;
-        }
-      }
+      const uint32_t     lim = std::min<uint32_t>(ncce_sf, LTEPHY_SEARCH_MAX_CCE);
+      const LocTemplate& tp  = tmpl[info.cfi - 1];
+      const uint32_t     k   = tp.n;
+      memcpy(loc, tp.loc, k * sizeof(Loc));
+      memcpy(loc_of, tp.loc_of, sizeof(loc_of));
       stats.nof_locations += k;
       for (uint32_t c = 0; c < lim; c++)
         if (info.cce_power[c] < 0.7f)
@@ -719,6 +721,21 @@ ltephy_search_t* ltephy_search_create_cell(uint32_t nof_prb, uint32_t nof_ports,
   s->cell          = cell;
   s->st = ltehost::dci_size_table(s->cell);
   for (uint32_t cfi = 1; cfi <= 3; cfi++) s->nof_cce[cfi - 1] = cm.nof_cce[cfi - 1];
+  for (uint32_t cfi = 0; cfi < 3; cfi++) { // srsran_pdcch_ue_locations_all_map, falcon_pdcch.c:321-356
+    auto& tp = s->tmpl[cfi];
+    memset(tp.loc_of, 0xFF, sizeof(tp.loc_of));
+    const uint32_t lim = std::min<uint32_t>(s->nof_cce[cfi], LTEPHY_SEARCH_MAX_CCE);
+    uint32_t       k   = 0;
+    for (int l = 3; l >= 0; l--) {
+      const uint32_t Lc = 1u << l;
+      for (uint32_t i = 0; i < lim / Lc && k < LTEPHY_MAX_LOC; i++) {
+        tp.loc[k]            = {(uint8_t)l, (uint8_t)(Lc * i), false, false, false, true};
+        tp.loc_of[l][Lc * i] = (int16_t)k;
+        k++;
+      }
+    }
+    tp.n = k;
+  }
   {
     const uint32_t cls_sf[3] = {0, 5, 1};
     uint16_t       kk[12];

@@ -10,22 +10,41 @@ import torch.distributed as dist
 from . import capi
 
 
+_stage = {}
+
+
+def _buffers(B, world, device):
+    key = (B, world, str(device))
+    if key not in _stage:
+        isz = C.sizeof(capi.SfInfo)
+        csz = capi.MAX_LOC * capi.MAX_SIZES * 16
+        pin = torch.device(device).type == "cuda"
+        _stage[key] = dict(
+            gi=torch.empty((world, B, isz), dtype=torch.uint8, device=device), gc=torch.empty((world, B, csz), dtype=torch.uint8, device=device),
+            oi=torch.empty((B, world, isz), dtype=torch.uint8, device=device), oc=torch.empty((B, world, csz), dtype=torch.uint8, device=device),
+            hi=torch.empty((B * world, isz), dtype=torch.uint8, pin_memory=pin), hc=torch.empty((B * world, capi.MAX_LOC, capi.MAX_SIZES, 16), dtype=torch.uint8, pin_memory=pin),
+            info_all=(capi.SfInfo * (B * world))())
+    return _stage[key]
+
+
 def gather_tables(info_local, cands_local, world, device):
-    """info_local: ctypes (SfInfo * B); cands_local: uint8 tensor [B, MAX_LOC, MAX_SIZES, 16] (host).
-    Returns (info_all ctypes array [B*world] in global order, cands_all uint8 host tensor [B*world, ...])."""
+    """info_local: ctypes (SfInfo * B); cands_local: uint8 tensor [B, MAX_LOC, MAX_SIZES, 16] (host, pinned if possible).
+    Returns (info_all ctypes array [B*world] in global order g = i*world + r, cands_all uint8 host tensor [B*world, ...]).
+    The returned buffers are reused by the next call with the same shape."""
     B = len(info_local)
-    isz = C.sizeof(capi.SfInfo)
-    li = torch.frombuffer(info_local, dtype=torch.uint8).clone().to(device)
-    lc = cands_local.reshape(-1).to(device)
-    gi = [torch.empty_like(li) for _ in range(world)]
-    gc = [torch.empty_like(lc) for _ in range(world)]
-    dist.all_gather(gi, li)
-    dist.all_gather(gc, lc)
-    ia = torch.stack(gi).view(world, B, isz).transpose(0, 1).contiguous().cpu().numpy()   # [B][world] -> g = i*world + r
-    info_all = (capi.SfInfo * (B * world))()
-    C.memmove(info_all, ia.ctypes.data, ia.nbytes)
-    ca = torch.stack(gc).view(world, B, capi.MAX_LOC, capi.MAX_SIZES, 16).transpose(0, 1).reshape(B * world, capi.MAX_LOC, capi.MAX_SIZES, 16).contiguous().cpu()
-    return info_all, ca
+    st = _buffers(B, world, device)
+    li = torch.frombuffer(info_local, dtype=torch.uint8).to(device, non_blocking=True)
+    lc = cands_local.reshape(-1).to(device, non_blocking=True)
+    dist.all_gather_into_tensor(st["gi"].view(-1), li)
+    dist.all_gather_into_tensor(st["gc"].view(-1), lc)
+    st["oi"].copy_(st["gi"].transpose(0, 1))          # [world][B] -> [B][world]
+    st["oc"].copy_(st["gc"].transpose(0, 1))
+    st["hi"].copy_(st["oi"].view(B * world, -1), non_blocking=True)
+    st["hc"].view(B * world, -1).copy_(st["oc"].view(B * world, -1), non_blocking=True)
+    if torch.device(device).type == "cuda":
+        torch.cuda.current_stream().synchronize()
+    C.memmove(st["info_all"], st["hi"].data_ptr(), st["hi"].numel())
+    return st["info_all"], st["hc"]
 
 
 def search_and_select(L, srch, info_all, cands_all, world, rank, max_dcis, max_grants):
