@@ -38,6 +38,26 @@ def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
 
+_JSON_OUT = None
+
+
+def claim_stdout():
+    """The contract is ONE JSON line on stdout: keep the real stdout for it and point fd 1 at stderr, so that library
+    chatter (NCCL prints its version on stdout under NCCL_DEBUG=VERSION/WARN) cannot land in front of the line."""
+    global _JSON_OUT
+    if _JSON_OUT is None:
+        sys.stdout.flush()
+        _JSON_OUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+    return _JSON_OUT
+
+
+def emit_json(obj):
+    out = claim_stdout()
+    out.write(json.dumps(obj) + "\n")
+    out.flush()
+
+
 # ------------------------------------------------------------------------------------------------------
 def generate_capture(n_unique, threads):
     """synthetic eNB capture (sim/, input generator -- not measured): n_unique distinct subframes"""
@@ -149,7 +169,7 @@ def run_reference(args):
            "cpu_baseline": {"value": v, "unit": "subframes/s", "cores": cores, "kind": "port",
                             "sample": "%d subframes per step (CPU oracle port of the srsRAN chain + the reference's own RNTIManager; srsRAN itself is not buildable here)" % per_step},
            "e2e": {"value": v, "unit": "subframes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(out), flush=True)
+    emit_json(out)
 
 
 # ------------------------------------------------------------------------------------------------------
@@ -164,8 +184,9 @@ def main():
     ap.add_argument("--ref-subframes", type=int, default=96, help="subframes per step for --impl reference")
     ap.add_argument("--cpu-sample", type=int, default=0, help="subframes for the cpu_baseline leg (0 = 40 per core)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--pipelines", type=int, default=2, help="PHY handles driven concurrently (host search of batch k overlaps GPU work of batch k+1)")
+    ap.add_argument("--pipelines", type=int, default=3, help="PHY handles driven concurrently (host search of batch k overlaps GPU work of batch k+1)")
     args = ap.parse_args()
+    claim_stdout()
     if args.impl == "reference":
         return run_reference(args)
 
@@ -229,6 +250,7 @@ def main():
         def __init__(self):
             self.info = (capi.SfInfo * B)()
             self.cands = torch.empty((B, capi.MAX_LOC, capi.MAX_SIZES, 16), dtype=torch.uint8, pin_memory=True)
+            self.comp = torch.empty((B, capi.COMPACT_DTYPE.itemsize), dtype=torch.uint8, pin_memory=True)
             self.dcis = np.zeros(max_dcis, capi.DCI_DTYPE)
             self.tbs = (capi.TbResult * (2 * max_dcis))()
             self.payload = torch.empty(B * 48000, dtype=torch.uint8, pin_memory=True)
@@ -300,9 +322,13 @@ def main():
             if k + 1 < nsteps:
                 sh_submit_a((k + 1) % T, device_resident)
             S = scr[t]
-            phys[t]._chk(L.ltephy_get_phase_a(phys[t].h, S.info, p(S.cands)), "get_phase_a")
-            info_all, cands_all = shard.gather_tables(S.info, S.cands, world, "cuda")
-            d, grants, gidx, ng = shard.search_and_select(L, srch, info_all, cands_all, world, rank, max_dcis, 24 * B)
+            phys[t]._chk(L.ltephy_get_phase_a_compact(phys[t].h, S.info, p(S.comp)), "get_phase_a_compact")
+            info_all, comp_all = shard.gather_tables(S.info, S.comp, world, "cuda")
+
+            def full_fetch():   # survivor form refused (never on this workload): all-gather the full tables instead
+                phys[t]._chk(L.ltephy_get_phase_a(phys[t].h, None, p(S.cands)), "get_phase_a")
+                return shard.gather_full_tables(S.cands, world, "cuda")
+            d, grants, gidx, ng = shard.search_and_select(L, srch, info_all, comp_all, world, rank, max_dcis, 24 * B, full_fetch)
             nd.value = len(d)
             if pending is not None:
                 sh_finish_b(pending)
@@ -381,7 +407,7 @@ def main():
     if world > 1:
         dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
     e2e_ms = float(t_e2e.item())
-    d2h = B * (C.sizeof(capi.SfInfo) + capi.MAX_LOC * capi.MAX_SIZES * 16) + int(info_bits // 8) + 12 * 2 * 24 * B // 8
+    d2h = B * (C.sizeof(capi.SfInfo) + capi.COMPACT_DTYPE.itemsize) + int(info_bits // 8) + 12 * 2 * 24 * B // 8
 
     # ---------------- roofline of the dominant kernel (turbo decoder) ----------------
     peaks = {}
@@ -405,7 +431,7 @@ def main():
                "data": "synthetic",
                "config": {"workload": WORKLOAD, "subframes_per_step_per_gpu": B, "pipelines": T, "unique_subframes": len(iq_u), "turbo_max_iter": 8,
                           "cache_note": "inputs larger than L2: %.0f MB of IQ per step per GPU" % (iq_pin.numel() * 4 / 1e6),
-                          "sharding": "subframe g -> GPU g mod N; all-gather of candidate tables; walk replayed on every rank; one gather of TBs" if world > 1 else "single GPU",
+                          "sharding": "subframe g -> GPU g mod N; all-gather of the survivor forms of the candidate tables; walk replayed on every rank; one gather of TBs" if world > 1 else "single GPU",
                           "tb_crc_ok": tb_ok, "tb_total": ntb, "dcis_per_step": int(nd.value)},
                "wall_ms_per_step": wall_ms / args.steps, "phase_a_ms": float(np.mean(phase_a_ms)), "phase_b_ms": float(np.mean(phase_b_ms)),
                "host_ms": dict(zip(["submit_a", "wait_a", "search", "grants", "submit_b", "wait_b"], [round(float(x), 3) for x in host_ms[:6]])),
@@ -416,7 +442,7 @@ def main():
     if rank == 0 and cpu_base is not None:
         out["cpu_baseline"] = cpu_base
     if rank == 0:
-        print(json.dumps(out), flush=True)
+        emit_json(out)
     for ph in phys:
         ph.close()
     if world > 1:

@@ -28,6 +28,7 @@ extern "C" {
 #define LTEPHY_SUCCESS 0
 #define LTEPHY_ERROR -1
 #define LTEPHY_ERROR_INVALID_INPUTS -2
+#define LTEPHY_NEED_FULL_TABLE -3 /* survivor form insufficient for this walk (see ltephy_compact_t); nothing was consumed */
 
 #define LTEPHY_MAX_PRB 110
 #define LTEPHY_MAX_CCE 88
@@ -75,6 +76,33 @@ typedef struct {
   uint8_t  valid; /* 1 decoded; 0 skipped (no such location / all-zero LLRs / low power with the flag set) */
   uint8_t  pad[5];
 } ltephy_cand_t;
+
+/* Survivor form of one subframe's candidate table: the entries the FALCON walk can possibly act on.
+ * An entry (location li, size column si) is listed iff the location has sufficient power (no CCE below 0.7,
+ * src/src/DCISearch.cc:473-489) and at least one of
+ *   - its RNTI lies in a search space that contains the location (srsran_pdcch_validate_location, falcon_pdcch.c:223-250),
+ *   - its RNTI is 0 (includes undecoded all-zero entries),
+ *   - it is the first child of a location whose entry in the same column decoded the same RNTI (shortcut test,
+ *     DCISearch.cc:163-178).
+ * Every other entry makes inspect_dci_location_recursively take the "rnti = 0; continue" branch whatever the RNTI
+ * history holds, so the walk over the survivor form equals the walk over the full table (as long as no RNTI is
+ * active with reason RAR: that path looks at every format-0 candidate and needs the full table).
+ * list[loc[li].off + popcount(loc[li].mask & ((1 << si) - 1))] is the entry of (li, si) when bit si of mask is set.
+ * In a listed entry pad[0] = search-space match (0 none, 1 ambiguous, 2 unique) | zero-RNTI << 2 | parent-match << 3,
+ * pad[1] = li, pad[2] = si. */
+#define LTEPHY_COMPACT_CAP 248
+typedef struct {
+  uint16_t off;
+  uint8_t  mask;
+  uint8_t  pad;
+} ltephy_cloc_t;
+typedef struct {
+  uint32_t      count;    /* survivors of this subframe; > LTEPHY_COMPACT_CAP: list is truncated, use the full table */
+  uint32_t      reserved;
+  ltephy_cloc_t loc[LTEPHY_MAX_LOC];
+  uint8_t       pad[8];
+  ltephy_cand_t list[LTEPHY_COMPACT_CAP];
+} ltephy_compact_t;       /* 4624 bytes instead of 20480 */
 
 /* ---- phase B ------------------------------------------------------------------------------ */
 enum { LTEPHY_TX_PORT0 = 0, LTEPHY_TX_DIVERSITY = 1, LTEPHY_TX_CDD = 2, LTEPHY_TX_SPATIALMUX = 3 };
@@ -138,6 +166,11 @@ int ltephy_submit_iq_device(ltephy_t* h, const void* iq_dev, const uint32_t* tti
 /* blocks until phase A of the current batch is done and copies its results to the host:
  * info[n], cands[n][LTEPHY_MAX_LOC][LTEPHY_MAX_SIZES] */
 int ltephy_get_phase_a(ltephy_t* h, ltephy_sf_info_t* info, ltephy_cand_t* cands);
+/* same, fetching the survivor form (4.5 KB instead of 20 KB per subframe); comp[n].  ltephy_get_phase_a may still be
+ * called afterwards for the full table (needed only for subframes whose count exceeds LTEPHY_COMPACT_CAP). */
+int ltephy_get_phase_a_compact(ltephy_t* h, ltephy_sf_info_t* info, ltephy_compact_t* comp);
+/* comp may be NULL above: the survivor forms then stay in the handle's pinned buffer, valid until the next submit_iq */
+const ltephy_compact_t* ltephy_phase_a_compact_buffer(const ltephy_t* h);
 
 /* ---- phase B ------------------------------------------------------------------------------ */
 int ltephy_submit_grants(ltephy_t* h, const ltephy_grant_t* grants, uint32_t n);

@@ -67,6 +67,12 @@ void ltephy_search_activate(ltephy_search_t* s, uint16_t rnti, uint32_t format_i
  * subframe.  Writes the accepted DCIs in the order DCICollection::addCandidate would receive them. */
 int ltephy_search_subframe(ltephy_search_t* s, const ltephy_sf_info_t* info, const ltephy_cand_t* cands, uint32_t sf_in_batch, ltephy_dci_t* out,
                            uint32_t max_out, uint32_t* n_out);
+/* same walk over the survivor form of the table (ltephy_compact_t); LTEPHY_NEED_FULL_TABLE if it cannot serve */
+int ltephy_search_subframe_compact(ltephy_search_t* s, const ltephy_sf_info_t* info, const ltephy_compact_t* comp, uint32_t sf_in_batch, ltephy_dci_t* out,
+                                   uint32_t max_out, uint32_t* n_out);
+/* host restatement of the GPU's survivor selection: full table of one subframe -> survivor form (tests, and callers
+ * that obtained the table elsewhere) */
+int ltephy_compact_from_table(const ltephy_search_t* s, const ltephy_sf_info_t* info, const ltephy_cand_t* cands, ltephy_compact_t* out);
 void ltephy_search_get_stats(const ltephy_search_t* s, ltephy_search_stats_t* st);
 uint32_t ltephy_search_validate_location(uint32_t nof_cce, uint32_t ncce, uint32_t L, uint32_t sf_idx, uint16_t rnti);
 
@@ -113,6 +119,8 @@ void ltephy_last_host_timing(double* ms8);
  * and keeps the grants of the subframes it owns (sf % mod == rem; grant.sf becomes sf / mod). */
 int ltephy_search_batch(ltephy_search_t* s, const ltephy_sf_info_t* info, const ltephy_cand_t* cands, uint32_t n, ltephy_dci_t* dcis, uint32_t max_dcis,
                         uint32_t* n_dcis);
+int ltephy_search_batch_compact(ltephy_search_t* s, const ltephy_sf_info_t* info, const ltephy_compact_t* comp, const ltephy_cand_t* full_or_null,
+                                uint32_t n, ltephy_dci_t* dcis, uint32_t max_dcis, uint32_t* n_dcis);
 int ltephy_grants_from_dcis(const ltephy_search_t* s, const ltephy_sf_info_t* info, const ltephy_dci_t* dcis, uint32_t nd, uint32_t mod, uint32_t rem,
                             ltephy_grant_t* grants, uint32_t* grant_dci, uint32_t max_grants, uint32_t* n_grants);
 

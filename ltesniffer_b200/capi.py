@@ -60,6 +60,11 @@ class UlChest(C.Structure):
 TAP_UL_SYM = 5
 CAND_DTYPE = np.dtype([("bits", "<u8"), ("rnti", "<u2"), ("valid", "u1"), ("pad", "u1", 5)])
 assert CAND_DTYPE.itemsize == C.sizeof(Cand) == 16
+COMPACT_CAP = 248
+NEED_FULL_TABLE = -3
+COMPACT_DTYPE = np.dtype([("count", "<u4"), ("reserved", "<u4"), ("loc", [("off", "<u2"), ("mask", "u1"), ("pad", "u1")], MAX_LOC), ("pad", "u1", 8),
+                          ("list", CAND_DTYPE, COMPACT_CAP)])   # ltephy_compact_t
+assert COMPACT_DTYPE.itemsize == 4624
 
 _lib = None
 
@@ -90,6 +95,9 @@ def load_library(build_if_missing=True):
     L.ltephy_submit_iq.argtypes = [P, P, P, C.c_uint32]
     L.ltephy_submit_iq_device.argtypes = [P, P, P, C.c_uint32]
     L.ltephy_get_phase_a.argtypes = [P, P, P]
+    L.ltephy_get_phase_a_compact.argtypes = [P, P, P]
+    L.ltephy_phase_a_compact_buffer.argtypes = [P]
+    L.ltephy_phase_a_compact_buffer.restype = P
     L.ltephy_submit_grants.argtypes = [P, P, C.c_uint32]
     L.ltephy_get_phase_b.argtypes = [P, P, P, C.c_size_t]
     L.ltephy_dci_sweep.argtypes = [P, P, P, C.c_uint32, P]
@@ -173,6 +181,13 @@ class LtePhy:
         cands = np.zeros((self.n, MAX_LOC, MAX_SIZES), CAND_DTYPE) if want_cands else None
         self._chk(self.L.ltephy_get_phase_a(self.h, info, _p(cands) if want_cands else None), "get_phase_a")
         return info, cands
+
+    def get_phase_a_compact(self):
+        """-> (info, survivor forms as a COMPACT_DTYPE array [n])"""
+        info = (SfInfo * self.n)()
+        comp = np.zeros(self.n, COMPACT_DTYPE)
+        self._chk(self.L.ltephy_get_phase_a_compact(self.h, info, _p(comp)), "get_phase_a_compact")
+        return info, comp
 
     def tap(self, what, shape, dtype):
         out = np.zeros(shape, dtype)
@@ -298,6 +313,9 @@ def _bind_search(L):
     L.ltephy_search_add_forbidden.argtypes = [P, C.c_uint16, C.c_uint16, C.c_uint32]
     L.ltephy_search_activate.argtypes = [P, C.c_uint16, C.c_uint32, C.c_int]
     L.ltephy_search_subframe.argtypes = [P, P, P, C.c_uint32, P, C.c_uint32, P]
+    L.ltephy_search_subframe_compact.argtypes = [P, P, P, C.c_uint32, P, C.c_uint32, P]
+    L.ltephy_compact_from_table.argtypes = [P, P, P, P]
+    L.ltephy_search_batch_compact.argtypes = [P, P, P, P, C.c_uint32, P, C.c_uint32, P]
     L.ltephy_search_get_stats.argtypes = [P, P]
     L.ltephy_search_validate_location.argtypes = [C.c_uint32] * 4 + [C.c_uint16]
     L.ltephy_search_validate_location.restype = C.c_uint32
@@ -351,6 +369,27 @@ class Search:
         r = self.L.ltephy_search_subframe(self.h, C.byref(info), _p(cands), sf_in_batch, _p(out), max_out, C.byref(n))
         if r < 0:
             raise RuntimeError("ltephy_search_subframe failed (%d)" % r)
+        return out[:n.value].copy()
+
+    def compact_from_table(self, info, cands):
+        """host restatement of the GPU's survivor selection for one subframe -> COMPACT_DTYPE scalar array [1]"""
+        out = np.zeros(1, COMPACT_DTYPE)
+        cands = np.ascontiguousarray(cands)
+        r = self.L.ltephy_compact_from_table(self.h, C.byref(info), _p(cands), _p(out))
+        if r < 0:
+            raise RuntimeError("ltephy_compact_from_table failed (%d)" % r)
+        return out
+
+    def subframe_compact(self, info, comp, sf_in_batch=0, max_out=64):
+        """walk over the survivor form; returns None when the full table is needed (nothing consumed)"""
+        out = np.zeros(max_out, DCI_DTYPE)
+        n = C.c_uint32(0)
+        comp = np.ascontiguousarray(comp)
+        r = self.L.ltephy_search_subframe_compact(self.h, C.byref(info), _p(comp), sf_in_batch, _p(out), max_out, C.byref(n))
+        if r == NEED_FULL_TABLE:
+            return None
+        if r < 0:
+            raise RuntimeError("ltephy_search_subframe_compact failed (%d)" % r)
         return out[:n.value].copy()
 
     def stats(self):

@@ -99,13 +99,14 @@ struct RntiManager {
     hist[f].add(r);
     remaining[f]--;
   }
-  void activate(uint16_t r, uint8_t why)
+  uint32_t n_rar = 0; // RNTIs currently active with reason RAR (they make the walk look at every format-0 candidate)
+  void     activate(uint16_t r, uint8_t why)
   {
-    if (!active[r]) active[r] = 1, reason[r] = why;
+    if (!active[r]) active[r] = 1, reason[r] = why, n_rar += why == ACT_RAR;
   }
   void deactivate(uint16_t r)
   {
-    if (active[r]) active[r] = 0, assoc[r] = 0, reason[r] = ACT_UNSET;
+    if (active[r]) n_rar -= reason[r] == ACT_RAR, active[r] = 0, assoc[r] = 0, reason[r] = ACT_UNSET;
   }
   bool expired(uint16_t r) const { return !(active[r] && timestamp - last_seen[r] < LIFETIME); }
   bool validate(uint16_t r, uint32_t f)
@@ -228,8 +229,9 @@ struct ltephy_search {
   uint32_t           update_interval = 500, sf_cnt = 0;
   ltephy_search_stats_t stats{};
   // per-subframe scratch
-  const ltephy_cand_t* T = nullptr;
-  uint32_t             sf_idx = 0, ncce_sf = 0, sf_batch = 0;
+  const ltephy_cand_t*    T  = nullptr;
+  const ltephy_compact_t* CT = nullptr; // survivor form (then T is null)
+  uint32_t                sf_idx = 0, ncce_sf = 0, sf_batch = 0;
   Loc                  loc[LTEPHY_MAX_LOC];
   int16_t              loc_of[4][LTEPHY_MAX_CCE]; // [L][ncce] -> location index or -1
   struct LocTemplate {
@@ -270,11 +272,14 @@ struct ltephy_search {
   }
   inline void fetch(uint32_t li, uint32_t format, Cand& c) const
   {
-    const ltephy_cand_t& t = T[(size_t)li * LTEPHY_MAX_SIZES + st.index_of[format]];
-    c                      = Cand{};
+    const uint32_t       si = st.index_of[format];
+    const ltephy_cand_t& t  = CT ? CT->list[CT->loc[li].off + (uint32_t)__builtin_popcount(CT->loc[li].mask & ((1u << si) - 1u))]
+                                 : T[(size_t)li * LTEPHY_MAX_SIZES + si];
+    c                       = Cand{};
     c.nof_bits             = (uint16_t)st.sizes[st.index_of[format]];
     if (!t.valid) return; // all-zero LLRs: the reference leaves the calloc'ed candidate untouched
     c.bits = t.bits, c.rnti = t.rnti;
+    if (CT) c.ssm = t.pad[0] & 3u;
     if (format == ltehost::F0 || format == ltehost::F1A)
       c.format = (t.bits >> 63) ? ltehost::F1A : ltehost::F0;
     else
@@ -300,8 +305,9 @@ struct ltephy_search {
     uint32_t best_val = 0, n_above = 0;
     for (uint32_t f = 0; f < nf; f++) {
       const uint32_t fmt = mf[f];
-      fetch((uint32_t)li, fmt, cand[f]);
       stats.nof_decoded_locations++;
+      if (CT && !((CT->loc[li].mask >> st.index_of[fmt]) & 1u)) continue; // not a survivor: every path below ends in rnti = 0
+      fetch((uint32_t)li, fmt, cand[f]);
       if (rm.reason[cand[f].rnti] == ACT_RAR && cand[f].format == 0) {
         bool add = true;
         for (auto& m : temp_dci0)
@@ -322,7 +328,7 @@ struct ltephy_search {
         continue;
       }
       if (shortcut && discovery && parent && parent[f].rnti == r && !rm.is_forbidden(r, fmt)) return -((int)f + 1);
-      cand[f].ssm = (uint8_t)validate_location(ncce_sf, ncce, L, sf_idx, r);
+      cand[f].ssm = CT ? cand[f].ssm : (uint8_t)validate_location(ncce_sf, ncce, L, sf_idx, r); // the survivor form carries it
       if (cand[f].ssm == 0) {
         cand[f].rnti = 0;
         continue;
@@ -392,11 +398,15 @@ struct ltephy_search {
     }
     return 0;
   }
-  int search_subframe(const ltephy_sf_info_t& info, const ltephy_cand_t* table, uint32_t sf_in_batch, ltephy_dci_t* o, uint32_t cap, uint32_t* n)
+  // exactly one of table / comp is given.  The survivor form cannot serve a walk that has RAR-activated RNTIs (the
+  // temp_dci0 rule looks at every format-0 candidate) nor a truncated list: LTEPHY_NEED_FULL_TABLE, nothing consumed.
+  int search_subframe(const ltephy_sf_info_t& info, const ltephy_cand_t* table, const ltephy_compact_t* comp, uint32_t sf_in_batch, ltephy_dci_t* o,
+                      uint32_t cap, uint32_t* n)
   {
+    if (comp && (rm.n_rar || comp->count > LTEPHY_COMPACT_CAP)) return LTEPHY_NEED_FULL_TABLE;
     if (update_interval && (sf_cnt % update_interval) == 0) update_formats();
     sf_cnt++;
-    out = o, out_cap = cap, out_n = 0, sf_batch = sf_in_batch, T = table;
+    out = o, out_cap = cap, out_n = 0, sf_batch = sf_in_batch, T = table, CT = comp;
     int ret = LTEPHY_ERROR;
     if (info.snr_db > 6.0f && info.cfi >= 1 && info.cfi <= 3) {
       temp_dci0.clear();
@@ -782,7 +792,55 @@ int  ltephy_search_subframe(ltephy_search_t* s, const ltephy_sf_info_t* info, co
                             uint32_t max_out, uint32_t* n_out)
 {
   if (!s || !info || !cands) return LTEPHY_ERROR_INVALID_INPUTS;
-  return s->search_subframe(*info, cands, sf_in_batch, out, max_out, n_out);
+  return s->search_subframe(*info, cands, nullptr, sf_in_batch, out, max_out, n_out);
+}
+int ltephy_search_subframe_compact(ltephy_search_t* s, const ltephy_sf_info_t* info, const ltephy_compact_t* comp, uint32_t sf_in_batch, ltephy_dci_t* out,
+                                   uint32_t max_out, uint32_t* n_out)
+{
+  if (!s || !info || !comp) return LTEPHY_ERROR_INVALID_INPUTS;
+  return s->search_subframe(*info, nullptr, comp, sf_in_batch, out, max_out, n_out);
+}
+// Host restatement of the survivor selection the GPU does in cand_compact_kernel (k_viterbi.cu); same bytes out.
+int ltephy_compact_from_table(const ltephy_search_t* s, const ltephy_sf_info_t* info, const ltephy_cand_t* cands, ltephy_compact_t* out)
+{
+  if (!s || !info || !cands || !out) return LTEPHY_ERROR_INVALID_INPUTS;
+  memset(out, 0, sizeof(*out));
+  if (info->cfi < 1 || info->cfi > 3) return LTEPHY_SUCCESS;
+  const auto&    tp      = s->tmpl[info->cfi - 1];
+  const uint32_t ncce_sf = s->nof_cce[info->cfi - 1], lim = std::min<uint32_t>(ncce_sf, LTEPHY_SEARCH_MAX_CCE), sf_idx = info->tti % 10;
+  uint32_t       cnt     = 0;
+  for (uint32_t li = 0; li < tp.n; li++) {
+    const uint32_t L = tp.loc[li].L, ncce = tp.loc[li].ncce;
+    bool           suff = true;
+    for (uint32_t c = ncce; c < ncce + (1u << L); c++)
+      if (c < lim && info->cce_power[c] < 0.7f) suff = false;
+    const int par = (L < 3 && (ncce & ((2u << L) - 1u)) == 0) ? tp.loc_of[L + 1][ncce] : -1;
+    out->loc[li].off = (uint16_t)std::min<uint32_t>(cnt, 0xFFFF);
+    uint32_t mask    = 0;
+    for (uint32_t si = 0; suff && si < s->st.sizes.size(); si++) {
+      const ltephy_cand_t& e  = cands[(size_t)li * LTEPHY_MAX_SIZES + si];
+      const uint16_t       r  = e.valid ? e.rnti : 0;
+      const uint32_t       sm = validate_location(ncce_sf, ncce, L, sf_idx, r);
+      bool                 eq = false;
+      if (par >= 0) {
+        const ltephy_cand_t& pe = cands[(size_t)par * LTEPHY_MAX_SIZES + si];
+        eq                      = (pe.valid ? pe.rnti : 0) == r;
+      }
+      if (sm == 0 && r != 0 && !eq) continue;
+      mask |= 1u << si;
+      if (cnt < LTEPHY_COMPACT_CAP) {
+        ltephy_cand_t& o = out->list[cnt];
+        o                = e;
+        if (!e.valid) o.bits = 0, o.rnti = 0;
+        memset(o.pad, 0, sizeof(o.pad));
+        o.pad[0] = (uint8_t)(sm | ((r == 0) << 2) | (eq << 3)), o.pad[1] = (uint8_t)li, o.pad[2] = (uint8_t)si;
+      }
+      cnt++;
+    }
+    out->loc[li].mask = (uint8_t)mask;
+  }
+  out->count = cnt;
+  return LTEPHY_SUCCESS;
 }
 void ltephy_search_get_stats(const ltephy_search_t* s, ltephy_search_stats_t* st) { *st = s->stats; }
 uint32_t ltephy_search_validate_location(uint32_t nof_cce, uint32_t ncce, uint32_t L, uint32_t sf_idx, uint16_t rnti)
@@ -808,7 +866,30 @@ int ltephy_search_batch(ltephy_search_t* s, const ltephy_sf_info_t* info, const 
   uint32_t nd = 0;
   for (uint32_t i = 0; i < n; i++) {
     uint32_t k = 0;
-    int      r = s->search_subframe(info[i], cands + (size_t)i * LTEPHY_MAX_LOC * LTEPHY_MAX_SIZES, i, dcis + nd, max_dcis - nd, &k);
+    int      r = s->search_subframe(info[i], cands + (size_t)i * LTEPHY_MAX_LOC * LTEPHY_MAX_SIZES, nullptr, i, dcis + nd, max_dcis - nd, &k);
+    if (r < 0) return r;
+    nd += std::min(k, max_dcis - nd);
+  }
+  *n_dcis = nd;
+  return LTEPHY_SUCCESS;
+}
+// Same walk over the survivor form.  full (optional) is the full table of the same batch; it is consulted for the
+// subframes the survivor form cannot serve.  Without it such a batch is refused up front, before anything is consumed
+// (RAR activations only arrive between batches, so the check is exact).
+int ltephy_search_batch_compact(ltephy_search_t* s, const ltephy_sf_info_t* info, const ltephy_compact_t* comp, const ltephy_cand_t* full, uint32_t n,
+                                ltephy_dci_t* dcis, uint32_t max_dcis, uint32_t* n_dcis)
+{
+  if (!s || !info || !comp || !dcis || !n_dcis) return LTEPHY_ERROR_INVALID_INPUTS;
+  if (!full) {
+    if (s->rm.n_rar) return LTEPHY_NEED_FULL_TABLE;
+    for (uint32_t i = 0; i < n; i++)
+      if (comp[i].count > LTEPHY_COMPACT_CAP) return LTEPHY_NEED_FULL_TABLE;
+  }
+  uint32_t nd = 0;
+  for (uint32_t i = 0; i < n; i++) {
+    uint32_t k = 0;
+    int      r = s->search_subframe(info[i], nullptr, &comp[i], i, dcis + nd, max_dcis - nd, &k);
+    if (r == LTEPHY_NEED_FULL_TABLE) r = s->search_subframe(info[i], full + (size_t)i * LTEPHY_MAX_LOC * LTEPHY_MAX_SIZES, nullptr, i, dcis + nd, max_dcis - nd, &k);
     if (r < 0) return r;
     nd += std::min(k, max_dcis - nd);
   }
@@ -854,14 +935,19 @@ static int decode_common(ltephy_t* h, ltephy_search_t* s, const void* iq, bool i
   int r = iq_on_device ? ltephy_submit_iq_device(h, iq, tti, n) : ltephy_submit_iq(h, (const float*)iq, tti, n);
   if (r) return r;
   double t1 = now_ms();
-  r = ltephy_get_phase_a(h, info, cand_scratch);
+  r = ltephy_get_phase_a_compact(h, info, nullptr); // survivor form (4.5 KB / subframe) stays in the handle's pinned buffer
   if (r) return r;
+  const ltephy_compact_t* comp = ltephy_phase_a_compact_buffer(h);
   double t2 = now_ms();
   uint32_t nd = 0;
   {
     std::unique_lock<std::mutex> lk(s->mtx);
     s->cv.wait(lk, [&] { return s->next_seq == seq || seq == LTEPHY_SEQ_NONE; });
-    r = ltephy_search_batch(s, info, cand_scratch, n, dcis, max_dcis, &nd);
+    r = ltephy_search_batch_compact(s, info, comp, nullptr, n, dcis, max_dcis, &nd);
+    if (r == LTEPHY_NEED_FULL_TABLE) { // RAR-activated RNTIs or an overfull subframe: fetch the 20 KB / subframe table after all
+      r = ltephy_get_phase_a(h, nullptr, cand_scratch);
+      if (r == LTEPHY_SUCCESS) r = ltephy_search_batch_compact(s, info, comp, cand_scratch, n, dcis, max_dcis, &nd);
+    }
     if (seq != LTEPHY_SEQ_NONE) s->next_seq = seq + 1;
     lk.unlock();
     s->cv.notify_all();

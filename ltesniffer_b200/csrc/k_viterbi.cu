@@ -219,3 +219,129 @@ extern "C" void launch_viterbi(const DevCell& c, const float* llr, const DevSfIn
   dci_viterbi_kernel<<<dim3(max_pairs, c.nsizes, n), VIT_WARPS * 32, 0, st>>>(c, llr, info, cands);
   *launches += 1;
 }
+
+// ---------------------------------------------------------------------------------------------------
+// Survivor selection (ltephy_compact_t, include/ltephy_b200.h): the RNTI-history-independent part of
+// DCISearch::inspect_dci_location_recursively (src/src/DCISearch.cc:133-190) done for every entry of the table at once:
+// sufficient-power rule (:473-489), srsran_pdcch_validate_location (falcon_pdcch.c:223-250), zero-RNTI and
+// first-child-equals-parent (shortcut, :163-178) tests.  One CTA per subframe, one thread per location; the block-wide
+// exclusive scan makes the list order (location, then size column) deterministic.
+__device__ __forceinline__ bool dev_in_ue_space(uint32_t nof_cce, uint32_t ncce, uint32_t l, uint32_t Yk)
+{
+  const uint32_t L = 1u << l, M = l < 2 ? 6u : 2u;
+  if (nof_cce < L || (ncce & (L - 1))) return false;
+  const uint32_t n = nof_cce >> l, q = ncce >> l;
+  if (q >= n) return false;
+  return (q + n - Yk % n) % n < M;
+}
+__device__ __forceinline__ bool dev_in_common_space(uint32_t nof_cce, uint32_t ncce, uint32_t l)
+{
+  if (l < 2) return false;
+  const uint32_t L = 1u << l;
+  if (nof_cce < L || (ncce & (L - 1))) return false;
+  const uint32_t lim = min(nof_cce, 16u) >> l, q = ncce >> l;
+  return q < lim && q < (nof_cce >> l);
+}
+__device__ __forceinline__ uint32_t dev_validate_location(uint32_t nof_cce, uint32_t ncce, uint32_t l, uint32_t sf_idx, uint32_t rnti)
+{
+  bool ue = false, common = false;
+  if (rnti >= 0x0001u && rnti <= 0x000Au)
+    common = true;
+  else if (rnti >= 0x000Bu && rnti <= 0xFFF3u)
+    ue = common = true;
+  else if (rnti >= 0xFFFDu)
+    common = true;
+  else
+    return 0;
+  uint32_t Yk = rnti;
+  if (ue)
+    for (uint32_t m = 0; m < sf_idx + 1; m++) Yk = (39827u * Yk) % 65537u;
+  const bool valid = (ue && dev_in_ue_space(nof_cce, ncce, l, Yk)) || (common && dev_in_common_space(nof_cce, ncce, l));
+  if (!valid) return 0;
+  const bool amb = l > 0 && ((ue && dev_in_ue_space(nof_cce, ncce, l - 1, Yk)) || (common && dev_in_common_space(nof_cce, ncce, l - 1)));
+  return amb ? 1u : 2u;
+}
+
+__global__ void __launch_bounds__(LTEPHY_MAX_LOC) cand_compact_kernel(const __grid_constant__ DevCell c, const DevSfInfo* __restrict__ info,
+                                                                       const ltephy_cand_t* __restrict__ cands, ltephy_compact_t* __restrict__ out)
+{
+  static_assert(LTEPHY_MAX_LOC % 32 == 0 && LTEPHY_MAX_SIZES == 8, "layout");
+  __shared__ uint32_t wtot[LTEPHY_MAX_LOC / 32];
+  const uint32_t sf = blockIdx.x, li = threadIdx.x, lane = li & 31u, warp = li >> 5;
+  const uint32_t cfi = info[sf].cfi;
+  const bool     ok  = cfi >= 1 && cfi <= 3;
+  const uint32_t nloc = ok ? c.nloc[cfi - 1] : 0;
+  uint4          e[LTEPHY_MAX_SIZES];
+  uint32_t       mask = 0;
+  if (li < nloc) {
+    const uint32_t ent = c.loc_tab[cfi - 1][li], ncce = ent & 0xFFu, L = ent >> 8;
+    const uint32_t ncce_sf = c.nof_cce[cfi - 1], lim = min(ncce_sf, (uint32_t)LTEPHY_SEARCH_MAX_CCE), sf_idx = info[sf].tti % 10;
+    bool           suff = true;
+    for (uint32_t i = ncce; i < ncce + (1u << L); i++)
+      if (i < lim && info[sf].cce_power[i] < 0.7f) suff = false;
+    if (suff) {
+      int par = -1; // location index of (L + 1, ncce): levels are laid out 3,2,1,0 with lim >> l entries each
+      if (L < 3 && (ncce & ((2u << L) - 1u)) == 0) {
+        const uint32_t lp = L + 1, q = ncce >> lp;
+        uint32_t       base = 0;
+        for (uint32_t l2 = 3; l2 > lp; l2--) base += lim >> l2;
+        if (q < (lim >> lp) && base + q < nloc) par = (int)(base + q);
+      }
+      const uint4* row  = reinterpret_cast<const uint4*>(cands + ((size_t)sf * LTEPHY_MAX_LOC + li) * LTEPHY_MAX_SIZES);
+      const uint4* prow = reinterpret_cast<const uint4*>(cands + ((size_t)sf * LTEPHY_MAX_LOC + (par >= 0 ? par : 0)) * LTEPHY_MAX_SIZES);
+#pragma unroll
+      for (uint32_t si = 0; si < LTEPHY_MAX_SIZES; si++) {
+        if (si >= c.nsizes) continue;
+        uint4          v  = row[si];
+        const uint32_t vl = (v.z >> 16) & 0xFFu, r = vl ? (v.z & 0xFFFFu) : 0u;
+        const uint32_t sm = dev_validate_location(ncce_sf, ncce, L, sf_idx, r);
+        bool           eq = false;
+        if (par >= 0) {
+          const uint4 pv = prow[si];
+          eq             = (((pv.z >> 16) & 0xFFu) ? (pv.z & 0xFFFFu) : 0u) == r;
+        }
+        if (sm == 0 && r != 0 && !eq) continue;
+        mask |= 1u << si;
+        if (!vl) v.x = 0, v.y = 0;
+        v.z   = r | (vl << 16) | ((sm | ((r == 0) << 2) | ((uint32_t)eq << 3)) << 24);
+        v.w   = li | (si << 8);
+        e[si] = v;
+      }
+    }
+  }
+  const uint32_t cnt = __popc(mask);
+  uint32_t       inc = cnt;
+#pragma unroll
+  for (int off = 1; off < 32; off <<= 1) {
+    const uint32_t t = __shfl_up_sync(0xffffffffu, inc, off);
+    if ((int)lane >= off) inc += t;
+  }
+  if (lane == 31) wtot[warp] = inc;
+  __syncthreads();
+  uint32_t base = 0, total = 0;
+#pragma unroll
+  for (uint32_t w = 0; w < LTEPHY_MAX_LOC / 32; w++) {
+    if (w < warp) base += wtot[w];
+    total += wtot[w];
+  }
+  ltephy_compact_t& o   = out[sf];
+  uint32_t          pos = base + inc - cnt;
+  ltephy_cloc_t     cl;
+  cl.off = li < nloc ? (uint16_t)min(pos, 0xFFFFu) : (uint16_t)0, cl.mask = (uint8_t)mask, cl.pad = 0;
+  o.loc[li] = cl;
+  if (li == 0) o.count = total, o.reserved = 0;
+  uint4* lst = reinterpret_cast<uint4*>(o.list);
+#pragma unroll
+  for (uint32_t si = 0; si < LTEPHY_MAX_SIZES; si++)
+    if ((mask >> si) & 1u) {
+      if (pos < LTEPHY_COMPACT_CAP) lst[pos] = e[si];
+      pos++;
+    }
+}
+
+extern "C" void launch_compact(const DevCell& c, const DevSfInfo* info, const ltephy_cand_t* cands, ltephy_compact_t* out, uint32_t n, cudaStream_t st,
+                               uint64_t* launches)
+{
+  cand_compact_kernel<<<n, LTEPHY_MAX_LOC, 0, st>>>(c, info, cands, out);
+  *launches += 1;
+}

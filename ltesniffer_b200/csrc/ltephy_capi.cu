@@ -19,6 +19,7 @@
 extern "C" {
 void launch_frontend(const DevCell&, const float2*, float2*, float2*, float*, DevSfInfo*, uint32_t, cudaStream_t, uint64_t*);
 void launch_viterbi(const DevCell&, const float*, const DevSfInfo*, ltephy_cand_t*, uint32_t, cudaStream_t, uint64_t*);
+void launch_compact(const DevCell&, const DevSfInfo*, const ltephy_cand_t*, ltephy_compact_t*, uint32_t, cudaStream_t, uint64_t*);
 void launch_pdsch_front(const DevCell&, const DevGrant*, uint32_t, uint32_t, const float2*, const float2*, const uint32_t*, const uint32_t*, uint32_t,
                         uint32_t*, short*, cudaStream_t, uint64_t*);
 void launch_rm_turbo_rx(const DevCb*, uint32_t, const DevPair*, const short*, const uint32_t*, uint32_t*, cudaStream_t, uint64_t*);
@@ -115,6 +116,8 @@ struct ltephy {
   DevBuf<DevSfInfo>     d_info;
   DevBuf<ltephy_cand_t> d_cands;
   PinBuf<DevSfInfo>     h_info;
+  DevBuf<ltephy_compact_t> d_compact;
+  PinBuf<ltephy_compact_t> h_compact;
   uint32_t              n_cur = 0;
   std::vector<uint8_t>  re_cnt; // [3 sf class][3 cfi][14][nof_prb]
 
@@ -316,7 +319,7 @@ extern "C" int ltephy_create(const ltephy_cfg_t* cfg, ltephy_t** out)
   const size_t S = cfg->max_subframes, g = (size_t)14 * c.nsc;
   if (h->d_iq.reserve(S * c.nof_rx * c.sf_len) || h->d_sym.reserve(S * c.nof_rx * g) || h->d_ce.reserve(S * c.nof_ports * c.nof_rx * g) ||
       h->d_llr.reserve(S * LLR_STRIDE) || h->d_info.reserve(S) || h->d_cands.reserve(S * LTEPHY_MAX_LOC * LTEPHY_MAX_SIZES) ||
-      h->h_info.reserve(S) || h->d_rm.reserve((size_t)16 << 20) || h->d_pi.reserve((size_t)188 * 6144)) {
+      h->h_info.reserve(S) || h->d_compact.reserve(S) || h->h_compact.reserve(S) || h->d_rm.reserve((size_t)16 << 20) || h->d_pi.reserve((size_t)188 * 6144)) {
     ltephy_destroy(h);
     return fail(LTEPHY_ERROR, "device allocation failed");
   }
@@ -331,7 +334,7 @@ extern "C" void ltephy_destroy(ltephy_t* h)
   cudaDeviceSynchronize();
   for (void* p : h->tables) cudaFree(p);
   h->d_iq.release(), h->d_sym.release(), h->d_ce.release(), h->d_llr.release(), h->d_info.release(), h->d_cands.release();
-  h->h_info.release(), h->d_grants.release(), h->d_cbs.release(), h->d_pairs.release(), h->d_tbs.release(), h->d_pair_pi_off.release();
+  h->h_info.release(), h->d_compact.release(), h->h_compact.release(), h->d_grants.release(), h->d_cbs.release(), h->d_pairs.release(), h->d_tbs.release(), h->d_pair_pi_off.release();
   h->d_seq.release(), h->d_rm.release(), h->d_turbo.release(), h->d_pllr.release(), h->d_pi.release(), h->d_payload.release();
   h->d_cb_iters.release(), h->d_cb_crc.release(), h->d_res.release(), h->h_res.release(), h->h_payload.release();
   h->d_uliq.release(), h->d_ulsym.release(), h->d_ulpool.release(), h->d_ulgrants.release(), h->d_ulchest.release(), h->h_ulchest.release();
@@ -398,6 +401,7 @@ static int phase_a_common(ltephy* h, const float2* iq_dev, const uint32_t* tti, 
   CU(cudaMemcpyAsync(h->d_info.p, h->h_info.p, n * sizeof(DevSfInfo), cudaMemcpyHostToDevice, h->stream));
   launch_frontend(h->dc, iq_dev, h->d_sym.p, h->d_ce.p, h->d_llr.p, h->d_info.p, n, h->stream, &h->launches);
   launch_viterbi(h->dc, h->d_llr.p, h->d_info.p, h->d_cands.p, n, h->stream, &h->launches);
+  launch_compact(h->dc, h->d_info.p, h->d_cands.p, h->d_compact.p, n, h->stream, &h->launches);
   CU(cudaEventRecord(h->ev[1], h->stream));
   CU(cudaGetLastError());
   h->n_cur = n;
@@ -418,7 +422,7 @@ extern "C" int ltephy_submit_iq_device(ltephy_t* h, const void* iq_dev, const ui
   CU(cudaEventRecord(h->ev[0], h->stream));
   return phase_a_common(h, reinterpret_cast<const float2*>(iq_dev), tti, n); // read in place: the caller keeps the buffer alive until phase A is fetched
 }
-extern "C" int ltephy_get_phase_a(ltephy_t* h, ltephy_sf_info_t* info, ltephy_cand_t* cands)
+static int fetch_phase_a(ltephy_t* h, ltephy_sf_info_t* info, ltephy_cand_t* cands, bool compact, ltephy_compact_t* comp)
 {
   if (!h || !h->n_cur) return fail(LTEPHY_ERROR_INVALID_INPUTS, "get_phase_a: nothing submitted");
   const uint32_t n = h->n_cur;
@@ -426,6 +430,7 @@ extern "C" int ltephy_get_phase_a(ltephy_t* h, ltephy_sf_info_t* info, ltephy_ca
   if (cands)
     CU(cudaMemcpyAsync(cands, h->d_cands.p, (size_t)n * LTEPHY_MAX_LOC * LTEPHY_MAX_SIZES * sizeof(ltephy_cand_t), cudaMemcpyDeviceToHost,
                        h->stream));
+  if (compact) CU(cudaMemcpyAsync(comp ? comp : h->h_compact.p, h->d_compact.p, (size_t)n * sizeof(ltephy_compact_t), cudaMemcpyDeviceToHost, h->stream));
   CU(cudaStreamSynchronize(h->stream));
   cudaEventElapsedTime(&h->t_ms[0], h->ev[0], h->ev[1]);
   const float npa = (float)(h->dc.nof_ports * h->dc.nof_rx);
@@ -445,6 +450,9 @@ extern "C" int ltephy_get_phase_a(ltephy_t* h, ltephy_sf_info_t* info, ltephy_ca
   }
   return LTEPHY_SUCCESS;
 }
+extern "C" int ltephy_get_phase_a(ltephy_t* h, ltephy_sf_info_t* info, ltephy_cand_t* cands) { return fetch_phase_a(h, info, cands, false, nullptr); }
+extern "C" int ltephy_get_phase_a_compact(ltephy_t* h, ltephy_sf_info_t* info, ltephy_compact_t* comp) { return fetch_phase_a(h, info, nullptr, true, comp); }
+extern "C" const ltephy_compact_t* ltephy_phase_a_compact_buffer(const ltephy_t* h) { return h ? h->h_compact.p : nullptr; }
 
 // ---------------------------------------------------------------------------------------- phase B
 static int rm_table_for(ltephy* h, uint32_t K, uint32_t F, uint32_t rv, uint32_t& off, uint32_t& nn)
@@ -932,6 +940,7 @@ extern "C" int ltephy_dci_sweep(ltephy_t* h, const float* llr, const uint32_t* c
   CU(cudaMemcpyAsync(h->d_llr.p, llr, (size_t)n * LLR_STRIDE * sizeof(float), cudaMemcpyHostToDevice, h->stream));
   CU(cudaEventRecord(h->ev[0], h->stream));
   launch_viterbi(h->dc, h->d_llr.p, h->d_info.p, h->d_cands.p, n, h->stream, &h->launches);
+  launch_compact(h->dc, h->d_info.p, h->d_cands.p, h->d_compact.p, n, h->stream, &h->launches);
   CU(cudaEventRecord(h->ev[1], h->stream));
   CU(cudaMemcpyAsync(cands, h->d_cands.p, (size_t)n * LTEPHY_MAX_LOC * LTEPHY_MAX_SIZES * sizeof(ltephy_cand_t), cudaMemcpyDeviceToHost, h->stream));
   CU(cudaStreamSynchronize(h->stream));

@@ -1,7 +1,9 @@
 """Round-robin subframe sharding across ranks: global subframe g is owned by rank g % world.
-Every rank runs phase A on its own subframes; the per-subframe records (ltephy_sf_info_t) and candidate tables
-are all-gathered, re-interleaved into global order, and the FALCON walk is replayed over ALL subframes on every
-rank (its RNTI history is inherently sequential); each rank then keeps the grants of the subframes it owns.
+Every rank runs phase A on its own subframes; the per-subframe records (ltephy_sf_info_t) and the survivor forms of the
+candidate tables (ltephy_compact_t, 4.5 KB per subframe) are all-gathered, re-interleaved into global order, and the
+FALCON walk is replayed over ALL subframes on every rank (its RNTI history is inherently sequential); each rank then
+keeps the grants of the subframes it owns.  When the survivor form cannot serve the walk (RAR-activated RNTIs, an
+overfull subframe) every rank sees that on the same data and the full tables are all-gathered instead.
 Host logic only: works with NCCL (CUDA tensors) and gloo (CPU tensors)."""
 import ctypes as C
 import numpy as np
@@ -11,51 +13,70 @@ from . import capi
 
 
 _stage = {}
+ISZ = C.sizeof(capi.SfInfo)
+CSZ = capi.COMPACT_DTYPE.itemsize
+FSZ = capi.MAX_LOC * capi.MAX_SIZES * 16
 
 
-def _buffers(B, world, device):
-    key = (B, world, str(device))
+def _buffers(B, world, device, esz):
+    key = (B, world, str(device), esz)
     if key not in _stage:
-        isz = C.sizeof(capi.SfInfo)
-        csz = capi.MAX_LOC * capi.MAX_SIZES * 16
         pin = torch.device(device).type == "cuda"
-        _stage[key] = dict(
-            gi=torch.empty((world, B, isz), dtype=torch.uint8, device=device), gc=torch.empty((world, B, csz), dtype=torch.uint8, device=device),
-            oi=torch.empty((B, world, isz), dtype=torch.uint8, device=device), oc=torch.empty((B, world, csz), dtype=torch.uint8, device=device),
-            hi=torch.empty((B * world, isz), dtype=torch.uint8, pin_memory=pin), hc=torch.empty((B * world, capi.MAX_LOC, capi.MAX_SIZES, 16), dtype=torch.uint8, pin_memory=pin),
-            info_all=(capi.SfInfo * (B * world))())
+        _stage[key] = dict(g=torch.empty((world, B, esz), dtype=torch.uint8, device=device), o=torch.empty((B, world, esz), dtype=torch.uint8, device=device),
+                           h=torch.empty((B * world, esz), dtype=torch.uint8, pin_memory=pin))
     return _stage[key]
 
 
-def gather_tables(info_local, cands_local, world, device):
-    """info_local: ctypes (SfInfo * B); cands_local: uint8 tensor [B, MAX_LOC, MAX_SIZES, 16] (host, pinned if possible).
-    Returns (info_all ctypes array [B*world] in global order g = i*world + r, cands_all uint8 host tensor [B*world, ...]).
-    The returned buffers are reused by the next call with the same shape."""
-    B = len(info_local)
-    st = _buffers(B, world, device)
-    li = torch.frombuffer(info_local, dtype=torch.uint8).to(device, non_blocking=True)
-    lc = cands_local.reshape(-1).to(device, non_blocking=True)
-    dist.all_gather_into_tensor(st["gi"].view(-1), li)
-    dist.all_gather_into_tensor(st["gc"].view(-1), lc)
-    st["oi"].copy_(st["gi"].transpose(0, 1))          # [world][B] -> [B][world]
-    st["oc"].copy_(st["gc"].transpose(0, 1))
-    st["hi"].copy_(st["oi"].view(B * world, -1), non_blocking=True)
-    st["hc"].view(B * world, -1).copy_(st["oc"].view(B * world, -1), non_blocking=True)
+def _gather_interleaved(local_u8, B, world, device, esz):
+    """local_u8: uint8 host tensor [B*esz] -> host tensor [B*world, esz] in global order g = i*world + r (buffer reused)"""
+    st = _buffers(B, world, device, esz)
+    loc = local_u8.reshape(-1).to(device, non_blocking=True)
+    dist.all_gather_into_tensor(st["g"].view(-1), loc)
+    st["o"].copy_(st["g"].transpose(0, 1))            # [world][B] -> [B][world]
+    st["h"].copy_(st["o"].view(B * world, esz), non_blocking=True)
     if torch.device(device).type == "cuda":
         torch.cuda.current_stream().synchronize()
-    C.memmove(st["info_all"], st["hi"].data_ptr(), st["hi"].numel())
-    return st["info_all"], st["hc"]
+    return st["h"]
 
 
-def search_and_select(L, srch, info_all, cands_all, world, rank, max_dcis, max_grants):
-    """walk over all subframes in global order; -> (dcis structured array, grants ctypes array, grant->dci index, n_grants)"""
+_info_all = {}
+
+
+def gather_tables(info_local, comp_local, world, device):
+    """info_local: ctypes (SfInfo * B); comp_local: uint8 tensor [B, sizeof(ltephy_compact_t)] (host, pinned if possible).
+    -> (info_all ctypes array [B*world] in global order, comp_all uint8 host tensor [B*world, sizeof(ltephy_compact_t)]).
+    The returned buffers are reused by the next call with the same shape."""
+    B = len(info_local)
+    hi = _gather_interleaved(torch.frombuffer(info_local, dtype=torch.uint8), B, world, device, ISZ)
+    hc = _gather_interleaved(comp_local, B, world, device, CSZ)
+    if (B, world) not in _info_all:
+        _info_all[(B, world)] = (capi.SfInfo * (B * world))()
+    info_all = _info_all[(B, world)]
+    C.memmove(info_all, hi.data_ptr(), hi.numel())
+    return info_all, hc
+
+
+def gather_full_tables(cands_local, world, device):
+    """cands_local: uint8 tensor [B, MAX_LOC, MAX_SIZES, 16] -> host tensor [B*world, MAX_LOC*MAX_SIZES*16] in global order"""
+    return _gather_interleaved(cands_local, cands_local.shape[0], world, device, FSZ)
+
+
+def search_and_select(L, srch, info_all, comp_all, world, rank, max_dcis, max_grants, full_fetch=None):
+    """walk over all subframes in global order; -> (dcis structured array, grants ctypes array, grant->dci index, n_grants).
+    full_fetch: callable returning the all-gathered FULL tables (collective: every rank calls it on the same condition)."""
     capi._bind_search(L)
     n = len(info_all)
     dcis = np.zeros(max_dcis, capi.DCI_DTYPE)
     nd = C.c_uint32(0)
-    r = L.ltephy_search_batch(srch.h, info_all, C.c_void_p(cands_all.data_ptr()), n, dcis.ctypes.data_as(C.c_void_p), max_dcis, C.byref(nd))
+    r = L.ltephy_search_batch_compact(srch.h, info_all, C.c_void_p(comp_all.data_ptr()), None, n, dcis.ctypes.data_as(C.c_void_p), max_dcis, C.byref(nd))
+    if r == capi.NEED_FULL_TABLE:
+        if full_fetch is None:
+            raise RuntimeError("the survivor form cannot serve this batch and no full-table fetch was given")
+        full = full_fetch()
+        r = L.ltephy_search_batch_compact(srch.h, info_all, C.c_void_p(comp_all.data_ptr()), C.c_void_p(full.data_ptr()), n,
+                                          dcis.ctypes.data_as(C.c_void_p), max_dcis, C.byref(nd))
     if r != 0:
-        raise RuntimeError("ltephy_search_batch failed (%d)" % r)
+        raise RuntimeError("ltephy_search_batch_compact failed (%d)" % r)
     grants = (capi.Grant * max_grants)()
     gidx = np.zeros(max_grants, np.uint32)
     ng = C.c_uint32(0)

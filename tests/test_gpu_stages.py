@@ -106,6 +106,36 @@ def test_dci_table_bit_exact(case):
     assert nchecked > 100
 
 
+@pytest.mark.parametrize("flags", [0, capi.FLAG_SKIP_LOW_POWER])
+def test_survivor_form_matches_host_restatement(case, flags):
+    """cand_compact_kernel (search-space validation, zero-RNTI and parent-match tests on the GPU) against
+    ltephy_compact_from_table applied to the GPU's own full table: same counts, location records and listed entries;
+    and the walk over the survivor form accepts what the walk over the full table accepts."""
+    cell, n = case["cell"], case["n"]
+    phy = capi.LtePhy(cell.nof_prb, cell.nof_ports, cell.cell_id, cell.nof_rx, max_subframes=n, turbo_max_iter=8, flags=flags)
+    phy.submit_iq(case["iq"], case["tti"])
+    info, cands = phy.get_phase_a()
+    info_c, comp = phy.get_phase_a_compact()
+    assert bytes(info) == bytes(info_c)
+    sa = capi.Search(cell.nof_prb, cell.nof_ports, cell.cell_id, cell.nof_rx)
+    sb = capi.Search(cell.nof_prb, cell.nof_ports, cell.cell_id, cell.nof_rx)
+    total = 0
+    for i in range(n):
+        ref = sa.compact_from_table(info[i], cands[i])[0]
+        got = comp[i]
+        assert int(got["count"]) == int(ref["count"]) and int(got["count"]) <= capi.COMPACT_CAP, (i, int(got["count"]), int(ref["count"]))
+        assert got["loc"].tobytes() == ref["loc"].tobytes(), (i, "location records differ")
+        k = int(ref["count"])
+        assert got["list"][:k].tobytes() == ref["list"][:k].tobytes(), (i, "listed entries differ")
+        total += k
+        for _ in range(3):     # a few repetitions so that the RNTI histogram crosses its threshold and DCIs are accepted
+            a = sa.subframe(info[i], cands[i])
+            b = sb.subframe_compact(info[i], comp[i:i + 1])
+            assert b is not None and len(a) == len(b) and all(np.array_equal(a[f], b[f]) for f in a.dtype.names)
+    assert total > 0
+    phy.close()
+
+
 def test_pdsch_llr_and_tb_bit_exact(case):
     cell, phy, o = case["cell"], case["phy"], case["o"]
     tg = truth_grants(cell, case["truths"], case["tti"], case["alt"])

@@ -71,8 +71,11 @@ def test_search_matches_oracle_walk(infra, name, cell, n, kw):
     s, o = Sim(cell=cell, **kw), Oracle(cell)
     walk = OracleWalk(cell)
     srch = capi.Search(cell.nof_prb, cell.nof_ports, cell.cell_id, cell.nof_rx)
+    srch_c = capi.Search(cell.nof_prb, cell.nof_ports, cell.cell_id, cell.nof_rx)   # same walk over the survivor form of the table
     walk.config(1, 0, 10)
     srch.config(1, 0, 10)
+    srch_c.config(1, 0, 10)
+    counts = []
     geo = host_geometry(cell)
     found = set()
     sent = set()
@@ -94,6 +97,11 @@ def test_search_matches_oracle_walk(infra, name, cell, n, kw):
         nc, Ls = locations(ncce)
         T = oracle_table(o, geo, nc, Ls, llr) if res.snr_db > 6.0 else np.zeros((capi.MAX_LOC, capi.MAX_SIZES), capi.CAND_DTYPE)
         got = srch.subframe(info, T)
+        comp = srch_c.compact_from_table(info, T)
+        counts.append(int(comp["count"][0]))
+        got_c = srch_c.subframe_compact(info, comp)
+        assert got_c is not None and len(got_c) == len(got) and all(np.array_equal(got_c[k], got[k]) for k in got.dtype.names), \
+            (name, tti, "survivor-form walk differs")
         assert len(got) == len(ref), (name, tti, len(got), len(ref))
         for a, b in zip(got, ref):
             assert (int(a["rnti"]), int(a["format"]), int(a["L"]), int(a["ncce"]), int(a["nof_bits"]), int(a["histogram_value"])) == \
@@ -103,9 +111,13 @@ def test_search_matches_oracle_walk(infra, name, cell, n, kw):
         total += len(got)
         for i in range(tr.nof_dci):
             sent.add((tti, tr.dci[i].rnti, tr.dci[i].ncce))
-    ws, ps = walk.stats(), srch.stats()
+    ws, ps, cs = walk.stats(), srch.stats(), srch_c.stats()
     assert (ws.nof_decoded_locations, ws.nof_cce, ws.nof_missed_cce, ws.nof_subframes, ws.nof_locations) == \
            (ps.nof_decoded_locations, ps.nof_cce, ps.nof_missed_cce, ps.nof_subframes, ps.nof_locations)
+    assert (cs.nof_decoded_locations, cs.nof_cce, cs.nof_missed_cce, cs.nof_subframes, cs.nof_locations) == \
+           (ps.nof_decoded_locations, ps.nof_cce, ps.nof_missed_cce, ps.nof_subframes, ps.nof_locations)
+    print(name, "survivors per subframe: max", max(counts), "mean", sum(counts) / len(counts))
+    assert max(counts) <= capi.COMPACT_CAP
     if name == "low_snr_gate":
         assert total == 0
     else:

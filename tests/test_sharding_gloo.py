@@ -1,6 +1,8 @@
 """Multi-rank sharding logic on CPU (gloo, world_size 2): candidate tables built per rank for the subframes it
-owns (with the CPU oracle standing in for the GPU phase A), all-gathered and re-interleaved; the walk replayed
-on every rank must accept exactly what a single process accepts, and the grants must partition by owner."""
+owns (with the CPU oracle standing in for the GPU phase A, and the host restatement of the survivor selection
+standing in for cand_compact_kernel), all-gathered and re-interleaved; the walk replayed on every rank must accept
+exactly what a single process walking the FULL tables accepts, and the grants must partition by owner.  A second
+pass with a RAR-activated RNTI forces the full-table fallback on both ranks."""
 import os
 import sys
 import numpy as np
@@ -43,6 +45,17 @@ def _tables(cell_args, ttis):
     return cell, info, cands
 
 
+def _compact(srch, info, cands):
+    from ltesniffer_b200 import capi
+    comp = np.zeros(len(info), capi.COMPACT_DTYPE)
+    for i in range(len(info)):
+        comp[i] = srch.compact_from_table(info[i], cands[i])[0]
+    return torch.from_numpy(comp.view(np.uint8).reshape(len(info), capi.COMPACT_DTYPE.itemsize))
+
+
+RAR_RNTI = 0x4321
+
+
 def _worker(rank, world, port, q):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
@@ -53,18 +66,29 @@ def _worker(rank, world, port, q):
     mine = np.arange(rank, N_SF, world)
     cell, info, cands = _tables(cell_args, mine)
     ct = torch.from_numpy(cands.view(np.uint8).reshape(len(mine), capi.MAX_LOC, capi.MAX_SIZES, 16))
-    info_all, cands_all = shard.gather_tables(info, ct, world, "cpu")
-    assert [info_all[g].tti for g in range(N_SF)] == list(range(N_SF))
     L = capi.load_library()
     srch = capi.Search(*cell_args)
-    dcis, grants, gidx, ng = shard.search_and_select(L, srch, info_all, cands_all, world, rank, 64 * N_SF, 64 * N_SF)
-    q.put((rank, [(int(d["sf"]), int(d["rnti"]), int(d["format"]), int(d["ncce"]), int(d["L"]), int(d["bits"])) for d in dcis],
-           [(int(grants[i].sf), int(grants[i].rnti), int(grants[i].nof_re), int(gidx[i])) for i in range(ng)]))
+    info_all, comp_all = shard.gather_tables(info, _compact(srch, info, cands), world, "cpu")
+    assert [info_all[g].tti for g in range(N_SF)] == list(range(N_SF))
+    dcis, grants, gidx, ng = shard.search_and_select(L, srch, info_all, comp_all, world, rank, 64 * N_SF, 64 * N_SF)
+    # second pass on a fresh history with a RAR-activated RNTI: the survivor form must be refused and the full tables gathered
+    srch2 = capi.Search(*cell_args)
+    L.ltephy_search_activate(srch2.h, RAR_RNTI, 0, 2)
+    fetched = []
+
+    def full_fetch():
+        fetched.append(1)
+        return shard.gather_full_tables(ct, world, "cpu")
+    dcis2, _, _, _ = shard.search_and_select(L, srch2, info_all, comp_all, world, rank, 64 * N_SF, 64 * N_SF, full_fetch)
+    key = lambda d: (int(d["sf"]), int(d["rnti"]), int(d["format"]), int(d["ncce"]), int(d["L"]), int(d["bits"]))
+    q.put((rank, [key(d) for d in dcis], [(int(grants[i].sf), int(grants[i].rnti), int(grants[i].nof_re), int(gidx[i])) for i in range(ng)],
+           [key(d) for d in dcis2], len(fetched)))
     dist.destroy_process_group()
 
 
 def test_two_rank_sharding_matches_single_process(infra):
     sys.path.insert(0, ROOT)
+    import ctypes as C
     from ltesniffer_b200 import capi, shard
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
@@ -76,17 +100,28 @@ def test_two_rank_sharding_matches_single_process(infra):
     for p in procs:
         p.join(60)
         assert p.exitcode == 0
-    # single-process reference
+    # single-process reference: one history, FULL tables
     cell_args = (50, 1, 3, 1)
     cell, info, cands = _tables(cell_args, np.arange(N_SF))
     L = capi.load_library()
     capi._bind_search(L)
-    srch = capi.Search(*cell_args)
-    ct = torch.from_numpy(cands.view(np.uint8).reshape(N_SF, capi.MAX_LOC, capi.MAX_SIZES, 16))
-    dcis, grants, gidx, ng = shard.search_and_select(L, srch, info, ct, 1, 0, 64 * N_SF, 64 * N_SF)
-    ref_dcis = [(int(d["sf"]), int(d["rnti"]), int(d["format"]), int(d["ncce"]), int(d["L"]), int(d["bits"])) for d in dcis]
+    key = lambda d: (int(d["sf"]), int(d["rnti"]), int(d["format"]), int(d["ncce"]), int(d["L"]), int(d["bits"]))
+
+    def walk_full(srch):
+        dcis = np.zeros(64 * N_SF, capi.DCI_DTYPE)
+        nd = C.c_uint32(0)
+        assert L.ltephy_search_batch(srch.h, info, cands.ctypes.data_as(C.c_void_p), N_SF, dcis.ctypes.data_as(C.c_void_p), len(dcis), C.byref(nd)) == 0
+        return [key(d) for d in dcis[:nd.value]]
+    ref_dcis = walk_full(capi.Search(*cell_args))
     assert len(ref_dcis) >= N_SF // 2
     assert out[0][1] == ref_dcis and out[1][1] == ref_dcis           # every rank accepts the same DCIs as one process
+    srch2 = capi.Search(*cell_args)
+    L.ltephy_search_activate(srch2.h, RAR_RNTI, 0, 2)
+    ref_dcis2 = walk_full(srch2)
+    assert all(o[3] == ref_dcis2 and o[4] == 1 for o in out)         # fallback taken once per rank, same result as one process
+    srch3 = capi.Search(*cell_args)
+    dcis, grants, gidx, ng = shard.search_and_select(L, srch3, info, _compact(srch3, info, cands), 1, 0, 64 * N_SF, 64 * N_SF)
+    assert [key(d) for d in dcis] == ref_dcis
     ref_grants = [(int(grants[i].sf), int(grants[i].rnti), int(grants[i].nof_re), int(gidx[i])) for i in range(ng)]
     merged = sorted([(g[0] * 2 + r, g[1], g[2], g[3]) for r in range(2) for g in out[r][2]], key=lambda x: x[3])
     assert merged == sorted(ref_grants, key=lambda x: x[3])          # grants partition by owner, local sf = g // world
