@@ -92,9 +92,9 @@ typedef struct {
  * pad[1] = li, pad[2] = si. */
 #define LTEPHY_COMPACT_CAP 248
 typedef struct {
-  uint16_t off;
-  uint8_t  mask;
-  uint8_t  pad;
+  uint16_t off;   /* index of the location's first listed entry */
+  uint8_t  mask;  /* bit si: column si of this location is listed */
+  uint8_t  pad;   /* union of mask over the location and all locations nested in it (aggregation-level tree) */
 } ltephy_cloc_t;
 typedef struct {
   uint32_t      count;    /* survivors of this subframe; > LTEPHY_COMPACT_CAP: list is truncated, use the full table */

@@ -32,19 +32,27 @@ struct RntiManager {
   // Sliding histogram over the last HIST_DEPTH added entries (Histogram.cc).  Only non-zero RNTIs are stored,
   // with the add-position they were written at, so the zero padding of stepTime costs O(1) plus the entries it
   // expires; observable behaviour (getFrequency of any value, including 0) is unchanged.
+  // Everything the walk needs to know about one RNTI sits in one 32-byte record (histogram counts of all formats,
+  // active-set state), so that validating a candidate touches one cache line instead of a dozen arrays.
+  struct alignas(32) Rec {
+    uint16_t cnt[NF];
+    uint8_t  active, reason, assoc, pad;
+    uint32_t last_seen;
+  };
   struct Hist {
     struct Ent {
       uint64_t pos;
       uint16_t rnti;
     };
-    std::vector<Ent>      q     = std::vector<Ent>(HIST_DEPTH); // circular FIFO of the non-zero entries in the window
-    std::vector<uint16_t> count = std::vector<uint16_t>(65536, 0);
-    uint32_t              head = 0, size = 0;
+    std::vector<Ent> q = std::vector<Ent>(HIST_DEPTH); // circular FIFO of the non-zero entries in the window
+    Rec*             rec = nullptr;                       // shared per-RNTI records; this histogram owns cnt[f]
+    uint32_t         f   = 0;
+    uint32_t         head = 0, size = 0;
     uint64_t              pos  = 0; // number of adds so far
     inline void           expire()
     {
       while (size && q[head].pos + HIST_DEPTH <= pos - 1) {
-        count[q[head].rnti]--;
+        rec[q[head].rnti].cnt[f]--;
         head = head + 1 == HIST_DEPTH ? 0 : head + 1;
         size--;
       }
@@ -58,7 +66,7 @@ struct RntiManager {
         if (tail >= HIST_DEPTH) tail -= HIST_DEPTH;
         q[tail] = {pos - 1, v};
         size++;
-        count[v]++;
+        rec[v].cnt[f]++;
       }
     }
     inline void add_zeros(uint32_t n)
@@ -66,20 +74,23 @@ struct RntiManager {
       pos += n;
       expire();
     }
-    inline uint32_t freq(uint16_t v) const { return v ? count[v] : (uint32_t)(std::min<uint64_t>(pos, HIST_DEPTH) - size); }
+    inline uint32_t freq(uint16_t v) const { return v ? rec[v].cnt[f] : (uint32_t)(std::min<uint64_t>(pos, HIST_DEPTH) - size); }
   };
   struct Interval {
     uint16_t a, b;
   };
   Hist                  hist[NF];
   std::vector<Interval> evergreen[NF], forbidden[NF];
-  std::vector<uint8_t>  active  = std::vector<uint8_t>(65536, 0);
-  std::vector<uint8_t>  reason  = std::vector<uint8_t>(65536, 0);
-  std::vector<uint32_t> last_seen = std::vector<uint32_t>(65536, 0);
-  std::vector<uint32_t> assoc   = std::vector<uint32_t>(65536, 0);
+  std::vector<Rec>      rec = std::vector<Rec>(65536, Rec{});
   uint32_t              timestamp = 0, threshold = 5;
   int32_t               remaining[NF];
-  RntiManager() { std::fill(remaining, remaining + NF, (int32_t)PER_SF); }
+  RntiManager()
+  {
+    std::fill(remaining, remaining + NF, (int32_t)PER_SF);
+    for (int i = 0; i < NF; i++) hist[i].rec = rec.data(), hist[i].f = (uint32_t)i;
+  }
+  RntiManager(const RntiManager&)            = delete;
+  RntiManager& operator=(const RntiManager&) = delete;
 
   bool is_evergreen(uint16_t r, uint32_t f) const
   {
@@ -102,18 +113,18 @@ struct RntiManager {
   uint32_t n_rar = 0; // RNTIs currently active with reason RAR (they make the walk look at every format-0 candidate)
   void     activate(uint16_t r, uint8_t why)
   {
-    if (!active[r]) active[r] = 1, reason[r] = why, n_rar += why == ACT_RAR;
+    if (!rec[r].active) rec[r].active = 1, rec[r].reason = why, n_rar += why == ACT_RAR;
   }
   void deactivate(uint16_t r)
   {
-    if (active[r]) n_rar -= reason[r] == ACT_RAR, active[r] = 0, assoc[r] = 0, reason[r] = ACT_UNSET;
+    if (rec[r].active) n_rar -= rec[r].reason == ACT_RAR, rec[r].active = 0, rec[r].assoc = 0, rec[r].reason = ACT_UNSET;
   }
-  bool expired(uint16_t r) const { return !(active[r] && timestamp - last_seen[r] < LIFETIME); }
+  bool expired(uint16_t r) const { return !(rec[r].active && timestamp - rec[r].last_seen < LIFETIME); }
   bool validate(uint16_t r, uint32_t f)
   {
     if (is_evergreen(r, f)) return true;
     if (is_forbidden(r, f)) return false;
-    if (active[r]) {
+    if (rec[r].active) {
       if (!expired(r)) return true;
       deactivate(r);
     }
@@ -125,7 +136,7 @@ struct RntiManager {
     const uint32_t ul = hist[0].freq(r), dl = likely ? hist[likely].freq(r) : 0;
     if (ul + dl > threshold) {
       activate(r, ACT_HISTOGRAM);
-      assoc[r] = dl > threshold ? likely : 0;
+      rec[r].assoc = (uint8_t)(dl > threshold ? likely : 0);
       return true;
     }
     return false;
@@ -133,14 +144,14 @@ struct RntiManager {
   bool validate_and_refresh(uint16_t r, uint32_t f)
   {
     const bool ok = validate(r, f);
-    if (ok) last_seen[r] = timestamp;
+    if (ok) rec[r].last_seen = timestamp;
     return ok;
   }
   void activate_and_refresh(uint16_t r, uint32_t f, uint8_t why)
   {
     activate(r, why);
-    last_seen[r] = timestamp;
-    assoc[r]     = f;
+    rec[r].last_seen = timestamp;
+    rec[r].assoc     = (uint8_t)f;
   }
   void step_time()
   {
@@ -197,6 +208,7 @@ struct Cand {
   uint8_t  ssm    = 0;
   uint16_t nof_bits = 0;
 };
+typedef unsigned __int128 u128;
 struct Loc {
   uint8_t L;
   uint8_t ncce;
@@ -231,13 +243,30 @@ struct ltephy_search {
   // per-subframe scratch
   const ltephy_cand_t*    T  = nullptr;
   const ltephy_compact_t* CT = nullptr; // survivor form (then T is null)
-  uint32_t                sf_idx = 0, ncce_sf = 0, sf_batch = 0;
-  Loc                  loc[LTEPHY_MAX_LOC];
-  int16_t              loc_of[4][LTEPHY_MAX_CCE]; // [L][ncce] -> location index or -1
+  uint32_t                sf_idx = 0, ncce_sf = 0, sf_batch = 0, pass_mask = 0;
+  // Location state of the subframe being walked, as bit masks in CCE space: location (L, ncce) is bit ncce of the level-L
+  // masks (only multiples of 2^L are meaningful there).
+  //   low    - CCEs whose mean |LLR| is below 0.7 (a location covering one has insufficient power, DCISearch.cc:473-489)
+  //   occ    - CCEs of the accepted locations (= the reference's `used` of the location itself, and `occupied` of every
+  //            location overlapping it, DCISearch.cc:381-392)
+  //   blk[L] - locations of level L that cover a CCE of low | occ (fold of the CCE mask, refreshed on acceptance)
+  //   chk[L] - locations of level L already inspected in the current pass
+  //   val[L] - locations of level L that exist in this subframe (srsran_pdcch_ue_locations_all_map, falcon_pdcch.c:321-356)
+  u128     low = 0, occ = 0, blk[4]{}, chk[4]{}, val[4]{};
+  uint32_t nq[4]{};
+  inline void refold()
+  {
+    blk[0] = low | occ;
+    blk[1] = blk[0] | (blk[0] >> 1);
+    blk[2] = blk[1] | (blk[1] >> 2);
+    blk[3] = blk[2] | (blk[2] >> 4);
+  }
   struct LocTemplate {
     uint32_t n = 0;
     Loc      loc[LTEPHY_MAX_LOC];
     int16_t  loc_of[4][LTEPHY_MAX_CCE];
+    u128     val[4]{};
+    uint32_t nq[4]{};
   } tmpl[3];
   std::vector<TempDci0> temp_dci0;
   ltephy_dci_t*        out = nullptr;
@@ -294,21 +323,47 @@ struct ltephy_search {
     }
     out_n++;
   }
+  static inline u128 cce_range(uint32_t ncce, uint32_t L) { return ((((u128)1) << (1u << L)) - 1) << ncce; }
+  inline bool        skip(uint32_t ncce, uint32_t L) const { return (uint64_t)((blk[L] | chk[L]) >> ncce) & 1u; }
+  // location index in the candidate table: levels are laid out 3,2,1,0
+  inline uint32_t loc_index(uint32_t ncce, uint32_t L) const
+  {
+    uint32_t b = 0;
+    for (uint32_t l = 3; l > L; l--) b += nq[l];
+    return b + (ncce >> L);
+  }
+  // A location whose whole subtree holds no survivor for the formats of this pass: the reference's recursion decodes
+  // every reachable location, finds nothing, and marks them inspected.  Returns the number of locations it would visit.
+  uint32_t sweep_empty(uint32_t ncce, uint32_t L, uint32_t max_depth)
+  {
+    chk[L] |= (u128)1 << ncce;
+    uint32_t n = 1;
+    if (L > 0 && max_depth > 0) {
+      if (!skip(ncce, L - 1)) n += sweep_empty(ncce, L - 1, max_depth - 1);
+      if (!skip(ncce + (1u << (L - 1)), L - 1)) n += sweep_empty(ncce + (1u << (L - 1)), L - 1, max_depth - 1);
+    }
+    return n;
+  }
   int inspect(uint32_t ncce, uint32_t L, uint32_t max_depth, const uint8_t* mf, uint32_t nf, bool discovery, const Cand* parent)
   {
-    const int li = loc_of[L][ncce];
-    if (li < 0) return 0;
-    Loc& lc = loc[li];
-    if (lc.occupied || lc.checked || !lc.sufficient_power) return 0;
+    if (!((uint64_t)(val[L] >> ncce) & 1u) || skip(ncce, L)) return 0;
+    const uint32_t li = loc_index(ncce, L);
+    if (CT && !(CT->loc[li].pad & pass_mask)) { // pad = union of the survivor masks over the subtree
+      stats.nof_decoded_locations += nf * sweep_empty(ncce, L, max_depth);
+      return 0;
+    }
     Cand     cand[NF];
     int      best = -1;
     uint32_t best_val = 0, n_above = 0;
+    if (CT && !(CT->loc[li].mask & pass_mask)) // no survivor in any column this pass looks at: every candidate ends as rnti = 0
+      stats.nof_decoded_locations += nf;
+    else
     for (uint32_t f = 0; f < nf; f++) {
       const uint32_t fmt = mf[f];
       stats.nof_decoded_locations++;
       if (CT && !((CT->loc[li].mask >> st.index_of[fmt]) & 1u)) continue; // not a survivor: every path below ends in rnti = 0
       fetch((uint32_t)li, fmt, cand[f]);
-      if (rm.reason[cand[f].rnti] == ACT_RAR && cand[f].format == 0) {
+      if (rm.rec[cand[f].rnti].reason == ACT_RAR && cand[f].format == 0) {
         bool add = true;
         for (auto& m : temp_dci0)
           if (m.format == cand[f].format && m.rnti == cand[f].rnti && m.ncce == ncce) add = false;
@@ -349,7 +404,7 @@ struct ltephy_search {
         }
       if (best < 0) n_above = 0;
     }
-    lc.checked = true;
+    chk[L] |= (u128)1 << ncce;
     int disamb = 0;
     if (n_above > 0 && cand[best].ssm == 1) {
       if (L > 0 && max_depth > 0) disamb = inspect(ncce + (1u << (L - 1)), L - 1, max_depth - 1, mf, nf, false, nullptr);
@@ -375,12 +430,8 @@ struct ltephy_search {
       if (rr > 0) return rr;
     }
     if (n_above > 0) {
-      lc.used = true;
-      for (uint32_t c = ncce; c < ncce + (1u << L); c++)
-        for (int a = 0; a < 4; a++) {
-          const int j = loc_of[a][c & ~((1u << a) - 1)];
-          if (j >= 0) loc[j].occupied = loc[j].checked = true;
-        }
+      occ |= cce_range(ncce, L);
+      refold();
       rm.add_candidate(cand[best].rnti, mf[best]);
       all[mf[best]].hits++;
       const uint32_t L_dis = disamb > 0 ? L - 1 : L;
@@ -413,34 +464,32 @@ struct ltephy_search {
       sf_idx  = info.tti % 10;
       ncce_sf = nof_cce[info.cfi - 1];
       stats.nof_cce += ncce_sf;
-      const uint32_t     lim = std::min<uint32_t>(ncce_sf, LTEPHY_SEARCH_MAX_CCE);
-      const LocTemplate& tp  = tmpl[info.cfi - 1];
-      const uint32_t     k   = tp.n;
-      memcpy(loc, tp.loc, k * sizeof(Loc));
-      memcpy(loc_of, tp.loc_of, sizeof(loc_of));
+      const uint32_t lim = std::min<uint32_t>(ncce_sf, LTEPHY_SEARCH_MAX_CCE);
+      const uint32_t k   = tmpl[info.cfi - 1].n;
       stats.nof_locations += k;
+      low = occ = 0;
       for (uint32_t c = 0; c < lim; c++)
-        if (info.cce_power[c] < 0.7f)
-          for (int a = 0; a < 4; a++) {
-            const int j = loc_of[a][c & ~((1u << a) - 1)];
-            if (j >= 0) loc[j].sufficient_power = false;
-          }
+        if (info.cce_power[c] < 0.7f) low |= (u128)1 << c;
+      refold();
+      for (uint32_t l = 0; l < 4; l++) nq[l] = tmpl[info.cfi - 1].nq[l], val[l] = tmpl[info.cfi - 1].val[l];
       ret = 0;
-      for (uint32_t i = 0; i < k; i++) ret += inspect(loc[i].ncce, loc[i].L, 99, primary, n_primary, true, nullptr);
-      if (!skip_secondary) {
-        for (uint32_t i = 0; i < k; i++) loc[i].checked = false;
-        for (uint32_t i = 0; i < k; i++) ret += inspect(loc[i].ncce, loc[i].L, 99, secondary, n_secondary, true, nullptr);
+      for (int pass = 0; pass < (skip_secondary ? 1 : 2); pass++) {
+        const uint8_t* mf = pass ? secondary : primary;
+        const uint32_t nf = pass ? n_secondary : n_primary;
+        pass_mask = 0;
+        for (uint32_t f = 0; f < nf; f++) pass_mask |= 1u << st.index_of[mf[f]];
+        chk[0] = chk[1] = chk[2] = chk[3] = 0;
+        for (int l = 3; l >= 0; l--) // table order: level 3 first, ascending CCE; inspecting only ever removes locations from `todo`
+          for (;;) {
+            const u128     todo = val[l] & ~(blk[l] | chk[l]);
+            const uint64_t lo = (uint64_t)todo, hi = (uint64_t)(todo >> 64);
+            if (!(lo | hi)) break;
+            const uint32_t ncce = lo ? (uint32_t)__builtin_ctzll(lo) : 64u + (uint32_t)__builtin_ctzll(hi);
+            ret += inspect(ncce, (uint32_t)l, 99, mf, nf, true, nullptr);
+          }
       }
-      uint32_t missed = 0;
-      for (uint32_t c = 0; c < lim; c++) {
-        if (info.cce_power[c] < 0.7f) continue;
-        bool m = true;
-        for (int a = 0; a < 4 && m; a++) {
-          const int j = loc_of[a][c & ~((1u << a) - 1)];
-          if (j >= 0 && loc[j].used) m = false;
-        }
-        missed += m;
-      }
+      const u128     all = lim >= 128 ? ~(u128)0 : (((u128)1 << lim) - 1), rest = all & ~low & ~occ;
+      const uint32_t missed = (uint32_t)(__builtin_popcountll((uint64_t)rest) + __builtin_popcountll((uint64_t)(rest >> 64)));
       stats.nof_missed_cce += missed;
       rm.step_time();
     }
@@ -738,9 +787,11 @@ ltephy_search_t* ltephy_search_create_cell(uint32_t nof_prb, uint32_t nof_ports,
     uint32_t       k   = 0;
     for (int l = 3; l >= 0; l--) {
       const uint32_t Lc = 1u << l;
+      tp.nq[l] = lim / Lc;
       for (uint32_t i = 0; i < lim / Lc && k < LTEPHY_MAX_LOC; i++) {
         tp.loc[k]            = {(uint8_t)l, (uint8_t)(Lc * i), false, false, false, true};
         tp.loc_of[l][Lc * i] = (int16_t)k;
+        tp.val[l] |= (u128)1 << (Lc * i);
         k++;
       }
     }
@@ -839,6 +890,16 @@ int ltephy_compact_from_table(const ltephy_search_t* s, const ltephy_sf_info_t* 
     }
     out->loc[li].mask = (uint8_t)mask;
   }
+  for (uint32_t li = 0; li < tp.n; li++) { // pad = union of the masks over the location's subtree (itself included)
+    const uint32_t L = tp.loc[li].L, ncce = tp.loc[li].ncce;
+    uint32_t       u = out->loc[li].mask;
+    for (uint32_t l2 = 0; l2 < L; l2++)
+      for (uint32_t c = ncce; c < ncce + (1u << L); c += 1u << l2) {
+        const int j = tp.loc_of[l2][c];
+        if (j >= 0) u |= out->loc[j].mask;
+      }
+    out->loc[li].pad = (uint8_t)u;
+  }
   out->count = cnt;
   return LTEPHY_SUCCESS;
 }
@@ -852,8 +913,8 @@ int      ltephy_search_rnti_validate_and_refresh(ltephy_search_t* s, uint16_t r,
 void     ltephy_search_rnti_add_candidate(ltephy_search_t* s, uint16_t r, uint32_t f) { s->rm.add_candidate(r, f); }
 void     ltephy_search_rnti_step_time(ltephy_search_t* s) { s->rm.step_time(); }
 uint32_t ltephy_search_rnti_frequency(const ltephy_search_t* s, uint16_t r, uint32_t f) { return s->rm.freq(r, f); }
-uint32_t ltephy_search_rnti_assoc_format(const ltephy_search_t* s, uint16_t r) { return s->rm.assoc[r]; }
-int      ltephy_search_rnti_reason(const ltephy_search_t* s, uint16_t r) { return s->rm.reason[r]; }
+uint32_t ltephy_search_rnti_assoc_format(const ltephy_search_t* s, uint16_t r) { return s->rm.rec[r].assoc; }
+int      ltephy_search_rnti_reason(const ltephy_search_t* s, uint16_t r) { return s->rm.rec[r].reason; }
 int      ltephy_search_rnti_is_forbidden(const ltephy_search_t* s, uint16_t r, uint32_t f) { return s->rm.is_forbidden(r, f); }
 int      ltephy_search_rnti_is_evergreen(const ltephy_search_t* s, uint16_t r, uint32_t f) { return s->rm.is_evergreen(r, f); }
 

@@ -267,15 +267,17 @@ __global__ void __launch_bounds__(LTEPHY_MAX_LOC) cand_compact_kernel(const __gr
 {
   static_assert(LTEPHY_MAX_LOC % 32 == 0 && LTEPHY_MAX_SIZES == 8, "layout");
   __shared__ uint32_t wtot[LTEPHY_MAX_LOC / 32];
+  __shared__ uint8_t  smask[LTEPHY_MAX_LOC];
   const uint32_t sf = blockIdx.x, li = threadIdx.x, lane = li & 31u, warp = li >> 5;
   const uint32_t cfi = info[sf].cfi;
   const bool     ok  = cfi >= 1 && cfi <= 3;
   const uint32_t nloc = ok ? c.nloc[cfi - 1] : 0;
   uint4          e[LTEPHY_MAX_SIZES];
-  uint32_t       mask = 0;
+  uint32_t       mask = 0, my_L = 0, my_q = 0, lim = 0;
   if (li < nloc) {
     const uint32_t ent = c.loc_tab[cfi - 1][li], ncce = ent & 0xFFu, L = ent >> 8;
-    const uint32_t ncce_sf = c.nof_cce[cfi - 1], lim = min(ncce_sf, (uint32_t)LTEPHY_SEARCH_MAX_CCE), sf_idx = info[sf].tti % 10;
+    const uint32_t ncce_sf = c.nof_cce[cfi - 1], sf_idx = info[sf].tti % 10;
+    lim = min(ncce_sf, (uint32_t)LTEPHY_SEARCH_MAX_CCE), my_L = L, my_q = ncce >> L;
     bool           suff = true;
     for (uint32_t i = ncce; i < ncce + (1u << L); i++)
       if (i < lim && info[sf].cce_power[i] < 0.7f) suff = false;
@@ -317,7 +319,19 @@ __global__ void __launch_bounds__(LTEPHY_MAX_LOC) cand_compact_kernel(const __gr
     if ((int)lane >= off) inc += t;
   }
   if (lane == 31) wtot[warp] = inc;
+  smask[li] = (uint8_t)mask;
   __syncthreads();
+  uint32_t sub = mask; // union of the masks over the location's subtree: levels are laid out 3,2,1,0 with lim >> l entries each
+  if (li < nloc)
+    for (uint32_t l2 = 0; l2 < my_L; l2++) {
+      uint32_t b = 0;
+      for (uint32_t l3 = 3; l3 > l2; l3--) b += lim >> l3;
+      const uint32_t span = 1u << (my_L - l2);
+      for (uint32_t j = 0; j < span; j++) {
+        const uint32_t q2 = my_q * span + j;
+        if (q2 < (lim >> l2) && b + q2 < nloc) sub |= smask[b + q2];
+      }
+    }
   uint32_t base = 0, total = 0;
 #pragma unroll
   for (uint32_t w = 0; w < LTEPHY_MAX_LOC / 32; w++) {
@@ -327,7 +341,7 @@ __global__ void __launch_bounds__(LTEPHY_MAX_LOC) cand_compact_kernel(const __gr
   ltephy_compact_t& o   = out[sf];
   uint32_t          pos = base + inc - cnt;
   ltephy_cloc_t     cl;
-  cl.off = li < nloc ? (uint16_t)min(pos, 0xFFFFu) : (uint16_t)0, cl.mask = (uint8_t)mask, cl.pad = 0;
+  cl.off = li < nloc ? (uint16_t)min(pos, 0xFFFFu) : (uint16_t)0, cl.mask = (uint8_t)mask, cl.pad = (uint8_t)sub;
   o.loc[li] = cl;
   if (li == 0) o.count = total, o.reserved = 0;
   uint4* lst = reinterpret_cast<uint4*>(o.list);
