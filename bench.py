@@ -307,35 +307,69 @@ def main():
             phys[t]._chk(L.ltephy_submit_iq(phys[t].h, p(iq_pin), tti_c.ctypes.data_as(C.c_void_p), B), "submit_iq")
         phys[t].n = B
 
-    def sh_finish_b(t):
-        phys[t]._chk(L.ltephy_get_phase_b(phys[t].h, res[t], p(scr[t].payload), scr[t].payload.numel()), "get_phase_b")
-        nby = int(np.frombuffer(res[t], dtype=TB_DTYPE, count=2 * ngr[t])["payload_len"].sum()) if ngr[t] else 0
-        n = min(nby, gather_sz)
-        out_local[:n].copy_(scr[t].payload[:n], non_blocking=True)
-        dist.gather(out_local, out_all, dst=0)   # the single gather of decoded transport blocks
+    def sh_gather_tbs(t):
+        nb = C.c_size_t(0)
+        phys[t]._chk(L.ltephy_copy_phase_b_device(phys[t].h, p(out_local), gather_sz, C.byref(nb)), "copy_phase_b_device")
+        dist.gather(out_local, out_all, dst=0)   # the single gather of decoded transport blocks (device to device over NVLink)
+
+    # T host threads, one PHY handle each (thread t takes batches t, t+T, ...).  Collectives and the walk happen in batch
+    # order inside a turn-taking section, so every rank issues the same sequence on the one communicator:
+    #   turn k: [gather of the transport blocks of batch k-T, decoded by this thread one round earlier]
+    #           all-gather of batch k's survivor forms -> walk over all N*B subframes -> this rank's grants
+    # Phase A of batches k+1.. and phase B of k-1.. run on the GPU meanwhile.
+    turn = threading.Condition()
+    sh_next = [0]
+    sh_base = [0]
 
     def run_sharded(nsteps, device_resident):
-        sh_submit_a(0, device_resident)
-        pending = None
-        for k in range(nsteps):
-            t = k % T
-            if k + 1 < nsteps:
-                sh_submit_a((k + 1) % T, device_resident)
-            S = scr[t]
-            phys[t]._chk(L.ltephy_get_phase_a_compact(phys[t].h, S.info, p(S.comp)), "get_phase_a_compact")
-            info_all, comp_all = shard.gather_tables(S.info, S.comp, world, "cuda")
+        base = sh_base[0]
+        sh_base[0] += nsteps
+        pend = [False] * T
+        errs = []
 
-            def full_fetch():   # survivor form refused (never on this workload): all-gather the full tables instead
-                phys[t]._chk(L.ltephy_get_phase_a(phys[t].h, None, p(S.cands)), "get_phase_a")
-                return shard.gather_full_tables(S.cands, world, "cuda")
-            d, grants, gidx, ng = shard.search_and_select(L, srch, info_all, comp_all, world, rank, max_dcis, 24 * B, full_fetch)
-            nd.value = len(d)
-            if pending is not None:
-                sh_finish_b(pending)
-            phys[t]._chk(L.ltephy_submit_grants(phys[t].h, grants, ng), "submit_grants")
-            ngr[t] = ng
-            pending = t
-        sh_finish_b(pending)
+        def worker(t):
+            try:
+                torch.cuda.set_device(local)
+                for k in range(t, nsteps, T):
+                    sh_submit_a(t, device_resident)
+                    S = scr[t]
+                    phys[t]._chk(L.ltephy_get_phase_a_compact(phys[t].h, S.info, p(S.comp)), "get_phase_a_compact")
+                    with turn:
+                        turn.wait_for(lambda: sh_next[0] == base + k or errs)
+                    if errs:
+                        return
+                    if pend[t]:
+                        sh_gather_tbs(t)
+                        pend[t] = False
+                    info_all, comp_all = shard.gather_tables(S.info, S.comp, world, "cuda")
+
+                    def full_fetch():   # survivor form refused (never on this workload): all-gather the full tables instead
+                        phys[t]._chk(L.ltephy_get_phase_a(phys[t].h, None, p(S.cands)), "get_phase_a")
+                        return shard.gather_full_tables(S.cands, world, "cuda")
+                    d, grants, gidx, ng = shard.search_and_select(L, srch, info_all, comp_all, world, rank, max_dcis, 24 * B, full_fetch)
+                    nd.value = len(d)
+                    with turn:
+                        sh_next[0] += 1
+                        turn.notify_all()
+                    phys[t]._chk(L.ltephy_submit_grants(phys[t].h, grants, ng), "submit_grants")
+                    ngr[t] = ng
+                    phys[t]._chk(L.ltephy_get_phase_b(phys[t].h, res[t], p(scr[t].payload), scr[t].payload.numel()), "get_phase_b")
+                    pend[t] = True
+            except BaseException as e:     # never leave the other threads waiting for a turn that will not come
+                with turn:
+                    errs.append(e)
+                    turn.notify_all()
+        if T == 1 or nsteps == 1:
+            worker(0)
+        else:
+            with ThreadPoolExecutor(T) as ex:
+                list(ex.map(worker, range(T)))
+        if errs:
+            raise errs[0]
+        for k in range(max(0, nsteps - T), nsteps):      # transport blocks of the last round, same order on every rank
+            if pend[k % T]:
+                sh_gather_tbs(k % T)
+                pend[k % T] = False
 
     def step_sharded(device_resident):
         run_sharded(1, device_resident)

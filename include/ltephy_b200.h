@@ -176,6 +176,10 @@ const ltephy_compact_t* ltephy_phase_a_compact_buffer(const ltephy_t* h);
 int ltephy_submit_grants(ltephy_t* h, const ltephy_grant_t* grants, uint32_t n);
 /* results[n][2]; payload receives the TB bytes back to back */
 int ltephy_get_phase_b(ltephy_t* h, ltephy_tb_result_t* results, uint8_t* payload, size_t payload_cap);
+/* device-to-device copy of the raw payload buffer of the current phase B (transport block i at the running offset
+ * sum_{j<i} ((tbs_j/8 + 6) & ~3), followed by its 3 CRC bytes) into dst_dev, for a collective without a host round trip
+ * (the "single NCCL gather of decoded transport blocks").  Blocks until the copy is done. */
+int ltephy_copy_phase_b_device(ltephy_t* h, void* dst_dev, size_t cap, size_t* nbytes);
 
 /* ---- uplink: PUSCH (PUSCH_Decoder::decode / decode_run, src/src/UL_Sniffer_PUSCH.cc:250-263,389-392) ------------ */
 typedef struct {

@@ -100,6 +100,7 @@ def load_library(build_if_missing=True):
     L.ltephy_phase_a_compact_buffer.restype = P
     L.ltephy_submit_grants.argtypes = [P, P, C.c_uint32]
     L.ltephy_get_phase_b.argtypes = [P, P, P, C.c_size_t]
+    L.ltephy_copy_phase_b_device.argtypes = [P, P, C.c_size_t, P]
     L.ltephy_dci_sweep.argtypes = [P, P, P, C.c_uint32, P]
     L.ltephy_turbo_batch.argtypes = [P, P, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, P, P, P]
     L.ltephy_tap.argtypes = [P, C.c_int, P, C.c_size_t]

@@ -721,6 +721,18 @@ extern "C" int ltephy_submit_grants(ltephy_t* h, const ltephy_grant_t* gin, uint
   return LTEPHY_SUCCESS;
 }
 
+// Device-to-device copy of the raw phase-B payload buffer (TB i at the running offset sum_{j<i} ((tbs_j/8 + 6) & ~3), its 3 CRC
+// bytes behind it), for callers that hand the decoded transport blocks to a collective without a host round trip.
+extern "C" int ltephy_copy_phase_b_device(ltephy_t* h, void* dst_dev, size_t cap, size_t* nbytes)
+{
+  if (!h || !dst_dev || !nbytes) return fail(LTEPHY_ERROR_INVALID_INPUTS, "copy_phase_b_device: bad arguments");
+  CU(cudaSetDevice(h->cfg.device));
+  const size_t n = h->payload_bytes < cap ? h->payload_bytes : cap;
+  if (n) CU(cudaMemcpyAsync(dst_dev, h->d_payload.p, n, cudaMemcpyDeviceToDevice, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  *nbytes = n;
+  return LTEPHY_SUCCESS;
+}
 extern "C" int ltephy_get_phase_b(ltephy_t* h, ltephy_tb_result_t* results, uint8_t* payload, size_t payload_cap)
 {
   if (!h || !results) return fail(LTEPHY_ERROR_INVALID_INPUTS, "get_phase_b: bad arguments");
