@@ -312,20 +312,33 @@ def main():
         phys[t]._chk(L.ltephy_copy_phase_b_device(phys[t].h, p(out_local), gather_sz, C.byref(nb)), "copy_phase_b_device")
         dist.gather(out_local, out_all, dst=0)   # the single gather of decoded transport blocks (device to device over NVLink)
 
-    # T host threads, one PHY handle each (thread t takes batches t, t+T, ...).  Collectives and the walk happen in batch
-    # order inside a turn-taking section, so every rank issues the same sequence on the one communicator:
-    #   turn k: [gather of the transport blocks of batch k-T, decoded by this thread one round earlier]
-    #           all-gather of batch k's survivor forms -> walk over all N*B subframes -> this rank's grants
+    # T host threads, one PHY handle each (thread t takes batches t, t+T, ...).  Two turn-taking sections, each entered in
+    # batch order, so that every rank issues the same sequence of collectives on the one communicator while the walk of
+    # batch k overlaps the exchange of batch k+1:
+    #   exchange turn k: [gather of the transport blocks of batch k-T, decoded by this thread one round earlier]
+    #                    all-gather of batch k's survivor forms (and of the full tables if the walk may need them)
+    #   walk turn k:     FALCON walk over all N*B subframes -> this rank's grants (no collective inside)
     # Phase A of batches k+1.. and phase B of k-1.. run on the GPU meanwhile.
     turn = threading.Condition()
-    sh_next = [0]
+    sh_next = [0, 0]     # next batch allowed into the exchange turn / the walk turn
     sh_base = [0]
+    wbufs = [shard.WalkBuffers(max_dcis, 24 * B) for _ in range(T)] if world > 1 else None
 
     def run_sharded(nsteps, device_resident):
         base = sh_base[0]
         sh_base[0] += nsteps
         pend = [False] * T
         errs = []
+
+        def take(which, k):
+            with turn:
+                turn.wait_for(lambda: sh_next[which] == base + k or errs)
+            return not errs
+
+        def give(which):
+            with turn:
+                sh_next[which] += 1
+                turn.notify_all()
 
         def worker(t):
             try:
@@ -334,23 +347,22 @@ def main():
                     sh_submit_a(t, device_resident)
                     S = scr[t]
                     phys[t]._chk(L.ltephy_get_phase_a_compact(phys[t].h, S.info, p(S.comp)), "get_phase_a_compact")
-                    with turn:
-                        turn.wait_for(lambda: sh_next[0] == base + k or errs)
-                    if errs:
+                    if not take(0, k):
                         return
                     if pend[t]:
                         sh_gather_tbs(t)
                         pend[t] = False
-                    info_all, comp_all = shard.gather_tables(S.info, S.comp, world, "cuda")
-
-                    def full_fetch():   # survivor form refused (never on this workload): all-gather the full tables instead
+                    info_all, comp_all = shard.gather_tables(S.info, S.comp, world, "cuda", slot=t)
+                    full = None
+                    if shard.need_full_tables(L, srch, comp_all, B * world):   # never on this workload
                         phys[t]._chk(L.ltephy_get_phase_a(phys[t].h, None, p(S.cands)), "get_phase_a")
-                        return shard.gather_full_tables(S.cands, world, "cuda")
-                    d, grants, gidx, ng = shard.search_and_select(L, srch, info_all, comp_all, world, rank, max_dcis, 24 * B, full_fetch)
+                        full = shard.gather_full_tables(S.cands, world, "cuda", slot=t)
+                    give(0)
+                    if not take(1, k):
+                        return
+                    d, grants, gidx, ng = shard.search_and_select(L, srch, info_all, comp_all, world, rank, max_dcis, 24 * B, full=full, bufs=wbufs[t])
                     nd.value = len(d)
-                    with turn:
-                        sh_next[0] += 1
-                        turn.notify_all()
+                    give(1)
                     phys[t]._chk(L.ltephy_submit_grants(phys[t].h, grants, ng), "submit_grants")
                     ngr[t] = ng
                     phys[t]._chk(L.ltephy_get_phase_b(phys[t].h, res[t], p(scr[t].payload), scr[t].payload.numel()), "get_phase_b")

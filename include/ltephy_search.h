@@ -121,6 +121,10 @@ int ltephy_search_batch(ltephy_search_t* s, const ltephy_sf_info_t* info, const 
                         uint32_t* n_dcis);
 int ltephy_search_batch_compact(ltephy_search_t* s, const ltephy_sf_info_t* info, const ltephy_compact_t* comp, const ltephy_cand_t* full_or_null,
                                 uint32_t n, ltephy_dci_t* dcis, uint32_t max_dcis, uint32_t* n_dcis);
+/* 1 if a walk over these survivor forms may ask for the full tables: a subframe overflows, or some RNTI has ever been
+ * RAR-activated on this search object.  Unlike the walk's own (exact) test this does not depend on how far the walk has
+ * progressed, so the ranks of a sharded run can decide on a collective fetch of the full tables before walking. */
+int ltephy_search_needs_full_table(const ltephy_search_t* s, const ltephy_compact_t* comp, uint32_t n);
 int ltephy_grants_from_dcis(const ltephy_search_t* s, const ltephy_sf_info_t* info, const ltephy_dci_t* dcis, uint32_t nd, uint32_t mod, uint32_t rem,
                             ltephy_grant_t* grants, uint32_t* grant_dci, uint32_t max_grants, uint32_t* n_grants);
 

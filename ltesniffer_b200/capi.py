@@ -317,6 +317,7 @@ def _bind_search(L):
     L.ltephy_search_subframe_compact.argtypes = [P, P, P, C.c_uint32, P, C.c_uint32, P]
     L.ltephy_compact_from_table.argtypes = [P, P, P, P]
     L.ltephy_search_batch_compact.argtypes = [P, P, P, P, C.c_uint32, P, C.c_uint32, P]
+    L.ltephy_search_needs_full_table.argtypes = [P, P, C.c_uint32]
     L.ltephy_search_get_stats.argtypes = [P, P]
     L.ltephy_search_validate_location.argtypes = [C.c_uint32] * 4 + [C.c_uint16]
     L.ltephy_search_validate_location.restype = C.c_uint32

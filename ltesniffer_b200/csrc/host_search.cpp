@@ -110,10 +110,12 @@ struct RntiManager {
     hist[f].add(r);
     remaining[f]--;
   }
-  uint32_t n_rar = 0; // RNTIs currently active with reason RAR (they make the walk look at every format-0 candidate)
+  uint32_t n_rar = 0;        // RNTIs currently active with reason RAR (they make the walk look at every format-0 candidate)
+  bool     rar_seen = false; // sticky: some RNTI has been RAR-activated since creation (a superset of n_rar > 0 that does not
+                             // depend on how far the walk has progressed, so that all ranks of a sharded run decide alike)
   void     activate(uint16_t r, uint8_t why)
   {
-    if (!rec[r].active) rec[r].active = 1, rec[r].reason = why, n_rar += why == ACT_RAR;
+    if (!rec[r].active) rec[r].active = 1, rec[r].reason = why, n_rar += why == ACT_RAR, rar_seen |= why == ACT_RAR;
   }
   void deactivate(uint16_t r)
   {
@@ -956,6 +958,14 @@ int ltephy_search_batch_compact(ltephy_search_t* s, const ltephy_sf_info_t* info
   }
   *n_dcis = nd;
   return LTEPHY_SUCCESS;
+}
+int ltephy_search_needs_full_table(const ltephy_search_t* s, const ltephy_compact_t* comp, uint32_t n)
+{
+  if (!s || !comp) return LTEPHY_ERROR_INVALID_INPUTS;
+  if (s->rm.rar_seen) return 1;
+  for (uint32_t i = 0; i < n; i++)
+    if (comp[i].count > LTEPHY_COMPACT_CAP) return 1;
+  return 0;
 }
 // Accepted DL DCIs -> PDSCH grants, applying decode_dl_mode's skip rule (src/src/DL_Sniffer_PDSCH.cc:887-889).
 // Only subframes with sf % mod == rem are taken (multi-GPU sharding); grant.sf = sf / mod (local index).

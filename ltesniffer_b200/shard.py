@@ -18,8 +18,8 @@ CSZ = capi.COMPACT_DTYPE.itemsize
 FSZ = capi.MAX_LOC * capi.MAX_SIZES * 16
 
 
-def _buffers(B, world, device, esz):
-    key = (B, world, str(device), esz)
+def _buffers(B, world, device, esz, slot=0):
+    key = (B, world, str(device), esz, slot)
     if key not in _stage:
         pin = torch.device(device).type == "cuda"
         _stage[key] = dict(g=torch.empty((world, B, esz), dtype=torch.uint8, device=device), o=torch.empty((B, world, esz), dtype=torch.uint8, device=device),
@@ -27,9 +27,10 @@ def _buffers(B, world, device, esz):
     return _stage[key]
 
 
-def _gather_interleaved(local_u8, B, world, device, esz):
-    """local_u8: uint8 host tensor [B*esz] -> host tensor [B*world, esz] in global order g = i*world + r (buffer reused)"""
-    st = _buffers(B, world, device, esz)
+def _gather_interleaved(local_u8, B, world, device, esz, slot=0):
+    """local_u8: uint8 host tensor [B*esz] -> host tensor [B*world, esz] in global order g = i*world + r.
+    The result lives in a staging buffer owned by `slot` and is overwritten by the next call with the same slot."""
+    st = _buffers(B, world, device, esz, slot)
     loc = local_u8.reshape(-1).to(device, non_blocking=True)
     dist.all_gather_into_tensor(st["g"].view(-1), loc)
     st["o"].copy_(st["g"].transpose(0, 1))            # [world][B] -> [B][world]
@@ -42,32 +43,55 @@ def _gather_interleaved(local_u8, B, world, device, esz):
 _info_all = {}
 
 
-def gather_tables(info_local, comp_local, world, device):
+def gather_tables(info_local, comp_local, world, device, slot=0):
     """info_local: ctypes (SfInfo * B); comp_local: uint8 tensor [B, sizeof(ltephy_compact_t)] (host, pinned if possible).
     -> (info_all ctypes array [B*world] in global order, comp_all uint8 host tensor [B*world, sizeof(ltephy_compact_t)]).
-    The returned buffers are reused by the next call with the same shape."""
+    The returned buffers belong to `slot` (one per pipeline) and are reused by its next call with the same shape."""
     B = len(info_local)
-    hi = _gather_interleaved(torch.frombuffer(info_local, dtype=torch.uint8), B, world, device, ISZ)
-    hc = _gather_interleaved(comp_local, B, world, device, CSZ)
-    if (B, world) not in _info_all:
-        _info_all[(B, world)] = (capi.SfInfo * (B * world))()
-    info_all = _info_all[(B, world)]
+    hi = _gather_interleaved(torch.frombuffer(info_local, dtype=torch.uint8), B, world, device, ISZ, slot)
+    hc = _gather_interleaved(comp_local, B, world, device, CSZ, slot)
+    if (B, world, slot) not in _info_all:
+        _info_all[(B, world, slot)] = (capi.SfInfo * (B * world))()
+    info_all = _info_all[(B, world, slot)]
     C.memmove(info_all, hi.data_ptr(), hi.numel())
     return info_all, hc
 
 
-def gather_full_tables(cands_local, world, device):
+def gather_full_tables(cands_local, world, device, slot=0):
     """cands_local: uint8 tensor [B, MAX_LOC, MAX_SIZES, 16] -> host tensor [B*world, MAX_LOC*MAX_SIZES*16] in global order"""
-    return _gather_interleaved(cands_local, cands_local.shape[0], world, device, FSZ)
+    return _gather_interleaved(cands_local, cands_local.shape[0], world, device, FSZ, slot)
 
 
-def search_and_select(L, srch, info_all, comp_all, world, rank, max_dcis, max_grants, full_fetch=None):
+class WalkBuffers:
+    """output buffers of search_and_select, allocated once per pipeline"""
+
+    def __init__(self, max_dcis, max_grants):
+        self.dcis = np.zeros(max_dcis, capi.DCI_DTYPE)
+        self.grants = (capi.Grant * max_grants)()
+        self.gidx = np.zeros(max_grants, np.uint32)
+
+
+def need_full_tables(L, srch, comp_all, n):
+    """True iff the walk over these survivor forms would be refused (decided before anything is consumed; every rank
+    sees the same data and history, so every rank decides the same)."""
+    return L.ltephy_search_needs_full_table(srch.h, C.c_void_p(comp_all.data_ptr()), n) != 0
+
+
+def search_and_select(L, srch, info_all, comp_all, world, rank, max_dcis, max_grants, full_fetch=None, full=None, bufs=None):
     """walk over all subframes in global order; -> (dcis structured array, grants ctypes array, grant->dci index, n_grants).
-    full_fetch: callable returning the all-gathered FULL tables (collective: every rank calls it on the same condition)."""
+    full: all-gathered FULL tables when already fetched; else full_fetch: callable returning them on demand (collective:
+    every rank calls it on the same condition)."""
     capi._bind_search(L)
     n = len(info_all)
-    dcis = np.zeros(max_dcis, capi.DCI_DTYPE)
+    bufs = bufs or WalkBuffers(max_dcis, max_grants)
+    dcis, grants, gidx = bufs.dcis, bufs.grants, bufs.gidx
     nd = C.c_uint32(0)
+    if full is not None:
+        r = L.ltephy_search_batch_compact(srch.h, info_all, C.c_void_p(comp_all.data_ptr()), C.c_void_p(full.data_ptr()), n,
+                                          dcis.ctypes.data_as(C.c_void_p), max_dcis, C.byref(nd))
+        if r != 0:
+            raise RuntimeError("ltephy_search_batch_compact failed (%d)" % r)
+        return _select(L, srch, info_all, dcis, nd, world, rank, grants, gidx, max_grants)
     r = L.ltephy_search_batch_compact(srch.h, info_all, C.c_void_p(comp_all.data_ptr()), None, n, dcis.ctypes.data_as(C.c_void_p), max_dcis, C.byref(nd))
     if r == capi.NEED_FULL_TABLE:
         if full_fetch is None:
@@ -77,8 +101,10 @@ def search_and_select(L, srch, info_all, comp_all, world, rank, max_dcis, max_gr
                                           dcis.ctypes.data_as(C.c_void_p), max_dcis, C.byref(nd))
     if r != 0:
         raise RuntimeError("ltephy_search_batch_compact failed (%d)" % r)
-    grants = (capi.Grant * max_grants)()
-    gidx = np.zeros(max_grants, np.uint32)
+    return _select(L, srch, info_all, dcis, nd, world, rank, grants, gidx, max_grants)
+
+
+def _select(L, srch, info_all, dcis, nd, world, rank, grants, gidx, max_grants):
     ng = C.c_uint32(0)
     r = L.ltephy_grants_from_dcis(srch.h, info_all, dcis.ctypes.data_as(C.c_void_p), nd.value, world, rank, grants, gidx.ctypes.data_as(C.c_void_p),
                                   max_grants, C.byref(ng))

@@ -74,6 +74,7 @@ def _worker(rank, world, port, q):
     # second pass on a fresh history with a RAR-activated RNTI: the survivor form must be refused and the full tables gathered
     srch2 = capi.Search(*cell_args)
     L.ltephy_search_activate(srch2.h, RAR_RNTI, 0, 2)
+    assert not shard.need_full_tables(L, srch, comp_all, N_SF) and shard.need_full_tables(L, srch2, comp_all, N_SF)
     fetched = []
 
     def full_fetch():
