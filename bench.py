@@ -167,7 +167,7 @@ def run_reference(args):
            "dtype": "f32+int16", "data": "synthetic",
            "config": {"workload": WORKLOAD, "subframes_per_step": per_step},
            "cpu_baseline": {"value": v, "unit": "subframes/s", "cores": cores, "kind": "port",
-                            "sample": "%d subframes per step (CPU oracle port of the srsRAN chain + the reference's own RNTIManager; srsRAN itself is not buildable here)" % per_step},
+                            "sample": "%d subframes per step (scalar C port of the srsRAN chain, no SIMD, + the reference's own RNTIManager; srsRAN itself is not buildable here)" % per_step},
            "e2e": {"value": v, "unit": "subframes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     emit_json(out)
 
@@ -206,7 +206,7 @@ def main():
             iq_s = np.tile(iq_u, (reps2, 1, 1))[:ns]
             rate, dt = cpu_pipeline_rate(cell, iq_s, (np.arange(ns) % len(iq_u)).astype(np.uint32), cores)
             cpu_base = {"value": rate, "unit": "subframes/s", "cores": cores, "kind": "port",
-                        "sample": "%d subframes of the same capture in %.1f s, %d worker processes (CPU oracle port of the srsRAN chain + the reference's own RNTIManager)" % (ns, dt, cores)}
+                        "sample": "%d subframes of the same capture in %.1f s, %d worker processes (scalar C port of the srsRAN chain, no SIMD, + the reference's own RNTIManager; srsRAN's AVX decoders are roughly an order of magnitude faster per core)" % (ns, dt, cores)}
         except Exception as e:  # the baseline is a report, never a reason to lose the GPU number
             cpu_base = {"value": None, "unit": "subframes/s", "cores": cores, "kind": "port", "sample": "failed: %r" % (e,)}
         log("[rank 0] cpu_baseline: %r" % (cpu_base,))
@@ -464,7 +464,14 @@ def main():
     peak = float(peaks.get("hbm_gbs", 6650.0))
     t_turbo = float(np.mean(turbo_ms)) * 1e-3
     achieved = tbytes / t_turbo / 1e9 if t_turbo > 0 else 0.0
-    roofline = {"kernel": "turbo_kernel", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+    traffic = None   # dram__bytes_read + dram__bytes_write of the step's turbo launches, from the committed ncu --set full capture of this workload
+    try:
+        tt = json.load(open(os.path.join(ROOT, "profiles", "r1_kernel_traffic.json")))["turbo_kernel_step_total"]
+        if tt["subframes_per_step"] == B:
+            traffic = tt["traffic_bytes"]
+    except Exception:
+        pass
+    roofline = {"kernel": "turbo_kernel", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                 "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback 6.65 TB/s", "launch_ms": t_turbo * 1e3,
                 "algorithmic_bytes_per_launch": tbytes, "code_blocks": ncb, "turbo_info_mbit_s": info_bits / t_turbo / 1e6 if t_turbo > 0 else 0.0,
                 "note": "max-log-MAP is ALU/issue bound (~1e3 int ops per info bit); the HBM fraction is small by construction (SURVEY.md 8d)"}
