@@ -408,6 +408,15 @@ class Search:
         return r, g, f
 
 
+def ul_dci_to_grant(search, dci_row, enable_64qam=1):
+    """accepted format-0 DCI -> (return code, UlGrant) via ltephy_ul_dci_to_grant"""
+    d = DciOut(sf=int(dci_row["sf"]), rnti=int(dci_row["rnti"]), format=int(dci_row["format"]), L=int(dci_row["L"]), ncce=int(dci_row["ncce"]),
+               nof_bits=int(dci_row["nof_bits"]), bits=int(dci_row["bits"]), histogram_value=int(dci_row["histogram_value"]))
+    g = UlGrant()
+    r = search.L.ltephy_ul_dci_to_grant(search.h, C.byref(d), enable_64qam, C.byref(g))
+    return r, g
+
+
 def decode_subframes(phy, search, iq, tti, seq=SEQ_NONE, max_dcis=None, scratch=None):
     """One call through the reference-facing pipeline: host IQ -> (info, dcis, tb results, payload)."""
     L = phy.L

@@ -319,6 +319,7 @@ int lte_sim_subframe(lte_sim_t* s, uint32_t tti, cf_t* iq, lte_sim_truth_t* trut
     d->tb_en[1] = (kind == 3 || kind == 4);
     if (kind == 101 && d->mcs[0] > 28) d->mcs[0] = 28;
   }
+  uint32_t ul_next = 0;
   for (uint32_t i = 0; i < n_ul && njobs < LTE_SIM_MAX_DCI; i++) {
     job_t* j = &jobs[njobs++];
     memset(j, 0, sizeof(*j));
@@ -327,8 +328,18 @@ int lte_sim_subframe(lte_sim_t* s, uint32_t tti, cf_t* iq, lte_sim_truth_t* trut
     d->format     = LTE_DCI_FORMAT0;
     d->alloc_type = 2;
     uint32_t L = 1 + (uint32_t)(lte_rng_u64(&rng) % 8), S = (uint32_t)(lte_rng_u64(&rng) % (N - L));
+    if (cfg->ul_pusch) {
+      static const uint8_t okL[8] = {3, 4, 5, 6, 8, 9, 10, 12};
+      L = okL[lte_rng_u64(&rng) % 8];
+      S = ul_next;
+      if (S + L > N) {
+        njobs--;
+        break;
+      }
+      ul_next += L;
+    }
     d->riv        = N * (L - 1) + S;
-    d->mcs[0]     = (uint8_t)(10 + lte_rng_u64(&rng) % 15);
+    d->mcs[0]     = cfg->ul_pusch ? (uint8_t)(2 + lte_rng_u64(&rng) % 19) : (uint8_t)(10 + lte_rng_u64(&rng) % 15);
     d->ndi[0]     = (uint8_t)(lte_rng_u64(&rng) & 1);
     d->tpc        = 1;
     d->n_dmrs     = (uint8_t)(lte_rng_u64(&rng) % 8);

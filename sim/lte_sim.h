@@ -28,7 +28,8 @@ typedef struct {
   uint32_t   fixed_L;      /* 0xFF = random aggregation level, else 0..3 */
   uint32_t   full_band;    /* 1: partition all PRBs between the scheduled UEs */
   uint32_t   alt_table;    /* 1: C-RNTI grants use the 256QAM MCS table */
-  uint32_t   reserved[7];
+  uint32_t   ul_pusch;     /* 1: DCI-0 grants are decodable PUSCH allocations (L_prb in the DFT set, >= 3, back to back from PRB 0, MCS <= 20) */
+  uint32_t   reserved[6];
 } lte_sim_cfg_t;
 
 #define LTE_SIM_MAX_DCI 32

@@ -22,7 +22,7 @@ class SimCfg(C.Structure):
                 ("dl_min", C.c_uint32), ("dl_max", C.c_uint32), ("ul_min", C.c_uint32), ("ul_max", C.c_uint32),
                 ("tm", C.c_uint32), ("mcs_min", C.c_uint32), ("mcs_max", C.c_uint32), ("si_period", C.c_uint32),
                 ("snr_db", C.c_float), ("chan_delay", C.c_uint32), ("fixed_L", C.c_uint32), ("full_band", C.c_uint32),
-                ("alt_table", C.c_uint32), ("reserved", C.c_uint32 * 7)]
+                ("alt_table", C.c_uint32), ("ul_pusch", C.c_uint32), ("reserved", C.c_uint32 * 6)]
 
 
 class DciTruth(C.Structure):
@@ -157,7 +157,7 @@ class Sim:
         cfg = SimCfg()
         cfg.cell = cell
         d = dict(seed=1, cfi=2, nof_ues=1, dl_min=1, dl_max=1, ul_min=0, ul_max=0, tm=1, mcs_min=5, mcs_max=5, si_period=0,
-                 snr_db=30.0, chan_delay=0, fixed_L=0xFF, full_band=0, alt_table=0)
+                 snr_db=30.0, chan_delay=0, fixed_L=0xFF, full_band=0, alt_table=0, ul_pusch=0)
         d.update(kw)
         for k, v in d.items():
             setattr(cfg, k, v)

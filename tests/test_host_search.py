@@ -161,3 +161,39 @@ def test_dci_to_grant_matches_oracle(infra):
                 for prb in range(cell.nof_prb):
                     assert ((pg.prb_mask[sl][prb >> 5] >> (prb & 31)) & 1) == g.prb_mask[sl][prb]
     assert ncheck > 2000
+
+
+def test_ul_dci_to_grant_matches_oracle(infra):
+    """random format-0 DCIs: product ltephy_ul_dci_to_grant == oracle lte_dci_unpack + lte_ul_dci_to_grant, restricted to what
+    PUSCH_Decoder accepts (valid_prb_ul, src/src/UL_Sniffer_PUSCH.cc:3-10: L_prb = 2^a 3^b 5^c; the product also needs L_prb >= 3)"""
+    S = infra.sim()
+    S.lte_ul_dci_to_grant.argtypes = [C.POINTER(Cell), C.POINTER(ltelib.Dci), C.c_int, C.POINTER(ltelib.UlGrant)]
+    S.lte_ul_valid_prb.argtypes = [C.c_uint32]
+    rng = np.random.default_rng(8)
+    nok = 0
+    for cell in (Cell(100, 2, 3, 2), Cell(50, 1, 9, 1), Cell(25, 2, 100, 2), Cell(75, 2, 5, 2), Cell(15, 1, 2, 1)):
+        srch = capi.Search(cell.nof_prb, cell.nof_ports, cell.cell_id, cell.nof_rx)
+        nb = S.lte_dci_sizeof(C.byref(cell), 0)
+        for it in range(2500):
+            bits = rng.integers(0, 2, nb).astype(np.uint8)
+            bits[0] = 0
+            if it % 4:
+                bits[1] = 0                                  # mostly non-hopping
+            rnti, q64 = int(rng.integers(11, 0xFFF3)), int(rng.integers(0, 2))
+            d, g0 = ltelib.Dci(), ltelib.UlGrant()
+            r0 = S.lte_dci_unpack(C.byref(cell), 0, rnti, ltelib.ptr(bits), nb, C.byref(d))
+            if r0 == 0:
+                r0 = S.lte_ul_dci_to_grant(C.byref(cell), C.byref(d), q64, C.byref(g0))
+            expect = r0 == 0 and g0.L_prb >= 3 and bool(S.lte_ul_valid_prb(g0.L_prb))
+            v = 0
+            for i, b in enumerate(bits):
+                v |= int(b) << (63 - i)
+            row = np.zeros(1, capi.DCI_DTYPE)[0]
+            row["sf"], row["rnti"], row["format"], row["nof_bits"], row["bits"] = 7, rnti, 0, nb, v
+            r1, g1 = capi.ul_dci_to_grant(srch, row, q64)
+            assert (r1 == 0) == expect, (cell.nof_prb, it, r0, r1, g0.L_prb, g0.n_prb)
+            if r1 == 0:
+                assert (g1.sf, g1.rnti, g1.qm, g1.rv, g1.L_prb, g1.n_prb, g1.n_dmrs2, g1.tbs) == \
+                       (7, rnti, g0.qm, g0.rv, g0.L_prb, g0.n_prb, g0.n_dmrs2, g0.tbs)
+                nok += 1
+    assert nok > 500
