@@ -61,3 +61,34 @@ def test_decode_subframes_matches_oracle_pipeline(infra, phylib, name, cell, n, 
                 hits += 1
     assert hits >= 1 and ntb_ok >= 1
     phy.close()
+
+
+def test_decode_subframes_falls_back_to_full_table_for_rar_rntis(infra, phylib):
+    """A RAR-activated RNTI makes the walk look at every format-0 candidate (temp_dci0, DCISearch.cc:150-161), which the
+    survivor form cannot serve: ltephy_decode_subframes must fetch the full table and give what a walk over the full table gives."""
+    import ctypes as C
+    cell = Cell(50, 2, 301, 2)
+    n = 24
+    sim, iq, tti, truths, payloads = make_capture(cell, n, seed=9, cfi=3, nof_ues=5, dl_min=2, dl_max=3, ul_min=1, ul_max=2, tm=13, mcs_min=2, mcs_max=14, snr_db=26.0)
+    rar = int(sim.rntis()[0])
+    L = capi.load_library()
+    capi._bind_search(L)
+    out = []
+    for mode in ("pipeline", "full_table_walk", "no_rar"):
+        phy = capi.LtePhy(cell.nof_prb, cell.nof_ports, cell.cell_id, cell.nof_rx, max_subframes=n, turbo_max_iter=8, flags=capi.FLAG_SKIP_LOW_POWER)
+        srch = capi.Search(cell.nof_prb, cell.nof_ports, cell.cell_id, cell.nof_rx)
+        if mode != "no_rar":
+            L.ltephy_search_activate(srch.h, rar, 0, 2)      # ActivationReason RAR
+        if mode == "full_table_walk":
+            phy.submit_iq(iq, tti)
+            info, cands = phy.get_phase_a()
+            dcis = np.zeros(64 * n, capi.DCI_DTYPE)
+            nd = C.c_uint32(0)
+            assert L.ltephy_search_batch(srch.h, info, cands.ctypes.data_as(C.c_void_p), n, dcis.ctypes.data_as(C.c_void_p), len(dcis), C.byref(nd)) == 0
+            dcis = dcis[:nd.value]
+        else:
+            info, dcis, tbs, payload = capi.decode_subframes(phy, srch, iq, tti)
+        out.append([tuple(int(d[k]) for k in ("sf", "rnti", "format", "L", "ncce", "nof_bits", "bits", "histogram_value")) for d in dcis])
+        phy.close()
+    assert out[0] == out[1] and len(out[0]) > n
+    assert out[0] != out[2], "the RAR activation should change what the walk reports (otherwise this test exercises nothing)"
