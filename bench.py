@@ -453,6 +453,10 @@ def main():
     if world > 1:
         dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
     e2e_ms = float(t_e2e.item())
+    e2e_pa = float(np.mean([ph.timing()[0] for ph in phys]))   # H2D copy + phase A of the last e2e batch of each pipeline (CUDA events)
+    e2e_pb = float(np.mean([ph.timing()[1] for ph in phys]))
+    hm2 = np.zeros(8)
+    L.ltephy_last_host_timing(hm2.ctypes.data_as(C.c_void_p))
     d2h = B * (C.sizeof(capi.SfInfo) + capi.COMPACT_DTYPE.itemsize) + int(info_bits // 8) + 12 * 2 * 24 * B // 8
 
     # ---------------- roofline of the dominant kernel (turbo decoder) ----------------
@@ -489,7 +493,9 @@ def main():
                "wall_ms_per_step": wall_ms / args.steps, "phase_a_ms": float(np.mean(phase_a_ms)), "phase_b_ms": float(np.mean(phase_b_ms)),
                "host_ms": dict(zip(["submit_a", "wait_a", "search", "grants", "submit_b", "wait_b"], [round(float(x), 3) for x in host_ms[:6]])),
                "e2e": {"value": B * world * args.steps / (e2e_ms * 1e-3), "unit": "subframes/s",
-                       "h2d_bytes_per_step": int(iq_pin.numel() * 4 + B * 4), "d2h_bytes_per_step": int(d2h)},
+                       "h2d_bytes_per_step": int(iq_pin.numel() * 4 + B * 4), "d2h_bytes_per_step": int(d2h),
+                       "ms_per_step": e2e_ms / args.steps, "h2d_plus_phase_a_ms": e2e_pa, "phase_b_ms": e2e_pb,
+                       "host_ms": dict(zip(["submit_a", "wait_a", "search", "grants", "submit_b", "wait_b"], [round(float(x), 3) for x in hm2[:6]]))},
                "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline}
 
     if rank == 0 and cpu_base is not None:
