@@ -2,7 +2,7 @@
 # ltesniffer_b200/build.py / __graft_entry__.build().
 CC ?= gcc
 CXX ?= g++
-CFLAGS = -O2 -g -fPIC -std=gnu11 -Wall -Wno-unused-function -ffp-contract=off -fno-fast-math
+CFLAGS = -O3 -g -fPIC -std=gnu11 -Wall -Wno-unused-function -ffp-contract=off -fno-fast-math
 CXXFLAGS = -O2 -g -fPIC -std=c++17 -Wall -ffp-contract=off -fno-fast-math
 
 all: sim/libltesim.so oracle/liblteoracle.so

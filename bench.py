@@ -34,6 +34,25 @@ SIM_KW = dict(seed=2, cfi=3, nof_ues=150, dl_min=8, dl_max=12, tm=3, mcs_min=17,
 WORKLOAD = "cfg2: offline DL 20 MHz FDD, 150 RNTIs, TM3 2x2 64QAM, CFI 3, 8-12 DCI/sf, 100 PRB full band"
 
 
+def effective_cores():
+    """CPUs this process may actually use: affinity mask, capped by the cgroup CPU quota (a container often sees every core of the
+    host in os.cpu_count() but is throttled to a few)"""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        q, p = open("/sys/fs/cgroup/cpu.max").read().split()[:2]
+        if q != "max":
+            n = min(n, max(1, int(-(-int(q) // int(p)))))
+    except Exception:
+        try:
+            q = int(open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us").read())
+            p = int(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+            if q > 0:
+                n = min(n, max(1, -(-q // p)))
+        except Exception:
+            pass
+    return max(1, n)
+
+
 def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
@@ -150,7 +169,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    cores = os.cpu_count() or 1
+    cores = effective_cores()
     per_step = max(4 * cores, int(args.ref_subframes))
     cell, iq = generate_capture(min(per_step, 64), min(cores, 8))
     reps = (per_step + len(iq) - 1) // len(iq)
@@ -193,7 +212,7 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
-    cores = os.cpu_count() or 1
+    cores = effective_cores()
     B = args.batch
     t0 = time.time()
     cell, iq_u = generate_capture(min(args.unique, B), min(cores, 16))
