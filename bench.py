@@ -139,21 +139,24 @@ _CPU_JOB = {}
 def _cpu_chunk(b):
     import ltelib
     cell = ltelib.Cell(CELL["nof_prb"], CELL["nof_ports"], CELL["cell_id"], CELL["nof_rx"])
-    iq, tti = _CPU_JOB["iq"], _CPU_JOB["tti"]
+    iq, idx = _CPU_JOB["iq"], _CPU_JOB["idx"]
     if b[1] > b[0]:
-        ltelib.oracle_pipeline(cell, iq[b[0]:b[1]], tti[b[0]:b[1]])
+        walk = ltelib.OracleWalk(cell)              # one RNTI history per worker, kept across its whole chunk
+        for lo in range(b[0], b[1], 8):
+            sel = idx[lo:min(lo + 8, b[1])]
+            ltelib.oracle_pipeline(cell, iq[sel], sel.astype(np.uint32), walk=walk)
     return b[1] - b[0]
 
 
-def cpu_pipeline_rate(cell, iq, tti, workers):
-    """CPU oracle pipeline (phase A, FALCON walk on the reference's RNTIManager, PDSCH decode) over the given
-    subframes: `workers` PROCESSES (fork, so the capture is shared copy-on-write) on disjoint contiguous chunks,
-    each with its own RNTI history -- the SubframeWorker-style pool of src/src/Phy.cc:29-54.  -> (sf/s, seconds)"""
+def cpu_pipeline_rate(cell, iq, idx, workers):
+    """CPU oracle pipeline (phase A, FALCON walk on the reference's RNTIManager, PDSCH decode) over the subframes iq[idx[i]]
+    (tti = idx[i]): `workers` PROCESSES (fork, so the capture is shared copy-on-write) on disjoint contiguous chunks, each with its
+    own RNTI history -- the SubframeWorker-style pool of src/src/Phy.cc:29-54.  -> (sf/s, seconds)"""
     import multiprocessing as mp
     import ltelib
     ltelib.walklib()          # build / load before forking
-    n = len(tti)
-    _CPU_JOB["iq"], _CPU_JOB["tti"] = iq, tti
+    n = len(idx)
+    _CPU_JOB["iq"], _CPU_JOB["idx"] = iq, np.asarray(idx)
     bounds = [(n * t // workers, n * (t + 1) // workers) for t in range(workers)]
     ctx = mp.get_context("fork")
     with ctx.Pool(workers) as pool:
@@ -170,16 +173,14 @@ def run_reference(args):
     if rank != 0:
         return
     cores = effective_cores()
-    per_step = max(4 * cores, int(args.ref_subframes))
-    cell, iq = generate_capture(min(per_step, 64), min(cores, 8))
-    reps = (per_step + len(iq) - 1) // len(iq)
-    iqb = np.tile(iq, (reps, 1, 1))[:per_step]
-    ttib = (np.arange(per_step) % len(iq)).astype(np.uint32)
+    per_step = int(args.ref_subframes) or 40 * cores
+    cell, iq = generate_capture(64, min(cores, 8))
+    idx = np.arange(per_step) % len(iq)
     for _ in range(args.warmup):
-        cpu_pipeline_rate(cell, iqb[:cores], ttib[:cores], cores)
+        cpu_pipeline_rate(cell, iq, idx[:2 * cores], cores)
     dt = 0.0
     for _ in range(args.steps):
-        dt += cpu_pipeline_rate(cell, iqb, ttib, cores)[1]
+        dt += cpu_pipeline_rate(cell, iq, idx, cores)[1]
     v = per_step * args.steps / dt
     out = {"impl": "reference", "metric": "subframes/s", "value": v, "unit": "subframes/s", "n_gpus": args.gpus, "steps": args.steps,
            "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -200,8 +201,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=1000, help="subframes per step per GPU")
     ap.add_argument("--unique", type=int, default=100, help="distinct synthetic subframes (tiled to the batch; every step still moves/decodes the full batch)")
-    ap.add_argument("--ref-subframes", type=int, default=96, help="subframes per step for --impl reference")
-    ap.add_argument("--cpu-sample", type=int, default=0, help="subframes for the cpu_baseline leg (0 = 40 per core)")
+    ap.add_argument("--ref-subframes", type=int, default=0, help="subframes per step for --impl reference (0 = 40 per usable core)")
+    ap.add_argument("--cpu-sample", type=int, default=0, help="subframes for the cpu_baseline leg (0 = 400 per usable core, about 10 s)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--pipelines", type=int, default=3, help="PHY handles driven concurrently (host search of batch k overlaps GPU work of batch k+1)")
     args = ap.parse_args()
@@ -220,10 +221,8 @@ def main():
     cpu_base = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:   # before CUDA is touched: the workers are forked
         try:
-            ns = args.cpu_sample or 12 * cores
-            reps2 = (ns + len(iq_u) - 1) // len(iq_u)
-            iq_s = np.tile(iq_u, (reps2, 1, 1))[:ns]
-            rate, dt = cpu_pipeline_rate(cell, iq_s, (np.arange(ns) % len(iq_u)).astype(np.uint32), cores)
+            ns = args.cpu_sample or 400 * cores
+            rate, dt = cpu_pipeline_rate(cell, iq_u, np.arange(ns) % len(iq_u), cores)
             cpu_base = {"value": rate, "unit": "subframes/s", "cores": cores, "kind": "port",
                         "sample": "%d subframes of the same capture in %.1f s, %d worker processes (scalar C port of the srsRAN chain, no SIMD, + the reference's own RNTIManager; srsRAN's AVX decoders are roughly an order of magnitude faster per core)" % (ns, dt, cores)}
         except Exception as e:  # the baseline is a report, never a reason to lose the GPU number
