@@ -364,13 +364,13 @@ def main():
                 for k in range(t, nsteps, T):
                     sh_submit_a(t, device_resident)
                     S = scr[t]
-                    phys[t]._chk(L.ltephy_get_phase_a_compact(phys[t].h, S.info, p(S.comp)), "get_phase_a_compact")
+                    phys[t]._chk(L.ltephy_get_phase_a(phys[t].h, S.info, None), "get_phase_a")   # waits for phase A; the handle keeps cfi/tti
                     if not take(0, k):
                         return
                     if pend[t]:
                         sh_gather_tbs(t)
                         pend[t] = False
-                    info_all, comp_all = shard.gather_tables(S.info, S.comp, world, "cuda", slot=t)
+                    info_all, comp_all = shard.gather_tables_device(L, phys[t].h, B, world, cell.nof_ports, cell.nof_rx, slot=t)
                     full = None
                     if shard.need_full_tables(L, srch, comp_all, B * world):   # never on this workload
                         phys[t]._chk(L.ltephy_get_phase_a(phys[t].h, None, p(S.cands)), "get_phase_a")

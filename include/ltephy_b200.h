@@ -171,6 +171,13 @@ int ltephy_get_phase_a(ltephy_t* h, ltephy_sf_info_t* info, ltephy_cand_t* cands
 int ltephy_get_phase_a_compact(ltephy_t* h, ltephy_sf_info_t* info, ltephy_compact_t* comp);
 /* comp may be NULL above: the survivor forms then stay in the handle's pinned buffer, valid until the next submit_iq */
 const ltephy_compact_t* ltephy_phase_a_compact_buffer(const ltephy_t* h);
+/* sharded operation: device-to-device copies of the raw per-subframe records (ltephy_sf_info_t before the host-side
+ * snr_db / cfo step) and of the survivor forms of the current batch into caller-owned device buffers, for an all-gather
+ * without a host round trip; either pointer may be NULL.  Blocks until the copies are done. */
+int ltephy_copy_phase_a_device(ltephy_t* h, void* dst_info_dev, void* dst_compact_dev);
+/* host: fills noise_avg / rsrp_avg / snr_db / cfo of raw records from their per-path sums (what ltephy_get_phase_a does
+ * before it returns; idempotent) */
+void ltephy_finalize_info(ltephy_sf_info_t* info, uint32_t n, uint32_t nof_ports, uint32_t nof_rx);
 
 /* ---- phase B ------------------------------------------------------------------------------ */
 int ltephy_submit_grants(ltephy_t* h, const ltephy_grant_t* grants, uint32_t n);

@@ -98,6 +98,9 @@ def load_library(build_if_missing=True):
     L.ltephy_get_phase_a_compact.argtypes = [P, P, P]
     L.ltephy_phase_a_compact_buffer.argtypes = [P]
     L.ltephy_phase_a_compact_buffer.restype = P
+    L.ltephy_copy_phase_a_device.argtypes = [P, P, P]
+    L.ltephy_finalize_info.argtypes = [P, C.c_uint32, C.c_uint32, C.c_uint32]
+    L.ltephy_finalize_info.restype = None
     L.ltephy_submit_grants.argtypes = [P, P, C.c_uint32]
     L.ltephy_get_phase_b.argtypes = [P, P, P, C.c_size_t]
     L.ltephy_copy_phase_b_device.argtypes = [P, P, C.c_size_t, P]

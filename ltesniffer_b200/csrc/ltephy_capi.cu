@@ -450,6 +450,36 @@ extern "C" int ltephy_submit_iq_device(ltephy_t* h, const void* iq_dev, const ui
   CU(cudaEventRecord(h->ev[0], h->stream));
   return phase_a_common(h, reinterpret_cast<const float2*>(iq_dev), tti, n); // read in place: the caller keeps the buffer alive until phase A is fetched
 }
+// log10f / atan2f of the bit-exact device sums are taken on the host; idempotent
+extern "C" void ltephy_finalize_info(ltephy_sf_info_t* info, uint32_t n, uint32_t nof_ports, uint32_t nof_rx)
+{
+  const float npa = (float)(nof_ports * nof_rx);
+  for (uint32_t i = 0; i < n; i++) {
+    DevSfInfo& s  = reinterpret_cast<DevSfInfo*>(info)[i];
+    float      ns = 0.0f, ps = 0.0f;
+    for (uint32_t p = 0; p < nof_ports; p++)
+      for (uint32_t a = 0; a < nof_rx; a++) {
+        ns = ns + s.noise[p][a];
+        ps = ps + s.rsrp[p][a];
+      }
+    s.noise_avg = ns / npa;
+    s.rsrp_avg  = ps / npa;
+    s.snr_db    = 10.0f * log10f(s.rsrp_avg / s.noise_avg);
+    s.cfo       = atan2f(s.cfo_im, s.cfo_re) / (2.0f * (float)M_PI * 7.5f);
+  }
+}
+// Device-to-device copies of the raw per-subframe records and the survivor forms of the current batch, for an all-gather
+// without a host round trip (a host->device DMA would queue behind the other pipelines' IQ copies).  Blocks until done.
+extern "C" int ltephy_copy_phase_a_device(ltephy_t* h, void* dst_info_dev, void* dst_compact_dev)
+{
+  if (!h || !h->n_cur) return fail(LTEPHY_ERROR_INVALID_INPUTS, "copy_phase_a_device: nothing submitted");
+  CU(cudaSetDevice(h->cfg.device));
+  const uint32_t n = h->n_cur;
+  if (dst_info_dev) CU(cudaMemcpyAsync(dst_info_dev, h->d_info.p, (size_t)n * sizeof(DevSfInfo), cudaMemcpyDeviceToDevice, h->stream));
+  if (dst_compact_dev) CU(cudaMemcpyAsync(dst_compact_dev, h->d_compact.p, (size_t)n * sizeof(ltephy_compact_t), cudaMemcpyDeviceToDevice, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  return LTEPHY_SUCCESS;
+}
 static int fetch_phase_a(ltephy_t* h, ltephy_sf_info_t* info, ltephy_cand_t* cands, bool compact, ltephy_compact_t* comp)
 {
   if (!h || !h->n_cur) return fail(LTEPHY_ERROR_INVALID_INPUTS, "get_phase_a: nothing submitted");
@@ -461,21 +491,8 @@ static int fetch_phase_a(ltephy_t* h, ltephy_sf_info_t* info, ltephy_cand_t* can
   if (compact) CU(cudaMemcpyAsync(comp ? comp : h->h_compact.p, h->d_compact.p, (size_t)n * sizeof(ltephy_compact_t), cudaMemcpyDeviceToHost, h->stream));
   CU(cudaStreamSynchronize(h->stream));
   cudaEventElapsedTime(&h->t_ms[0], h->ev[0], h->ev[1]);
-  const float npa = (float)(h->dc.nof_ports * h->dc.nof_rx);
-  for (uint32_t i = 0; i < n; i++) {
-    DevSfInfo& s  = h->h_info.p[i];
-    float      ns = 0.0f, ps = 0.0f;
-    for (uint32_t p = 0; p < h->dc.nof_ports; p++)
-      for (uint32_t a = 0; a < h->dc.nof_rx; a++) {
-        ns = ns + s.noise[p][a];
-        ps = ps + s.rsrp[p][a];
-      }
-    s.noise_avg = ns / npa;
-    s.rsrp_avg  = ps / npa;
-    s.snr_db    = 10.0f * log10f(s.rsrp_avg / s.noise_avg);
-    s.cfo       = atan2f(s.cfo_im, s.cfo_re) / (2.0f * (float)M_PI * 7.5f);
-    if (info) memcpy(&info[i], &s, sizeof(s));
-  }
+  ltephy_finalize_info(reinterpret_cast<ltephy_sf_info_t*>(h->h_info.p), n, h->dc.nof_ports, h->dc.nof_rx);
+  if (info) memcpy(info, h->h_info.p, (size_t)n * sizeof(DevSfInfo));
   return LTEPHY_SUCCESS;
 }
 extern "C" int ltephy_get_phase_a(ltephy_t* h, ltephy_sf_info_t* info, ltephy_cand_t* cands) { return fetch_phase_a(h, info, cands, false, nullptr); }

@@ -28,10 +28,12 @@ def _buffers(B, world, device, esz, slot=0):
 
 
 def _gather_interleaved(local_u8, B, world, device, esz, slot=0):
-    """local_u8: uint8 host tensor [B*esz] -> host tensor [B*world, esz] in global order g = i*world + r.
-    The result lives in a staging buffer owned by `slot` and is overwritten by the next call with the same slot."""
+    """local_u8: uint8 tensor [B*esz] (host, or already on `device`) -> host tensor [B*world, esz] in global order
+    g = i*world + r.  The result lives in a staging buffer owned by `slot` and is overwritten by its next call."""
     st = _buffers(B, world, device, esz, slot)
-    loc = local_u8.reshape(-1).to(device, non_blocking=True)
+    loc = local_u8.reshape(-1)
+    if loc.is_cuda != (torch.device(device).type == "cuda"):
+        loc = loc.to(device, non_blocking=True)
     dist.all_gather_into_tensor(st["g"].view(-1), loc)
     st["o"].copy_(st["g"].transpose(0, 1))            # [world][B] -> [B][world]
     st["h"].copy_(st["o"].view(B * world, esz), non_blocking=True)
@@ -54,6 +56,30 @@ def gather_tables(info_local, comp_local, world, device, slot=0):
         _info_all[(B, world, slot)] = (capi.SfInfo * (B * world))()
     info_all = _info_all[(B, world, slot)]
     C.memmove(info_all, hi.data_ptr(), hi.numel())
+    return info_all, hc
+
+
+_dev_local = {}
+
+
+def gather_tables_device(L, phy_handle, B, world, nof_ports, nof_rx, slot=0):
+    """CUDA path: the handle's raw per-subframe records and survivor forms go device -> device -> NCCL all-gather -> host,
+    with no host->device copy (which would queue behind the IQ transfers of the other pipelines).  Same result as
+    gather_tables(); the records are finalised (snr_db, cfo) on the host after the exchange."""
+    key = (B, slot)
+    if key not in _dev_local:
+        _dev_local[key] = (torch.empty(B * ISZ, dtype=torch.uint8, device="cuda"), torch.empty(B * CSZ, dtype=torch.uint8, device="cuda"))
+    di, dc = _dev_local[key]
+    r = L.ltephy_copy_phase_a_device(phy_handle, C.c_void_p(di.data_ptr()), C.c_void_p(dc.data_ptr()))
+    if r != 0:
+        raise RuntimeError("ltephy_copy_phase_a_device failed (%d)" % r)
+    hi = _gather_interleaved(di, B, world, "cuda", ISZ, slot)
+    hc = _gather_interleaved(dc, B, world, "cuda", CSZ, slot)
+    if (B, world, slot) not in _info_all:
+        _info_all[(B, world, slot)] = (capi.SfInfo * (B * world))()
+    info_all = _info_all[(B, world, slot)]
+    C.memmove(info_all, hi.data_ptr(), hi.numel())
+    L.ltephy_finalize_info(info_all, B * world, nof_ports, nof_rx)
     return info_all, hc
 
 

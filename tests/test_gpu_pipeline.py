@@ -92,3 +92,31 @@ def test_decode_subframes_falls_back_to_full_table_for_rar_rntis(infra, phylib):
         phy.close()
     assert out[0] == out[1] and len(out[0]) > n
     assert out[0] != out[2], "the RAR activation should change what the walk reports (otherwise this test exercises nothing)"
+
+
+def test_device_side_exchange_equals_host_fetch(infra, phylib):
+    """shard.gather_tables_device (device -> NCCL all-gather -> host, records finalised after the exchange) must hand the walk
+    exactly what ltephy_get_phase_a_compact hands it (world size 1 here; the interleaving is covered by the gloo test)."""
+    import os
+    import torch
+    import torch.distributed as dist
+    from ltesniffer_b200 import shard
+    cell = Cell(50, 2, 301, 2)
+    n = 6
+    sim, iq, tti, truths, payloads = make_capture(cell, n, seed=4, cfi=3, nof_ues=5, dl_min=2, dl_max=3, tm=13, mcs_min=2, mcs_max=14, snr_db=26.0)
+    phy = capi.LtePhy(cell.nof_prb, cell.nof_ports, cell.cell_id, cell.nof_rx, max_subframes=n, flags=capi.FLAG_SKIP_LOW_POWER)
+    phy.submit_iq(iq, tti)
+    info, comp = phy.get_phase_a_compact()
+    torch.cuda.set_device(0)
+    dist.init_process_group("nccl", init_method="tcp://127.0.0.1:%d" % (29600 + os.getpid() % 300), rank=0, world_size=1)
+    try:
+        info_all, comp_all = shard.gather_tables_device(phy.L, phy.h, n, 1, cell.nof_ports, cell.nof_rx)
+        assert bytes(info_all) == bytes(info)
+        got = comp_all.numpy().view(capi.COMPACT_DTYPE).reshape(n)
+        for i in range(n):
+            k = int(comp[i]["count"])
+            assert int(got[i]["count"]) == k and got[i]["loc"].tobytes() == comp[i]["loc"].tobytes()
+            assert got[i]["list"][:k].tobytes() == comp[i]["list"][:k].tobytes()
+    finally:
+        dist.destroy_process_group()
+    phy.close()
