@@ -204,7 +204,7 @@ def main():
     ap.add_argument("--ref-subframes", type=int, default=0, help="subframes per step for --impl reference (0 = 40 per usable core)")
     ap.add_argument("--cpu-sample", type=int, default=0, help="subframes for the cpu_baseline leg (0 = 400 per usable core, about 10 s)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--pipelines", type=int, default=3, help="PHY handles driven concurrently (host search of batch k overlaps GPU work of batch k+1)")
+    ap.add_argument("--pipelines", type=int, default=4, help="PHY handles driven concurrently (host search of batch k overlaps GPU work of batch k+1)")
     args = ap.parse_args()
     claim_stdout()
     if args.impl == "reference":
@@ -475,6 +475,7 @@ def main():
     e2e_pb = float(np.mean([ph.timing()[1] for ph in phys]))
     hm2 = np.zeros(8)
     L.ltephy_last_host_timing(hm2.ctypes.data_as(C.c_void_p))
+    e2e_tb_ok = int(np.frombuffer(tbs, dtype=TB_DTYPE, count=2 * nd.value)["crc"].sum()) if world == 1 else None   # same count as the device-resident run
     d2h = B * (C.sizeof(capi.SfInfo) + capi.COMPACT_DTYPE.itemsize) + int(info_bits // 8) + 12 * 2 * 24 * B // 8
 
     # ---------------- roofline of the dominant kernel (turbo decoder) ----------------
@@ -512,7 +513,7 @@ def main():
                "host_ms": dict(zip(["submit_a", "wait_a", "search", "grants", "submit_b", "wait_b"], [round(float(x), 3) for x in host_ms[:6]])),
                "e2e": {"value": B * world * args.steps / (e2e_ms * 1e-3), "unit": "subframes/s",
                        "h2d_bytes_per_step": int(iq_pin.numel() * 4 + B * 4), "d2h_bytes_per_step": int(d2h),
-                       "ms_per_step": e2e_ms / args.steps, "h2d_plus_phase_a_ms": e2e_pa, "phase_b_ms": e2e_pb,
+                       "ms_per_step": e2e_ms / args.steps, "tb_crc_ok": e2e_tb_ok, "h2d_plus_phase_a_ms": e2e_pa, "phase_b_ms": e2e_pb,
                        "host_ms": dict(zip(["submit_a", "wait_a", "search", "grants", "submit_b", "wait_b"], [round(float(x), 3) for x in hm2[:6]]))},
                "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline}
 

@@ -420,16 +420,29 @@ extern "C" int      ltephy_last_timing(ltephy_t* h, float ms[4])
 }
 
 // ---------------------------------------------------------------------------------------- phase A
-static int phase_a_common(ltephy* h, const float2* iq_dev, const uint32_t* tti, uint32_t n)
+// Phase A over n subframes.  iq_host != nullptr: the samples are still in (pinned) host memory; they are copied in a few
+// chunks, each followed by its own kernels, so that the front end of chunk c runs under the transfer of chunk c+1 (the first
+// kernels start after a quarter of the 0.5 GB copy instead of after all of it).
+static int phase_a_common(ltephy* h, const float2* iq_dev, const float2* iq_host, const uint32_t* tti, uint32_t n)
 {
   for (uint32_t i = 0; i < n; i++) {
     memset(&h->h_info.p[i], 0, sizeof(DevSfInfo));
     h->h_info.p[i].tti = tti[i];
   }
   pull(h, h->d_info.p, h->h_info.p, n * sizeof(DevSfInfo));
-  launch_frontend(h->dc, iq_dev, h->d_sym.p, h->d_ce.p, h->d_llr.p, h->d_info.p, n, h->stream, &h->launches);
-  launch_viterbi(h->dc, h->d_llr.p, h->d_info.p, h->d_cands.p, n, h->stream, &h->launches);
-  launch_compact(h->dc, h->d_info.p, h->d_cands.p, h->d_compact.p, n, h->stream, &h->launches);
+  const DevCell& c      = h->dc;
+  const size_t   g      = (size_t)14 * c.nsc, iq_sf = (size_t)c.nof_rx * c.sf_len;
+  const uint32_t chunks = (iq_host && n >= 256) ? 4 : 1;
+  for (uint32_t k = 0; k < chunks; k++) {
+    const uint32_t s0 = (uint32_t)((uint64_t)n * k / chunks), s1 = (uint32_t)((uint64_t)n * (k + 1) / chunks), m = s1 - s0;
+    if (!m) continue;
+    if (iq_host) CU(cudaMemcpyAsync(h->d_iq.p + s0 * iq_sf, iq_host + s0 * iq_sf, m * iq_sf * sizeof(float2), cudaMemcpyHostToDevice, h->stream));
+    launch_frontend(c, iq_dev + s0 * iq_sf, h->d_sym.p + s0 * c.nof_rx * g, h->d_ce.p + s0 * c.nof_ports * c.nof_rx * g, h->d_llr.p + (size_t)s0 * LLR_STRIDE,
+                    h->d_info.p + s0, m, h->stream, &h->launches);
+    launch_viterbi(c, h->d_llr.p + (size_t)s0 * LLR_STRIDE, h->d_info.p + s0, h->d_cands.p + (size_t)s0 * LTEPHY_MAX_LOC * LTEPHY_MAX_SIZES, m, h->stream,
+                   &h->launches);
+    launch_compact(c, h->d_info.p + s0, h->d_cands.p + (size_t)s0 * LTEPHY_MAX_LOC * LTEPHY_MAX_SIZES, h->d_compact.p + s0, m, h->stream, &h->launches);
+  }
   CU(cudaEventRecord(h->ev[1], h->stream));
   CU(cudaGetLastError());
   h->n_cur = n;
@@ -440,15 +453,14 @@ extern "C" int ltephy_submit_iq(ltephy_t* h, const float* iq, const uint32_t* tt
   if (!h || !iq || !tti || n == 0 || n > h->cfg.max_subframes) return fail(LTEPHY_ERROR_INVALID_INPUTS, "submit_iq: bad arguments");
   CU(cudaSetDevice(h->cfg.device));
   CU(cudaEventRecord(h->ev[0], h->stream));
-  CU(cudaMemcpyAsync(h->d_iq.p, iq, (size_t)n * h->dc.nof_rx * h->dc.sf_len * sizeof(float2), cudaMemcpyHostToDevice, h->stream));
-  return phase_a_common(h, h->d_iq.p, tti, n);
+  return phase_a_common(h, h->d_iq.p, reinterpret_cast<const float2*>(iq), tti, n);
 }
 extern "C" int ltephy_submit_iq_device(ltephy_t* h, const void* iq_dev, const uint32_t* tti, uint32_t n)
 {
   if (!h || !iq_dev || !tti || n == 0 || n > h->cfg.max_subframes) return fail(LTEPHY_ERROR_INVALID_INPUTS, "submit_iq_device: bad arguments");
   CU(cudaSetDevice(h->cfg.device));
   CU(cudaEventRecord(h->ev[0], h->stream));
-  return phase_a_common(h, reinterpret_cast<const float2*>(iq_dev), tti, n); // read in place: the caller keeps the buffer alive until phase A is fetched
+  return phase_a_common(h, reinterpret_cast<const float2*>(iq_dev), nullptr, tti, n); // read in place: the caller keeps the buffer alive until phase A is fetched
 }
 // log10f / atan2f of the bit-exact device sums are taken on the host; idempotent
 extern "C" void ltephy_finalize_info(ltephy_sf_info_t* info, uint32_t n, uint32_t nof_ports, uint32_t nof_rx)
