@@ -420,9 +420,9 @@ extern "C" int      ltephy_last_timing(ltephy_t* h, float ms[4])
 }
 
 // ---------------------------------------------------------------------------------------- phase A
-// Phase A over n subframes.  iq_host != nullptr: the samples are still in (pinned) host memory; they are copied in a few
-// chunks, each followed by its own kernels, so that the front end of chunk c runs under the transfer of chunk c+1 (the first
-// kernels start after a quarter of the 0.5 GB copy instead of after all of it).
+// Phase A over n subframes.  iq_host != nullptr: the samples are still in (pinned) host memory and are copied first, as ONE
+// transfer: splitting it into chunks with per-chunk kernels was measured and is slower with several pipelines (the chunks of
+// different batches interleave on the copy engine, so every batch's front end finishes later: e2e 87-91 k -> 82 k subframes/s).
 static int phase_a_common(ltephy* h, const float2* iq_dev, const float2* iq_host, const uint32_t* tti, uint32_t n)
 {
   for (uint32_t i = 0; i < n; i++) {
@@ -430,19 +430,11 @@ static int phase_a_common(ltephy* h, const float2* iq_dev, const float2* iq_host
     h->h_info.p[i].tti = tti[i];
   }
   pull(h, h->d_info.p, h->h_info.p, n * sizeof(DevSfInfo));
-  const DevCell& c      = h->dc;
-  const size_t   g      = (size_t)14 * c.nsc, iq_sf = (size_t)c.nof_rx * c.sf_len;
-  const uint32_t chunks = (iq_host && n >= 256) ? 4 : 1;
-  for (uint32_t k = 0; k < chunks; k++) {
-    const uint32_t s0 = (uint32_t)((uint64_t)n * k / chunks), s1 = (uint32_t)((uint64_t)n * (k + 1) / chunks), m = s1 - s0;
-    if (!m) continue;
-    if (iq_host) CU(cudaMemcpyAsync(h->d_iq.p + s0 * iq_sf, iq_host + s0 * iq_sf, m * iq_sf * sizeof(float2), cudaMemcpyHostToDevice, h->stream));
-    launch_frontend(c, iq_dev + s0 * iq_sf, h->d_sym.p + s0 * c.nof_rx * g, h->d_ce.p + s0 * c.nof_ports * c.nof_rx * g, h->d_llr.p + (size_t)s0 * LLR_STRIDE,
-                    h->d_info.p + s0, m, h->stream, &h->launches);
-    launch_viterbi(c, h->d_llr.p + (size_t)s0 * LLR_STRIDE, h->d_info.p + s0, h->d_cands.p + (size_t)s0 * LTEPHY_MAX_LOC * LTEPHY_MAX_SIZES, m, h->stream,
-                   &h->launches);
-    launch_compact(c, h->d_info.p + s0, h->d_cands.p + (size_t)s0 * LTEPHY_MAX_LOC * LTEPHY_MAX_SIZES, h->d_compact.p + s0, m, h->stream, &h->launches);
-  }
+  const DevCell& c = h->dc;
+  if (iq_host) CU(cudaMemcpyAsync(h->d_iq.p, iq_host, (size_t)n * c.nof_rx * c.sf_len * sizeof(float2), cudaMemcpyHostToDevice, h->stream));
+  launch_frontend(c, iq_dev, h->d_sym.p, h->d_ce.p, h->d_llr.p, h->d_info.p, n, h->stream, &h->launches);
+  launch_viterbi(c, h->d_llr.p, h->d_info.p, h->d_cands.p, n, h->stream, &h->launches);
+  launch_compact(c, h->d_info.p, h->d_cands.p, h->d_compact.p, n, h->stream, &h->launches);
   CU(cudaEventRecord(h->ev[1], h->stream));
   CU(cudaGetLastError());
   h->n_cur = n;
