@@ -494,7 +494,19 @@ def main():
             traffic = tt["traffic_bytes"]
     except Exception:
         pass
+    # the same launches with nothing else on the GPU (one pipeline, one extra step after the timed regions): with several pipelines
+    # the in-region duration above includes the time the turbo CTAs share the SMs with the other streams' kernels
+    alone = None
+    if world == 1:
+        barrier()
+        step_on(0, capi.SEQ_NONE, True)
+        barrier()
+        t_alone = phys[0].timing()[2] * 1e-3
+        if t_alone > 0:
+            alone = {"launch_ms": t_alone * 1e3, "achieved": tbytes / t_alone / 1e9, "frac": tbytes / t_alone / 1e9 / peak,
+                     "turbo_info_mbit_s": info_bits / t_alone / 1e6}
     roofline = {"kernel": "turbo_kernel", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                "timed_alone": alone,
                 "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback 6.65 TB/s", "launch_ms": t_turbo * 1e3,
                 "algorithmic_bytes_per_launch": tbytes, "code_blocks": ncb, "turbo_info_mbit_s": info_bits / t_turbo / 1e6 if t_turbo > 0 else 0.0,
                 "note": "max-log-MAP is ALU/issue bound (~1e3 int ops per info bit); the HBM fraction is small by construction (SURVEY.md 8d)"}
