@@ -198,7 +198,7 @@ typedef struct {
 typedef struct {
   uint32_t sf;            /* index of the UL subframe inside the submitted UL batch */
   uint16_t rnti;
-  uint8_t  qm, rv;        /* srsran_pusch_grant_t.tb.mod / .rv */
+  uint8_t  qm, rv;        /* srsran_pusch_grant_t.tb.mod (2, 4, 6 or 8) / .rv */
   uint32_t L_prb, n_prb;  /* contiguous allocation (no hopping); L_prb in the 2^a 3^b 5^c set, >= 3 */
   uint32_t n_dmrs2;       /* 36.211 Table 5.5.2.1.1-1 value of the DCI-0 cyclic shift field */
   int32_t  tbs;

@@ -92,9 +92,12 @@ int      ltephy_search_rnti_is_evergreen(const ltephy_search_t* s, uint16_t rnti
 int ltephy_dci_to_grant(const ltephy_search_t* s, const ltephy_dci_t* dci, uint32_t sf_idx, uint32_t cfi, int use_256qam_table, ltephy_grant_t* grant,
                         ltephy_dci_fields_t* fields);
 
-/* DCI format 0 -> PUSCH grant (srsran_ra_ul_dci_to_grant as used at falcon_dci.c:222, no hopping).
- * enable_64qam: 0 caps the modulation at 16QAM (UE category without 64QAM), 1 uses Table 8.6.1-1 as is.
- * Returns 0, or LTEPHY_ERROR for hopping / retransmission MCS / invalid RIV / L_prb outside the DFT set or < 3. */
+/* DCI format 0 -> PUSCH grant (srsran_ra_ul_dci_to_grant as used at falcon_dci.c:222, and ulsniffer_ra_ul_dci_to_grant_256,
+ * lib/src/phy/falcon_phch/ul_sniffer_pusch.c:138-172; no hopping).  enable_64qam selects the MCS interpretation, i.e. one of the
+ * three attempts of PUSCH_Decoder::decode (src/src/UL_Sniffer_PUSCH.cc:498-521): 0 = Table 8.6.1-1 capped at 16QAM, 1 = Table
+ * 8.6.1-1 as is (64QAM), 2 = Table 8.6.1-3 (256QAM, Qm up to 8, MCS 26 -> TBS row 32A).  A caller that does not know the UE's
+ * table submits the alternatives as separate grants of one ltephy_submit_ul batch and keeps the one whose CRC passes.
+ * Returns 0, or LTEPHY_ERROR for hopping / retransmission MCS / invalid RIV / L_prb outside the DFT set or < 3 / no TBS. */
 int ltephy_ul_dci_to_grant(const ltephy_search_t* s, const ltephy_dci_t* dci, int enable_64qam, ltephy_ul_grant_t* grant);
 
 /* Whole batch: IQ in host memory -> accepted DCIs + transport blocks.  seq orders concurrent calls on

@@ -760,15 +760,33 @@ int ltephy_ul_dci_to_grant(const ltephy_search_t* s, const ltephy_dci_t* d, int 
   if (t != 1) return LTEPHY_ERROR;                   // valid_prb_ul, src/src/UL_Sniffer_PUSCH.cc:3-10
   memset(g, 0, sizeof(*g));
   int itbs;
-  if (mcs <= 10)
-    g->qm = 2, itbs = (int)mcs;
-  else if (mcs <= 20)
-    g->qm = 4, itbs = (int)mcs - 1;
-  else if (mcs <= 28)
-    g->qm = enable_64qam ? 6 : 4, itbs = (int)mcs - 2;
-  else
-    return LTEPHY_ERROR;
-  g->sf = d->sf, g->rnti = d->rnti, g->rv = 0, g->L_prb = L, g->n_prb = S, g->n_dmrs2 = dmrs2_map[cs & 7], g->tbs = lte_tbs_table[itbs][L - 1];
+  if (mcs > 28) return LTEPHY_ERROR;
+  if (enable_64qam == 2) { // 36.213 Table 8.6.1-3 as restated by ul_fill_ra_mcs_256 (lib/src/phy/falcon_phch/ul_sniffer_pusch.c:91-135)
+    if (mcs < 6)
+      g->qm = 2, itbs = 2 * (int)mcs;
+    else if (mcs < 14)
+      g->qm = 4, itbs = (int)mcs + (mcs < 10 ? 5 : 6);
+    else if (mcs < 23)
+      g->qm = 6, itbs = (int)mcs + (mcs < 19 ? 6 : 7);
+    else
+      g->qm = 8, itbs = (int)mcs + (mcs < 26 ? 7 : 6);
+    if (mcs == 26)
+      g->tbs = lte_tbs_32a(L); // row 32A
+    else if (itbs > 33)
+      return LTEPHY_ERROR;     // MCS 28 -> I_TBS 34: srsran_ra_tbs_from_idx has no such row
+    else
+      g->tbs = lte_tbs_table[itbs][L - 1];
+  } else {
+    if (mcs <= 10)
+      g->qm = 2, itbs = (int)mcs;
+    else if (mcs <= 20)
+      g->qm = 4, itbs = (int)mcs - 1;
+    else
+      g->qm = enable_64qam ? 6 : 4, itbs = (int)mcs - 2;
+    g->tbs = lte_tbs_table[itbs][L - 1];
+  }
+  if (g->tbs <= 0) return LTEPHY_ERROR;
+  g->sf = d->sf, g->rnti = d->rnti, g->rv = 0, g->L_prb = L, g->n_prb = S, g->n_dmrs2 = dmrs2_map[cs & 7];
   return LTEPHY_SUCCESS;
 }
 

@@ -24,11 +24,17 @@ __device__ __forceinline__ void ul_demod_s(float2 x, uint32_t qm, short* z)
     const int yr = ul_f2s(x.x * 400.0f), yi = ul_f2s(x.y * 400.0f);
     z[0] = (short)-yr, z[1] = (short)-yi;
     z[2] = (short)(ul_iabs(yr) - 252), z[3] = (short)(ul_iabs(yi) - 252);
-  } else {
+  } else if (qm == 6) {
     const int yr = ul_f2s(x.x * 700.0f), yi = ul_f2s(x.y * 700.0f);
     z[0] = (short)-yr, z[1] = (short)-yi;
     z[2] = (short)(ul_iabs(yr) - 432), z[3] = (short)(ul_iabs(yi) - 432);
     z[4] = (short)(ul_iabs(z[2]) - 216), z[5] = (short)(ul_iabs(z[3]) - 216);
+  } else { // 256QAM (third attempt of PUSCH_Decoder::decode, src/src/UL_Sniffer_PUSCH.cc:508-520)
+    const int yr = ul_f2s(x.x * 1000.0f), yi = ul_f2s(x.y * 1000.0f);
+    z[0] = (short)-yr, z[1] = (short)-yi;
+    z[2] = (short)(ul_iabs(yr) - 613), z[3] = (short)(ul_iabs(yi) - 613);
+    z[4] = (short)(ul_iabs(z[2]) - 306), z[5] = (short)(ul_iabs(z[3]) - 306);
+    z[6] = (short)(ul_iabs(z[4]) - 153), z[7] = (short)(ul_iabs(z[5]) - 153);
   }
 }
 

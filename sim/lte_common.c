@@ -928,16 +928,32 @@ int lte_ul_dci_to_grant(const lte_cell_t* c, const lte_dci_t* d, int table, lte_
   g->rnti = d->rnti, g->L_prb = L, g->n_prb = S, g->mcs = d->mcs[0], g->n_dmrs2 = dmrs2_map[d->n_dmrs & 7];
   uint32_t m = d->mcs[0];
   int      itbs;
-  if (m <= 10)
+  if (m > 28) return -2; /* retransmission MCS: needs the HARQ state the sniffer does not have */
+  if (table == 2) {      /* 36.213 Table 8.6.1-3 (256QAM), ul_fill_ra_mcs_256, lib/src/phy/falcon_phch/ul_sniffer_pusch.c:91-135 */
+    if (m < 6)
+      g->qm = 2, itbs = 2 * (int)m;
+    else if (m < 10)
+      g->qm = 4, itbs = (int)m + 5;
+    else if (m < 14)
+      g->qm = 4, itbs = (int)m + 6;
+    else if (m < 19)
+      g->qm = 6, itbs = (int)m + 6;
+    else if (m < 23)
+      g->qm = 6, itbs = (int)m + 7;
+    else if (m < 26)
+      g->qm = 8, itbs = (int)m + 7;
+    else if (m == 26)
+      g->qm = 8, itbs = -32; /* row 32A */
+    else
+      g->qm = 8, itbs = (int)m + 6;
+  } else if (m <= 10)
     g->qm = 2, itbs = (int)m;
   else if (m <= 20)
     g->qm = 4, itbs = (int)m - 1;
-  else if (m <= 28)
-    g->qm = table ? 6 : 4, itbs = (int)m - 2;
   else
-    return -2; /* retransmission MCS: needs the HARQ state the sniffer does not have */
+    g->qm = table ? 6 : 4, itbs = (int)m - 2;
   g->rv  = 0;
-  g->tbs = lte_tbs_from_idx(itbs, L);
+  g->tbs = itbs == -32 ? lte_tbs_32a(L) : lte_tbs_from_idx(itbs, L);
   if (g->tbs <= 0) return -2;
   g->nof_re   = 12 * L * 12; /* 12 data SC-FDMA symbols, no SRS */
   g->nof_bits = g->nof_re * g->qm;

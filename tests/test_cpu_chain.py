@@ -106,3 +106,30 @@ def test_sim_to_oracle_ground_truth(infra, name):
                     assert ok[t] and np.array_equal(pay[t][:nby], pl[d.payload_off[t]:d.payload_off[t] + nby]), (name, tti, hex(d.rnti), t)
                     ntb += 1
     assert ndci >= n and ntb >= 1
+
+
+def test_pusch_all_mcs_tables_roundtrip(infra):
+    """synthetic UEs -> oracle PUSCH receiver for the three MCS interpretations PUSCH_Decoder::decode tries
+    (src/src/UL_Sniffer_PUSCH.cc:498-521): 16QAM cap, 64QAM table, 256QAM table (36.213 Table 8.6.1-3, Qm up to 8)"""
+    from ltelib import UlCfg
+    cell = Cell(50, 1, 17, 1)
+    o = ltelib.Oracle(cell)
+    ucfg = UlCfg(n_dmrs1=3, delta_ss=2)
+    for table in (0, 1, 2):
+        s = ltelib.Sim(cell=cell, seed=5 + table, snr_db=36.0, nof_ues=1, chan_delay=2)
+        rng = np.random.default_rng(3 + table)
+        tot = ok = 0
+        qms = set()
+        for tti in range(4, 8):
+            gr = ltelib.make_ul_grants(cell, rng, 4, table=table)
+            x, pl, off = ltelib.sim_ul_subframe(s, tti, ucfg, gr)
+            sym, ref = ltelib.oracle_ul(o, ucfg, tti, gr, x)
+            for g, (r, opl, crc, ch, _), of in zip(gr, ref, off):
+                assert r == 0
+                tot += 1
+                ok += crc
+                qms.add(g.qm)
+                if crc:
+                    assert np.array_equal(opl[:g.tbs // 8], pl[of:of + g.tbs // 8])
+        assert ok == tot, (table, ok, tot)
+        assert max(qms) == (4, 6, 8)[table]

@@ -11,8 +11,9 @@ from ltesniffer_b200 import capi
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("cell,snr,nsf,ngr", [(Cell(50, 1, 17, 1), 25.0, 3, 4), (Cell(100, 2, 301, 2), 23.0, 3, 6), (Cell(25, 1, 5, 1), 20.0, 2, 2)])
-def test_pusch_bit_exact(infra, phylib, cell, snr, nsf, ngr):
+@pytest.mark.parametrize("cell,snr,nsf,ngr,table", [(Cell(50, 1, 17, 1), 25.0, 3, 4, 1), (Cell(100, 2, 301, 2), 23.0, 3, 6, 1), (Cell(25, 1, 5, 1), 20.0, 2, 2, 1),
+                                                      (Cell(50, 1, 9, 1), 34.0, 3, 4, 2)])     # table 2: 36.213 Table 8.6.1-3, Qm up to 8
+def test_pusch_bit_exact(infra, phylib, cell, snr, nsf, ngr, table):
     s = Sim(cell=cell, seed=21, snr_db=snr, nof_ues=1, chan_delay=3)
     o = Oracle(cell)
     rng = np.random.default_rng(cell.nof_prb)
@@ -23,7 +24,7 @@ def test_pusch_bit_exact(infra, phylib, cell, snr, nsf, ngr):
     tti = np.arange(4, 4 + nsf, dtype=np.uint32)
     grants_o, pls, offs, grants_p = [], [], [], []
     for i in range(nsf):
-        gr = ltelib.make_ul_grants(cell, rng, ngr, table=1)
+        gr = ltelib.make_ul_grants(cell, rng, ngr, table=table)
         x, pl, off = ltelib.sim_ul_subframe(s, int(tti[i]), ucfg, gr)
         iq[i] = x
         grants_o.append(gr), pls.append(pl), offs.append(off)

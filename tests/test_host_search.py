@@ -179,7 +179,7 @@ def test_ul_dci_to_grant_matches_oracle(infra):
             bits[0] = 0
             if it % 4:
                 bits[1] = 0                                  # mostly non-hopping
-            rnti, q64 = int(rng.integers(11, 0xFFF3)), int(rng.integers(0, 2))
+            rnti, q64 = int(rng.integers(11, 0xFFF3)), int(rng.integers(0, 3))     # 16QAM cap / 64QAM table / 256QAM table
             d, g0 = ltelib.Dci(), ltelib.UlGrant()
             r0 = S.lte_dci_unpack(C.byref(cell), 0, rnti, ltelib.ptr(bits), nb, C.byref(d))
             if r0 == 0:

@@ -38,3 +38,6 @@ def test_anchors_in_reference_tree():
     # 32A lies between rows 32 and 33 of Table 7.1.7.2.1-1 and only uses transport block sizes of the table
     assert np.all(row32a >= T[31]) and np.all(row32a[:100] <= T[33][:100])   # (32A keeps growing to 101840 above 100 PRB)
     assert set(row32a.tolist()) <= set(T.ravel().tolist()) | {101840}
+    hdr = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include", "lte_tables.h")).read()
+    m = re.search(r"lte_tbs_row_32a\[LTE_TBS_NOF_PRB\]\s*=\s*\{(.*?)\};", hdr, re.S)
+    assert [int(x) for x in re.findall(r"\d+", m.group(1))] == row32a.tolist()      # our copy of the row == the reference's
