@@ -912,7 +912,7 @@ extern "C" int ltephy_submit_ul(ltephy_t* h, const float* iq_ul, const uint32_t*
     const ltephy_ul_grant_t& g = gin[gi];
     if (g.sf >= n) return fail(LTEPHY_ERROR_INVALID_INPUTS, "UL grant %u: subframe outside the batch", gi);
     const uint32_t M = 12 * g.L_prb;
-    if (g.L_prb < 3 || g.n_prb + g.L_prb > c.nof_prb || (g.qm != 2 && g.qm != 4 && g.qm != 6) || g.tbs <= 0)
+    if (g.L_prb < 3 || g.n_prb + g.L_prb > c.nof_prb || (g.qm != 2 && g.qm != 4 && g.qm != 6 && g.qm != 8) || g.tbs <= 0)
       return fail(LTEPHY_ERROR_INVALID_INPUTS, "UL grant %u: unsupported allocation / modulation", gi);
     DevUlGrant d{};
     d.sf = g.sf, d.sf_idx = tti[g.sf] % 10, d.rnti = g.rnti, d.M = M, d.k0 = 12 * g.n_prb, d.qm = g.qm;
