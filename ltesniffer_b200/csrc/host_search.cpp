@@ -38,6 +38,7 @@ struct RntiManager {
     uint16_t cnt[NF];
     uint8_t  active, reason, assoc, pad;
     uint32_t last_seen;
+    uint16_t ever, forb; // bit f: this RNTI lies in an evergreen / forbidden interval of format f
   };
   struct Hist {
     struct Ent {
@@ -92,17 +93,17 @@ struct RntiManager {
   RntiManager(const RntiManager&)            = delete;
   RntiManager& operator=(const RntiManager&) = delete;
 
-  bool is_evergreen(uint16_t r, uint32_t f) const
+  bool is_evergreen(uint16_t r, uint32_t f) const { return (rec[r].ever >> f) & 1u; }
+  bool is_forbidden(uint16_t r, uint32_t f) const { return (rec[r].forb >> f) & 1u; }
+  void add_evergreen(uint16_t a, uint16_t b, uint32_t f)
   {
-    for (auto& i : evergreen[f])
-      if (r >= i.a && r <= i.b) return true;
-    return false;
+    evergreen[f].push_back({a, b});
+    for (uint32_t r = a; r <= b; r++) rec[r].ever |= (uint16_t)(1u << f);
   }
-  bool is_forbidden(uint16_t r, uint32_t f) const
+  void add_forbidden(uint16_t a, uint16_t b, uint32_t f)
   {
-    for (auto& i : forbidden[f])
-      if (r >= i.a && r <= i.b) return true;
-    return false;
+    forbidden[f].push_back({a, b});
+    for (uint32_t r = a; r <= b; r++) rec[r].forb |= (uint16_t)(1u << f);
   }
   uint32_t freq(uint16_t r, uint32_t f) const { return hist[f].freq(r); }
   void     add_candidate(uint16_t r, uint32_t f)
@@ -469,9 +470,10 @@ struct ltephy_search {
       const uint32_t lim = std::min<uint32_t>(ncce_sf, LTEPHY_SEARCH_MAX_CCE);
       const uint32_t k   = tmpl[info.cfi - 1].n;
       stats.nof_locations += k;
-      low = occ = 0;
-      for (uint32_t c = 0; c < lim; c++)
-        if (info.cce_power[c] < 0.7f) low |= (u128)1 << c;
+      uint64_t low_lo = 0, low_hi = 0;
+      for (uint32_t c = 0; c < std::min<uint32_t>(lim, 64); c++) low_lo |= (uint64_t)(info.cce_power[c] < 0.7f) << c;
+      for (uint32_t c = 64; c < lim; c++) low_hi |= (uint64_t)(info.cce_power[c] < 0.7f) << (c - 64);
+      low = ((u128)low_hi << 64) | low_lo, occ = 0;
       refold();
       for (uint32_t l = 0; l < 4; l++) nq[l] = tmpl[info.cfi - 1].nq[l], val[l] = tmpl[info.cfi - 1].val[l];
       ret = 0;
@@ -832,10 +834,10 @@ ltephy_search_t* ltephy_search_create_cell(uint32_t nof_prb, uint32_t nof_ports,
   s->update_formats();
   // evergreen / forbidden ranges exactly as LTESniffer_Core.cc:398-417 seeds them after the MIB
   for (int f : {(int)ltehost::F1A, (int)ltehost::F1C}) {
-    s->rm.evergreen[f].push_back({RARNTI_START, RARNTI_END});
-    s->rm.evergreen[f].push_back({PRNTI, 0xFFFF});
+    s->rm.add_evergreen(RARNTI_START, RARNTI_END, (uint32_t)f);
+    s->rm.add_evergreen(PRNTI, 0xFFFF, (uint32_t)f);
   }
-  for (int f = 0; f < NF; f++) s->rm.forbidden[f].push_back({0, 0});
+  for (int f = 0; f < NF; f++) s->rm.add_forbidden(0, 0, (uint32_t)f);
   return s;
 }
 ltephy_search_t* ltephy_search_create(const ltephy_t* h, uint32_t histogram_threshold)
@@ -852,11 +854,11 @@ void ltephy_search_config(ltephy_search_t* s, int shortcut, int skip_secondary, 
 }
 void ltephy_search_add_evergreen(ltephy_search_t* s, uint16_t a, uint16_t b, uint32_t f)
 {
-  if (f < NF) s->rm.evergreen[f].push_back({a, b});
+  if (f < NF && a <= b) s->rm.add_evergreen(a, b, f);
 }
 void ltephy_search_add_forbidden(ltephy_search_t* s, uint16_t a, uint16_t b, uint32_t f)
 {
-  if (f < NF) s->rm.forbidden[f].push_back({a, b});
+  if (f < NF && a <= b) s->rm.add_forbidden(a, b, f);
 }
 void ltephy_search_activate(ltephy_search_t* s, uint16_t rnti, uint32_t format_idx, int reason) { s->rm.activate_and_refresh(rnti, format_idx, (uint8_t)reason); }
 int  ltephy_search_subframe(ltephy_search_t* s, const ltephy_sf_info_t* info, const ltephy_cand_t* cands, uint32_t sf_in_batch, ltephy_dci_t* out,
