@@ -197,3 +197,44 @@ def test_ul_dci_to_grant_matches_oracle(infra):
                        (7, rnti, g0.qm, g0.rv, g0.L_prb, g0.n_prb, g0.n_dmrs2, g0.tbs)
                 nok += 1
     assert nok > 500
+
+
+def test_finalize_info_and_full_table_decision(infra):
+    """host-only helpers of the sharded path: ltephy_finalize_info reproduces the averages / dB / CFO step and is idempotent;
+    ltephy_search_needs_full_table reacts to an overfull subframe and to a RAR activation, and only to those"""
+    L = capi.load_library()
+    capi._bind_search(L)
+    rng = np.random.default_rng(12)
+    n = 5
+    info = (capi.SfInfo * n)()
+    for i in range(n):
+        for p in range(2):
+            for a in range(2):
+                info[i].noise[p][a] = float(rng.uniform(1e-3, 2e-3))
+                info[i].rsrp[p][a] = float(rng.uniform(0.5, 1.5))
+        info[i].cfo_re, info[i].cfo_im = float(rng.uniform(0.5, 1.0)), float(rng.uniform(-0.1, 0.1))
+    L.ltephy_finalize_info(info, n, 2, 2)
+    first = bytes(info)
+    for i in range(n):
+        ns = np.float32(0)
+        ps = np.float32(0)
+        for p in range(2):
+            for a in range(2):
+                ns = np.float32(ns + np.float32(info[i].noise[p][a]))
+                ps = np.float32(ps + np.float32(info[i].rsrp[p][a]))
+        assert info[i].noise_avg == np.float32(ns / np.float32(4)) and info[i].rsrp_avg == np.float32(ps / np.float32(4))
+        assert abs(info[i].snr_db - 10 * np.log10(float(info[i].rsrp_avg) / float(info[i].noise_avg))) < 1e-4
+        assert abs(info[i].cfo - np.arctan2(info[i].cfo_im, info[i].cfo_re) / (2 * np.pi * 7.5)) < 1e-7
+    L.ltephy_finalize_info(info, n, 2, 2)
+    assert bytes(info) == first
+    srch = capi.Search(50, 2, 3, 2)
+    comp = np.zeros(n, capi.COMPACT_DTYPE)
+    assert L.ltephy_search_needs_full_table(srch.h, comp.ctypes.data_as(C.c_void_p), n) == 0
+    comp["count"][3] = capi.COMPACT_CAP + 1
+    assert L.ltephy_search_needs_full_table(srch.h, comp.ctypes.data_as(C.c_void_p), n) == 1
+    comp["count"][3] = capi.COMPACT_CAP
+    assert L.ltephy_search_needs_full_table(srch.h, comp.ctypes.data_as(C.c_void_p), n) == 0
+    L.ltephy_search_activate(srch.h, 0x1234, 2, 4)          # activation for another reason does not count
+    assert L.ltephy_search_needs_full_table(srch.h, comp.ctypes.data_as(C.c_void_p), n) == 0
+    L.ltephy_search_activate(srch.h, 0x2345, 0, 2)          # RAR
+    assert L.ltephy_search_needs_full_table(srch.h, comp.ctypes.data_as(C.c_void_p), n) == 1
