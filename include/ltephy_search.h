@@ -58,6 +58,12 @@ void             ltephy_search_destroy(ltephy_search_t* s);
 /* shortcut discovery on/off (DCISearch::setShortcutDiscovery), -m skip_secondary_meta_formats,
  * dci_format_split_update_interval_ms (0 = never re-split) */
 void ltephy_search_config(ltephy_search_t* s, int shortcut, int skip_secondary, uint32_t update_interval);
+/* MCS table of C-RNTI grants unknown (no MCSTracking answer yet): ltephy_grants_from_dcis then emits BOTH readings of such a DCI
+ * -- 36.213 Table 7.1.7.1-1 first, Table 7.1.7.1-1A (256QAM) second, flagged with LTEPHY_GRANT_ALT_TABLE in grant_dci[] -- when
+ * they differ, and ltephy_decode_subframes reports the first reading unless only the second passes a CRC (then crc = 2): the
+ * batched form of "try the 64QAM table, then the 256QAM table" (src/src/DL_Sniffer_PDSCH.cc:1089-1210).  Off by default. */
+void ltephy_search_speculate_256qam(ltephy_search_t* s, int on);
+#define LTEPHY_GRANT_ALT_TABLE 0x80000000u
 void ltephy_search_add_evergreen(ltephy_search_t* s, uint16_t rnti_start, uint16_t rnti_end, uint32_t format_idx);
 void ltephy_search_add_forbidden(ltephy_search_t* s, uint16_t rnti_start, uint16_t rnti_end, uint32_t format_idx);
 /* rntiManager.activateAndRefresh, e.g. for T-CRNTIs found in a RAR (src/src/DL_Sniffer_PDSCH.cc:659,794) */

@@ -313,6 +313,7 @@ def _bind_search(L):
     L.ltephy_search_create_cell.restype = P
     L.ltephy_search_destroy.argtypes = [P]
     L.ltephy_search_config.argtypes = [P, C.c_int, C.c_int, C.c_uint32]
+    L.ltephy_search_speculate_256qam.argtypes = [P, C.c_int]
     L.ltephy_search_add_evergreen.argtypes = [P, C.c_uint16, C.c_uint16, C.c_uint32]
     L.ltephy_search_add_forbidden.argtypes = [P, C.c_uint16, C.c_uint16, C.c_uint32]
     L.ltephy_search_activate.argtypes = [P, C.c_uint16, C.c_uint32, C.c_int]

@@ -241,6 +241,7 @@ struct ltephy_search {
   uint32_t           n_primary = 0, n_secondary = 0;
   double             split_ratio     = 0.99;
   bool               skip_secondary  = false, shortcut = true;
+  bool               speculate_256qam = false; // grants_from_dcis emits both MCS-table readings of a C-RNTI DCI (DL_Sniffer_PDSCH.cc:1089-1210)
   uint32_t           update_interval = 500, sf_cnt = 0;
   ltephy_search_stats_t stats{};
   // per-subframe scratch
@@ -848,6 +849,10 @@ ltephy_search_t* ltephy_search_create(const ltephy_t* h, uint32_t histogram_thre
   return ltephy_search_create_cell(a, b, c, d, histogram_threshold);
 }
 void ltephy_search_destroy(ltephy_search_t* s) { delete s; }
+void ltephy_search_speculate_256qam(ltephy_search_t* s, int on)
+{
+  if (s) s->speculate_256qam = on != 0;
+}
 void ltephy_search_config(ltephy_search_t* s, int shortcut, int skip_secondary, uint32_t update_interval)
 {
   s->shortcut = shortcut != 0, s->skip_secondary = skip_secondary != 0, s->update_interval = update_interval;
@@ -994,18 +999,33 @@ int ltephy_grants_from_dcis(const ltephy_search_t* s, const ltephy_sf_info_t* in
 {
   if (!s || !info || !dcis || !grants || !grant_dci || !n_grants || mod == 0) return LTEPHY_ERROR_INVALID_INPUTS;
   uint32_t ng = 0;
+  auto eligible = [&](const ltephy_grant_t& g) {
+    if (!(g.tb[0].tbs > 0 && !(s->cell.nof_rx == 1 && g.nof_tb == 2))) return false;
+    if (g.tx_scheme == LTEPHY_TX_SPATIALMUX && (s->cell.nof_ports != 2 || (g.nof_tb == 2 && s->cell.nof_rx != 2))) return false;
+    return true;
+  };
   for (uint32_t i = 0; i < nd; i++) {
     const ltephy_dci_t& d = dcis[i];
     if (d.sf % mod != rem || d.format == ltehost::F0 || d.rnti == 0) continue;
-    ltephy_grant_t g;
-    if (ltephy_dci_to_grant(s, &d, info[d.sf].tti % 10, info[d.sf].cfi, 0, &g, nullptr) != LTEPHY_SUCCESS) continue;
-    if (!(g.tb[0].tbs > 0 && !(s->cell.nof_rx == 1 && g.nof_tb == 2))) continue;
-    if (g.tx_scheme == LTEPHY_TX_SPATIALMUX && (s->cell.nof_ports != 2 || (g.nof_tb == 2 && s->cell.nof_rx != 2))) continue;
-    if (ng >= max_grants) return LTEPHY_ERROR_INVALID_INPUTS;
-    g.sf          = d.sf / mod;
-    grants[ng]    = g;
-    grant_dci[ng] = i;
-    ng++;
+    ltephy_grant_t g[2];
+    bool           ok[2] = {false, false};
+    ok[0] = ltephy_dci_to_grant(s, &d, info[d.sf].tti % 10, info[d.sf].cfi, 0, &g[0], nullptr) == LTEPHY_SUCCESS && eligible(g[0]);
+    if (s->speculate_256qam && user_rnti(d.rnti)) { // MCS table of the UE unknown: 64QAM reading first, then the 256QAM one
+      ok[1] = ltephy_dci_to_grant(s, &d, info[d.sf].tti % 10, info[d.sf].cfi, 1, &g[1], nullptr) == LTEPHY_SUCCESS && eligible(g[1]);
+      if (ok[0] && ok[1]) {
+        bool same = g[0].nof_tb == g[1].nof_tb;
+        for (int t = 0; t < 2 && same; t++) same = g[0].tb[t].enabled == g[1].tb[t].enabled && g[0].tb[t].qm == g[1].tb[t].qm && g[0].tb[t].tbs == g[1].tb[t].tbs;
+        if (same) ok[1] = false;
+      }
+    }
+    for (uint32_t a = 0; a < 2; a++) {
+      if (!ok[a]) continue;
+      if (ng >= max_grants) return LTEPHY_ERROR_INVALID_INPUTS;
+      g[a].sf       = d.sf / mod;
+      grants[ng]    = g[a];
+      grant_dci[ng] = i | (a ? LTEPHY_GRANT_ALT_TABLE : 0u);
+      ng++;
+    }
   }
   *n_grants = ng;
   return LTEPHY_SUCCESS;
@@ -1046,10 +1066,10 @@ static int decode_common(ltephy_t* h, ltephy_search_t* s, const void* iq, bool i
   if (r < 0) return r;
   double t3 = now_ms();
   *n_dcis = nd;
-  std::vector<ltephy_grant_t> grants(nd + 1);
-  std::vector<uint32_t>       grant_dci(nd + 1);
+  std::vector<ltephy_grant_t> grants(2 * (size_t)nd + 1);
+  std::vector<uint32_t>       grant_dci(2 * (size_t)nd + 1);
   uint32_t                    ng = 0;
-  r = ltephy_grants_from_dcis(s, info, dcis, nd, 1, 0, grants.data(), grant_dci.data(), nd + 1, &ng);
+  r = ltephy_grants_from_dcis(s, info, dcis, nd, 1, 0, grants.data(), grant_dci.data(), 2 * nd + 1, &ng);
   if (r) return r;
   double t4 = now_ms();
   for (uint32_t i = 0; i < 2 * nd; i++) tbs[i] = ltephy_tb_result_t{};
@@ -1061,9 +1081,22 @@ static int decode_common(ltephy_t* h, ltephy_search_t* s, const void* iq, bool i
   if (r) return r;
   double t6 = now_ms();
   g_host_ms[0] = t1 - t0, g_host_ms[1] = t2 - t1, g_host_ms[2] = t3 - t2, g_host_ms[3] = t4 - t3, g_host_ms[4] = t5 - t4, g_host_ms[5] = t6 - t5;
+  // one result per DCI: the 64QAM-table reading unless only the 256QAM-table reading (speculative second grant) passes a CRC,
+  // in which case its transport blocks are reported with crc = 2
   for (uint32_t gi = 0; gi < ng; gi++) {
-    tbs[2 * grant_dci[gi]]     = res[2 * gi];
-    tbs[2 * grant_dci[gi] + 1] = res[2 * gi + 1];
+    const uint32_t di = grant_dci[gi] & ~LTEPHY_GRANT_ALT_TABLE;
+    const bool     alt = (grant_dci[gi] & LTEPHY_GRANT_ALT_TABLE) != 0;
+    if (!alt) {
+      tbs[2 * di] = res[2 * gi], tbs[2 * di + 1] = res[2 * gi + 1];
+      continue;
+    }
+    const bool have_primary = tbs[2 * di].payload_len || tbs[2 * di + 1].payload_len; // grants of one DCI are adjacent, primary first
+    if (have_primary && (tbs[2 * di].crc || tbs[2 * di + 1].crc)) continue;
+    if (!have_primary || res[2 * gi].crc || res[2 * gi + 1].crc) {
+      tbs[2 * di] = res[2 * gi], tbs[2 * di + 1] = res[2 * gi + 1];
+      for (int t = 0; t < 2; t++)
+        if (tbs[2 * di + t].crc) tbs[2 * di + t].crc = 2;
+    }
   }
   return LTEPHY_SUCCESS;
 }

@@ -120,3 +120,47 @@ def test_device_side_exchange_equals_host_fetch(infra, phylib):
     finally:
         dist.destroy_process_group()
     phy.close()
+
+
+@pytest.mark.parametrize("alt", [1, 0])
+def test_speculative_mcs_table(infra, phylib, alt):
+    """UEs configured with the 256QAM MCS table (alt = 1) or the normal one (alt = 0), receiver not told which:
+    ltephy_search_speculate_256qam makes the pipeline decode both readings of every C-RNTI DCI in the same batch and report the
+    one whose CRC passes (crc = 1: Table 7.1.7.1-1, crc = 2: Table 7.1.7.1-1A), DL_Sniffer_PDSCH.cc:1089-1210."""
+    cell = Cell(50, 2, 11, 2)
+    n = 30
+    kw = dict(seed=15 + alt, cfi=2, nof_ues=5, dl_min=2, dl_max=3, tm=4 if alt else 3, mcs_min=5, mcs_max=20, snr_db=33.0, alt_table=alt)
+    sim, iq, tti, truths, payloads = make_capture(cell, n, **kw)
+    sent = {}
+    for sf, tr in enumerate(truths):
+        for i in range(tr.nof_dci):
+            d = tr.dci[i]
+            for tb in range(2):
+                if d.tbs[tb] > 0:
+                    sent[(sf, d.rnti, tb)] = payloads[sf][d.payload_off[tb]:d.payload_off[tb] + d.tbs[tb] // 8]
+    L = capi.load_library()
+    capi._bind_search(L)
+    hits = {}
+    for spec in (1, 0):
+        phy = capi.LtePhy(cell.nof_prb, cell.nof_ports, cell.cell_id, cell.nof_rx, max_subframes=n, turbo_max_iter=8, flags=capi.FLAG_SKIP_LOW_POWER)
+        srch = capi.Search(cell.nof_prb, cell.nof_ports, cell.cell_id, cell.nof_rx)
+        L.ltephy_search_speculate_256qam(srch.h, spec)
+        info, dcis, tbs, payload = capi.decode_subframes(phy, srch, iq, tti)
+        ok = {}
+        for i, d in enumerate(dcis):
+            for tb in range(2):
+                r = tbs[2 * i + tb]
+                key = (int(d["sf"]), int(d["rnti"]), tb)
+                if r.crc and key in sent:
+                    assert r.payload_len == len(sent[key]) and np.array_equal(payload[r.payload_off:r.payload_off + r.payload_len], sent[key])
+                    ok[key] = int(r.crc)
+        hits[spec] = ok
+        phy.close()
+    late = [k for k in sent if k[0] >= n // 2]
+    got = [k for k in late if k in hits[1]]
+    assert len(got) >= 0.8 * len(late), (alt, len(got), len(late))
+    assert set(hits[1].values()) == ({2} if alt else {1}), (alt, set(hits[1].values()))
+    if alt:
+        assert len(hits[0]) < 0.2 * max(1, len(hits[1]))      # without speculation the 256QAM-table UEs are (almost) never decoded
+    else:
+        assert hits[0] == hits[1]                             # speculation does not change what is reported for normal UEs
