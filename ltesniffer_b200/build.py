@@ -8,7 +8,7 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libltephy_b200.so")
-SOURCES = ["k_frontend.cu", "k_viterbi.cu", "k_pdsch.cu", "k_turbo.cu", "k_pusch.cu", "ltephy_capi.cu", "lte_host.cpp", "host_search.cpp"]
+SOURCES = ["k_frontend.cu", "k_viterbi.cu", "k_pdsch.cu", "k_turbo.cu", "k_pusch.cu", "ltephy_capi.cu", "lte_host.cpp", "host_search.cpp", "sinks.cpp"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-fmad=false",
               "-Xcompiler", "-fPIC,-ffp-contract=off,-fno-fast-math,-Wall,-Wno-unused-function", "--shared", "-Xptxas", "-v"]
 

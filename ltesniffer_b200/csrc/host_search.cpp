@@ -6,12 +6,13 @@
 //   lib/src/phy/falcon_phch/falcon_pdcch.c:183-250 (search-space validation), falcon_dci.c:148-352 and
 //   dl_sniffer_pdsch.c:14-276 (DCI -> grant).  Integer control flow only: the GPU never sees this state.
 #include "../../include/ltephy_b200.h"
-#include "../../include/ltephy_search.h"
+#include "../../include/ltephy_sinks.h"
 #include "../../include/lte_tables.h"
 #include "lte_host.hpp"
 #include <algorithm>
 #include <chrono>
 #include <condition_variable>
+#include <cstdio>
 #include <cstring>
 #include <mutex>
 #include <vector>
@@ -791,6 +792,43 @@ int ltephy_ul_dci_to_grant(const ltephy_search_t* s, const ltephy_dci_t* d, int 
   if (g->tbs <= 0) return LTEPHY_ERROR;
   g->sf = d->sf, g->rnti = d->rnti, g->rv = 0, g->L_prb = L, g->n_prb = S, g->n_dmrs2 = dmrs2_map[cs & 7];
   return LTEPHY_SUCCESS;
+}
+
+// One line of the DCI trace file, DCIToFile::printDCICollection (reference src/src/SubframeInfoConsumer.cc:66-138); the hex column is
+// sprint_hex of the payload bits (lib/src/phy/falcon_phch/falcon_dci.c:37-58).  Declared in include/ltephy_sinks.h.
+extern "C" int ltephy_dci_trace_line(const ltephy_search_t* s, const ltephy_dci_t* d, uint32_t tti, uint32_t cfi, int use_256qam_table, uint32_t ts_sec,
+                                     uint32_t ts_usec, char* out, size_t cap)
+{
+  if (!s || !d || !out || cap < 2 || d->nof_bits == 0 || d->nof_bits > 64) return LTEPHY_ERROR_INVALID_INPUTS;
+  char           hex[2 * 8 + 1];
+  const uint32_t nbytes = (d->nof_bits + 7) / 8;
+  for (uint32_t i = 0; i < nbytes; i++) snprintf(hex + 2 * i, 3, "%02x", (unsigned)((d->bits >> (56 - 8 * i)) & 0xFFu));
+  const uint32_t sfn = tti / 10, sf = tti % 10;
+  int            n;
+  if (d->format == ltehost::F0) {
+    const uint32_t N = s->cell.nof_prb, rivb = clog2(N * (N + 1) / 2);
+    Bits           b{d->bits};
+    b.get(1), b.get(1);
+    const uint32_t riv = b.get(rivb), mcs = b.get(5), ndi = b.get(1);
+    uint32_t       L, S;
+    riv_decode(riv, N, L, S);
+    if (L < 1 || L > N || S >= N || S + L > N) return LTEPHY_ERROR;
+    const int itbs = mcs <= 10 ? (int)mcs : mcs <= 20 ? (int)mcs - 1 : (int)mcs - 2;
+    const int tbs  = mcs < 29 ? lte_tbs_table[itbs][L - 1] : 0;
+    n = snprintf(out, cap, "%ld.%06ld\t%04d\t%d\t%d\t0\t%d\t%d\t%d\t%d\t%d\t0\t%d\t-1\t%d\t%d\t%d\t%d\t%d\t%d\t%s\n", (long)ts_sec, (long)ts_usec, (int)sfn,
+                 (int)sf, (int)d->rnti, (int)mcs, (int)L, tbs, -1, -1, (int)ndi, (int)((10 * sfn + sf) % 8), (int)d->ncce, (int)d->L, (int)cfi,
+                 (int)d->histogram_value, (int)d->nof_bits, hex);
+  } else {
+    ltephy_grant_t      g;
+    ltephy_dci_fields_t f;
+    if (ltephy_dci_to_grant(s, d, sf, cfi, use_256qam_table, &g, &f) != LTEPHY_SUCCESS) return LTEPHY_ERROR;
+    const bool two  = d->format >= ltehost::F2;
+    const int  tbs0 = g.tb[0].tbs > 0 ? g.tb[0].tbs : 0, tbs1 = g.tb[1].tbs > 0 ? g.tb[1].tbs : 0;
+    n = snprintf(out, cap, "%ld.%06ld\t%04d\t%d\t%d\t1\t%d\t%d\t%d\t%d\t%d\t%d\t%d\t%d\t%d\t%d\t%d\t%d\t%d\t%d\t%s\n", (long)ts_sec, (long)ts_usec, (int)sfn,
+                 (int)sf, (int)d->rnti, (int)f.mcs[0], (int)f.nof_prb, two ? tbs0 + tbs1 : tbs0, two ? tbs0 : -1, two ? tbs1 : -1, (int)d->format + 1,
+                 (int)f.ndi[0], two ? (int)f.ndi[1] : -1, (int)f.harq_pid, (int)d->ncce, (int)d->L, (int)cfi, (int)d->histogram_value, (int)d->nof_bits, hex);
+  }
+  return (n < 0 || (size_t)n >= cap) ? LTEPHY_ERROR_INVALID_INPUTS : n;
 }
 
 // ===================================================================================================
