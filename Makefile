@@ -13,5 +13,9 @@ sim/libltesim.so: sim/lte_common.c sim/lte_sim.c sim/lte_common.h sim/lte_sim.h 
 oracle/liblteoracle.so: oracle/lte_oracle.c oracle/lte_oracle.h sim/lte_common.c sim/lte_common.h include/lte_tables.h
 	$(CC) $(CFLAGS) -shared -o $@ oracle/lte_oracle.c sim/lte_common.c -lm -lpthread
 
+# C++ example of the C-ABI (needs ltesniffer_b200/libltephy_b200.so, built by ltesniffer_b200/build.py)
+examples/offline_decode: examples/offline_decode.cpp include/ltephy_b200.h include/ltephy_search.h include/ltephy_sinks.h
+	$(CXX) -O2 -std=c++17 -Wall -Iinclude -o $@ examples/offline_decode.cpp -Lltesniffer_b200 -lltephy_b200 -Wl,-rpath,'$$ORIGIN/../ltesniffer_b200'
+
 clean:
-	rm -f sim/*.so oracle/*.so
+	rm -f sim/*.so oracle/*.so examples/offline_decode
