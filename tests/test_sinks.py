@@ -30,6 +30,7 @@ def _lib():
     L.ltephy_rnti_type.argtypes = [C.c_uint16]
     L.ltephy_rnti_type.restype = C.c_uint8
     L.ltephy_pcap_write_dl_batch.argtypes = [P, P, P, C.c_uint32, P, P, C.c_uint16, C.c_uint32, C.c_uint32]
+    L.ltephy_pcap_write_ul_batch.argtypes = [P, P, P, C.c_uint32, P, P, C.c_uint16, C.c_uint32, C.c_uint32]
     L.ltephy_dci_trace_line.argtypes = [P, P, C.c_uint32, C.c_uint32, C.c_int, C.c_uint32, C.c_uint32, C.c_char_p, C.c_size_t]
     return L
 
@@ -104,6 +105,23 @@ def test_dl_batch_writes_crc_passing_blocks_only(infra, tmp_path):
     assert [(r["rnti"], r["rnti_type"], r["tti"], len(r["pdu"]), r["ueid"], r["direction"]) for r in recs] == \
            [(0xFFFF, 4, 4301, 10, 7, 1), (0x1234, 3, 4302, 6, 7, 1), (0x0005, 2, 4302, 4, 7, 1)]
     assert recs[1]["pdu"] == bytes(range(18, 24))
+
+
+def test_ul_batch_writes_crc_passing_blocks_only(infra, tmp_path):
+    L = _lib()
+    grants = (capi.UlGrant * 3)(capi.UlGrant(sf=0, rnti=0x46, qm=2, L_prb=3, tbs=208), capi.UlGrant(sf=1, rnti=0x47, qm=4, L_prb=4, tbs=256),
+                                capi.UlGrant(sf=1, rnti=0x48, qm=2, L_prb=3, tbs=208))
+    res = (capi.TbResult * 3)()
+    payload = np.arange(200, dtype=np.uint8)
+    for i, (crc, off, ln) in enumerate([(1, 0, 26), (0, 26, 32), (1, 58, 26)]):
+        res[i].crc, res[i].payload_off, res[i].payload_len = crc, off, ln
+    tti = np.array([1234, 1235], np.uint32)
+    out = str(tmp_path / "u.pcap")
+    p = L.ltephy_pcap_open(out.encode())
+    assert L.ltephy_pcap_write_ul_batch(p, tti.ctypes.data_as(C.c_void_p), grants, 3, res, payload.ctypes.data_as(C.c_void_p), 0, 9, 8) == 2
+    L.ltephy_pcap_close(p)
+    _, recs = parse(out)
+    assert [(r["rnti"], r["rnti_type"], r["direction"], r["tti"], len(r["pdu"])) for r in recs] == [(0x46, 3, 0, 1234, 26), (0x48, 3, 0, 1235, 26)]
 
 
 def test_dci_trace_line_format(infra):
