@@ -20,6 +20,9 @@ def nvcc_path():
     return p
 
 
+COMPAT_OUT = os.path.join(HERE, "libltephy_srsran_compat.so")
+
+
 def stale():
     if not os.path.exists(OUT):
         return True
@@ -30,6 +33,8 @@ def stale():
 
 def build(force=False, verbose=False):
     if not force and not stale():
+        if not os.path.exists(COMPAT_OUT):
+            build_compat()
         return OUT
     srcs = [os.path.join(CSRC, s) for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
     cmd = [nvcc_path()] + NVCC_FLAGS + ["-o", OUT] + srcs
@@ -41,7 +46,20 @@ def build(force=False, verbose=False):
         raise RuntimeError("nvcc failed:\n" + log[-6000:])
     if verbose:
         print(log)
+    build_compat()
     return OUT
+
+
+def build_compat():
+    """tier-2 shim (srsRAN / FALCON names over the tier-1 C-ABI): host code only, links libltephy_b200.so"""
+    import shutil as _sh
+    cxx = _sh.which("g++") or "g++"
+    cmd = [cxx, "-O2", "-std=c++17", "-fPIC", "-shared", "-Wall", "-o", COMPAT_OUT, os.path.join(CSRC, "srsran_compat.cpp"), "-L" + HERE, "-lltephy_b200",
+           "-Wl,-rpath,$ORIGIN"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("building the srsRAN compatibility shim failed:\n" + (r.stdout + r.stderr)[-4000:])
+    return COMPAT_OUT
 
 
 if __name__ == "__main__":
