@@ -238,3 +238,61 @@ def test_finalize_info_and_full_table_decision(infra):
     assert L.ltephy_search_needs_full_table(srch.h, comp.ctypes.data_as(C.c_void_p), n) == 0
     L.ltephy_search_activate(srch.h, 0x2345, 0, 2)          # RAR
     assert L.ltephy_search_needs_full_table(srch.h, comp.ctypes.data_as(C.c_void_p), n) == 1
+
+
+def test_grants_from_dcis_speculation_and_sharding_filters(infra):
+    """ltephy_grants_from_dcis (host only): owner filter sf % mod == rem with local sf = sf // mod; with ltephy_search_speculate_256qam
+    a C-RNTI DCI whose two MCS-table readings differ yields two adjacent grants, the second flagged LTEPHY_GRANT_ALT_TABLE; SI / RA /
+    paging RNTIs and DCI format 0 never do."""
+    S = infra.sim()
+    L = capi.load_library()
+    capi._bind_search(L)
+    cell = Cell(50, 2, 3, 2)
+    srch = capi.Search(cell.nof_prb, cell.nof_ports, cell.cell_id, cell.nof_rx)
+    rng = np.random.default_rng(21)
+    n_sf = 6
+    info = (capi.SfInfo * n_sf)()
+    for i in range(n_sf):
+        info[i].tti, info[i].cfi = 20 + i, 2
+    rows = []
+    for sf in range(n_sf):
+        for rnti, f in ((0xFFFF, 2), (0x0004, 2), (int(rng.integers(0x100, 0xFFF0)), 1), (int(rng.integers(0x100, 0xFFF0)), 7), (int(rng.integers(0x100, 0xFFF0)), 0)):
+            nb = S.lte_dci_sizeof(C.byref(cell), f)
+            for _ in range(50):                                  # draw until the 64QAM-table reading is a valid grant (format 0 excepted)
+                bits = rng.integers(0, 2, nb).astype(np.uint8)
+                bits[0] = 1 if f == 2 else (0 if f == 0 else bits[0])
+                r0, d, g = ltelib.unpack_and_grant(cell, f, rnti, bits, info[sf].tti % 10, 2, 0) if f else (0, None, None)
+                if f == 0 or (r0 == 0 and g.tb[0].tbs > 0):
+                    break
+            v = 0
+            for k, b in enumerate(bits):
+                v |= int(b) << (63 - k)
+            rows.append((sf, rnti, f, nb, v))
+    dcis = np.zeros(len(rows), capi.DCI_DTYPE)
+    for i, (sf, rnti, f, nb, v) in enumerate(rows):
+        dcis[i]["sf"], dcis[i]["rnti"], dcis[i]["format"], dcis[i]["nof_bits"], dcis[i]["bits"] = sf, rnti, f, nb, v
+    grants = (capi.Grant * (4 * len(rows)))()
+    gidx = np.zeros(4 * len(rows), np.uint32)
+    ng = C.c_uint32(0)
+
+    def run(mod, rem):
+        assert L.ltephy_grants_from_dcis(srch.h, info, dcis.ctypes.data_as(C.c_void_p), len(rows), mod, rem, grants, gidx.ctypes.data_as(C.c_void_p), len(gidx),
+                                         C.byref(ng)) == 0
+        return [(int(gidx[i]) & 0x7FFFFFFF, int(gidx[i]) >> 31, int(grants[i].sf), int(grants[i].rnti), int(grants[i].tb[0].qm), int(grants[i].tb[0].tbs)) for i in range(ng.value)]
+    plain = run(1, 0)
+    assert all(a == 0 for _, a, *_ in plain) and all(rows[di][2] != 0 for di, *_ in plain)      # no alternates, no format 0
+    assert len(plain) >= 3 * n_sf
+    halves = [run(2, r) for r in range(2)]
+    assert sorted([(di, a) for h in halves for di, a, *_ in h]) == sorted([(di, a) for di, a, *_ in plain])
+    for r, h in enumerate(halves):
+        assert all(rows[di][0] % 2 == r and sf == rows[di][0] // 2 for di, a, sf, *_ in h)
+    L.ltephy_search_speculate_256qam(srch.h, 1)
+    spec = run(1, 0)
+    alts = [x for x in spec if x[1] == 1]
+    assert alts and [x for x in spec if x[1] == 0] == plain
+    for k, x in enumerate(spec):
+        if x[1] == 1:
+            di = x[0]
+            assert 0x000A < rows[di][1] < 0xFFF4                  # user RNTIs only
+            assert spec[k - 1][0] == di and spec[k - 1][1] == 0  # adjacent to its primary, after it
+            assert (x[4], x[5]) != (spec[k - 1][4], spec[k - 1][5])
