@@ -296,3 +296,47 @@ def test_grants_from_dcis_speculation_and_sharding_filters(infra):
             assert 0x000A < rows[di][1] < 0xFFF4                  # user RNTIs only
             assert spec[k - 1][0] == di and spec[k - 1][1] == 0  # adjacent to its primary, after it
             assert (x[4], x[5]) != (spec[k - 1][4], spec[k - 1][5])
+
+
+def test_empty_and_degenerate_inputs(infra):
+    """host entry points on empty batches, an invalid CFI, a subframe below the 6 dB gate and null pointers: defined results, no crash"""
+    L = capi.load_library()
+    capi._bind_search(L)
+    srch = capi.Search(100, 2, 1, 2)
+    dcis = np.zeros(8, capi.DCI_DTYPE)
+    nd = C.c_uint32(77)
+    info = (capi.SfInfo * 2)()
+    cands = np.zeros((2, capi.MAX_LOC, capi.MAX_SIZES), capi.CAND_DTYPE)
+    comp = np.zeros(2, capi.COMPACT_DTYPE)
+    assert L.ltephy_search_batch(srch.h, info, cands.ctypes.data_as(C.c_void_p), 0, dcis.ctypes.data_as(C.c_void_p), 8, C.byref(nd)) == 0 and nd.value == 0
+    assert L.ltephy_search_batch_compact(srch.h, info, comp.ctypes.data_as(C.c_void_p), None, 0, dcis.ctypes.data_as(C.c_void_p), 8, C.byref(nd)) == 0 and nd.value == 0
+    assert L.ltephy_search_batch(None, info, cands.ctypes.data_as(C.c_void_p), 1, dcis.ctypes.data_as(C.c_void_p), 8, C.byref(nd)) == -2
+    # cfi 0 / 4 and low SNR: the subframe is counted but nothing is walked (DCISearch.cc:569)
+    for cfi, snr in ((0, 20.0), (4, 20.0), (2, 5.9)):
+        info[0].cfi, info[0].snr_db, info[0].tti = cfi, snr, 3
+        before = srch.stats().nof_subframes
+        assert len(srch.subframe(info[0], cands[0])) == 0
+        c = srch.compact_from_table(info[0], cands[0])
+        assert len(srch.subframe_compact(info[0], c)) == 0
+        assert srch.stats().nof_subframes == before + 2
+        if cfi in (0, 4):
+            assert int(c["count"][0]) == 0 and not c["loc"]["mask"].any()
+    # an all-zero table at good SNR: every entry is "undecoded", nothing is accepted, statistics still advance
+    info[0].cfi, info[0].snr_db = 3, 20.0
+    for i in range(87):
+        info[0].cce_power[i] = 1.0
+    assert len(srch.subframe(info[0], cands[0])) == 0
+    # grants from no DCIs
+    grants = (capi.Grant * 4)()
+    gidx = np.zeros(4, np.uint32)
+    ng = C.c_uint32(9)
+    assert L.ltephy_grants_from_dcis(srch.h, info, dcis.ctypes.data_as(C.c_void_p), 0, 1, 0, grants, gidx.ctypes.data_as(C.c_void_p), 4, C.byref(ng)) == 0 and ng.value == 0
+    assert L.ltephy_grants_from_dcis(srch.h, info, dcis.ctypes.data_as(C.c_void_p), 0, 0, 0, grants, gidx.ctypes.data_as(C.c_void_p), 4, C.byref(ng)) == -2   # mod 0
+    # an all-zero DL DCI (RIV 0, MCS 0): converts or is rejected, but never crashes; format index out of range is rejected
+    row = np.zeros(1, capi.DCI_DTYPE)[0]
+    row["rnti"], row["format"], row["nof_bits"] = 0x1234, 2, 28
+    r, g, f = srch.dci_to_grant(row, 0, 2, 0)
+    assert r in (0, -1)
+    row["format"] = 9
+    r, g, f = srch.dci_to_grant(row, 0, 2, 0)
+    assert r != 0
