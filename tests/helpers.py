@@ -1,8 +1,7 @@
 """Shared helpers for the parity tests: run the CPU oracle over a capture, convert grants."""
-import ctypes as C
 import numpy as np
 import ltelib
-from ltelib import Cell, Sim, Oracle, FORMATS
+from ltelib import Sim
 from ltesniffer_b200 import capi
 
 

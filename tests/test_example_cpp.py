@@ -6,7 +6,6 @@ import struct
 import subprocess
 import numpy as np
 import pytest
-import ltelib
 from ltelib import Cell
 from helpers import make_capture
 from ltesniffer_b200 import capi

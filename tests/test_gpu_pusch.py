@@ -1,6 +1,5 @@
 """GPU parity of the PUSCH path (pytest -m gpu): UL OFDM demodulation and every PUSCH grant's channel estimate
 figures, transport-block bytes and CRC against the CPU oracle, bit-exact; ground truth from the synthetic UEs."""
-import ctypes as C
 import numpy as np
 import pytest
 import ltelib

@@ -6,7 +6,6 @@ pass with a RAR-activated RNTI forces the full-table fallback on both ranks."""
 import os
 import sys
 import numpy as np
-import pytest
 import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp

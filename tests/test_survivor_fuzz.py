@@ -20,7 +20,7 @@ def _locations(nof_cce):
     return out
 
 
-def _random_table(rng, L, srch_geo, nof_cce, sf_idx, pool, sizes_n):
+def _random_table(rng, L, nof_cce, sf_idx, pool, sizes_n):
     """-> CAND_DTYPE [MAX_LOC][MAX_SIZES] with structure"""
     T = np.zeros((capi.MAX_LOC, capi.MAX_SIZES), capi.CAND_DTYPE)
     locs = _locations(nof_cce)
@@ -87,7 +87,7 @@ def test_full_and_survivor_walks_agree_on_random_tables(infra, cellp, seed):
             for s in (full, comp):
                 L.ltephy_search_activate(s.h, rar, 0, 2)
             pool = np.append(pool, rar)
-        T = _random_table(rng, L, None, nof_cce, sf % 10, pool, sizes_n)
+        T = _random_table(rng, L, nof_cce, sf % 10, pool, sizes_n)
         a = full.subframe(info, T, max_out=256)
         cf = comp.compact_from_table(info, T)
         b = comp.subframe_compact(info, cf, max_out=256)
