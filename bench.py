@@ -412,6 +412,10 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    # nvidia-smi clocks / throttle reasons are sampled every 100 ms from here to the end of the device-resident timed region: the
+    # warm-up steps are the same load, and the timed region alone (~0.1 s) would yield a single sample
+    clk = ClockSampler(local)
+    clk.start()
     # ---------------- warm-up ----------------
     for _ in range(max(3, args.warmup)):
         if world > 1:
@@ -420,8 +424,6 @@ def main():
             run_steps(T, True)
     barrier()
     launches0 = sum(ph.launch_count() for ph in phys)
-    clk = ClockSampler(local)
-    clk.start()
     # ---------------- value: IQ resident in HBM ----------------
     turbo_ms, phase_a_ms, phase_b_ms = [], [], []
     host_ms = np.zeros(8)
