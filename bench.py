@@ -120,7 +120,8 @@ class ClockSampler:
         if self.p:
             self.p.terminate()
         sm, mx, reasons = [], [], set()
-        for r in self.rows:
+        rows = self.rows[1:] if len(self.rows) >= 3 else self.rows   # the first sample may predate the load (sampling starts just before the warm-up)
+        for r in rows:
             try:
                 sm.append(float(r[1]))
                 mx.append(float(r[2]))
