@@ -12,6 +12,7 @@
 #include <algorithm>
 #include <chrono>
 #include <condition_variable>
+#include <cstddef>
 #include <cstdio>
 #include <cstring>
 #include <mutex>
@@ -126,21 +127,31 @@ struct RntiManager {
   bool expired(uint16_t r) const { return !(rec[r].active && timestamp - rec[r].last_seen < LIFETIME); }
   bool validate(uint16_t r, uint32_t f)
   {
-    if (is_evergreen(r, f)) return true;
-    if (is_forbidden(r, f)) return false;
-    if (rec[r].active) {
-      if (!expired(r)) return true;
+    Rec& R = rec[r];
+    if ((R.ever >> f) & 1u) return true;
+    if ((R.forb >> f) & 1u) return false;
+    if (R.active) {
+      if (timestamp - R.last_seen < LIFETIME) return true;
       deactivate(r);
     }
-    // validateByHistogram
+    // validateByHistogram (RNTIManager.cc:335-365).  Most candidates that reach this point carry a chance RNTI that is in
+    // no histogram at all: likely = 0 and ul + dl = 0 <= threshold, whatever f is.
     uint32_t likely = 0, maxf = 0;
-    for (uint32_t i = 1; i < NF; i++)
-      if (hist[i].freq(r) > maxf) maxf = hist[i].freq(r), likely = i;
+    if (r) {
+      uint64_t a, b;
+      memcpy(&a, &R.cnt[0], 8), memcpy(&b, &R.cnt[4], 8);
+      if (!(a | b | R.cnt[8])) return false;
+      for (uint32_t i = 1; i < NF; i++)
+        if (R.cnt[i] > maxf) maxf = R.cnt[i], likely = i;
+    } else {
+      for (uint32_t i = 1; i < NF; i++)
+        if (hist[i].freq(r) > maxf) maxf = hist[i].freq(r), likely = i;
+    }
     if (f != 0 && f != likely) return false;
-    const uint32_t ul = hist[0].freq(r), dl = likely ? hist[likely].freq(r) : 0;
+    const uint32_t ul = hist[0].freq(r), dl = likely ? maxf : 0;
     if (ul + dl > threshold) {
       activate(r, ACT_HISTOGRAM);
-      rec[r].assoc = (uint8_t)(dl > threshold ? likely : 0);
+      R.assoc = (uint8_t)(dl > threshold ? likely : 0);
       return true;
     }
     return false;
@@ -205,12 +216,12 @@ uint32_t validate_location(uint32_t nof_cce, uint32_t ncce, uint32_t l, uint32_t
   return amb ? 1 : 2;
 }
 
-struct Cand {
-  uint64_t bits   = 0;
-  uint16_t rnti   = 0;
-  uint8_t  format = 0; // decoded format
-  uint8_t  ssm    = 0;
-  uint16_t nof_bits = 0;
+struct Cand { // no default initialisers: inspect() creates nine of them per visited location and clears only what it reads
+  uint64_t bits;
+  uint16_t rnti;
+  uint8_t  format; // decoded format
+  uint8_t  ssm;
+  uint16_t nof_bits;
 };
 typedef unsigned __int128 u128;
 struct Loc {
@@ -309,7 +320,7 @@ struct ltephy_search {
     const uint32_t       si = st.index_of[format];
     const ltephy_cand_t& t  = CT ? CT->list[CT->loc[li].off + (uint32_t)__builtin_popcount(CT->loc[li].mask & ((1u << si) - 1u))]
                                  : T[(size_t)li * LTEPHY_MAX_SIZES + si];
-    c                       = Cand{};
+    c.bits = 0, c.rnti = 0, c.format = 0, c.ssm = 0;
     c.nof_bits             = (uint16_t)st.sizes[st.index_of[format]];
     if (!t.valid) return; // all-zero LLRs: the reference leaves the calloc'ed candidate untouched
     c.bits = t.bits, c.rnti = t.rnti;
@@ -358,6 +369,7 @@ struct ltephy_search {
       return 0;
     }
     Cand     cand[NF];
+    for (uint32_t f = 0; f < nf; f++) cand[f].rnti = 0, cand[f].ssm = 0;
     int      best = -1;
     uint32_t best_val = 0, n_above = 0;
     if (CT && !(CT->loc[li].mask & pass_mask)) // no survivor in any column this pass looks at: every candidate ends as rnti = 0
@@ -1014,6 +1026,14 @@ int ltephy_search_batch_compact(ltephy_search_t* s, const ltephy_sf_info_t* info
   uint32_t nd = 0;
   for (uint32_t i = 0; i < n; i++) {
     uint32_t k = 0;
+    if (i + 2 < n) __builtin_prefetch(&comp[i + 2], 0, 3), __builtin_prefetch(&info[i + 2], 0, 3);
+    if (i + 1 < n) { // the inputs stream through once: have the next subframe's records in cache when its walk starts
+      const char*    c  = reinterpret_cast<const char*>(&comp[i + 1]);
+      const uint32_t nb = (uint32_t)offsetof(ltephy_compact_t, list) + 16u * std::min<uint32_t>(comp[i + 1].count, LTEPHY_COMPACT_CAP);
+      for (uint32_t o = 64; o < nb; o += 64) __builtin_prefetch(c + o, 0, 3);
+      const char* f = reinterpret_cast<const char*>(&info[i + 1]);
+      for (uint32_t o = 0; o < sizeof(ltephy_sf_info_t); o += 64) __builtin_prefetch(f + o, 0, 3);
+    }
     int      r = s->search_subframe(info[i], nullptr, &comp[i], i, dcis + nd, max_dcis - nd, &k);
     if (r == LTEPHY_NEED_FULL_TABLE) r = s->search_subframe(info[i], full + (size_t)i * LTEPHY_MAX_LOC * LTEPHY_MAX_SIZES, nullptr, i, dcis + nd, max_dcis - nd, &k);
     if (r < 0) return r;
