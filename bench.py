@@ -252,7 +252,7 @@ def main():
     tti = (np.arange(B, dtype=np.uint32) * world + rank).astype(np.uint32)
     tti_local = (np.arange(B, dtype=np.uint32) % len(iq_u)).astype(np.uint32)  # the tti each subframe was generated for
 
-    T = 3 if world > 1 else max(1, args.pipelines)
+    T = max(1, args.pipelines)
     phys = [capi.LtePhy(cell.nof_prb, cell.nof_ports, cell.cell_id, cell.nof_rx, max_subframes=B, turbo_max_iter=8, device=local,
                         flags=capi.FLAG_SKIP_LOW_POWER) for _ in range(T)]
     phy = phys[0]
@@ -305,91 +305,38 @@ def main():
     def step_single(device_resident):
         run_steps(1, device_resident)
 
-    # ---- sharded operation (N > 1): subframe g -> GPU g mod N.  Phase A local; candidate tables all-gathered and
-    # re-interleaved into global order; the walk is replayed over ALL subframes on every rank (its RNTI history is
-    # sequential by nature); phase B for the owned subframes; one gather of the decoded TBs to rank 0.
-    # Software pipeline over 3 handles in ONE thread (one communicator): A(k+1) and B(k-1) run while the host walks k.
-    TB_DTYPE = np.dtype({"names": ["crc", "avg_iters", "nof_cb", "payload_off", "payload_len"], "formats": ["u1", "u1", "<u2", "<u4", "<u4"],
-                         "offsets": [0, 1, 2, 4, 8], "itemsize": C.sizeof(capi.TbResult)})
+    # ---- sharded operation (N > 1): subframe g -> GPU g mod N, through the library's own entry point
+    # ltephy_decode_subframes_sharded (include/ltephy_shard.h): phase A local; packed survivor forms all-gathered over NCCL; the
+    # walk replayed on every rank; phase B local; one NCCL gather of the decoded transport blocks to rank 0.  T host threads,
+    # one PHY handle each (thread t takes batches t, t+T, ...); the library orders the exchange / walk / gather sections by seq.
+    sh = None
+    sh_seq = [0]
+    sh_stats = []          # (seq, ShardStats) of every batch of the last run_sharded call
     if world > 1:
-        from ltesniffer_b200 import shard
-        gather_sz = B * 20000
-        out_local = torch.zeros(gather_sz, dtype=torch.uint8, device="cuda")
-        out_all = [torch.zeros(gather_sz, dtype=torch.uint8, device="cuda") for _ in range(world)] if rank == 0 else None
-        res = [(capi.TbResult * (2 * 24 * B))() for _ in range(T)]
-        ngr = [0] * T
-
-    def sh_submit_a(t, device_resident):
-        if device_resident:
-            phys[t]._chk(L.ltephy_submit_iq_device(phys[t].h, p(iq_dev), tti_c.ctypes.data_as(C.c_void_p), B), "submit_iq_device")
-        else:
-            phys[t]._chk(L.ltephy_submit_iq(phys[t].h, p(iq_pin), tti_c.ctypes.data_as(C.c_void_p), B), "submit_iq")
-        phys[t].n = B
-
-    def sh_gather_tbs(t):
-        nb = C.c_size_t(0)
-        phys[t]._chk(L.ltephy_copy_phase_b_device(phys[t].h, p(out_local), gather_sz, C.byref(nb)), "copy_phase_b_device")
-        dist.gather(out_local, out_all, dst=0)   # the single gather of decoded transport blocks (device to device over NVLink)
-
-    # T host threads, one PHY handle each (thread t takes batches t, t+T, ...).  Two turn-taking sections, each entered in
-    # batch order, so that every rank issues the same sequence of collectives on the one communicator while the walk of
-    # batch k overlaps the exchange of batch k+1:
-    #   exchange turn k: [gather of the transport blocks of batch k-T, decoded by this thread one round earlier]
-    #                    all-gather of batch k's survivor forms (and of the full tables if the walk may need them)
-    #   walk turn k:     FALCON walk over all N*B subframes -> this rank's grants (no collective inside)
-    # Phase A of batches k+1.. and phase B of k-1.. run on the GPU meanwhile.
-    turn = threading.Condition()
-    sh_next = [0, 0]     # next batch allowed into the exchange turn / the walk turn
-    sh_base = [0]
-    wbufs = [shard.WalkBuffers(max_dcis, 24 * B) for _ in range(T)] if world > 1 else None
+        uid = [capi.Shard.unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        sh = capi.Shard(uid[0], rank, world, local)
+        sh_payload = [torch.empty(B * 24000 * (world if rank == 0 else 1) + (1 << 20), dtype=torch.uint8, pin_memory=True) for _ in range(T)]
 
     def run_sharded(nsteps, device_resident):
-        base = sh_base[0]
-        sh_base[0] += nsteps
-        pend = [False] * T
+        base = sh_seq[0]
+        sh_seq[0] += nsteps
+        del sh_stats[:]
         errs = []
-
-        def take(which, k):
-            with turn:
-                turn.wait_for(lambda: sh_next[which] == base + k or errs)
-            return not errs
-
-        def give(which):
-            with turn:
-                sh_next[which] += 1
-                turn.notify_all()
+        src = p(iq_dev) if device_resident else p(iq_pin)
 
         def worker(t):
-            try:
-                torch.cuda.set_device(local)
-                for k in range(t, nsteps, T):
-                    sh_submit_a(t, device_resident)
-                    S = scr[t]
-                    phys[t]._chk(L.ltephy_get_phase_a(phys[t].h, S.info, None), "get_phase_a")   # waits for phase A; the handle keeps cfi/tti
-                    if not take(0, k):
-                        return
-                    if pend[t]:
-                        sh_gather_tbs(t)
-                        pend[t] = False
-                    info_all, comp_all = shard.gather_tables_device(L, phys[t].h, B, world, cell.nof_ports, cell.nof_rx, slot=t)
-                    full = None
-                    if shard.need_full_tables(L, srch, comp_all, B * world):   # never on this workload
-                        phys[t]._chk(L.ltephy_get_phase_a(phys[t].h, None, p(S.cands)), "get_phase_a")
-                        full = shard.gather_full_tables(S.cands, world, "cuda", slot=t)
-                    give(0)
-                    if not take(1, k):
-                        return
-                    d, grants, gidx, ng = shard.search_and_select(L, srch, info_all, comp_all, world, rank, max_dcis, 24 * B, full=full, bufs=wbufs[t])
-                    nd.value = len(d)
-                    give(1)
-                    phys[t]._chk(L.ltephy_submit_grants(phys[t].h, grants, ng), "submit_grants")
-                    ngr[t] = ng
-                    phys[t]._chk(L.ltephy_get_phase_b(phys[t].h, res[t], p(scr[t].payload), scr[t].payload.numel()), "get_phase_b")
-                    pend[t] = True
-            except BaseException as e:     # never leave the other threads waiting for a turn that will not come
-                with turn:
-                    errs.append(e)
-                    turn.notify_all()
+            torch.cuda.set_device(local)
+            for k in range(t, nsteps, T):
+                S = scr[t]
+                st = capi.ShardStats()
+                r = L.ltephy_decode_subframes_sharded(sh.h, phys[t].h, srch.h, src, 1 if device_resident else 0, tti_c.ctypes.data_as(C.c_void_p), B,
+                                                      base + k, S.info, S.dcis.ctypes.data_as(C.c_void_p), max_dcis, C.byref(S.nd), S.tbs,
+                                                      p(sh_payload[t]), sh_payload[t].numel(), C.byref(st))
+                if r != 0:
+                    errs.append(RuntimeError("decode_subframes_sharded failed: %s" % L.ltephy_last_error().decode()))
+                    return
+                sh_stats.append((base + k, t, st))
         if T == 1 or nsteps == 1:
             worker(0)
         else:
@@ -397,10 +344,6 @@ def main():
                 list(ex.map(worker, range(T)))
         if errs:
             raise errs[0]
-        for k in range(max(0, nsteps - T), nsteps):      # transport blocks of the last round, same order on every rank
-            if pend[k % T]:
-                sh_gather_tbs(k % T)
-                pend[k % T] = False
 
     def step_sharded(device_resident):
         run_sharded(1, device_resident)
@@ -453,9 +396,24 @@ def main():
     if world > 1:
         dist.all_reduce(t_val, op=dist.ReduceOp.MAX)
     dev_ms = float(t_val.item())
-    tbv = np.frombuffer(tbs, dtype=TB_DTYPE, count=2 * nd.value) if world == 1 else None
-    tb_ok = int(tbv["crc"].sum()) if world == 1 else None
-    ntb = int((tbv["payload_len"] > 0).sum()) if world == 1 else None
+    def tb_counts(S):
+        """CRC-ok / total transport blocks of the last batch decoded into scratch S; at N > 1 rank 0 holds the gathered blocks of
+        every rank, and (all ranks decode the same capture) must see exactly N times what its own subframes yield"""
+        ndv = S.nd.value
+        tbv = np.frombuffer(S.tbs, dtype=TB_DTYPE, count=2 * ndv)
+        ok = np.repeat(S.dcis["sf"][:ndv] % world == 0, 2)
+        return int((tbv["crc"] > 0).sum()), int((tbv["payload_len"] > 0).sum()), int(((tbv["crc"] > 0) & ok).sum())
+
+    def shard_host_ms():
+        if not sh_stats:
+            return None
+        m = np.mean([[st.host_ms[i] for i in range(8)] for _, _, st in sh_stats], axis=0)
+        d = dict(zip(capi.SHARD_HOST_MS, [round(float(x), 3) for x in m]))
+        d["exchanged_bytes_per_step"] = int(np.mean([st.exchanged_bytes for _, _, st in sh_stats]))
+        d["full_table_fallbacks"] = int(sum(st.used_full_table for _, _, st in sh_stats))
+        return d
+    tb_ok, ntb, tb_ok_own = tb_counts(scr[0])
+    sh_host_value = shard_host_ms() if world > 1 else None
     tbytes, ncb, info_bits = phy.turbo_work()
     # ---------------- e2e: host IQ through the C-ABI ----------------
     if world > 1:
@@ -478,7 +436,8 @@ def main():
     e2e_pb = float(np.mean([ph.timing()[1] for ph in phys]))
     hm2 = np.zeros(8)
     L.ltephy_last_host_timing(hm2.ctypes.data_as(C.c_void_p))
-    e2e_tb_ok = int(np.frombuffer(tbs, dtype=TB_DTYPE, count=2 * nd.value)["crc"].sum()) if world == 1 else None   # same count as the device-resident run
+    e2e_tb_ok = tb_counts(scr[0])[0]    # same count as the device-resident run
+    sh_host_e2e = shard_host_ms() if world > 1 else None
     d2h = B * (C.sizeof(capi.SfInfo) + capi.COMPACT_DTYPE.itemsize) + int(info_bits // 8) + 12 * 2 * 24 * B // 8
 
     # ---------------- roofline of the dominant kernel (turbo decoder) ----------------
@@ -522,20 +481,24 @@ def main():
                "data": "synthetic",
                "config": {"workload": WORKLOAD, "subframes_per_step_per_gpu": B, "pipelines": T, "unique_subframes": len(iq_u), "turbo_max_iter": 8,
                           "cache_note": "inputs larger than L2: %.0f MB of IQ per step per GPU" % (iq_pin.numel() * 4 / 1e6),
-                          "sharding": "subframe g -> GPU g mod N; all-gather of the survivor forms of the candidate tables; walk replayed on every rank; one gather of TBs" if world > 1 else "single GPU",
-                          "tb_crc_ok": tb_ok, "tb_total": ntb, "dcis_per_step": int(nd.value)},
+                          "sharding": "ltephy_decode_subframes_sharded: subframe g -> GPU g mod N; NCCL all-gather of the packed survivor forms; walk replayed on every rank; one NCCL gather of the decoded TBs to rank 0" if world > 1 else "single GPU",
+                          "tb_crc_ok": tb_ok, "tb_total": ntb, "tb_crc_ok_own_subframes": tb_ok_own,
+                          "tb_check": "gathered CRC-ok count == N x rank 0's own" if tb_ok == world * tb_ok_own else "MISMATCH: %d != %d x %d" % (tb_ok, world, tb_ok_own),
+                          "dcis_per_step": int(nd.value)},
                "wall_ms_per_step": wall_ms / args.steps, "phase_a_ms": float(np.mean(phase_a_ms)), "phase_b_ms": float(np.mean(phase_b_ms)),
-               "host_ms": dict(zip(["submit_a", "wait_a", "search", "grants", "submit_b", "wait_b"], [round(float(x), 3) for x in host_ms[:6]])),
+               "host_ms": sh_host_value if world > 1 else dict(zip(["submit_a", "wait_a", "search", "grants", "submit_b", "wait_b"], [round(float(x), 3) for x in host_ms[:6]])),
                "e2e": {"value": B * world * args.steps / (e2e_ms * 1e-3), "unit": "subframes/s",
                        "h2d_bytes_per_step": int(iq_pin.numel() * 4 + B * 4), "d2h_bytes_per_step": int(d2h),
                        "ms_per_step": e2e_ms / args.steps, "tb_crc_ok": e2e_tb_ok, "h2d_plus_phase_a_ms": e2e_pa, "phase_b_ms": e2e_pb,
-                       "host_ms": dict(zip(["submit_a", "wait_a", "search", "grants", "submit_b", "wait_b"], [round(float(x), 3) for x in hm2[:6]]))},
+                       "host_ms": sh_host_e2e if world > 1 else dict(zip(["submit_a", "wait_a", "search", "grants", "submit_b", "wait_b"], [round(float(x), 3) for x in hm2[:6]]))},
                "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline}
 
     if rank == 0 and cpu_base is not None:
         out["cpu_baseline"] = cpu_base
     if rank == 0:
         emit_json(out)
+    if sh is not None:
+        sh.close()
     for ph in phys:
         ph.close()
     if world > 1:

@@ -92,7 +92,7 @@ int main(int argc, char** argv)
       for (int sl = 0; sl < 2; sl++)
         for (uint32_t prb = 0; prb < cell.nof_prb; prb++) s.prb_idx[sl][prb] = (r.g.prb_mask[sl][prb >> 5] >> (prb & 31)) & 1u, s.nof_prb += sl == 0 && s.prb_idx[sl][prb];
       for (int t = 0; t < 2; t++) {
-        s.tb[t].enabled = r.g.tb[t].enabled, s.tb[t].tbs = r.g.tb[t].tbs, s.tb[t].rv = r.g.tb[t].rv;
+        s.tb[t].enabled = r.g.tb[t].enabled, s.tb[t].tbs = r.g.tb[t].tbs, s.tb[t].rv = r.g.tb[t].rv, s.tb[t].cw_idx = r.g.tb[t].cw_idx;
         s.tb[t].mod = r.g.tb[t].qm == 2 ? SRSRAN_MOD_QPSK : r.g.tb[t].qm == 4 ? SRSRAN_MOD_16QAM : r.g.tb[t].qm == 6 ? SRSRAN_MOD_64QAM : SRSRAN_MOD_256QAM;
       }
       std::vector<uint8_t> pl0(16000), pl1(16000); // srsran_vec_u8_malloc(2000 * 8), DL_Sniffer_PDSCH.cc:47

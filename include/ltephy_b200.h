@@ -120,7 +120,8 @@ typedef struct {
     uint8_t qm;             /* 2,4,6,8 */
     uint8_t rv;
     uint8_t enabled;
-    uint8_t pad;
+    uint8_t cw_idx;         /* srsran_ra_tb_t.cw_idx (dl_sniffer_pdsch.c:24): codeword this TB travels on -- 1 for TB 1 and 0 for TB 2 when both are
+                               enabled and the DCI 2/2A swap flag is set, otherwise the TB's rank among the enabled ones */
   } tb[2];
 } ltephy_grant_t;
 

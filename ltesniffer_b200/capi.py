@@ -32,7 +32,7 @@ class Cand(C.Structure):
 
 
 class GrantTb(C.Structure):
-    _fields_ = [("tbs", C.c_int32), ("qm", C.c_uint8), ("rv", C.c_uint8), ("enabled", C.c_uint8), ("pad", C.c_uint8)]
+    _fields_ = [("tbs", C.c_int32), ("qm", C.c_uint8), ("rv", C.c_uint8), ("enabled", C.c_uint8), ("cw_idx", C.c_uint8)]
 
 
 class Grant(C.Structure):
@@ -340,6 +340,18 @@ def _bind_search(L):
     L.ltephy_decode_subframes_device.argtypes = [P, P, P, P, C.c_uint32, C.c_uint64, P, P, P, C.c_uint32, P, P, P, C.c_size_t]
     L.ltephy_search_batch.argtypes = [P, P, P, C.c_uint32, P, C.c_uint32, P]
     L.ltephy_grants_from_dcis.argtypes = [P, P, P, C.c_uint32, C.c_uint32, C.c_uint32, P, P, C.c_uint32, P]
+    # sharded operation (include/ltephy_shard.h)
+    L.ltephy_packed_size.argtypes = [C.c_uint32, C.c_uint32]
+    L.ltephy_packed_size.restype = C.c_size_t
+    L.ltephy_pack_subframes.argtypes = [P, P, P, C.c_uint32, P, C.c_size_t, P]
+    L.ltephy_search_batch_packed.argtypes = [P, P, P, P, C.c_uint32, C.c_uint32, P, C.c_uint32, P, P]
+    L.ltephy_packed_needs_full_table.argtypes = [P, P, P, C.c_uint32, C.c_uint32]
+    L.ltephy_grants_from_dcis_tc.argtypes = [P, P, P, C.c_uint32, C.c_uint32, C.c_uint32, P, P, C.c_uint32, P]
+    L.ltephy_shard_unique_id.argtypes = [P]
+    L.ltephy_shard_create.argtypes = [P, C.c_uint32, C.c_uint32, C.c_int, C.POINTER(P)]
+    L.ltephy_shard_destroy.argtypes = [P]
+    L.ltephy_decode_subframes_sharded.argtypes = [P, P, P, P, C.c_int, P, C.c_uint32, C.c_uint64, P, P, C.c_uint32, P, P, P, C.c_size_t, P]
+    L.ltephy_pack_phase_a.argtypes = [P, P, C.c_size_t, P]
     L._search_bound = True
 
 
@@ -439,3 +451,87 @@ def decode_subframes(phy, search, iq, tti, seq=SEQ_NONE, max_dcis=None, scratch=
         raise RuntimeError("ltephy_decode_subframes failed (%d): %s" % (r, L.ltephy_last_error().decode()))
     phy.n = n
     return scratch["info"], scratch["dcis"][:nd.value], scratch["tbs"], scratch["payload"]
+
+
+# ------------------------------------------------------------------------------------------------
+# sharded operation (include/ltephy_shard.h)
+SHARD_ID_BYTES = 256
+PACK_MAX_BYTES = 64 + 4 * MAX_LOC + 16 * COMPACT_CAP
+PACKED_HDR_DTYPE = np.dtype([("count", "<u4"), ("tti", "<u4"), ("cfi", "<u4"), ("nloc", "<u4"), ("noise", "<f4", (2, 2)), ("rsrp", "<f4", (2, 2)),
+                             ("low", "<u8", 2)])
+assert PACKED_HDR_DTYPE.itemsize == 64
+
+
+class ShardStats(C.Structure):
+    _fields_ = [("host_ms", C.c_double * 8), ("exchanged_bytes", C.c_uint64), ("n_grants", C.c_uint32), ("used_full_table", C.c_uint32)]
+
+
+SHARD_HOST_MS = ["submit_a", "wait_a", "exchange_turn", "walk_wait", "walk", "grants", "phase_b", "gather_turn"]
+
+
+def pack_subframes(search, info, comp):
+    """host restatement of the GPU pack kernel: (SfInfo * n), COMPACT_DTYPE[n] -> (uint8 records, uint32 offsets[n + 1])"""
+    n = len(comp)
+    out = np.zeros(n * PACK_MAX_BYTES, np.uint8)
+    offs = np.zeros(n + 1, np.uint32)
+    comp = np.ascontiguousarray(comp)
+    r = search.L.ltephy_pack_subframes(search.h, info, _p(comp), n, _p(out), out.nbytes, _p(offs))
+    if r != 0:
+        raise RuntimeError("ltephy_pack_subframes failed (%d)" % r)
+    return out[:offs[n]].copy(), offs
+
+
+def search_batch_packed(search, bufs, offs, n, max_dcis, full=None):
+    """walk turn of a sharded batch: bufs[r] uint8 records / offs[r] uint32[n + 1] of every rank ->
+    (dcis (sf = global index), tti_cfi uint32 [n * world][2]); None when the full tables are needed and were not given"""
+    world = len(bufs)
+    bp = (C.c_void_p * world)(*[b.ctypes.data for b in bufs])
+    op = (C.c_void_p * world)(*[o.ctypes.data for o in offs])
+    fp = (C.c_void_p * world)(*[f.ctypes.data for f in full]) if full is not None else None
+    dcis = np.zeros(max_dcis, DCI_DTYPE)
+    tc = np.zeros((n * world, 2), np.uint32)
+    nd = C.c_uint32(0)
+    r = search.L.ltephy_search_batch_packed(search.h, bp, op, fp, world, n, _p(dcis), max_dcis, C.byref(nd), _p(tc))
+    if r == NEED_FULL_TABLE:
+        return None
+    if r != 0:
+        raise RuntimeError("ltephy_search_batch_packed failed (%d)" % r)
+    return dcis[:nd.value].copy(), tc
+
+
+class Shard:
+    """NCCL communicators + ordered sections of the sharded pipeline (one per process / GPU)."""
+
+    @staticmethod
+    def unique_id():
+        L = load_library()
+        _bind_search(L)
+        buf = (C.c_uint8 * SHARD_ID_BYTES)()
+        if L.ltephy_shard_unique_id(buf) != 0:
+            raise RuntimeError("ltephy_shard_unique_id failed: %s" % L.ltephy_last_error().decode())
+        return bytes(buf)
+
+    def __init__(self, uid, rank, world, device):
+        self.L = load_library()
+        _bind_search(self.L)
+        self.h = C.c_void_p()
+        buf = (C.c_uint8 * SHARD_ID_BYTES).from_buffer_copy(uid)
+        r = self.L.ltephy_shard_create(buf, rank, world, device, C.byref(self.h))
+        if r != 0:
+            raise RuntimeError("ltephy_shard_create failed (%d): %s" % (r, self.L.ltephy_last_error().decode()))
+        self.rank, self.world = rank, world
+
+    def close(self):
+        if self.h:
+            self.L.ltephy_shard_destroy(self.h)
+            self.h = None
+
+
+def pack_phase_a(phy):
+    """GPU pack kernel over the current batch of phy -> (uint8 records, uint32 offsets[n + 1])"""
+    n = phy.n
+    out = np.zeros(n * PACK_MAX_BYTES, np.uint8)
+    offs = np.zeros(n + 1, np.uint32)
+    _bind_search(phy.L)
+    phy._chk(phy.L.ltephy_pack_phase_a(phy.h, _p(out), out.nbytes, _p(offs)), "pack_phase_a")
+    return out[:offs[n]].copy(), offs

@@ -7,10 +7,13 @@
 //   dl_sniffer_pdsch.c:14-276 (DCI -> grant).  Integer control flow only: the GPU never sees this state.
 #include "../../include/ltephy_b200.h"
 #include "../../include/ltephy_sinks.h"
+#include "../../include/ltephy_shard.h"
 #include "../../include/lte_tables.h"
 #include "lte_host.hpp"
+#include "tb_merge.hpp"
 #include <algorithm>
 #include <chrono>
+#include <cmath>
 #include <condition_variable>
 #include <cstddef>
 #include <cstdio>
@@ -258,7 +261,8 @@ struct ltephy_search {
   ltephy_search_stats_t stats{};
   // per-subframe scratch
   const ltephy_cand_t*    T  = nullptr;
-  const ltephy_compact_t* CT = nullptr; // survivor form (then T is null)
+  const ltephy_cloc_t*    CL = nullptr; // survivor form (then T is null): per-location records ...
+  const ltephy_cand_t*    CLIST = nullptr; // ... and the survivor list (ltephy_compact_t, or a packed record of ltephy_shard.h)
   uint32_t                sf_idx = 0, ncce_sf = 0, sf_batch = 0, pass_mask = 0;
   // Location state of the subframe being walked, as bit masks in CCE space: location (L, ncce) is bit ncce of the level-L
   // masks (only multiples of 2^L are meaningful there).
@@ -318,13 +322,13 @@ struct ltephy_search {
   inline void fetch(uint32_t li, uint32_t format, Cand& c) const
   {
     const uint32_t       si = st.index_of[format];
-    const ltephy_cand_t& t  = CT ? CT->list[CT->loc[li].off + (uint32_t)__builtin_popcount(CT->loc[li].mask & ((1u << si) - 1u))]
+    const ltephy_cand_t& t  = CL ? CLIST[CL[li].off + (uint32_t)__builtin_popcount(CL[li].mask & ((1u << si) - 1u))]
                                  : T[(size_t)li * LTEPHY_MAX_SIZES + si];
     c.bits = 0, c.rnti = 0, c.format = 0, c.ssm = 0;
     c.nof_bits             = (uint16_t)st.sizes[st.index_of[format]];
     if (!t.valid) return; // all-zero LLRs: the reference leaves the calloc'ed candidate untouched
     c.bits = t.bits, c.rnti = t.rnti;
-    if (CT) c.ssm = t.pad[0] & 3u;
+    if (CL) c.ssm = t.pad[0] & 3u;
     if (format == ltehost::F0 || format == ltehost::F1A)
       c.format = (t.bits >> 63) ? ltehost::F1A : ltehost::F0;
     else
@@ -364,7 +368,7 @@ struct ltephy_search {
   {
     if (!((uint64_t)(val[L] >> ncce) & 1u) || skip(ncce, L)) return 0;
     const uint32_t li = loc_index(ncce, L);
-    if (CT && !(CT->loc[li].pad & pass_mask)) { // pad = union of the survivor masks over the subtree
+    if (CL && !(CL[li].pad & pass_mask)) { // pad = union of the survivor masks over the subtree
       stats.nof_decoded_locations += nf * sweep_empty(ncce, L, max_depth);
       return 0;
     }
@@ -372,13 +376,13 @@ struct ltephy_search {
     for (uint32_t f = 0; f < nf; f++) cand[f].rnti = 0, cand[f].ssm = 0;
     int      best = -1;
     uint32_t best_val = 0, n_above = 0;
-    if (CT && !(CT->loc[li].mask & pass_mask)) // no survivor in any column this pass looks at: every candidate ends as rnti = 0
+    if (CL && !(CL[li].mask & pass_mask)) // no survivor in any column this pass looks at: every candidate ends as rnti = 0
       stats.nof_decoded_locations += nf;
     else
     for (uint32_t f = 0; f < nf; f++) {
       const uint32_t fmt = mf[f];
       stats.nof_decoded_locations++;
-      if (CT && !((CT->loc[li].mask >> st.index_of[fmt]) & 1u)) continue; // not a survivor: every path below ends in rnti = 0
+      if (CL && !((CL[li].mask >> st.index_of[fmt]) & 1u)) continue; // not a survivor: every path below ends in rnti = 0
       fetch((uint32_t)li, fmt, cand[f]);
       if (rm.rec[cand[f].rnti].reason == ACT_RAR && cand[f].format == 0) {
         bool add = true;
@@ -400,7 +404,7 @@ struct ltephy_search {
         continue;
       }
       if (shortcut && discovery && parent && parent[f].rnti == r && !rm.is_forbidden(r, fmt)) return -((int)f + 1);
-      cand[f].ssm = CT ? cand[f].ssm : (uint8_t)validate_location(ncce_sf, ncce, L, sf_idx, r); // the survivor form carries it
+      cand[f].ssm = CL ? cand[f].ssm : (uint8_t)validate_location(ncce_sf, ncce, L, sf_idx, r); // the survivor form carries it
       if (cand[f].ssm == 0) {
         cand[f].rnti = 0;
         continue;
@@ -466,15 +470,38 @@ struct ltephy_search {
     }
     return 0;
   }
+  // What the walk needs to know about one subframe: either the full table, or the survivor form (loc + list).
+  struct WalkIn {
+    uint32_t             tti, cfi;
+    float                snr_db;
+    uint64_t             low[2]; // bit c: CCE c has mean |LLR| < 0.7 (DCISearch.cc:473-489), c < min(nof_cce, 84)
+    uint32_t             count;  // survivors (survivor form only)
+    const ltephy_cand_t* table;
+    const ltephy_cloc_t* loc;
+    const ltephy_cand_t* list;
+  };
+  WalkIn walk_in(const ltephy_sf_info_t& info, const ltephy_cand_t* table, const ltephy_compact_t* comp) const
+  {
+    WalkIn w{info.tti, info.cfi, info.snr_db, {0, 0}, comp ? comp->count : 0, table, comp ? comp->loc : nullptr, comp ? comp->list : nullptr};
+    if (info.cfi >= 1 && info.cfi <= 3) {
+      const uint32_t lim = std::min<uint32_t>(nof_cce[info.cfi - 1], LTEPHY_SEARCH_MAX_CCE);
+      for (uint32_t c = 0; c < lim; c++) w.low[c >> 6] |= (uint64_t)(info.cce_power[c] < 0.7f) << (c & 63u);
+    }
+    return w;
+  }
   // exactly one of table / comp is given.  The survivor form cannot serve a walk that has RAR-activated RNTIs (the
   // temp_dci0 rule looks at every format-0 candidate) nor a truncated list: LTEPHY_NEED_FULL_TABLE, nothing consumed.
   int search_subframe(const ltephy_sf_info_t& info, const ltephy_cand_t* table, const ltephy_compact_t* comp, uint32_t sf_in_batch, ltephy_dci_t* o,
                       uint32_t cap, uint32_t* n)
   {
-    if (comp && (rm.n_rar || comp->count > LTEPHY_COMPACT_CAP)) return LTEPHY_NEED_FULL_TABLE;
+    return search_subframe(walk_in(info, table, comp), sf_in_batch, o, cap, n);
+  }
+  int search_subframe(const WalkIn& info, uint32_t sf_in_batch, ltephy_dci_t* o, uint32_t cap, uint32_t* n)
+  {
+    if (info.loc && (rm.n_rar || info.count > LTEPHY_COMPACT_CAP)) return LTEPHY_NEED_FULL_TABLE;
     if (update_interval && (sf_cnt % update_interval) == 0) update_formats();
     sf_cnt++;
-    out = o, out_cap = cap, out_n = 0, sf_batch = sf_in_batch, T = table, CT = comp;
+    out = o, out_cap = cap, out_n = 0, sf_batch = sf_in_batch, T = info.table, CL = info.loc, CLIST = info.list;
     int ret = LTEPHY_ERROR;
     if (info.snr_db > 6.0f && info.cfi >= 1 && info.cfi <= 3) {
       temp_dci0.clear();
@@ -484,10 +511,7 @@ struct ltephy_search {
       const uint32_t lim = std::min<uint32_t>(ncce_sf, LTEPHY_SEARCH_MAX_CCE);
       const uint32_t k   = tmpl[info.cfi - 1].n;
       stats.nof_locations += k;
-      uint64_t low_lo = 0, low_hi = 0;
-      for (uint32_t c = 0; c < std::min<uint32_t>(lim, 64); c++) low_lo |= (uint64_t)(info.cce_power[c] < 0.7f) << c;
-      for (uint32_t c = 64; c < lim; c++) low_hi |= (uint64_t)(info.cce_power[c] < 0.7f) << (c - 64);
-      low = ((u128)low_hi << 64) | low_lo, occ = 0;
+      low = ((u128)info.low[1] << 64) | info.low[0], occ = 0;
       refold();
       for (uint32_t l = 0; l < 4; l++) nq[l] = tmpl[info.cfi - 1].nq[l], val[l] = tmpl[info.cfi - 1].val[l];
       ret = 0;
@@ -696,8 +720,12 @@ int ltephy_dci_to_grant(const ltephy_search_t* s, const ltephy_dci_t* d, uint32_
   if (d->format == ltehost::F1A || !user_rnti(d->rnti)) alt = false;
   for (int i = 0; i < 2; i++) {
     g->tb[i].rv = f.rv[i];
-    if ((tb_en[i] && d->format >= ltehost::F2) || (d->format < ltehost::F2 && i == 0)) g->tb[i].enabled = 1, g->nof_tb++;
+    if ((tb_en[i] && d->format >= ltehost::F2) || (d->format < ltehost::F2 && i == 0)) g->tb[i].enabled = 1, g->tb[i].cw_idx = g->nof_tb, g->nof_tb++;
   }
+  // transport block to codeword swap flag (36.212 Table 5.3.3.1.5-1): with both TBs enabled, TB1 -> codeword 1 and TB2 -> codeword 0;
+  // with one TB disabled the other one always maps to codeword 0 (Table 5.3.3.1.5-2).  srsRAN carries this as tb[i].cw_idx
+  // (dl_sniffer_pdsch.c:24) into scrambling (q << 13) and layer mapping.
+  if (g->nof_tb == 2 && f.tb_cw_swap) g->tb[0].cw_idx = 1, g->tb[1].cw_idx = 0;
   if (!user_rnti(d->rnti)) {
     int tbs;
     if (d->format == ltehost::F1A)
@@ -909,13 +937,19 @@ void ltephy_search_config(ltephy_search_t* s, int shortcut, int skip_secondary, 
 }
 void ltephy_search_add_evergreen(ltephy_search_t* s, uint16_t a, uint16_t b, uint32_t f)
 {
+  std::lock_guard<std::mutex> lk(s->mtx);
   if (f < NF && a <= b) s->rm.add_evergreen(a, b, f);
 }
 void ltephy_search_add_forbidden(ltephy_search_t* s, uint16_t a, uint16_t b, uint32_t f)
 {
+  std::lock_guard<std::mutex> lk(s->mtx);
   if (f < NF && a <= b) s->rm.add_forbidden(a, b, f);
 }
-void ltephy_search_activate(ltephy_search_t* s, uint16_t rnti, uint32_t format_idx, int reason) { s->rm.activate_and_refresh(rnti, format_idx, (uint8_t)reason); }
+void ltephy_search_activate(ltephy_search_t* s, uint16_t rnti, uint32_t format_idx, int reason)
+{
+  std::lock_guard<std::mutex> lk(s->mtx); // another pipeline thread may be inside the walk
+  s->rm.activate_and_refresh(rnti, format_idx, (uint8_t)reason);
+}
 int  ltephy_search_subframe(ltephy_search_t* s, const ltephy_sf_info_t* info, const ltephy_cand_t* cands, uint32_t sf_in_batch, ltephy_dci_t* out,
                             uint32_t max_out, uint32_t* n_out)
 {
@@ -1052,10 +1086,11 @@ int ltephy_search_needs_full_table(const ltephy_search_t* s, const ltephy_compac
 }
 // Accepted DL DCIs -> PDSCH grants, applying decode_dl_mode's skip rule (src/src/DL_Sniffer_PDSCH.cc:887-889).
 // Only subframes with sf % mod == rem are taken (multi-GPU sharding); grant.sf = sf / mod (local index).
-int ltephy_grants_from_dcis(const ltephy_search_t* s, const ltephy_sf_info_t* info, const ltephy_dci_t* dcis, uint32_t nd, uint32_t mod, uint32_t rem,
-                            ltephy_grant_t* grants, uint32_t* grant_dci, uint32_t max_grants, uint32_t* n_grants)
+} // extern "C"
+template <class TtiCfi>
+static int grants_from_dcis_impl(const ltephy_search_t* s, TtiCfi tc, const ltephy_dci_t* dcis, uint32_t nd, uint32_t mod, uint32_t rem,
+                                 ltephy_grant_t* grants, uint32_t* grant_dci, uint32_t max_grants, uint32_t* n_grants)
 {
-  if (!s || !info || !dcis || !grants || !grant_dci || !n_grants || mod == 0) return LTEPHY_ERROR_INVALID_INPUTS;
   uint32_t ng = 0;
   auto eligible = [&](const ltephy_grant_t& g) {
     if (!(g.tb[0].tbs > 0 && !(s->cell.nof_rx == 1 && g.nof_tb == 2))) return false;
@@ -1067,9 +1102,11 @@ int ltephy_grants_from_dcis(const ltephy_search_t* s, const ltephy_sf_info_t* in
     if (d.sf % mod != rem || d.format == ltehost::F0 || d.rnti == 0) continue;
     ltephy_grant_t g[2];
     bool           ok[2] = {false, false};
-    ok[0] = ltephy_dci_to_grant(s, &d, info[d.sf].tti % 10, info[d.sf].cfi, 0, &g[0], nullptr) == LTEPHY_SUCCESS && eligible(g[0]);
+    uint32_t tti_sf, cfi_sf;
+    tc(d.sf, tti_sf, cfi_sf);
+    ok[0] = ltephy_dci_to_grant(s, &d, tti_sf % 10, cfi_sf, 0, &g[0], nullptr) == LTEPHY_SUCCESS && eligible(g[0]);
     if (s->speculate_256qam && user_rnti(d.rnti)) { // MCS table of the UE unknown: 64QAM reading first, then the 256QAM one
-      ok[1] = ltephy_dci_to_grant(s, &d, info[d.sf].tti % 10, info[d.sf].cfi, 1, &g[1], nullptr) == LTEPHY_SUCCESS && eligible(g[1]);
+      ok[1] = ltephy_dci_to_grant(s, &d, tti_sf % 10, cfi_sf, 1, &g[1], nullptr) == LTEPHY_SUCCESS && eligible(g[1]);
       if (ok[0] && ok[1]) {
         bool same = g[0].nof_tb == g[1].nof_tb;
         for (int t = 0; t < 2 && same; t++) same = g[0].tb[t].enabled == g[1].tb[t].enabled && g[0].tb[t].qm == g[1].tb[t].qm && g[0].tb[t].tbs == g[1].tb[t].tbs;
@@ -1088,12 +1125,121 @@ int ltephy_grants_from_dcis(const ltephy_search_t* s, const ltephy_sf_info_t* in
   *n_grants = ng;
   return LTEPHY_SUCCESS;
 }
+extern "C" {
+int ltephy_grants_from_dcis(const ltephy_search_t* s, const ltephy_sf_info_t* info, const ltephy_dci_t* dcis, uint32_t nd, uint32_t mod, uint32_t rem,
+                            ltephy_grant_t* grants, uint32_t* grant_dci, uint32_t max_grants, uint32_t* n_grants)
+{
+  if (!s || !info || !dcis || !grants || !grant_dci || !n_grants || mod == 0) return LTEPHY_ERROR_INVALID_INPUTS;
+  return grants_from_dcis_impl(s, [&](uint32_t sf, uint32_t& t, uint32_t& c) { t = info[sf].tti, c = info[sf].cfi; }, dcis, nd, mod, rem, grants,
+                               grant_dci, max_grants, n_grants);
+}
+int ltephy_grants_from_dcis_tc(const ltephy_search_t* s, const uint32_t* tti_cfi, const ltephy_dci_t* dcis, uint32_t nd, uint32_t mod, uint32_t rem,
+                               ltephy_grant_t* grants, uint32_t* grant_dci, uint32_t max_grants, uint32_t* n_grants)
+{
+  if (!s || !tti_cfi || !dcis || !grants || !grant_dci || !n_grants || mod == 0) return LTEPHY_ERROR_INVALID_INPUTS;
+  return grants_from_dcis_impl(s, [&](uint32_t sf, uint32_t& t, uint32_t& c) { t = tti_cfi[2 * sf], c = tti_cfi[2 * sf + 1]; }, dcis, nd, mod, rem,
+                               grants, grant_dci, max_grants, n_grants);
+}
+
+// ===================================================================================================
+// Packed survivor form (include/ltephy_shard.h): header + location records + survivor list, back to back.
+size_t ltephy_packed_size(uint32_t nloc, uint32_t count)
+{
+  return sizeof(ltephy_packed_hdr_t) + sizeof(ltephy_cloc_t) * ((nloc + 3u) & ~3u) + sizeof(ltephy_cand_t) * std::min<uint32_t>(count, LTEPHY_COMPACT_CAP);
+}
+int ltephy_pack_subframes(const ltephy_search_t* s, const ltephy_sf_info_t* info, const ltephy_compact_t* comp, uint32_t n, uint8_t* out, size_t cap,
+                          uint32_t* offs)
+{
+  if (!s || !info || !comp || !out || !offs) return LTEPHY_ERROR_INVALID_INPUTS;
+  size_t pos = 0;
+  for (uint32_t i = 0; i < n; i++) {
+    const bool     ok   = info[i].cfi >= 1 && info[i].cfi <= 3;
+    const uint32_t nloc = ok ? s->tmpl[info[i].cfi - 1].n : 0, cnt = ok ? comp[i].count : 0;
+    const size_t   sz   = ltephy_packed_size(nloc, cnt);
+    if (pos + sz > cap) return LTEPHY_ERROR_INVALID_INPUTS;
+    offs[i] = (uint32_t)pos;
+    ltephy_packed_hdr_t hd{};
+    hd.count = cnt, hd.tti = info[i].tti, hd.cfi = info[i].cfi, hd.nloc = nloc;
+    memcpy(hd.noise, info[i].noise, sizeof(hd.noise)), memcpy(hd.rsrp, info[i].rsrp, sizeof(hd.rsrp));
+    if (ok) {
+      const ltephy_search::WalkIn w = s->walk_in(info[i], nullptr, nullptr);
+      hd.low[0] = w.low[0], hd.low[1] = w.low[1];
+    }
+    memcpy(out + pos, &hd, sizeof(hd));
+    ltephy_cloc_t* loc = reinterpret_cast<ltephy_cloc_t*>(out + pos + sizeof(hd));
+    for (uint32_t j = 0; j < ((nloc + 3u) & ~3u); j++) loc[j] = j < nloc ? comp[i].loc[j] : ltephy_cloc_t{0, 0, 0};
+    memcpy(out + pos + sizeof(hd) + sizeof(ltephy_cloc_t) * ((nloc + 3u) & ~3u), comp[i].list, sizeof(ltephy_cand_t) * std::min<uint32_t>(cnt, LTEPHY_COMPACT_CAP));
+    pos += sz;
+  }
+  offs[n] = (uint32_t)pos;
+  return LTEPHY_SUCCESS;
+}
+static inline ltephy_search::WalkIn walk_in_packed(const ltephy_search_t* s, const uint8_t* rec, const ltephy_cand_t* full)
+{
+  const ltephy_packed_hdr_t* hd = reinterpret_cast<const ltephy_packed_hdr_t*>(rec);
+  // snr_db exactly as ltephy_finalize_info evaluates it (log10f on the host from bit-exact device sums)
+  const uint32_t P = s->cell.nof_ports, A = s->cell.nof_rx;
+  float          ns = 0.0f, ps = 0.0f;
+  for (uint32_t p = 0; p < P; p++)
+    for (uint32_t a = 0; a < A; a++) ns = ns + hd->noise[p][a], ps = ps + hd->rsrp[p][a];
+  const float npa = (float)(P * A), snr = 10.0f * log10f((ps / npa) / (ns / npa));
+  const ltephy_cloc_t* loc = reinterpret_cast<const ltephy_cloc_t*>(rec + sizeof(*hd));
+  ltephy_search::WalkIn w{hd->tti, hd->cfi, snr, {hd->low[0], hd->low[1]}, hd->count, full, nullptr, nullptr};
+  if (!full) w.loc = loc, w.list = reinterpret_cast<const ltephy_cand_t*>(loc + ((hd->nloc + 3u) & ~3u));
+  return w;
+}
+int ltephy_packed_needs_full_table(const ltephy_search_t* s, const uint8_t* const* bufs, const uint32_t* const* offs, uint32_t world, uint32_t n)
+{
+  if (!s || !bufs || !offs) return LTEPHY_ERROR_INVALID_INPUTS;
+  if (s->rm.rar_seen) return 1;
+  for (uint32_t r = 0; r < world; r++)
+    for (uint32_t i = 0; i < n; i++)
+      if (reinterpret_cast<const ltephy_packed_hdr_t*>(bufs[r] + offs[r][i])->count > LTEPHY_COMPACT_CAP) return 1;
+  return 0;
+}
+int ltephy_search_batch_packed(ltephy_search_t* s, const uint8_t* const* bufs, const uint32_t* const* offs, const ltephy_cand_t* const* full,
+                               uint32_t world, uint32_t n, ltephy_dci_t* dcis, uint32_t max_dcis, uint32_t* n_dcis, uint32_t* tti_cfi)
+{
+  if (!s || !bufs || !offs || !dcis || !n_dcis || world == 0) return LTEPHY_ERROR_INVALID_INPUTS;
+  if (!full) {
+    if (s->rm.n_rar) return LTEPHY_NEED_FULL_TABLE;
+    for (uint32_t r = 0; r < world; r++)
+      for (uint32_t i = 0; i < n; i++)
+        if (reinterpret_cast<const ltephy_packed_hdr_t*>(bufs[r] + offs[r][i])->count > LTEPHY_COMPACT_CAP) return LTEPHY_NEED_FULL_TABLE;
+  }
+  uint32_t nd = 0;
+  const uint32_t total = n * world;
+  for (uint32_t g = 0; g < total; g++) {
+    const uint32_t r = g % world, i = g / world;
+    if (g + 1 < total) { // the records stream through once: pull the next one towards the core while this one is walked
+      const uint32_t r2 = (g + 1) % world, i2 = (g + 1) / world;
+      const uint8_t* nx = bufs[r2] + offs[r2][i2];
+      const uint32_t nb = offs[r2][i2 + 1] - offs[r2][i2];
+      for (uint32_t o = 0; o < nb; o += 64) __builtin_prefetch(nx + o, 0, 3);
+    }
+    const uint8_t* rec = bufs[r] + offs[r][i];
+    if (tti_cfi) tti_cfi[2 * g] = reinterpret_cast<const ltephy_packed_hdr_t*>(rec)->tti, tti_cfi[2 * g + 1] = reinterpret_cast<const ltephy_packed_hdr_t*>(rec)->cfi;
+    uint32_t k   = 0;
+    int      ret = s->search_subframe(walk_in_packed(s, rec, nullptr), g, dcis + nd, max_dcis - nd, &k);
+    if (ret == LTEPHY_NEED_FULL_TABLE) // only reachable with full != NULL (checked above)
+      ret = s->search_subframe(walk_in_packed(s, rec, full[r] + (size_t)i * LTEPHY_MAX_LOC * LTEPHY_MAX_SIZES), g, dcis + nd, max_dcis - nd, &k);
+    if (ret < 0) return ret;
+    nd += std::min(k, max_dcis - nd);
+  }
+  *n_dcis = nd;
+  return LTEPHY_SUCCESS;
+}
 
 // One call = what SubframeWorker::work does for every subframe of the batch (src/src/SubframeWorker.cc:142-207):
 // phase A on the GPU, FALCON search on the host in subframe order, phase B on the GPU for the DL grants.
-static double g_host_ms[8];
+static double     g_host_ms[8];
+static std::mutex g_host_ms_mtx;
 static inline double now_ms() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
-void ltephy_last_host_timing(double* ms8) { memcpy(ms8, g_host_ms, sizeof(g_host_ms)); }
+void ltephy_last_host_timing(double* ms8)
+{
+  std::lock_guard<std::mutex> lk(g_host_ms_mtx);
+  memcpy(ms8, g_host_ms, sizeof(g_host_ms));
+}
 
 static int decode_common(ltephy_t* h, ltephy_search_t* s, const void* iq, bool iq_on_device, const uint32_t* tti, uint32_t n, uint64_t seq,
                          ltephy_sf_info_t* info, ltephy_cand_t* cand_scratch, ltephy_dci_t* dcis, uint32_t max_dcis, uint32_t* n_dcis,
@@ -1101,6 +1247,25 @@ static int decode_common(ltephy_t* h, ltephy_search_t* s, const void* iq, bool i
 {
   if (!h || !s || !iq || !tti || !info || !cand_scratch || !dcis || !n_dcis || !tbs) return LTEPHY_ERROR_INVALID_INPUTS;
   double t0 = now_ms();
+  // Whatever happens before this batch's turn in the walk, the turn is taken and passed on: a failing batch must not leave the
+  // other pipelines of this search object waiting for a sequence number that never comes.
+  struct SeqGuard {
+    ltephy_search_t* s;
+    uint64_t         seq;
+    bool             done = false;
+    void             pass()
+    {
+      if (done || seq == LTEPHY_SEQ_NONE) return;
+      {
+        std::unique_lock<std::mutex> lk(s->mtx);
+        s->cv.wait(lk, [&] { return s->next_seq == seq; });
+        s->next_seq = seq + 1;
+      }
+      s->cv.notify_all();
+      done = true;
+    }
+    ~SeqGuard() { pass(); }
+  } guard{s, seq};
   int r = iq_on_device ? ltephy_submit_iq_device(h, iq, tti, n) : ltephy_submit_iq(h, (const float*)iq, tti, n);
   if (r) return r;
   double t1 = now_ms();
@@ -1118,6 +1283,7 @@ static int decode_common(ltephy_t* h, ltephy_search_t* s, const void* iq, bool i
       if (r == LTEPHY_SUCCESS) r = ltephy_search_batch_compact(s, info, comp, cand_scratch, n, dcis, max_dcis, &nd);
     }
     if (seq != LTEPHY_SEQ_NONE) s->next_seq = seq + 1;
+    guard.done = true;
     lk.unlock();
     s->cv.notify_all();
   }
@@ -1138,24 +1304,11 @@ static int decode_common(ltephy_t* h, ltephy_search_t* s, const void* iq, bool i
   r = ltephy_get_phase_b(h, res.data(), payload, payload_cap);
   if (r) return r;
   double t6 = now_ms();
-  g_host_ms[0] = t1 - t0, g_host_ms[1] = t2 - t1, g_host_ms[2] = t3 - t2, g_host_ms[3] = t4 - t3, g_host_ms[4] = t5 - t4, g_host_ms[5] = t6 - t5;
-  // one result per DCI: the 64QAM-table reading unless only the 256QAM-table reading (speculative second grant) passes a CRC,
-  // in which case its transport blocks are reported with crc = 2
-  for (uint32_t gi = 0; gi < ng; gi++) {
-    const uint32_t di = grant_dci[gi] & ~LTEPHY_GRANT_ALT_TABLE;
-    const bool     alt = (grant_dci[gi] & LTEPHY_GRANT_ALT_TABLE) != 0;
-    if (!alt) {
-      tbs[2 * di] = res[2 * gi], tbs[2 * di + 1] = res[2 * gi + 1];
-      continue;
-    }
-    const bool have_primary = tbs[2 * di].payload_len || tbs[2 * di + 1].payload_len; // grants of one DCI are adjacent, primary first
-    if (have_primary && (tbs[2 * di].crc || tbs[2 * di + 1].crc)) continue;
-    if (!have_primary || res[2 * gi].crc || res[2 * gi + 1].crc) {
-      tbs[2 * di] = res[2 * gi], tbs[2 * di + 1] = res[2 * gi + 1];
-      for (int t = 0; t < 2; t++)
-        if (tbs[2 * di + t].crc) tbs[2 * di + t].crc = 2;
-    }
+  {
+    std::lock_guard<std::mutex> lk(g_host_ms_mtx);
+    g_host_ms[0] = t1 - t0, g_host_ms[1] = t2 - t1, g_host_ms[2] = t3 - t2, g_host_ms[3] = t4 - t3, g_host_ms[4] = t5 - t4, g_host_ms[5] = t6 - t5;
   }
+  for (uint32_t gi = 0; gi < ng; gi++) ltephy_place_grant_result(tbs, grant_dci[gi], res[2 * gi], res[2 * gi + 1]);
   return LTEPHY_SUCCESS;
 }
 int ltephy_decode_subframes(ltephy_t* h, ltephy_search_t* s, const float* iq, const uint32_t* tti, uint32_t n, uint64_t seq, ltephy_sf_info_t* info,

@@ -153,11 +153,7 @@ extern "C" void launch_pusch(const DevCell& c, const DevUlGrant* grants, uint32_
   if (!ngrants) return;
   scr_seq_ul_kernel<<<dim3((max_words + 255) / 256, ngrants), 256, 0, st>>>(grants, x1, basis, basis_words, c.cell_id, seq_pool);
   const size_t smem = (size_t)6 * max_M * sizeof(float2);
-  static bool  attr = false;
-  if (!attr) {
-    cudaFuncSetAttribute(pusch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 6 * 1200 * (int)sizeof(float2));
-    attr = true;
-  }
+  cudaFuncSetAttribute(pusch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 6 * 1200 * (int)sizeof(float2)); // per device / context
   pusch_kernel<<<dim3(12, ngrants), 256, smem, st>>>(c, grants, ulsym, dmrs_pool, idft_pool, seq_pool, llr_pool, chest);
   *launches += 2;
 }

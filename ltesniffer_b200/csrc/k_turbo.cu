@@ -301,8 +301,10 @@ __global__ void __launch_bounds__(NT, (NT > 128 ? 2 : (NT > 64 ? 3 : 6))) turbo_
     it++;
     // ---- CRC over the K decided bits of each code block -------------------------------------------
     bool all_done = true;
+    const uint32_t was_done[2] = {done_s[0], done_s[1]}; // read before anybody can set it below (every path to here passed a barrier)
+    __syncthreads();
     for (uint32_t h = 0; h < 2; h++) {
-      if (done_s[h]) continue;
+      if (was_done[h]) continue;
       const uint32_t ct = P.crc_type[h];
       bool           ok = false;
       if (ct) {
@@ -387,11 +389,8 @@ static void launch_turbo_t(const DevPair* pairs, uint32_t npairs, uint32_t* pool
                            const uint32_t* xpowB, uint8_t* payload, uint8_t* cb_iters, uint8_t* cb_crc, uint32_t max_iter, cudaStream_t st)
 {
   const size_t smem = (size_t)NT * (TD_SUB * 2 * sizeof(uint4) + TD_WL * sizeof(uint2) + TD_WL * sizeof(uint16_t));
-  static bool  attr_set = false;
-  if (!attr_set) {
-    cudaFuncSetAttribute(turbo_kernel<NT, FULL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    attr_set = true;
-  }
+  // the attribute belongs to the current device / context (handles may live on different devices): set it on every launch
+  cudaFuncSetAttribute(turbo_kernel<NT, FULL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   turbo_kernel<NT, FULL><<<npairs, NT, smem, st>>>(pairs, pool, pi_pool, pi_off, xpowA, xpowB, payload, cb_iters, cb_crc, max_iter);
 }
 // all pairs of one launch share the CTA size class `max_threads` (32..192) and `full` (every K a multiple of 32)

@@ -3,9 +3,7 @@
 // There is no CPU fallback: creation fails when no CUDA device can be used.
 #include "../../include/ltephy_b200.h"
 #include "../../include/ltephy_search.h"
-#include "dev_common.cuh"
-#include "dev_ul.cuh"
-#include "lte_host.hpp"
+#include "ltephy_internal.cuh"
 #include "../../include/lte_tables.h"
 #include <cmath>
 #include <cstdarg>
@@ -32,144 +30,7 @@ void launch_pusch(const DevCell&, const DevUlGrant*, uint32_t, uint32_t, uint32_
                   const uint32_t*, uint32_t, uint32_t*, short*, ltephy_ul_chest_t*, cudaStream_t, uint64_t*);
 }
 
-static thread_local std::string g_err;
-static int fail(int code, const char* fmt, ...)
-{
-  char    buf[512];
-  va_list ap;
-  va_start(ap, fmt);
-  vsnprintf(buf, sizeof(buf), fmt, ap);
-  va_end(ap);
-  g_err = buf;
-  return code;
-}
-#define CU(x)                                                                                      \
-  do {                                                                                             \
-    cudaError_t e_ = (x);                                                                          \
-    if (e_ != cudaSuccess) return fail(LTEPHY_ERROR, "%s: %s", #x, cudaGetErrorString(e_));        \
-  } while (0)
-
-template <typename T>
-struct DevBuf { // growable device buffer
-  T*     p   = nullptr;
-  size_t cap = 0;
-  int    reserve(size_t n)
-  {
-    if (n <= cap) return 0;
-    size_t want = n + n / 4 + 1024;
-    if (p) {
-      cudaDeviceSynchronize();
-      cudaFree(p);
-      p = nullptr;
-    }
-    if (cudaMalloc(&p, want * sizeof(T)) != cudaSuccess) {
-      cap = 0;
-      return -1;
-    }
-    cap = want;
-    return 0;
-  }
-  void release()
-  {
-    if (p) cudaFree(p);
-    p = nullptr, cap = 0;
-  }
-};
-template <typename T>
-struct PinBuf { // growable pinned host buffer
-  T*     p   = nullptr;
-  size_t cap = 0;
-  int    reserve(size_t n)
-  {
-    if (n <= cap) return 0;
-    size_t want = n + n / 4 + 1024;
-    if (p) cudaFreeHost(p);
-    p = nullptr;
-    if (cudaMallocHost(&p, want * sizeof(T)) != cudaSuccess) {
-      cap = 0;
-      return -1;
-    }
-    cap = want;
-    return 0;
-  }
-  void release()
-  {
-    if (p) cudaFreeHost(p);
-    p = nullptr, cap = 0;
-  }
-};
-
-struct ltephy {
-  ltephy_cfg_t       cfg{};
-  ltehost::Cell      cell;
-  ltehost::CtrlMap   cm;
-  ltehost::SizeTable st;
-  DevCell            dc{};
-  cudaStream_t       stream = nullptr;
-  cudaEvent_t        ev[6]{}, mark[2]{};
-  std::vector<void*> tables; // device tables freed at destroy
-  uint64_t           launches = 0;
-
-  // phase A
-  DevBuf<float2>        d_iq, d_sym, d_ce;
-  DevBuf<float>         d_llr;
-  DevBuf<DevSfInfo>     d_info;
-  DevBuf<ltephy_cand_t> d_cands;
-  PinBuf<DevSfInfo>     h_info;
-  DevBuf<ltephy_compact_t> d_compact;
-  PinBuf<ltephy_compact_t> h_compact;
-  uint32_t              n_cur = 0;
-  std::vector<uint8_t>  re_cnt; // [3 sf class][3 cfi][14][nof_prb]
-
-  // phase B
-  std::vector<DevGrant> grants;
-  std::vector<DevCb>    cbs;
-  std::vector<DevPair>  pairs;
-  std::vector<DevTb>    tbs;
-  std::vector<uint32_t> pair_pi_off;
-  std::vector<uint32_t> tb_slot; // result slot [grant*2 + tb] -> tb index or ~0
-  DevBuf<DevGrant>      d_grants;
-  DevBuf<DevCb>         d_cbs;
-  DevBuf<DevPair>       d_pairs;
-  DevBuf<DevTb>         d_tbs;
-  DevBuf<uint32_t>      d_pair_pi_off;
-  DevBuf<uint32_t>      d_seq, d_rm, d_turbo;
-  DevBuf<short>         d_pllr;
-  DevBuf<uint16_t>      d_pi;
-  DevBuf<uint8_t>       d_payload, d_cb_iters, d_cb_crc;
-  DevBuf<ltephy_tb_result_t> d_res;
-  PinBuf<ltephy_tb_result_t> h_res;
-  PinBuf<uint8_t>            h_payload;
-  PinBuf<uint8_t>            h_stage;      // pinned arena for the job descriptors of one phase B (see pull())
-  size_t                     stage_used = 0;
-  bool                       stage_busy = false; // descriptors staged and possibly still being pulled
-  size_t                     payload_bytes = 0, pllr_elems = 0;
-  uint32_t *                 d_gold_x1 = nullptr, *d_gold_basis = nullptr, gold_words = 0;
-  uint32_t *                 d_xpowA = nullptr, *d_xpowB = nullptr;
-  std::map<std::tuple<uint32_t, uint32_t, uint32_t>, std::pair<uint32_t, uint32_t>> rm_cache; // (K,F,rv) -> (offset, nn)
-  int64_t  rm_fast[188][4];   // F == 0 fast path: offset or -1
-  uint32_t rm_fast_nn[188][4];
-  int64_t  pi_fast[188];
-  std::vector<ltehost::Segm> segm_fast; // index tbs/8, C == 0 means "not computed"
-  // uplink
-  ltephy_ul_cfg_t            ulcfg{};
-  bool                       ulcfg_set = false;
-  uint32_t                   n_prs[20]{};
-  DevBuf<float2>             d_uliq, d_ulsym, d_ulpool; // d_ulpool: DMRS sequences and IDFT twiddles
-  DevBuf<DevUlGrant>         d_ulgrants;
-  DevBuf<ltephy_ul_chest_t>  d_ulchest;
-  PinBuf<ltephy_ul_chest_t>  h_ulchest;
-  std::vector<DevUlGrant>    ulgrants;
-  std::map<uint64_t, uint32_t> ul_tab_cache; // (kind, M, ncs) -> offset in d_ulpool
-  size_t                     ulpool_used = 0;
-  uint32_t                   n_ul = 0;
-  size_t                                                                            rm_used = 0;
-  std::map<uint32_t, uint32_t>                                                      pi_cache; // K -> offset
-  size_t                                                                            pi_used = 0;
-  std::map<uint32_t, ltehost::Segm>                                                 segm_cache;
-  float                                                                             t_ms[4]{};
-};
-
+thread_local std::string ltephy_g_err;
 template <typename T>
 static T* upload(ltephy* h, const T* src, size_t n)
 {
@@ -187,14 +48,15 @@ __global__ void __launch_bounds__(256) pull_kernel(uint4* __restrict__ dst, cons
 {
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (size_t)gridDim.x * blockDim.x) dst[i] = src_host[i];
 }
-static void pull(ltephy* h, void* dst_dev, const void* src_pinned, size_t bytes)
+void ltephy_pull(ltephy* h, void* dst_dev, const void* src_pinned, size_t bytes, cudaStream_t st)
 {
   const size_t n16 = (bytes + 15) / 16;
   if (!n16) return;
   const unsigned grid = (unsigned)std::min<size_t>((n16 + 255) / 256, 592);
-  pull_kernel<<<grid, 256, 0, h->stream>>>(reinterpret_cast<uint4*>(dst_dev), reinterpret_cast<const uint4*>(src_pinned), n16);
+  pull_kernel<<<grid, 256, 0, st>>>(reinterpret_cast<uint4*>(dst_dev), reinterpret_cast<const uint4*>(src_pinned), n16);
   h->launches++;
 }
+static void pull(ltephy* h, void* dst_dev, const void* src_pinned, size_t bytes) { ltephy_pull(h, dst_dev, src_pinned, bytes, h->stream); }
 // stage `bytes` from pageable memory into the handle's pinned arena (16-byte slots) and pull them to dst_dev
 static void stage_and_pull(ltephy* h, void* dst_dev, const void* src, size_t bytes)
 {
@@ -205,7 +67,7 @@ static void stage_and_pull(ltephy* h, void* dst_dev, const void* src, size_t byt
   pull(h, dst_dev, slot, bytes);
 }
 
-extern "C" const char* ltephy_last_error(void) { return g_err.c_str(); }
+extern "C" const char* ltephy_last_error(void) { return ltephy_g_err.c_str(); }
 
 extern "C" int ltephy_create(const ltephy_cfg_t* cfg, ltephy_t** out)
 {
@@ -217,14 +79,19 @@ extern "C" int ltephy_create(const ltephy_cfg_t* cfg, ltephy_t** out)
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(LTEPHY_ERROR, "no CUDA device: this library has no CPU path");
   CU(cudaSetDevice(cfg->device));
   ltephy* h = new ltephy();
+  struct CreateGuard { // every failing return below releases what was created so far
+    ltephy* h;
+    bool    ok = false;
+    ~CreateGuard()
+    {
+      if (!ok) ltephy_destroy(h);
+    }
+  } guard{h};
   h->cfg    = *cfg;
   if (!h->cfg.turbo_max_iter) h->cfg.turbo_max_iter = 8;
   if (!h->cfg.max_grants) h->cfg.max_grants = 24 * cfg->max_subframes;
   h->cell = {cfg->nof_prb, cfg->nof_ports, cfg->cell_id, cfg->nof_rx};
-  if (!ltehost::build_ctrl_map(h->cell, h->cm)) {
-    delete h;
-    return fail(LTEPHY_ERROR_INVALID_INPUTS, "control region map failed");
-  }
+  if (!ltehost::build_ctrl_map(h->cell, h->cm)) return fail(LTEPHY_ERROR_INVALID_INPUTS, "control region map failed");
   h->st = ltehost::dci_size_table(h->cell);
   memset(h->rm_fast, 0xFF, sizeof(h->rm_fast));
   memset(h->pi_fast, 0xFF, sizeof(h->pi_fast));
@@ -347,12 +214,11 @@ extern "C" int ltephy_create(const ltephy_cfg_t* cfg, ltephy_t** out)
   const size_t S = cfg->max_subframes, g = (size_t)14 * c.nsc;
   if (h->d_iq.reserve(S * c.nof_rx * c.sf_len) || h->d_sym.reserve(S * c.nof_rx * g) || h->d_ce.reserve(S * c.nof_ports * c.nof_rx * g) ||
       h->d_llr.reserve(S * LLR_STRIDE) || h->d_info.reserve(S) || h->d_cands.reserve(S * LTEPHY_MAX_LOC * LTEPHY_MAX_SIZES) ||
-      h->h_info.reserve(S) || h->d_compact.reserve(S) || h->h_compact.reserve(S) || h->d_rm.reserve((size_t)16 << 20) || h->d_pi.reserve((size_t)188 * 6144)) {
-    ltephy_destroy(h);
+      h->h_info.reserve(S) || h->d_compact.reserve(S) || h->h_compact.reserve(S) || h->d_rm.reserve((size_t)16 << 20) || h->d_pi.reserve((size_t)188 * 6144))
     return fail(LTEPHY_ERROR, "device allocation failed");
-  }
   CU(cudaMemset(h->d_cands.p, 0, h->d_cands.cap * sizeof(ltephy_cand_t)));
-  *out = h;
+  guard.ok = true;
+  *out     = h;
   return LTEPHY_SUCCESS;
 }
 
@@ -367,6 +233,8 @@ extern "C" void ltephy_destroy(ltephy_t* h)
   h->d_cb_iters.release(), h->d_cb_crc.release(), h->d_res.release(), h->h_res.release(), h->h_payload.release(), h->h_stage.release();
   h->d_uliq.release(), h->d_ulsym.release(), h->d_ulpool.release(), h->d_ulgrants.release(), h->d_ulchest.release(), h->h_ulchest.release();
   for (auto& e : h->ev)
+    if (e) cudaEventDestroy(e);
+  for (auto& e : h->mark)
     if (e) cudaEventDestroy(e);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
@@ -525,11 +393,16 @@ static int rm_table_for(ltephy* h, uint32_t K, uint32_t F, uint32_t rv, uint32_t
       v = i < K ? st * 32 * NW + (i & 31u) * NW + (i >> 5) : 5 * 32 * NW + st * 4 + (i - K);
     }
   }
-  if (h->rm_used + t.order.size() > h->d_rm.cap) { // cache full: start over (tables already queued stay valid until the stream drains)
-    cudaStreamSynchronize(h->stream);
-    h->rm_cache.clear();
-    memset(h->rm_fast, 0xFF, sizeof(h->rm_fast));
-    h->rm_used = 0;
+  if (h->rm_used + t.order.size() > h->d_rm.cap) { // pool full: grow it and keep every offset handed out so far valid
+    const size_t want = 2 * h->d_rm.cap + t.order.size();
+    uint32_t*    np   = nullptr;
+    if (cudaStreamSynchronize(h->stream) != cudaSuccess || cudaMalloc(&np, want * sizeof(uint32_t)) != cudaSuccess) return -1;
+    if (cudaMemcpy(np, h->d_rm.p, h->rm_used * sizeof(uint32_t), cudaMemcpyDeviceToDevice) != cudaSuccess) {
+      cudaFree(np);
+      return -1;
+    }
+    cudaFree(h->d_rm.p);
+    h->d_rm.p = np, h->d_rm.cap = want;
   }
   off = (uint32_t)h->rm_used, nn = t.nn;
   if (cudaMemcpyAsync(h->d_rm.p + off, t.order.data(), t.order.size() * 4, cudaMemcpyHostToDevice, h->stream) != cudaSuccess) return -1;
@@ -671,10 +544,15 @@ static int build_jobs(ltephy* h, const ltephy_grant_t* gin, uint32_t n, size_t& 
     d.pmi = g.pmi;
     if (g.tx_scheme == LTEPHY_TX_CDD && !(c.nof_ports == 2 && c.nof_rx == 2)) return fail(LTEPHY_ERROR_INVALID_INPUTS, "grant %u: CDD needs 2x2", gi);
     if (g.tx_scheme == LTEPHY_TX_DIVERSITY && c.nof_ports != 2) return fail(LTEPHY_ERROR_INVALID_INPUTS, "grant %u: tx diversity needs 2 ports", gi);
-    uint32_t cw = 0;
+    // codeword of each enabled TB: srsran_ra_tb_t.cw_idx (dl_sniffer_pdsch.c:24) -- scrambling (q << 13) and the layer the
+    // demapper writes follow the codeword, not the TB (DCI 2/2A swap flag)
+    const uint32_t n_en = (g.tb[0].enabled ? 1u : 0u) + (g.tb[1].enabled ? 1u : 0u);
+    if (n_en > (two_cw ? 2u : 1u)) return fail(LTEPHY_ERROR_INVALID_INPUTS, "grant %u: too many transport blocks for the tx scheme", gi);
+    if (n_en == 2 && (g.tb[0].cw_idx > 1 || g.tb[1].cw_idx > 1 || g.tb[0].cw_idx == g.tb[1].cw_idx))
+      return fail(LTEPHY_ERROR_INVALID_INPUTS, "grant %u: transport blocks must map to distinct codewords 0 / 1", gi);
     for (int t = 0; t < 2; t++) {
       if (!g.tb[t].enabled) continue;
-      if (cw >= (two_cw ? 2u : 1u)) return fail(LTEPHY_ERROR_INVALID_INPUTS, "grant %u: too many transport blocks for the tx scheme", gi);
+      const uint32_t cw = n_en == 2 ? g.tb[t].cw_idx : 0u;
       const uint32_t qm = g.tb[t].qm, G = acc * qm;
       if (qm != 2 && qm != 4 && qm != 6 && qm != 8) return fail(LTEPHY_ERROR_INVALID_INPUTS, "grant %u: bad modulation order", gi);
       d.qm[cw]      = qm;
@@ -691,9 +569,8 @@ static int build_jobs(ltephy* h, const ltephy_grant_t* gin, uint32_t n, size_t& 
         if (r) return r;
         h->tb_slot[(size_t)gi * 2 + t] = tbi;
       }
-      cw++;
     }
-    d.ncw = cw;
+    d.ncw = n_en;
     h->grants.push_back(d);
   }
   return LTEPHY_SUCCESS;
@@ -971,6 +848,7 @@ extern "C" int ltephy_get_ul(ltephy_t* h, ltephy_tb_result_t* results, ltephy_ul
       CU(cudaMemcpyAsync(h->h_payload.p, h->d_payload.p, h->payload_bytes, cudaMemcpyDeviceToHost, h->stream));
     }
     CU(cudaStreamSynchronize(h->stream));
+    h->stage_busy = false;
   }
   size_t wp = 0;
   for (size_t i = 0; i < ng; i++) {

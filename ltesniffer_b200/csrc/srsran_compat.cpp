@@ -130,6 +130,8 @@ extern "C" int srsran_ue_dl_decode_pdsch(srsran_ue_dl_t* q, srsran_dl_sf_cfg_t* 
     g.tb[t].qm = (unsigned)s.tb[t].mod < 5 ? qm_of[s.tb[t].mod] : 0;
     data[t].crc = false, data[t].avg_iterations_block = 0.0f;
   }
+  if (s.tb[0].enabled && s.tb[1].enabled) // srsran_ra_tb_t.cw_idx (dl_sniffer_pdsch.c:24): DCI 2/2A swap flag
+    g.tb[0].cw_idx = (uint8_t)(s.tb[0].cw_idx & 1u), g.tb[1].cw_idx = (uint8_t)(s.tb[1].cw_idx & 1u);
   if (ltephy_submit_grants(p->phy, &g, 1) != LTEPHY_SUCCESS) return SRSRAN_ERROR;
   ltephy_tb_result_t   r[2]{};
   std::vector<uint8_t> pl(2 * 16000);

@@ -578,7 +578,7 @@ int lteo_pdsch_llr(lteo_t* q, uint32_t sf_idx, uint32_t cfi, uint16_t rnti, cons
   cf_t* x[2] = {(cf_t*)malloc(sizeof(cf_t) * (n + 2)), (cf_t*)malloc(sizeof(cf_t) * (n + 2))};
   uint32_t ncw = 0, qm[2] = {0, 0};
   for (int t = 0; t < 2; t++)
-    if (g->tb[t].enabled) qm[ncw++] = g->tb[t].qm;
+    if (g->tb[t].enabled) qm[g->cw_swap ? 1 - ncw : ncw] = g->tb[t].qm, ncw++; /* srsran_ra_tb_t.cw_idx (dl_sniffer_pdsch.c:24) */
   if (g->tx_scheme == LTE_TX_PORT0) {
     for (uint32_t i = 0; i < n; i++) x[0][i] = eq_port0(q, sym, ce, idx[i]);
   } else if (g->tx_scheme == LTE_TX_DIVERSITY) {
@@ -819,7 +819,7 @@ int lteo_pdsch_decode(lteo_t* q, uint32_t sf_idx, uint32_t cfi, uint16_t rnti, c
       if (!g->tb[t].enabled) continue;
       uint32_t NL = g->tx_scheme == LTE_TX_DIVERSITY ? 2 : 1;
       if (g->tb[t].tbs > 0)
-        crc_ok[t] = lteo_dlsch_decode(llr[cw], g->tb[t].nof_bits, (uint32_t)g->tb[t].tbs, g->tb[t].rv, g->tb[t].qm, NL, max_iter, 1,
+        crc_ok[t] = lteo_dlsch_decode(llr[g->cw_swap ? 1 - cw : cw], g->tb[t].nof_bits, (uint32_t)g->tb[t].tbs, g->tb[t].rv, g->tb[t].qm, NL, max_iter, 1,
                                       payload[t], NULL);
       cw++;
     }

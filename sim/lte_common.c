@@ -728,6 +728,7 @@ int lte_dl_dci_to_grant(const lte_cell_t* c, uint32_t sf_idx, uint32_t cfi, int 
       g->nof_tb++;
     }
   }
+  g->cw_swap = (uint8_t)(d->format >= LTE_DCI_FORMAT2 && g->nof_tb == 2 && d->tb_cw_swap); /* one TB: always codeword 0 (Table 5.3.3.1.5-2) */
   if (d->format == LTE_DCI_FORMAT1A || !LTE_RNTI_ISUSER(d->rnti)) alt = 0;
   if (!LTE_RNTI_ISUSER(d->rnti)) {
     int tbs;

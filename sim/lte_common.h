@@ -167,6 +167,7 @@ typedef struct {
   uint8_t  tx_scheme;
   uint8_t  nof_layers;
   uint8_t  pmi;
+  uint8_t  cw_swap; /* 2 TBs and the "transport block to codeword swap flag" of DCI 2/2A set (36.212 Table 5.3.3.1.5-1): TB1 -> codeword 1, TB2 -> codeword 0 */
 } lte_dl_grant_t;
 
 #define LTE_SIRNTI 0xFFFF

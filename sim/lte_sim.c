@@ -317,6 +317,7 @@ int lte_sim_subframe(lte_sim_t* s, uint32_t tti, cf_t* iq, lte_sim_truth_t* trut
     }
     d->tb_en[0] = 1;
     d->tb_en[1] = (kind == 3 || kind == 4);
+    if (cfg->tb_swap && d->tb_en[1]) d->tb_cw_swap = (uint8_t)(lte_rng_u64(&rng) & 1);
     if (kind == 101 && d->mcs[0] > 28) d->mcs[0] = 28;
   }
   uint32_t ul_next = 0;
@@ -435,10 +436,10 @@ int lte_sim_subframe(lte_sim_t* s, uint32_t tti, cf_t* iq, lte_sim_truth_t* trut
         return -10;
       }
       uint8_t* sc = s->tbbits;
-      uint32_t q  = ncw; /* codeword index */
+      uint32_t q  = g.cw_swap ? 1 - ncw : ncw; /* codeword index (36.212 Table 5.3.3.1.5-1) */
       lte_gold_bits(((uint32_t)d->rnti << 14) + (q << 13) + (sf_idx << 9) + cell->cell_id, sc, G);
       for (uint32_t i = 0; i < G; i++) s->ebits[i] ^= sc[i];
-      lte_modulate(s->ebits, G / Qm, Qm, s->dsym[ncw]);
+      lte_modulate(s->ebits, G / Qm, Qm, s->dsym[q]);
       ncw++;
     }
     /* layer mapping + precoding + RE mapping */

@@ -29,7 +29,8 @@ typedef struct {
   uint32_t   full_band;    /* 1: partition all PRBs between the scheduled UEs */
   uint32_t   alt_table;    /* 1: C-RNTI grants use the 256QAM MCS table */
   uint32_t   ul_pusch;     /* 1: DCI-0 grants are decodable PUSCH allocations (L_prb in the DFT set, >= 3, back to back from PRB 0, MCS <= 20) */
-  uint32_t   reserved[6];
+  uint32_t   tb_swap;      /* 1: two-TB DCIs (2 / 2A) set the TB-to-codeword swap flag at random */
+  uint32_t   reserved[5];
 } lte_sim_cfg_t;
 
 #define LTE_SIM_MAX_DCI 32

@@ -52,6 +52,9 @@ def to_phy_grant(sf, rnti, g):
         pg.tb[t].qm = g.tb[t].qm
         pg.tb[t].rv = g.tb[t].rv
         pg.tb[t].enabled = g.tb[t].enabled
+    en = [t for t in range(2) if g.tb[t].enabled]
+    for k, t in enumerate(en):
+        pg.tb[t].cw_idx = (1 - k) if (len(en) == 2 and g.cw_swap) else k
     return pg
 
 

@@ -22,7 +22,7 @@ class SimCfg(C.Structure):
                 ("dl_min", C.c_uint32), ("dl_max", C.c_uint32), ("ul_min", C.c_uint32), ("ul_max", C.c_uint32),
                 ("tm", C.c_uint32), ("mcs_min", C.c_uint32), ("mcs_max", C.c_uint32), ("si_period", C.c_uint32),
                 ("snr_db", C.c_float), ("chan_delay", C.c_uint32), ("fixed_L", C.c_uint32), ("full_band", C.c_uint32),
-                ("alt_table", C.c_uint32), ("ul_pusch", C.c_uint32), ("reserved", C.c_uint32 * 6)]
+                ("alt_table", C.c_uint32), ("ul_pusch", C.c_uint32), ("tb_swap", C.c_uint32), ("reserved", C.c_uint32 * 5)]
 
 
 class DciTruth(C.Structure):
@@ -53,7 +53,7 @@ class GrantTb(C.Structure):
 
 class DlGrant(C.Structure):
     _fields_ = [("prb_mask", (C.c_uint8 * MAX_PRB) * 2), ("nof_prb", C.c_uint32), ("nof_tb", C.c_uint32), ("tb", GrantTb * 2),
-                ("nof_re", C.c_uint32), ("tx_scheme", C.c_uint8), ("nof_layers", C.c_uint8), ("pmi", C.c_uint8)]
+                ("nof_re", C.c_uint32), ("tx_scheme", C.c_uint8), ("nof_layers", C.c_uint8), ("pmi", C.c_uint8), ("cw_swap", C.c_uint8)]
 
 
 class ChestRes(C.Structure):

@@ -71,6 +71,8 @@ CAPS = {
     "tm3_2x2_64qam": (Cell(100, 2, 7, 2), 2, dict(seed=2, cfi=3, nof_ues=150, dl_min=8, dl_max=12, tm=3, mcs_min=17, mcs_max=24, snr_db=28.0, full_band=1)),
     "mix_50prb_delay": (Cell(50, 2, 301, 2), 3, dict(seed=3, cfi=3, nof_ues=20, dl_min=3, dl_max=5, ul_min=1, ul_max=2, tm=13, mcs_min=0, mcs_max=20, snr_db=22.0, chan_delay=6)),
     "tm4_2x2_256qam_alt_table": (Cell(50, 2, 11, 2), 3, dict(seed=6, cfi=2, nof_ues=8, dl_min=2, dl_max=4, tm=4, mcs_min=4, mcs_max=22, snr_db=33.0, alt_table=1)),
+    "tm3_cw_swap": (Cell(50, 2, 21, 2), 4, dict(seed=8, cfi=2, nof_ues=8, dl_min=2, dl_max=4, tm=3, mcs_min=6, mcs_max=24, snr_db=29.0, tb_swap=1)),
+    "tm4_cw_swap": (Cell(50, 2, 11, 2), 4, dict(seed=9, cfi=2, nof_ues=8, dl_min=2, dl_max=4, tm=4, mcs_min=4, mcs_max=20, snr_db=33.0, tb_swap=1)),
     "sf0_sf5_sync_re_exclusion_25prb": (Cell(25, 2, 77, 1), 6, dict(seed=4, cfi=2, nof_ues=3, dl_min=1, dl_max=2, tm=1, mcs_min=4, mcs_max=10, snr_db=26.0, full_band=1)),
 }
 
@@ -80,7 +82,7 @@ def test_sim_to_oracle_ground_truth(infra, name):
     """every transmitted DCI and transport block is recovered by the oracle receiver"""
     cell, n, kw = CAPS[name]
     s, o = Sim(cell=cell, **kw), Oracle(cell)
-    ndci = ntb = 0
+    ndci = ntb = nswap = 0
     for tti in range(n):
         iq, tr, pl = s.subframe(tti)
         sym = o.ofdm(iq)
@@ -98,6 +100,7 @@ def test_sim_to_oracle_ground_truth(infra, name):
                 continue
             r, dd, g = ltelib.unpack_and_grant(cell, d.format, crc, bits, tti % 10, cfi, kw.get("alt_table", 0))
             assert r == 0 and g.nof_re == d.nof_re
+            nswap += g.cw_swap
             r, pay, ok = o.pdsch_decode(tti % 10, cfi, crc, g, sym, ce, 8)
             assert r == 0
             for t in range(2):
@@ -106,6 +109,8 @@ def test_sim_to_oracle_ground_truth(infra, name):
                     assert ok[t] and np.array_equal(pay[t][:nby], pl[d.payload_off[t]:d.payload_off[t] + nby]), (name, tti, hex(d.rnti), t)
                     ntb += 1
     assert ndci >= n and ntb >= 1
+    if kw.get("tb_swap"):
+        assert nswap >= 2          # the swap flag was exercised (TB 1 on codeword 1, TB 2 on codeword 0) and both TBs still decode
 
 
 def test_pusch_all_mcs_tables_roundtrip(infra):

@@ -17,6 +17,8 @@ CASES = {
     "20MHz_2p2a_tm3": dict(cell=Cell(100, 2, 7, 2), n=3, kw=dict(seed=12, cfi=3, nof_ues=30, dl_min=6, dl_max=10, ul_min=1, ul_max=3, tm=3, mcs_min=10, mcs_max=24, snr_db=27.0, full_band=1, chan_delay=4)),
     "10MHz_2p2a_mix": dict(cell=Cell(50, 2, 301, 2), n=4, kw=dict(seed=13, cfi=3, nof_ues=12, dl_min=3, dl_max=5, ul_min=1, ul_max=2, tm=13, mcs_min=0, mcs_max=22, snr_db=24.0, chan_delay=6, tti0=4)),
     "10MHz_tm4_256qam": dict(cell=Cell(50, 2, 11, 2), n=3, kw=dict(seed=15, cfi=2, nof_ues=8, dl_min=2, dl_max=4, tm=4, mcs_min=4, mcs_max=22, snr_db=33.0, alt_table=1)),
+    "10MHz_tm3_tm4_cw_swap": dict(cell=Cell(50, 2, 21, 2), n=4, kw=dict(seed=16, cfi=2, nof_ues=8, dl_min=2, dl_max=4, tm=3, mcs_min=6, mcs_max=24, snr_db=29.0, tb_swap=1)),
+    "10MHz_tm4_cw_swap": dict(cell=Cell(50, 2, 11, 2), n=3, kw=dict(seed=17, cfi=2, nof_ues=8, dl_min=2, dl_max=4, tm=4, mcs_min=4, mcs_max=20, snr_db=33.0, tb_swap=1)),
     "5MHz_2p1a": dict(cell=Cell(25, 2, 150, 1), n=3, kw=dict(seed=14, cfi=2, nof_ues=5, dl_min=1, dl_max=3, tm=1, mcs_min=2, mcs_max=12, snr_db=25.0, tti0=9)),
 }
 

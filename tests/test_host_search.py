@@ -129,7 +129,7 @@ def test_dci_to_grant_matches_oracle(infra):
     """random valid DCIs of every decodable DL format: product ltephy_dci_to_grant == oracle lte_dl_dci_to_grant"""
     S = infra.sim()
     rng = np.random.default_rng(5)
-    ncheck = 0
+    ncheck = nswap = 0
     for cell in (Cell(100, 2, 3, 2), Cell(50, 1, 9, 1), Cell(25, 2, 100, 2), Cell(75, 2, 5, 2)):
         srch = capi.Search(cell.nof_prb, cell.nof_ports, cell.cell_id, cell.nof_rx)
         for _ in range(1500):
@@ -157,10 +157,15 @@ def test_dci_to_grant_matches_oracle(infra):
                        (g.tb[t].enabled, g.tb[t].tbs if g.tb[t].enabled else 0, g.tb[t].qm if g.tb[t].enabled else 0)
                 if g.tb[t].enabled:
                     assert pg.tb[t].rv == g.tb[t].rv
+            if g.nof_tb == 2:        # srsran_ra_tb_t.cw_idx: TB -> codeword, swapped by the DCI 2/2A flag
+                assert (pg.tb[0].cw_idx, pg.tb[1].cw_idx) == ((1, 0) if g.cw_swap else (0, 1))
+                nswap += g.cw_swap
+            else:
+                assert all(pg.tb[t].cw_idx == 0 for t in range(2) if g.tb[t].enabled)
             for sl in range(2):
                 for prb in range(cell.nof_prb):
                     assert ((pg.prb_mask[sl][prb >> 5] >> (prb & 31)) & 1) == g.prb_mask[sl][prb]
-    assert ncheck > 2000
+    assert ncheck > 2000 and nswap > 50
 
 
 def test_ul_dci_to_grant_matches_oracle(infra):

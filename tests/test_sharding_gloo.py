@@ -35,6 +35,9 @@ def _tables(cell_args, ttis):
         llr = o.pdcch_llr(int(tti) % 10, cfi, sym, ce)
         ncce = len(llr) // 72
         info[i].tti, info[i].cfi, info[i].nof_cce, info[i].snr_db = int(tti), cfi, ncce, res.snr_db
+        for pp in range(2):                      # per-path sums: the packed exchange format derives snr_db from them
+            for aa in range(2):
+                info[i].noise[pp][aa], info[i].rsrp[pp][aa] = res.noise[pp][aa], res.rsrp[pp][aa]
         pw = np.zeros(ncce, np.float32)
         ltelib.oracle().lteo_cce_power(ltelib.ptr(llr), ncce, ltelib.ptr(pw))
         for c in range(ncce):
@@ -60,6 +63,7 @@ def _worker(rank, world, port, q):
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     sys.path.insert(0, ROOT)
+    import ctypes as C
     from ltesniffer_b200 import capi, shard
     cell_args = (50, 1, 3, 1)
     mine = np.arange(rank, N_SF, world)
@@ -81,8 +85,39 @@ def _worker(rank, world, port, q):
         return shard.gather_full_tables(ct, world, "cpu")
     dcis2, _, _, _ = shard.search_and_select(L, srch2, info_all, comp_all, world, rank, 64 * N_SF, 64 * N_SF, full_fetch)
     key = lambda d: (int(d["sf"]), int(d["rnti"]), int(d["format"]), int(d["ncce"]), int(d["L"]), int(d["bits"]))
+    # ---- the packed exchange format of ltephy_decode_subframes_sharded (include/ltephy_shard.h): records packed to their used
+    # length per rank, offsets and records all-gathered, the walk reads them in place
+    comp_np = _compact(srch, info, cands).numpy().view(capi.COMPACT_DTYPE).reshape(-1)
+    rec, offs = capi.pack_subframes(srch, info, comp_np)
+    n_loc = len(mine)
+    assert offs[n_loc] == len(rec) < n_loc * capi.PACK_MAX_BYTES and all(int(o) % 16 == 0 for o in offs)
+    offs_all = [torch.zeros(n_loc + 1, dtype=torch.int32) for _ in range(world)]
+    dist.all_gather(offs_all, torch.from_numpy(offs.view(np.int32)))
+    pad = torch.zeros(n_loc * capi.PACK_MAX_BYTES, dtype=torch.uint8)
+    pad[:len(rec)] = torch.from_numpy(rec)
+    rec_all = [torch.zeros_like(pad) for _ in range(world)]
+    dist.all_gather(rec_all, pad)
+    bufs = [np.ascontiguousarray(t.numpy()) for t in rec_all]
+    offl = [np.ascontiguousarray(t.numpy().view(np.uint32)) for t in offs_all]
+    srch3 = capi.Search(*cell_args)
+    pk = capi.search_batch_packed(srch3, bufs, offl, n_loc, 64 * N_SF)
+    assert pk is not None
+    dcis3, tc = pk
+    assert [int(x) for x in tc[:, 0]] == list(range(N_SF))
+    gr3 = (capi.Grant * (64 * N_SF))()
+    gi3 = np.zeros(64 * N_SF, np.uint32)
+    ng3 = C.c_uint32(0)
+    assert L.ltephy_grants_from_dcis_tc(srch3.h, tc.ctypes.data_as(C.c_void_p), dcis3.ctypes.data_as(C.c_void_p), len(dcis3), world, rank, gr3,
+                                        gi3.ctypes.data_as(C.c_void_p), 64 * N_SF, C.byref(ng3)) == 0
+    srch4 = capi.Search(*cell_args)
+    L.ltephy_search_activate(srch4.h, RAR_RNTI, 0, 2)
+    assert capi.search_batch_packed(srch4, bufs, offl, n_loc, 64 * N_SF) is None      # refused, nothing consumed
+    full_all = shard.gather_full_tables(ct, world, "cpu").numpy().reshape(n_loc, world, -1)   # [i][r] global order -> per rank
+    fulls = [np.ascontiguousarray(full_all[:, r]) for r in range(world)]
+    dcis4, _ = capi.search_batch_packed(srch4, bufs, offl, n_loc, 64 * N_SF, full=fulls)
     q.put((rank, [key(d) for d in dcis], [(int(grants[i].sf), int(grants[i].rnti), int(grants[i].nof_re), int(gidx[i])) for i in range(ng)],
-           [key(d) for d in dcis2], len(fetched)))
+           [key(d) for d in dcis2], len(fetched), [key(d) for d in dcis3],
+           [(int(gr3[i].sf), int(gr3[i].rnti), int(gr3[i].nof_re), int(gi3[i])) for i in range(ng3.value)], [key(d) for d in dcis4]))
     dist.destroy_process_group()
 
 
@@ -119,6 +154,8 @@ def test_two_rank_sharding_matches_single_process(infra):
     L.ltephy_search_activate(srch2.h, RAR_RNTI, 0, 2)
     ref_dcis2 = walk_full(srch2)
     assert all(o[3] == ref_dcis2 and o[4] == 1 for o in out)         # fallback taken once per rank, same result as one process
+    # packed exchange format: same DCIs, same grants, same fallback result
+    assert all(o[5] == ref_dcis and o[6] == o[2] and o[7] == ref_dcis2 for o in out)
     srch3 = capi.Search(*cell_args)
     dcis, grants, gidx, ng = shard.search_and_select(L, srch3, info, _compact(srch3, info, cands), 1, 0, 64 * N_SF, 64 * N_SF)
     assert [key(d) for d in dcis] == ref_dcis
