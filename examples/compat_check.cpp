@@ -1,11 +1,11 @@
-// compat_check.cpp -- drives the tier-2 shim (include/ltephy_srsran_compat.h) the way the reference's SubframeWorker / DCISearch /
+// compat_check.cpp -- drives the tier-2 shim (the srsRAN-compatible header tree compat/srsran/..., libltephy_srsran_compat.so) the way the reference's SubframeWorker / DCISearch /
 // PDSCH_Decoder drive srsRAN, and dumps what it gets so that tests/test_compat_shim.py can compare it with the tier-1 results:
 //   per subframe: srsran_ue_dl_decode_fft_estimate; cfi, snr_db, FNV-1a of sf_symbols / ce, the PDCCH LLRs;
 //                 srsran_pdcch_dci_decode for every (location, payload size) given on the command line;
 //                 srsran_ue_dl_decode_pdsch for the grants of that subframe read from <grants.bin>.
 //   compat_check <iq.cf32> <nof_prb> <nof_ports> <cell_id> <nof_rx> <n_sf> <first_tti> <grants.bin> <out.bin> <nof_bits>...
 #include "ltephy_b200.h"
-#include "ltephy_srsran_compat.h"
+#include "srsran/srsran.h"
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -41,7 +41,8 @@ int main(int argc, char** argv)
   GrantRec              gr;
   while (fread(&gr, sizeof(gr), 1, gf) == 1) grants.push_back(gr);
 
-  const uint32_t sf_len = cell.nof_prb == 100 ? 30720 : cell.nof_prb == 75 ? 23040 : cell.nof_prb == 50 ? 15360 : cell.nof_prb == 25 ? 7680 : cell.nof_prb == 15 ? 3840 : 1920;
+  srsran_use_standard_symbol_size(true); // the capture handed to this program is sampled at the standard LTE rate (30.72 Msps at 100 PRB)
+  const uint32_t sf_len = SRSRAN_SF_LEN_PRB(cell.nof_prb);
   std::vector<cf_t> buf[2];
   cf_t*             in_buffer[SRSRAN_MAX_PORTS] = {};
   for (uint32_t a = 0; a < nof_rx; a++) buf[a].resize(3 * sf_len), in_buffer[a] = buf[a].data(); // SubframeBuffer over-allocates (src/src/SubframeBuffer.cc:25)

@@ -49,7 +49,10 @@ typedef struct {
   uint32_t turbo_max_iter; /* max-log-MAP iterations, >= 1 */
   int32_t  device;         /* CUDA device ordinal */
   uint32_t flags;          /* LTEPHY_FLAG_* */
-  uint32_t reserved[7];
+  uint32_t symbol_sz;      /* FFT size of one OFDM symbol = samples per subframe / 15.  0: the standard LTE rate (128 * 2^k: 2048 at 100 PRB,
+                              30.72 Msps).  srsRAN built without FORCE_STANDARD_RATE -- the reference's default, CMakeLists.txt:289-292 --
+                              samples 25 / 50 / 100 PRB at 3/4 of that (384 / 768 / 1536, srsran_symbol_sz): pass that value then. */
+  uint32_t reserved[6];
 } ltephy_cfg_t;
 
 #define LTEPHY_FLAG_SKIP_LOW_POWER 1u /* do not decode locations covering a CCE with mean|LLR| < 0.7 (they are never consulted) */
@@ -200,10 +203,19 @@ typedef struct {
   uint32_t sf;            /* index of the UL subframe inside the submitted UL batch */
   uint16_t rnti;
   uint8_t  qm, rv;        /* srsran_pusch_grant_t.tb.mod (2, 4, 6 or 8) / .rv */
-  uint32_t L_prb, n_prb;  /* contiguous allocation (no hopping); L_prb in the 2^a 3^b 5^c set, >= 3 */
+  uint32_t L_prb, n_prb;  /* contiguous allocation of slot 0; L_prb in the 2^a 3^b 5^c set (srsran_pusch_grant_t.L_prb / .n_prb[0]) */
   uint32_t n_dmrs2;       /* 36.211 Table 5.5.2.1.1-1 value of the DCI-0 cyclic shift field */
   int32_t  tbs;
+  uint32_t n_prb_slot1;   /* with LTEPHY_UL_FLAG_SLOT1: first PRB of slot 1 (srsran_pusch_grant_t.n_prb[1]), which differs from n_prb under
+                             type-1 PUSCH hopping (36.213 8.4.1); without the flag slot 1 uses n_prb */
+  /* UCI multiplexed with the data (36.212 5.2.2.6 - 5.2.4), as the reference configures it (src/src/UL_Sniffer_PUSCH.cc:429-450) */
+  uint8_t  nof_ack;       /* HARQ-ACK bits (0, 1, 2)            -> uci_cfg.ack[0].nof_acks */
+  uint8_t  ri_len;        /* rank-indicator bits (0, 1)         -> uci_cfg.cqi.ri_len */
+  uint16_t cqi_len;       /* CQI/PMI bits (0 = none)            -> srsran_cqi_size(&uci_cfg.cqi) */
+  uint8_t  I_offset_ack, I_offset_cqi, I_offset_ri; /* beta-offset indices (36.213 Tables 8.6.3-1..3) -> uci_offset */
+  uint8_t  flags;         /* LTEPHY_UL_FLAG_* */
 } ltephy_ul_grant_t;
+#define LTEPHY_UL_FLAG_SLOT1 1u
 typedef struct {
   float noise, rsrp;      /* srsran_chest_ul_res_t.noise_estimate, RSRP (linear) */
   float snr_db;           /* .snr_db   (UL_Sniffer_PUSCH.cc:268) */

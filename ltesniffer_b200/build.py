@@ -53,6 +53,8 @@ def stale():
         return True
     t = os.path.getmtime(OUT)
     deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(INC, f) for f in os.listdir(INC)]
+    comp = os.path.join(HERE, "..", "compat")
+    deps += [os.path.join(r, f) for r, _, fs in os.walk(comp) for f in fs]
     return any(os.path.getmtime(d) > t for d in deps)
 
 
@@ -108,8 +110,9 @@ def build(force=False, verbose=False):
 def build_compat():
     """tier-2 shim (srsRAN / FALCON names over the tier-1 C-ABI): host code only, links libltephy_b200.so"""
     cxx = shutil.which("g++") or "g++"
-    cmd = [cxx, "-O2", "-std=c++17", "-fPIC", "-shared", "-Wall", "-I" + os.path.join(HERE, "..", "compat"), "-o", COMPAT_OUT,
-           os.path.join(CSRC, "srsran_compat.cpp"), "-L" + HERE, "-lltephy_b200", "-Wl,-rpath,$ORIGIN"]
+    comp = os.path.join(HERE, "..", "compat")
+    cmd = [cxx, "-O2", "-std=c++17", "-fPIC", "-shared", "-Wall", "-I" + comp, "-o", COMPAT_OUT,
+           os.path.join(comp, "src", "srsran_host.cpp"), os.path.join(comp, "src", "srsran_phy.cpp"), "-L" + HERE, "-lltephy_b200", "-Wl,-rpath,$ORIGIN"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("building the srsRAN compatibility shim failed:\n" + (r.stdout + r.stderr)[-4000:])

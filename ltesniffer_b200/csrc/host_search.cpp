@@ -601,118 +601,142 @@ inline bool user_rnti(uint16_t r) { return r >= CRNTI_START && r <= CRNTI_END; }
 
 extern "C" {
 
+} // extern "C"
+
+// ---- stage 1: srsran_dci_msg_unpack_pdsch -- payload bits -> fields (36.212 5.3.3.1.2-5.3.3.1.5A), formats 1, 1A, 1C, 2, 2A
+int ltehost_unpack_dl_dci(const ltehost::Cell& c, uint32_t format, uint16_t rnti, uint64_t bits, ltehost::DlDciFields& f)
+{
+  const uint32_t N = c.nof_prb, P = rbg_size(N), nrbg = (N + P - 1) / P, hdr = N > 10, rivb = clog2(N * (N + 1) / 2);
+  f        = ltehost::DlDciFields{};
+  f.format = (uint8_t)format, f.rnti = rnti, f.n_prb1a = 2;
+  Bits b{bits};
+  switch (format) {
+    case ltehost::F1A:
+      if (b.get(1) != 1) return LTEPHY_ERROR;
+      f.alloc = 2;
+      f.dist  = b.get(1);
+      if (f.dist && N >= 50) {
+        f.ngap2 = b.get(1);
+        f.riv   = b.get(rivb - 1);
+      } else
+        f.riv = b.get(rivb);
+      f.mcs[0] = (uint8_t)b.get(5), f.harq_pid = (uint8_t)b.get(3), f.ndi[0] = (uint8_t)b.get(1), f.rv[0] = (uint8_t)b.get(2);
+      {
+        const uint32_t t = b.get(2);
+        if (user_rnti(rnti))
+          f.tpc = (uint8_t)t;
+        else
+          f.n_prb1a = (t & 1) ? 3 : 2;
+      }
+      f.tb_en[0] = true;
+      break;
+    case ltehost::F1C:
+      f.alloc = 2, f.dist = true;
+      if (N >= 50) f.ngap2 = b.get(1);
+      {
+        const uint32_t nv = nvrb(N, false) / (N < 50 ? 2 : 4);
+        f.riv             = b.get(clog2(nv * (nv + 1) / 2));
+      }
+      f.mcs[0]   = (uint8_t)b.get(5);
+      f.tb_en[0] = true;
+      break;
+    case ltehost::F1:
+    case ltehost::F2:
+    case ltehost::F2A:
+      f.alloc = hdr ? b.get(1) : 0;
+      if (f.alloc == 0)
+        f.rbg_mask = b.get(nrbg);
+      else {
+        const uint32_t sb = clog2(P);
+        f.t1_subset = b.get(sb), f.t1_shift = b.get(1), f.t1_mask = b.get(nrbg - sb - 1);
+      }
+      if (format == ltehost::F1) {
+        f.mcs[0] = (uint8_t)b.get(5), f.harq_pid = (uint8_t)b.get(3), f.ndi[0] = (uint8_t)b.get(1), f.rv[0] = (uint8_t)b.get(2), f.tpc = (uint8_t)b.get(2);
+        f.tb_en[0] = true;
+      } else {
+        f.tpc = (uint8_t)b.get(2), f.harq_pid = (uint8_t)b.get(3), f.tb_cw_swap = (uint8_t)b.get(1);
+        for (int i = 0; i < 2; i++) {
+          f.mcs[i] = (uint8_t)b.get(5), f.ndi[i] = (uint8_t)b.get(1), f.rv[i] = (uint8_t)b.get(2);
+          f.tb_en[i] = !(f.mcs[i] == 0 && f.rv[i] == 1);
+        }
+        if (format == ltehost::F2) f.pinfo = (uint8_t)b.get(c.nof_ports == 2 ? 3 : c.nof_ports == 4 ? 6 : 0);
+        if (format == ltehost::F2A && c.nof_ports == 4) f.pinfo = (uint8_t)b.get(2);
+      }
+      break;
+    default: return LTEPHY_ERROR; // format 0 is an uplink grant; 1B/1D/2B are rejected by dl_sniffer_config_mimo_type
+  }
+  return LTEPHY_SUCCESS;
+}
+// ---- stage 2: srsran_ra_dl_grant_to_grant_prb_allocation -- allocation fields -> PRBs of both slots (36.213 7.1.6)
+int ltehost_dl_prb_allocation(uint32_t N, const ltehost::DlDciFields& f, uint32_t mask[2][4], uint32_t* nof_prb_out)
+{
+  const uint32_t P = rbg_size(N), nrbg = (N + P - 1) / P;
+  auto           set = [&](uint32_t sl, uint32_t prb) { mask[sl][prb >> 5] |= 1u << (prb & 31u); };
+  memset(mask, 0, sizeof(uint32_t) * 8);
+  uint32_t nof_prb = 0;
+  if (f.alloc == 0) {
+    for (uint32_t i = 0; i < nrbg; i++)
+      if (f.rbg_mask & (1u << (nrbg - 1 - i)))
+        for (uint32_t j = i * P; j < (i + 1) * P && j < N; j++) set(0, j), set(1, j), nof_prb++;
+  } else if (f.alloc == 1) {
+    const uint32_t sb = clog2(P), nb = nrbg - sb - 1, q = (N - 1) / (P * P), pm = ((N - 1) / P) % P;
+    const uint32_t nsub  = f.t1_subset < pm ? q * P + P : f.t1_subset == pm ? q * P + (N - 1) % P + 1 : q * P;
+    const uint32_t shift = f.t1_shift ? nsub - nb : 0;
+    for (uint32_t i = 0; i < nb; i++)
+      if (f.t1_mask & (1u << (nb - 1 - i))) {
+        const uint32_t v = ((i + shift) / P) * P * P + f.t1_subset * P + (i + shift) % P;
+        if (v >= N) return LTEPHY_ERROR;
+        set(0, v), set(1, v), nof_prb++;
+      }
+  } else {
+    uint32_t L, S;
+    if (f.format == ltehost::F1C) {
+      const uint32_t step = N < 50 ? 2 : 4;
+      riv_decode(f.riv, nvrb(N, f.ngap2) / step, L, S);
+      L *= step, S *= step;
+    } else if (f.dist)
+      riv_decode(f.riv, nvrb(N, f.ngap2), L, S);
+    else
+      riv_decode(f.riv, N, L, S);
+    {
+      const uint32_t lim = f.dist ? nvrb(N, f.ngap2) : N; // an out-of-range RIV decodes to nonsense: reject it
+      if (L < 1 || L > lim || S >= lim || S + L > lim) return LTEPHY_ERROR;
+    }
+    if (!f.dist) {
+      for (uint32_t j = S; j < S + L; j++) set(0, j), set(1, j);
+    } else {
+      for (uint32_t v = S; v < S + L; v++) {
+        uint32_t p0, p1;
+        dvrb(N, f.ngap2, v, p0, p1);
+        if (p0 >= N || p1 >= N) return LTEPHY_ERROR;
+        set(0, p0), set(1, p1);
+      }
+    }
+    nof_prb = L;
+  }
+  if (!nof_prb) return LTEPHY_ERROR;
+  *nof_prb_out = nof_prb;
+  return LTEPHY_SUCCESS;
+}
+
+extern "C" {
 int ltephy_dci_to_grant(const ltephy_search_t* s, const ltephy_dci_t* d, uint32_t sf_idx, uint32_t cfi, int use_256qam_table, ltephy_grant_t* g,
                         ltephy_dci_fields_t* fields)
 {
   if (!s || !d || !g || cfi < 1 || cfi > 3 || sf_idx > 9) return LTEPHY_ERROR_INVALID_INPUTS;
   const ltehost::Cell& c = s->cell;
-  const uint32_t       N = c.nof_prb, P = rbg_size(N), nrbg = (N + P - 1) / P, hdr = N > 10, rivb = clog2(N * (N + 1) / 2);
+  const uint32_t       N = c.nof_prb;
   memset(g, 0, sizeof(*g));
+  ltehost::DlDciFields u;
+  if (ltehost_unpack_dl_dci(c, d->format, d->rnti, d->bits, u)) return LTEPHY_ERROR;
   ltephy_dci_fields_t f{};
-  Bits                b{d->bits};
-  f.format = d->format, f.rnti = d->rnti;
-  uint32_t alloc = 0, rbg_mask = 0, t1_subset = 0, t1_shift = 0, t1_mask = 0, riv = 0;
-  bool     dist = false, ngap2 = false;
-  uint32_t n_prb1a = 2;
-  bool     tb_en[2] = {false, false};
-  switch (d->format) {
-    case ltehost::F1A:
-      if (b.get(1) != 1) return LTEPHY_ERROR;
-      alloc = 2;
-      dist  = b.get(1);
-      if (dist && N >= 50) {
-        ngap2 = b.get(1);
-        riv   = b.get(rivb - 1);
-      } else
-        riv = b.get(rivb);
-      f.mcs[0] = (uint8_t)b.get(5), f.harq_pid = (uint8_t)b.get(3), f.ndi[0] = (uint8_t)b.get(1), f.rv[0] = (uint8_t)b.get(2);
-      {
-        const uint32_t t = b.get(2);
-        if (user_rnti(d->rnti))
-          f.tpc = (uint8_t)t;
-        else
-          n_prb1a = (t & 1) ? 3 : 2;
-      }
-      tb_en[0] = true;
-      break;
-    case ltehost::F1C:
-      alloc = 2, dist = true;
-      if (N >= 50) ngap2 = b.get(1);
-      {
-        const uint32_t nv = nvrb(N, false) / (N < 50 ? 2 : 4);
-        riv               = b.get(clog2(nv * (nv + 1) / 2));
-      }
-      f.mcs[0] = (uint8_t)b.get(5);
-      tb_en[0] = true;
-      break;
-    case ltehost::F1:
-    case ltehost::F2:
-    case ltehost::F2A:
-      alloc = hdr ? b.get(1) : 0;
-      if (alloc == 0)
-        rbg_mask = b.get(nrbg);
-      else {
-        const uint32_t sb = clog2(P);
-        t1_subset = b.get(sb), t1_shift = b.get(1), t1_mask = b.get(nrbg - sb - 1);
-      }
-      if (d->format == ltehost::F1) {
-        f.mcs[0] = (uint8_t)b.get(5), f.harq_pid = (uint8_t)b.get(3), f.ndi[0] = (uint8_t)b.get(1), f.rv[0] = (uint8_t)b.get(2), f.tpc = (uint8_t)b.get(2);
-        tb_en[0] = true;
-      } else {
-        f.tpc = (uint8_t)b.get(2), f.harq_pid = (uint8_t)b.get(3), f.tb_cw_swap = (uint8_t)b.get(1);
-        for (int i = 0; i < 2; i++) {
-          f.mcs[i] = (uint8_t)b.get(5), f.ndi[i] = (uint8_t)b.get(1), f.rv[i] = (uint8_t)b.get(2);
-          tb_en[i] = !(f.mcs[i] == 0 && f.rv[i] == 1);
-        }
-        if (d->format == ltehost::F2) f.pinfo = (uint8_t)b.get(c.nof_ports == 2 ? 3 : c.nof_ports == 4 ? 6 : 0);
-        if (d->format == ltehost::F2A && c.nof_ports == 4) f.pinfo = (uint8_t)b.get(2);
-      }
-      break;
-    default: return LTEPHY_ERROR; // format 0 is an uplink grant; 1B/1D/2B are rejected by dl_sniffer_config_mimo_type
-  }
-  f.alloc_type = (uint8_t)alloc;
-  // ---- PRB allocation (srsran_ra_dl_grant_to_grant_prb_allocation) ----
-  uint32_t nof_prb = 0;
-  if (alloc == 0) {
-    for (uint32_t i = 0; i < nrbg; i++)
-      if (rbg_mask & (1u << (nrbg - 1 - i)))
-        for (uint32_t j = i * P; j < (i + 1) * P && j < N; j++) set_prb(*g, 0, j), set_prb(*g, 1, j), nof_prb++;
-  } else if (alloc == 1) {
-    const uint32_t sb = clog2(P), nb = nrbg - sb - 1, q = (N - 1) / (P * P), pm = ((N - 1) / P) % P;
-    const uint32_t nsub  = t1_subset < pm ? q * P + P : t1_subset == pm ? q * P + (N - 1) % P + 1 : q * P;
-    const uint32_t shift = t1_shift ? nsub - nb : 0;
-    for (uint32_t i = 0; i < nb; i++)
-      if (t1_mask & (1u << (nb - 1 - i))) {
-        const uint32_t v = ((i + shift) / P) * P * P + t1_subset * P + (i + shift) % P;
-        if (v >= N) return LTEPHY_ERROR;
-        set_prb(*g, 0, v), set_prb(*g, 1, v), nof_prb++;
-      }
-  } else {
-    uint32_t L, S;
-    if (d->format == ltehost::F1C) {
-      const uint32_t step = N < 50 ? 2 : 4;
-      riv_decode(riv, nvrb(N, ngap2) / step, L, S);
-      L *= step, S *= step;
-    } else if (dist)
-      riv_decode(riv, nvrb(N, ngap2), L, S);
-    else
-      riv_decode(riv, N, L, S);
-    {
-      const uint32_t lim = dist ? nvrb(N, ngap2) : N; // an out-of-range RIV decodes to nonsense: reject it
-      if (L < 1 || L > lim || S >= lim || S + L > lim) return LTEPHY_ERROR;
-    }
-    if (!dist) {
-      for (uint32_t j = S; j < S + L; j++) set_prb(*g, 0, j), set_prb(*g, 1, j);
-    } else {
-      for (uint32_t v = S; v < S + L; v++) {
-        uint32_t p0, p1;
-        dvrb(N, ngap2, v, p0, p1);
-        if (p0 >= N || p1 >= N) return LTEPHY_ERROR;
-        set_prb(*g, 0, p0), set_prb(*g, 1, p1);
-      }
-    }
-    nof_prb = L;
-  }
+  f.format = d->format, f.rnti = d->rnti, f.alloc_type = (uint8_t)u.alloc, f.harq_pid = u.harq_pid, f.tpc = u.tpc, f.tb_cw_swap = u.tb_cw_swap,
+  f.pinfo = u.pinfo;
+  for (int i = 0; i < 2; i++) f.mcs[i] = u.mcs[i], f.rv[i] = u.rv[i], f.ndi[i] = u.ndi[i];
+  const bool     tb_en[2] = {u.tb_en[0], u.tb_en[1]};
+  const uint32_t n_prb1a  = u.n_prb1a;
+  uint32_t       nof_prb  = 0;
+  if (ltehost_dl_prb_allocation(N, u, g->prb_mask, &nof_prb)) return LTEPHY_ERROR;
   if (!nof_prb) return LTEPHY_ERROR;
   f.nof_prb = nof_prb;
   // ---- transport blocks (dl_sniffer_compute_tb, dl_sniffer_pdsch.c:14-92) ----

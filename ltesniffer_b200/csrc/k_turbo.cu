@@ -10,73 +10,112 @@
 #include "dev_common.cuh"
 
 #define TD_WL 32
-#define TD_HALF 16
 #define TD_NINF (-8192)
+#define TD_BIAS 0x4C00u                 // every state metric is kept as (true value + TD_BIAS) in both 16-bit fields
+#define TD_BIASW 0x4C004C00u
 
+// ---- arithmetic model ------------------------------------------------------------------------------------------------
+// Integer adds issue on two pipes of an SM sub-partition at 16 lanes / clk each: the ALU pipe (IADD3, LOP3, VIADD.16x2,
+// VIMNMX.S16x2, VIADDMNMX.S16x2) and the FMA pipe (IMAD).  A decoder written only with packed 16x2 adds and maxes is bound by the
+// ALU pipe at half the issue rate (round-1 ncu: math-pipe-throttle stalls, 51-62 % issue slots).  Here every plain add runs as a
+// 32-bit IMAD (a * 1 + b, with the 1 in a kernel parameter so that it stays an IMAD), which is exact field-wise as long as the low
+// field of the left operand and of the result is non-negative: state metrics therefore carry a bias of 0x4C00 per field (bounds
+// below), and the signed addends (branch metrics, normalisation reference) are used in "32-form" hi * 65536 + lo.  Maxes and add-max stay packed on the ALU pipe.  The decisions are offset-
+// invariant, so bias, branch-metric offset and normalisation schedule do not change any output (oracle/lte_oracle.c, siso()).
+//
+// Branch metrics: the oracle's edge metric for (u, parity) is +-xa +- p.  Adding xa + p to all 16 edges of a step gives
+//   (0,0) -> 0,  (1,1) -> G0 = 2 (xa + p),  (1,0) -> X = 2 xa,  (0,1) -> P = 2 p,
+// so 4 of the 8 add-compare-selects of a step need one add instead of two.  |X| <= 1532, |P| <= 510, |G0| <= 2042.
+// Ranges, inputs |sys|, |par| <= 255 and |a-priori| <= 511 (true values relative to the last normalisation, which sets state 0 to 0
+// and happens every 2 steps): the metrics of any two states differ by at most 3 * 2042 = 6126 (every state is reached from every
+// state in 3 steps), state 0 drifts by at most 2 * 2042 between normalisations, an add-compare-select candidate adds one more
+// edge: stored values lie in [-10210, +10210], candidates in [-12252, +12252].  The first window starts from (0, -8192 x 7): its
+// -8192-derived values survive two steps (after three steps every state has a path from state 0): stored >= -16360, candidates
+// >= -18402.  The termination metrics are real after the three tail steps (>= -3060).  With the bias 0x4C00 = 19456 every field
+// stays in [1054, 31708] (signed and unsigned compares agree), and alpha + (beta + edge), which carries the bias twice and is
+// compared unsigned, stays below 61374 < 65536.
+struct TdConst {
+  uint32_t one, minus_one, minus_two, three; // run-time constants: keep the multiplies in IMAD form (FMA pipe)
+};
 __device__ __forceinline__ uint32_t vadd(uint32_t a, uint32_t b) { return __vadd2(a, b); }
-__device__ __forceinline__ uint32_t vneg(uint32_t a) { return __vneg2(a); }
-__device__ __forceinline__ uint32_t vamax(uint32_t a, uint32_t b, uint32_t c) { return __viaddmax_s16x2(a, b, c); } // max(a+b, c)
+__device__ __forceinline__ uint32_t vsub(uint32_t a, uint32_t b) { return __vsub2(a, b); }
+__device__ __forceinline__ uint32_t vamax(uint32_t a, uint32_t b, uint32_t c) { return __viaddmax_s16x2(a, b, c); }  // max(a+b, c), signed fields
+__device__ __forceinline__ uint32_t vamaxu(uint32_t a, uint32_t b, uint32_t c) { return __viaddmax_u16x2(a, b, c); } // unsigned fields
 __device__ __forceinline__ uint32_t vmax(uint32_t a, uint32_t b) { return __vmaxs2(a, b); }
+__device__ __forceinline__ uint32_t vmin(uint32_t a, uint32_t b) { return __vmins2(a, b); }
 __device__ __forceinline__ uint32_t pk2(int lo, int hi) { return ((uint32_t)lo & 0xFFFFu) | ((uint32_t)hi << 16); }
 __device__ __forceinline__ int      lo_s(uint32_t v) { return (int)(short)(v & 0xFFFFu); }
 __device__ __forceinline__ int      hi_s(uint32_t v) { return (int)(short)(v >> 16); }
+__device__ __forceinline__ uint32_t add32(const TdConst& c, uint32_t a, uint32_t b) { return a * c.one + b; }       // a + b on the FMA pipe
+__device__ __forceinline__ uint32_t sub32(const TdConst& c, uint32_t a, uint32_t b) { return b * c.minus_one + a; } // a - b on the FMA pipe
+// packed signed pair -> 32-form (hi * 65536 + lo): subtract 0x10000 when the low field is negative
+__device__ __forceinline__ uint32_t to32(const TdConst& c, uint32_t p) { return (p & 0x8000u) * c.minus_two + p; }
 
 struct St8 {
   uint32_t s[8];
 };
 
-__device__ __forceinline__ void alpha_step(St8& a, uint32_t g0, uint32_t g1, uint32_t ng0, uint32_t ng1)
+// X32: 2 xa in 32-form; Pp: 2 p packed; G0p: 2 (xa + p) packed
+__device__ __forceinline__ void alpha_step(const TdConst& c, St8& a, uint32_t X32, uint32_t Pp, uint32_t G0p)
 {
   St8 n;
-  n.s[0] = vamax(a.s[0], ng0, vadd(a.s[1], g0));
-  n.s[4] = vamax(a.s[0], g0, vadd(a.s[1], ng0));
-  n.s[1] = vamax(a.s[2], g1, vadd(a.s[3], ng1));
-  n.s[5] = vamax(a.s[2], ng1, vadd(a.s[3], g1));
-  n.s[2] = vamax(a.s[4], ng1, vadd(a.s[5], g1));
-  n.s[6] = vamax(a.s[4], g1, vadd(a.s[5], ng1));
-  n.s[3] = vamax(a.s[6], g0, vadd(a.s[7], ng0));
-  n.s[7] = vamax(a.s[6], ng0, vadd(a.s[7], g0));
+  n.s[0] = vamax(a.s[1], G0p, a.s[0]);
+  n.s[4] = vamax(a.s[0], G0p, a.s[1]);
+  n.s[1] = vamax(a.s[3], Pp, add32(c, a.s[2], X32));
+  n.s[5] = vamax(a.s[2], Pp, add32(c, a.s[3], X32));
+  n.s[2] = vamax(a.s[4], Pp, add32(c, a.s[5], X32));
+  n.s[6] = vamax(a.s[5], Pp, add32(c, a.s[4], X32));
+  n.s[3] = vamax(a.s[6], G0p, a.s[7]);
+  n.s[7] = vamax(a.s[7], G0p, a.s[6]);
   a      = n;
 }
-__device__ __forceinline__ void norm8(St8& a)
+__device__ __forceinline__ void norm8(const TdConst& c, St8& a)
 {
-  const uint32_t r = vneg(a.s[0]);
+  const uint32_t r = sub32(c, a.s[0], TD_BIASW); // 32-form of (state 0 - bias)
 #pragma unroll
-  for (int i = 0; i < 8; i++) a.s[i] = vadd(a.s[i], r);
+  for (int i = 0; i < 8; i++) a.s[i] = sub32(c, a.s[i], r);
 }
-// beta update + LLR numerators. b = beta_{k+1} in, beta_k out; al = alpha_k.
-__device__ __forceinline__ void beta_llr_step(St8& b, const St8& al, uint32_t g0, uint32_t g1, uint32_t ng0, uint32_t ng1, uint32_t& m1, uint32_t& m0)
+// beta update + LLR numerators. b = beta_{k+1} in, beta_k out; al = alpha_k.  m1, m0 carry a double bias (compare unsigned).
+__device__ __forceinline__ void beta_llr_step(const TdConst& c, St8& b, const St8& al, uint32_t X32, uint32_t P32, uint32_t G032, uint32_t& m1,
+                                              uint32_t& m0)
 {
   uint32_t c0[8], c1[8];
-  c0[0] = vadd(b.s[0], ng0), c1[0] = vadd(b.s[4], g0);
-  c0[1] = vadd(b.s[4], ng0), c1[1] = vadd(b.s[0], g0);
-  c0[2] = vadd(b.s[5], ng1), c1[2] = vadd(b.s[1], g1);
-  c0[3] = vadd(b.s[1], ng1), c1[3] = vadd(b.s[5], g1);
-  c0[4] = vadd(b.s[2], ng1), c1[4] = vadd(b.s[6], g1);
-  c0[5] = vadd(b.s[6], ng1), c1[5] = vadd(b.s[2], g1);
-  c0[6] = vadd(b.s[7], ng0), c1[6] = vadd(b.s[3], g0);
-  c0[7] = vadd(b.s[3], ng0), c1[7] = vadd(b.s[7], g0);
-  m1    = vadd(al.s[0], c1[0]);
-  m0    = vadd(al.s[0], c0[0]);
+  c0[0] = b.s[0], c1[0] = add32(c, b.s[4], G032);
+  c0[1] = b.s[4], c1[1] = add32(c, b.s[0], G032);
+  c0[2] = add32(c, b.s[5], P32), c1[2] = add32(c, b.s[1], X32);
+  c0[3] = add32(c, b.s[1], P32), c1[3] = add32(c, b.s[5], X32);
+  c0[4] = add32(c, b.s[2], P32), c1[4] = add32(c, b.s[6], X32);
+  c0[5] = add32(c, b.s[6], P32), c1[5] = add32(c, b.s[2], X32);
+  c0[6] = b.s[7], c1[6] = add32(c, b.s[3], G032);
+  c0[7] = b.s[3], c1[7] = add32(c, b.s[7], G032);
+  m1    = add32(c, al.s[0], c1[0]);
+  m0    = add32(c, al.s[0], c0[0]);
 #pragma unroll
   for (int s = 1; s < 8; s++) {
-    m1 = vamax(al.s[s], c1[s], m1);
-    m0 = vamax(al.s[s], c0[s], m0);
+    m1 = vamaxu(al.s[s], c1[s], m1);
+    m0 = vamaxu(al.s[s], c0[s], m0);
   }
 #pragma unroll
   for (int s = 0; s < 8; s++) b.s[s] = vmax(c0[s], c1[s]);
 }
-__device__ __forceinline__ int ext_of(int L, int xa)
+// extrinsic of both code blocks: clamp((3 (L - 2 xa)) >> 3, +-511) per field, L = m1 - m0, Xp = 2 xa packed.
+// |3 v >> 3| reaches 512 at |v| >= 1366, so v is clamped to +-1365 first; then t = v + 1400 >= 0 per field, 3 t is a plain
+// multiply, (3 t) >> 3 - 525 = floor(3 v / 8) (4200 = 8 * 525), and only the negative side can still land on -512.
+__device__ __forceinline__ uint32_t ext_pair(const TdConst& c, uint32_t L, uint32_t Xp)
 {
-  int e = (3 * (L - 2 * xa)) >> 3;
-  return e > 511 ? 511 : (e < -511 ? -511 : e);
+  uint32_t v = vsub(L, Xp);
+  v          = vmax(vmin(v, 0x05550555u), 0xFAABFAABu);          // +-1365
+  const uint32_t t = vadd(v, 0x05780578u) * c.three;             // 3 (v + 1400), fields < 8400: no carry between fields
+  const uint32_t e = vsub((t >> 3) & 0x07FF07FFu, 0x020D020Du);  // - 525
+  return vmax(e, 0xFE01FE01u);                                   // -511
 }
 
 struct TurboView {
-  uint32_t *sysT, *p1T, *p2T, *aprT, *extT, *tails;
-  uint32_t* bnd; // [2 siso][2 (A,B)][NW][8]
+  const uint32_t *sysT, *p1T, *p2T, *tails;
+  uint32_t*       ext; // [32][NW] a-priori / extrinsic values, window-transposed, updated in place by both constituent decoders
+  uint32_t*       bnd; // [2 siso][2 (A,B)][NW][8]
   const uint16_t* piT;
-  uint32_t  K, NW;
+  uint32_t        K, NW;
 };
 
 #define TD_SUB 8 // alpha is kept in shared memory for TD_SUB steps at a time
@@ -84,29 +123,29 @@ struct TurboView {
 
 // one SISO pass for window w.  IL = second constituent decoder (interleaved order); NT = threads per CTA
 // (compile time, so every shared-memory access is base + immediate); FULL = every window has 32 steps.
-// Shared memory per thread: g_s[32] (branch metrics g0 = xa+p, g1 = xa-p, staged once per pass with all the
-// global loads in flight together), pos_s[32] (where the extrinsic goes), alpha_s[TD_SUB][2] (uint4).
+// Shared memory per thread: g_s[32] ((2 xa, 2 p) packed, staged once per pass with all the global loads of the window in flight
+// together), pos_s[32] (natural bit index of the step in the interleaved pass), alpha_s[TD_SUB][2] (uint4).
 template <bool IL, int NT, bool FULL>
-__device__ __forceinline__ void siso_pass(const TurboView& tv, uint4* __restrict__ alpha_t, uint2* __restrict__ g_t, uint16_t* __restrict__ pos_t,
-                                          uint32_t* bits_s, uint32_t w, bool active, const uint32_t* btail, bool first_iter)
+__device__ __forceinline__ void siso_pass(const TdConst& c, const TurboView& tv, uint4* __restrict__ alpha_t, uint2* __restrict__ g_t,
+                                          uint16_t* __restrict__ pos_t, uint32_t* bits_s, uint32_t w, bool active, const uint32_t* btail,
+                                          bool first_iter)
 {
   const uint32_t  K = tv.K, NW = tv.NW;
   const uint32_t  len = FULL ? (uint32_t)TD_WL : (active ? min((uint32_t)TD_WL, K - w * TD_WL) : 0u);
   uint32_t*       A  = tv.bnd + (size_t)(IL ? 2 : 0) * NW * 8;
   uint32_t*       B  = A + (size_t)NW * 8;
   const uint32_t* par = IL ? tv.p2T : tv.p1T;
-  const uint32_t* apr = IL ? tv.extT : tv.aprT;
-  uint32_t*       out = IL ? tv.aprT : tv.extT;
+  uint32_t*       ext = tv.ext;
 
   St8 a0, b;
   if (active) {
 #pragma unroll
     for (int s = 0; s < 8; s++) {
-      a0.s[s] = (w == 0) ? (s ? pk2(TD_NINF, TD_NINF) : 0u) : A[(size_t)w * 8 + s];
+      a0.s[s] = (w == 0) ? (s ? pk2(TD_NINF + (int)TD_BIAS, TD_NINF + (int)TD_BIAS) : TD_BIASW) : A[(size_t)w * 8 + s];
       b.s[s]  = (w == NW - 1) ? btail[s] : B[(size_t)w * 8 + s];
     }
     // ---- stage the window: every load of the pass is issued here, independent of the recursions ----
-#pragma unroll 8
+#pragma unroll 16
     for (uint32_t j = 0; j < TD_WL; j++) {
       if (FULL || j < len) {
         uint32_t pos;
@@ -115,11 +154,11 @@ __device__ __forceinline__ void siso_pass(const TurboView& tv, uint4* __restrict
         else {
           const uint32_t pi = tv.piT[j * NW + w];
           pos               = (pi & 31u) * NW + (pi >> 5);
+          pos_t[j * NT]     = (uint16_t)pi;
         }
-        const uint32_t sy = tv.sysT[pos], ap = (!IL && first_iter) ? 0u : apr[pos], p = par[j * NW + w];
+        const uint32_t sy = tv.sysT[pos], ap = (!IL && first_iter) ? 0u : ext[pos], p = par[j * NW + w];
         const uint32_t xa = vadd(sy, ap);
-        g_t[j * NT]       = make_uint2(vadd(xa, p), vadd(xa, vneg(p)));
-        pos_t[j * NT]     = (uint16_t)pos;
+        g_t[j * NT]       = make_uint2(vadd(xa, xa), vadd(p, p));
       }
     }
   }
@@ -136,12 +175,12 @@ __device__ __forceinline__ void siso_pass(const TurboView& tv, uint4* __restrict
         const uint32_t j = sw * TD_SUB + jj;
         if (FULL || j < len) {
           const uint2 g = g_t[j * NT];
-          alpha_step(a, g.x, g.y, vneg(g.x), vneg(g.y));
-          if ((jj & 3u) == 3u) norm8(a);
+          alpha_step(c, a, to32(c, g.x), g.y, vadd(g.x, g.y));
+          if ((jj & 1u) == 1u) norm8(c, a);
         }
       }
     }
-    norm8(a);
+    norm8(c, a);
     if (w + 1 < NW) {
 #pragma unroll
       for (int s = 0; s < 8; s++) A[(size_t)(w + 1) * 8 + s] = a.s[s];
@@ -160,8 +199,8 @@ __device__ __forceinline__ void siso_pass(const TurboView& tv, uint4* __restrict
           alpha_t[(jj * 2 + 1) * NT] = make_uint4(af.s[4], af.s[5], af.s[6], af.s[7]);
           if (jj + 1 < TD_SUB) {
             const uint2 g = g_t[j * NT];
-            alpha_step(af, g.x, g.y, vneg(g.x), vneg(g.y));
-            if ((jj & 3u) == 3u) norm8(af);
+            alpha_step(c, af, to32(c, g.x), g.y, vadd(g.x, g.y));
+            if ((jj & 1u) == 1u) norm8(c, af);
           }
         }
       }
@@ -173,23 +212,25 @@ __device__ __forceinline__ void siso_pass(const TurboView& tv, uint4* __restrict
           const uint4 u0 = alpha_t[(jj * 2 + 0) * NT], u1 = alpha_t[(jj * 2 + 1) * NT];
           St8         al;
           al.s[0] = u0.x, al.s[1] = u0.y, al.s[2] = u0.z, al.s[3] = u0.w, al.s[4] = u1.x, al.s[5] = u1.y, al.s[6] = u1.z, al.s[7] = u1.w;
-          uint32_t m1, m0;
-          beta_llr_step(b, al, g.x, g.y, vneg(g.x), vneg(g.y), m1, m0);
-          if ((jj & 3) == 0) norm8(b);
-          // xa = (g0 + g1) / 2 exactly, per half
-          const int      xal = (lo_s(g.x) + lo_s(g.y)) >> 1, xah = (hi_s(g.x) + hi_s(g.y)) >> 1;
-          const int      Ll = lo_s(m1) - lo_s(m0), Lh = hi_s(m1) - hi_s(m0);
-          const uint32_t ps = pos_t[j * NT];
-          out[ps]           = pk2(ext_of(Ll, xal), ext_of(Lh, xah));
-          if (IL) {
-            const uint32_t pi = (ps % NW) * 32u + ps / NW; // natural bit index back from the transposed position
-            if (Ll > 0) atomicOr(&bits_s[pi >> 5], 0x80000000u >> (pi & 31u));
-            if (Lh > 0) atomicOr(&bits_s[(TD_WL * 6) + (pi >> 5)], 0x80000000u >> (pi & 31u));
+          const uint32_t X32 = to32(c, g.x), P32 = to32(c, g.y);
+          uint32_t       m1, m0;
+          beta_llr_step(c, b, al, X32, P32, add32(c, X32, P32), m1, m0);
+          if ((jj & 1) == 0) norm8(c, b);
+          const uint32_t L = vsub(m1, m0); // the double bias cancels
+          uint32_t       ps;
+          if (!IL)
+            ps = j * NW + w;
+          else {
+            const uint32_t pi = pos_t[j * NT];
+            ps                = (pi & 31u) * NW + (pi >> 5);
+            if ((int)(L << 16) > 0) atomicOr(&bits_s[pi >> 5], 0x80000000u >> (pi & 31u));
+            if ((int)L >= 0x10000) atomicOr(&bits_s[(TD_WL * 6) + (pi >> 5)], 0x80000000u >> (pi & 31u));
           }
+          ext[ps] = ext_pair(c, L, g.x);
         }
       }
     }
-    norm8(b);
+    norm8(c, b);
     if (w > 0) {
 #pragma unroll
       for (int s = 0; s < 8; s++) B[(size_t)(w - 1) * 8 + s] = b.s[s];
@@ -220,11 +261,18 @@ __device__ __forceinline__ uint32_t gf_mod24(uint32_t v, uint32_t nbits, uint32_
   return r;
 }
 
+// Persistent CTAs: the grid is sized to the number of CTAs the GPU can hold; each CTA takes code-block pairs from a queue
+// (early CRC stop makes the pairs' run times vary by up to 8x) and keeps the extrinsic values and the window-boundary metrics of
+// the pair it is working on in ITS OWN scratch slot (scratch + slot * slot_words).  A slot is rewritten for every pair, so its
+// lines stay dirty in L2 and are never written back for a finished pair: round 1 kept this state inside each pair's buffer and
+// paid 433 MB of DRAM write-back per 1000-subframe step for it.
 template <int NT, bool FULL>
-__global__ void __launch_bounds__(NT, (NT > 128 ? 2 : (NT > 64 ? 3 : 6))) turbo_kernel(const DevPair* __restrict__ pairs, uint32_t* __restrict__ pool, const uint16_t* __restrict__ pi_pool,
+__global__ void __launch_bounds__(NT, (NT > 128 ? 2 : (NT > 64 ? 3 : 6))) turbo_kernel(const DevPair* __restrict__ pairs, uint32_t npairs, uint32_t* __restrict__ queue,
+                                                    const uint32_t* __restrict__ pool, uint32_t* __restrict__ scratch, uint32_t slot_words,
+                                                    const uint16_t* __restrict__ pi_pool,
                                                     const uint32_t* __restrict__ pi_off, const uint32_t* __restrict__ xpowA,
                                                     const uint32_t* __restrict__ xpowB, uint8_t* __restrict__ payload, uint8_t* __restrict__ cb_iters,
-                                                    uint8_t* __restrict__ cb_crc, uint32_t max_iter)
+                                                    uint8_t* __restrict__ cb_crc, uint32_t max_iter, const TdConst c)
 {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   uint4*             alpha_t = reinterpret_cast<uint4*>(smem_raw) + threadIdx.x;                          // [TD_SUB][2][NT]
@@ -234,23 +282,31 @@ __global__ void __launch_bounds__(NT, (NT > 128 ? 2 : (NT > 64 ? 3 : 6))) turbo_
   __shared__ uint32_t btail[2][8];
   __shared__ uint32_t red_s[8];
   __shared__ uint32_t done_s[2];
+  __shared__ uint32_t next_s;
 
-  const DevPair  P = pairs[blockIdx.x];
-  const uint32_t K = P.K, NW = P.NW, tid = threadIdx.x, nthreads = NT;
+  const uint32_t tid = threadIdx.x, nthreads = NT;
+  uint32_t* const my_scratch = scratch + (size_t)blockIdx.x * slot_words;
+  for (;;) {
+    __syncthreads(); // the previous pair is completely done (shared memory and scratch slot are free)
+    if (tid == 0) next_s = atomicAdd(queue, 1u);
+    __syncthreads();
+    const uint32_t pidx = next_s;
+    if (pidx >= npairs) break;
+  const DevPair  P = pairs[pidx];
+  const uint32_t K = P.K, NW = P.NW;
   const bool     active = tid < NW;
   TurboView      tv;
   tv.sysT  = pool + P.buf_off;
   tv.p1T   = tv.sysT + 32 * NW;
   tv.p2T   = tv.p1T + 32 * NW;
-  tv.aprT  = tv.p2T + 32 * NW;
-  tv.extT  = tv.aprT + 32 * NW;
-  tv.tails = tv.extT + 32 * NW;
-  tv.bnd   = tv.tails + 12;
-  tv.piT   = pi_pool + pi_off[blockIdx.x];
+  tv.tails = tv.p2T + 32 * NW;
+  tv.ext   = my_scratch;
+  tv.bnd   = my_scratch + 32 * NW;
+  tv.piT   = pi_pool + pi_off[pidx];
   tv.K = K, tv.NW = NW;
 
-  // boundary metrics start "unknown" (all zero); the a-priori input of the very first half iteration is zero
-  for (uint32_t i = tid; i < 4 * NW * 8; i += nthreads) tv.bnd[i] = 0u;
+  // boundary metrics start "unknown" (all equal: the bias); the a-priori input of the very first half iteration is zero
+  for (uint32_t i = tid; i < 4 * NW * 8; i += nthreads) tv.bnd[i] = TD_BIASW;
   if (tid < 2) done_s[tid] = (tid < P.ncb) ? 0u : 1u;
   if (tid == 0) {
     // beta at K from the termination bits, both constituent codes, both code blocks (scalar int32)
@@ -284,7 +340,7 @@ __global__ void __launch_bounds__(NT, (NT > 128 ? 2 : (NT > 64 ? 3 : 6))) turbo_
         }
         const int ref = bt[0];
         for (int s = 0; s < 8; s++) {
-          const int      v = bt[s] - ref;
+          const int      v = bt[s] - ref + (int)TD_BIAS;
           const uint32_t o = btail[dec][s];
           btail[dec][s]    = h ? ((o & 0xFFFFu) | ((uint32_t)v << 16)) : ((uint32_t)v & 0xFFFFu);
         }
@@ -296,8 +352,8 @@ __global__ void __launch_bounds__(NT, (NT > 128 ? 2 : (NT > 64 ? 3 : 6))) turbo_
   uint32_t it = 0;
   while (it < max_iter) {
     for (uint32_t i = tid; i < 2 * TD_WL * 6; i += nthreads) bits_s[i] = 0u;
-    siso_pass<false, NT, FULL>(tv, alpha_t, g_t, pos_t, bits_s, tid, active, btail[0], it == 0);
-    siso_pass<true, NT, FULL>(tv, alpha_t, g_t, pos_t, bits_s, tid, active, btail[1], false);
+    siso_pass<false, NT, FULL>(c, tv, alpha_t, g_t, pos_t, bits_s, tid, active, btail[0], it == 0);
+    siso_pass<true, NT, FULL>(c, tv, alpha_t, g_t, pos_t, bits_s, tid, active, btail[1], false);
     it++;
     // ---- CRC over the K decided bits of each code block -------------------------------------------
     bool all_done = true;
@@ -342,6 +398,7 @@ __global__ void __launch_bounds__(NT, (NT > 128 ? 2 : (NT > 64 ? 3 : 6))) turbo_
     __syncthreads();
     if (all_done) break;
   }
+  } // pair queue
 }
 
 // ---- transport-block CRC24A over the assembled payload (tbs/8 data bytes + 3 CRC bytes) -------------
@@ -385,27 +442,42 @@ __global__ void __launch_bounds__(256) tb_crc_kernel(const DevTb* __restrict__ t
 }
 
 template <int NT, bool FULL>
-static void launch_turbo_t(const DevPair* pairs, uint32_t npairs, uint32_t* pool, const uint16_t* pi_pool, const uint32_t* pi_off, const uint32_t* xpowA,
-                           const uint32_t* xpowB, uint8_t* payload, uint8_t* cb_iters, uint8_t* cb_crc, uint32_t max_iter, cudaStream_t st)
+static void launch_turbo_t(const DevPair* pairs, uint32_t npairs, uint32_t* queue, const uint32_t* pool, uint32_t* scratch, size_t scratch_words,
+                           const uint16_t* pi_pool, const uint32_t* pi_off, const uint32_t* xpowA, const uint32_t* xpowB, uint8_t* payload,
+                           uint8_t* cb_iters, uint8_t* cb_crc, uint32_t max_iter, cudaStream_t st)
 {
   const size_t smem = (size_t)NT * (TD_SUB * 2 * sizeof(uint4) + TD_WL * sizeof(uint2) + TD_WL * sizeof(uint16_t));
   // the attribute belongs to the current device / context (handles may live on different devices): set it on every launch
   cudaFuncSetAttribute(turbo_kernel<NT, FULL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  turbo_kernel<NT, FULL><<<npairs, NT, smem, st>>>(pairs, pool, pi_pool, pi_off, xpowA, xpowB, payload, cb_iters, cb_crc, max_iter);
+  int dev = 0, sms = 148, per_sm = 1;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, turbo_kernel<NT, FULL>, NT, smem);
+  const uint32_t slot_words = 64u * NT; // extrinsic [32][NW] + boundary metrics [4][NW][8], NW <= NT
+  uint32_t       grid       = (uint32_t)(sms * (per_sm > 0 ? per_sm : 1));
+  grid                      = grid < npairs ? grid : npairs;
+  if ((size_t)grid * slot_words > scratch_words) grid = (uint32_t)(scratch_words / slot_words);
+  const TdConst c{1u, 0xFFFFFFFFu, 0xFFFFFFFEu, 3u};
+  turbo_kernel<NT, FULL><<<grid, NT, smem, st>>>(pairs, npairs, queue, pool, scratch, slot_words, pi_pool, pi_off, xpowA, xpowB, payload, cb_iters,
+                                                 cb_crc, max_iter, c);
 }
-// all pairs of one launch share the CTA size class `max_threads` (32..192) and `full` (every K a multiple of 32)
-extern "C" void launch_turbo(const DevPair* pairs, uint32_t npairs, uint32_t max_threads, int full, uint32_t* pool, const uint16_t* pi_pool,
-                             const uint32_t* pi_off, const uint32_t* xpowA, const uint32_t* xpowB, uint8_t* payload, uint8_t* cb_iters,
-                             uint8_t* cb_crc, uint32_t max_iter, cudaStream_t st, uint64_t* launches)
+// all pairs of one launch share the CTA size class `max_threads` (32..192) and `full` (every K a multiple of 32);
+// queue: one zeroed uint32 (the pair counter of this launch); scratch: per-CTA extrinsic / boundary state (see turbo_kernel)
+extern "C" void launch_turbo(const DevPair* pairs, uint32_t npairs, uint32_t max_threads, int full, uint32_t* queue, const uint32_t* pool,
+                             uint32_t* scratch, size_t scratch_words, const uint16_t* pi_pool, const uint32_t* pi_off, const uint32_t* xpowA,
+                             const uint32_t* xpowB, uint8_t* payload, uint8_t* cb_iters, uint8_t* cb_crc, uint32_t max_iter, cudaStream_t st,
+                             uint64_t* launches)
 {
   if (!npairs) return;
   const uint32_t nt = ((max_threads + 31) / 32) * 32;
-#define TURBO_CASE(N)                                                                                                              \
-  case N:                                                                                                                          \
-    if (full)                                                                                                                      \
-      launch_turbo_t<N, true>(pairs, npairs, pool, pi_pool, pi_off, xpowA, xpowB, payload, cb_iters, cb_crc, max_iter, st);        \
-    else                                                                                                                           \
-      launch_turbo_t<N, false>(pairs, npairs, pool, pi_pool, pi_off, xpowA, xpowB, payload, cb_iters, cb_crc, max_iter, st);       \
+#define TURBO_CASE(N)                                                                                                                            \
+  case N:                                                                                                                                        \
+    if (full)                                                                                                                                    \
+      launch_turbo_t<N, true>(pairs, npairs, queue, pool, scratch, scratch_words, pi_pool, pi_off, xpowA, xpowB, payload, cb_iters, cb_crc,      \
+                              max_iter, st);                                                                                                     \
+    else                                                                                                                                         \
+      launch_turbo_t<N, false>(pairs, npairs, queue, pool, scratch, scratch_words, pi_pool, pi_off, xpowA, xpowB, payload, cb_iters, cb_crc,     \
+                               max_iter, st);                                                                                                    \
     break;
   switch (nt) {
     TURBO_CASE(32)

@@ -84,4 +84,21 @@ RmTurboTable rm_turbo_table(uint32_t K, uint32_t F, uint32_t rv);
 // ---- PDSCH resource elements: count of data REs of symbol l in PRB prb (and which k) ---------
 uint32_t pdsch_re_in_prb(const Cell& c, uint32_t sf_idx, uint32_t cfi, uint32_t l, uint32_t prb, uint16_t* k /*12*/);
 
+// ---- DCI fields as unpacked from the payload (stage 1 of the DCI -> grant chain; srsran_dci_dl_t without the grant) -------------
+struct DlDciFields {
+  uint8_t  format;
+  uint16_t rnti;
+  uint32_t alloc;                                    // resource allocation type 0 / 1 / 2
+  uint32_t rbg_mask, t1_subset, t1_shift, t1_mask;   // type 0 / type 1
+  uint32_t riv;                                      // type 2
+  bool     dist, ngap2;                              // distributed VRBs, N_gap2
+  uint32_t n_prb1a;                                  // 2 or 3 (format 1A to a non-user RNTI: TBS column)
+  uint8_t  mcs[2], rv[2], ndi[2];
+  bool     tb_en[2];
+  uint8_t  harq_pid, tpc, tb_cw_swap, pinfo;
+};
+
 } // namespace ltehost
+// host_search.cpp: the stages of ltephy_dci_to_grant, shared with the srsRAN-compatible shim (compat/src)
+int ltehost_unpack_dl_dci(const ltehost::Cell& c, uint32_t format, uint16_t rnti, uint64_t bits, ltehost::DlDciFields& f);
+int ltehost_dl_prb_allocation(uint32_t N, const ltehost::DlDciFields& f, uint32_t mask[2][4], uint32_t* nof_prb);

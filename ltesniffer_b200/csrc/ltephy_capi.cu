@@ -21,8 +21,8 @@ void launch_compact(const DevCell&, const DevSfInfo*, const ltephy_cand_t*, ltep
 void launch_pdsch_front(const DevCell&, const DevGrant*, uint32_t, uint32_t, const float2*, const float2*, const uint32_t*, const uint32_t*, uint32_t,
                         uint32_t*, short*, cudaStream_t, uint64_t*);
 void launch_rm_turbo_rx(const DevCb*, uint32_t, const DevPair*, const short*, const uint32_t*, uint32_t*, cudaStream_t, uint64_t*);
-void launch_turbo(const DevPair*, uint32_t, uint32_t, int, uint32_t*, const uint16_t*, const uint32_t*, const uint32_t*, const uint32_t*, uint8_t*,
-                  uint8_t*, uint8_t*, uint32_t, cudaStream_t, uint64_t*);
+void launch_turbo(const DevPair*, uint32_t, uint32_t, int, uint32_t*, const uint32_t*, uint32_t*, size_t, const uint16_t*, const uint32_t*,
+                  const uint32_t*, const uint32_t*, uint8_t*, uint8_t*, uint8_t*, uint32_t, cudaStream_t, uint64_t*);
 void launch_tb_crc(const DevTb*, uint32_t, const uint8_t*, const uint8_t*, const uint8_t*, const uint32_t*, ltephy_tb_result_t*, cudaStream_t,
                    uint64_t*);
 void launch_ul_ofdm(const DevCell&, const float2*, float2*, uint32_t, cudaStream_t, uint64_t*);
@@ -75,6 +75,8 @@ extern "C" int ltephy_create(const ltephy_cfg_t* cfg, ltephy_t** out)
   if (cfg->nof_prb <= 10 || cfg->nof_prb > 100 || cfg->nof_ports < 1 || cfg->nof_ports > 2 || cfg->nof_rx < 1 || cfg->nof_rx > 2 ||
       cfg->max_subframes == 0)
     return fail(LTEPHY_ERROR_INVALID_INPUTS, "unsupported cell/batch configuration");
+  if (cfg->symbol_sz && cfg->symbol_sz != ltehost::fft_size(cfg->nof_prb))
+    return fail(LTEPHY_ERROR_INVALID_INPUTS, "symbol size %u not supported for %u PRB (standard rate: %u)", cfg->symbol_sz, cfg->nof_prb, ltehost::fft_size(cfg->nof_prb));
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(LTEPHY_ERROR, "no CUDA device: this library has no CPU path");
   CU(cudaSetDevice(cfg->device));
@@ -229,6 +231,7 @@ extern "C" void ltephy_destroy(ltephy_t* h)
   for (void* p : h->tables) cudaFree(p);
   h->d_iq.release(), h->d_sym.release(), h->d_ce.release(), h->d_llr.release(), h->d_info.release(), h->d_cands.release();
   h->h_info.release(), h->d_compact.release(), h->h_compact.release(), h->d_grants.release(), h->d_cbs.release(), h->d_pairs.release(), h->d_tbs.release(), h->d_pair_pi_off.release();
+  h->d_tscratch.release(), h->d_tqueue.release();
   h->d_seq.release(), h->d_rm.release(), h->d_turbo.release(), h->d_pllr.release(), h->d_pi.release(), h->d_payload.release();
   h->d_cb_iters.release(), h->d_cb_crc.release(), h->d_res.release(), h->h_res.release(), h->h_payload.release(), h->h_stage.release();
   h->d_uliq.release(), h->d_ulsym.release(), h->d_ulpool.release(), h->d_ulgrants.release(), h->d_ulchest.release(), h->h_ulchest.release();
@@ -372,6 +375,19 @@ extern "C" int ltephy_get_phase_a_compact(ltephy_t* h, ltephy_sf_info_t* info, l
 extern "C" const ltephy_compact_t* ltephy_phase_a_compact_buffer(const ltephy_t* h) { return h ? h->h_compact.p : nullptr; }
 
 // ---------------------------------------------------------------------------------------- phase B
+// words of one code-block pair in the turbo pool: the three window-transposed input streams (sys, p1, p2: [32][NW] each) and the
+// 12 termination words; the decoder's own state (extrinsic values, window-boundary metrics) lives in per-CTA scratch
+static inline size_t ltephy_pair_words(uint32_t NW) { return (size_t)3 * 32 * NW + 16; }
+// per-CTA scratch of the persistent turbo kernel: 64 * NT words per resident CTA (k_turbo.cu); sized for the largest launch
+static int ltephy_turbo_scratch(ltephy* h)
+{
+  int sms = 148;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->cfg.device);
+  // resident CTAs x threads is at most 2048 threads per SM; 64 words per thread
+  if (h->d_tscratch.reserve((size_t)sms * 2048 * 64)) return -1;
+  if (h->d_tqueue.reserve(16)) return -1;
+  return 0;
+}
 static int rm_table_for(ltephy* h, uint32_t K, uint32_t F, uint32_t rv, uint32_t& off, uint32_t& nn)
 {
   const int ki = lte_qpp_index_ge(K);
@@ -390,7 +406,7 @@ static int rm_table_for(ltephy* h, uint32_t K, uint32_t F, uint32_t rv, uint32_t
     const uint32_t D = K + 4, NW = (K + 31) / 32;
     for (auto& v : t.order) {
       const uint32_t st = v / D, i = v % D;
-      v = i < K ? st * 32 * NW + (i & 31u) * NW + (i >> 5) : 5 * 32 * NW + st * 4 + (i - K);
+      v = i < K ? st * 32 * NW + (i & 31u) * NW + (i >> 5) : 3 * 32 * NW + st * 4 + (i - K);
     }
   }
   if (h->rm_used + t.order.size() > h->d_rm.cap) { // pool full: grow it and keep every offset handed out so far valid
@@ -468,7 +484,7 @@ static int add_transport_block(ltephy* h, uint32_t tbs, uint32_t G, uint32_t qm,
       p.K = cb.K, p.NW = (cb.K + 31) / 32;
       ltehost::qpp_params(cb.K, p.f1, p.f2);
       p.buf_off = (uint32_t)turbo_words;
-      turbo_words += (size_t)6 * 32 * p.NW + 16 + (size_t)4 * 8 * p.NW;
+      turbo_words += ltephy_pair_words(p.NW);
       uint32_t po;
       if (pi_table_for(h, cb.K, po)) return fail(LTEPHY_ERROR, "interleaver table upload failed");
       pi = (uint32_t)h->pairs.size();
@@ -605,11 +621,14 @@ static int run_turbo_stage(ltephy* h, uint32_t max_iter)
   stage_and_pull(h, h->d_pair_pi_off.p, h->pair_pi_off.data(), h->pairs.size() * 4);
   stage_and_pull(h, h->d_cbs.p, h->cbs.data(), h->cbs.size() * sizeof(DevCb));
   launch_rm_turbo_rx(h->d_cbs.p, (uint32_t)h->cbs.size(), h->d_pairs.p, h->d_pllr.p, h->d_rm.p, h->d_turbo.p, h->stream, &h->launches);
+  if (ltephy_turbo_scratch(h)) return fail(LTEPHY_ERROR, "device allocation failed");
+  CU(cudaMemsetAsync(h->d_tqueue.p, 0, 16 * sizeof(uint32_t), h->stream));
   CU(cudaEventRecord(h->ev[4], h->stream));
-  uint32_t first = 0;
+  uint32_t first = 0, bi = 0;
   for (auto& r : ranges) {
-    launch_turbo(h->d_pairs.p + first, r.second, r.first / 2, (r.first & 1u) == 0, h->d_turbo.p, h->d_pi.p, h->d_pair_pi_off.p + first, h->d_xpowA,
-                 h->d_xpowB, h->d_payload.p, h->d_cb_iters.p, h->d_cb_crc.p, max_iter, h->stream, &h->launches);
+    launch_turbo(h->d_pairs.p + first, r.second, r.first / 2, (r.first & 1u) == 0, h->d_tqueue.p + (bi++ & 15u), h->d_turbo.p, h->d_tscratch.p,
+                 h->d_tscratch.cap, h->d_pi.p, h->d_pair_pi_off.p + first, h->d_xpowA, h->d_xpowB, h->d_payload.p, h->d_cb_iters.p, h->d_cb_crc.p,
+                 max_iter, h->stream, &h->launches);
     first += r.second;
   }
   CU(cudaEventRecord(h->ev[5], h->stream));
@@ -791,6 +810,8 @@ extern "C" int ltephy_submit_ul(ltephy_t* h, const float* iq_ul, const uint32_t*
     const uint32_t M = 12 * g.L_prb;
     if (g.L_prb < 3 || g.n_prb + g.L_prb > c.nof_prb || (g.qm != 2 && g.qm != 4 && g.qm != 6 && g.qm != 8) || g.tbs <= 0)
       return fail(LTEPHY_ERROR_INVALID_INPUTS, "UL grant %u: unsupported allocation / modulation", gi);
+    if (((g.flags & LTEPHY_UL_FLAG_SLOT1) && g.n_prb_slot1 != g.n_prb) || g.nof_ack || g.cqi_len || g.ri_len)
+      return fail(LTEPHY_ERROR_INVALID_INPUTS, "UL grant %u: hopping / UCI multiplexing not supported", gi);
     DevUlGrant d{};
     d.sf = g.sf, d.sf_idx = tti[g.sf] % 10, d.rnti = g.rnti, d.M = M, d.k0 = 12 * g.n_prb, d.qm = g.qm;
     for (uint32_t sl = 0; sl < 2; sl++) {
@@ -907,7 +928,7 @@ extern "C" int ltephy_turbo_batch(ltephy_t* h, const int16_t* d, uint32_t K, uin
   if (!ltehost::qpp_params(K, f1, f2)) return fail(LTEPHY_ERROR_INVALID_INPUTS, "turbo_batch: K=%u is not a turbo block size", K);
   CU(cudaSetDevice(h->cfg.device));
   const uint32_t NW = (K + 31) / 32, D = K + 4, npairs = (ncb + 1) / 2;
-  const size_t   pw = (size_t)6 * 32 * NW + 16 + (size_t)4 * 8 * NW; // words per pair
+  const size_t   pw = ltephy_pair_words(NW); // words per pair
   h->pairs.clear(), h->pair_pi_off.clear(), h->cbs.clear(), h->tbs.clear();
   uint32_t po;
   if (pi_table_for(h, K, po)) return fail(LTEPHY_ERROR, "interleaver table upload failed");
@@ -923,8 +944,9 @@ extern "C" int ltephy_turbo_batch(ltephy_t* h, const int16_t* d, uint32_t K, uin
       const int16_t* src = d + (size_t)cbi * 3 * D;
       for (uint32_t s = 0; s < 3; s++)
         for (uint32_t i = 0; i < D; i++) {
-          const uint32_t word = i < K ? s * 32 * NW + (i & 31u) * NW + (i >> 5) : 5 * 32 * NW + s * 4 + (i - K);
-          buf[2 * word + hh]  = src[s * D + i];
+          const uint32_t word = i < K ? s * 32 * NW + (i & 31u) * NW + (i >> 5) : 3 * 32 * NW + s * 4 + (i - K);
+          const int      v    = src[s * D + i]; // conditioned LLRs: the decoder's range analysis (k_turbo.cu) assumes |d| <= 255
+          buf[2 * word + hh]  = (short)(v > 255 ? 255 : (v < -255 ? -255 : v));
         }
     }
     h->pairs.push_back(pr);
@@ -936,9 +958,12 @@ extern "C" int ltephy_turbo_batch(ltephy_t* h, const int16_t* d, uint32_t K, uin
   CU(cudaMemcpyAsync(h->d_turbo.p, pool.data(), pool.size() * 4, cudaMemcpyHostToDevice, h->stream));
   CU(cudaMemcpyAsync(h->d_pairs.p, h->pairs.data(), npairs * sizeof(DevPair), cudaMemcpyHostToDevice, h->stream));
   CU(cudaMemcpyAsync(h->d_pair_pi_off.p, h->pair_pi_off.data(), npairs * 4, cudaMemcpyHostToDevice, h->stream));
+  if (ltephy_turbo_scratch(h)) return fail(LTEPHY_ERROR, "device allocation failed");
+  CU(cudaMemsetAsync(h->d_tqueue.p, 0, 16 * sizeof(uint32_t), h->stream));
   CU(cudaEventRecord(h->ev[4], h->stream));
-  launch_turbo(h->d_pairs.p, npairs, NW, (K & 31u) == 0, h->d_turbo.p, h->d_pi.p, h->d_pair_pi_off.p, h->d_xpowA, h->d_xpowB, h->d_payload.p,
-               h->d_cb_iters.p, h->d_cb_crc.p, max_iter ? max_iter : 1, h->stream, &h->launches);
+  launch_turbo(h->d_pairs.p, npairs, NW, (K & 31u) == 0, h->d_tqueue.p, h->d_turbo.p, h->d_tscratch.p, h->d_tscratch.cap, h->d_pi.p,
+               h->d_pair_pi_off.p, h->d_xpowA, h->d_xpowB, h->d_payload.p, h->d_cb_iters.p, h->d_cb_crc.p, max_iter ? max_iter : 1, h->stream,
+               &h->launches);
   CU(cudaEventRecord(h->ev[5], h->stream));
   std::vector<uint8_t> packed((size_t)ncb * out_bytes), it(ncb), ok(ncb);
   CU(cudaMemcpyAsync(packed.data(), h->d_payload.p, packed.size(), cudaMemcpyDeviceToHost, h->stream));

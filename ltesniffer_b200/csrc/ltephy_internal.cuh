@@ -115,6 +115,7 @@ struct ltephy {
   DevBuf<DevTb>         d_tbs;
   DevBuf<uint32_t>      d_pair_pi_off;
   DevBuf<uint32_t>      d_seq, d_rm, d_turbo;
+  DevBuf<uint32_t>      d_tscratch, d_tqueue; // persistent turbo kernel: per-CTA state slots, pair counters of the launches
   DevBuf<short>         d_pllr;
   DevBuf<uint16_t>      d_pi;
   DevBuf<uint8_t>       d_payload, d_cb_iters, d_cb_crc;

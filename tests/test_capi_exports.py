@@ -15,7 +15,7 @@ def declared_functions(header):
     return sorted(set(re.findall(r"\b(ltephy_[a-z0-9_]+)\s*\(", txt)))
 
 
-@pytest.mark.parametrize("header", ["ltephy_b200.h", "ltephy_search.h", "ltephy_sinks.h"])
+@pytest.mark.parametrize("header", ["ltephy_b200.h", "ltephy_search.h", "ltephy_sinks.h", "ltephy_shard.h"])
 def test_every_declared_symbol_is_exported(phylib, header):
     names = declared_functions(header)
     assert len(names) >= 7
@@ -39,12 +39,22 @@ def test_invalid_inputs_are_rejected(phylib):
 
 
 def test_srsran_compat_shim_exports(phylib):
-    """tier-2 library: loads on top of libltephy_b200.so and exports every srsran_* function its header declares"""
+    """tier-2 library: loads on top of libltephy_b200.so and exports every function the srsRAN-compatible header tree compat/srsran declares"""
     from ltesniffer_b200 import build
     assert os.path.exists(build.COMPAT_OUT)
     lib = C.CDLL(build.COMPAT_OUT)
-    txt = re.sub(r"/\*.*?\*/", "", open(os.path.join(ROOT, "include", "ltephy_srsran_compat.h")).read(), flags=re.S)
-    names = sorted(set(re.findall(r"\b(srsran_[a-z0-9_]+)\s*\(", txt)))
-    assert names == ["srsran_pdcch_dci_decode", "srsran_ue_dl_decode_fft_estimate", "srsran_ue_dl_decode_pdsch", "srsran_ue_dl_free", "srsran_ue_dl_init",
-                     "srsran_ue_dl_set_cell"]
-    assert all(hasattr(lib, n) for n in names)
+    names = set()
+    for r, _, fs in os.walk(os.path.join(ROOT, "compat", "srsran")):
+        for f in fs:
+            txt = re.sub(r"/\*.*?\*/", "", open(os.path.join(r, f)).read(), flags=re.S)
+            txt = re.sub(r"//.*", "", txt)
+            names |= set(re.findall(r"\b(srsran_[a-z0-9_]+)\s*\(", txt))
+    must = {"srsran_ue_dl_init", "srsran_ue_dl_set_cell", "srsran_ue_dl_free", "srsran_ue_dl_decode_fft_estimate", "srsran_pdcch_dci_decode",
+            "srsran_ue_dl_decode_pdsch", "srsran_enb_ul_init", "srsran_enb_ul_set_cell", "srsran_enb_ul_fft", "srsran_chest_ul_estimate_pusch",
+            "srsran_pusch_decode", "srsran_softbuffer_rx_init", "srsran_softbuffer_rx_free", "srsran_softbuffer_rx_reset_tbs", "srsran_dci_format_sizeof",
+            "srsran_dci_msg_unpack_pdsch", "srsran_dci_msg_unpack_pusch", "srsran_ra_dl_grant_to_grant_prb_allocation", "srsran_ra_tbs_from_idx",
+            "srsran_ra_ul_dci_to_grant", "srsran_pdcch_ue_locations_ncce", "srsran_pdcch_common_locations_ncce"}
+    assert must <= names and len(names) >= 100
+    missing = [n for n in sorted(names) if not hasattr(lib, n)]
+    assert not missing, "declared in compat/srsran but not exported: %s" % missing
+    assert hasattr(lib, "ltephy_compat_inject") and hasattr(lib, "ltephy_compat_phy")

@@ -1,0 +1,257 @@
+"""The product against the REFERENCE'S OWN code, compiled unmodified from /root/reference by oracle/build_ref.sh against the
+srsRAN-compatible header tree compat/srsran (oracle/_ref/libfalcon_ref.so, wrapper oracle/ref_walk.cc):
+  * DCISearch::search / recursive_blind_dci_search / inspect_dci_location_recursively (src/src/DCISearch.cc) on the reference's
+    RNTIManager and DCIMetaFormats -- vs ltephy_search_batch (full table) and the survivor-form walk, on identical tables;
+  * dl_sniffer_ra_dl_dci_to_grant + dl_sniffer_config_mimo (lib/src/phy/falcon_phch/dl_sniffer_pdsch.c) and the two UL conversions
+    (srsran_ra_ul_dci_to_grant path / ulsniffer_ra_ul_dci_to_grant_256, ul_sniffer_pusch.c) -- vs ltephy_dci_to_grant /
+    ltephy_ul_dci_to_grant for every accepted DCI;
+  * srsran_pdcch_validate_location (falcon_pdcch.c:223-250), srsran_pdcch_ue_locations_all_map (:321-356),
+    srsran_pdcch_cce_avg_llr_power (:595-620) -- vs the product's O(1) validation, location list and per-CCE power rule.
+The candidate tables come from the CPU oracle here (no GPU needed); tests/test_gpu_reference_code.py repeats the walk comparison
+on the tables the GPU produced."""
+import ctypes as C
+import os
+import numpy as np
+import pytest
+import ltelib
+from ltelib import Cell, Sim, Oracle
+from ltesniffer_b200 import capi
+from test_host_search import oracle_table, host_geometry, locations
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF_SO = os.path.join(ROOT, "oracle", "_ref", "libfalcon_ref.so")
+
+
+class RefDci(C.Structure):
+    _fields_ = [("rnti", C.c_uint16), ("format", C.c_uint8), ("L", C.c_uint8), ("ncce", C.c_uint16), ("nof_bits", C.c_uint16), ("histval", C.c_uint32),
+                ("bits", C.c_uint8 * 64), ("grant_ret", C.c_int32 * 2), ("nof_prb", C.c_uint32), ("nof_re", C.c_uint32 * 2), ("nof_tb", C.c_uint32 * 2),
+                ("tx_scheme", C.c_uint32 * 2), ("pmi", C.c_uint32 * 2), ("nof_layers", C.c_uint32 * 2), ("tbs", (C.c_int32 * 2) * 2),
+                ("qm", (C.c_uint8 * 2) * 2), ("rv", (C.c_uint8 * 2) * 2), ("tb_en", (C.c_uint8 * 2) * 2), ("cw_idx", (C.c_uint8 * 2) * 2),
+                ("prb_mask", (C.c_uint8 * 110) * 2), ("ul_L_prb", C.c_uint32), ("ul_n_prb", C.c_uint32 * 2), ("ul_n_dmrs", C.c_uint32),
+                ("ul_tbs", C.c_int32 * 2), ("ul_qm", C.c_uint8 * 2)]
+
+
+class RefStats(C.Structure):
+    _fields_ = [("nof_decoded_locations", C.c_uint32), ("nof_cce", C.c_uint32), ("nof_missed_cce", C.c_uint32), ("nof_subframes", C.c_uint32),
+                ("nof_locations", C.c_uint32)]
+
+
+def reflib():
+    if not os.path.exists(REF_SO):
+        if os.path.isdir("/root/reference"):
+            import subprocess
+            capi.load_library()
+            subprocess.run(["bash", os.path.join(ROOT, "oracle", "build_ref.sh")], check=True)
+    if not os.path.exists(REF_SO):
+        pytest.skip("oracle/_ref/libfalcon_ref.so not built (needs /root/reference)")
+    L = C.CDLL(REF_SO)
+    P = C.c_void_p
+    L.refwalk_create.argtypes = [C.c_uint32] * 5
+    L.refwalk_create.restype = P
+    L.refwalk_destroy.argtypes = [P]
+    L.refwalk_config.argtypes = [P, C.c_int, C.c_int, C.c_uint32]
+    L.refwalk_activate.argtypes = [P, C.c_uint16, C.c_uint32, C.c_int]
+    L.refwalk_subframe.argtypes = [P, P, P, P, P, C.c_uint32, P]
+    L.refwalk_get_stats.argtypes = [P, P]
+    L.refwalk_validate_location.argtypes = [C.c_uint32] * 4 + [C.c_uint16]
+    L.refwalk_validate_location.restype = C.c_uint32
+    L.refwalk_locations.argtypes = [P, C.c_uint32, P, P, P, P, P]
+    L.refwalk_locations.restype = C.c_uint32
+    return L
+
+
+class RefWalk:
+    def __init__(self, cell, threshold=5):
+        self.L = reflib()
+        self.h = self.L.refwalk_create(cell.nof_prb, cell.nof_ports, cell.cell_id, cell.nof_rx, threshold)
+        assert self.h
+
+    def subframe(self, info, table, llr):
+        out = (RefDci * 64)()
+        n = C.c_uint32(0)
+        table = np.ascontiguousarray(table)
+        llr = np.ascontiguousarray(llr, np.float32)
+        assert self.L.refwalk_subframe(self.h, C.byref(info), table.ctypes.data_as(C.c_void_p), llr.ctypes.data_as(C.c_void_p), out, 64, C.byref(n)) == 0
+        return [out[i] for i in range(n.value)]
+
+    def stats(self):
+        st = RefStats()
+        self.L.refwalk_get_stats(self.h, C.byref(st))
+        return st
+
+    def close(self):
+        if self.h:
+            self.L.refwalk_destroy(self.h)
+            self.h = None
+
+
+def phase_a_oracle(s, o, geo, tti):
+    iq, tr, pl = s.subframe(tti)
+    sym = o.ofdm(iq)
+    ce, res = o.chest(tti % 10, sym)
+    cfi, corr = o.pcfich(tti % 10, sym, ce)
+    llr = o.pdcch_llr(tti % 10, cfi, sym, ce)
+    ncce = len(llr) // 72
+    info = capi.SfInfo()
+    info.tti, info.cfi, info.nof_cce, info.snr_db = tti, cfi, ncce, res.snr_db
+    info.noise_avg, info.rsrp_avg = res.noise_avg, res.rsrp_avg
+    for p in range(2):
+        for a in range(2):
+            info.noise[p][a], info.rsrp[p][a] = res.noise[p][a], res.rsrp[p][a]
+    pw = np.zeros(ncce, np.float32)
+    ltelib.oracle().lteo_cce_power(ltelib.ptr(llr), ncce, ltelib.ptr(pw))
+    for i in range(ncce):
+        info.cce_power[i] = pw[i]
+    nc, Ls = locations(ncce)
+    T = oracle_table(o, geo, nc, Ls, llr) if res.snr_db > 6.0 else np.zeros((capi.MAX_LOC, capi.MAX_SIZES), capi.CAND_DTYPE)
+    return info, T, llr, tr
+
+
+def compare_grants(srch, cell, info, d, r):
+    """product DCI -> grant conversions of accepted DCI d against what the reference's own conversion made of r"""
+    if d["format"] == 0:
+        for table in (0, 1):      # reference: Table 8.6.1-1 (64QAM reading), Table 8.6.1-3; product: enable_64qam 1 / 2
+            rc, g = capi.ul_dci_to_grant(srch, d, 1 if table == 0 else 2)
+            if r.grant_ret[0] != 0:
+                continue
+            L = r.ul_L_prb
+            decodable = L >= 3 and all(L % p for p in ()) and _dft_size(L) and r.ul_n_prb[0] == r.ul_n_prb[1]
+            ref_tbs = r.ul_tbs[table]
+            if decodable and ref_tbs > 0 and int(d_mcs(d, cell)) <= 28:
+                assert rc == 0, (hex(r.rnti), table, L, ref_tbs)
+                assert (g.L_prb, g.n_prb, g.tbs, g.qm) == (L, r.ul_n_prb[0], ref_tbs, r.ul_qm[table]), (hex(r.rnti), table)
+        return
+    for table in (0, 1):
+        rc, g, f = srch.dci_to_grant(d, info.tti % 10, info.cfi, table)
+        assert (rc == 0) == (r.grant_ret[table] == 0), (hex(r.rnti), capi.NOF_FORMATS, d["format"], table, rc, r.grant_ret[table])
+        if rc != 0:
+            continue
+        assert (g.nof_re, g.nof_tb, g.tx_scheme) == (r.nof_re[table], r.nof_tb[table], r.tx_scheme[table]), (hex(r.rnti), table)
+        if g.tx_scheme == capi.TX_SPATIALMUX:
+            assert g.pmi == r.pmi[table]
+        for t in range(2):
+            assert bool(g.tb[t].enabled) == bool(r.tb_en[table][t])
+            if g.tb[t].enabled:
+                assert (g.tb[t].tbs, g.tb[t].qm, g.tb[t].rv) == (r.tbs[table][t], r.qm[table][t], r.rv[table][t]), (hex(r.rnti), table, t)
+                if g.nof_tb == 2:
+                    assert g.tb[t].cw_idx == r.cw_idx[table][t]
+        if table == 0:
+            for sl in range(2):
+                for prb in range(cell.nof_prb):
+                    assert ((g.prb_mask[sl][prb >> 5] >> (prb & 31)) & 1) == r.prb_mask[sl][prb], (hex(r.rnti), sl, prb)
+
+
+def _dft_size(L):
+    for p in (2, 3, 5):
+        while L % p == 0:
+            L //= p
+    return L == 1
+
+
+def d_mcs(d, cell):
+    N = cell.nof_prb
+    rivb = int(np.ceil(np.log2(N * (N + 1) / 2)))
+    return (int(d["bits"]) >> (63 - (2 + rivb + 4))) & 31
+
+
+needs_ref = pytest.mark.skipif(not (os.path.exists(REF_SO) or os.path.isdir("/root/reference")), reason="reference sources not available")
+
+
+@needs_ref
+@pytest.mark.parametrize("name,cell,n,kw", [
+    ("tm1_shortcut", Cell(100, 1, 1, 1), 30, dict(seed=1, cfi=2, nof_ues=2, dl_min=1, dl_max=2, tm=1, mcs_min=5, mcs_max=5, snr_db=30.0, fixed_L=2, si_period=5)),
+    ("busy_mix_ul", Cell(50, 2, 7, 2), 60, dict(seed=2, cfi=3, nof_ues=12, dl_min=3, dl_max=5, ul_min=1, ul_max=2, tm=13, mcs_min=3, mcs_max=12, snr_db=26.0)),
+    ("tm4_swap_256qam", Cell(50, 2, 11, 2), 40, dict(seed=6, cfi=2, nof_ues=8, dl_min=2, dl_max=4, tm=4, mcs_min=4, mcs_max=22, snr_db=33.0, alt_table=1, tb_swap=1)),
+    ("cfg2_like_20MHz", Cell(100, 2, 7, 2), 24, dict(seed=2, cfi=3, nof_ues=150, dl_min=8, dl_max=12, tm=3, mcs_min=17, mcs_max=26, snr_db=28.0, full_band=1)),
+    ("low_snr_gate", Cell(25, 1, 9, 1), 6, dict(seed=3, cfi=2, nof_ues=2, dl_min=1, dl_max=1, tm=1, mcs_min=2, mcs_max=2, snr_db=3.0)),
+])
+def test_product_walk_and_grants_equal_the_reference_code(infra, name, cell, n, kw):
+    s, o = Sim(cell=cell, **kw), Oracle(cell)
+    geo = host_geometry(cell)
+    ref = RefWalk(cell)
+    srch = capi.Search(cell.nof_prb, cell.nof_ports, cell.cell_id, cell.nof_rx)
+    srch_c = capi.Search(cell.nof_prb, cell.nof_ports, cell.cell_id, cell.nof_rx)
+    ref.L.refwalk_config(ref.h, 1, 0, 10)
+    srch.config(1, 0, 10)
+    srch_c.config(1, 0, 10)
+    total = nul = 0
+    for tti in range(n):
+        info, T, llr, tr = phase_a_oracle(s, o, geo, tti)
+        want = ref.subframe(info, T, llr)
+        got = srch.subframe(info, T)
+        got_c = srch_c.subframe_compact(info, srch_c.compact_from_table(info, T))
+        assert got_c is not None and len(got_c) == len(got) and all(np.array_equal(got_c[k], got[k]) for k in got.dtype.names)
+        # the reference keeps DL and UL DCIs in separate containers (each in acceptance order): compare per direction
+        for is_ul in (False, True):
+            a = [d for d in got if (d["format"] == 0) == is_ul]
+            b = [r for r in want if (r.format == 0) == is_ul]
+            assert len(a) == len(b), (name, tti, is_ul, len(a), len(b))
+            for d, r in zip(a, b):
+                assert (int(d["rnti"]), int(d["format"]), int(d["L"]), int(d["ncce"]), int(d["nof_bits"]), int(d["histogram_value"])) == \
+                       (r.rnti, r.format, r.L, r.ncce, r.nof_bits, r.histval), (name, tti, is_ul)
+                assert np.array_equal(capi.cand_bits(d["bits"], r.nof_bits), np.frombuffer(bytes(r.bits), np.uint8)[:r.nof_bits])
+                compare_grants(srch, cell, info, d, r)
+                nul += is_ul
+        total += len(got)
+    rs, ps = ref.stats(), srch.stats()
+    assert (rs.nof_decoded_locations, rs.nof_cce, rs.nof_missed_cce, rs.nof_subframes, rs.nof_locations) == \
+           (ps.nof_decoded_locations, ps.nof_cce, ps.nof_missed_cce, ps.nof_subframes, ps.nof_locations)
+    if name == "low_snr_gate":
+        assert total == 0
+    else:
+        assert total >= n // 2
+    if kw.get("ul_min"):
+        assert nul >= 5
+    ref.close()
+
+
+@needs_ref
+def test_validate_location_equals_reference(infra):
+    R, L = reflib(), capi.load_library()
+    capi._bind_search(L)
+    rng = np.random.default_rng(1)
+    for nof_cce in (20, 25, 54, 87, 41, 8, 3):
+        for _ in range(3000):
+            rnti = int(rng.choice([rng.integers(0, 65536), rng.integers(0, 12), rng.integers(0xFFF0, 0x10000)]))
+            l = int(rng.integers(0, 4))
+            ncce = int(rng.integers(0, max(1, nof_cce))) // (1 << l) * (1 << l)
+            sf = int(rng.integers(0, 10))
+            assert L.ltephy_search_validate_location(nof_cce, ncce, l, sf, rnti) == R.refwalk_validate_location(nof_cce, ncce, l, sf, rnti), (nof_cce, ncce, l, sf, rnti)
+
+
+@needs_ref
+def test_locations_and_cce_power_equal_reference(infra):
+    """srsran_pdcch_ue_locations_all_map order and the sufficient-power rule over srsran_pdcch_cce_avg_llr_power, reference code vs product"""
+    cell = Cell(100, 2, 7, 2)
+    ref = RefWalk(cell)
+    srch = capi.Search(cell.nof_prb, cell.nof_ports, cell.cell_id, cell.nof_rx)
+    rng = np.random.default_rng(3)
+    ncce_of = {1: 20, 2: 54, 3: 87}
+    for cfi in (1, 2, 3):
+        ncce = ncce_of[cfi]
+        llr = rng.standard_normal(72 * ncce).astype(np.float32)
+        for c in rng.choice(ncce, 6, replace=False):
+            llr[72 * c:72 * c + 72] *= 0.3          # some CCEs below the 0.7 threshold
+        nc = np.zeros(160, np.uint16)
+        Ls = np.zeros(160, np.uint8)
+        sp = np.zeros(160, np.uint8)
+        pw = np.zeros(88, np.float32)
+        n = ref.L.refwalk_locations(ref.h, cfi, llr.ctypes.data_as(C.c_void_p), nc.ctypes.data_as(C.c_void_p), Ls.ctypes.data_as(C.c_void_p),
+                                    sp.ctypes.data_as(C.c_void_p), pw.ctypes.data_as(C.c_void_p))
+        enc, eL = locations(ncce)
+        assert n == len(enc) and np.array_equal(nc[:n], enc) and np.array_equal(Ls[:n], eL)
+        opw = np.zeros(ncce, np.float32)
+        ltelib.oracle().lteo_cce_power(ltelib.ptr(llr), ncce, ltelib.ptr(opw))
+        lim = min(ncce, 84)
+        assert np.array_equal(pw[:lim], opw[:lim])                       # double-accumulated mean |LLR| (falcon_pdcch.c:595-620)
+        # product: survivor form lists nothing for a location without sufficient power
+        info = capi.SfInfo()
+        info.tti, info.cfi, info.nof_cce, info.snr_db = 0, cfi, ncce, 20.0
+        for i in range(ncce):
+            info.cce_power[i] = opw[i]
+        T = np.zeros((capi.MAX_LOC, capi.MAX_SIZES), capi.CAND_DTYPE)
+        T["valid"] = 1
+        comp = srch.compact_from_table(info, T)[0]
+        for i in range(n):
+            assert (comp["loc"][i]["mask"] != 0) == bool(sp[i]), (cfi, i)
+    ref.close()
