@@ -30,8 +30,8 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 import numpy as np  # noqa: E402
 
 CELL = dict(nof_prb=100, nof_ports=2, cell_id=7, nof_rx=2)
-SIM_KW = dict(seed=2, cfi=3, nof_ues=150, dl_min=8, dl_max=12, tm=3, mcs_min=17, mcs_max=28, snr_db=28.0, full_band=1)
-WORKLOAD = "cfg2: offline DL 20 MHz FDD, 150 RNTIs, TM3 2x2 64QAM, CFI 3, 8-12 DCI/sf, 100 PRB full band"
+SIM_KW = dict(seed=2, cfi=3, nof_ues=150, dl_min=8, dl_max=12, tm=3, mcs_min=17, mcs_max=28, snr_db=25.0, full_band=1)
+WORKLOAD = "cfg2: offline DL 20 MHz FDD, 150 RNTIs, TM3 2x2 64QAM, CFI 3, 8-12 DCI/sf, 100 PRB full band, SNR 25 dB"
 
 
 def effective_cores():
@@ -194,6 +194,78 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------------------------------------
+def bench_turbo_fixed(capi, phy, K, ncb, iters):
+    """cfg-4 (BASELINE.json): turbo decoder alone, ncb code blocks of size K (TBS 75 376 -> C = 13, K = 5824), FIXED number of
+    iterations (no CRC stop), conditioned int16 inputs resident in HBM when the timed launch starts.  -> information Mbit/s."""
+    rng = np.random.default_rng(4)
+    d = rng.integers(-40, 41, size=(ncb, 3 * (K + 4)), dtype=np.int16)   # decode time does not depend on the data without early stop
+    best = None
+    for _ in range(3):
+        phy.turbo_batch(d, K, iters, 0)
+        ms = phy.timing()[2]
+        best = ms if best is None else min(best, ms)
+    bits = ncb * K
+    return {"K": K, "code_blocks": ncb, "iterations": iters, "kernel_ms": best, "info_mbit_s": bits / best / 1e3,
+            "algorithmic_GB_s": ncb * (3 * (K + 4) * 2 + K // 8) / best / 1e6,
+            "note": "device time of the turbo launch (CUDA events); inputs copied to HBM before the timed launch; best of 3"}
+
+
+def bench_dci_sweep(capi, cell, device, n_sf):
+    """cfg-3 (BASELINE.json): blind-DCI sweep, full CCE / aggregation-level candidate space of n_sf subframes in one batch, every
+    distinct payload size of the 9 formats -> decodes/s of the Viterbi + survivor-selection kernels."""
+    rng = np.random.default_rng(3)
+    phy = capi.LtePhy(cell.nof_prb, cell.nof_ports, cell.cell_id, cell.nof_rx, max_subframes=n_sf, turbo_max_iter=8, device=device)
+    try:
+        base = (rng.standard_normal((64, capi.LLR_STRIDE)) * 0.3).astype(np.float32)   # sigma 0.3 noise (SURVEY 8d cfg-3)
+        base[:, :72 * 26] += np.sign(rng.standard_normal((64, 72 * 26))).astype(np.float32)   # 30 % of the CCEs carry signal-level LLRs
+        llr = np.ascontiguousarray(np.tile(base, (n_sf // 64, 1)))
+        cfi = np.full(n_sf, 3, np.uint32)
+        best = None
+        for _ in range(2):
+            phy.dci_sweep(llr, cfi)
+            ms = phy.timing()[3]
+            best = ms if best is None else min(best, ms)
+        nloc = len(phy.locations(3)[0])
+        nsz = phy.L.ltephy_nof_sizes(phy.h)
+        dec = n_sf * nloc * nsz
+        return {"subframes": n_sf, "locations": nloc, "payload_sizes": nsz, "decodes": dec, "kernel_ms": best, "decodes_per_s": dec / best * 1e3}
+    finally:
+        phy.close()
+
+
+def bench_tm4_256qam(capi, cell, device, threads):
+    """cfg-4 variant: 256QAM TM4 two-codeword PDSCH, one UE over all 100 PRB (MCS 27 of the 256QAM table: TBS 97 896 per codeword,
+    C = 16, K = 6144), decoded through the batched pipeline; CFI 1, 38 dB."""
+    import ltelib
+    kw = dict(seed=4, cfi=1, nof_ues=1, dl_min=1, dl_max=1, tm=4, mcs_min=27, mcs_max=27, snr_db=38.0, full_band=1, alt_table=1)
+    n_u, n = 16, 256
+    s = ltelib.Sim(cell=cell, **kw)
+    sf_len = ltelib.sim().lte_sf_len(cell.nof_prb)
+    iq = np.zeros((n_u, cell.nof_rx, sf_len), np.complex64)
+    for i in range(n_u):
+        iq[i] = s.subframe(i)[0]
+    iq = np.ascontiguousarray(np.tile(iq, (n // n_u, 1, 1)))
+    tti = (np.arange(n) % n_u).astype(np.uint32)
+    phy = capi.LtePhy(cell.nof_prb, cell.nof_ports, cell.cell_id, cell.nof_rx, max_subframes=n, turbo_max_iter=8, device=device, flags=capi.FLAG_SKIP_LOW_POWER)
+    try:
+        srch = capi.Search(cell.nof_prb, cell.nof_ports, cell.cell_id, cell.nof_rx)
+        srch.L.ltephy_search_speculate_256qam(srch.h, 1)
+        best, ok, tot, bits = None, 0, 0, 0
+        for _ in range(3):
+            t0 = time.perf_counter()
+            info, dcis, tbs, payload = capi.decode_subframes(phy, srch, iq, tti)
+            dt = time.perf_counter() - t0
+            best = dt if best is None else min(best, dt)
+            ok = sum(1 for i in range(2 * len(dcis)) if tbs[i].crc)
+            tot = sum(1 for i in range(2 * len(dcis)) if tbs[i].payload_len)
+            bits = sum(8 * tbs[i].payload_len for i in range(2 * len(dcis)) if tbs[i].crc)
+        return {"subframes": n, "tb_total": tot, "tb_crc_ok": ok, "max_tb_bits": max([8 * tbs[i].payload_len for i in range(2 * len(dcis))] + [0]),
+                "e2e_s": best, "decoded_info_mbit_s": bits / best / 1e6, "turbo_kernel_ms": phy.timing()[2],
+                "note": "whole pipeline from host IQ (wall clock, best of 3); 16 distinct subframes tiled"}
+    finally:
+        phy.close()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -201,7 +273,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=1000, help="subframes per step per GPU")
-    ap.add_argument("--unique", type=int, default=100, help="distinct synthetic subframes (tiled to the batch; every step still moves/decodes the full batch)")
+    ap.add_argument("--unique", type=int, default=1000, help="distinct synthetic subframes (tiled to the batch if fewer; cfg-2 asks for 1000 distinct ones)")
+    ap.add_argument("--no-sub-records", action="store_true", help="skip the stand-alone cfg-3 / cfg-4 measurements")
     ap.add_argument("--ref-subframes", type=int, default=0, help="subframes per step for --impl reference (0 = 40 per usable core)")
     ap.add_argument("--cpu-sample", type=int, default=0, help="subframes for the cpu_baseline leg (0 = 400 per usable core, about 10 s)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -309,6 +382,8 @@ def main():
     # ltephy_decode_subframes_sharded (include/ltephy_shard.h): phase A local; packed survivor forms all-gathered over NCCL; the
     # walk replayed on every rank; phase B local; one NCCL gather of the decoded transport blocks to rank 0.  T host threads,
     # one PHY handle each (thread t takes batches t, t+T, ...); the library orders the exchange / walk / gather sections by seq.
+    TB_DTYPE = np.dtype({"names": ["crc", "avg_iters", "nof_cb", "payload_off", "payload_len"], "formats": ["u1", "u1", "<u2", "<u4", "<u4"],
+                         "offsets": [0, 1, 2, 4, 8], "itemsize": C.sizeof(capi.TbResult)})
     sh = None
     sh_seq = [0]
     sh_stats = []          # (seq, ShardStats) of every batch of the last run_sharded call
@@ -440,6 +515,24 @@ def main():
     sh_host_e2e = shard_host_ms() if world > 1 else None
     d2h = B * (C.sizeof(capi.SfInfo) + capi.COMPACT_DTYPE.itemsize) + int(info_bits // 8) + 12 * 2 * 24 * B // 8
 
+    # ---------------- sub-records: BASELINE.json configs 3 and 4 through the stand-alone batched entry points (N = 1 only) --------
+    sub_records = None
+    if world == 1 and rank == 0 and not args.no_sub_records:
+        sub_records = {}
+        try:
+            sub_records["cfg4_turbo_fixed8"] = bench_turbo_fixed(capi, phys[0], 5824, 13 * 2000, 8)
+        except Exception as e:
+            sub_records["cfg4_turbo_fixed8"] = {"error": repr(e)}
+        try:
+            sub_records["cfg3_dci_sweep"] = bench_dci_sweep(capi, cell, local, 8192)
+        except Exception as e:
+            sub_records["cfg3_dci_sweep"] = {"error": repr(e)}
+        try:
+            sub_records["cfg4_tm4_256qam_2cw"] = bench_tm4_256qam(capi, cell, local, min(cores, 16))
+        except Exception as e:
+            sub_records["cfg4_tm4_256qam_2cw"] = {"error": repr(e)}
+        log("[rank 0] sub-records: %r" % (sub_records,))
+
     # ---------------- roofline of the dominant kernel (turbo decoder) ----------------
     peaks = {}
     try:
@@ -491,7 +584,7 @@ def main():
                        "h2d_bytes_per_step": int(iq_pin.numel() * 4 + B * 4), "d2h_bytes_per_step": int(d2h),
                        "ms_per_step": e2e_ms / args.steps, "tb_crc_ok": e2e_tb_ok, "h2d_plus_phase_a_ms": e2e_pa, "phase_b_ms": e2e_pb,
                        "host_ms": sh_host_e2e if world > 1 else dict(zip(["submit_a", "wait_a", "search", "grants", "submit_b", "wait_b"], [round(float(x), 3) for x in hm2[:6]]))},
-               "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline}
+               "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "sub_records": sub_records}
 
     if rank == 0 and cpu_base is not None:
         out["cpu_baseline"] = cpu_base

@@ -29,6 +29,8 @@ def _phy_grant(sf, rnti, prb, num):
                 pg.prb_mask[s][p >> 5] |= 1 << (p & 31)
     for t in range(2):
         pg.tb[t].enabled, pg.tb[t].qm, pg.tb[t].rv, pg.tb[t].tbs = int(num[4 + 4 * t]), int(num[5 + 4 * t]), int(num[6 + 4 * t]), int(num[7 + 4 * t])
+    if pg.tb[0].enabled and pg.tb[1].enabled:      # the fixtures carry no swapped grants: TB 1 -> codeword 0, TB 2 -> codeword 1
+        pg.tb[1].cw_idx = 1
     return pg
 
 
