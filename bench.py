@@ -15,6 +15,7 @@ PDSCH demap/descramble/rate-dematch/turbo/CRC.  Metric: subframes/s (whole job, 
 """
 import argparse
 import ctypes as C
+import faulthandler
 import json
 import os
 import subprocess
@@ -281,6 +282,7 @@ def main():
     ap.add_argument("--pipelines", type=int, default=4, help="PHY handles driven concurrently (host search of batch k overlaps GPU work of batch k+1)")
     args = ap.parse_args()
     claim_stdout()
+    faulthandler.enable()
     if args.impl == "reference":
         return run_reference(args)
 
@@ -435,6 +437,7 @@ def main():
     # warm-up steps are the same load, and the timed region alone (~0.1 s) would yield a single sample
     clk = ClockSampler(local)
     clk.start()
+    log("[rank %d] warm-up" % rank)
     # ---------------- warm-up ----------------
     for _ in range(max(3, args.warmup)):
         if world > 1:
@@ -443,6 +446,7 @@ def main():
             run_steps(T, True)
     barrier()
     launches0 = sum(ph.launch_count() for ph in phys)
+    log("[rank %d] timed region (device-resident IQ)" % rank)
     # ---------------- value: IQ resident in HBM ----------------
     turbo_ms, phase_a_ms, phase_b_ms = [], [], []
     host_ms = np.zeros(8)
@@ -490,6 +494,7 @@ def main():
     tb_ok, ntb, tb_ok_own = tb_counts(scr[0])
     sh_host_value = shard_host_ms() if world > 1 else None
     tbytes, ncb, info_bits = phy.turbo_work()
+    log("[rank %d] timed region (host IQ)" % rank)
     # ---------------- e2e: host IQ through the C-ABI ----------------
     if world > 1:
         run_sharded(T, False)
@@ -519,6 +524,7 @@ def main():
     sub_records = None
     if world == 1 and rank == 0 and not args.no_sub_records:
         sub_records = {}
+        log("[rank 0] sub-records")
         try:
             sub_records["cfg4_turbo_fixed8"] = bench_turbo_fixed(capi, phys[0], 5824, 13 * 2000, 8)
         except Exception as e:

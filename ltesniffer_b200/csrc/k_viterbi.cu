@@ -1,32 +1,64 @@
 // k_viterbi.cu -- K5: exhaustive blind-DCI decode.  One warp decodes TWO PDCCH candidates of the same
-// payload size at once (their path metrics share registers as packed int16x2, VIADD.16x2 / VIMNMX.S16x2);
-// the 64 trellis states are spread two per lane.  Restates srsran_pdcch_dci_decode as called from
+// payload size at once (their path metrics share registers as packed int16x2); the 64 trellis states are
+// spread two per lane.  Restates srsran_pdcch_dci_decode as called from
 // srsran_pdcch_decode_msg_limit_avg_llr_power (reference lib/src/phy/falcon_phch/falcon_pdcch.c:110-170):
 // conv rate-dematch with accumulation, uint8 quantisation (gain 32 / max|x|), K=7 r=1/3 tail-biting
 // Viterbi run over three concatenated copies of which the middle one is kept, CRC16, RNTI = parity ^ crc.
 // The table T[location][size] this kernel fills is what DCISearch::inspect_dci_location_recursively
 // (src/src/DCISearch.cc:102-447) consults one entry at a time.
+//
+// Layout (tests/test_viterbi_model.py restates it lane by lane and checks it against the oracle without a GPU):
+//  * ROTATING BUTTERFLY.  Before step t (phase f = t mod 5) lane bit i holds state bit ((i + f) mod 5) + 1 and the register index
+//    (a0 / a1) holds state bit 0.  One exchange with lane ^ (16 >> f) brings the two predecessors of a butterfly (state bit 5)
+//    into one lane; the two new states it produces are already where phase f + 1 wants them.  Round 1 routed every new state back
+//    to a fixed owner: 2 SHFL + 4 SEL per step instead of 1 SHFL + 3 LOP3.
+//  * DUAL-PIPE ARITHMETIC.  Integer adds issue at 16 lanes / clk on the ALU pipe and on the FMA pipe (IMAD); max / select / logic
+//    only on the ALU pipe.  Branch metrics are offset by +765 (the common offset of both competitors of an add-compare-select changes no
+//    decision), so every metric field is non-negative and the packed adds can run as 32-bit IMADs (a * 1 + b with the 1 in a
+//    kernel parameter): no carry ever crosses from the low into the high field.  Renormalisation every 5 steps subtracts
+//    (metric of state 0) - 9180; any two path metrics differ by at most 6 * 1530 = 9180 (every state is reached from every state
+//    in 6 steps), so fields stay within [0, 2 * 9180 + 5 * 1530] = [0, 26010].
+//  * Survivor decisions are ballot words in the layout of the step; the traceback walks in the same rotated coordinates (one bit
+//    of the lane index is replaced per step), so it needs no permutation either.  CRC16 by GF(2) folding across the warp.
 #include "dev_common.cuh"
 
 #define VIT_KMAX 80          // nof_bits <= 64 -> K = nof_bits + 16 <= 80
 #define VIT_WARPS 4
-#define VIT_RENORM 16
+#define VIT_OFFS 765         // 3 * 255: makes every branch metric non-negative
+#define VIT_SPREAD 9180      // 6 * 2 * 765
 
 struct __align__(16) VitWarpSmem {
   float    rm[2][3 * VIT_KMAX]; // dematched soft bits, stream-major
   uint32_t R[3][VIT_KMAX];      // quantised symbols 2q-255, packed (cand0 lo, cand1 hi)
-  uint32_t S[VIT_KMAX][8];      // branch metrics for the 8 output sign patterns (o0 o1 o2), packed; S[k][p ^ 7] = -S[k][p]
-  uint4    dec[2 * VIT_KMAX];   // survivor decisions of steps K..3K-1: {c0 even, c0 odd, c1 even, c1 odd}
+  uint32_t S[VIT_KMAX][8];      // branch metrics + 765 for the 8 output sign patterns (o0 o1 o2), packed; S[k][p ^ 7] = 1530 - S[k][p]
+  uint4    dec[2 * VIT_KMAX];   // survivor decisions of steps K..3K-1: {c0 u=0, c0 u=1, c1 u=0, c1 u=1}, bit = lane of the step's layout
+};
+
+struct VitConst {
+  uint32_t one, minus_one; // run-time constants: keep a * 1 + b an IMAD (FMA pipe)
 };
 
 __device__ __forceinline__ uint32_t pk(int lo, int hi) { return ((uint32_t)lo & 0xFFFFu) | ((uint32_t)hi << 16); }
 __device__ __forceinline__ int      lo16(uint32_t v) { return (int)(short)(v & 0xFFFFu); }
 __device__ __forceinline__ int      hi16(uint32_t v) { return (int)(short)(v >> 16); }
 
+// x^(e + 16) mod (x^16 + x^12 + x^5 + 1), e = 0..63: the CRC16 of a message is the XOR of these over its set bits
+__device__ __forceinline__ uint32_t crc16_xpow(uint32_t e)
+{
+  uint32_t r = 0x1021u; // x^16 mod P
+  for (uint32_t i = 0; i < e; i++) {
+    r <<= 1;
+    if (r & 0x10000u) r ^= 0x11021u;
+  }
+  return r;
+}
+
 __global__ void __launch_bounds__(VIT_WARPS * 32) dci_viterbi_kernel(const __grid_constant__ DevCell c, const float* __restrict__ llr_all,
-                                                                      const DevSfInfo* __restrict__ info, ltephy_cand_t* __restrict__ cands)
+                                                                      const DevSfInfo* __restrict__ info, ltephy_cand_t* __restrict__ cands,
+                                                                      const VitConst vc)
 {
   __shared__ VitWarpSmem sm_all[VIT_WARPS];
+  __shared__ uint32_t    xpow_s[64];
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t pair = blockIdx.x * VIT_WARPS + warp, si = blockIdx.y, sf = blockIdx.z;
   VitWarpSmem&   sm   = sm_all[warp];
@@ -34,6 +66,8 @@ __global__ void __launch_bounds__(VIT_WARPS * 32) dci_viterbi_kernel(const __gri
   const uint32_t cfi = info[sf].cfi;
   if (cfi < 1 || cfi > 3) return;
   const uint32_t nloc = c.nloc[cfi - 1];
+  if (threadIdx.x < 64) xpow_s[threadIdx.x] = crc16_xpow(threadIdx.x);
+  __syncthreads();
   if (2 * pair >= nloc) return;
   const uint32_t nb = c.sizes[si], K = nb + 16, n3 = 3 * K;
   const float*   llr = llr_all + (size_t)sf * LLR_STRIDE;
@@ -84,117 +118,167 @@ __global__ void __launch_bounds__(VIT_WARPS * 32) dci_viterbi_kernel(const __gri
     }
     return;
   }
-  // branch-metric table for all 8 output patterns p = o0*4 + o1*2 + o2: bm = sum_i (o_i ? +r_i : -r_i)
+  // branch-metric table for all 8 output patterns p = o0*4 + o1*2 + o2: 765 + sum_i (o_i ? +r_i : -r_i), both candidates
   for (uint32_t k = lane; k < K; k += 32) {
     const uint32_t r0 = sm.R[0][k], r1 = sm.R[1][k], r2 = sm.R[2][k];
     const uint32_t n0 = __vneg2(r0), n1 = __vneg2(r1), n2 = __vneg2(r2);
 #pragma unroll
     for (uint32_t pat = 0; pat < 8; pat++)
-      sm.S[k][pat] = __vadd2(__vadd2((pat & 4u) ? r0 : n0, (pat & 2u) ? r1 : n1), (pat & 1u) ? r2 : n2);
+      sm.S[k][pat] = __vadd2(__vadd2(__vadd2((pat & 4u) ? r0 : n0, (pat & 2u) ? r1 : n1), (pat & 1u) ? r2 : n2), pk(VIT_OFFS, VIT_OFFS));
   }
   __syncwarp();
 
-  // ---- per-lane constants: lane j owns old states j and j+32, produces new states 2j and 2j+1 ------
-  // state bit i = c_{k-1-i}; outputs for (state j < 32, input 0): parity(j & mask); polys 133,171,165
-  const uint32_t o0 = __popc(lane & 0x36u) & 1u, o1 = __popc(lane & 0x27u) & 1u, o2 = __popc(lane & 0x2Bu) & 1u;
-  const uint32_t pat = o0 * 4 + o1 * 2 + o2; // m = bm(j, input 0) = S[k][pat], -m = S[k][pat ^ 7]
-  const uint32_t odd = lane & 1u, lo_half = lane < 16;
-  const uint32_t src1 = odd ? 16 + (lane >> 1) : (lane >> 1);
-  const uint32_t src2 = odd ? (lane >> 1) : 16 + (lane >> 1);
-  const uint32_t* Sp = &sm.S[0][pat];
-  const uint32_t* Sn = &sm.S[0][pat ^ 7u];
-
-  uint32_t X0 = 0, X1 = 0; // packed path metrics of states j and j+32
-  // one trellis step; STORE: keep the survivor decisions of this step
-  auto step = [&](uint32_t k, uint4* dst, bool store) {
-    const uint32_t m = Sp[k * 8], mn = Sn[k * 8];
-    // new 2j   (input 0): max(X0 + m, X1 - m) ; new 2j+1 (input 1): max(X0 - m, X1 + m); ties keep the j branch
-    bool           p0h, p0l, p1h, p1l;
-    const uint32_t N0 = __vibmax_s16x2(__vadd2(X0, m), __vadd2(X1, mn), &p0h, &p0l);
-    const uint32_t N1 = __vibmax_s16x2(__vadd2(X0, mn), __vadd2(X1, m), &p1h, &p1l);
-    if (store) {
-      uint4 d;
-      d.x = __ballot_sync(0xffffffffu, !p0l); // cand0, new state 2j   -> bit j
-      d.y = __ballot_sync(0xffffffffu, !p1l); // cand0, new state 2j+1
-      d.z = __ballot_sync(0xffffffffu, !p0h); // cand1
-      d.w = __ballot_sync(0xffffffffu, !p1h);
-      if (lane == 0) *dst = d;
-    }
-    // re-distribute: lane j needs new[j], new[j+32]
-    const uint32_t v1 = lo_half ? N0 : N1, v2 = lo_half ? N1 : N0;
-    const uint32_t r1 = __shfl_sync(0xffffffffu, v1, src1), r2 = __shfl_sync(0xffffffffu, v2, src2);
-    X0 = odd ? r2 : r1;
-    X1 = odd ? r1 : r2;
-  };
-  auto renorm = [&]() {
-    const uint32_t ref = __vneg2(__shfl_sync(0xffffffffu, X0, 0));
-    X0 = __vadd2(X0, ref);
-    X1 = __vadd2(X1, ref);
-  };
-  // three concatenated copies of the K-step frame; decisions are kept for copies 2 and 3
-  for (uint32_t pass = 0; pass < 3; pass++) {
-    uint4* dst = &sm.dec[(pass ? pass - 1 : 0) * K];
-    uint32_t k = 0;
-    for (; k + VIT_RENORM <= K; k += VIT_RENORM) {
-      if (pass == 0) {
+  // ---- per-lane constants of the five phases ---------------------------------------------------------------------------
+  // phase f, after the exchange: state bit 0 = lane bit (4 - f) mod 5, state bit k (1..4) = lane bit (k - 1 - f) mod 5; the register
+  // index is state bit 5.  pat = output pattern of (old state with bit 5 = 0, input 0): polynomials 133, 171, 165 (octal).
+  uint32_t xm[5];      // exchange mask: all ones if this lane's bit (16 >> f) is set
+  uint32_t po[5];      // byte offset of this lane's pattern inside a row of S
 #pragma unroll
-        for (uint32_t u = 0; u < VIT_RENORM; u++) step(k + u, nullptr, false);
-      } else {
+  for (int f = 0; f < 5; f++) {
+    uint32_t p = (lane >> ((4 - f + 5) % 5)) & 1u;
 #pragma unroll
-        for (uint32_t u = 0; u < VIT_RENORM; u++) step(k + u, dst + k + u, true);
-      }
-      renorm();
-    }
-    for (; k < K; k++) step(k, dst + k, pass != 0);
-    renorm();
+    for (int k = 1; k < 5; k++) p |= ((lane >> ((k - 1 - f + 10) % 5)) & 1u) << k;
+    const uint32_t o0 = __popc(p & 0x36u) & 1u, o1 = __popc(p & 0x27u) & 1u, o2 = __popc(p & 0x2Bu) & 1u;
+    po[f] = (o0 * 4 + o1 * 2 + o2) * 4u;
+    xm[f] = (lane & (16u >> f)) ? 0xFFFFFFFFu : 0u;
   }
+  const uint32_t C1530 = pk(2 * VIT_OFFS, 2 * VIT_OFFS), CSPREAD = pk(VIT_SPREAD, VIT_SPREAD);
+  const unsigned char* Sb  = reinterpret_cast<const unsigned char*>(&sm.S[0][0]);
+  const uint32_t       Kb  = K * 32u; // bytes of S in use
+  uint32_t             kb  = 0;       // byte offset of row (t mod K)
+  uint32_t a0 = 0, a1 = 0;            // packed path metrics of the lane's two states, non-negative fields
+  uint4*   dst = sm.dec;
+
+  // one trellis step in phase F; store: keep the survivor decisions of this step
+#define VIT_STEP(F, STORE)                                                                                                     \
+  {                                                                                                                            \
+    const uint32_t snd = (a0 & xm[F]) | (a1 & ~xm[F]);                                                                         \
+    const uint32_t rcv = __shfl_xor_sync(0xffffffffu, snd, 16u >> F);                                                          \
+    a0                 = (rcv & xm[F]) | (a0 & ~xm[F]);                                                                        \
+    a1                 = (a1 & xm[F]) | (rcv & ~xm[F]);                                                                        \
+    const uint32_t m   = *reinterpret_cast<const uint32_t*>(Sb + kb + po[F]);                                                  \
+    const uint32_t mn  = m * vc.minus_one + C1530;                                                                             \
+    bool           p0h, p0l, p1h, p1l;                                                                                         \
+    const uint32_t N0 = __vibmax_s16x2(a0 * vc.one + m, a1 * vc.one + mn, &p0h, &p0l);                                         \
+    const uint32_t N1 = __vibmax_s16x2(a0 * vc.one + mn, a1 * vc.one + m, &p1h, &p1l);                                         \
+    if (STORE) {                                                                                                               \
+      uint4 d;                                                                                                                 \
+      d.x = __ballot_sync(0xffffffffu, !p0l);                                                                                  \
+      d.y = __ballot_sync(0xffffffffu, !p1l);                                                                                  \
+      d.z = __ballot_sync(0xffffffffu, !p0h);                                                                                  \
+      d.w = __ballot_sync(0xffffffffu, !p1h);                                                                                  \
+      if (lane == 0) *dst = d;                                                                                                 \
+      dst++;                                                                                                                   \
+    }                                                                                                                          \
+    a0 = N0, a1 = N1;                                                                                                          \
+    kb += 32u;                                                                                                                 \
+    if (kb == Kb) kb = 0;                                                                                                      \
+  }
+#define VIT_RENORM()                                                                                                           \
+  {                                                                                                                            \
+    const uint32_t ref = __shfl_sync(0xffffffffu, a0, 0) * vc.one + (0u - CSPREAD); /* state 0 sits in a0 of lane 0 in every phase */ \
+    a0                 = ref * vc.minus_one + a0;                                                                              \
+    a1                 = ref * vc.minus_one + a1;                                                                              \
+  }
+  // three concatenated copies of the K-step frame = 3K steps in groups of five phases; decisions are kept from step K on
+  const uint32_t T3 = 3 * K;
+  uint32_t       t  = 0;
+  for (; t + 5 <= K; t += 5) {
+    VIT_STEP(0, false) VIT_STEP(1, false) VIT_STEP(2, false) VIT_STEP(3, false) VIT_STEP(4, false)
+    VIT_RENORM()
+  }
+  if (t < K) { // the group that straddles step K: per-step store flag
+    const uint32_t b = K - t; // steps of this group that belong to the first copy (1..4)
+    VIT_STEP(0, false)
+    if (b > 1) VIT_STEP(1, false) else VIT_STEP(1, true)
+    if (b > 2) VIT_STEP(2, false) else VIT_STEP(2, true)
+    if (b > 3) VIT_STEP(3, false) else VIT_STEP(3, true)
+    VIT_STEP(4, true)
+    VIT_RENORM()
+    t += 5;
+  }
+  for (; t + 5 <= T3; t += 5) {
+    VIT_STEP(0, true) VIT_STEP(1, true) VIT_STEP(2, true) VIT_STEP(3, true) VIT_STEP(4, true)
+    VIT_RENORM()
+  }
+  const uint32_t tail = T3 - t; // 0..4 steps left, phases 0..
+  if (tail > 0) VIT_STEP(0, true)
+  if (tail > 1) VIT_STEP(1, true)
+  if (tail > 2) VIT_STEP(2, true)
+  if (tail > 3) VIT_STEP(3, true)
+#undef VIT_STEP
+#undef VIT_RENORM
   __syncwarp();
   // ---- best final state (lowest index on ties), per candidate ------------------------------------
-  int best_s[2];
+  // layout after the last step: phase psi = T3 mod 5 before an exchange: lane bit i = state bit ((i + psi) mod 5) + 1, register = bit 0
+  const uint32_t psi = T3 % 5u;
+  uint32_t       sidx = 0;
+#pragma unroll
+  for (uint32_t i = 0; i < 5; i++) sidx |= ((lane >> i) & 1u) << (((i + psi) % 5u) + 1u);
+  uint32_t best_y[2], best_u[2];
   for (int cd = 0; cd < 2; cd++) {
-    int v0 = cd ? hi16(X0) : lo16(X0), v1 = cd ? hi16(X1) : lo16(X1);
-    int bv = v0, bs = (int)lane;
-    if (v1 > bv) bv = v1, bs = (int)lane + 32;
+    const int v0 = cd ? hi16(a0) : lo16(a0), v1 = cd ? hi16(a1) : lo16(a1);
+    int       bv = v0, bs = (int)sidx;
+    if (v1 > bv) bv = v1, bs = (int)sidx + 1; // same lane: the state with bit 0 set is the larger index
+    uint32_t by = lane;
 #pragma unroll
     for (int off = 16; off >= 1; off >>= 1) {
-      const int ov = __shfl_xor_sync(0xffffffffu, bv, off), os = __shfl_xor_sync(0xffffffffu, bs, off);
-      if (ov > bv || (ov == bv && os < bs)) bv = ov, bs = os;
+      const int      ov = __shfl_xor_sync(0xffffffffu, bv, off), os = __shfl_xor_sync(0xffffffffu, bs, off);
+      const uint32_t oy = __shfl_xor_sync(0xffffffffu, by, off);
+      if (ov > bv || (ov == bv && os < bs)) bv = ov, bs = os, by = oy;
     }
-    best_s[cd] = bs;
+    best_y[cd] = by, best_u[cd] = (uint32_t)bs & 1u;
   }
-  // ---- traceback (lanes 0,1: one candidate each), steps 3K-1 .. K, keep K..2K-1 --------------------
+  // ---- traceback (lanes 0,1: one candidate each) in the rotated coordinates of each step: (y, u) = (lane, register) of the state;
+  // going back one step, the bit of y that held state bit 1 becomes the new u and is replaced by the decision
+  uint32_t w0 = 0, w1 = 0, w2 = 0;
   if (lane < 2) {
     const int       cd = (int)lane;
-    uint32_t        st = (uint32_t)best_s[cd];
-    const uint32_t* dw = reinterpret_cast<const uint32_t*>(sm.dec) + cd * 2; // word (t-K)*4 + cd*2 + (st&1)
+    uint32_t        y = best_y[cd], u = best_u[cd], pos = (5u - psi) % 5u;
+    const uint32_t* dw = reinterpret_cast<const uint32_t*>(sm.dec) + cd * 2; // word (t-K)*4 + cd*2 + u
     auto back = [&](int idx) { // idx = t - K
-      const uint32_t word = dw[idx * 4 + (int)(st & 1u)];
-      st                  = (st >> 1) | (((word >> (st >> 1)) & 1u) << 5);
+      const uint32_t d = (dw[idx * 4 + (int)u] >> y) & 1u;
+      u                = (y >> pos) & 1u;
+      y                = (y & ~(1u << pos)) | (d << pos);
+      pos              = pos == 4 ? 0 : pos + 1;
     };
     for (int idx = 2 * (int)K - 1; idx >= (int)K; idx--) back(idx); // third copy: only gives traceback depth
     // second copy: data bit i = idx (K-1 .. 0), bit i at position 31 - (i & 31) of word i >> 5
-    uint32_t w0 = 0, w1 = 0, w2 = 0;
-    int      idx = (int)K - 1;
+    int idx = (int)K - 1;
     for (; idx >= 64; idx--) {
-      w2 |= (st & 1u) << (31 - (idx & 31));
+      w2 |= u << (31 - (idx & 31));
       back(idx);
     }
     for (; idx >= 32; idx--) {
-      w1 |= (st & 1u) << (31 - (idx & 31));
+      w1 |= u << (31 - (idx & 31));
       back(idx);
     }
     for (; idx >= 0; idx--) {
-      w0 |= (st & 1u) << (31 - (idx & 31));
+      w0 |= u << (31 - (idx & 31));
       back(idx);
     }
-    // CRC16 (poly 0x11021, zero init) over the first nb bits; RNTI = received parity ^ computed
+  }
+  // ---- CRC16 (poly 0x11021, zero init) over the first nb bits of both candidates at once: XOR over the set bits of
+  // x^(nb - 1 - i + 16) mod P, folded across the warp; candidate 0 in the low half, candidate 1 in the high half
+  uint32_t cw0[2], cw1[2], cw2[2];
+#pragma unroll
+  for (int cd = 0; cd < 2; cd++) {
+    cw0[cd] = __shfl_sync(0xffffffffu, w0, cd), cw1[cd] = __shfl_sync(0xffffffffu, w1, cd), cw2[cd] = __shfl_sync(0xffffffffu, w2, cd);
+  }
+  uint32_t acc = 0;
+#pragma unroll
+  for (int cd = 0; cd < 2; cd++) {
+    uint32_t r = 0;
+    if (lane < nb && ((cw0[cd] >> (31 - lane)) & 1u)) r ^= xpow_s[nb - 1 - lane];
+    if (lane + 32 < nb && ((cw1[cd] >> (31 - lane)) & 1u)) r ^= xpow_s[nb - 1 - (lane + 32)];
+    acc |= r << (16 * cd);
+  }
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) acc ^= __shfl_xor_sync(0xffffffffu, acc, off);
+  if (lane < 2) {
+    const int      cd  = (int)lane;
+    const uint32_t reg = (acc >> (16 * cd)) & 0xFFFFu;
     const unsigned long long lo64 = ((unsigned long long)w0 << 32) | (unsigned long long)w1; // bits 0..63, bit i at 63 - i
-    uint32_t                 reg  = 0;
-    for (uint32_t i = 0; i < nb + 16; i++) {
-      const uint32_t bit = i < nb ? (uint32_t)((lo64 >> (63 - i)) & 1ull) : 0u;
-      reg                = (reg << 1) | bit;
-      if (reg & 0x10000u) reg ^= 0x11021u;
-    }
     // the 16 parity bits nb .. nb+15 (bit i of the frame: word i>>5)
     uint32_t par = 0;
     for (uint32_t i = nb; i < nb + 16; i++) {
@@ -216,7 +300,8 @@ extern "C" void launch_viterbi(const DevCell& c, const float* llr, const DevSfIn
                                uint64_t* launches)
 {
   const uint32_t max_pairs = (LTEPHY_MAX_LOC / 2 + VIT_WARPS - 1) / VIT_WARPS;
-  dci_viterbi_kernel<<<dim3(max_pairs, c.nsizes, n), VIT_WARPS * 32, 0, st>>>(c, llr, info, cands);
+  const VitConst vc{1u, 0xFFFFFFFFu};
+  dci_viterbi_kernel<<<dim3(max_pairs, c.nsizes, n), VIT_WARPS * 32, 0, st>>>(c, llr, info, cands, vc);
   *launches += 1;
 }
 

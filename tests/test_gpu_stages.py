@@ -161,7 +161,8 @@ def test_pdsch_llr_and_tb_bit_exact(case):
             if not g.tb[t].enabled:
                 continue
             G = g.nof_re * g.tb[t].qm
-            assert np.array_equal(gl[off:off + G], ollr[cw][:G]), describe_mismatch(gl[off:off + G], ollr[cw][:G], "pdsch llr grant %d cw %d" % (gi, cw))
+            ocw = (1 - cw) if (g.nof_tb == 2 and g.cw_swap) else cw     # the oracle indexes LLRs by CODEWORD, the pool is in TB order
+            assert np.array_equal(gl[off:off + G], ollr[ocw][:G]), describe_mismatch(gl[off:off + G], ollr[ocw][:G], "pdsch llr grant %d cw %d" % (gi, ocw))
             off += (G + 7) & ~7
             cw += 1
             rr = res[2 * gi + t]
