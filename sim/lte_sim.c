@@ -133,7 +133,7 @@ lte_sim_t* lte_sim_create(const lte_sim_cfg_t* cfg)
   s->fre    = (double*)calloc(s->fft, sizeof(double));
   s->fim    = (double*)calloc(s->fft, sizeof(double));
   s->ebits  = (uint8_t*)calloc(110 * 12 * 14 * 8 + 64, 1);
-  s->tbbits = (uint8_t*)calloc(110000, 1);
+  s->tbbits = (uint8_t*)calloc(110 * 12 * 14 * 8 + 64, 1);
   for (int q = 0; q < 2; q++) s->dsym[q] = (cf_t*)calloc(110 * 12 * 14, sizeof(cf_t));
   return s;
 }
