@@ -36,7 +36,7 @@ struct UlPriv {
   std::vector<cfx_t> sym;
   std::vector<uint8_t> payload;
   // result of the last srsran_chest_ul_estimate_pusch (the GPU decodes the grant in the same pass)
-  bool               have = false;
+  bool               have = false, fft_done = false;
   ltephy_ul_grant_t  grant{};
   ltephy_tb_result_t res{};
   ltephy_ul_chest_t  chest{};
@@ -273,8 +273,9 @@ void srsran_enb_ul_fft(srsran_enb_ul_t* q)
   UlPriv* u = U(q);
   if (!u || !u->phy || !q->in_buffer) return;
   const uint32_t tti = 0;
-  u->have            = false;
+  u->have = u->fft_done = false;
   if (ltephy_submit_ul(u->phy, reinterpret_cast<const float*>(q->in_buffer), &tti, 1, nullptr, 0) != LTEPHY_SUCCESS) return;
+  u->fft_done = true;
   ltephy_tb_result_t r{};
   ltephy_get_ul(u->phy, &r, nullptr, nullptr, 0);
   ltephy_tap(u->phy, LTEPHY_TAP_UL_SYM, u->sym.data(), u->sym.size() * sizeof(cfx_t));
@@ -290,7 +291,9 @@ static int run_pusch(srsran_enb_ul_t* q, UlPriv* u, srsran_ul_sf_cfg_t* sf, srsr
   g.I_offset_ack = cfg->uci_offset.I_offset_ack, g.I_offset_cqi = cfg->uci_offset.I_offset_cqi, g.I_offset_ri = cfg->uci_offset.I_offset_ri;
   if (cfg->uci_cfg.cqi.data_enable) g.cqi_len = (uint32_t)srsran_cqi_size(&cfg->uci_cfg.cqi);
   const uint32_t tti = sf ? sf->tti : 0;
-  if (ltephy_submit_ul(u->phy, reinterpret_cast<const float*>(q->in_buffer), &tti, 1, &g, 1) != LTEPHY_SUCCESS) return SRSRAN_ERROR;
+  // the symbols of srsran_enb_ul_fft stay on the device: only the grant travels
+  if (ltephy_submit_ul(u->phy, u->fft_done ? nullptr : reinterpret_cast<const float*>(q->in_buffer), &tti, 1, &g, 1) != LTEPHY_SUCCESS) return SRSRAN_ERROR;
+  u->fft_done = true;
   if (ltephy_get_ul(u->phy, &u->res, &u->chest, u->payload.data(), u->payload.size()) != LTEPHY_SUCCESS) return SRSRAN_ERROR;
   u->grant = g, u->have = true;
   return SRSRAN_SUCCESS;
@@ -312,7 +315,9 @@ int srsran_chest_ul_estimate_pusch(srsran_chest_ul_t* c, srsran_ul_sf_cfg_t* sf,
 static bool same_grant(const ltephy_ul_grant_t& a, const srsran_pusch_cfg_t* cfg)
 {
   const srsran_pusch_grant_t& s = cfg->grant;
-  return a.rnti == cfg->rnti && a.L_prb == s.L_prb && a.n_prb == s.n_prb[0] && a.tbs == s.tb.tbs && a.qm == ((unsigned)s.tb.mod < 5 ? QM_OF[s.tb.mod] : 0);
+  return a.rnti == cfg->rnti && a.L_prb == s.L_prb && a.n_prb == s.n_prb[0] && a.n_prb_slot1 == s.n_prb[1] && a.tbs == s.tb.tbs &&
+         a.qm == ((unsigned)s.tb.mod < 5 ? QM_OF[s.tb.mod] : 0) && a.nof_ack == cfg->uci_cfg.ack[0].nof_acks && a.ri_len == cfg->uci_cfg.cqi.ri_len &&
+         (a.cqi_len != 0) == cfg->uci_cfg.cqi.data_enable;
 }
 int srsran_pusch_decode(srsran_pusch_t* pq, srsran_ul_sf_cfg_t* sf, srsran_pusch_cfg_t* cfg, srsran_chest_ul_res_t* channel, cf_t* sf_symbols, srsran_pusch_res_t* data)
 {

@@ -196,8 +196,8 @@ int ltephy_copy_phase_b_device(ltephy_t* h, void* dst_dev, size_t cap, size_t* n
 typedef struct {
   uint32_t n_dmrs1;       /* cyclicShift of SIB2 (ULSchedule::set_config, src/src/ULSchedule.cc:140-158) */
   uint32_t delta_ss;      /* groupAssignmentPUSCH */
-  uint32_t group_hopping; /* 0 (group / sequence hopping are not implemented yet) */
-  uint32_t seq_hopping;   /* 0 */
+  uint32_t group_hopping; /* groupHoppingEnabled    (dmrs_cfg.group_hopping_en, ULSchedule.cc:145): u = (f_gh(ns) + f_ss) mod 30 */
+  uint32_t seq_hopping;   /* sequenceHoppingEnabled (dmrs_cfg.sequence_hopping_en, :146): v = c(ns) from 6 PRB on when group hopping is off */
 } ltephy_ul_cfg_t;
 typedef struct {
   uint32_t sf;            /* index of the UL subframe inside the submitted UL batch */
@@ -219,10 +219,12 @@ typedef struct {
 typedef struct {
   float noise, rsrp;      /* srsran_chest_ul_res_t.noise_estimate, RSRP (linear) */
   float snr_db;           /* .snr_db   (UL_Sniffer_PUSCH.cc:268) */
-  float ta_us;            /* .ta_us    (not estimated yet: 0) */
+  float ta_us;            /* .ta_us    timing offset from the phase slope of the DMRS estimates (meas_ta_en, UL_Sniffer_PUSCH.cc:424,574) */
 } ltephy_ul_chest_t;
 int ltephy_set_ul_cfg(ltephy_t* h, const ltephy_ul_cfg_t* cfg);
-/* iq_ul: n * sf_len cf32 of the UL carrier (one antenna: the reference uses antenna buffer 1); host memory */
+/* iq_ul: n * sf_len cf32 of the UL carrier (one antenna: the reference uses antenna buffer 1); host memory.  iq_ul may be NULL when the previous
+ * call demodulated the same n subframes: their symbols are decoded again with the new grants (srsran_enb_ul_fft once, decode_run per grant).
+ * L_prb >= 3: the 1- and 2-PRB DMRS base sequences (36.211 Tables 5.5.1.2-1 / -2) are not carried. */
 int ltephy_submit_ul(ltephy_t* h, const float* iq_ul, const uint32_t* tti, uint32_t n, const ltephy_ul_grant_t* grants, uint32_t ngrants);
 /* results[ngrants], chest[ngrants]; payload receives the TB bytes back to back */
 int ltephy_get_ul(ltephy_t* h, ltephy_tb_result_t* results, ltephy_ul_chest_t* chest, uint8_t* payload, size_t payload_cap);

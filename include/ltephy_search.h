@@ -63,6 +63,8 @@ void ltephy_search_config(ltephy_search_t* s, int shortcut, int skip_secondary, 
  * they differ, and ltephy_decode_subframes reports the first reading unless only the second passes a CRC (then crc = 2): the
  * batched form of "try the 64QAM table, then the 256QAM table" (src/src/DL_Sniffer_PDSCH.cc:1089-1210).  Off by default. */
 void ltephy_search_speculate_256qam(ltephy_search_t* s, int on);
+/* pusch-HoppingOffset of SIB2 (hopping_cfg.n_rb_ho, src/src/DCICollection.cc:166-168), used by ltephy_ul_dci_to_grant for type-1 hopping grants; default 0 */
+void ltephy_search_set_ul_hopping(ltephy_search_t* s, uint32_t n_rb_ho);
 #define LTEPHY_GRANT_ALT_TABLE 0x80000000u
 void ltephy_search_add_evergreen(ltephy_search_t* s, uint16_t rnti_start, uint16_t rnti_end, uint32_t format_idx);
 void ltephy_search_add_forbidden(ltephy_search_t* s, uint16_t rnti_start, uint16_t rnti_end, uint32_t format_idx);

@@ -59,6 +59,7 @@ class UlChest(C.Structure):
 
 
 TAP_UL_SYM = 5
+UL_FLAG_SLOT1 = 1
 CAND_DTYPE = np.dtype([("bits", "<u8"), ("rnti", "<u2"), ("valid", "u1"), ("pad", "u1", 5)])
 assert CAND_DTYPE.itemsize == C.sizeof(Cand) == 16
 COMPACT_CAP = 248
@@ -214,16 +215,16 @@ class LtePhy:
         return res, pl
 
     # ---- uplink
-    def set_ul_cfg(self, n_dmrs1=0, delta_ss=0):
-        cfg = UlCfg(n_dmrs1=n_dmrs1, delta_ss=delta_ss)
+    def set_ul_cfg(self, n_dmrs1=0, delta_ss=0, group_hopping=0, seq_hopping=0):
+        cfg = UlCfg(n_dmrs1=n_dmrs1, delta_ss=delta_ss, group_hopping=group_hopping, seq_hopping=seq_hopping)
         self._chk(self.L.ltephy_set_ul_cfg(self.h, C.byref(cfg)), "set_ul_cfg")
 
     def decode_ul(self, iq_ul, tti, grants):
-        """iq_ul complex64 [n][sf_len]; grants: list of UlGrant -> (results, chest, payload)"""
-        iq_ul = np.ascontiguousarray(iq_ul, np.complex64)
+        """iq_ul complex64 [n][sf_len] (None: decode the subframes of the previous call again); grants: list of UlGrant -> (results, chest, payload)"""
+        iq_ul = None if iq_ul is None else np.ascontiguousarray(iq_ul, np.complex64)
         tti = np.ascontiguousarray(tti, np.uint32)
         arr = (UlGrant * max(1, len(grants)))(*grants)
-        self._chk(self.L.ltephy_submit_ul(self.h, _p(iq_ul), _p(tti), len(tti), arr, len(grants)), "submit_ul")
+        self._chk(self.L.ltephy_submit_ul(self.h, None if iq_ul is None else _p(iq_ul), _p(tti), len(tti), arr, len(grants)), "submit_ul")
         res = (TbResult * max(1, len(grants)))()
         ch = (UlChest * max(1, len(grants)))()
         pl = np.zeros(len(grants) * 10000 + 64, np.uint8)
@@ -315,6 +316,7 @@ def _bind_search(L):
     L.ltephy_search_destroy.argtypes = [P]
     L.ltephy_search_config.argtypes = [P, C.c_int, C.c_int, C.c_uint32]
     L.ltephy_search_speculate_256qam.argtypes = [P, C.c_int]
+    L.ltephy_search_set_ul_hopping.argtypes = [P, C.c_uint32]
     L.ltephy_search_add_evergreen.argtypes = [P, C.c_uint16, C.c_uint16, C.c_uint32]
     L.ltephy_search_add_forbidden.argtypes = [P, C.c_uint16, C.c_uint16, C.c_uint32]
     L.ltephy_search_activate.argtypes = [P, C.c_uint16, C.c_uint32, C.c_int]

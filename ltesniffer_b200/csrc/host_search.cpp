@@ -258,6 +258,7 @@ struct ltephy_search {
   bool               skip_secondary  = false, shortcut = true;
   bool               speculate_256qam = false; // grants_from_dcis emits both MCS-table readings of a C-RNTI DCI (DL_Sniffer_PDSCH.cc:1089-1210)
   uint32_t           update_interval = 500, sf_cnt = 0;
+  uint32_t           ul_n_rb_ho = 0; // pusch-HoppingOffset of SIB2 (hopping_cfg.n_rb_ho, src/src/DCICollection.cc:168)
   ltephy_search_stats_t stats{};
   // per-subframe scratch
   const ltephy_cand_t*    T  = nullptr;
@@ -813,12 +814,18 @@ int ltephy_ul_dci_to_grant(const ltephy_search_t* s, const ltephy_dci_t* d, int 
   const uint32_t N = s->cell.nof_prb, rivb = clog2(N * (N + 1) / 2);
   Bits           b{d->bits};
   if (b.get(1) != 0) return LTEPHY_ERROR;            // format 0/1A flag
-  if (b.get(1) != 0) return LTEPHY_ERROR;            // frequency hopping: not supported
-  const uint32_t riv = b.get(rivb), mcs = b.get(5);
+  const uint32_t hop = b.get(1);                     // frequency hopping flag
+  uint32_t       riv = b.get(rivb), hop_kind = 0xFF;
+  const uint32_t mcs = b.get(5);
   b.get(1);                                          // ndi
   b.get(2);                                          // tpc
   const uint32_t cs = b.get(3);
-  uint32_t       L, S;
+  if (hop) { // the N_UL_hop most significant bits of the allocation select the hop (36.213 Tables 8.4-1 / 8.4-2): 0 +1/4, 1 -1/4, 2 +1/2, 3 type 2
+    const uint32_t nh = N < 50 ? 1 : 2, hb = riv >> (rivb - nh);
+    riv &= (1u << (rivb - nh)) - 1;
+    hop_kind = nh == 1 ? (hb == 0 ? 2 : 3) : hb;
+  }
+  uint32_t L, S;
   riv_decode(riv, N, L, S);
   if (L < 3 || L > N || S >= N || S + L > N) return LTEPHY_ERROR;
   uint32_t t = L;
@@ -826,6 +833,15 @@ int ltephy_ul_dci_to_grant(const ltephy_search_t* s, const ltephy_dci_t* d, int 
   while (t % 3 == 0) t /= 3;
   while (t % 5 == 0) t /= 5;
   if (t != 1) return LTEPHY_ERROR;                   // valid_prb_ul, src/src/UL_Sniffer_PUSCH.cc:3-10
+  uint32_t S1 = S;
+  if (hop_kind < 3) { // type 1: ul_sniffer_ra_ul_grant_to_grant_prb_allocation, lib/src/phy/falcon_phch/ul_sniffer_pusch.c:48-80
+    uint32_t ho = s->ul_n_rb_ho;
+    if (ho % 2) ho++;
+    const uint32_t nrb = N - ho - (N % 2);
+    if (S < ho / 2) return LTEPHY_ERROR;
+    S1 = hop_kind == 0 ? (nrb / 4 + S) % nrb : hop_kind == 1 ? (S < nrb / 4 ? nrb + S - nrb / 4 : S - nrb / 4) : (nrb / 2 + S) % nrb;
+    if (S1 + L > N) return LTEPHY_ERROR;
+  } // type 2 (hop_kind 3): the reference keeps n_prb_tilde = n_prb for both slots (ul_sniffer_pusch.c:32-44,224-226)
   memset(g, 0, sizeof(*g));
   int itbs;
   if (mcs > 28) return LTEPHY_ERROR;
@@ -855,6 +871,7 @@ int ltephy_ul_dci_to_grant(const ltephy_search_t* s, const ltephy_dci_t* d, int 
   }
   if (g->tbs <= 0) return LTEPHY_ERROR;
   g->sf = d->sf, g->rnti = d->rnti, g->rv = 0, g->L_prb = L, g->n_prb = S, g->n_dmrs2 = dmrs2_map[cs & 7];
+  g->n_prb_slot1 = S1, g->flags = LTEPHY_UL_FLAG_SLOT1;
   return LTEPHY_SUCCESS;
 }
 
@@ -951,6 +968,10 @@ ltephy_search_t* ltephy_search_create(const ltephy_t* h, uint32_t histogram_thre
   return ltephy_search_create_cell(a, b, c, d, histogram_threshold);
 }
 void ltephy_search_destroy(ltephy_search_t* s) { delete s; }
+void ltephy_search_set_ul_hopping(ltephy_search_t* s, uint32_t n_rb_ho)
+{
+  if (s) s->ul_n_rb_ho = n_rb_ho;
+}
 void ltephy_search_speculate_256qam(ltephy_search_t* s, int on)
 {
   if (s) s->speculate_256qam = on != 0;

@@ -290,6 +290,39 @@ bool cb_segmentation(uint32_t tbs, Segm& s)
   s.F = s.Cp * s.Kp + s.Cm * s.Km - Bp;
   return true;
 }
+bool uci_layout(uint32_t L_prb, uint32_t qm, uint32_t tbs, uint32_t nof_ack, uint32_t ri_len, uint32_t cqi_len, uint32_t I_ack, uint32_t I_ri, uint32_t I_cqi,
+                UciLayout& out)
+{
+  // betaOffset tables, 36.213 8.6.3 (-1: reserved index)
+  static const float B_ACK[16] = {2.000f, 2.500f, 3.125f, 4.000f, 5.000f, 6.250f, 8.000f, 10.000f, 12.625f, 15.875f, 20.000f, 31.000f, 50.000f, 80.000f, 126.000f, -1.0f};
+  static const float B_RI[16]  = {1.250f, 1.625f, 2.000f, 2.500f, 3.125f, 4.000f, 5.000f, 6.250f, 8.000f, 10.000f, 12.625f, 15.875f, 20.000f, -1.0f, -1.0f, -1.0f};
+  static const float B_CQI[16] = {-1.0f, -1.0f, 1.125f, 1.250f, 1.375f, 1.625f, 1.750f, 2.000f, 2.250f, 2.500f, 2.875f, 3.125f, 3.500f, 4.000f, 5.000f, 6.250f};
+  out = UciLayout{};
+  const uint32_t M = 12 * L_prb, nsymb = 12; // no SRS: 12 data SC-FDMA symbols (ul_sf.shortened = false, src/src/DL_Sniffer_PDSCH.cc:655)
+  Segm           sg;
+  if (!cb_segmentation(tbs, sg)) return false;
+  const uint32_t Ksum = sg.Cm * sg.Km + sg.Cp * sg.Kp;
+  if (!Ksum) return false;
+  // Q' = min(ceil(O M_sc N_symb beta / sum K_r), 4 M_sc), in float like srsRAN's Q_prime_ri_ack / Q_prime_cqi
+  auto qprime = [&](uint32_t O, float beta) { return (uint32_t)ceilf((float)O * (float)M * (float)nsymb * beta / (float)Ksum); };
+  if (ri_len) {
+    const float b = B_RI[I_ri & 15];
+    if (b < 0) return false;
+    out.Qp_ri = std::min(qprime(ri_len, b), 4 * M);
+  }
+  if (nof_ack) {
+    const float b = B_ACK[I_ack & 15];
+    if (b < 0) return false;
+    out.Qp_ack = std::min(qprime(nof_ack, b), 4 * M);
+  }
+  if (cqi_len) {
+    const float b = B_CQI[I_cqi & 15];
+    if (b < 0) return false;
+    out.Qp_cqi = std::min(qprime(cqi_len + (cqi_len <= 11 ? 0u : 8u), b), M * nsymb - out.Qp_ri); // CRC-8 from 12 bits on (36.212 5.2.2.6.4)
+  }
+  out.G = (M * nsymb - out.Qp_cqi - out.Qp_ri) * qm;
+  return true;
+}
 bool qpp_params(uint32_t K, uint32_t& f1, uint32_t& f2)
 {
   int i = lte_qpp_index_ge(K);

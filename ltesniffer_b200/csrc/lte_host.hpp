@@ -71,6 +71,13 @@ struct Segm {
   uint32_t K(uint32_t r) const { return r < Cm ? Km : Kp; }
 };
 bool     cb_segmentation(uint32_t tbs, Segm& s);
+// control information multiplexed on PUSCH (36.212 5.2.2.6): Q' modulation symbols of HARQ-ACK, RI, CQI and the UL-SCH bits G that remain.
+// false: invalid TBS or a reserved beta-offset index (36.213 Tables 8.6.3-1..3)
+struct UciLayout {
+  uint32_t Qp_ack, Qp_ri, Qp_cqi, G;
+};
+bool uci_layout(uint32_t L_prb, uint32_t qm, uint32_t tbs, uint32_t nof_ack, uint32_t ri_len, uint32_t cqi_len, uint32_t I_ack, uint32_t I_ri, uint32_t I_cqi,
+                UciLayout& out);
 bool     qpp_params(uint32_t K, uint32_t& f1, uint32_t& f2);
 uint32_t rm_turbo_E(uint32_t G, uint32_t C, uint32_t r, uint32_t Qm, uint32_t NL);
 // order[k], k in [0, nn): the stream position (s*(K+4)+i) that receives soft bit k, k+nn, k+2nn, ...

@@ -27,7 +27,7 @@ void launch_tb_crc(const DevTb*, uint32_t, const uint8_t*, const uint8_t*, const
                    uint64_t*);
 void launch_ul_ofdm(const DevCell&, const float2*, float2*, uint32_t, cudaStream_t, uint64_t*);
 void launch_pusch(const DevCell&, const DevUlGrant*, uint32_t, uint32_t, uint32_t, const float2*, const float2*, const float2*, const uint32_t*,
-                  const uint32_t*, uint32_t, uint32_t*, short*, ltephy_ul_chest_t*, cudaStream_t, uint64_t*);
+                  const uint32_t*, uint32_t, uint32_t*, short*, DevUlChest*, cudaStream_t, uint64_t*);
 }
 
 thread_local std::string ltephy_g_err;
@@ -719,17 +719,20 @@ extern "C" int ltephy_get_phase_b(ltephy_t* h, ltephy_tb_result_t* results, uint
 extern "C" int ltephy_set_ul_cfg(ltephy_t* h, const ltephy_ul_cfg_t* cfg)
 {
   if (!h || !cfg) return fail(LTEPHY_ERROR_INVALID_INPUTS, "set_ul_cfg: bad arguments");
-  if (cfg->group_hopping || cfg->seq_hopping) return fail(LTEPHY_ERROR_INVALID_INPUTS, "set_ul_cfg: group / sequence hopping not implemented");
   h->ulcfg = *cfg, h->ulcfg_set = true;
   const uint32_t fss = ((h->cell.cell_id % 30) + cfg->delta_ss) % 30;
   auto           cw  = ltehost::gold_words((h->cell.cell_id / 30) * 32 + fss, 8 * 7 * 20 + 8);
-  for (uint32_t ns = 0; ns < 20; ns++) { // n_PRS(ns), 36.211 5.5.2.1.1
-    uint32_t v = 0;
+  auto           gh  = ltehost::gold_words(h->cell.cell_id / 30, 8 * 20 + 8);
+  for (uint32_t ns = 0; ns < 20; ns++) {
+    uint32_t v = 0, f = 0;
     for (uint32_t i = 0; i < 8; i++) {
-      const uint32_t b = 8 * 7 * ns + i;
-      v += ((cw[b >> 5] >> (b & 31)) & 1u) << i;
+      const uint32_t b = 8 * 7 * ns + i, b2 = 8 * ns + i;
+      v += ((cw[b >> 5] >> (b & 31)) & 1u) << i; // n_PRS(ns), 36.211 5.5.2.1.1
+      f += ((gh[b2 >> 5] >> (b2 & 31)) & 1u) << i; // f_gh(ns), 36.211 5.5.1.3 (c_init = floor(cell_id / 30))
     }
     h->n_prs[ns] = v;
+    h->ul_u[ns]  = ((cfg->group_hopping ? f % 30 : 0) + fss) % 30;
+    h->ul_v[ns]  = (!cfg->group_hopping && cfg->seq_hopping) ? (cw[ns >> 5] >> (ns & 31)) & 1u : 0; // 36.211 5.5.1.4 (same c_init as n_PRS); used from 6 PRB on
   }
   h->ul_tab_cache.clear();
   h->ulpool_used = 0;
@@ -748,10 +751,10 @@ static uint32_t largest_prime_below(uint32_t n)
   }
   return 2;
 }
-// kind 0: DMRS r_{u,0}^{(alpha)} for (M, ncs); kind 1: IDFT twiddles for M
-static int ul_table_for(ltephy* h, uint32_t kind, uint32_t M, uint32_t ncs, uint32_t& off)
+// kind 0: DMRS r_{u,v}^{(alpha)} for (M, ncs, u, v); kind 1: IDFT twiddles for M
+static int ul_table_for(ltephy* h, uint32_t kind, uint32_t M, uint32_t ncs, uint32_t u, uint32_t v, uint32_t& off)
 {
-  const uint64_t key = ((uint64_t)kind << 40) | ((uint64_t)M << 8) | ncs;
+  const uint64_t key = ((uint64_t)kind << 40) | ((uint64_t)M << 16) | (u << 9) | (v << 8) | ncs;
   auto           it  = h->ul_tab_cache.find(key);
   if (it != h->ul_tab_cache.end()) {
     off = it->second;
@@ -759,9 +762,10 @@ static int ul_table_for(ltephy* h, uint32_t kind, uint32_t M, uint32_t ncs, uint
   }
   std::vector<float2> t(M);
   if (kind == 0) {
-    const uint32_t fss = ((h->cell.cell_id % 30) + h->ulcfg.delta_ss) % 30, Nzc = largest_prime_below(M);
-    const double   qb  = (double)Nzc * (fss + 1) / 31.0;
-    const uint32_t q   = (uint32_t)std::floor(qb + 0.5);
+    const uint32_t Nzc = largest_prime_below(M);
+    const double   qb  = (double)Nzc * (u + 1) / 31.0;
+    uint32_t       q   = (uint32_t)std::floor(qb + 0.5);
+    if (v) q = ((uint32_t)std::floor(2.0 * qb) & 1u) ? q - 1 : q + 1; // q = floor(qb + 1/2) + v (-1)^floor(2 qb), 36.211 5.5.1.1
     for (uint32_t n = 0; n < M; n++) {
       const uint64_t m  = n % Nzc, tt = ((uint64_t)q * m * (m + 1)) % (2ull * Nzc);
       const uint32_t a  = (ncs * n) % 12;
@@ -785,16 +789,19 @@ static int ul_table_for(ltephy* h, uint32_t kind, uint32_t M, uint32_t ncs, uint
 
 extern "C" int ltephy_submit_ul(ltephy_t* h, const float* iq_ul, const uint32_t* tti, uint32_t n, const ltephy_ul_grant_t* gin, uint32_t ng)
 {
-  if (!h || !iq_ul || !tti || n == 0 || n > h->cfg.max_subframes || (!gin && ng)) return fail(LTEPHY_ERROR_INVALID_INPUTS, "submit_ul: bad arguments");
+  if (!h || !tti || n == 0 || n > h->cfg.max_subframes || (!gin && ng)) return fail(LTEPHY_ERROR_INVALID_INPUTS, "submit_ul: bad arguments");
   if (!h->ulcfg_set) return fail(LTEPHY_ERROR_INVALID_INPUTS, "submit_ul: ltephy_set_ul_cfg has not been called");
+  if (!iq_ul && h->n_ul != n) return fail(LTEPHY_ERROR_INVALID_INPUTS, "submit_ul: no IQ given and the previous call demodulated %u subframes, not %u", h->n_ul, n);
   CU(cudaSetDevice(h->cfg.device));
   const DevCell& c = h->dc;
   if (h->d_uliq.reserve((size_t)h->cfg.max_subframes * c.sf_len) || h->d_ulsym.reserve((size_t)h->cfg.max_subframes * 14 * c.nsc) ||
       h->d_ulpool.reserve((size_t)1 << 20))
     return fail(LTEPHY_ERROR, "device allocation failed");
   CU(cudaEventRecord(h->ev[2], h->stream));
-  CU(cudaMemcpyAsync(h->d_uliq.p, iq_ul, (size_t)n * c.sf_len * sizeof(float2), cudaMemcpyHostToDevice, h->stream));
-  launch_ul_ofdm(c, h->d_uliq.p, h->d_ulsym.p, n, h->stream, &h->launches);
+  if (iq_ul) { // NULL: the demodulated symbols of the previous call stay (srsran_enb_ul_fft once, then one decode per grant)
+    CU(cudaMemcpyAsync(h->d_uliq.p, iq_ul, (size_t)n * c.sf_len * sizeof(float2), cudaMemcpyHostToDevice, h->stream));
+    launch_ul_ofdm(c, h->d_uliq.p, h->d_ulsym.p, n, h->stream, &h->launches);
+  }
   h->n_ul = n;
   // jobs
   h->ulgrants.clear(), h->cbs.clear(), h->pairs.clear(), h->tbs.clear(), h->pair_pi_off.clear();
@@ -807,20 +814,31 @@ extern "C" int ltephy_submit_ul(ltephy_t* h, const float* iq_ul, const uint32_t*
   for (uint32_t gi = 0; gi < ng; gi++) {
     const ltephy_ul_grant_t& g = gin[gi];
     if (g.sf >= n) return fail(LTEPHY_ERROR_INVALID_INPUTS, "UL grant %u: subframe outside the batch", gi);
-    const uint32_t M = 12 * g.L_prb;
-    if (g.L_prb < 3 || g.n_prb + g.L_prb > c.nof_prb || (g.qm != 2 && g.qm != 4 && g.qm != 6 && g.qm != 8) || g.tbs <= 0)
+    const uint32_t M = 12 * g.L_prb, n_prb1 = (g.flags & LTEPHY_UL_FLAG_SLOT1) ? g.n_prb_slot1 : g.n_prb;
+    // L_prb 1 and 2 use the 30 + 30 computer-generated QPSK base sequences of 36.211 Tables 5.5.1.2-1 / -2, which this build does not carry
+    if (g.L_prb < 3 || g.n_prb + g.L_prb > c.nof_prb || n_prb1 + g.L_prb > c.nof_prb || (g.qm != 2 && g.qm != 4 && g.qm != 6 && g.qm != 8) || g.tbs <= 0)
       return fail(LTEPHY_ERROR_INVALID_INPUTS, "UL grant %u: unsupported allocation / modulation", gi);
-    if (((g.flags & LTEPHY_UL_FLAG_SLOT1) && g.n_prb_slot1 != g.n_prb) || g.nof_ack || g.cqi_len || g.ri_len)
-      return fail(LTEPHY_ERROR_INVALID_INPUTS, "UL grant %u: hopping / UCI multiplexing not supported", gi);
     DevUlGrant d{};
-    d.sf = g.sf, d.sf_idx = tti[g.sf] % 10, d.rnti = g.rnti, d.M = M, d.k0 = 12 * g.n_prb, d.qm = g.qm;
+    uint32_t   rad = M;
+    while (rad % 5 == 0) d.rad |= 5u << (4 * d.nrad++), rad /= 5;
+    while (rad % 3 == 0) d.rad |= 3u << (4 * d.nrad++), rad /= 3;
+    while (rad % 4 == 0) d.rad |= 4u << (4 * d.nrad++), rad /= 4;
+    if (rad % 2 == 0) d.rad |= 2u << (4 * d.nrad++), rad /= 2;
+    if (rad != 1) return fail(LTEPHY_ERROR_INVALID_INPUTS, "UL grant %u: L_prb %u is not 2^a 3^b 5^c (valid_prb_ul)", gi, g.L_prb);
+    if (g.nof_ack > 2 || g.ri_len > 2) return fail(LTEPHY_ERROR_INVALID_INPUTS, "UL grant %u: more than 2 ACK / RI bits", gi);
+    ltehost::UciLayout L;
+    if (!ltehost::uci_layout(g.L_prb, g.qm, (uint32_t)g.tbs, g.nof_ack, g.ri_len, g.cqi_len, g.I_offset_ack, g.I_offset_ri, g.I_offset_cqi, L))
+      return fail(LTEPHY_ERROR_INVALID_INPUTS, "UL grant %u: invalid TBS / reserved beta offset index", gi);
+    d.sf = g.sf, d.sf_idx = tti[g.sf] % 10, d.rnti = g.rnti, d.M = M, d.k0[0] = 12 * g.n_prb, d.k0[1] = 12 * n_prb1, d.qm = g.qm;
+    d.qp_ack = L.Qp_ack, d.qp_ri = L.Qp_ri, d.qp_cqi = L.Qp_cqi;
     for (uint32_t sl = 0; sl < 2; sl++) {
-      const uint32_t ncs = (h->ulcfg.n_dmrs1 + g.n_dmrs2 + h->n_prs[2 * d.sf_idx + sl]) % 12;
-      if (ul_table_for(h, 0, M, ncs, d.dmrs_off[sl])) return fail(LTEPHY_ERROR, "UL table upload failed");
+      const uint32_t ns = 2 * d.sf_idx + sl, ncs = (h->ulcfg.n_dmrs1 + g.n_dmrs2 + h->n_prs[ns]) % 12;
+      if (ul_table_for(h, 0, M, ncs, h->ul_u[ns], M >= 72 ? h->ul_v[ns] : 0, d.dmrs_off[sl])) return fail(LTEPHY_ERROR, "UL table upload failed");
     }
-    if (ul_table_for(h, 1, M, 0, d.idft_off)) return fail(LTEPHY_ERROR, "UL table upload failed");
-    const uint32_t G = 12 * M * g.qm, w = (G + 31) / 32;
+    if (ul_table_for(h, 1, M, 0, 0, 0, d.idft_off)) return fail(LTEPHY_ERROR, "UL table upload failed");
+    const uint32_t G = L.G, w = (12 * M * g.qm + 31) / 32;
     if (w > h->gold_words) return fail(LTEPHY_ERROR, "UL grant %u: codeword longer than the scrambling basis", gi);
+    if (G < g.qm * 12) return fail(LTEPHY_ERROR_INVALID_INPUTS, "UL grant %u: the control information leaves no room for the transport block", gi);
     d.llr_off = (uint32_t)h->pllr_elems, d.scr_off = (uint32_t)seq_words;
     seq_words += w + 1;
     h->pllr_elems += (G + 7) & ~7u;
@@ -887,9 +905,13 @@ extern "C" int ltephy_get_ul(ltephy_t* h, ltephy_tb_result_t* results, ltephy_ul
     }
     results[i] = o;
     if (chest) {
-      chest[i]        = h->h_ulchest.p[i];
-      chest[i].snr_db = 10.0f * log10f(chest[i].rsrp / chest[i].noise);
-      chest[i].ta_us  = 0.0f;
+      const DevUlChest& dcst = h->h_ulchest.p[i];
+      chest[i].noise = dcst.noise, chest[i].rsrp = dcst.rsrp;
+      chest[i].snr_db = 10.0f * log10f(dcst.rsrp / dcst.noise);
+      // timing offset: -arg(sum ls[n+1] conj(ls[n])) / 2 pi per slot (srsran_vec_estimate_frequency over the pilots, meas_ta_en), slot average, / 15e-3 -> us
+      float ta = 0.0f;
+      for (int sl = 0; sl < 2; sl++) ta = ta + (-atan2f(dcst.ci[sl], dcst.cr[sl]) / 6.28318530717958647692f) / 2.0f;
+      chest[i].ta_us = std::isnormal(ta) ? ta / 15e-3f : 0.0f;
     }
   }
   return LTEPHY_SUCCESS;

@@ -136,11 +136,11 @@ struct ltephy {
   // uplink
   ltephy_ul_cfg_t            ulcfg{};
   bool                       ulcfg_set = false;
-  uint32_t                   n_prs[20]{};
+  uint32_t                   n_prs[20]{}, ul_u[20]{}, ul_v[20]{}; // per slot: n_PRS, base-sequence group u and sequence v
   DevBuf<float2>             d_uliq, d_ulsym, d_ulpool; // d_ulpool: DMRS sequences and IDFT twiddles
   DevBuf<DevUlGrant>         d_ulgrants;
-  DevBuf<ltephy_ul_chest_t>  d_ulchest;
-  PinBuf<ltephy_ul_chest_t>  h_ulchest;
+  DevBuf<DevUlChest>         d_ulchest;
+  PinBuf<DevUlChest>         h_ulchest;
   std::vector<DevUlGrant>    ulgrants;
   std::map<uint64_t, uint32_t> ul_tab_cache; // (kind, M, ncs) -> offset in d_ulpool
   size_t                     ulpool_used = 0;

@@ -871,12 +871,62 @@ void lteo_ul_ofdm(lteo_t* q, const cf_t* iq, cf_t* sym)
   free(re), free(im), free(x);
 }
 
+/* M-point inverse DFT, M = 2^a 3^b 5^c: Stockham autosort, decimation in time, radices in the order 5.., 3.., 4.., 2; every butterfly is the
+ * plain sum over its inputs in index order (twiddle first), W[m] = exp(+j 2 pi m / M).  The CUDA kernel evaluates the same expression tree. */
+static uint32_t idft_radices(uint32_t M, uint32_t* rad)
+{
+  uint32_t n = 0;
+  while (M % 5 == 0) rad[n++] = 5, M /= 5;
+  while (M % 3 == 0) rad[n++] = 3, M /= 3;
+  while (M % 4 == 0) rad[n++] = 4, M /= 4;
+  if (M % 2 == 0) rad[n++] = 2, M /= 2;
+  return M == 1 ? n : 0;
+}
+static cf_t* idft_mixed(const cf_t* W, uint32_t M, cf_t* a, cf_t* b)
+{
+  uint32_t rad[16], ns = idft_radices(M, rad), Ns = 1;
+  cf_t *   src = a, *dst = b;
+  for (uint32_t st = 0; st < ns; st++) {
+    const uint32_t R = rad[st], Q = M / R;
+    for (uint32_t j = 0; j < Q; j++) {
+      const uint32_t k = j % Ns, tstep = k * (M / (Ns * R));
+      cf_t           v[5];
+      for (uint32_t r = 0; r < R; r++) {
+        cf_t x = src[j + r * Q];
+        if (r * tstep) {
+          cf_t w = W[r * tstep];
+          v[r]   = (cf_t){x.re * w.re - x.im * w.im, x.re * w.im + x.im * w.re};
+        } else
+          v[r] = x;
+      }
+      const uint32_t o0 = (j / Ns) * Ns * R + k;
+      for (uint32_t qq = 0; qq < R; qq++) {
+        float ar = v[0].re, ai = v[0].im;
+        for (uint32_t r = 1; r < R; r++) {
+          cf_t w = W[((r * qq) % R) * Q];
+          ar     = ar + (v[r].re * w.re - v[r].im * w.im);
+          ai     = ai + (v[r].re * w.im + v[r].im * w.re);
+        }
+        dst[o0 + qq * Ns] = (cf_t){ar, ai};
+      }
+    }
+    cf_t* t = src;
+    src = dst, dst = t, Ns *= R;
+  }
+  return src;
+}
+
 int lteo_pusch_decode(lteo_t* q, const lte_ul_cfg_t* ucfg, uint32_t sf_idx, const lte_ul_grant_t* g, const cf_t* sym, uint32_t max_iter,
                       uint8_t* payload, int* crc_ok, lteo_ul_chest_t* chest, int16_t* llr_out)
 {
   static const uint32_t DATA_SYM[12] = {0, 1, 2, 4, 5, 6, 7, 8, 9, 11, 12, 13};
-  const uint32_t        M = 12 * g->L_prb, k0 = 12 * g->n_prb, nsc = q->nsc, Qm = g->qm, G = g->nof_bits;
-  if (M < 36 || k0 + M > nsc || G != 12 * M * Qm) return -1;
+  const uint32_t        M = 12 * g->L_prb, nsc = q->nsc, Qm = g->qm;
+  const uint32_t        k0s[2] = {12 * g->n_prb, 12 * (g->hop ? g->n_prb_slot1 : g->n_prb)};
+  const int             hop = k0s[0] != k0s[1];
+  lte_uci_layout_t      L;
+  lte_uci_layout(g, &L);
+  const uint32_t G = L.G;
+  if (M < 36 || k0s[0] + M > nsc || k0s[1] + M > nsc || !lte_ul_valid_prb(g->L_prb)) return -1;
   cf_t*  r   = (cf_t*)malloc(sizeof(cf_t) * M);
   cf_t*  ls  = (cf_t*)malloc(sizeof(cf_t) * 2 * M);
   cf_t*  sm  = (cf_t*)malloc(sizeof(cf_t) * 2 * M);
@@ -884,14 +934,14 @@ int lteo_pusch_decode(lteo_t* q, const lte_ul_cfg_t* ucfg, uint32_t sf_idx, cons
   /* smoothing taps (w, 1-2w, w), w = 0.3333 (srsRAN chest_ul default 3-tap filter), edges renormalised */
   const float f[3] = {0.3333f, 1.0f - 2.0f * 0.3333f, 0.3333f};
   const float ncorr = (1.0f - 2.0f * f[1]) + (f[0] * f[0] + f[1] * f[1] + f[2] * f[2]);
-  float       nsum = 0.0f, psum = 0.0f;
+  float       nsum = 0.0f, psum = 0.0f, ta = 0.0f;
   for (uint32_t sl = 0; sl < 2; sl++) {
     if (lte_pusch_dmrs(&q->cell, ucfg, 2 * sf_idx + sl, g->n_dmrs2, M, r)) {
       free(r), free(ls), free(sm), free(tmp);
       return -2;
     }
     for (uint32_t n = 0; n < M; n++) {
-      cf_t y = sym[(7 * sl + 3) * nsc + k0 + n];
+      cf_t y = sym[(7 * sl + 3) * nsc + k0s[sl] + n];
       ls[sl * M + n].re = y.re * r[n].re + y.im * r[n].im;
       ls[sl * M + n].im = y.im * r[n].re - y.re * r[n].im;
     }
@@ -914,11 +964,21 @@ int lteo_pusch_decode(lteo_t* q, const lte_ul_cfg_t* ucfg, uint32_t sf_idx, cons
     nsum = nsum + lteo_det_sum(tmp, M);
     for (uint32_t n = 0; n < M; n++) tmp[n] = sm[sl * M + n].re * sm[sl * M + n].re + sm[sl * M + n].im * sm[sl * M + n].im;
     psum = psum + lteo_det_sum(tmp, M);
+    /* timing offset from the phase slope of the least-squares estimates (srsran_vec_estimate_frequency over the pilots of one slot, meas_ta_en,
+     * UL_Sniffer_PUSCH.cc:424): -arg(sum ls[n+1] conj(ls[n])) / 2 pi, averaged over the slots, / 15e-3 -> microseconds */
+    const cf_t* e = ls + sl * M;
+    for (uint32_t n = 0; n + 1 < M; n++) tmp[n] = e[n + 1].re * e[n].re + e[n + 1].im * e[n].im;
+    tmp[M - 1] = 0.0f;
+    float cr = lteo_det_sum(tmp, M);
+    for (uint32_t n = 0; n + 1 < M; n++) tmp[n] = e[n + 1].im * e[n].re - e[n + 1].re * e[n].im;
+    float ci = lteo_det_sum(tmp, M);
+    ta       = ta + (-atan2f(ci, cr) / 6.28318530717958647692f) / 2.0f;
   }
   if (chest) {
     chest->noise  = (nsum / (float)(2 * M)) / ncorr;
     chest->rsrp   = psum / (float)(2 * M);
     chest->snr_db = 10.0f * log10f(chest->rsrp / chest->noise);
+    chest->ta_us  = isnormal(ta) ? ta / 15e-3f : 0.0f;
   }
   /* IDFT twiddles W[m] = exp(+j 2 pi m / M) */
   cf_t* W = (cf_t*)malloc(sizeof(cf_t) * M);
@@ -928,37 +988,39 @@ int lteo_pusch_decode(lteo_t* q, const lte_ul_cfg_t* ucfg, uint32_t sf_idx, cons
   }
   const float scl = 1.0f / sqrtf((float)M);
   cf_t*       x   = (cf_t*)malloc(sizeof(cf_t) * M);
-  int16_t*    e   = (int16_t*)malloc(sizeof(int16_t) * (G + 16));
-  uint8_t*    scr = (uint8_t*)malloc(G);
-  lte_gold_bits(((uint32_t)g->rnti << 14) + (sf_idx << 9) + q->cell.cell_id, scr, G);
+  cf_t*       x2  = (cf_t*)malloc(sizeof(cf_t) * M);
+  int16_t*    e   = (int16_t*)calloc(G + 16, sizeof(int16_t));
+  uint8_t*    scr = (uint8_t*)malloc(12 * M * Qm);
+  uint8_t*    kind = (uint8_t*)malloc(12 * M);
+  uint32_t*   dpos = (uint32_t*)malloc(sizeof(uint32_t) * 12 * M);
+  lte_uci_map(M, &L, kind, dpos);
+  lte_gold_bits(((uint32_t)g->rnti << 14) + (sf_idx << 9) + q->cell.cell_id, scr, 12 * M * Qm);
   for (uint32_t c = 0; c < 12; c++) {
-    const uint32_t l = DATA_SYM[c];
+    const uint32_t l = DATA_SYM[c], sl = c / 6, k0 = k0s[sl];
     const float    t = (float)((int)l - 3) / 7.0f;
     for (uint32_t n = 0; n < M; n++) {
       cf_t A = sm[n], B = sm[M + n];
-      cf_t h = {A.re + (B.re - A.re) * t, A.im + (B.im - A.im) * t};
+      cf_t h = hop ? sm[sl * M + n] : (cf_t){A.re + (B.re - A.re) * t, A.im + (B.im - A.im) * t}; /* hopping: each slot stands alone */
       cf_t y = sym[l * nsc + k0 + n];
       float den = h.re * h.re + h.im * h.im;
       x[n].re   = (y.re * h.re + y.im * h.im) / den;
       x[n].im   = (y.im * h.re - y.re * h.im) / den;
     }
+    const cf_t* zt = idft_mixed(W, M, x, x2);
     for (uint32_t k = 0; k < M; k++) {
-      float ar = 0.0f, ai = 0.0f;
-      for (uint32_t i = 0; i < M; i++) {
-        cf_t w = W[(uint32_t)(((uint64_t)i * k) % M)];
-        ar     = ar + (x[i].re * w.re - x[i].im * w.im);
-        ai     = ai + (x[i].re * w.im + x[i].im * w.re);
-      }
-      cf_t    z = {ar * scl, ai * scl};
+      cf_t    z = {zt[k].re * scl, zt[k].im * scl};
       int16_t v[8];
       demod_s(z, Qm, v);
+      const uint32_t p = k * 12 + c, kd = kind[p]; /* row k, column c of the channel interleaver (36.212 5.2.2.8) */
+      if (kd != 0 && kd != 3) continue;            /* CQI / RI symbol: not part of the UL-SCH codeword */
       for (uint32_t b = 0; b < Qm; b++) {
         uint32_t hb = (c * M + k) * Qm + b; /* position in the interleaved (transmitted) order */
         int16_t  d  = scr[hb] ? (int16_t)-v[b] : v[b];
-        e[(k * 12 + c) * Qm + b] = d;       /* channel de-interleaver, 36.212 5.2.2.8 */
+        e[dpos[p] * Qm + b] = kd == 3 ? 0 : d; /* an ACK symbol overwrote these coded bits: erasure */
       }
     }
   }
+  free(x2), free(kind), free(dpos);
   if (llr_out) memcpy(llr_out, e, sizeof(int16_t) * G);
   *crc_ok = lteo_dlsch_decode(e, G, (uint32_t)g->tbs, g->rv, Qm, 1, max_iter, 1, payload, NULL);
   free(r), free(ls), free(sm), free(tmp), free(W), free(x), free(e), free(scr);

@@ -90,7 +90,7 @@ int lteo_phase_a(lteo_t* q, const cf_t* iq, uint32_t sf_idx, cf_t* sym, cf_t* ce
 extern "C" {
 #endif
 typedef struct {
-  float noise, rsrp, snr_db;
+  float noise, rsrp, snr_db, ta_us;
 } lteo_ul_chest_t;
 /* K1-UL: iq[sf_len] -> sym[14*nsc] with the 7.5 kHz shift removed */
 void lteo_ul_ofdm(lteo_t* q, const cf_t* iq, cf_t* sym);

@@ -918,14 +918,39 @@ uint32_t lte_largest_prime_below(uint32_t n)
   }
   return 2;
 }
-int lte_ul_dci_to_grant(const lte_cell_t* c, const lte_dci_t* d, int table, lte_ul_grant_t* g)
+int lte_ul_dci_to_grant(const lte_cell_t* c, const lte_dci_t* d, int table, lte_ul_grant_t* g) { return lte_ul_dci_to_grant_hop(c, NULL, d, table, g); }
+int lte_ul_dci_to_grant_hop(const lte_cell_t* c, const lte_ul_cfg_t* ucfg, const lte_dci_t* d, int table, lte_ul_grant_t* g)
 {
   static const uint8_t dmrs2_map[8] = {0, 6, 3, 4, 2, 8, 10, 9}; /* 36.211 Table 5.5.2.1.1-1 */
   memset(g, 0, sizeof(*g));
-  if (d->format != LTE_DCI_FORMAT0 || d->hop) return -1;
-  uint32_t L, S;
-  riv_decode(d->riv, c->nof_prb, &L, &S);
-  if (L < 1 || L > c->nof_prb || S + L > c->nof_prb) return -1;
+  if (d->format != LTE_DCI_FORMAT0) return -1;
+  uint32_t L, S, riv = d->riv, hop_kind = 0xFF;
+  const uint32_t N = c->nof_prb;
+  if (d->hop) { /* the N_UL_hop most significant bits of the allocation field select the hop (36.213 Tables 8.4-1 / 8.4-2) */
+    uint32_t rivb = 0, nh = N < 50 ? 1 : 2;
+    while ((1u << rivb) < N * (N + 1) / 2) rivb++;
+    uint32_t hb = riv >> (rivb - nh);
+    riv &= (1u << (rivb - nh)) - 1;
+    hop_kind = nh == 1 ? (hb == 0 ? 2 : 3) : hb; /* 0 +1/4, 1 -1/4, 2 +1/2, 3 type 2 */
+  }
+  riv_decode(riv, N, &L, &S);
+  if (L < 1 || L > N || S + L > N) return -1;
+  g->n_prb_slot1 = S;
+  if (hop_kind < 3) { /* type 1: ul_sniffer_ra_ul_grant_to_grant_prb_allocation, lib/src/phy/falcon_phch/ul_sniffer_pusch.c:48-80 */
+    uint32_t ho = ucfg ? ucfg->n_rb_ho : 0;
+    if (ho % 2) ho++;
+    const uint32_t nrb = N - ho - (N % 2);
+    if (S < ho / 2) return -1;
+    uint32_t s1 = S;
+    if (hop_kind == 0)
+      s1 = (nrb / 4 + S) % nrb;
+    else if (hop_kind == 1)
+      s1 = S < nrb / 4 ? nrb + S - nrb / 4 : S - nrb / 4;
+    else
+      s1 = (nrb / 2 + S) % nrb;
+    if (s1 + L > N) return -1;
+    g->hop = 1, g->n_prb_slot1 = s1;
+  }
   g->rnti = d->rnti, g->L_prb = L, g->n_prb = S, g->mcs = d->mcs[0], g->n_dmrs2 = dmrs2_map[d->n_dmrs & 7];
   uint32_t m = d->mcs[0];
   int      itbs;
@@ -960,11 +985,26 @@ int lte_ul_dci_to_grant(const lte_cell_t* c, const lte_dci_t* d, int table, lte_
   g->nof_bits = g->nof_re * g->qm;
   return 0;
 }
+void lte_pusch_uv(const lte_cell_t* c, const lte_ul_cfg_t* u, uint32_t ns, uint32_t M, uint32_t* u_out, uint32_t* v_out)
+{
+  const uint32_t fss = ((c->cell_id % 30) + u->delta_ss) % 30; /* f_ss^PUSCH */
+  uint32_t       fgh = 0, v = 0;
+  uint8_t        cb[8 * 20 + 8];
+  if (u->group_hopping) { /* f_gh(ns) = sum c(8 ns + i) 2^i mod 30, c_init = floor(cell_id / 30) */
+    lte_gold_bits(c->cell_id / 30, cb, 8 * 20);
+    for (uint32_t i = 0; i < 8; i++) fgh += (uint32_t)cb[8 * ns + i] << i;
+    fgh %= 30;
+  } else if (u->seq_hopping && M >= 72) { /* v = c(ns), c_init = floor(cell_id / 30) 2^5 + f_ss^PUSCH */
+    lte_gold_bits((c->cell_id / 30) * 32 + fss, cb, 20);
+    v = cb[ns];
+  }
+  *u_out = (fgh + fss) % 30, *v_out = v;
+}
 int lte_pusch_dmrs(const lte_cell_t* c, const lte_ul_cfg_t* u, uint32_t ns, uint32_t n_dmrs2, uint32_t M, cf_t* r)
 {
-  if (M < 36 || u->group_hopping || u->seq_hopping) return -1;
-  uint32_t fss  = ((c->cell_id % 30) + u->delta_ss) % 30; /* f_ss^PUSCH; group hopping off -> u = f_ss */
-  uint32_t useq = fss;
+  if (M < 36) return -1;
+  uint32_t fss = ((c->cell_id % 30) + u->delta_ss) % 30, useq, v;
+  lte_pusch_uv(c, u, ns, M, &useq, &v);
   /* n_PRS(ns), 36.211 5.5.2.1.1 */
   uint8_t  cbits[8 * 7 * 20 + 8];
   lte_gold_bits((c->cell_id / 30) * 32 + fss, cbits, 8 * 7 * 20 + 8);
@@ -973,7 +1013,8 @@ int lte_pusch_dmrs(const lte_cell_t* c, const lte_ul_cfg_t* u, uint32_t ns, uint
   uint32_t ncs = (u->n_dmrs1 + n_dmrs2 + nprs) % 12;
   uint32_t Nzc = lte_largest_prime_below(M);
   double   qb  = (double)Nzc * (useq + 1) / 31.0;
-  uint32_t q   = (uint32_t)floor(qb + 0.5); /* v = 0 */
+  uint32_t q   = (uint32_t)floor(qb + 0.5);
+  if (v) q = ((uint32_t)floor(2.0 * qb) & 1u) ? q - 1 : q + 1; /* q = floor(qb + 1/2) + v (-1)^floor(2 qb) */
   for (uint32_t n = 0; n < M; n++) {
     uint64_t m  = n % Nzc;
     uint64_t t  = ((uint64_t)q * m * (m + 1)) % (2ull * Nzc);   /* phase = -pi t / Nzc */
@@ -983,4 +1024,62 @@ int lte_pusch_dmrs(const lte_cell_t* c, const lte_ul_cfg_t* u, uint32_t ns, uint
     r[n].im     = (float)sin(ph);
   }
   return 0;
+}
+
+/* ---- control information on PUSCH (36.212 5.2.2.6 - 5.2.2.8) ---- */
+static const float BETA_ACK[16] = {2.000f, 2.500f, 3.125f, 4.000f, 5.000f, 6.250f, 8.000f, 10.000f, 12.625f, 15.875f, 20.000f, 31.000f, 50.000f, 80.000f, 126.000f, -1.0f};
+static const float BETA_RI[16]  = {1.250f, 1.625f, 2.000f, 2.500f, 3.125f, 4.000f, 5.000f, 6.250f, 8.000f, 10.000f, 12.625f, 15.875f, 20.000f, -1.0f, -1.0f, -1.0f};
+static const float BETA_CQI[16] = {-1.0f, -1.0f, 1.125f, 1.250f, 1.375f, 1.625f, 1.750f, 2.000f, 2.250f, 2.500f, 2.875f, 3.125f, 3.500f, 4.000f, 5.000f, 6.250f};
+void lte_uci_layout(const lte_ul_grant_t* g, lte_uci_layout_t* L)
+{
+  const uint32_t M = 12 * g->L_prb, nsymb = 12;
+  lte_cbsegm_t   sg;
+  uint32_t       K = 0;
+  memset(L, 0, sizeof(*L));
+  if (g->tbs > 0 && lte_cbsegm(&sg, (uint32_t)g->tbs) == 0)
+    for (uint32_t r = 0; r < sg.C; r++) K += lte_cb_K(&sg, r);
+  if (K) {
+    /* Q' = min(ceil(O M_sc N_symb beta / sum K_r), 4 M_sc), evaluated in float like srsRAN's Q_prime_ri_ack */
+    if (g->ri_len) {
+      float    b = BETA_RI[g->I_offset_ri & 15];
+      uint32_t x = (uint32_t)ceilf((float)g->ri_len * (float)M * (float)nsymb * b / (float)K);
+      L->Qp_ri   = x < 4 * M ? x : 4 * M;
+    }
+    if (g->nof_ack) {
+      float    b = BETA_ACK[g->I_offset_ack & 15];
+      uint32_t x = (uint32_t)ceilf((float)g->nof_ack * (float)M * (float)nsymb * b / (float)K);
+      L->Qp_ack  = x < 4 * M ? x : 4 * M;
+    }
+    if (g->cqi_len) { /* CRC-8 is attached from 12 bits on */
+      float    b   = BETA_CQI[g->I_offset_cqi & 15];
+      uint32_t Lc  = g->cqi_len <= 11 ? 0 : 8;
+      uint32_t x   = (uint32_t)ceilf((float)(g->cqi_len + Lc) * (float)M * (float)nsymb * b / (float)K);
+      uint32_t lim = M * nsymb - L->Qp_ri;
+      L->Qp_cqi    = x < lim ? x : lim;
+    }
+  }
+  L->G = (M * nsymb - L->Qp_cqi - L->Qp_ri) * g->qm;
+}
+void lte_uci_map(uint32_t M, const lte_uci_layout_t* L, uint8_t* kind, uint32_t* dpos)
+{
+  static const uint32_t RI_COL[4] = {1, 4, 7, 10}, ACK_COL[4] = {2, 3, 8, 9}; /* normal CP, 36.212 Tables 5.2.2.8-1 / -2 */
+  memset(kind, 0, 12 * M);
+  for (uint32_t i = 0, j = 0; i < L->Qp_ri; i++, j = (j + 3) % 4) kind[(M - 1 - i / 4) * 12 + RI_COL[j]] = 2;
+  uint32_t k = 0;
+  for (uint32_t p = 0; p < 12 * M; p++) {
+    if (kind[p] == 2) {
+      dpos[p] = 0;
+      continue;
+    }
+    if (k < L->Qp_cqi)
+      kind[p] = 1, dpos[p] = k;
+    else
+      dpos[p] = k - L->Qp_cqi;
+    k++;
+  }
+  for (uint32_t i = 0, j = 0; i < L->Qp_ack; i++, j = (j + 3) % 4) {
+    uint32_t p = (M - 1 - i / 4) * 12 + ACK_COL[j];
+    if (kind[p] == 0) kind[p] = 3; /* the data symbol is overwritten (an ACK over a CQI symbol cannot happen: Q'_cqi rows come first) */
+    else if (kind[p] == 1) kind[p] = 4;
+  }
 }

@@ -217,27 +217,48 @@ extern "C" {
 typedef struct {
   uint32_t n_dmrs1;       /* cyclicShift (SIB2 -> ULSchedule::set_config, src/src/ULSchedule.cc:140-158) */
   uint32_t delta_ss;      /* groupAssignmentPUSCH */
-  uint32_t group_hopping; /* must be 0 (disabled) in this round */
-  uint32_t seq_hopping;   /* must be 0 */
+  uint32_t group_hopping; /* groupHoppingEnabled: u = (f_gh(ns) + f_ss) mod 30, 36.211 5.5.1.3 */
+  uint32_t seq_hopping;   /* sequenceHoppingEnabled: v = c(ns) for M_sc >= 72 when group hopping is off, 36.211 5.5.1.4 */
+  uint32_t n_rb_ho;       /* pusch-HoppingOffset (SubframeWorker.cc:271, DCICollection.cc:168) */
 } lte_ul_cfg_t;
 
 typedef struct {
   uint16_t rnti;
-  uint32_t L_prb, n_prb; /* contiguous allocation, no hopping */
+  uint32_t L_prb, n_prb; /* contiguous allocation; n_prb = first PRB of slot 0 */
   uint32_t mcs, qm, rv;
   int32_t  tbs;
   uint32_t n_dmrs2;      /* mapped from the 3-bit cyclic shift field of DCI format 0 */
-  uint32_t nof_re, nof_bits;
+  uint32_t nof_re, nof_bits; /* nof_bits = G: the bits of the UL-SCH codeword after the CQI / RI symbols are taken out */
+  uint32_t hop;          /* 0: both slots at n_prb; 1: type-1 hopping, slot 1 at n_prb_slot1 (ul_sniffer_pusch.c:48-80) */
+  uint32_t n_prb_slot1;
+  /* control information multiplexed with the data (36.212 5.2.2.6-8); what PUSCH_Decoder::decode sets at UL_Sniffer_PUSCH.cc:429-450 */
+  uint32_t nof_ack, ri_len, cqi_len;                  /* O_ACK (0..2), O_RI (0..2), O_CQI (bits, without CRC) */
+  uint32_t I_offset_ack, I_offset_ri, I_offset_cqi;   /* betaOffset indices (36.213 Tables 8.6.3-1..3) */
+  float    ta_us;        /* simulator only: timing offset of this UE's transmission (decoder ignores it) */
 } lte_ul_grant_t;
+
+/* where the control information sits in the R' x 12 channel-interleaver matrix */
+typedef struct {
+  uint32_t Qp_ack, Qp_ri, Qp_cqi; /* Q' (modulation symbols) */
+  uint32_t G;                     /* UL-SCH bits left: (12 M_sc - Q'_cqi - Q'_ri) Qm */
+} lte_uci_layout_t;
 
 /* L_prb must be 2^a 3^b 5^c (valid_prb_ul, src/src/UL_Sniffer_PUSCH.cc:3-10) */
 int lte_ul_valid_prb(uint32_t L_prb);
 /* restates srsran_ra_ul_dci_to_grant as used at falcon_dci.c:222; table: 0 = 16QAM cap (enable_64qam false), 1 = 64QAM.
- * returns 0 ok */
+ * ucfg may be NULL (n_rb_ho = 0).  returns 0 ok */
 int lte_ul_dci_to_grant(const lte_cell_t* c, const lte_dci_t* d, int table, lte_ul_grant_t* g);
+int lte_ul_dci_to_grant_hop(const lte_cell_t* c, const lte_ul_cfg_t* ucfg, const lte_dci_t* d, int table, lte_ul_grant_t* g);
 /* DMRS for PUSCH (36.211 5.5.2.1) for slot ns: M_sc complex values; returns 0, or -1 if M_sc < 36 (the
  * computer-generated 1- and 2-PRB base sequences are not implemented) */
 int lte_pusch_dmrs(const lte_cell_t* c, const lte_ul_cfg_t* u, uint32_t ns, uint32_t n_dmrs2, uint32_t M_sc, cf_t* r);
+/* base-sequence group u and sequence v of slot ns (36.211 5.5.1.3 / 5.5.1.4) */
+void lte_pusch_uv(const lte_cell_t* c, const lte_ul_cfg_t* u, uint32_t ns, uint32_t M_sc, uint32_t* u_out, uint32_t* v_out);
+/* Q' of ACK, RI, CQI and the remaining G (36.212 5.2.2.6; srsRAN Q_prime_ri_ack / Q_prime_cqi in phy/phch/uci.c, sch.c) */
+void lte_uci_layout(const lte_ul_grant_t* g, lte_uci_layout_t* L);
+/* kind[r * 12 + c] for the R' = 12 L_prb rows x 12 columns: 0 data, 1 CQI, 2 RI, 3 ACK (punctures data / CQI); dpos[] = index of the symbol in the
+ * UL-SCH (kind 0 / 3) or CQI (kind 1) stream.  36.212 5.2.2.7 / 5.2.2.8 */
+void lte_uci_map(uint32_t M_sc, const lte_uci_layout_t* L, uint8_t* kind, uint32_t* dpos);
 uint32_t lte_largest_prime_below(uint32_t n);
 #ifdef __cplusplus
 }

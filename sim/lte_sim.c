@@ -562,7 +562,11 @@ int lte_sim_ul_subframe(lte_sim_t* s, uint32_t tti, const lte_ul_cfg_t* ucfg, co
   static const uint32_t DATA_SYM[12] = {0, 1, 2, 4, 5, 6, 7, 8, 9, 11, 12, 13};
   for (uint32_t gi = 0; gi < n; gi++) {
     const lte_ul_grant_t* g = &grants[gi];
-    const uint32_t        M = 12 * g->L_prb, k0 = 12 * g->n_prb, G = g->nof_bits, Qm = g->qm, H = G / Qm;
+    const uint32_t        M = 12 * g->L_prb, Qm = g->qm, H = 12 * M;
+    const uint32_t        k0s[2] = {12 * g->n_prb, 12 * (g->hop ? g->n_prb_slot1 : g->n_prb)};
+    lte_uci_layout_t      L;
+    lte_uci_layout(g, &L);
+    const uint32_t G = L.G;
     if ((uint32_t)g->tbs / 8 + pl_off > payload_cap) return -1;
     uint8_t* pl = payload + pl_off;
     payload_off[gi] = pl_off;
@@ -570,16 +574,57 @@ int lte_sim_ul_subframe(lte_sim_t* s, uint32_t tti, const lte_ul_cfg_t* ucfg, co
     pl_off += (uint32_t)g->tbs / 8;
     uint8_t* e = s->ebits;
     if (lte_sim_dlsch_encode(pl, (uint32_t)g->tbs, g->rv, G, Qm, 1, e)) return -2;
-    /* channel interleaver 36.212 5.2.2.8 (no UCI): R' x 12 matrix of Qm-bit groups, row-wise in, column-wise out */
+    /* data / control multiplexing and channel interleaver, 36.212 5.2.2.7 / 5.2.2.8: R' x 12 matrix of Qm-bit groups, row-wise in,
+     * column-wise out.  Values: 0 / 1 bits, 2 = placeholder x, 3 = placeholder y (36.212 Tables 5.2.2.6-1 / -2) */
+    uint8_t*  kind = (uint8_t*)malloc(H);
+    uint32_t* dpos = (uint32_t*)malloc(sizeof(uint32_t) * H);
+    lte_uci_map(M, &L, kind, dpos);
+    uint8_t o_ack[3], o_ri[3];
+    for (int i = 0; i < 2; i++) o_ack[i] = (uint8_t)(lte_rng_u64(&rng) & 1), o_ri[i] = (uint8_t)(lte_rng_u64(&rng) & 1);
+    o_ack[2] = o_ack[0] ^ o_ack[1], o_ri[2] = o_ri[0] ^ o_ri[1];
     uint8_t* h = s->tbbits;
+    uint32_t n_ack = 0, n_ri = 0;
+    /* the i-th ACK / RI symbol is counted from the bottom row upwards in column-set order, as lte_uci_map lays them out */
+    static const uint32_t RI_COL[4] = {1, 4, 7, 10}, ACK_COL[4] = {2, 3, 8, 9};
     for (uint32_t c = 0; c < 12; c++)
-      for (uint32_t r = 0; r < M; r++) memcpy(&h[(c * M + r) * Qm], &e[(r * 12 + c) * Qm], Qm);
-    uint8_t* sc = (uint8_t*)malloc(G);
-    lte_gold_bits(((uint32_t)g->rnti << 14) + (sf_idx << 9) + cell->cell_id, sc, G);
-    for (uint32_t i = 0; i < G; i++) h[i] ^= sc[i];
+      for (uint32_t r = 0; r < M; r++) {
+        uint8_t*       dst = &h[(c * M + r) * Qm];
+        const uint32_t p = r * 12 + c, kd = kind[p];
+        if (kd == 0)
+          memcpy(dst, &e[dpos[p] * Qm], Qm);
+        else if (kd == 1)
+          for (uint32_t b = 0; b < Qm; b++) dst[b] = (uint8_t)(lte_rng_u64(&rng) & 1); /* CQI codeword bits: content is not examined by the receiver */
+        else {
+          const int       is_ri = kd == 2;
+          const uint32_t* cols = is_ri ? RI_COL : ACK_COL;
+          uint32_t        j = 0;
+          while (cols[j] != c) j++;
+          const uint32_t  t = (3 * j) % 4, i = 4 * (M - 1 - r) + t; /* index of this symbol in the coded ACK / RI sequence */
+          const uint32_t  O = is_ri ? g->ri_len : g->nof_ack;
+          const uint8_t*  o = is_ri ? o_ri : o_ack;
+          for (uint32_t b = 0; b < Qm; b++) dst[b] = 2;
+          if (O <= 1)
+            dst[0] = o[0], dst[1] = 3;
+          else
+            dst[0] = o[(2 * i) % 3], dst[1] = o[(2 * i + 1) % 3];
+          if (is_ri) n_ri++; else n_ack++;
+        }
+      }
+    if (n_ri != L.Qp_ri || n_ack != L.Qp_ack) return -4;
+    free(kind), free(dpos);
+    uint8_t* sc = (uint8_t*)malloc(H * Qm);
+    lte_gold_bits(((uint32_t)g->rnti << 14) + (sf_idx << 9) + cell->cell_id, sc, H * Qm);
+    for (uint32_t i = 0; i < H * Qm; i++) { /* 36.211 5.3.1: x -> 1, y -> the previous scrambled bit */
+      if (h[i] == 2)
+        h[i] = 1;
+      else if (h[i] == 3)
+        h[i] = i ? h[i - 1] : 0;
+      else
+        h[i] ^= sc[i];
+    }
     free(sc);
     lte_modulate(h, H, Qm, s->dsym[0]);
-    /* transform precoding + mapping */
+    /* transform precoding + mapping (slot 1 at its own PRBs under type-1 hopping); the UE's timing offset is a phase ramp over its sub-carriers */
     double* wr = (double*)malloc(sizeof(double) * M * 2);
     for (uint32_t m = 0; m < M; m++) {
       wr[2 * m]     = cos(2.0 * M_PI * m / M);
@@ -587,7 +632,8 @@ int lte_sim_ul_subframe(lte_sim_t* s, uint32_t tti, const lte_ul_cfg_t* ucfg, co
     }
     double sc_dft = 1.0 / sqrt((double)M);
     for (uint32_t c = 0; c < 12; c++) {
-      const cf_t* d = &s->dsym[0][c * M];
+      const cf_t*    d  = &s->dsym[0][c * M];
+      const uint32_t k0 = k0s[c / 6];
       for (uint32_t k = 0; k < M; k++) {
         double ar = 0, ai = 0;
         for (uint32_t i = 0; i < M; i++) {
@@ -605,9 +651,20 @@ int lte_sim_ul_subframe(lte_sim_t* s, uint32_t tti, const lte_ul_cfg_t* ucfg, co
         free(r);
         return -3;
       }
-      for (uint32_t k = 0; k < M; k++) grid[(7 * sl + 3) * nsc + k0 + k] = r[k];
+      for (uint32_t k = 0; k < M; k++) grid[(7 * sl + 3) * nsc + k0s[sl] + k] = r[k];
     }
     free(r);
+    if (g->ta_us != 0.0f)
+      for (uint32_t l = 0; l < 14; l++) {
+        const uint32_t k0 = k0s[l / 7];
+        for (uint32_t k = 0; k < M; k++) {
+          const double f  = ((double)(k0 + k) - (double)nsc / 2.0 + 0.5) * 15e3; /* Hz */
+          const double ph = -2.0 * M_PI * f * (double)g->ta_us * 1e-6;
+          cf_t*        x  = &grid[l * nsc + k0 + k];
+          const double xr = x->re * cos(ph) - x->im * sin(ph), xi = x->re * sin(ph) + x->im * cos(ph);
+          *x              = (cf_t){(float)xr, (float)xi};
+        }
+      }
   }
   /* SC-FDMA modulation with the half-subcarrier shift (36.211 5.6) */
   double scl = 1.0 / sqrt((double)N);

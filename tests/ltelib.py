@@ -407,16 +407,31 @@ def oracle_pipeline(cell, iq, tti, walk=None, max_iter=8, want_tb=True):
 
 # ------------------------------------------------------------------------------------------------ uplink
 class UlCfg(C.Structure):
-    _fields_ = [("n_dmrs1", C.c_uint32), ("delta_ss", C.c_uint32), ("group_hopping", C.c_uint32), ("seq_hopping", C.c_uint32)]
+    _fields_ = [("n_dmrs1", C.c_uint32), ("delta_ss", C.c_uint32), ("group_hopping", C.c_uint32), ("seq_hopping", C.c_uint32), ("n_rb_ho", C.c_uint32)]
 
 
 class UlGrant(C.Structure):
     _fields_ = [("rnti", C.c_uint16), ("L_prb", C.c_uint32), ("n_prb", C.c_uint32), ("mcs", C.c_uint32), ("qm", C.c_uint32), ("rv", C.c_uint32),
-                ("tbs", C.c_int32), ("n_dmrs2", C.c_uint32), ("nof_re", C.c_uint32), ("nof_bits", C.c_uint32)]
+                ("tbs", C.c_int32), ("n_dmrs2", C.c_uint32), ("nof_re", C.c_uint32), ("nof_bits", C.c_uint32),
+                ("hop", C.c_uint32), ("n_prb_slot1", C.c_uint32), ("nof_ack", C.c_uint32), ("ri_len", C.c_uint32), ("cqi_len", C.c_uint32),
+                ("I_offset_ack", C.c_uint32), ("I_offset_ri", C.c_uint32), ("I_offset_cqi", C.c_uint32), ("ta_us", C.c_float)]
+
+
+class UciLayout(C.Structure):
+    _fields_ = [("Qp_ack", C.c_uint32), ("Qp_ri", C.c_uint32), ("Qp_cqi", C.c_uint32), ("G", C.c_uint32)]
+
+
+def uci_layout(g):
+    """Q' of ACK / RI / CQI and the UL-SCH bit count G of a grant (36.212 5.2.2.6)"""
+    S = sim()
+    S.lte_uci_layout.argtypes = [C.POINTER(UlGrant), C.POINTER(UciLayout)]
+    L = UciLayout()
+    S.lte_uci_layout(C.byref(g), C.byref(L))
+    return L
 
 
 class UlChest(C.Structure):
-    _fields_ = [("noise", C.c_float), ("rsrp", C.c_float), ("snr_db", C.c_float)]
+    _fields_ = [("noise", C.c_float), ("rsrp", C.c_float), ("snr_db", C.c_float), ("ta_us", C.c_float)]
 
 
 def make_ul_grants(cell, rng, n, table=1, min_prb=3):
@@ -468,7 +483,7 @@ def oracle_ul(o, ucfg, tti, grants, iq, max_iter=8, want_llr=False):
         pl = np.zeros(16000, np.uint8)
         ok = C.c_int(0)
         ch = UlChest()
-        llr = np.zeros(g.nof_bits + 16, np.int16) if want_llr else None
+        llr = np.zeros(uci_layout(g).G + 16, np.int16) if want_llr else None
         r = O.lteo_pusch_decode(o.h, C.byref(ucfg), tti % 10, C.byref(g), ptr(sym), max_iter, ptr(pl), C.byref(ok), C.byref(ch), ptr(llr) if want_llr else None)
         res.append((r, pl, ok.value, ch, llr))
     return sym, res

@@ -138,3 +138,130 @@ def test_pusch_all_mcs_tables_roundtrip(infra):
                     assert np.array_equal(opl[:g.tbs // 8], pl[of:of + g.tbs // 8])
         assert ok == tot, (table, ok, tot)
         assert max(qms) == (4, 6, 8)[table]
+
+
+def _ul_roundtrip(cell, ucfg, seed, mutate, n_tti=3, n_gr=3, snr=34.0, min_prb=3, table=1):
+    """sim -> oracle PUSCH for grants altered by mutate(g, rng); returns [(grant, crc, chest)]"""
+    o = ltelib.Oracle(cell)
+    s = ltelib.Sim(cell=cell, seed=seed, snr_db=snr, nof_ues=1)
+    rng = np.random.default_rng(seed)
+    out = []
+    for tti in range(2, 2 + n_tti):
+        gr = ltelib.make_ul_grants(cell, rng, n_gr, table=table, min_prb=min_prb)
+        for g in gr:
+            mutate(g, rng)
+        x, pl, off = ltelib.sim_ul_subframe(s, tti, ucfg, gr)
+        sym, ref = ltelib.oracle_ul(o, ucfg, tti, gr, x)
+        for g, (r, opl, crc, ch, _), of in zip(gr, ref, off):
+            assert r == 0
+            if crc:
+                assert np.array_equal(opl[:g.tbs // 8], pl[of:of + g.tbs // 8])
+            out.append((g, crc, ch))
+    return out
+
+
+def test_pusch_uci_multiplexing_roundtrip(infra):
+    """HARQ-ACK, RI and CQI multiplexed with the data (36.212 5.2.2.6-8, what PUSCH_Decoder::decode configures at src/src/UL_Sniffer_PUSCH.cc:429-450):
+    the UL-SCH still decodes when the receiver takes the CQI / RI symbols out and erases the ACK ones -- and does NOT when it is told nothing"""
+    from ltelib import UlCfg
+    cell = Cell(50, 1, 23, 1)
+    ucfg = UlCfg(n_dmrs1=4, delta_ss=7)
+    combos = [dict(nof_ack=1, I_offset_ack=9), dict(nof_ack=2, I_offset_ack=10, ri_len=1, I_offset_ri=8), dict(cqi_len=4, I_offset_cqi=8),
+              dict(cqi_len=30, I_offset_cqi=6, ri_len=1, I_offset_ri=5, nof_ack=2, I_offset_ack=5)]
+    for ci, cmb in enumerate(combos):
+        def mut(g, rng):
+            for k, v in cmb.items():
+                setattr(g, k, v)
+        res = _ul_roundtrip(cell, ucfg, 40 + ci, mut)
+        assert all(crc for _, crc, _ in res), (cmb, [crc for _, crc, _ in res])
+        for g, _, _ in res:
+            L = ltelib.uci_layout(g)
+            assert L.G == (144 * g.L_prb - L.Qp_cqi - L.Qp_ri) * g.qm
+            assert (L.Qp_ack > 0) == (g.nof_ack > 0) and (L.Qp_ri > 0) == (g.ri_len > 0) and (L.Qp_cqi > 0) == (g.cqi_len > 0)
+    # a receiver that ignores the CQI (wrong G, shifted codeword) must fail: the multiplexing really moves the data
+    o = ltelib.Oracle(cell)
+    s = ltelib.Sim(cell=cell, seed=77, snr_db=34.0, nof_ues=1)
+    rng = np.random.default_rng(77)
+    gr = ltelib.make_ul_grants(cell, rng, 2)
+    for g in gr:
+        g.cqi_len, g.I_offset_cqi = 30, 8
+    x, pl, off = ltelib.sim_ul_subframe(s, 3, ucfg, gr)
+    for g in gr:
+        g.cqi_len = 0
+    _, ref = ltelib.oracle_ul(o, ucfg, 3, gr, x)
+    assert not any(crc for _, _, crc, _, _ in ref)
+
+
+def test_pusch_group_and_sequence_hopping_roundtrip(infra):
+    """DMRS base-sequence group hopping and sequence hopping (36.211 5.5.1.3 / 5.5.1.4; dmrs_cfg.group_hopping_en / sequence_hopping_en from SIB2,
+    src/src/ULSchedule.cc:143-146): transmitter and receiver agree on u, v per slot; a receiver with the wrong setting loses the channel estimate"""
+    from ltelib import UlCfg
+    cell = Cell(50, 1, 301, 1)
+    for gh, sh in ((1, 0), (0, 1), (1, 1)):
+        ucfg = UlCfg(n_dmrs1=2, delta_ss=11, group_hopping=gh, seq_hopping=sh)
+        res = _ul_roundtrip(cell, ucfg, 50 + 2 * gh + sh, lambda g, rng: None, min_prb=6)
+        assert all(crc for _, crc, _ in res) and len(res) >= 6
+    S = ltelib.sim()
+    S.lte_pusch_uv.argtypes = [C.POINTER(Cell), C.POINTER(UlCfg), C.c_uint32, C.c_uint32, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
+    u, v = C.c_uint32(), C.c_uint32()
+    us, vs = set(), set()
+    for ns in range(20):
+        S.lte_pusch_uv(C.byref(cell), C.byref(UlCfg(delta_ss=11, group_hopping=1)), ns, 72, C.byref(u), C.byref(v))
+        us.add(u.value)
+        assert v.value == 0
+        S.lte_pusch_uv(C.byref(cell), C.byref(UlCfg(delta_ss=11, seq_hopping=1)), ns, 72, C.byref(u), C.byref(v))
+        vs.add(v.value)
+        assert u.value == (301 % 30 + 11) % 30
+        S.lte_pusch_uv(C.byref(cell), C.byref(UlCfg(delta_ss=11, seq_hopping=1)), ns, 60, C.byref(u), C.byref(v))
+        assert v.value == 0            # below 6 PRB there is one base sequence per group
+    assert len(us) > 5 and vs == {0, 1}
+    # mismatch: hopping transmitter, static receiver
+    o = ltelib.Oracle(cell)
+    s = ltelib.Sim(cell=cell, seed=9, snr_db=34.0, nof_ues=1)
+    gr = ltelib.make_ul_grants(cell, np.random.default_rng(9), 2, min_prb=6)
+    x, pl, off = ltelib.sim_ul_subframe(s, 3, UlCfg(n_dmrs1=2, delta_ss=11, group_hopping=1), gr)
+    _, ref = ltelib.oracle_ul(o, UlCfg(n_dmrs1=2, delta_ss=11), 3, gr, x)
+    assert not all(crc for _, _, crc, _, _ in ref)
+
+
+def test_pusch_type1_hopping_and_timing_offset(infra):
+    """type-1 PUSCH hopping (slot 1 on other PRBs, 36.213 8.4.1 as restated by ul_sniffer_ra_ul_grant_to_grant_prb_allocation,
+    lib/src/phy/falcon_phch/ul_sniffer_pusch.c:48-80) and the timing-offset estimate from the DMRS phase slope (chest_res.ta_us, UL_Sniffer_PUSCH.cc:424,574)"""
+    from ltelib import UlCfg
+    cell = Cell(50, 1, 5, 1)
+    ucfg = UlCfg(n_dmrs1=1, delta_ss=0, n_rb_ho=4)
+    o = ltelib.Oracle(cell)
+    s = ltelib.Sim(cell=cell, seed=12, snr_db=32.0, nof_ues=1)
+    S = ltelib.sim()
+    S.lte_ul_dci_to_grant_hop.argtypes = [C.POINTER(Cell), C.POINTER(UlCfg), C.POINTER(ltelib.Dci), C.c_int, C.POINTER(ltelib.UlGrant)]
+    N, rivb = 50, 11
+    seen = set()
+    for hb, (L, S0) in zip((0, 1, 2, 0, 2), ((6, 4), (5, 30), (8, 10), (10, 20), (4, 2))):
+        d = ltelib.Dci()
+        d.format, d.rnti, d.alloc_type, d.hop = 0, 0x4000 + hb, 2, 1
+        riv = N * (L - 1) + S0
+        assert riv < (1 << (rivb - 2))
+        d.riv = (hb << (rivb - 2)) | riv
+        d.mcs[0], d.n_dmrs = 12, 3
+        g = ltelib.UlGrant()
+        assert S.lte_ul_dci_to_grant_hop(C.byref(cell), C.byref(ucfg), C.byref(d), 1, C.byref(g)) == 0
+        nrb = N - 4
+        want = {0: (nrb // 4 + S0) % nrb, 1: (nrb + S0 - nrb // 4) if S0 < nrb // 4 else S0 - nrb // 4, 2: (nrb // 2 + S0) % nrb}[hb]
+        assert (g.hop, g.n_prb, g.n_prb_slot1, g.L_prb) == (1, S0, want, L)
+        seen.add(hb)
+        g.ta_us = 0.4 + 0.3 * hb
+        x, pl, off = ltelib.sim_ul_subframe(s, 6, ucfg, [g])
+        _, ref = ltelib.oracle_ul(o, ucfg, 6, [g], x)
+        r, opl, crc, ch, _ = ref[0]
+        assert r == 0 and crc and np.array_equal(opl[:g.tbs // 8], pl[:g.tbs // 8])
+        assert abs(ch.ta_us - g.ta_us) < 0.05, (ch.ta_us, g.ta_us)
+    assert seen == {0, 1, 2}
+    # no offset -> estimate near zero; negative offset (early UE) keeps its sign
+    for ta in (0.0, -0.7):
+        gr = ltelib.make_ul_grants(cell, np.random.default_rng(4), 2)
+        for g in gr:
+            g.ta_us = ta
+        x, pl, off = ltelib.sim_ul_subframe(s, 7, ucfg, gr)
+        _, ref = ltelib.oracle_ul(o, ucfg, 7, gr, x)
+        for r, opl, crc, ch, _ in ref:
+            assert crc and abs(ch.ta_us - ta) < 0.05
