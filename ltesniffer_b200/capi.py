@@ -502,11 +502,29 @@ def search_batch_packed(search, bufs, offs, n, max_dcis, full=None):
     return dcis[:nd.value].copy(), tc
 
 
+def _prefer_torch_nccl():
+    """libltephy_b200 binds NCCL with dlopen("libnccl.so.2").  In a Python process that will also import torch, torch's bundled NCCL has to be the
+    copy the process holds (an older system libnccl loaded first makes `import torch` fail on missing symbols), so point LTEPHY_NCCL_LIB at it."""
+    if os.environ.get("LTEPHY_NCCL_LIB"):
+        return
+    try:
+        import importlib.util
+        spec = importlib.util.find_spec("nvidia.nccl")
+        for base in (list(spec.submodule_search_locations) if spec and spec.submodule_search_locations else []):
+            cand = os.path.join(base, "lib", "libnccl.so.2")
+            if os.path.exists(cand):
+                os.environ["LTEPHY_NCCL_LIB"] = cand
+                return
+    except Exception:
+        pass
+
+
 class Shard:
     """NCCL communicators + ordered sections of the sharded pipeline (one per process / GPU)."""
 
     @staticmethod
     def unique_id():
+        _prefer_torch_nccl()
         L = load_library()
         _bind_search(L)
         buf = (C.c_uint8 * SHARD_ID_BYTES)()
@@ -515,6 +533,7 @@ class Shard:
         return bytes(buf)
 
     def __init__(self, uid, rank, world, device):
+        _prefer_torch_nccl()
         self.L = load_library()
         _bind_search(self.L)
         self.h = C.c_void_p()

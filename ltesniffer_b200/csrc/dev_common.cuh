@@ -21,6 +21,7 @@ struct DevCell {
   uint16_t pcfich_idx[16];
   uint32_t pdcch_scr_words;       // words per subframe index
   const float2*   tw;             // [fft/2]
+  const float2*   tw_st;          // [fft] per-stage tables: tw_st[H + pos] = tw[pos * fft / (2 H)], H = 1, 2, .. fft/2, pos < H
   const float2*   ul_rot;         // [fft] exp(-j pi i / N)
   const float2*   crs;            // [10][2][4][2*nof_prb]
   const uint16_t* pdcch_idx[3];   // [nof_cce*9][4]

@@ -7,40 +7,51 @@
 #include "dev_eq.cuh"
 
 // =================================================================================================
-// K1: batched OFDM receive.  One CTA per (symbol, antenna, subframe): the fft-sample window after the
-// cyclic prefix is staged into shared memory with one TMA bulk copy (cp.async.bulk -> UBLKCP),
-// bit-reversed, then log2(fft) radix-2 DIT stages are executed three at a time from registers.
-// HBM traffic per antenna-subframe: 30720 cf32 read once (coalesced 16 KB bursts), 16800 cf32 written.
+// K1: batched OFDM receive.  One CTA per (symbol, antenna, subframe), fft/8 threads.  The transform is the oracle's radix-2 decimation-in-time
+// FFT (bit-reversed input, stages 1..log2 n, same twiddle table, same operation order -> bit-identical output) with three stages fused per
+// pass in registers:
+//  * pass 1 (stages 1-3) reads its 8 inputs x[t + m n/8] straight from global memory (thread t owns the group whose index is the bit reversal
+//    of t, so the bit-reversal permutation costs nothing and every load instruction is one coalesced 256-byte row per warp);
+//  * later passes exchange through ONE shared-memory array in the layout i ^ ((i >> 6) & 31): the lanes of a warp differ either in index bits
+//    10..6 (pass 1 write, pass 2) or in bits 4..0 (later passes, final read), so every access is bank-conflict free;
+//  * twiddles come from per-stage contiguous tables (tw_st[H + pos] = W_{2H}^pos) through the read-only path: coalesced, no staging.
+// HBM traffic per antenna-subframe: 30720 cf32 read once, 16800 cf32 written.
 // =================================================================================================
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-template <int G> // G = number of radix-2 stages fused in this pass (1..3)
-__device__ __forceinline__ void fft_pass(float2* work, const float2* __restrict__ tw, uint32_t n, uint32_t s0, uint32_t tid, uint32_t nthreads)
+__device__ __forceinline__ uint32_t fft_swz(uint32_t i) { return i ^ ((i >> 6) & 31u); }
+__device__ __forceinline__ void     fft_bfly(float2& a, float2& b, const float2 w)
 {
-  constexpr uint32_t GS = 1u << G;      // elements per group
-  const uint32_t     h0 = 1u << (s0 - 1); // half size of the first stage of the pass
-  for (uint32_t gid = tid; gid < n / GS; gid += nthreads) {
-    const uint32_t base = (gid / h0) * (h0 * GS) + (gid % h0);
+  const float  tr = w.x * b.x - w.y * b.y;
+  const float  ti = w.x * b.y + w.y * b.x;
+  const float2 x  = a;
+  a               = make_float2(x.x + tr, x.y + ti);
+  b               = make_float2(x.x - tr, x.y - ti);
+}
+
+template <int G> // G = number of radix-2 stages fused in this pass (1..3), first stage s0 (half block h0 = 2^(s0-1))
+__device__ __forceinline__ void fft_pass(float2* work, const float2* __restrict__ tw_st, uint32_t n, uint32_t s0, uint32_t tid, uint32_t nthreads)
+{
+  constexpr uint32_t GS = 1u << G;        // elements per group
+  const uint32_t     h0 = 1u << (s0 - 1), ngroups = n / GS, hi = ngroups / h0;
+  for (uint32_t w = tid; w < ngroups; w += nthreads) {
+    // small h0: the lanes of a warp take the high index bits (conflict-free with the swizzle), otherwise the low ones
+    const uint32_t gid  = h0 < 32 ? (w % hi) * h0 + w / hi : w;
+    const uint32_t lo   = gid % h0, base = (gid / h0) * (h0 * GS) + lo;
     float2         v[GS];
 #pragma unroll
-    for (uint32_t j = 0; j < GS; j++) v[j] = work[base + j * h0];
+    for (uint32_t j = 0; j < GS; j++) v[j] = work[fft_swz(base + j * h0)];
 #pragma unroll
     for (uint32_t ss = 0; ss < (uint32_t)G; ss++) {
-      const uint32_t half = h0 << ss, step = n / (2 * half);
+      const uint32_t half = h0 << ss;
 #pragma unroll
-      for (uint32_t j = 0; j < GS; j++) {
-        if (j & (1u << ss)) continue;
-        const uint32_t pos = (gid % h0) + (j & ((1u << ss) - 1)) * h0; // index inside the half block
-        const float2   w   = tw[pos * step];
-        const float2   a = v[j], b = v[j + (1u << ss)];
-        const float    tr = w.x * b.x - w.y * b.y;
-        const float    ti = w.x * b.y + w.y * b.x;
-        v[j]              = make_float2(a.x + tr, a.y + ti);
-        v[j + (1u << ss)] = make_float2(a.x - tr, a.y - ti);
+      for (uint32_t q = 0; q < (1u << ss); q++) { // one twiddle W_{2 half}^{lo + q h0} per q, shared by the butterflies that differ in the bits above ss
+        const float2 wv = __ldg(&tw_st[half + lo + q * h0]);
+#pragma unroll
+        for (uint32_t j = 0; j < GS; j++)
+          if (!(j & (1u << ss)) && (j & ((1u << ss) - 1)) == q) fft_bfly(v[j], v[j + (1u << ss)], wv);
       }
     }
 #pragma unroll
-    for (uint32_t j = 0; j < GS; j++) work[base + j * h0] = v[j];
+    for (uint32_t j = 0; j < GS; j++) work[fft_swz(base + j * h0)] = v[j];
   }
 }
 
@@ -48,73 +59,59 @@ template <bool UL>
 __global__ void __launch_bounds__(256) ofdm_rx_kernel(const __grid_constant__ DevCell c, const float2* __restrict__ iq, float2* __restrict__ sym)
 {
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  float2*   stage = reinterpret_cast<float2*>(smem_raw);            // [fft]
-  float2*   work  = stage + c.fft;                                   // [fft]
-  float2*   tw    = work + c.fft;                                    // [fft/2]
-  __shared__ __align__(8) unsigned long long mbar;
-
-  const uint32_t l = blockIdx.x, a = blockIdx.y, sf = blockIdx.z, tid = threadIdx.x, nt = blockDim.x, n = c.fft;
+  float2*        work = reinterpret_cast<float2*>(smem_raw); // [fft], swizzled
+  const uint32_t l = blockIdx.x, a = blockIdx.y, sf = blockIdx.z, tid = threadIdx.x, nt = blockDim.x, n = c.fft, L = c.log2n;
   const uint32_t nant = UL ? 1u : c.nof_rx; // the UL carrier is decoded from one antenna (UL_Sniffer_PUSCH.cc:391-392)
   const float2*  src = iq + ((size_t)sf * nant + a) * c.sf_len + c.sym_off[l];
-  const bool     bulk_ok = ((reinterpret_cast<uintptr_t>(src) & 15u) == 0) && ((n * 8u) % 16u == 0);
+  const float2*  tw_st = c.tw_st;
 
-  if (bulk_ok) {
-    if (tid == 0) {
-      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&mbar)));
-      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  // ---- pass 1: stages 1..3 of group g = bitrev(t): A[8 g + j] = x[bitrev3(j) n/8 + t]
+  {
+    const uint32_t q8 = n >> 3;
+    const float2   w1 = __ldg(&tw_st[1]), w20 = __ldg(&tw_st[2]), w21 = __ldg(&tw_st[3]);
+    const float2   w40 = __ldg(&tw_st[4]), w41 = __ldg(&tw_st[5]), w42 = __ldg(&tw_st[6]), w43 = __ldg(&tw_st[7]);
+    for (uint32_t t = tid; t < q8; t += nt) {
+      const uint32_t g = __brev(t) >> (32 - (L - 3));
+      float2         v[8];
+#pragma unroll
+      for (uint32_t j = 0; j < 8; j++) {
+        const uint32_t m = ((j & 1u) << 2) | (j & 2u) | (j >> 2), idx = t + m * q8;
+        float2         x = src[idx];
+        if (UL) { // remove the 7.5 kHz half-subcarrier shift: multiply by exp(-j pi i / N) (srsran_enb_ul_fft)
+          const float2 r = __ldg(&c.ul_rot[idx]);
+          x              = make_float2(x.x * r.x - x.y * r.y, x.x * r.y + x.y * r.x);
+        }
+        v[j] = x;
+      }
+      fft_bfly(v[0], v[1], w1), fft_bfly(v[2], v[3], w1), fft_bfly(v[4], v[5], w1), fft_bfly(v[6], v[7], w1);
+      fft_bfly(v[0], v[2], w20), fft_bfly(v[1], v[3], w21), fft_bfly(v[4], v[6], w20), fft_bfly(v[5], v[7], w21);
+      fft_bfly(v[0], v[4], w40), fft_bfly(v[1], v[5], w41), fft_bfly(v[2], v[6], w42), fft_bfly(v[3], v[7], w43);
+#pragma unroll
+      for (uint32_t j = 0; j < 8; j++) work[fft_swz(8 * g + j)] = v[j];
     }
-    __syncthreads();
-    if (tid == 0) {
-      const uint32_t bytes = n * 8u;
-      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&mbar)), "r"(bytes) : "memory");
-      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(stage)),
-                   "l"(src), "r"(bytes), "r"(smem_u32(&mbar))
-                   : "memory");
-    }
-  }
-  for (uint32_t i = tid; i < n / 2; i += nt) tw[i] = c.tw[i]; // overlaps with the bulk copy
-  if (bulk_ok) {
-    uint32_t done = 0;
-    while (!done) {
-      asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                   : "=r"(done)
-                   : "r"(smem_u32(&mbar)), "r"(0u)
-                   : "memory");
-    }
-  } else {
-    for (uint32_t i = tid; i < n; i += nt) stage[i] = src[i];
-  }
-  __syncthreads();
-  if (UL) { // remove the 7.5 kHz half-subcarrier shift: multiply by exp(-j pi i / N) (srsran_enb_ul_fft)
-    for (uint32_t i = tid; i < n; i += nt) {
-      const float2 v = stage[i], r = c.ul_rot[i];
-      work[__brev(i) >> (32 - c.log2n)] = make_float2(v.x * r.x - v.y * r.y, v.x * r.y + v.y * r.x);
-    }
-  } else {
-    for (uint32_t i = tid; i < n; i += nt) work[__brev(i) >> (32 - c.log2n)] = stage[i];
   }
   __syncthreads();
-  uint32_t s = 1;
-  while (s + 2 <= c.log2n) {
-    fft_pass<3>(work, tw, n, s, tid, nt);
+  uint32_t s = 4;
+  while (s + 2 <= L) {
+    fft_pass<3>(work, tw_st, n, s, tid, nt);
     __syncthreads();
     s += 3;
   }
-  if (s + 1 <= c.log2n) {
-    fft_pass<2>(work, tw, n, s, tid, nt);
+  if (s + 1 <= L) {
+    fft_pass<2>(work, tw_st, n, s, tid, nt);
     __syncthreads();
     s += 2;
   }
-  if (s <= c.log2n) {
-    fft_pass<1>(work, tw, n, s, tid, nt);
+  if (s <= L) {
+    fft_pass<1>(work, tw_st, n, s, tid, nt);
     __syncthreads();
   }
   float2*        dst = sym + (((size_t)sf * nant + a) * 14 + l) * c.nsc;
   const uint32_t h   = c.nsc / 2;
   if (UL) {
-    for (uint32_t k = tid; k < c.nsc; k += nt) dst[k] = work[(k + n - h) % n]; // no DC gap on the uplink
+    for (uint32_t k = tid; k < c.nsc; k += nt) dst[k] = work[fft_swz((k + n - h) % n)]; // no DC gap on the uplink
   } else {
-    for (uint32_t k = tid; k < c.nsc; k += nt) dst[k] = work[k < h ? n - h + k : k - h + 1];
+    for (uint32_t k = tid; k < c.nsc; k += nt) dst[k] = work[fft_swz(k < h ? n - h + k : k - h + 1)];
   }
 }
 
@@ -330,7 +327,7 @@ extern "C" void launch_frontend(const DevCell& c, const float2* iq, float2* sym,
                                 cudaStream_t st, uint64_t* launches)
 {
   const uint32_t fft_threads = c.fft / 8 < 32 ? 32 : c.fft / 8;
-  const size_t   smem_fft    = (size_t)c.fft * 8 * 2 + (size_t)c.fft * 4;
+  const size_t   smem_fft    = (size_t)c.fft * sizeof(float2);
   ofdm_rx_kernel<false><<<dim3(14, c.nof_rx, n), fft_threads, smem_fft, st>>>(c, iq, sym);
   const size_t smem_ch = (size_t)2 * NPILSYM * 2 * c.nof_prb * sizeof(float2);
   chest_kernel<<<dim3(c.nof_ports * c.nof_rx, n), 256, smem_ch, st>>>(c, sym, ce, info);
@@ -342,7 +339,7 @@ extern "C" void launch_frontend(const DevCell& c, const float2* iq, float2* sym,
 extern "C" void launch_ul_ofdm(const DevCell& c, const float2* iq, float2* sym, uint32_t n, cudaStream_t st, uint64_t* launches)
 {
   const uint32_t fft_threads = c.fft / 8 < 32 ? 32 : c.fft / 8;
-  const size_t   smem_fft    = (size_t)c.fft * 8 * 2 + (size_t)c.fft * 4;
+  const size_t   smem_fft    = (size_t)c.fft * sizeof(float2);
   ofdm_rx_kernel<true><<<dim3(14, 1, n), fft_threads, smem_fft, st>>>(c, iq, sym);
   *launches += 1;
 }

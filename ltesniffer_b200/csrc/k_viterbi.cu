@@ -28,10 +28,14 @@
 #define VIT_SPREAD 9180      // 6 * 2 * 765
 
 struct __align__(16) VitWarpSmem {
-  float    rm[2][3 * VIT_KMAX]; // dematched soft bits, stream-major
-  uint32_t R[3][VIT_KMAX];      // quantised symbols 2q-255, packed (cand0 lo, cand1 hi)
-  uint32_t S[VIT_KMAX][8];      // branch metrics + 765 for the 8 output sign patterns (o0 o1 o2), packed; S[k][p ^ 7] = 1530 - S[k][p]
-  uint4    dec[2 * VIT_KMAX];   // survivor decisions of steps K..3K-1: {c0 u=0, c0 u=1, c1 u=0, c1 u=1}, bit = lane of the step's layout
+  union {
+    struct {
+      float    rm[2][3 * VIT_KMAX]; // dematched soft bits, stream-major (prologue only)
+      uint32_t R[3][VIT_KMAX];      // quantised symbols 2q-255, packed (cand0 lo, cand1 hi) (prologue only)
+    } p;
+    uint4 dec[2 * VIT_KMAX];        // survivor decisions of steps K..3K-1: {c0 u=0, c0 u=1, c1 u=0, c1 u=1}, bit = lane of the step's layout
+  };
+  uint32_t S[VIT_KMAX][8];          // branch metrics + 765 for the 8 output sign patterns (o0 o1 o2), packed; S[k][p ^ 7] = 1530 - S[k][p]
 };
 
 struct VitConst {
@@ -43,14 +47,64 @@ __device__ __forceinline__ int      lo16(uint32_t v) { return (int)(short)(v & 0
 __device__ __forceinline__ int      hi16(uint32_t v) { return (int)(short)(v >> 16); }
 
 // x^(e + 16) mod (x^16 + x^12 + x^5 + 1), e = 0..63: the CRC16 of a message is the XOR of these over its set bits
-__device__ __forceinline__ uint32_t crc16_xpow(uint32_t e)
+__device__ const uint16_t vit_xpow[64] = {
+    0x1021, 0x2042, 0x4084, 0x8108, 0x1231, 0x2462, 0x48C4, 0x9188, 0x3331, 0x6662, 0xCCC4, 0x89A9, 0x0373, 0x06E6, 0x0DCC, 0x1B98,
+    0x3730, 0x6E60, 0xDCC0, 0xA9A1, 0x4363, 0x86C6, 0x1DAD, 0x3B5A, 0x76B4, 0xED68, 0xCAF1, 0x85C3, 0x1BA7, 0x374E, 0x6E9C, 0xDD38,
+    0xAA51, 0x4483, 0x8906, 0x022D, 0x045A, 0x08B4, 0x1168, 0x22D0, 0x45A0, 0x8B40, 0x06A1, 0x0D42, 0x1A84, 0x3508, 0x6A10, 0xD420,
+    0xB861, 0x60E3, 0xC1C6, 0x93AD, 0x377B, 0x6EF6, 0xDDEC, 0xABF9, 0x47D3, 0x8FA6, 0x0F6D, 0x1EDA, 0x3DB4, 0x7B68, 0xF6D0, 0xFD81};
+
+// Traceback of one candidate in the rotated coordinates of each step: (y, u) = (lane, register) of the state.  Going back one step, the bit of
+// y at position pos (the one that held state bit 1) becomes the new u and is replaced by the survivor decision; pos advances by one (mod 5)
+// per step, so with the start position as a template parameter every step of a group of five has a compile-time position.
+// Steps idx = 2K-1 .. K (third copy) only give traceback depth; idx = K-1 .. 0 (second copy) are the data bits: bit i at position
+// 31 - (i & 31) of word i >> 5, collected by a funnel shift and flushed when a word is complete.
+template <int P0> __device__ __forceinline__ void vit_traceback(const uint32_t* __restrict__ dw, int K, uint32_t y, uint32_t u, uint32_t& w0, uint32_t& w1,
+                                                                uint32_t& w2)
 {
-  uint32_t r = 0x1021u; // x^16 mod P
-  for (uint32_t i = 0; i < e; i++) {
-    r <<= 1;
-    if (r & 0x10000u) r ^= 0x11021u;
+  int      idx = 2 * K - 1;
+  uint32_t cur = 0;
+#define TB_BACK(POS)                                                                                                           \
+  {                                                                                                                            \
+    const uint32_t d = (dw[idx * 4 + (int)u] >> y) & 1u;                                                                       \
+    u                = (y >> (POS)) & 1u;                                                                                      \
+    y                = (y & ~(1u << (POS))) | (d << (POS));                                                                    \
+    idx--;                                                                                                                     \
   }
-  return r;
+#define TB_REC()                                                                                                               \
+  {                                                                                                                            \
+    cur = __funnelshift_r(cur, u, 1);                                                                                          \
+  }
+#define TB_SLOW(POS)                                                                                                           \
+  {                                                                                                                            \
+    if (idx < K) {                                                                                                             \
+      TB_REC()                                                                                                                 \
+      if ((idx & 31) == 0) {                                                                                                   \
+        if (idx == 64)                                                                                                         \
+          w2 = cur;                                                                                                            \
+        else if (idx == 32)                                                                                                    \
+          w1 = cur;                                                                                                            \
+        else                                                                                                                   \
+          w0 = cur;                                                                                                            \
+      }                                                                                                                        \
+    }                                                                                                                          \
+    TB_BACK(POS)                                                                                                               \
+  }
+  while (idx >= 4) {
+    if (idx - 4 >= K) {
+      TB_BACK((P0) % 5) TB_BACK((P0 + 1) % 5) TB_BACK((P0 + 2) % 5) TB_BACK((P0 + 3) % 5) TB_BACK((P0 + 4) % 5)
+    } else if (idx < K && ((idx ^ (idx - 4)) & ~31) == 0 && ((idx - 4) & 31) != 0) { // five bits of one word, none of them its last
+      TB_REC() TB_BACK((P0) % 5) TB_REC() TB_BACK((P0 + 1) % 5) TB_REC() TB_BACK((P0 + 2) % 5) TB_REC() TB_BACK((P0 + 3) % 5) TB_REC() TB_BACK((P0 + 4) % 5)
+    } else {
+      TB_SLOW((P0) % 5) TB_SLOW((P0 + 1) % 5) TB_SLOW((P0 + 2) % 5) TB_SLOW((P0 + 3) % 5) TB_SLOW((P0 + 4) % 5)
+    }
+  }
+  if (idx >= 0) TB_SLOW((P0) % 5)
+  if (idx >= 0) TB_SLOW((P0 + 1) % 5)
+  if (idx >= 0) TB_SLOW((P0 + 2) % 5)
+  if (idx >= 0) TB_SLOW((P0 + 3) % 5)
+#undef TB_BACK
+#undef TB_REC
+#undef TB_SLOW
 }
 
 __global__ void __launch_bounds__(VIT_WARPS * 32) dci_viterbi_kernel(const __grid_constant__ DevCell c, const float* __restrict__ llr_all,
@@ -58,7 +112,6 @@ __global__ void __launch_bounds__(VIT_WARPS * 32) dci_viterbi_kernel(const __gri
                                                                       const VitConst vc)
 {
   __shared__ VitWarpSmem sm_all[VIT_WARPS];
-  __shared__ uint32_t    xpow_s[64];
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t pair = blockIdx.x * VIT_WARPS + warp, si = blockIdx.y, sf = blockIdx.z;
   VitWarpSmem&   sm   = sm_all[warp];
@@ -66,51 +119,53 @@ __global__ void __launch_bounds__(VIT_WARPS * 32) dci_viterbi_kernel(const __gri
   const uint32_t cfi = info[sf].cfi;
   if (cfi < 1 || cfi > 3) return;
   const uint32_t nloc = c.nloc[cfi - 1];
-  if (threadIdx.x < 64) xpow_s[threadIdx.x] = crc16_xpow(threadIdx.x);
-  __syncthreads();
   if (2 * pair >= nloc) return;
   const uint32_t nb = c.sizes[si], K = nb + 16, n3 = 3 * K;
   const float*   llr = llr_all + (size_t)sf * LLR_STRIDE;
   const uint16_t* tab = c.conv_tab[si];
 
-  // ---- prologue: rate-dematch (accumulating), quantise -------------------------------------------
+  // ---- which of the two candidates are decoded at all (location exists, every CCE above the power floor) -------------------
   bool     valid[2];
-  uint32_t loc_i[2];
+  uint32_t loc_i[2], ncce_c[2], L_c[2];
   for (int cd = 0; cd < 2; cd++) {
     loc_i[cd] = 2 * pair + cd;
     valid[cd] = loc_i[cd] < nloc;
-    uint32_t ncce = 0, L = 0;
+    ncce_c[cd] = 0, L_c[cd] = 0;
     if (valid[cd]) {
       const uint32_t e = c.loc_tab[cfi - 1][loc_i[cd]];
-      ncce = e & 0xFFu, L = e >> 8;
+      ncce_c[cd] = e & 0xFFu, L_c[cd] = e >> 8;
       if (c.flags & LTEPHY_FLAG_SKIP_LOW_POWER)
-        for (uint32_t i = ncce; i < ncce + (1u << L); i++)
+        for (uint32_t i = ncce_c[cd]; i < ncce_c[cd] + (1u << L_c[cd]); i++)
           if (info[sf].cce_power[i] < 0.7f) valid[cd] = false;
     }
-    const uint32_t E  = 72u << L;
-    const float*   e  = llr + 72 * ncce;
-    float          mx = 0.0f;
-    for (uint32_t j = lane; j < n3; j += 32) {
-      float acc = 0.0f;
-      if (valid[cd])
-        for (uint32_t k = j; k < E; k += n3) acc = acc + e[k];
-      sm.rm[cd][tab[j]] = acc;
-      mx                = fmaxf(mx, fabsf(acc));
-    }
-#pragma unroll
-    for (int off = 16; off >= 1; off >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, off));
-    if (!(mx > 0.0f)) valid[cd] = false;
-    const float gain = valid[cd] ? 32.0f / mx : 0.0f;
-    __syncwarp();
-    for (uint32_t j = lane; j < n3; j += 32) {
-      float v = sm.rm[cd][j] * gain + 127.5f;
-      v       = fminf(fmaxf(v, 0.0f), 255.0f);
-      const int r = 2 * (int)v - 255;
-      uint16_t* dst = reinterpret_cast<uint16_t*>(&sm.R[j / K][j % K]);
-      dst[cd]       = (uint16_t)(short)r;
-    }
-    __syncwarp();
   }
+  // ---- prologue: rate-dematch (accumulating), quantise -------------------------------------------
+  if (valid[0] || valid[1])
+    for (int cd = 0; cd < 2; cd++) {
+      const uint32_t E  = 72u << L_c[cd];
+      const float*   e  = llr + 72 * ncce_c[cd];
+      float          mx = 0.0f;
+      for (uint32_t j = lane; j < n3; j += 32) {
+        float acc = 0.0f;
+        if (valid[cd])
+          for (uint32_t k = j; k < E; k += n3) acc = acc + e[k];
+        sm.p.rm[cd][tab[j]] = acc;
+        mx                  = fmaxf(mx, fabsf(acc));
+      }
+#pragma unroll
+      for (int off = 16; off >= 1; off >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, off));
+      if (!(mx > 0.0f)) valid[cd] = false;
+      const float gain = valid[cd] ? 32.0f / mx : 0.0f;
+      __syncwarp();
+      for (uint32_t st = 0; st < 3; st++)
+        for (uint32_t k = lane; k < K; k += 32) {
+          float v = sm.p.rm[cd][st * K + k] * gain + 127.5f;
+          v       = fminf(fmaxf(v, 0.0f), 255.0f);
+          const int r = 2 * (int)v - 255;
+          reinterpret_cast<uint16_t*>(&sm.p.R[st][k])[cd] = (uint16_t)(short)r;
+        }
+      __syncwarp();
+    }
   if (!valid[0] && !valid[1]) {
     if (lane < 2 && loc_i[lane] < LTEPHY_MAX_LOC) {
       ltephy_cand_t o{};
@@ -120,7 +175,7 @@ __global__ void __launch_bounds__(VIT_WARPS * 32) dci_viterbi_kernel(const __gri
   }
   // branch-metric table for all 8 output patterns p = o0*4 + o1*2 + o2: 765 + sum_i (o_i ? +r_i : -r_i), both candidates
   for (uint32_t k = lane; k < K; k += 32) {
-    const uint32_t r0 = sm.R[0][k], r1 = sm.R[1][k], r2 = sm.R[2][k];
+    const uint32_t r0 = sm.p.R[0][k], r1 = sm.p.R[1][k], r2 = sm.p.R[2][k];
     const uint32_t n0 = __vneg2(r0), n1 = __vneg2(r1), n2 = __vneg2(r2);
 #pragma unroll
     for (uint32_t pat = 0; pat < 8; pat++)
@@ -234,28 +289,13 @@ __global__ void __launch_bounds__(VIT_WARPS * 32) dci_viterbi_kernel(const __gri
   uint32_t w0 = 0, w1 = 0, w2 = 0;
   if (lane < 2) {
     const int       cd = (int)lane;
-    uint32_t        y = best_y[cd], u = best_u[cd], pos = (5u - psi) % 5u;
     const uint32_t* dw = reinterpret_cast<const uint32_t*>(sm.dec) + cd * 2; // word (t-K)*4 + cd*2 + u
-    auto back = [&](int idx) { // idx = t - K
-      const uint32_t d = (dw[idx * 4 + (int)u] >> y) & 1u;
-      u                = (y >> pos) & 1u;
-      y                = (y & ~(1u << pos)) | (d << pos);
-      pos              = pos == 4 ? 0 : pos + 1;
-    };
-    for (int idx = 2 * (int)K - 1; idx >= (int)K; idx--) back(idx); // third copy: only gives traceback depth
-    // second copy: data bit i = idx (K-1 .. 0), bit i at position 31 - (i & 31) of word i >> 5
-    int idx = (int)K - 1;
-    for (; idx >= 64; idx--) {
-      w2 |= u << (31 - (idx & 31));
-      back(idx);
-    }
-    for (; idx >= 32; idx--) {
-      w1 |= u << (31 - (idx & 31));
-      back(idx);
-    }
-    for (; idx >= 0; idx--) {
-      w0 |= u << (31 - (idx & 31));
-      back(idx);
+    switch ((5u - psi) % 5u) {
+      case 0: vit_traceback<0>(dw, (int)K, best_y[cd], best_u[cd], w0, w1, w2); break;
+      case 1: vit_traceback<1>(dw, (int)K, best_y[cd], best_u[cd], w0, w1, w2); break;
+      case 2: vit_traceback<2>(dw, (int)K, best_y[cd], best_u[cd], w0, w1, w2); break;
+      case 3: vit_traceback<3>(dw, (int)K, best_y[cd], best_u[cd], w0, w1, w2); break;
+      default: vit_traceback<4>(dw, (int)K, best_y[cd], best_u[cd], w0, w1, w2); break;
     }
   }
   // ---- CRC16 (poly 0x11021, zero init) over the first nb bits of both candidates at once: XOR over the set bits of
@@ -269,8 +309,8 @@ __global__ void __launch_bounds__(VIT_WARPS * 32) dci_viterbi_kernel(const __gri
 #pragma unroll
   for (int cd = 0; cd < 2; cd++) {
     uint32_t r = 0;
-    if (lane < nb && ((cw0[cd] >> (31 - lane)) & 1u)) r ^= xpow_s[nb - 1 - lane];
-    if (lane + 32 < nb && ((cw1[cd] >> (31 - lane)) & 1u)) r ^= xpow_s[nb - 1 - (lane + 32)];
+    if (lane < nb && ((cw0[cd] >> (31 - lane)) & 1u)) r ^= vit_xpow[nb - 1 - lane];
+    if (lane + 32 < nb && ((cw1[cd] >> (31 - lane)) & 1u)) r ^= vit_xpow[nb - 1 - (lane + 32)];
     acc |= r << (16 * cd);
   }
 #pragma unroll

@@ -148,6 +148,10 @@ extern "C" int ltephy_create(const ltephy_cfg_t* cfg, ltephy_t** out)
       tw[k]    = make_float2((float)std::cos(a), (float)std::sin(a));
     }
     c.tw = upload(h, tw.data(), tw.size());
+    std::vector<float2> tws(c.fft, make_float2(0.0f, 0.0f)); // per-stage contiguous copies: tws[H + pos] = tw[pos * fft / (2 H)]
+    for (uint32_t H = 1; H <= c.fft / 2; H *= 2)
+      for (uint32_t pos = 0; pos < H; pos++) tws[H + pos] = tw[(size_t)pos * (c.fft / (2 * H))];
+    c.tw_st = upload(h, tws.data(), tws.size());
     std::vector<float2> rot(c.fft);
     for (uint32_t i = 0; i < c.fft; i++) {
       double ph = M_PI * (double)i / (double)c.fft;
@@ -888,6 +892,8 @@ extern "C" int ltephy_get_ul(ltephy_t* h, ltephy_tb_result_t* results, ltephy_ul
     }
     CU(cudaStreamSynchronize(h->stream));
     h->stage_busy = false;
+    cudaEventElapsedTime(&h->t_ms[1], h->ev[2], h->ev[3]); // H2D of the UL samples + UL OFDM + PUSCH + rate-dematch + turbo + CRC
+    if (!h->cbs.empty()) cudaEventElapsedTime(&h->t_ms[2], h->ev[4], h->ev[5]);
   }
   size_t wp = 0;
   for (size_t i = 0; i < ng; i++) {

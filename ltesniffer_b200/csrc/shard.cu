@@ -91,7 +91,13 @@ int        nccl_load()
 {
   std::lock_guard<std::mutex> lk(g_nccl_mtx);
   if (g_nccl.lib) return 0;
-  void* lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL); // a process that already imported torch gets torch's copy
+  // LTEPHY_NCCL_LIB names the library explicitly.  Otherwise the copy the process already holds is used (a process that imported torch gets
+  // torch's bundled NCCL; loading an older system copy first would make a later "import torch" fail on the symbols it lacks), then the
+  // loader's default libnccl.so.2.
+  void*       lib = nullptr;
+  const char* env = getenv("LTEPHY_NCCL_LIB");
+  if (env && *env) lib = dlopen(env, RTLD_NOW | RTLD_GLOBAL);
+  if (!lib) lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
   if (!lib) lib = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
   if (!lib) return fail(LTEPHY_ERROR, "libnccl.so.2 cannot be loaded: %s", dlerror());
 #define BIND(field, name)                                                                          \
