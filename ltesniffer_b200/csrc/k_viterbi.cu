@@ -33,7 +33,7 @@ struct __align__(16) VitWarpSmem {
       float    rm[2][3 * VIT_KMAX]; // dematched soft bits, stream-major (prologue only)
       uint32_t R[3][VIT_KMAX];      // quantised symbols 2q-255, packed (cand0 lo, cand1 hi) (prologue only)
     } p;
-    uint4 dec[2 * VIT_KMAX];        // survivor decisions of steps K..3K-1: {c0 u=0, c0 u=1, c1 u=0, c1 u=1}, bit = lane of the step's layout
+    uint4 dec[2 * VIT_KMAX + 4];    // dec[4 + t - K]: survivor decisions of steps K..3K-1 (the up to 4 steps before K of the first stored group land in dec[0..3]): {c0 u=0, c0 u=1, c1 u=0, c1 u=1}, bit = lane of the step's layout
   };
   uint32_t S[VIT_KMAX][8];          // branch metrics + 765 for the 8 output sign patterns (o0 o1 o2), packed; S[k][p ^ 7] = 1530 - S[k][p]
 };
@@ -58,10 +58,9 @@ __device__ const uint16_t vit_xpow[64] = {
 // per step, so with the start position as a template parameter every step of a group of five has a compile-time position.
 // Steps idx = 2K-1 .. K (third copy) only give traceback depth; idx = K-1 .. 0 (second copy) are the data bits: bit i at position
 // 31 - (i & 31) of word i >> 5, collected by a funnel shift and flushed when a word is complete.
-template <int P0> __device__ __forceinline__ void vit_traceback(const uint32_t* __restrict__ dw, int K, uint32_t y, uint32_t u, uint32_t& w0, uint32_t& w1,
-                                                                uint32_t& w2)
+template <int P0> __device__ __forceinline__ void vit_traceback(const uint32_t* __restrict__ dw, int K, int idx, uint32_t y, uint32_t u, uint32_t& w0,
+                                                                uint32_t& w1, uint32_t& w2)
 {
-  int      idx = 2 * K - 1;
   uint32_t cur = 0;
 #define TB_BACK(POS)                                                                                                           \
   {                                                                                                                            \
@@ -145,6 +144,7 @@ __global__ void __launch_bounds__(VIT_WARPS * 32) dci_viterbi_kernel(const __gri
       const uint32_t E  = 72u << L_c[cd];
       const float*   e  = llr + 72 * ncce_c[cd];
       float          mx = 0.0f;
+#pragma unroll 1
       for (uint32_t j = lane; j < n3; j += 32) {
         float acc = 0.0f;
         if (valid[cd])
@@ -157,7 +157,9 @@ __global__ void __launch_bounds__(VIT_WARPS * 32) dci_viterbi_kernel(const __gri
       if (!(mx > 0.0f)) valid[cd] = false;
       const float gain = valid[cd] ? 32.0f / mx : 0.0f;
       __syncwarp();
+#pragma unroll 1
       for (uint32_t st = 0; st < 3; st++)
+#pragma unroll 1
         for (uint32_t k = lane; k < K; k += 32) {
           float v = sm.p.rm[cd][st * K + k] * gain + 127.5f;
           v       = fminf(fmaxf(v, 0.0f), 255.0f);
@@ -174,6 +176,7 @@ __global__ void __launch_bounds__(VIT_WARPS * 32) dci_viterbi_kernel(const __gri
     return;
   }
   // branch-metric table for all 8 output patterns p = o0*4 + o1*2 + o2: 765 + sum_i (o_i ? +r_i : -r_i), both candidates
+#pragma unroll 1
   for (uint32_t k = lane; k < K; k += 32) {
     const uint32_t r0 = sm.p.R[0][k], r1 = sm.p.R[1][k], r2 = sm.p.R[2][k];
     const uint32_t n0 = __vneg2(r0), n1 = __vneg2(r1), n2 = __vneg2(r2);
@@ -235,23 +238,17 @@ __global__ void __launch_bounds__(VIT_WARPS * 32) dci_viterbi_kernel(const __gri
     a0                 = ref * vc.minus_one + a0;                                                                              \
     a1                 = ref * vc.minus_one + a1;                                                                              \
   }
-  // three concatenated copies of the K-step frame = 3K steps in groups of five phases; decisions are kept from step K on
-  const uint32_t T3 = 3 * K;
+  // three concatenated copies of the K-step frame = 3K steps in groups of five phases; decisions are kept from the group that contains step K on
+  // (its steps before K are stored too, into dec[0..3], and never read)
+  const uint32_t T3 = 3 * K, t0 = (K / 5u) * 5u;
   uint32_t       t  = 0;
-  for (; t + 5 <= K; t += 5) {
+  dst               = sm.dec + 4 - (K - t0);
+#pragma unroll 1
+  for (; t < t0; t += 5) {
     VIT_STEP(0, false) VIT_STEP(1, false) VIT_STEP(2, false) VIT_STEP(3, false) VIT_STEP(4, false)
     VIT_RENORM()
   }
-  if (t < K) { // the group that straddles step K: per-step store flag
-    const uint32_t b = K - t; // steps of this group that belong to the first copy (1..4)
-    VIT_STEP(0, false)
-    if (b > 1) VIT_STEP(1, false) else VIT_STEP(1, true)
-    if (b > 2) VIT_STEP(2, false) else VIT_STEP(2, true)
-    if (b > 3) VIT_STEP(3, false) else VIT_STEP(3, true)
-    VIT_STEP(4, true)
-    VIT_RENORM()
-    t += 5;
-  }
+#pragma unroll 1
   for (; t + 5 <= T3; t += 5) {
     VIT_STEP(0, true) VIT_STEP(1, true) VIT_STEP(2, true) VIT_STEP(3, true) VIT_STEP(4, true)
     VIT_RENORM()
@@ -289,14 +286,17 @@ __global__ void __launch_bounds__(VIT_WARPS * 32) dci_viterbi_kernel(const __gri
   uint32_t w0 = 0, w1 = 0, w2 = 0;
   if (lane < 2) {
     const int       cd = (int)lane;
-    const uint32_t* dw = reinterpret_cast<const uint32_t*>(sm.dec) + cd * 2; // word (t-K)*4 + cd*2 + u
-    switch ((5u - psi) % 5u) {
-      case 0: vit_traceback<0>(dw, (int)K, best_y[cd], best_u[cd], w0, w1, w2); break;
-      case 1: vit_traceback<1>(dw, (int)K, best_y[cd], best_u[cd], w0, w1, w2); break;
-      case 2: vit_traceback<2>(dw, (int)K, best_y[cd], best_u[cd], w0, w1, w2); break;
-      case 3: vit_traceback<3>(dw, (int)K, best_y[cd], best_u[cd], w0, w1, w2); break;
-      default: vit_traceback<4>(dw, (int)K, best_y[cd], best_u[cd], w0, w1, w2); break;
+    const uint32_t* dw = reinterpret_cast<const uint32_t*>(sm.dec + 4) + cd * 2; // word (t-K)*4 + cd*2 + u
+    uint32_t        y = best_y[cd], u = best_u[cd], pos = (5u - psi) % 5u;
+    int             idx = 2 * (int)K - 1;
+    while (pos != 0) { // up to four steps (third copy, nothing recorded) bring the rotation to position 0; the rest runs with compile-time positions
+      const uint32_t d = (dw[idx * 4 + (int)u] >> y) & 1u;
+      u                = (y >> pos) & 1u;
+      y                = (y & ~(1u << pos)) | (d << pos);
+      pos              = pos == 4 ? 0 : pos + 1;
+      idx--;
     }
+    vit_traceback<0>(dw, (int)K, idx, y, u, w0, w1, w2);
   }
   // ---- CRC16 (poly 0x11021, zero init) over the first nb bits of both candidates at once: XOR over the set bits of
   // x^(nb - 1 - i + 16) mod P, folded across the warp; candidate 0 in the low half, candidate 1 in the high half
@@ -319,12 +319,10 @@ __global__ void __launch_bounds__(VIT_WARPS * 32) dci_viterbi_kernel(const __gri
     const int      cd  = (int)lane;
     const uint32_t reg = (acc >> (16 * cd)) & 0xFFFFu;
     const unsigned long long lo64 = ((unsigned long long)w0 << 32) | (unsigned long long)w1; // bits 0..63, bit i at 63 - i
-    // the 16 parity bits nb .. nb+15 (bit i of the frame: word i>>5)
-    uint32_t par = 0;
-    for (uint32_t i = nb; i < nb + 16; i++) {
-      const uint32_t wsel = (i >> 5) == 0 ? w0 : ((i >> 5) == 1 ? w1 : w2);
-      par                 = (par << 1) | ((wsel >> (31 - (i & 31))) & 1u);
-    }
+    // the 16 parity bits nb .. nb+15 of the frame (bit i at position 31 - (i & 31) of word i >> 5): top 16 bits of the 96-bit string shifted left by nb
+    const unsigned long long nx64 = (unsigned long long)w2 << 32;
+    const unsigned long long win  = nb >= 64 ? (nx64 << (nb - 64)) : (nb == 0 ? lo64 : ((lo64 << nb) | (nx64 >> (64 - nb))));
+    const uint32_t           par  = (uint32_t)(win >> 48);
     ltephy_cand_t o{};
     unsigned long long bits = lo64;
     if (nb < 64) bits &= ~((~0ull) >> nb);

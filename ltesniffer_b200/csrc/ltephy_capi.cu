@@ -881,7 +881,7 @@ extern "C" int ltephy_get_ul(ltephy_t* h, ltephy_tb_result_t* results, ltephy_ul
 {
   if (!h || !results) return fail(LTEPHY_ERROR_INVALID_INPUTS, "get_ul: bad arguments");
   const size_t ng = h->ulgrants.size();
-  if (ng) CU(cudaMemcpyAsync(h->h_ulchest.p, h->d_ulchest.p, ng * sizeof(ltephy_ul_chest_t), cudaMemcpyDeviceToHost, h->stream));
+  if (ng) CU(cudaMemcpyAsync(h->h_ulchest.p, h->d_ulchest.p, ng * sizeof(DevUlChest), cudaMemcpyDeviceToHost, h->stream));
   // transport blocks come back through the shared phase-B path (one result per grant)
   std::vector<ltephy_tb_result_t> res(ng + 1);
   {
