@@ -35,7 +35,8 @@ struct __align__(16) VitWarpSmem {
     } p;
     uint4 dec[2 * VIT_KMAX + 4];    // dec[4 + t - K]: survivor decisions of steps K..3K-1 (the up to 4 steps before K of the first stored group land in dec[0..3]): {c0 u=0, c0 u=1, c1 u=0, c1 u=1}, bit = lane of the step's layout
   };
-  uint32_t S[VIT_KMAX][8];          // branch metrics + 765 for the 8 output sign patterns (o0 o1 o2), packed; S[k][p ^ 7] = 1530 - S[k][p]
+  uint32_t S[VIT_KMAX + 4][8];      // branch metrics + 765 for the 8 output sign patterns (o0 o1 o2), packed; S[k][p ^ 7] = 1530 - S[k][p];
+                                    // rows K..K+3 repeat rows 0..3 so that a group of five steps never wraps inside the table
 };
 
 struct VitConst {
@@ -182,7 +183,11 @@ __global__ void __launch_bounds__(VIT_WARPS * 32) dci_viterbi_kernel(const __gri
     const uint32_t n0 = __vneg2(r0), n1 = __vneg2(r1), n2 = __vneg2(r2);
 #pragma unroll
     for (uint32_t pat = 0; pat < 8; pat++)
-      sm.S[k][pat] = __vadd2(__vadd2(__vadd2((pat & 4u) ? r0 : n0, (pat & 2u) ? r1 : n1), (pat & 1u) ? r2 : n2), pk(VIT_OFFS, VIT_OFFS));
+    {
+      const uint32_t m = __vadd2(__vadd2(__vadd2((pat & 4u) ? r0 : n0, (pat & 2u) ? r1 : n1), (pat & 1u) ? r2 : n2), pk(VIT_OFFS, VIT_OFFS));
+      sm.S[k][pat] = m;
+      if (k < 4) sm.S[K + k][pat] = m;
+    }
   }
   __syncwarp();
 
@@ -197,7 +202,7 @@ __global__ void __launch_bounds__(VIT_WARPS * 32) dci_viterbi_kernel(const __gri
 #pragma unroll
     for (int k = 1; k < 5; k++) p |= ((lane >> ((k - 1 - f + 10) % 5)) & 1u) << k;
     const uint32_t o0 = __popc(p & 0x36u) & 1u, o1 = __popc(p & 0x27u) & 1u, o2 = __popc(p & 0x2Bu) & 1u;
-    po[f] = (o0 * 4 + o1 * 2 + o2) * 4u;
+    po[f] = (o0 * 4 + o1 * 2 + o2) * 4u + 32u * (uint32_t)f; // + the row offset of step f inside its group
     xm[f] = (lane & (16u >> f)) ? 0xFFFFFFFFu : 0u;
   }
   const uint32_t C1530 = pk(2 * VIT_OFFS, 2 * VIT_OFFS), CSPREAD = pk(VIT_SPREAD, VIT_SPREAD);
@@ -208,12 +213,15 @@ __global__ void __launch_bounds__(VIT_WARPS * 32) dci_viterbi_kernel(const __gri
   uint4*   dst = sm.dec;
 
   // one trellis step in phase F; store: keep the survivor decisions of this step
+#define VIT_SEL(D, A, B, C) asm("lop3.b32 %0, %1, %2, %3, 0xE4;" : "=r"(D) : "r"(A), "r"(B), "r"(C)) /* (A & C) | (B & ~C): one LOP3, no compare */
 #define VIT_STEP(F, STORE)                                                                                                     \
   {                                                                                                                            \
-    const uint32_t snd = (a0 & xm[F]) | (a1 & ~xm[F]);                                                                         \
+    uint32_t snd, n0, n1;                                                                                                      \
+    VIT_SEL(snd, a0, a1, xm[F]);                                                                                               \
     const uint32_t rcv = __shfl_xor_sync(0xffffffffu, snd, 16u >> F);                                                          \
-    a0                 = (rcv & xm[F]) | (a0 & ~xm[F]);                                                                        \
-    a1                 = (a1 & xm[F]) | (rcv & ~xm[F]);                                                                        \
+    VIT_SEL(n0, rcv, a0, xm[F]);                                                                                               \
+    VIT_SEL(n1, a1, rcv, xm[F]);                                                                                               \
+    a0 = n0, a1 = n1;                                                                                                          \
     const uint32_t m   = *reinterpret_cast<const uint32_t*>(Sb + kb + po[F]);                                                  \
     const uint32_t mn  = m * vc.minus_one + C1530;                                                                             \
     bool           p0h, p0l, p1h, p1l;                                                                                         \
@@ -229,8 +237,11 @@ __global__ void __launch_bounds__(VIT_WARPS * 32) dci_viterbi_kernel(const __gri
       dst++;                                                                                                                   \
     }                                                                                                                          \
     a0 = N0, a1 = N1;                                                                                                          \
-    kb += 32u;                                                                                                                 \
-    if (kb == Kb) kb = 0;                                                                                                      \
+  }
+#define VIT_GROUP_END()  /* five rows further; the table has K rows (+ 4 repeated ones) */                                      \
+  {                                                                                                                            \
+    kb += 160u;                                                                                                                \
+    if (kb >= Kb) kb -= Kb;                                                                                                    \
   }
 #define VIT_RENORM()                                                                                                           \
   {                                                                                                                            \
@@ -246,11 +257,13 @@ __global__ void __launch_bounds__(VIT_WARPS * 32) dci_viterbi_kernel(const __gri
 #pragma unroll 1
   for (; t < t0; t += 5) {
     VIT_STEP(0, false) VIT_STEP(1, false) VIT_STEP(2, false) VIT_STEP(3, false) VIT_STEP(4, false)
+    VIT_GROUP_END()
     VIT_RENORM()
   }
 #pragma unroll 1
   for (; t + 5 <= T3; t += 5) {
     VIT_STEP(0, true) VIT_STEP(1, true) VIT_STEP(2, true) VIT_STEP(3, true) VIT_STEP(4, true)
+    VIT_GROUP_END()
     VIT_RENORM()
   }
   const uint32_t tail = T3 - t; // 0..4 steps left, phases 0..
@@ -260,6 +273,8 @@ __global__ void __launch_bounds__(VIT_WARPS * 32) dci_viterbi_kernel(const __gri
   if (tail > 3) VIT_STEP(3, true)
 #undef VIT_STEP
 #undef VIT_RENORM
+#undef VIT_GROUP_END
+#undef VIT_SEL
   __syncwarp();
   // ---- best final state (lowest index on ties), per candidate ------------------------------------
   // layout after the last step: phase psi = T3 mod 5 before an exchange: lane bit i = state bit ((i + psi) mod 5) + 1, register = bit 0
