@@ -186,7 +186,7 @@ struct Slot {
   PinBuf<TbMeta>     h_meta, h_g_meta;
   DevBuf<ltephy_tb_result_t> d_g_res;
   PinBuf<ltephy_tb_result_t> h_g_res;
-  cudaEvent_t        ev_pack = nullptr;
+  cudaEvent_t        ev_pack = nullptr, ev_g = nullptr;
   std::vector<uint32_t>           tti_cfi, grant_dci;
   std::vector<ltephy_grant_t>     grants;
   std::vector<ltephy_tb_result_t> res;
@@ -196,7 +196,8 @@ struct Slot {
     h_pack_all.release(), h_full_all.release(), h_offs_all.release(), d_hdr.release(), d_hdr_all.release(), h_hdr.release(), h_hdr_all.release();
     d_meta.release(), d_g_meta.release(), h_meta.release(), h_g_meta.release(), d_g_res.release(), h_g_res.release();
     if (ev_pack) cudaEventDestroy(ev_pack);
-    ev_pack = nullptr;
+    if (ev_g) cudaEventDestroy(ev_g);
+    ev_pack = ev_g = nullptr;
   }
 };
 inline double now_ms() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
@@ -245,8 +246,12 @@ extern "C" int ltephy_shard_create(const uint8_t* id, uint32_t rank, uint32_t wo
   memcpy(&u[0], id, NCCL_UNIQUE_ID_BYTES), memcpy(&u[1], id + NCCL_UNIQUE_ID_BYTES, NCCL_UNIQUE_ID_BYTES);
   ncclResult_t r = g_nccl.CommInitRank(&sh->comm_x, (int)world, u[0], (int)rank);
   if (r == ncclSuccess) r = g_nccl.CommInitRank(&sh->comm_g, (int)world, u[1], (int)rank);
-  if (r != ncclSuccess || cudaStreamCreateWithFlags(&sh->st_x, cudaStreamNonBlocking) != cudaSuccess ||
-      cudaStreamCreateWithFlags(&sh->st_g, cudaStreamNonBlocking) != cudaSuccess) {
+  // highest priority: the collectives are short but sit on the critical path of every batch, and the GPU is kept full by the decode kernels of
+  // the other pipelines -- without it an NCCL kernel waits behind whole grids of them
+  int prio_lo = 0, prio_hi = 0;
+  cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+  if (r != ncclSuccess || cudaStreamCreateWithPriority(&sh->st_x, cudaStreamNonBlocking, prio_hi) != cudaSuccess ||
+      cudaStreamCreateWithPriority(&sh->st_g, cudaStreamNonBlocking, prio_hi) != cudaSuccess) {
     ltephy_shard_destroy(sh);
     return fail(LTEPHY_ERROR, "shard_create: %s", r != ncclSuccess ? g_nccl.GetErrorString(r) : "stream creation failed");
   }
@@ -340,20 +345,19 @@ extern "C" int ltephy_decode_subframes_sharded(ltephy_shard_t* sh, ltephy_t* h, 
   // ---- exchange turn -----------------------------------------------------------------------------------
   gx.take();
   CU(cudaStreamWaitEvent(sh->st_x, sl->ev_pack, 0));
+  // two all-gathers back to back (offsets, then the records at their fixed per-rank capacity: 4.6 MB per 1000 subframes, a third of it used --
+  // NVLink does not notice, and no host round trip sits between the two collectives); only the used part of every rank's records goes to the host
   NC(g_nccl.AllGather(sl->d_offs.p, sl->d_offs_all.p, n + 1, ncclUint32, sh->comm_x, sh->st_x));
+  NC(g_nccl.AllGather(sl->d_pack.p, sl->d_pack_all.p, cap_rank, ncclUint8, sh->comm_x, sh->st_x));
   CU(cudaMemcpyAsync(sl->h_offs_all.p, sl->d_offs_all.p, (size_t)W * (n + 1) * 4, cudaMemcpyDeviceToHost, sh->st_x));
   CU(cudaStreamSynchronize(sh->st_x));
   uint64_t exch = 0;
-  NC(g_nccl.GroupStart());
   for (uint32_t q = 0; q < W; q++) {
     const uint32_t bytes = sl->h_offs_all.p[(size_t)q * (n + 1) + n];
     if (bytes > cap_rank) return fail(LTEPHY_ERROR, "rank %u announced %u packed bytes for %u subframes", q, bytes, n);
     exch += bytes;
-    NC(g_nccl.Broadcast(sl->d_pack.p, sl->d_pack_all.p + q * cap_rank, bytes, ncclUint8, (int)q, sh->comm_x, sh->st_x));
+    CU(cudaMemcpyAsync(sl->h_pack_all.p + q * cap_rank, sl->d_pack_all.p + q * cap_rank, bytes, cudaMemcpyDeviceToHost, sh->st_x));
   }
-  NC(g_nccl.GroupEnd());
-  for (uint32_t q = 0; q < W; q++)
-    CU(cudaMemcpyAsync(sl->h_pack_all.p + q * cap_rank, sl->d_pack_all.p + q * cap_rank, sl->h_offs_all.p[(size_t)q * (n + 1) + n], cudaMemcpyDeviceToHost, sh->st_x));
   CU(cudaStreamSynchronize(sh->st_x));
   std::vector<const uint8_t*>       bufs(W);
   std::vector<const uint32_t*>      offs(W);
@@ -403,6 +407,7 @@ extern "C" int ltephy_decode_subframes_sharded(ltephy_shard_t* sh, ltephy_t* h, 
   // ---- gather turn: the decoded transport blocks of every rank -> rank 0 -----------------------------------------------
   gg.take();
   if (W > 1) {
+    if (!sl->ev_g) CU(cudaEventCreateWithFlags(&sl->ev_g, cudaEventDisableTiming));
     const size_t ntb = h->tbs.size();
     if (sl->h_hdr.reserve(1) || sl->d_hdr.reserve(1) || sl->d_hdr_all.reserve(W) || sl->h_hdr_all.reserve(W) || sl->h_meta.reserve(2 * (size_t)ng + 1) ||
         sl->d_meta.reserve(2 * (size_t)ng + 1))
@@ -425,7 +430,9 @@ extern "C" int ltephy_decode_subframes_sharded(ltephy_shard_t* sh, ltephy_t* h, 
       if (ntb) NC(g_nccl.Send(h->d_res.p, ntb * sizeof(ltephy_tb_result_t), ncclUint8, 0, sh->comm_g, sh->st_g));
       if (h->payload_bytes) NC(g_nccl.Send(h->d_payload.p, h->payload_bytes, ncclUint8, 0, sh->comm_g, sh->st_g));
       NC(g_nccl.GroupEnd());
-      CU(cudaStreamSynchronize(sh->st_g)); // the handle's buffers are free for its next batch when this call returns
+      CU(cudaEventRecord(sl->ev_g, sh->st_g));
+      gg.give();                              // the turn orders the NCCL calls only; waiting for them happens outside it
+      CU(cudaEventSynchronize(sl->ev_g));     // the handle's buffers are free for its next batch when this call returns
     } else {
       size_t tm = 0, tr = 0, tp = 0;
       for (uint32_t q = 1; q < W; q++) tm += 2 * (size_t)sl->h_hdr_all.p[q].ng, tr += sl->h_hdr_all.p[q].ntb, tp += (sl->h_hdr_all.p[q].payload_bytes + 15) & ~(size_t)15;
@@ -443,10 +450,13 @@ extern "C" int ltephy_decode_subframes_sharded(ltephy_shard_t* sh, ltephy_t* h, 
         om += 2 * (size_t)gh.ng, orr += gh.ntb, op += (gh.payload_bytes + 15) & ~(size_t)15;
       }
       NC(g_nccl.GroupEnd());
-      if (tm) CU(cudaMemcpyAsync(sl->h_g_meta.p, sl->d_g_meta.p, tm * sizeof(TbMeta), cudaMemcpyDeviceToHost, sh->st_g));
-      if (tr) CU(cudaMemcpyAsync(sl->h_g_res.p, sl->d_g_res.p, tr * sizeof(ltephy_tb_result_t), cudaMemcpyDeviceToHost, sh->st_g));
-      if (tp) CU(cudaMemcpyAsync(payload + base0, sl->d_g_payload.p, tp, cudaMemcpyDeviceToHost, sh->st_g));
-      CU(cudaStreamSynchronize(sh->st_g));
+      CU(cudaEventRecord(sl->ev_g, sh->st_g));
+      gg.give(); // the copies to the host (the bulk of the time when `payload` is pageable memory) run on this handle's stream, outside the turn
+      CU(cudaStreamWaitEvent(h->stream, sl->ev_g, 0));
+      if (tm) CU(cudaMemcpyAsync(sl->h_g_meta.p, sl->d_g_meta.p, tm * sizeof(TbMeta), cudaMemcpyDeviceToHost, h->stream));
+      if (tr) CU(cudaMemcpyAsync(sl->h_g_res.p, sl->d_g_res.p, tr * sizeof(ltephy_tb_result_t), cudaMemcpyDeviceToHost, h->stream));
+      if (tp) CU(cudaMemcpyAsync(payload + base0, sl->d_g_payload.p, tp, cudaMemcpyDeviceToHost, h->stream));
+      CU(cudaStreamSynchronize(h->stream));
       om = 0, orr = 0, op = 0;
       for (uint32_t q = 1; q < W; q++) {
         const GatherHdr& gh = sl->h_hdr_all.p[q];
