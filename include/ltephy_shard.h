@@ -32,7 +32,7 @@ extern "C" {
 
 typedef struct ltephy_shard ltephy_shard_t;
 
-#define LTEPHY_SHARD_ID_BYTES 256 /* two ncclUniqueId (exchange communicator, gather communicator) */
+#define LTEPHY_SHARD_ID_BYTES 384 /* three ncclUniqueId (exchange, gather and full-table communicators) */
 
 /* ---- packed survivor form: what crosses the wire per subframe ------------------------------------------------------- */
 typedef struct {
@@ -70,6 +70,9 @@ int ltephy_shard_unique_id(uint8_t* id);
 /* collective: every rank calls it with the same id.  device = the CUDA device of this rank's PHY handles. */
 int  ltephy_shard_create(const uint8_t* id, uint32_t rank, uint32_t world, int device, ltephy_shard_t** out);
 void ltephy_shard_destroy(ltephy_shard_t* sh);
+/* Every rank sends its transport blocks to rank 0 in a message of fixed size (no size negotiation inside the ordered section): capacity in bytes
+ * per subframe of the batch, default 24576 (a 20 MHz 2x2 cell with both MCS-table readings decoded needs about 18 KB).  Same value on every rank. */
+int ltephy_shard_set_gather_capacity(ltephy_shard_t* sh, uint32_t bytes_per_subframe);
 
 typedef struct {
   double   host_ms[8];      /* submit A, wait A, exchange turn (incl. waiting for it), walk turn wait, walk, grants, phase B (submit + wait), gather turn */

@@ -317,6 +317,7 @@ def _bind_search(L):
     L.ltephy_search_config.argtypes = [P, C.c_int, C.c_int, C.c_uint32]
     L.ltephy_search_speculate_256qam.argtypes = [P, C.c_int]
     L.ltephy_search_set_ul_hopping.argtypes = [P, C.c_uint32]
+    L.ltephy_shard_set_gather_capacity.argtypes = [P, C.c_uint32]
     L.ltephy_search_add_evergreen.argtypes = [P, C.c_uint16, C.c_uint16, C.c_uint32]
     L.ltephy_search_add_forbidden.argtypes = [P, C.c_uint16, C.c_uint16, C.c_uint32]
     L.ltephy_search_activate.argtypes = [P, C.c_uint16, C.c_uint32, C.c_int]
@@ -458,7 +459,7 @@ def decode_subframes(phy, search, iq, tti, seq=SEQ_NONE, max_dcis=None, scratch=
 
 # ------------------------------------------------------------------------------------------------
 # sharded operation (include/ltephy_shard.h)
-SHARD_ID_BYTES = 256
+SHARD_ID_BYTES = 384
 PACK_MAX_BYTES = 64 + 4 * MAX_LOC + 16 * COMPACT_CAP
 PACKED_HDR_DTYPE = np.dtype([("count", "<u4"), ("tti", "<u4"), ("cfi", "<u4"), ("nloc", "<u4"), ("noise", "<f4", (2, 2)), ("rsrp", "<f4", (2, 2)),
                              ("low", "<u8", 2)])

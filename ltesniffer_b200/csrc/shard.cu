@@ -180,24 +180,20 @@ struct Slot {
   DevBuf<uint32_t>   d_offs, d_offs_all;
   PinBuf<uint8_t>    h_pack_all, h_full_all;
   PinBuf<uint32_t>   h_offs_all;
-  DevBuf<GatherHdr>  d_hdr, d_hdr_all;
-  PinBuf<GatherHdr>  h_hdr, h_hdr_all;
-  DevBuf<TbMeta>     d_meta, d_g_meta;
-  PinBuf<TbMeta>     h_meta, h_g_meta;
-  DevBuf<ltephy_tb_result_t> d_g_res;
-  PinBuf<ltephy_tb_result_t> h_g_res;
-  cudaEvent_t        ev_pack = nullptr, ev_g = nullptr;
+  DevBuf<uint8_t>    d_msg, d_g_msg;   // gather message of this rank / of every other rank (rank 0): GatherHdr, TbMeta[2 ng], ltephy_tb_result_t[ntb]
+  PinBuf<uint8_t>    h_msg, h_g_msg;
+  cudaEvent_t        ev_pack = nullptr, ev_g = nullptr, ev_x = nullptr, ev_msg = nullptr;
   std::vector<uint32_t>           tti_cfi, grant_dci;
   std::vector<ltephy_grant_t>     grants;
   std::vector<ltephy_tb_result_t> res;
   void release()
   {
     d_pack.release(), d_pack_all.release(), d_full_all.release(), d_g_payload.release(), d_offs.release(), d_offs_all.release();
-    h_pack_all.release(), h_full_all.release(), h_offs_all.release(), d_hdr.release(), d_hdr_all.release(), h_hdr.release(), h_hdr_all.release();
-    d_meta.release(), d_g_meta.release(), h_meta.release(), h_g_meta.release(), d_g_res.release(), h_g_res.release();
-    if (ev_pack) cudaEventDestroy(ev_pack);
-    if (ev_g) cudaEventDestroy(ev_g);
-    ev_pack = ev_g = nullptr;
+    h_pack_all.release(), h_full_all.release(), h_offs_all.release(), d_msg.release(), d_g_msg.release(), h_msg.release(), h_g_msg.release();
+    for (cudaEvent_t* e : {&ev_pack, &ev_g, &ev_x, &ev_msg}) {
+      if (*e) cudaEventDestroy(*e);
+      *e = nullptr;
+    }
   }
 };
 inline double now_ms() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
@@ -206,9 +202,10 @@ inline double now_ms() { return std::chrono::duration<double, std::milli>(std::c
 struct ltephy_shard {
   uint32_t     rank = 0, world = 1;
   int          device = 0;
-  ncclComm_t   comm_x = nullptr, comm_g = nullptr; // exchange / gather: one communicator per ordered section
-  cudaStream_t st_x = nullptr, st_g = nullptr;
-  Turn         turn_x, turn_w, turn_g;
+  ncclComm_t   comm_x = nullptr, comm_g = nullptr, comm_f = nullptr; // exchange / gather / full-table fetch: one communicator per ordered section
+  cudaStream_t st_x = nullptr, st_g = nullptr, st_f = nullptr;
+  Turn         turn_x, turn_f, turn_w, turn_g;
+  uint32_t     gather_bytes_per_sf = 24576; // fixed payload capacity of one rank's gather message, per subframe of the batch
   std::mutex   slots_mtx;
   std::map<ltephy_t*, Slot*> slots;
   bool         failed = false;
@@ -227,8 +224,8 @@ extern "C" int ltephy_shard_unique_id(uint8_t* id)
 {
   if (!id) return fail(LTEPHY_ERROR_INVALID_INPUTS, "shard_unique_id: null argument");
   if (nccl_load()) return LTEPHY_ERROR;
-  static_assert(LTEPHY_SHARD_ID_BYTES == 2 * NCCL_UNIQUE_ID_BYTES, "id size");
-  for (int i = 0; i < 2; i++) {
+  static_assert(LTEPHY_SHARD_ID_BYTES == 3 * NCCL_UNIQUE_ID_BYTES, "id size");
+  for (int i = 0; i < 3; i++) {
     ncclUniqueId u;
     NC(g_nccl.GetUniqueId(&u));
     memcpy(id + i * NCCL_UNIQUE_ID_BYTES, &u, NCCL_UNIQUE_ID_BYTES);
@@ -242,20 +239,28 @@ extern "C" int ltephy_shard_create(const uint8_t* id, uint32_t rank, uint32_t wo
   CU(cudaSetDevice(device));
   ltephy_shard* sh = new ltephy_shard();
   sh->rank = rank, sh->world = world, sh->device = device;
-  ncclUniqueId u[2];
-  memcpy(&u[0], id, NCCL_UNIQUE_ID_BYTES), memcpy(&u[1], id + NCCL_UNIQUE_ID_BYTES, NCCL_UNIQUE_ID_BYTES);
+  ncclUniqueId u[3];
+  for (int i = 0; i < 3; i++) memcpy(&u[i], id + i * NCCL_UNIQUE_ID_BYTES, NCCL_UNIQUE_ID_BYTES);
   ncclResult_t r = g_nccl.CommInitRank(&sh->comm_x, (int)world, u[0], (int)rank);
   if (r == ncclSuccess) r = g_nccl.CommInitRank(&sh->comm_g, (int)world, u[1], (int)rank);
+  if (r == ncclSuccess) r = g_nccl.CommInitRank(&sh->comm_f, (int)world, u[2], (int)rank);
   // highest priority: the collectives are short but sit on the critical path of every batch, and the GPU is kept full by the decode kernels of
   // the other pipelines -- without it an NCCL kernel waits behind whole grids of them
   int prio_lo = 0, prio_hi = 0;
   cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
   if (r != ncclSuccess || cudaStreamCreateWithPriority(&sh->st_x, cudaStreamNonBlocking, prio_hi) != cudaSuccess ||
-      cudaStreamCreateWithPriority(&sh->st_g, cudaStreamNonBlocking, prio_hi) != cudaSuccess) {
+      cudaStreamCreateWithPriority(&sh->st_g, cudaStreamNonBlocking, prio_hi) != cudaSuccess ||
+      cudaStreamCreateWithPriority(&sh->st_f, cudaStreamNonBlocking, prio_hi) != cudaSuccess) {
     ltephy_shard_destroy(sh);
     return fail(LTEPHY_ERROR, "shard_create: %s", r != ncclSuccess ? g_nccl.GetErrorString(r) : "stream creation failed");
   }
   *out = sh;
+  return LTEPHY_SUCCESS;
+}
+extern "C" int ltephy_shard_set_gather_capacity(ltephy_shard_t* sh, uint32_t bytes_per_subframe)
+{
+  if (!sh || bytes_per_subframe < 1024) return fail(LTEPHY_ERROR_INVALID_INPUTS, "shard_set_gather_capacity: bad arguments");
+  sh->gather_bytes_per_sf = (bytes_per_subframe + 15u) & ~15u;
   return LTEPHY_SUCCESS;
 }
 extern "C" void ltephy_shard_destroy(ltephy_shard_t* sh)
@@ -269,6 +274,8 @@ extern "C" void ltephy_shard_destroy(ltephy_shard_t* sh)
   }
   if (sh->comm_x) g_nccl.CommDestroy(sh->comm_x);
   if (sh->comm_g) g_nccl.CommDestroy(sh->comm_g);
+  if (sh->comm_f) g_nccl.CommDestroy(sh->comm_f);
+  if (sh->st_f) cudaStreamDestroy(sh->st_f);
   if (sh->st_x) cudaStreamDestroy(sh->st_x);
   if (sh->st_g) cudaStreamDestroy(sh->st_g);
   delete sh;
@@ -316,7 +323,7 @@ extern "C" int ltephy_decode_subframes_sharded(ltephy_shard_t* sh, ltephy_t* h, 
   if (!sh || !h || !s || !iq || !tti || !info || !dcis || !n_dcis || !tbs || n == 0) return fail(LTEPHY_ERROR_INVALID_INPUTS, "decode_subframes_sharded: bad arguments");
   const uint32_t W = sh->world, R = sh->rank;
   // the three ordered sections of this batch; the guards keep the order intact on every exit path
-  TurnGuard gx(sh->turn_x, seq), gw(sh->turn_w, seq), gg(sh->turn_g, seq);
+  TurnGuard gx(sh->turn_x, seq), gf(sh->turn_f, seq), gw(sh->turn_w, seq), gg(sh->turn_g, seq);
   if (sh->failed) return fail(LTEPHY_ERROR, "decode_subframes_sharded: an earlier batch failed on this rank");
   struct FailMark {
     ltephy_shard* sh;
@@ -342,42 +349,48 @@ extern "C" int ltephy_decode_subframes_sharded(ltephy_shard_t* sh, ltephy_t* h, 
   if (sl->d_offs_all.reserve((size_t)W * (n + 1)) || sl->h_offs_all.reserve((size_t)W * (n + 1)) || sl->d_pack_all.reserve(W * cap_rank) ||
       sl->h_pack_all.reserve(W * cap_rank))
     return fail(LTEPHY_ERROR, "allocation of the exchange buffers failed");
-  // ---- exchange turn -----------------------------------------------------------------------------------
+  // ---- exchange turn: the turn orders the two collectives of this batch among the batches in flight, nothing else.  Waiting for them
+  // (= for the slowest rank) and the copies to the host happen outside it, so a straggler delays its own batch only.
+  for (cudaEvent_t* e : {&sl->ev_x, &sl->ev_g, &sl->ev_msg})
+    if (!*e) CU(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
   gx.take();
   CU(cudaStreamWaitEvent(sh->st_x, sl->ev_pack, 0));
-  // two all-gathers back to back (offsets, then the records at their fixed per-rank capacity: 4.6 MB per 1000 subframes, a third of it used --
-  // NVLink does not notice, and no host round trip sits between the two collectives); only the used part of every rank's records goes to the host
+  // offsets, then the records at their fixed per-rank capacity (4.6 MB per 1000 subframes, a third of it used: NVLink does not notice, and
+  // no host round trip sits between the two collectives); only the used part of every rank's records goes to the host
   NC(g_nccl.AllGather(sl->d_offs.p, sl->d_offs_all.p, n + 1, ncclUint32, sh->comm_x, sh->st_x));
   NC(g_nccl.AllGather(sl->d_pack.p, sl->d_pack_all.p, cap_rank, ncclUint8, sh->comm_x, sh->st_x));
-  CU(cudaMemcpyAsync(sl->h_offs_all.p, sl->d_offs_all.p, (size_t)W * (n + 1) * 4, cudaMemcpyDeviceToHost, sh->st_x));
-  CU(cudaStreamSynchronize(sh->st_x));
+  CU(cudaEventRecord(sl->ev_x, sh->st_x));
+  gx.give();
+  CU(cudaStreamWaitEvent(h->stream, sl->ev_x, 0)); // the handle's stream is idle between phase A and phase B
+  CU(cudaMemcpyAsync(sl->h_offs_all.p, sl->d_offs_all.p, (size_t)W * (n + 1) * 4, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
   uint64_t exch = 0;
   for (uint32_t q = 0; q < W; q++) {
     const uint32_t bytes = sl->h_offs_all.p[(size_t)q * (n + 1) + n];
     if (bytes > cap_rank) return fail(LTEPHY_ERROR, "rank %u announced %u packed bytes for %u subframes", q, bytes, n);
     exch += bytes;
-    CU(cudaMemcpyAsync(sl->h_pack_all.p + q * cap_rank, sl->d_pack_all.p + q * cap_rank, bytes, cudaMemcpyDeviceToHost, sh->st_x));
+    CU(cudaMemcpyAsync(sl->h_pack_all.p + q * cap_rank, sl->d_pack_all.p + q * cap_rank, bytes, cudaMemcpyDeviceToHost, h->stream));
   }
-  CU(cudaStreamSynchronize(sh->st_x));
+  CU(cudaStreamSynchronize(h->stream));
   std::vector<const uint8_t*>       bufs(W);
   std::vector<const uint32_t*>      offs(W);
   std::vector<const ltephy_cand_t*> full;
   for (uint32_t q = 0; q < W; q++) bufs[q] = sl->h_pack_all.p + q * cap_rank, offs[q] = sl->h_offs_all.p + (size_t)q * (n + 1);
-  // The full tables are needed only for an overfull subframe or RAR-activated RNTIs; every rank sees the same records and
-  // the same history, so every rank takes this branch (a collective) or none does.
+  // The full tables are needed only for an overfull subframe or RAR-activated RNTIs; every rank sees the same records and the same
+  // history, so every rank fetches them (a collective on its own communicator, ordered by its own turn) or none does.
   const int need_full = ltephy_packed_needs_full_table(s, bufs.data(), offs.data(), W, n);
   if (need_full < 0) return need_full;
+  gf.take();
   if (need_full) {
     const size_t fb = (size_t)n * LTEPHY_MAX_LOC * LTEPHY_MAX_SIZES * sizeof(ltephy_cand_t);
     if (sl->d_full_all.reserve(W * fb) || sl->h_full_all.reserve(W * fb)) return fail(LTEPHY_ERROR, "allocation of the full-table exchange buffers failed");
-    CU(cudaStreamSynchronize(h->stream));
-    NC(g_nccl.AllGather(h->d_cands.p, sl->d_full_all.p, fb, ncclUint8, sh->comm_x, sh->st_x));
-    CU(cudaMemcpyAsync(sl->h_full_all.p, sl->d_full_all.p, W * fb, cudaMemcpyDeviceToHost, sh->st_x));
-    CU(cudaStreamSynchronize(sh->st_x));
+    NC(g_nccl.AllGather(h->d_cands.p, sl->d_full_all.p, fb, ncclUint8, sh->comm_f, sh->st_f));
+    CU(cudaMemcpyAsync(sl->h_full_all.p, sl->d_full_all.p, W * fb, cudaMemcpyDeviceToHost, sh->st_f));
+    CU(cudaStreamSynchronize(sh->st_f));
     full.resize(W);
     for (uint32_t q = 0; q < W; q++) full[q] = reinterpret_cast<const ltephy_cand_t*>(sl->h_full_all.p + q * fb);
   }
-  gx.give();
+  gf.give();
   t[3] = now_ms();
   // ---- walk turn -----------------------------------------------------------------------------------------
   gw.take();
@@ -395,6 +408,8 @@ extern "C" int ltephy_decode_subframes_sharded(ltephy_shard_t* sh, ltephy_t* h, 
   t[6] = now_ms();
   // ---- phase B (local) ----------------------------------------------------------------------------------------
   for (uint32_t i = 0; i < 2 * nd; i++) tbs[i] = ltephy_tb_result_t{};
+  const size_t cap_p = (size_t)n * sh->gather_bytes_per_sf; // fixed size of one rank's payload message
+  if (W > 1 && h->d_payload.reserve(cap_p + 16)) return fail(LTEPHY_ERROR, "device allocation failed");
   if ((r = ltephy_submit_grants(h, sl->grants.data(), ng))) return r;
   sl->res.assign(2 * (size_t)ng + 2, ltephy_tb_result_t{});
   if ((r = ltephy_get_phase_b(h, sl->res.data(), payload, payload_cap))) return r;
@@ -404,75 +419,87 @@ extern "C" int ltephy_decode_subframes_sharded(ltephy_shard_t* sh, ltephy_t* h, 
     own_bytes += sl->res[2 * gi].payload_len + sl->res[2 * gi + 1].payload_len;
   }
   t[7] = now_ms();
-  // ---- gather turn: the decoded transport blocks of every rank -> rank 0 -----------------------------------------------
-  gg.take();
+  // ---- gather: the decoded transport blocks of every rank -> rank 0.  Every rank sends two messages of FIXED size (header + per-slot
+  // records + result structs; the payload bytes), so no size has to be agreed on first and the turn holds nothing but the NCCL calls.
+  const size_t cap_m = 64 + (size_t)n * 64 * (sizeof(TbMeta) + sizeof(ltephy_tb_result_t)); // up to 32 grants (64 result slots) per subframe
   if (W > 1) {
-    if (!sl->ev_g) CU(cudaEventCreateWithFlags(&sl->ev_g, cudaEventDisableTiming));
     const size_t ntb = h->tbs.size();
-    if (sl->h_hdr.reserve(1) || sl->d_hdr.reserve(1) || sl->d_hdr_all.reserve(W) || sl->h_hdr_all.reserve(W) || sl->h_meta.reserve(2 * (size_t)ng + 1) ||
-        sl->d_meta.reserve(2 * (size_t)ng + 1))
-      return fail(LTEPHY_ERROR, "allocation of the gather buffers failed");
-    sl->h_hdr.p[0] = GatherHdr{ng, (uint32_t)ntb, (uint64_t)h->payload_bytes};
-    for (uint32_t j = 0; j < 2 * ng; j++) {
-      const uint32_t ti = h->tb_slot[j];
-      TbMeta&        m  = sl->h_meta.p[j];
-      m.grant_dci = sl->grant_dci[j / 2], m.tb_index = ti;
-      m.byte_off = ti != 0xFFFFFFFFu ? h->tbs[ti].byte_off : 0, m.nbytes = ti != 0xFFFFFFFFu ? h->tbs[ti].nbytes : 0;
-    }
-    ltephy_pull(h, sl->d_hdr.p, sl->h_hdr.p, sizeof(GatherHdr), sh->st_g);
-    if (R != 0 && ng) ltephy_pull(h, sl->d_meta.p, sl->h_meta.p, 2 * (size_t)ng * sizeof(TbMeta), sh->st_g);
-    NC(g_nccl.AllGather(sl->d_hdr.p, sl->d_hdr_all.p, sizeof(GatherHdr), ncclUint8, sh->comm_g, sh->st_g));
-    CU(cudaMemcpyAsync(sl->h_hdr_all.p, sl->d_hdr_all.p, W * sizeof(GatherHdr), cudaMemcpyDeviceToHost, sh->st_g));
-    CU(cudaStreamSynchronize(sh->st_g));
+    if (h->payload_bytes > cap_p)
+      return fail(LTEPHY_ERROR_INVALID_INPUTS, "%zu transport-block bytes in %u subframes exceed the gather capacity (ltephy_shard_set_gather_capacity)", h->payload_bytes, n);
+    if (64 + 2 * (size_t)ng * sizeof(TbMeta) + ntb * sizeof(ltephy_tb_result_t) > cap_m)
+      return fail(LTEPHY_ERROR_INVALID_INPUTS, "%u grants in %u subframes exceed the gather message", ng, n);
     if (R != 0) {
+      if (sl->h_msg.reserve(cap_m) || sl->d_msg.reserve(cap_m)) return fail(LTEPHY_ERROR, "allocation of the gather buffers failed");
+      GatherHdr gh{ng, (uint32_t)ntb, (uint64_t)h->payload_bytes};
+      memcpy(sl->h_msg.p, &gh, sizeof(gh));
+      TbMeta* hm = reinterpret_cast<TbMeta*>(sl->h_msg.p + 64);
+      for (uint32_t j = 0; j < 2 * ng; j++) {
+        const uint32_t ti = h->tb_slot[j];
+        hm[j].grant_dci = sl->grant_dci[j / 2], hm[j].tb_index = ti;
+        hm[j].byte_off = ti != 0xFFFFFFFFu ? h->tbs[ti].byte_off : 0, hm[j].nbytes = ti != 0xFFFFFFFFu ? h->tbs[ti].nbytes : 0;
+      }
+      const size_t mb = 64 + 2 * (size_t)ng * sizeof(TbMeta);
+      ltephy_pull(h, sl->d_msg.p, sl->h_msg.p, (mb + 15) & ~(size_t)15, h->stream);
+      if (ntb) CU(cudaMemcpyAsync(sl->d_msg.p + mb, h->d_res.p, ntb * sizeof(ltephy_tb_result_t), cudaMemcpyDeviceToDevice, h->stream));
+      CU(cudaEventRecord(sl->ev_msg, h->stream));
+      gg.take();
+      CU(cudaStreamWaitEvent(sh->st_g, sl->ev_msg, 0));
       NC(g_nccl.GroupStart());
-      if (ng) NC(g_nccl.Send(sl->d_meta.p, 2 * (size_t)ng * sizeof(TbMeta), ncclUint8, 0, sh->comm_g, sh->st_g));
-      if (ntb) NC(g_nccl.Send(h->d_res.p, ntb * sizeof(ltephy_tb_result_t), ncclUint8, 0, sh->comm_g, sh->st_g));
-      if (h->payload_bytes) NC(g_nccl.Send(h->d_payload.p, h->payload_bytes, ncclUint8, 0, sh->comm_g, sh->st_g));
+      NC(g_nccl.Send(sl->d_msg.p, cap_m, ncclUint8, 0, sh->comm_g, sh->st_g));
+      NC(g_nccl.Send(h->d_payload.p, cap_p, ncclUint8, 0, sh->comm_g, sh->st_g));
       NC(g_nccl.GroupEnd());
       CU(cudaEventRecord(sl->ev_g, sh->st_g));
-      gg.give();                              // the turn orders the NCCL calls only; waiting for them happens outside it
-      CU(cudaEventSynchronize(sl->ev_g));     // the handle's buffers are free for its next batch when this call returns
+      gg.give();
+      CU(cudaEventSynchronize(sl->ev_g)); // the handle's buffers are free for its next batch when this call returns
     } else {
-      size_t tm = 0, tr = 0, tp = 0;
-      for (uint32_t q = 1; q < W; q++) tm += 2 * (size_t)sl->h_hdr_all.p[q].ng, tr += sl->h_hdr_all.p[q].ntb, tp += (sl->h_hdr_all.p[q].payload_bytes + 15) & ~(size_t)15;
-      if (sl->d_g_meta.reserve(tm + 1) || sl->h_g_meta.reserve(tm + 1) || sl->d_g_res.reserve(tr + 1) || sl->h_g_res.reserve(tr + 1) || sl->d_g_payload.reserve(tp + 16))
+      if (sl->d_g_msg.reserve((W - 1) * cap_m) || sl->h_g_msg.reserve((W - 1) * cap_m) || sl->d_g_payload.reserve((W - 1) * cap_p + 16))
         return fail(LTEPHY_ERROR, "allocation of the gather buffers failed");
-      const size_t base0 = (own_bytes + 15) & ~(size_t)15;
-      if (base0 + tp > payload_cap) return fail(LTEPHY_ERROR_INVALID_INPUTS, "payload buffer too small for the gathered transport blocks (%zu needed)", base0 + tp);
+      gg.take();
       NC(g_nccl.GroupStart());
-      size_t om = 0, orr = 0, op = 0;
       for (uint32_t q = 1; q < W; q++) {
-        const GatherHdr& gh = sl->h_hdr_all.p[q];
-        if (gh.ng) NC(g_nccl.Recv(sl->d_g_meta.p + om, 2 * (size_t)gh.ng * sizeof(TbMeta), ncclUint8, (int)q, sh->comm_g, sh->st_g));
-        if (gh.ntb) NC(g_nccl.Recv(sl->d_g_res.p + orr, (size_t)gh.ntb * sizeof(ltephy_tb_result_t), ncclUint8, (int)q, sh->comm_g, sh->st_g));
-        if (gh.payload_bytes) NC(g_nccl.Recv(sl->d_g_payload.p + op, gh.payload_bytes, ncclUint8, (int)q, sh->comm_g, sh->st_g));
-        om += 2 * (size_t)gh.ng, orr += gh.ntb, op += (gh.payload_bytes + 15) & ~(size_t)15;
+        NC(g_nccl.Recv(sl->d_g_msg.p + (q - 1) * cap_m, cap_m, ncclUint8, (int)q, sh->comm_g, sh->st_g));
+        NC(g_nccl.Recv(sl->d_g_payload.p + (q - 1) * cap_p, cap_p, ncclUint8, (int)q, sh->comm_g, sh->st_g));
       }
       NC(g_nccl.GroupEnd());
       CU(cudaEventRecord(sl->ev_g, sh->st_g));
-      gg.give(); // the copies to the host (the bulk of the time when `payload` is pageable memory) run on this handle's stream, outside the turn
+      gg.give();
+      // host side, outside the turn: headers first, then exactly the used part of every rank's records and bytes
       CU(cudaStreamWaitEvent(h->stream, sl->ev_g, 0));
-      if (tm) CU(cudaMemcpyAsync(sl->h_g_meta.p, sl->d_g_meta.p, tm * sizeof(TbMeta), cudaMemcpyDeviceToHost, h->stream));
-      if (tr) CU(cudaMemcpyAsync(sl->h_g_res.p, sl->d_g_res.p, tr * sizeof(ltephy_tb_result_t), cudaMemcpyDeviceToHost, h->stream));
-      if (tp) CU(cudaMemcpyAsync(payload + base0, sl->d_g_payload.p, tp, cudaMemcpyDeviceToHost, h->stream));
+      CU(cudaMemcpy2DAsync(sl->h_g_msg.p, cap_m, sl->d_g_msg.p, cap_m, 64, W - 1, cudaMemcpyDeviceToHost, h->stream));
       CU(cudaStreamSynchronize(h->stream));
-      om = 0, orr = 0, op = 0;
+      const size_t base0 = (own_bytes + 15) & ~(size_t)15;
+      size_t       tp    = 0;
       for (uint32_t q = 1; q < W; q++) {
-        const GatherHdr& gh = sl->h_hdr_all.p[q];
+        GatherHdr gh;
+        memcpy(&gh, sl->h_g_msg.p + (q - 1) * cap_m, sizeof(gh));
+        const size_t mb = 2 * (size_t)gh.ng * sizeof(TbMeta) + (size_t)gh.ntb * sizeof(ltephy_tb_result_t);
+        if (64 + mb > cap_m || gh.payload_bytes > cap_p) return fail(LTEPHY_ERROR, "rank %u sent an inconsistent gather header", q);
+        if (base0 + tp + gh.payload_bytes > payload_cap)
+          return fail(LTEPHY_ERROR_INVALID_INPUTS, "payload buffer too small for the gathered transport blocks (%zu needed)", base0 + tp + (size_t)gh.payload_bytes);
+        if (mb) CU(cudaMemcpyAsync(sl->h_g_msg.p + (q - 1) * cap_m + 64, sl->d_g_msg.p + (q - 1) * cap_m + 64, mb, cudaMemcpyDeviceToHost, h->stream));
+        if (gh.payload_bytes) CU(cudaMemcpyAsync(payload + base0 + tp, sl->d_g_payload.p + (q - 1) * cap_p, gh.payload_bytes, cudaMemcpyDeviceToHost, h->stream));
+        tp += (gh.payload_bytes + 15) & ~(size_t)15;
+      }
+      CU(cudaStreamSynchronize(h->stream));
+      size_t op = 0;
+      for (uint32_t q = 1; q < W; q++) {
+        GatherHdr gh;
+        memcpy(&gh, sl->h_g_msg.p + (q - 1) * cap_m, sizeof(gh));
+        const TbMeta*             gm = reinterpret_cast<const TbMeta*>(sl->h_g_msg.p + (q - 1) * cap_m + 64);
+        const ltephy_tb_result_t* gr = reinterpret_cast<const ltephy_tb_result_t*>(sl->h_g_msg.p + (q - 1) * cap_m + 64 + 2 * (size_t)gh.ng * sizeof(TbMeta));
         for (uint32_t gi = 0; gi < gh.ng; gi++) {
           ltephy_tb_result_t rr[2] = {ltephy_tb_result_t{}, ltephy_tb_result_t{}};
           for (int tbi = 0; tbi < 2; tbi++) {
-            const TbMeta& m = sl->h_g_meta.p[om + 2 * gi + tbi];
+            const TbMeta& m = gm[2 * gi + tbi];
             if (m.tb_index == 0xFFFFFFFFu || m.tb_index >= gh.ntb) continue;
-            rr[tbi]             = sl->h_g_res.p[orr + m.tb_index];
+            rr[tbi]             = gr[m.tb_index];
             rr[tbi].payload_off = (uint32_t)(base0 + op + m.byte_off);
             rr[tbi].payload_len = m.nbytes;
           }
-          const uint32_t gd = sl->h_g_meta.p[om + 2 * gi].grant_dci;
+          const uint32_t gd = gm[2 * gi].grant_dci;
           if ((gd & ~LTEPHY_GRANT_ALT_TABLE) < nd) ltephy_place_grant_result(tbs, gd, rr[0], rr[1]);
         }
-        om += 2 * (size_t)gh.ng, orr += gh.ntb, op += (gh.payload_bytes + 15) & ~(size_t)15;
+        op += (gh.payload_bytes + 15) & ~(size_t)15;
       }
     }
   }
