@@ -10,9 +10,13 @@
 #include <cstdio>
 #include <cstring>
 #include <map>
+#include <mutex>
 #include <string>
 #include <tuple>
 #include <vector>
+
+static std::mutex  g_h2d_mtx;
+static cudaEvent_t g_h2d_last[64]; // per device: completion of the most recently issued sample upload (phase_a_common)
 
 extern "C" {
 void launch_frontend(const DevCell&, const float2*, float2*, float2*, float*, DevSfInfo*, uint32_t, cudaStream_t, uint64_t*);
@@ -100,6 +104,7 @@ extern "C" int ltephy_create(const ltephy_cfg_t* cfg, ltephy_t** out)
   h->segm_fast.assign(110000 / 8, ltehost::Segm{});
   CU(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
   for (auto& e : h->ev) CU(cudaEventCreate(&e));
+  CU(cudaEventCreateWithFlags(&h->ev_h2d, cudaEventDisableTiming));
   for (auto& e : h->mark) CU(cudaEventCreate(&e));
 
   DevCell& c = h->dc;
@@ -243,6 +248,11 @@ extern "C" void ltephy_destroy(ltephy_t* h)
     if (e) cudaEventDestroy(e);
   for (auto& e : h->mark)
     if (e) cudaEventDestroy(e);
+  if (h->ev_h2d) {
+    std::lock_guard<std::mutex> lk(g_h2d_mtx);
+    if (g_h2d_last[h->cfg.device & 63] == h->ev_h2d) g_h2d_last[h->cfg.device & 63] = nullptr;
+    cudaEventDestroy(h->ev_h2d);
+  }
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
 }
@@ -306,7 +316,16 @@ static int phase_a_common(ltephy* h, const float2* iq_dev, const float2* iq_host
   }
   pull(h, h->d_info.p, h->h_info.p, n * sizeof(DevSfInfo));
   const DevCell& c = h->dc;
-  if (iq_host) CU(cudaMemcpyAsync(h->d_iq.p, iq_host, (size_t)n * c.nof_rx * c.sf_len * sizeof(float2), cudaMemcpyHostToDevice, h->stream));
+  if (iq_host) {
+    // Host-to-device copies of different handles are chained (each waits for the one issued before it on this device): the copy engine would
+    // otherwise interleave them, and every batch would get its samples late instead of the first one getting them at full PCIe rate.
+    std::lock_guard<std::mutex> lk(g_h2d_mtx);
+    cudaEvent_t& last = g_h2d_last[h->cfg.device & 63];
+    if (last && last != h->ev_h2d) CU(cudaStreamWaitEvent(h->stream, last, 0));
+    CU(cudaMemcpyAsync(h->d_iq.p, iq_host, (size_t)n * c.nof_rx * c.sf_len * sizeof(float2), cudaMemcpyHostToDevice, h->stream));
+    CU(cudaEventRecord(h->ev_h2d, h->stream));
+    last = h->ev_h2d;
+  }
   launch_frontend(c, iq_dev, h->d_sym.p, h->d_ce.p, h->d_llr.p, h->d_info.p, n, h->stream, &h->launches);
   launch_viterbi(c, h->d_llr.p, h->d_info.p, h->d_cands.p, n, h->stream, &h->launches);
   launch_compact(c, h->d_info.p, h->d_cands.p, h->d_compact.p, n, h->stream, &h->launches);

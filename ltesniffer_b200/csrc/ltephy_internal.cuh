@@ -87,7 +87,7 @@ struct ltephy {
   ltehost::SizeTable st;
   DevCell            dc{};
   cudaStream_t       stream = nullptr;
-  cudaEvent_t        ev[6]{}, mark[2]{};
+  cudaEvent_t        ev[6]{}, mark[2]{}, ev_h2d = nullptr;
   std::vector<void*> tables; // device tables freed at destroy
   uint64_t           launches = 0;
 
