@@ -125,8 +125,16 @@ typedef struct {
     uint8_t enabled;
     uint8_t cw_idx;         /* srsran_ra_tb_t.cw_idx (dl_sniffer_pdsch.c:24): codeword this TB travels on -- 1 for TB 1 and 0 for TB 2 when both are
                                enabled and the DCI 2/2A swap flag is set, otherwise the TB's rank among the enabled ones */
+    uint8_t  harq_op;       /* LTEPHY_HARQ_*: what pdsch_cfg->softbuffers.rx[t] is at DL_Sniffer_PDSCH.cc:955-985 */
+    uint8_t  pad[3];
+    uint32_t harq_slot;     /* slot of the HARQ store (ltephy_harq_reserve) for LTEPHY_HARQ_NEW / _RETX */
   } tb[2];
 } ltephy_grant_t;
+/* HARQ soft-combining store (reference src/src/HARQ.cc:71-151, the -h mode): per-slot int16 accumulators of the rate-dematcher in HBM */
+#define LTEPHY_HARQ_NONE 0  /* scratch buffer, reset (srsran_softbuffer_rx_reset_tbs on buffer[i]) */
+#define LTEPHY_HARQ_NEW  1  /* the slot is overwritten with this transmission (getHARQBuffer + reset_tbs) */
+#define LTEPHY_HARQ_RETX 2  /* this transmission is added to the slot (getHARQBuffer, no reset) */
+#define LTEPHY_HARQ_SLOT_BYTES (16u * 18448u * 2u) /* one transport block: up to 16 code blocks of 3 x 6148 values (+ padding) */
 
 typedef struct {
   uint8_t  crc;             /* srsran_pdsch_res_t.crc */
@@ -191,6 +199,9 @@ int ltephy_get_phase_b(ltephy_t* h, ltephy_tb_result_t* results, uint8_t* payloa
  * sum_{j<i} ((tbs_j/8 + 6) & ~3), followed by its 3 CRC bytes) into dst_dev, for a collective without a host round trip
  * (the "single NCCL gather of decoded transport blocks").  Blocks until the copy is done. */
 int ltephy_copy_phase_b_device(ltephy_t* h, void* dst_dev, size_t cap, size_t* nbytes);
+
+/* nslots HARQ slots of LTEPHY_HARQ_SLOT_BYTES each (150 RNTIs x 8 processes x 2 TBs = 2400 slots = 1.4 GB); contents survive across batches */
+int ltephy_harq_reserve(ltephy_t* h, uint32_t nslots);
 
 /* ---- uplink: PUSCH (PUSCH_Decoder::decode / decode_run, src/src/UL_Sniffer_PUSCH.cc:250-263,389-392) ------------ */
 typedef struct {

@@ -100,6 +100,21 @@ int      ltephy_search_rnti_is_evergreen(const ltephy_search_t* s, uint16_t rnti
 int ltephy_dci_to_grant(const ltephy_search_t* s, const ltephy_dci_t* dci, uint32_t sf_idx, uint32_t cfi, int use_256qam_table, ltephy_grant_t* grant,
                         ltephy_dci_fields_t* fields);
 
+/* ---- HARQ bookkeeping (host): the decisions of HARQ::is_retransmission / updateHARQRNTI (reference src/src/HARQ.cc:71-188) -------------- */
+typedef struct ltephy_harq ltephy_harq_t;
+#define LTEPHY_HARQ_NEW_TX 0      /* DL_SNIFFER_NEW_TX */
+#define LTEPHY_HARQ_RE_TX 1       /* DL_SNIFFER_RE_TX */
+#define LTEPHY_HARQ_FULL_BUFFER 2 /* DL_SNIFFER_HARQ_FULL_BUFFER: no entity left for this RNTI, decode without a store */
+#define LTEPHY_HARQ_DECODED 3     /* DL_SNIFFER_DECODED: the block was already decoded, the reference disables the TB */
+ltephy_harq_t* ltephy_harq_create(uint32_t max_rnti); /* DL_SNIFFER_MAX_HARQ_SIZE = 150 in the reference */
+void           ltephy_harq_destroy(ltephy_harq_t* q);
+/* classification of transport block tb (0 / 1) of a C-RNTI DCI seen at tti; *slot = (entity * 8 + pid) * 2 + tb for NEW_TX / RE_TX */
+int ltephy_harq_classify(ltephy_harq_t* q, uint16_t rnti, uint32_t pid, uint32_t tb, uint32_t ndi, int32_t tbs, uint32_t tti, uint32_t* slot);
+/* after the decode (only for NEW_TX / RE_TX, as at DL_Sniffer_PDSCH.cc:1015-1018) */
+void ltephy_harq_update(ltephy_harq_t* q, uint16_t rnti, uint32_t pid, uint32_t tb, uint32_t ndi, uint32_t rv, int32_t tbs, uint32_t tti, int decoded);
+/* classify + fill grant->tb[t].harq_op / harq_slot of a C-RNTI grant from its DCI fields; DECODED disables the TB as the reference does */
+int ltephy_harq_prepare_grant(ltephy_harq_t* q, const ltephy_dci_fields_t* f, uint32_t tti, ltephy_grant_t* grant, int status[2]);
+
 /* DCI format 0 -> PUSCH grant (srsran_ra_ul_dci_to_grant as used at falcon_dci.c:222, and ulsniffer_ra_ul_dci_to_grant_256,
  * lib/src/phy/falcon_phch/ul_sniffer_pusch.c:138-172; no hopping).  enable_64qam selects the MCS interpretation, i.e. one of the
  * three attempts of PUSCH_Decoder::decode (src/src/UL_Sniffer_PUSCH.cc:498-521): 0 = Table 8.6.1-1 capped at 16QAM, 1 = Table

@@ -32,7 +32,8 @@ class Cand(C.Structure):
 
 
 class GrantTb(C.Structure):
-    _fields_ = [("tbs", C.c_int32), ("qm", C.c_uint8), ("rv", C.c_uint8), ("enabled", C.c_uint8), ("cw_idx", C.c_uint8)]
+    _fields_ = [("tbs", C.c_int32), ("qm", C.c_uint8), ("rv", C.c_uint8), ("enabled", C.c_uint8), ("cw_idx", C.c_uint8),
+                ("harq_op", C.c_uint8), ("pad", C.c_uint8 * 3), ("harq_slot", C.c_uint32)]
 
 
 class Grant(C.Structure):
@@ -59,6 +60,9 @@ class UlChest(C.Structure):
 
 
 TAP_UL_SYM = 5
+HARQ_NONE, HARQ_NEW, HARQ_RETX = 0, 1, 2            # grant.tb[t].harq_op
+HARQ_NEW_TX, HARQ_RE_TX, HARQ_FULL_BUFFER, HARQ_DECODED = 0, 1, 2, 3   # ltephy_harq_classify
+HARQ_SLOT_BYTES = 16 * 18448 * 2
 UL_FLAG_SLOT1 = 1
 CAND_DTYPE = np.dtype([("bits", "<u8"), ("rnti", "<u2"), ("valid", "u1"), ("pad", "u1", 5)])
 assert CAND_DTYPE.itemsize == C.sizeof(Cand) == 16
@@ -194,6 +198,10 @@ class LtePhy:
         comp = np.zeros(self.n, COMPACT_DTYPE)
         self._chk(self.L.ltephy_get_phase_a_compact(self.h, info, _p(comp)), "get_phase_a_compact")
         return info, comp
+
+    def harq_reserve(self, nslots):
+        self.L.ltephy_harq_reserve.argtypes = [C.c_void_p, C.c_uint32]
+        self._chk(self.L.ltephy_harq_reserve(self.h, nslots), "harq_reserve")
 
     def tap(self, what, shape, dtype):
         out = np.zeros(shape, dtype)
@@ -501,6 +509,34 @@ def search_batch_packed(search, bufs, offs, n, max_dcis, full=None):
     if r != 0:
         raise RuntimeError("ltephy_search_batch_packed failed (%d)" % r)
     return dcis[:nd.value].copy(), tc
+
+
+class Harq:
+    """host bookkeeping of the HARQ mode (ltephy_harq_*, include/ltephy_search.h): slot numbers and NEW_TX / RE_TX / DECODED decisions"""
+
+    def __init__(self, max_rnti=150):
+        self.L = load_library()
+        L = self.L
+        L.ltephy_harq_create.restype = C.c_void_p
+        L.ltephy_harq_create.argtypes = [C.c_uint32]
+        L.ltephy_harq_destroy.argtypes = [C.c_void_p]
+        L.ltephy_harq_classify.argtypes = [C.c_void_p, C.c_uint16, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int32, C.c_uint32, C.POINTER(C.c_uint32)]
+        L.ltephy_harq_update.argtypes = [C.c_void_p, C.c_uint16, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int32, C.c_uint32, C.c_int]
+        self.h = L.ltephy_harq_create(max_rnti)
+        assert self.h
+
+    def classify(self, rnti, pid, tb, ndi, tbs, tti):
+        slot = C.c_uint32(0)
+        r = self.L.ltephy_harq_classify(self.h, rnti, pid, tb, ndi, tbs, tti, C.byref(slot))
+        return r, slot.value
+
+    def update(self, rnti, pid, tb, ndi, rv, tbs, tti, decoded):
+        self.L.ltephy_harq_update(self.h, rnti, pid, tb, ndi, rv, tbs, tti, 1 if decoded else 0)
+
+    def close(self):
+        if self.h:
+            self.L.ltephy_harq_destroy(self.h)
+            self.h = None
 
 
 def _prefer_torch_nccl():

@@ -76,6 +76,9 @@ struct DevCb {             // one code block
   uint32_t rm_nn;
   uint32_t shift;          // conditioning shift from Qm
   uint32_t pair, half;     // turbo job and 16-bit lane it occupies
+  uint32_t harq_op;        // LTEPHY_HARQ_*: 0 none, 1 overwrite the store, 2 add to it
+  uint32_t harq_off;       // int16 offset of this code block's accumulators in the HARQ store
+  uint32_t harq_gen;       // 0: first use of the slot in this batch, 1: second, ... (one rate-dematch launch per generation)
 };
 
 struct DevPair {           // turbo job: up to two code blocks of equal K decoded by one CTA

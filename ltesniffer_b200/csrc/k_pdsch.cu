@@ -149,9 +149,10 @@ __device__ __forceinline__ int sat16(int v) { return v > 32767 ? 32767 : (v < -3
 
 __global__ void __launch_bounds__(256) rm_turbo_rx_kernel(const DevCb* __restrict__ cbs, const DevPair* __restrict__ pairs,
                                                           const short* __restrict__ llr_pool, const uint32_t* __restrict__ rm_pool,
-                                                          uint32_t* __restrict__ turbo_pool)
+                                                          uint32_t* __restrict__ turbo_pool, short* __restrict__ harq_pool, uint32_t gen)
 {
   const DevCb     cb = cbs[blockIdx.x];
+  if (cb.harq_gen != gen) return;
   const DevPair&  pr = pairs[cb.pair];
   const uint32_t  NW = pr.NW;
   const bool      alone = pr.ncb == 1;
@@ -159,12 +160,16 @@ __global__ void __launch_bounds__(256) rm_turbo_rx_kernel(const DevCb* __restric
   const uint32_t* ord = rm_pool + cb.rm_tab;
   uint32_t*       bw  = turbo_pool + pr.buf_off;
   short*          bh  = reinterpret_cast<short*>(bw);
+  // HARQ store (reference src/src/HARQ.cc, DL_Sniffer_PDSCH.cc:955-985): the accumulators of this code block live at the pair-buffer word index,
+  // which does not depend on the redundancy version; a retransmission starts from what earlier transmissions left there
+  short* hq = cb.harq_op ? harq_pool + cb.harq_off : nullptr;
   for (uint32_t k = threadIdx.x; k < cb.rm_nn; k += blockDim.x) {
-    int acc = 0;
+    const uint32_t w = ord[k];
+    int            acc = cb.harq_op == LTEPHY_HARQ_RETX ? (int)hq[w] : 0;
     for (uint32_t kk = k; kk < cb.E; kk += cb.rm_nn) acc = sat16(acc + (int)e[kk]);
+    if (hq) hq[w] = (short)acc;
     int v = acc >> cb.shift;
     v     = v > 255 ? 255 : (v < -255 ? -255 : v);
-    const uint32_t w = ord[k];
     if (alone)
       bw[w] = (uint32_t)v & 0xFFFFu;
     else
@@ -190,9 +195,9 @@ extern "C" void launch_pdsch_front(const DevCell& c, const DevGrant* grants, uin
   *launches += 2;
 }
 extern "C" void launch_rm_turbo_rx(const DevCb* cbs, uint32_t ncb, const DevPair* pairs, const short* llr_pool, const uint32_t* rm_pool,
-                                   uint32_t* turbo_pool, cudaStream_t st, uint64_t* launches)
+                                   uint32_t* turbo_pool, short* harq_pool, uint32_t gen, cudaStream_t st, uint64_t* launches)
 {
   if (!ncb) return;
-  rm_turbo_rx_kernel<<<ncb, 256, 0, st>>>(cbs, pairs, llr_pool, rm_pool, turbo_pool);
+  rm_turbo_rx_kernel<<<ncb, 256, 0, st>>>(cbs, pairs, llr_pool, rm_pool, turbo_pool, harq_pool, gen);
   *launches += 1;
 }

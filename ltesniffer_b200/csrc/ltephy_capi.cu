@@ -24,7 +24,7 @@ void launch_viterbi(const DevCell&, const float*, const DevSfInfo*, ltephy_cand_
 void launch_compact(const DevCell&, const DevSfInfo*, const ltephy_cand_t*, ltephy_compact_t*, uint32_t, cudaStream_t, uint64_t*);
 void launch_pdsch_front(const DevCell&, const DevGrant*, uint32_t, uint32_t, const float2*, const float2*, const uint32_t*, const uint32_t*, uint32_t,
                         uint32_t*, short*, cudaStream_t, uint64_t*);
-void launch_rm_turbo_rx(const DevCb*, uint32_t, const DevPair*, const short*, const uint32_t*, uint32_t*, cudaStream_t, uint64_t*);
+void launch_rm_turbo_rx(const DevCb*, uint32_t, const DevPair*, const short*, const uint32_t*, uint32_t*, short*, uint32_t, cudaStream_t, uint64_t*);
 void launch_turbo(const DevPair*, uint32_t, uint32_t, int, uint32_t*, const uint32_t*, uint32_t*, size_t, const uint16_t*, const uint32_t*,
                   const uint32_t*, const uint32_t*, uint8_t*, uint8_t*, uint8_t*, uint32_t, cudaStream_t, uint64_t*);
 void launch_tb_crc(const DevTb*, uint32_t, const uint8_t*, const uint8_t*, const uint8_t*, const uint32_t*, ltephy_tb_result_t*, cudaStream_t,
@@ -241,7 +241,7 @@ extern "C" void ltephy_destroy(ltephy_t* h)
   h->d_iq.release(), h->d_sym.release(), h->d_ce.release(), h->d_llr.release(), h->d_info.release(), h->d_cands.release();
   h->h_info.release(), h->d_compact.release(), h->h_compact.release(), h->d_grants.release(), h->d_cbs.release(), h->d_pairs.release(), h->d_tbs.release(), h->d_pair_pi_off.release();
   h->d_tscratch.release(), h->d_tqueue.release();
-  h->d_seq.release(), h->d_rm.release(), h->d_turbo.release(), h->d_pllr.release(), h->d_pi.release(), h->d_payload.release();
+  h->d_seq.release(), h->d_rm.release(), h->d_turbo.release(), h->d_pllr.release(), h->d_pi.release(), h->d_payload.release(), h->d_harq.release();
   h->d_cb_iters.release(), h->d_cb_crc.release(), h->d_res.release(), h->h_res.release(), h->h_payload.release(), h->h_stage.release();
   h->d_uliq.release(), h->d_ulsym.release(), h->d_ulpool.release(), h->d_ulgrants.release(), h->d_ulchest.release(), h->h_ulchest.release();
   for (auto& e : h->ev)
@@ -480,11 +480,18 @@ static int pi_table_for(ltephy* h, uint32_t K, uint32_t& off)
 
 // transport block -> code blocks -> turbo pairs (shared by the PDSCH and PUSCH paths)
 static int add_transport_block(ltephy* h, uint32_t tbs, uint32_t G, uint32_t qm, uint32_t rv, uint32_t NL, uint32_t llr_off, int32_t* open_pair,
-                               size_t& turbo_words, uint32_t& tb_index)
+                               size_t& turbo_words, uint32_t& tb_index, uint32_t harq_op = LTEPHY_HARQ_NONE, uint32_t harq_slot = 0)
 {
   if (tbs / 8 >= h->segm_fast.size() || (tbs & 7)) return fail(LTEPHY_ERROR_INVALID_INPUTS, "invalid TBS %u", tbs);
   if (h->segm_fast[tbs / 8].C == 0 && !ltehost::cb_segmentation(tbs, h->segm_fast[tbs / 8])) return fail(LTEPHY_ERROR_INVALID_INPUTS, "invalid TBS %u", tbs);
   const ltehost::Segm& s = h->segm_fast[tbs / 8];
+  uint32_t             harq_gen = 0;
+  if (harq_op != LTEPHY_HARQ_NONE) {
+    if (harq_op > LTEPHY_HARQ_RETX || harq_slot >= h->harq_slots) return fail(LTEPHY_ERROR_INVALID_INPUTS, "HARQ slot %u outside the store (%u slots, ltephy_harq_reserve)", harq_slot, h->harq_slots);
+    if (s.C > 16) return fail(LTEPHY_ERROR_INVALID_INPUTS, "transport block of %u code blocks does not fit a HARQ slot", s.C);
+    harq_gen        = h->harq_uses[harq_slot]++; // a slot used again inside one batch: its rate-dematch runs in a later launch, after the earlier use
+    h->harq_max_gen = std::max(h->harq_max_gen, harq_gen);
+  }
   DevTb                tb{};
   tb.byte_off = (uint32_t)h->payload_bytes, tb.nbytes = tbs / 8, tb.cb_first = (uint32_t)h->cbs.size(), tb.ncb = s.C;
   h->payload_bytes += (tb.nbytes + 3 + 3) & ~3u;
@@ -495,6 +502,7 @@ static int add_transport_block(ltephy* h, uint32_t tbs, uint32_t G, uint32_t qm,
     cb.llr_off = rp;
     rp += cb.E;
     cb.shift = qm == 2 ? 0 : qm == 4 ? 1 : 2;
+    cb.harq_op = harq_op, cb.harq_off = harq_op ? (uint32_t)((size_t)harq_slot * (LTEPHY_HARQ_SLOT_BYTES / 2) + (size_t)r * 18448u) : 0u, cb.harq_gen = harq_gen;
     if (rm_table_for(h, cb.K, cb.F, rv, cb.rm_tab, cb.rm_nn)) return fail(LTEPHY_ERROR, "rate-matching table upload failed");
     const int kq = lte_qpp_index_ge(cb.K);
     uint32_t  pi;
@@ -537,7 +545,7 @@ static int build_jobs(ltephy* h, const ltephy_grant_t* gin, uint32_t n, size_t& 
 {
   const DevCell& c = h->dc;
   const uint32_t N = c.nof_prb;
-  h->grants.clear(), h->cbs.clear(), h->pairs.clear(), h->tbs.clear(), h->pair_pi_off.clear();
+  h->grants.clear(), h->cbs.clear(), h->pairs.clear(), h->tbs.clear(), h->pair_pi_off.clear(), h->harq_uses.clear(), h->harq_max_gen = 0;
   h->tb_slot.assign((size_t)n * 2, 0xFFFFFFFFu);
   h->pllr_elems = 0, h->payload_bytes = 0;
   seq_words = 0, turbo_words = 0, max_scr_words = 0;
@@ -604,7 +612,8 @@ static int build_jobs(ltephy* h, const ltephy_grant_t* gin, uint32_t n, size_t& 
       h->pllr_elems += (G + 7) & ~7u;
       if (g.tb[t].tbs > 0) {
         uint32_t tbi;
-        int r = add_transport_block(h, (uint32_t)g.tb[t].tbs, G, qm, g.tb[t].rv, g.tx_scheme == LTEPHY_TX_DIVERSITY ? 2 : 1, d.llr_off[cw], open_pair, turbo_words, tbi);
+        int r = add_transport_block(h, (uint32_t)g.tb[t].tbs, G, qm, g.tb[t].rv, g.tx_scheme == LTEPHY_TX_DIVERSITY ? 2 : 1, d.llr_off[cw], open_pair, turbo_words, tbi,
+                                    g.tb[t].harq_op, g.tb[t].harq_slot);
         if (r) return r;
         h->tb_slot[(size_t)gi * 2 + t] = tbi;
       }
@@ -643,7 +652,8 @@ static int run_turbo_stage(ltephy* h, uint32_t max_iter)
   stage_and_pull(h, h->d_pairs.p, h->pairs.data(), h->pairs.size() * sizeof(DevPair));
   stage_and_pull(h, h->d_pair_pi_off.p, h->pair_pi_off.data(), h->pairs.size() * 4);
   stage_and_pull(h, h->d_cbs.p, h->cbs.data(), h->cbs.size() * sizeof(DevCb));
-  launch_rm_turbo_rx(h->d_cbs.p, (uint32_t)h->cbs.size(), h->d_pairs.p, h->d_pllr.p, h->d_rm.p, h->d_turbo.p, h->stream, &h->launches);
+  for (uint32_t gen = 0; gen <= h->harq_max_gen; gen++) // one launch unless a HARQ slot is used more than once in this batch
+    launch_rm_turbo_rx(h->d_cbs.p, (uint32_t)h->cbs.size(), h->d_pairs.p, h->d_pllr.p, h->d_rm.p, h->d_turbo.p, h->d_harq.p, gen, h->stream, &h->launches);
   if (ltephy_turbo_scratch(h)) return fail(LTEPHY_ERROR, "device allocation failed");
   CU(cudaMemsetAsync(h->d_tqueue.p, 0, 16 * sizeof(uint32_t), h->stream));
   CU(cudaEventRecord(h->ev[4], h->stream));
@@ -738,6 +748,19 @@ extern "C" int ltephy_get_phase_b(ltephy_t* h, ltephy_tb_result_t* results, uint
 }
 
 
+// ---------------------------------------------------------------------------------------- HARQ store
+extern "C" int ltephy_harq_reserve(ltephy_t* h, uint32_t nslots)
+{
+  if (!h || nslots == 0) return fail(LTEPHY_ERROR_INVALID_INPUTS, "harq_reserve: bad arguments");
+  CU(cudaSetDevice(h->cfg.device));
+  CU(cudaStreamSynchronize(h->stream));
+  const size_t words = (size_t)nslots * (LTEPHY_HARQ_SLOT_BYTES / 2);
+  if (h->d_harq.reserve(words)) return fail(LTEPHY_ERROR, "harq_reserve: %zu bytes of device memory not available", words * 2);
+  CU(cudaMemsetAsync(h->d_harq.p, 0, words * 2, h->stream));
+  h->harq_slots = nslots;
+  return LTEPHY_SUCCESS;
+}
+
 // ---------------------------------------------------------------------------------------- uplink (PUSCH)
 extern "C" int ltephy_set_ul_cfg(ltephy_t* h, const ltephy_ul_cfg_t* cfg)
 {
@@ -827,7 +850,7 @@ extern "C" int ltephy_submit_ul(ltephy_t* h, const float* iq_ul, const uint32_t*
   }
   h->n_ul = n;
   // jobs
-  h->ulgrants.clear(), h->cbs.clear(), h->pairs.clear(), h->tbs.clear(), h->pair_pi_off.clear();
+  h->ulgrants.clear(), h->cbs.clear(), h->pairs.clear(), h->tbs.clear(), h->pair_pi_off.clear(), h->harq_uses.clear(), h->harq_max_gen = 0;
   h->tb_slot.assign((size_t)ng, 0xFFFFFFFFu);
   h->pllr_elems = 0, h->payload_bytes = 0;
   size_t   seq_words = 0, turbo_words = 0;
@@ -976,7 +999,7 @@ extern "C" int ltephy_turbo_batch(ltephy_t* h, const int16_t* d, uint32_t K, uin
   CU(cudaSetDevice(h->cfg.device));
   const uint32_t NW = (K + 31) / 32, D = K + 4, npairs = (ncb + 1) / 2;
   const size_t   pw = ltephy_pair_words(NW); // words per pair
-  h->pairs.clear(), h->pair_pi_off.clear(), h->cbs.clear(), h->tbs.clear();
+  h->pairs.clear(), h->pair_pi_off.clear(), h->cbs.clear(), h->tbs.clear(), h->harq_uses.clear(), h->harq_max_gen = 0;
   uint32_t po;
   if (pi_table_for(h, K, po)) return fail(LTEPHY_ERROR, "interleaver table upload failed");
   std::vector<uint32_t> pool(pw * npairs, 0u);

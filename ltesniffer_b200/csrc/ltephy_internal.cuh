@@ -88,6 +88,9 @@ struct ltephy {
   DevCell            dc{};
   cudaStream_t       stream = nullptr;
   cudaEvent_t        ev[6]{}, mark[2]{}, ev_h2d = nullptr;
+  DevBuf<short>      d_harq;                 // HARQ store: harq_slots x LTEPHY_HARQ_SLOT_BYTES
+  uint32_t           harq_slots = 0, harq_max_gen = 0;
+  std::map<uint32_t, uint32_t> harq_uses;    // slot -> uses in the batch being built
   std::vector<void*> tables; // device tables freed at destroy
   uint64_t           launches = 0;
 

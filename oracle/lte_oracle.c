@@ -614,11 +614,16 @@ int lteo_pdsch_llr(lteo_t* q, uint32_t sf_idx, uint32_t cfi, uint16_t rnti, cons
  * (N_cb = K_w), then de-interleave to the three streams; turbo input conditioning
  * v = clamp(w >> sh(Qm), +-255), sh = {QPSK 0, 16QAM 1, 64QAM 2, 256QAM 2}. */
 static int sat16(int v) { return v > 32767 ? 32767 : v < -32768 ? -32768 : v; }
-void       lteo_rm_turbo_rx(const int16_t* e, uint32_t E, uint32_t K, uint32_t F, uint32_t rv, uint32_t Qm, int16_t* d)
+void lteo_rm_turbo_rx_harq(const int16_t* e, uint32_t E, uint32_t K, uint32_t F, uint32_t rv, uint32_t Qm, int16_t* d, int16_t* soft, int combine);
+void lteo_rm_turbo_rx(const int16_t* e, uint32_t E, uint32_t K, uint32_t F, uint32_t rv, uint32_t Qm, int16_t* d) { lteo_rm_turbo_rx_harq(e, E, K, F, rv, Qm, d, NULL, 0); }
+/* soft != NULL: the circular-buffer accumulators (stream-major, 3 (K + 4) values) live in the caller's HARQ buffer -- cleared first unless
+ * combine is set (srsran_softbuffer_rx_reset_tbs for a new transmission, plain accumulation for a retransmission; HARQ.cc:71-135) */
+void lteo_rm_turbo_rx_harq(const int16_t* e, uint32_t E, uint32_t K, uint32_t F, uint32_t rv, uint32_t Qm, int16_t* d, int16_t* soft, int combine)
 {
   static __thread uint32_t tab[3 * 6176];
-  static __thread int16_t  w[3 * 6176];
+  static __thread int16_t  wloc[3 * 6176];
   static __thread uint32_t order[3 * 6176];
+  int16_t*                 w = soft ? soft : wloc;
   uint32_t                 Kpi = lte_rm_turbo_table(K, tab), Kw = 3 * Kpi, D = K + 4;
   /* list of transmittable circular-buffer positions in order starting from k0 */
   uint32_t nn = 0, k0 = lte_rm_turbo_k0(K, rv);
@@ -628,7 +633,7 @@ void       lteo_rm_turbo_rx(const int16_t* e, uint32_t E, uint32_t K, uint32_t F
     if (t / D < 2 && t % D < F) continue;
     order[nn++] = t;
   }
-  memset(w, 0, sizeof(int16_t) * 3 * D);
+  if (!soft || !combine) memset(w, 0, sizeof(int16_t) * 3 * D);
   for (uint32_t k = 0; k < E; k++) {
     uint32_t t = order[k % nn];
     w[t]       = (int16_t)sat16((int)w[t] + (int)e[k]);
@@ -776,6 +781,11 @@ uint32_t lteo_turbo_decode(const int16_t* d, uint32_t K, uint32_t max_iter, int 
 int lteo_dlsch_decode(const int16_t* e, uint32_t G, uint32_t tbs, uint32_t rv, uint32_t Qm, uint32_t NL, uint32_t max_iter,
                       int early_stop, uint8_t* payload, uint32_t* iters_out)
 {
+  return lteo_dlsch_decode_harq(e, G, tbs, rv, Qm, NL, max_iter, early_stop, payload, iters_out, NULL, 0);
+}
+int lteo_dlsch_decode_harq(const int16_t* e, uint32_t G, uint32_t tbs, uint32_t rv, uint32_t Qm, uint32_t NL, uint32_t max_iter, int early_stop,
+                           uint8_t* payload, uint32_t* iters_out, int16_t* soft /* C x LTEO_HARQ_CB_STRIDE or NULL */, int combine)
+{
   lte_cbsegm_t s;
   if (lte_cbsegm(&s, tbs)) return -1;
   static __thread int16_t d[3 * 6148];
@@ -785,7 +795,7 @@ int lteo_dlsch_decode(const int16_t* e, uint32_t G, uint32_t tbs, uint32_t rv, u
   int                     all_cb_ok = 1;
   for (uint32_t r = 0; r < s.C; r++) {
     uint32_t K = lte_cb_K(&s, r), F = (r == 0) ? s.F : 0, E = lte_rm_turbo_E(G, s.C, r, Qm, NL);
-    lteo_rm_turbo_rx(e + rp, E, K, F, rv, Qm, d);
+    lteo_rm_turbo_rx_harq(e + rp, E, K, F, rv, Qm, d, soft ? soft + (size_t)r * LTEO_HARQ_CB_STRIDE : NULL, combine);
     rp += E;
     int      ok = 0;
     uint32_t it = lteo_turbo_decode(d, K, max_iter, early_stop ? (s.C > 1 ? 2 : 1) : 0, cb, &ok);
@@ -810,6 +820,13 @@ int lteo_dlsch_decode(const int16_t* e, uint32_t G, uint32_t tbs, uint32_t rv, u
 int lteo_pdsch_decode(lteo_t* q, uint32_t sf_idx, uint32_t cfi, uint16_t rnti, const lte_dl_grant_t* g, const cf_t* const* sym,
                       const cf_t* const* ce, uint32_t max_iter, uint8_t* const* payload, int* crc_ok)
 {
+  int16_t* none[2] = {NULL, NULL};
+  int      comb[2] = {0, 0};
+  return lteo_pdsch_decode_harq(q, sf_idx, cfi, rnti, g, sym, ce, max_iter, payload, crc_ok, none, comb);
+}
+int lteo_pdsch_decode_harq(lteo_t* q, uint32_t sf_idx, uint32_t cfi, uint16_t rnti, const lte_dl_grant_t* g, const cf_t* const* sym,
+                           const cf_t* const* ce, uint32_t max_iter, uint8_t* const* payload, int* crc_ok, int16_t* const* soft, const int* combine)
+{
   int16_t* llr[2] = {(int16_t*)malloc(sizeof(int16_t) * (g->nof_re * 8 + 16)), (int16_t*)malloc(sizeof(int16_t) * (g->nof_re * 8 + 16))};
   int      ret    = lteo_pdsch_llr(q, sf_idx, cfi, rnti, g, sym, ce, llr, NULL);
   if (ret == 0) {
@@ -819,8 +836,8 @@ int lteo_pdsch_decode(lteo_t* q, uint32_t sf_idx, uint32_t cfi, uint16_t rnti, c
       if (!g->tb[t].enabled) continue;
       uint32_t NL = g->tx_scheme == LTE_TX_DIVERSITY ? 2 : 1;
       if (g->tb[t].tbs > 0)
-        crc_ok[t] = lteo_dlsch_decode(llr[g->cw_swap ? 1 - cw : cw], g->tb[t].nof_bits, (uint32_t)g->tb[t].tbs, g->tb[t].rv, g->tb[t].qm, NL, max_iter, 1,
-                                      payload[t], NULL);
+        crc_ok[t] = lteo_dlsch_decode_harq(llr[g->cw_swap ? 1 - cw : cw], g->tb[t].nof_bits, (uint32_t)g->tb[t].tbs, g->tb[t].rv, g->tb[t].qm, NL, max_iter,
+                                           1, payload[t], NULL, soft[t], combine[t]);
       cw++;
     }
   }
@@ -893,7 +910,7 @@ static cf_t* idft_mixed(const cf_t* W, uint32_t M, cf_t* a, cf_t* b)
       cf_t           v[5];
       for (uint32_t r = 0; r < R; r++) {
         cf_t x = src[j + r * Q];
-        if (r * tstep) {
+        if (r * tstep != 0) {
           cf_t w = W[r * tstep];
           v[r]   = (cf_t){x.re * w.re - x.im * w.im, x.re * w.im + x.im * w.re};
         } else

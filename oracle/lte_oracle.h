@@ -63,14 +63,22 @@ int lteo_pdsch_llr(lteo_t* q, uint32_t sf_idx, uint32_t cfi, uint16_t rnti, cons
                    const cf_t* const* ce, int16_t* const* llr, cf_t* const* eq_out);
 /* K7+K8 for one transport block: e[G] int16 -> payload bytes; returns crc ok (1/0), <0 on error.
  * iters_out (optional) receives per-code-block iteration counts. */
+int lteo_dlsch_decode_harq(const int16_t* e, uint32_t G, uint32_t tbs, uint32_t rv, uint32_t Qm, uint32_t NL, uint32_t max_iter, int early_stop,
+                           uint8_t* payload, uint32_t* iters_out, int16_t* soft, int combine);
 int lteo_dlsch_decode(const int16_t* e, uint32_t G, uint32_t tbs, uint32_t rv, uint32_t Qm, uint32_t NL, uint32_t max_iter,
                       int early_stop, uint8_t* payload, uint32_t* iters_out);
 /* K7 alone: rate-dematch one code block into conditioned (sys, p1, p2) streams of K+4 */
 void lteo_rm_turbo_rx(const int16_t* e, uint32_t E, uint32_t K, uint32_t F, uint32_t rv, uint32_t Qm, int16_t* d /* 3*(K+4) */);
+/* HARQ soft combining (reference src/src/HARQ.cc:71-151, DL_Sniffer_PDSCH.cc:955-985): per code block LTEO_HARQ_CB_STRIDE int16 accumulators */
+#define LTEO_HARQ_CB_STRIDE 18448
+void lteo_rm_turbo_rx_harq(const int16_t* e, uint32_t E, uint32_t K, uint32_t F, uint32_t rv, uint32_t Qm, int16_t* d, int16_t* soft, int combine);
 /* K8 alone: decode one code block from conditioned streams; bits[K]; returns iterations run.
  * crc_type: 0 none (run max_iter), 1 CRC24A, 2 CRC24B */
 uint32_t lteo_turbo_decode(const int16_t* d, uint32_t K, uint32_t max_iter, int crc_type, uint8_t* bits, int* crc_ok);
 /* full PDSCH for one grant */
+/* soft[t] (NULL: no HARQ buffer): C x LTEO_HARQ_CB_STRIDE int16 of transport block t; combine[t] 0 = new transmission (buffer reset), 1 = add */
+int lteo_pdsch_decode_harq(lteo_t* q, uint32_t sf_idx, uint32_t cfi, uint16_t rnti, const lte_dl_grant_t* g, const cf_t* const* sym,
+                           const cf_t* const* ce, uint32_t max_iter, uint8_t* const* payload, int* crc_ok, int16_t* const* soft, const int* combine);
 int lteo_pdsch_decode(lteo_t* q, uint32_t sf_idx, uint32_t cfi, uint16_t rnti, const lte_dl_grant_t* g, const cf_t* const* sym,
                       const cf_t* const* ce, uint32_t max_iter, uint8_t* const* payload, int* crc_ok);
 

@@ -189,7 +189,8 @@ int lte_sim_subframe(lte_sim_t* s, uint32_t tti, cf_t* iq, lte_sim_truth_t* trut
   const lte_cell_t*    cell = &cfg->cell;
   uint32_t             sf_idx = tti % 10, cfi = cfg->cfi, nsc = s->nsc, N = cell->nof_prb;
   lte_rng_t            rng;
-  lte_rng_seed(&rng, cfg->seed * 0x9E3779B97F4A7C15ull + tti);
+  const int retx = cfg->harq_retx && ((tti / 8) & 1); /* scheduling and payload of tti - 8, sent again with rv 2 */
+  lte_rng_seed(&rng, cfg->seed * 0x9E3779B97F4A7C15ull + (retx ? tti - 8 : tti));
   memset(truth, 0, sizeof(*truth));
   truth->tti = tti;
   truth->cfi = cfi;
@@ -309,11 +310,12 @@ int lte_sim_subframe(lte_sim_t* s, uint32_t tti, cf_t* iq, lte_sim_truth_t* trut
       for (uint32_t r = rb0; r < rb0 + nr; r++) d->rbg_bitmask |= 1u << (nrbg - 1 - r);
     }
     d->pid = (uint8_t)(lte_rng_u64(&rng) % 8);
+    if (cfg->harq_retx) d->pid = (uint8_t)(tti % 8); /* one process per subframe of the 8 ms round trip, as an FDD eNB schedules them */
     d->tpc = 1;
     for (int t = 0; t < 2; t++) {
       d->mcs[t] = (uint8_t)(cfg->mcs_min + lte_rng_u64(&rng) % (cfg->mcs_max - cfg->mcs_min + 1));
       d->ndi[t] = (uint8_t)(lte_rng_u64(&rng) & 1);
-      d->rv[t]  = 0;
+      d->rv[t]  = retx ? 2 : 0;
     }
     d->tb_en[0] = 1;
     d->tb_en[1] = (kind == 3 || kind == 4);
@@ -530,6 +532,7 @@ int lte_sim_subframe(lte_sim_t* s, uint32_t tti, cf_t* iq, lte_sim_truth_t* trut
     }
   }
   /* ---- channel + AWGN ---- */
+  if (cfg->harq_retx) lte_rng_seed(&rng, cfg->seed * 0x2545F4914F6CDD1Dull + 31ull * tti + 7); /* a retransmission meets its own noise */
   double sigma = pow(10.0, -cfg->snr_db / 20.0) * M_SQRT1_2;
   for (uint32_t a = 0; a < cell->nof_rx; a++) {
     cf_t* out = iq + (size_t)a * s->sf_len;

@@ -22,7 +22,7 @@ class SimCfg(C.Structure):
                 ("dl_min", C.c_uint32), ("dl_max", C.c_uint32), ("ul_min", C.c_uint32), ("ul_max", C.c_uint32),
                 ("tm", C.c_uint32), ("mcs_min", C.c_uint32), ("mcs_max", C.c_uint32), ("si_period", C.c_uint32),
                 ("snr_db", C.c_float), ("chan_delay", C.c_uint32), ("fixed_L", C.c_uint32), ("full_band", C.c_uint32),
-                ("alt_table", C.c_uint32), ("ul_pusch", C.c_uint32), ("tb_swap", C.c_uint32), ("reserved", C.c_uint32 * 5)]
+                ("alt_table", C.c_uint32), ("ul_pusch", C.c_uint32), ("tb_swap", C.c_uint32), ("harq_retx", C.c_uint32), ("reserved", C.c_uint32 * 4)]
 
 
 class DciTruth(C.Structure):
@@ -61,6 +61,7 @@ class ChestRes(C.Structure):
                 ("cfo_re", C.c_float), ("cfo_im", C.c_float), ("snr_db", C.c_float), ("cfo", C.c_float)]
 
 
+HARQ_CB_STRIDE = 18448
 FORMATS = ["0", "1", "1A", "1B", "1C", "1D", "2", "2A", "2B"]
 _built = False
 
@@ -253,6 +254,17 @@ class Oracle:
         s, c = self._pp(sym, ce)
         r = self.L.lteo_pdsch_llr(self.h, sf_idx, cfi, rnti, C.byref(grant), s, c, ptr_array(llr), ptr_array(eq))
         return r, llr, eq
+
+    def pdsch_decode_harq(self, sf_idx, cfi, rnti, grant, sym, ce, soft, combine, max_iter=8):
+        """soft: [int16 array (16 * HARQ_CB_STRIDE) or None] per TB, combine: [0/1] per TB"""
+        pl = [np.zeros(16000, np.uint8) for _ in range(2)]
+        ok = (C.c_int * 2)(0, 0)
+        s, c = self._pp(sym, ce)
+        sp = (C.c_void_p * 2)(*[None if a is None else a.ctypes.data for a in soft])
+        cb = (C.c_int * 2)(*combine)
+        self.L.lteo_pdsch_decode_harq.argtypes = None
+        r = self.L.lteo_pdsch_decode_harq(self.h, sf_idx, cfi, rnti, C.byref(grant), s, c, max_iter, ptr_array(pl), ok, sp, cb)
+        return r, pl, [ok[0], ok[1]]
 
     def pdsch_decode(self, sf_idx, cfi, rnti, grant, sym, ce, max_iter=8):
         pl = [np.zeros(16000, np.uint8) for _ in range(2)]
