@@ -606,7 +606,7 @@ def main():
     achieved = tbytes / t_turbo / 1e9 if t_turbo > 0 else 0.0
     traffic = None   # dram__bytes_read + dram__bytes_write of the step's turbo launches, from the committed ncu --set full capture of this workload
     try:
-        tt = json.load(open(os.path.join(ROOT, "profiles", "r1_kernel_traffic.json")))["turbo_kernel_step_total"]
+        tt = json.load(open(os.path.join(ROOT, "profiles", "r2_kernel_traffic.json")))["turbo_kernel_step_total"]
         if tt["subframes_per_step"] == B:
             traffic = tt["traffic_bytes"]
     except Exception:
