@@ -120,18 +120,7 @@ __global__ void __launch_bounds__(256) ofdm_rx_kernel(const __grid_constant__ De
 // Reads 800 pilots (+ CRS table), writes ce[14][nsc].  Restates srsran_chest_dl_estimate_cfg with the
 // reference's cfg (src/src/SubframeWorker.cc:376-400).
 // =================================================================================================
-__device__ __forceinline__ float2 f_interp(const DevCell& c, const float2* sm, uint32_t np, uint32_t off, uint32_t k)
-{
-  int m = ((int)k - (int)off) / 6;
-  if ((int)k < (int)off) m = 0;
-  if (m > (int)np - 2) m = (int)np - 2;
-  const int    j  = (int)k - (6 * m + (int)off);
-  const float  cc = c.interp_c[j + 5];
-  const float2 A = sm[m], B = sm[m + 1];
-  return make_float2(A.x + (B.x - A.x) * cc, A.y + (B.y - A.y) * cc);
-}
-
-__global__ void __launch_bounds__(256) chest_kernel(const __grid_constant__ DevCell c, const float2* __restrict__ sym, float2* __restrict__ ce,
+__global__ void __launch_bounds__(256) chest_kernel(const __grid_constant__ DevCell c, const float2* __restrict__ sym, float2* __restrict__ pilg,
                                                     DevSfInfo* __restrict__ info)
 {
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -205,19 +194,19 @@ __global__ void __launch_bounds__(256) chest_kernel(const __grid_constant__ DevC
       info[sf].cfo_im = cfo_s[1];
     }
   }
-  float2* out = ce + (((size_t)sf * c.nof_ports + p) * c.nof_rx + a) * 14 * nsc;
-  for (uint32_t i = tid; i < 14 * nsc; i += nt) {
-    const uint32_t l = i / nsc, k = i % nsc, ia = c.t_ia[l], ib = c.t_ib[l];
-    const float    t = c.t_frac[l];
-    const float2   A = f_interp(c, sm + ia * np, np, c.crs_off[p][ia & 1], k);
-    const float2   B = f_interp(c, sm + ib * np, np, c.crs_off[p][ib & 1], k);
-    float2         r;
-    if (l < 11)
-      r = make_float2(A.x + (B.x - A.x) * t, A.y + (B.y - A.y) * t);
-    else
-      r = make_float2(B.x + (B.x - A.x) * t, B.y + (B.y - A.y) * t);
-    out[i] = r;
-  }
+  // the smoothed pilot grid is what the equalisers interpolate from (dev_eq.cuh: ce_at); 6.4 KB per (port, antenna, subframe) instead of 134 KB
+  float2* out = pilg + (((size_t)sf * c.nof_ports + p) * c.nof_rx + a) * NPILSYM * np;
+  for (uint32_t i = tid; i < NPILSYM * np; i += nt) out[i] = sm[i];
+}
+
+// The interpolated grid ce[port][ant][14][nsc] (q->chest_res.ce of the reference), materialised only when somebody asks for it
+// (ltephy_tap(LTEPHY_TAP_CE): tests, the srsRAN-compatible shim); grid (ports * rx, subframes)
+__global__ void __launch_bounds__(256) chest_interp_kernel(const __grid_constant__ DevCell c, const float2* __restrict__ pilg, float2* __restrict__ ce)
+{
+  const uint32_t np = 2 * c.nof_prb, nsc = c.nsc, p = blockIdx.x / c.nof_rx, sf = blockIdx.y;
+  const float2*  pil = pilg + ((size_t)sf * c.nof_ports * c.nof_rx + blockIdx.x) * NPILSYM * np;
+  float2*        out = ce + ((size_t)sf * c.nof_ports * c.nof_rx + blockIdx.x) * 14 * nsc;
+  for (uint32_t i = threadIdx.x; i < 14 * nsc; i += blockDim.x) out[i] = ce_at(c, pil, p, i / nsc, i % nsc);
 }
 
 // =================================================================================================
@@ -323,6 +312,11 @@ __global__ void __launch_bounds__(256) pdcch_llr_kernel(const __grid_constant__ 
 }
 
 // ---- launchers ----------------------------------------------------------------------------------
+extern "C" void launch_chest_interp(const DevCell& c, const float2* pil, float2* ce, uint32_t n, cudaStream_t st, uint64_t* launches)
+{
+  chest_interp_kernel<<<dim3(c.nof_ports * c.nof_rx, n), 256, 0, st>>>(c, pil, ce);
+  *launches += 1;
+}
 extern "C" void launch_frontend(const DevCell& c, const float2* iq, float2* sym, float2* ce, float* llr, DevSfInfo* info, uint32_t n,
                                 cudaStream_t st, uint64_t* launches)
 {

@@ -125,7 +125,7 @@ __global__ void __launch_bounds__(256) pdsch_demod_kernel(const __grid_constant_
       emit(g, 0, gi + 1, x1, seq_pool, llr_pool);
     } else if (g.tx_scheme == LTEPHY_TX_CDD) {
       float2 x0, x1;
-      eq_cdd(v, idx, (gi & 1u) != 0, x0, x1);
+      eq_cdd(c, v, idx, (gi & 1u) != 0, x0, x1);
       emit(g, 0, gi, x0, seq_pool, llr_pool);
       emit(g, 1, gi, x1, seq_pool, llr_pool);
     } else if (g.tx_scheme == LTEPHY_TX_SPATIALMUX) {
@@ -133,7 +133,7 @@ __global__ void __launch_bounds__(256) pdsch_demod_kernel(const __grid_constant_
         emit(g, 0, gi, eq_spmux1(c, v, idx, spmux_w(1, g.pmi)), seq_pool, llr_pool);
       } else {
         float2 x0, x1;
-        eq_spmux2(v, idx, spmux_w(2, g.pmi), x0, x1);
+        eq_spmux2(c, v, idx, spmux_w(2, g.pmi), x0, x1);
         emit(g, 0, gi, x0, seq_pool, llr_pool);
         emit(g, 1, gi, x1, seq_pool, llr_pool);
       }

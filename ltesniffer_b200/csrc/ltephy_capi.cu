@@ -20,6 +20,7 @@ static cudaEvent_t g_h2d_last[64]; // per device: completion of the most recentl
 
 extern "C" {
 void launch_frontend(const DevCell&, const float2*, float2*, float2*, float*, DevSfInfo*, uint32_t, cudaStream_t, uint64_t*);
+void launch_chest_interp(const DevCell&, const float2*, float2*, uint32_t, cudaStream_t, uint64_t*);
 void launch_viterbi(const DevCell&, const float*, const DevSfInfo*, ltephy_cand_t*, uint32_t, cudaStream_t, uint64_t*);
 void launch_compact(const DevCell&, const DevSfInfo*, const ltephy_cand_t*, ltephy_compact_t*, uint32_t, cudaStream_t, uint64_t*);
 void launch_pdsch_front(const DevCell&, const DevGrant*, uint32_t, uint32_t, const float2*, const float2*, const uint32_t*, const uint32_t*, uint32_t,
@@ -223,7 +224,7 @@ extern "C" int ltephy_create(const ltephy_cfg_t* cfg, ltephy_t** out)
     c.re_mask = upload(h, masks.data(), masks.size());
   }
   const size_t S = cfg->max_subframes, g = (size_t)14 * c.nsc;
-  if (h->d_iq.reserve(S * c.nof_rx * c.sf_len) || h->d_sym.reserve(S * c.nof_rx * g) || h->d_ce.reserve(S * c.nof_ports * c.nof_rx * g) ||
+  if (h->d_iq.reserve(S * c.nof_rx * c.sf_len) || h->d_sym.reserve(S * c.nof_rx * g) || h->d_pil.reserve(S * c.nof_ports * c.nof_rx * 4 * 2 * c.nof_prb) ||
       h->d_llr.reserve(S * LLR_STRIDE) || h->d_info.reserve(S) || h->d_cands.reserve(S * LTEPHY_MAX_LOC * LTEPHY_MAX_SIZES) ||
       h->h_info.reserve(S) || h->d_compact.reserve(S) || h->h_compact.reserve(S) || h->d_rm.reserve((size_t)16 << 20) || h->d_pi.reserve((size_t)188 * 6144))
     return fail(LTEPHY_ERROR, "device allocation failed");
@@ -238,7 +239,7 @@ extern "C" void ltephy_destroy(ltephy_t* h)
   if (!h) return;
   cudaDeviceSynchronize();
   for (void* p : h->tables) cudaFree(p);
-  h->d_iq.release(), h->d_sym.release(), h->d_ce.release(), h->d_llr.release(), h->d_info.release(), h->d_cands.release();
+  h->d_iq.release(), h->d_sym.release(), h->d_ce.release(), h->d_pil.release(), h->d_llr.release(), h->d_info.release(), h->d_cands.release();
   h->h_info.release(), h->d_compact.release(), h->h_compact.release(), h->d_grants.release(), h->d_cbs.release(), h->d_pairs.release(), h->d_tbs.release(), h->d_pair_pi_off.release();
   h->d_tscratch.release(), h->d_tqueue.release();
   h->d_seq.release(), h->d_rm.release(), h->d_turbo.release(), h->d_pllr.release(), h->d_pi.release(), h->d_payload.release(), h->d_harq.release();
@@ -326,7 +327,7 @@ static int phase_a_common(ltephy* h, const float2* iq_dev, const float2* iq_host
     CU(cudaEventRecord(h->ev_h2d, h->stream));
     last = h->ev_h2d;
   }
-  launch_frontend(c, iq_dev, h->d_sym.p, h->d_ce.p, h->d_llr.p, h->d_info.p, n, h->stream, &h->launches);
+  launch_frontend(c, iq_dev, h->d_sym.p, h->d_pil.p, h->d_llr.p, h->d_info.p, n, h->stream, &h->launches);
   launch_viterbi(c, h->d_llr.p, h->d_info.p, h->d_cands.p, n, h->stream, &h->launches);
   launch_compact(c, h->d_info.p, h->d_cands.p, h->d_compact.p, n, h->stream, &h->launches);
   CU(cudaEventRecord(h->ev[1], h->stream));
@@ -690,7 +691,7 @@ extern "C" int ltephy_submit_grants(ltephy_t* h, const ltephy_grant_t* gin, uint
   if (n) {
     stage_and_pull(h, h->d_grants.p, h->grants.data(), n * sizeof(DevGrant));
     stage_and_pull(h, h->d_tbs.p, h->tbs.data(), h->tbs.size() * sizeof(DevTb));
-    launch_pdsch_front(h->dc, h->d_grants.p, n, max_scr_words, h->d_sym.p, h->d_ce.p, h->d_gold_x1, h->d_gold_basis, h->gold_words, h->d_seq.p,
+    launch_pdsch_front(h->dc, h->d_grants.p, n, max_scr_words, h->d_sym.p, h->d_pil.p, h->d_gold_x1, h->d_gold_basis, h->gold_words, h->d_seq.p,
                        h->d_pllr.p, h->stream, &h->launches);
     if (!h->cbs.empty()) {
       r = run_turbo_stage(h, h->cfg.turbo_max_iter);
@@ -1056,7 +1057,12 @@ extern "C" int ltephy_tap(ltephy_t* h, int what, void* dst, size_t bytes)
   const size_t g = (size_t)14 * h->dc.nsc, n = h->n_cur;
   switch (what) {
     case LTEPHY_TAP_SYM: src = h->d_sym.p, avail = n * h->dc.nof_rx * g * sizeof(float2); break;
-    case LTEPHY_TAP_CE: src = h->d_ce.p, avail = n * h->dc.nof_ports * h->dc.nof_rx * g * sizeof(float2); break;
+    case LTEPHY_TAP_CE: // the interpolated grid is not kept (the equalisers interpolate on the fly): materialise it from the pilot grid now
+      CU(cudaSetDevice(h->cfg.device));
+      if (h->d_ce.reserve((size_t)h->cfg.max_subframes * h->dc.nof_ports * h->dc.nof_rx * g)) return fail(LTEPHY_ERROR, "device allocation failed");
+      if (n) launch_chest_interp(h->dc, h->d_pil.p, h->d_ce.p, (uint32_t)n, h->stream, &h->launches);
+      src = h->d_ce.p, avail = n * h->dc.nof_ports * h->dc.nof_rx * g * sizeof(float2);
+      break;
     case LTEPHY_TAP_LLR: src = h->d_llr.p, avail = n * LLR_STRIDE * sizeof(float); break;
     case LTEPHY_TAP_PDSCH_LLR: src = h->d_pllr.p, avail = h->pllr_elems * sizeof(short); break;
     case LTEPHY_TAP_TURBO_IN: src = h->d_turbo.p, avail = h->d_turbo.cap * 4; break;

@@ -95,7 +95,7 @@ struct ltephy {
   uint64_t           launches = 0;
 
   // phase A
-  DevBuf<float2>        d_iq, d_sym, d_ce;
+  DevBuf<float2>        d_iq, d_sym, d_pil, d_ce; // d_pil: smoothed CRS estimates [n][port][rx][4][2 nof_prb]; d_ce: interpolated grid, filled on demand (tap)
   DevBuf<float>         d_llr;
   DevBuf<DevSfInfo>     d_info;
   DevBuf<ltephy_cand_t> d_cands;
