@@ -200,6 +200,26 @@ int ltephy_get_phase_b(ltephy_t* h, ltephy_tb_result_t* results, uint8_t* payloa
  * (the "single NCCL gather of decoded transport blocks").  Blocks until the copy is done. */
 int ltephy_copy_phase_b_device(ltephy_t* h, void* dst_dev, size_t cap, size_t* nbytes);
 
+/* ---- file-mode front matter: what runs before the hot path when LTESniffer reads a recording --------------------------- */
+/* constant carrier-frequency-offset correction of every subframe of samples, fused into the OFDM kernel: srsran_cfo_correct in srsran_ue_sync's
+ * file mode (args.file_offset_freq -> srsran_ue_sync_init_file_multi, src/src/LTESniffer_Core.cc:252-257); phase restarts at each subframe;
+ * 0 switches it off.  Applies to ltephy_submit_iq / _device of this handle (downlink). */
+int ltephy_set_cfo(ltephy_t* h, float cfo_hz);
+typedef struct {
+  uint8_t  found;           /* SRSRAN_UE_MIB_FOUND */
+  uint8_t  nof_ports;       /* 1, 2 or 4: from the CRC mask */
+  uint8_t  sfn_offset;      /* position of this frame in the 40 ms PBCH period = SFN mod 4 */
+  uint8_t  phich_length;    /* 0 normal, 1 extended    (srsran_cell_t.phich_length) */
+  uint8_t  phich_resources; /* 0: 1/6, 1: 1/2, 2: 1, 3: 2 (srsran_cell_t.phich_resources) */
+  uint8_t  bch_payload[3];  /* the 24 MIB bits, first bit in bit 7 of byte 0 (bch_payload of srsran_ue_mib_decode, packed) */
+  uint32_t nof_prb;         /* 6, 15, 25, 50, 75, 100 */
+  uint32_t sfn;             /* (8 MSBs << 2) + sfn_offset, as LTESniffer_Core.cc:390-392 computes it */
+} ltephy_mib_t;
+/* PBCH decode of every subframe of the last ltephy_submit_iq whose tti % 10 == 0 (found = 0 elsewhere): srsran_ue_mib_decode +
+ * srsran_pbch_mib_unpack (src/src/LTESniffer_Core.cc:382-396).  out[n].  The equaliser uses the handle's port count; one frame is decoded on its
+ * own (no soft combining across the 40 ms period). */
+int ltephy_mib_decode(ltephy_t* h, ltephy_mib_t* out);
+
 /* nslots HARQ slots of LTEPHY_HARQ_SLOT_BYTES each (150 RNTIs x 8 processes x 2 TBs = 2400 slots = 1.4 GB); contents survive across batches */
 int ltephy_harq_reserve(ltephy_t* h, uint32_t nslots);
 

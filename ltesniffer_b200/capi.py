@@ -55,6 +55,11 @@ class UlGrant(C.Structure):
                 ("cqi_len", C.c_uint16), ("I_offset_ack", C.c_uint8), ("I_offset_cqi", C.c_uint8), ("I_offset_ri", C.c_uint8), ("flags", C.c_uint8)]
 
 
+class Mib(C.Structure):
+    _fields_ = [("found", C.c_uint8), ("nof_ports", C.c_uint8), ("sfn_offset", C.c_uint8), ("phich_length", C.c_uint8), ("phich_resources", C.c_uint8),
+                ("bch_payload", C.c_uint8 * 3), ("nof_prb", C.c_uint32), ("sfn", C.c_uint32)]
+
+
 class UlChest(C.Structure):
     _fields_ = [("noise", C.c_float), ("rsrp", C.c_float), ("snr_db", C.c_float), ("ta_us", C.c_float)]
 
@@ -198,6 +203,16 @@ class LtePhy:
         comp = np.zeros(self.n, COMPACT_DTYPE)
         self._chk(self.L.ltephy_get_phase_a_compact(self.h, info, _p(comp)), "get_phase_a_compact")
         return info, comp
+
+    def set_cfo(self, cfo_hz):
+        self.L.ltephy_set_cfo.argtypes = [C.c_void_p, C.c_float]
+        self._chk(self.L.ltephy_set_cfo(self.h, cfo_hz), "set_cfo")
+
+    def mib_decode(self):
+        out = (Mib * self.n)()
+        self.L.ltephy_mib_decode.argtypes = [C.c_void_p, C.c_void_p]
+        self._chk(self.L.ltephy_mib_decode(self.h, out), "mib_decode")
+        return out
 
     def harq_reserve(self, nslots):
         self.L.ltephy_harq_reserve.argtypes = [C.c_void_p, C.c_uint32]

@@ -29,6 +29,10 @@ struct DevCell {
   const uint16_t* conv_tab[LTEPHY_MAX_SIZES]; // [3K] circular position -> stream-major index
   const uint16_t* loc_tab[3];     // [nloc] ncce | (L << 8)
   const uint16_t* re_mask;        // [3 sf class][3 cfi][14][nof_prb]: 12-bit mask of PDSCH data REs of the PRB in the symbol
+  const uint32_t* pbch_re;        // [240] (symbol << 16) | sub-carrier of the PBCH resource elements of subframe 0
+  const uint32_t* pbch_scr;       // [60] c(cell_id), 1920 bits
+  const uint16_t* pbch_tab;       // [120] conv rate-matching table of K = 40
+  const float2*   cfo_rot;        // [sf_len] e^{-j 2 pi f n / (15000 fft)} or nullptr (ltephy_set_cfo)
 };
 
 // per-subframe device record (layout mirrors the leading part of ltephy_sf_info_t)

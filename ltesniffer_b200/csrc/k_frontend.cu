@@ -77,6 +77,10 @@ __global__ void __launch_bounds__(256) ofdm_rx_kernel(const __grid_constant__ De
       for (uint32_t j = 0; j < 8; j++) {
         const uint32_t m = ((j & 1u) << 2) | (j & 2u) | (j >> 2), idx = t + m * q8;
         float2         x = src[idx];
+        if (!UL && c.cfo_rot) { // constant frequency-offset correction of the file samples (srsran_cfo_correct in srsran_ue_sync's file mode)
+          const float2 r = __ldg(&c.cfo_rot[c.sym_off[l] + idx]);
+          x              = make_float2(x.x * r.x - x.y * r.y, x.x * r.y + x.y * r.x);
+        }
         if (UL) { // remove the 7.5 kHz half-subcarrier shift: multiply by exp(-j pi i / N) (srsran_enb_ul_fft)
           const float2 r = __ldg(&c.ul_rot[idx]);
           x              = make_float2(x.x * r.x - x.y * r.y, x.x * r.y + x.y * r.x);

@@ -21,6 +21,7 @@ static cudaEvent_t g_h2d_last[64]; // per device: completion of the most recentl
 extern "C" {
 void launch_frontend(const DevCell&, const float2*, float2*, float2*, float*, DevSfInfo*, uint32_t, cudaStream_t, uint64_t*);
 void launch_chest_interp(const DevCell&, const float2*, float2*, uint32_t, cudaStream_t, uint64_t*);
+void launch_pbch(const DevCell&, const float2*, const float2*, const DevSfInfo*, void*, uint32_t, cudaStream_t, uint64_t*);
 void launch_viterbi(const DevCell&, const float*, const DevSfInfo*, ltephy_cand_t*, uint32_t, cudaStream_t, uint64_t*);
 void launch_compact(const DevCell&, const DevSfInfo*, const ltephy_cand_t*, ltephy_compact_t*, uint32_t, cudaStream_t, uint64_t*);
 void launch_pdsch_front(const DevCell&, const DevGrant*, uint32_t, uint32_t, const float2*, const float2*, const uint32_t*, const uint32_t*, uint32_t,
@@ -176,6 +177,19 @@ extern "C" int ltephy_create(const ltephy_cfg_t* cfg, ltephy_t** out)
     auto t        = ltehost::conv_rm_table(c.sizes[i] + 16);
     c.conv_tab[i] = upload(h, t.data(), t.size());
   }
+  { // PBCH: resource elements of subframe 0 (slot 1, symbols 0..3, central 72 sub-carriers minus the CRS of four ports), c(cell_id), rate matching of K = 40
+    std::vector<uint32_t> re;
+    const uint32_t        k0 = c.nsc / 2 - 36;
+    for (uint32_t l = 7; l < 11; l++)
+      for (uint32_t k = k0; k < k0 + 72; k++)
+        if (!(l < 9 && k % 3 == c.cell_id % 3)) re.push_back((l << 16) | k);
+    c.pbch_re = upload(h, re.data(), re.size());
+    auto gw    = ltehost::gold_words(c.cell_id, 1920);
+    c.pbch_scr = upload(h, gw.data(), gw.size());
+    auto t40   = ltehost::conv_rm_table(40);
+    c.pbch_tab = upload(h, t40.data(), t40.size());
+    c.cfo_rot  = nullptr;
+  }
   for (uint32_t cfi = 0; cfi < 3; cfi++) {
     c.nof_cce[cfi] = h->cm.nof_cce[cfi];
     c.pdcch_idx[cfi] = upload(h, h->cm.pdcch_idx[cfi].data(), h->cm.pdcch_idx[cfi].size());
@@ -242,7 +256,7 @@ extern "C" void ltephy_destroy(ltephy_t* h)
   h->d_iq.release(), h->d_sym.release(), h->d_ce.release(), h->d_pil.release(), h->d_llr.release(), h->d_info.release(), h->d_cands.release();
   h->h_info.release(), h->d_compact.release(), h->h_compact.release(), h->d_grants.release(), h->d_cbs.release(), h->d_pairs.release(), h->d_tbs.release(), h->d_pair_pi_off.release();
   h->d_tscratch.release(), h->d_tqueue.release();
-  h->d_seq.release(), h->d_rm.release(), h->d_turbo.release(), h->d_pllr.release(), h->d_pi.release(), h->d_payload.release(), h->d_harq.release();
+  h->d_seq.release(), h->d_rm.release(), h->d_turbo.release(), h->d_pllr.release(), h->d_pi.release(), h->d_payload.release(), h->d_harq.release(), h->d_cfo.release(), h->d_mib.release();
   h->d_cb_iters.release(), h->d_cb_crc.release(), h->d_res.release(), h->h_res.release(), h->h_payload.release(), h->h_stage.release();
   h->d_uliq.release(), h->d_ulsym.release(), h->d_ulpool.release(), h->d_ulgrants.release(), h->d_ulchest.release(), h->h_ulchest.release();
   for (auto& e : h->ev)
@@ -748,6 +762,56 @@ extern "C" int ltephy_get_phase_b(ltephy_t* h, ltephy_tb_result_t* results, uint
   return LTEPHY_SUCCESS;
 }
 
+
+// ---------------------------------------------------------------------------------------- file-mode front matter
+// constant frequency-offset correction of every subframe of samples: srsran_cfo_correct(&q->file_cfo_correct, ..., file_cfo / 15000 / fft_size)
+// in srsran_ue_sync's file mode (args.file_offset_freq, reference src/src/LTESniffer_Core.cc:252-257); the rotation is applied by the OFDM kernel
+extern "C" int ltephy_set_cfo(ltephy_t* h, float cfo_hz)
+{
+  if (!h) return fail(LTEPHY_ERROR_INVALID_INPUTS, "set_cfo: bad arguments");
+  CU(cudaSetDevice(h->cfg.device));
+  CU(cudaStreamSynchronize(h->stream));
+  if (cfo_hz == 0.0f) {
+    h->dc.cfo_rot = nullptr;
+    return LTEPHY_SUCCESS;
+  }
+  std::vector<float2> rot(h->dc.sf_len);
+  for (uint32_t n = 0; n < h->dc.sf_len; n++) {
+    const double ph = -2.0 * M_PI * (double)cfo_hz * (double)n / (15000.0 * (double)h->dc.fft);
+    rot[n]          = make_float2((float)std::cos(ph), (float)std::sin(ph));
+  }
+  if (h->d_cfo.reserve(rot.size())) return fail(LTEPHY_ERROR, "device allocation failed");
+  CU(cudaMemcpy(h->d_cfo.p, rot.data(), rot.size() * sizeof(float2), cudaMemcpyHostToDevice));
+  h->dc.cfo_rot = h->d_cfo.p;
+  return LTEPHY_SUCCESS;
+}
+// PBCH / MIB of every subframe 0 of the last phase A: srsran_ue_mib_decode + srsran_pbch_mib_unpack (LTESniffer_Core.cc:382-396)
+extern "C" int ltephy_mib_decode(ltephy_t* h, ltephy_mib_t* out)
+{
+  if (!h || !out) return fail(LTEPHY_ERROR_INVALID_INPUTS, "mib_decode: bad arguments");
+  const uint32_t n = (uint32_t)h->n_cur;
+  if (!n) return fail(LTEPHY_ERROR_INVALID_INPUTS, "mib_decode: no subframes submitted");
+  CU(cudaSetDevice(h->cfg.device));
+  if (h->d_mib.reserve((size_t)4 * h->cfg.max_subframes)) return fail(LTEPHY_ERROR, "device allocation failed");
+  launch_pbch(h->dc, h->d_sym.p, h->d_pil.p, h->d_info.p, h->d_mib.p, n, h->stream, &h->launches);
+  std::vector<uint32_t> raw((size_t)4 * n);
+  CU(cudaMemcpyAsync(raw.data(), h->d_mib.p, raw.size() * 4, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  static const uint32_t BW[8] = {6, 15, 25, 50, 75, 100, 0, 0};
+  for (uint32_t i = 0; i < n; i++) {
+    ltephy_mib_t m{};
+    const uint32_t bits = raw[4 * i + 3];
+    m.found = (uint8_t)raw[4 * i], m.nof_ports = (uint8_t)raw[4 * i + 1], m.sfn_offset = (uint8_t)raw[4 * i + 2];
+    if (m.found) {
+      m.nof_prb = BW[(bits >> 21) & 7u], m.phich_length = (uint8_t)((bits >> 20) & 1u), m.phich_resources = (uint8_t)((bits >> 18) & 3u);
+      m.sfn = ((((bits >> 10) & 0xFFu) << 2) + m.sfn_offset) % 1024u; // sfn = (sfn + sfn_offset) % 1024, LTESniffer_Core.cc:392
+      m.bch_payload[0] = (uint8_t)(bits >> 16), m.bch_payload[1] = (uint8_t)(bits >> 8), m.bch_payload[2] = (uint8_t)bits;
+      if (!m.nof_prb) m.found = 0;
+    }
+    out[i] = m;
+  }
+  return LTEPHY_SUCCESS;
+}
 
 // ---------------------------------------------------------------------------------------- HARQ store
 extern "C" int ltephy_harq_reserve(ltephy_t* h, uint32_t nslots)

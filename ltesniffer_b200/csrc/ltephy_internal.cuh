@@ -88,6 +88,8 @@ struct ltephy {
   DevCell            dc{};
   cudaStream_t       stream = nullptr;
   cudaEvent_t        ev[6]{}, mark[2]{}, ev_h2d = nullptr;
+  DevBuf<float2>     d_cfo;                  // per-sample rotation of ltephy_set_cfo
+  DevBuf<uint32_t>   d_mib;                  // 4 words per subframe (pbch_kernel)
   DevBuf<short>      d_harq;                 // HARQ store: harq_slots x LTEPHY_HARQ_SLOT_BYTES
   uint32_t           harq_slots = 0, harq_max_gen = 0;
   std::map<uint32_t, uint32_t> harq_uses;    // slot -> uses in the batch being built

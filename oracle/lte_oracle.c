@@ -864,6 +864,46 @@ int lteo_phase_a(lteo_t* q, const cf_t* iq, uint32_t sf_idx, cf_t* sym /* [nof_r
   return (int)lteo_pdcch_extract_llr(q, sf_idx, *cfi_out, symp, (const cf_t* const*)cep, llr);
 }
 
+/* ================================================================== PBCH / MIB, CFO correction */
+int lteo_pbch_decode(lteo_t* q, const cf_t* const* sym, const cf_t* const* ce, uint8_t* mib, uint32_t* nof_ports, uint32_t* frame_q)
+{
+  const lte_cell_t* c = &q->cell;
+  uint16_t          ks[240];
+  uint8_t           ls[240];
+  const uint32_t    nre = lte_pbch_re(c, ks, ls), nsc = q->nsc;
+  cf_t              d[240];
+  if (c->nof_ports == 1) {
+    for (uint32_t i = 0; i < nre; i++) d[i] = eq_port0(q, sym, ce, ls[i] * nsc + ks[i]);
+  } else {
+    for (uint32_t i = 0; i + 1 < nre; i += 2) eq_sfbc(q, sym, ce, ls[i] * nsc + ks[i], ls[i + 1] * nsc + ks[i + 1], &d[i], &d[i + 1]);
+  }
+  float   llr[480], e[480];
+  uint8_t sc[1920];
+  const float ms2 = -1.41421354f;
+  for (uint32_t i = 0; i < nre; i++) llr[2 * i] = d[i].re * ms2, llr[2 * i + 1] = d[i].im * ms2;
+  lte_gold_bits(c->cell_id, sc, 1920);
+  for (uint32_t fq = 0; fq < 4; fq++) {
+    for (uint32_t i = 0; i < 480; i++) e[i] = sc[480 * fq + i] ? -llr[i] : llr[i];
+    uint8_t  bits[64];
+    uint16_t rem = 0;
+    if (lteo_dci_decode(e, 480, 24, bits, &rem)) continue;
+    const uint32_t np = rem == 0x0000 ? 1 : rem == 0xFFFF ? 2 : rem == 0x5555 ? 4 : 0;
+    if (!np) continue;
+    memcpy(mib, bits, 24);
+    *nof_ports = np, *frame_q = fq;
+    return 1;
+  }
+  return 0;
+}
+void lteo_cfo_correct(lteo_t* q, float cfo_hz, const cf_t* in, cf_t* out)
+{
+  for (uint32_t n = 0; n < q->sf_len; n++) {
+    double ph = -2.0 * M_PI * (double)cfo_hz * (double)n / (15000.0 * (double)q->fft);
+    float  cr = (float)cos(ph), ci = (float)sin(ph);
+    out[n]    = (cf_t){in[n].re * cr - in[n].im * ci, in[n].re * ci + in[n].im * cr};
+  }
+}
+
 /* ================================================================== uplink (PUSCH) */
 void lteo_ul_ofdm(lteo_t* q, const cf_t* iq, cf_t* sym)
 {

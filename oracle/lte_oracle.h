@@ -69,6 +69,12 @@ int lteo_dlsch_decode(const int16_t* e, uint32_t G, uint32_t tbs, uint32_t rv, u
                       int early_stop, uint8_t* payload, uint32_t* iters_out);
 /* K7 alone: rate-dematch one code block into conditioned (sys, p1, p2) streams of K+4 */
 void lteo_rm_turbo_rx(const int16_t* e, uint32_t E, uint32_t K, uint32_t F, uint32_t rv, uint32_t Qm, int16_t* d /* 3*(K+4) */);
+/* PBCH of subframe 0 (srsran_ue_mib_decode at src/src/LTESniffer_Core.cc:386): equalise the 240 resource elements with the cell's port count, QPSK soft
+ * bits, and for each of the four positions q of this frame inside the 40 ms period: descramble, rate-dematch 480 -> 120, tail-biting Viterbi, CRC16;
+ * the CRC remainder must be the mask of 1, 2 or 4 antenna ports.  Returns 1 (found: mib[24] bits, *nof_ports, *q = SFN mod 4) or 0. */
+int lteo_pbch_decode(lteo_t* q, const cf_t* const* sym, const cf_t* const* ce, uint8_t* mib, uint32_t* nof_ports, uint32_t* frame_q);
+/* e^{-j 2 pi f n / (15000 fft)} applied to one subframe of samples, n restarting at 0 (srsran_cfo_correct on the file samples, srsran_ue_sync file mode) */
+void lteo_cfo_correct(lteo_t* q, float cfo_hz, const cf_t* in, cf_t* out);
 /* HARQ soft combining (reference src/src/HARQ.cc:71-151, DL_Sniffer_PDSCH.cc:955-985): per code block LTEO_HARQ_CB_STRIDE int16 accumulators */
 #define LTEO_HARQ_CB_STRIDE 18448
 void lteo_rm_turbo_rx_harq(const int16_t* e, uint32_t E, uint32_t K, uint32_t F, uint32_t rv, uint32_t Qm, int16_t* d, int16_t* soft, int combine);

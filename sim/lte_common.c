@@ -1083,3 +1083,38 @@ void lte_uci_map(uint32_t M, const lte_uci_layout_t* L, uint8_t* kind, uint32_t*
     else if (kind[p] == 1) kind[p] = 4;
   }
 }
+
+/* ---- PBCH / MIB ---- */
+uint32_t lte_pbch_re(const lte_cell_t* c, uint16_t* k, uint8_t* l)
+{
+  const uint32_t nsc = 12 * c->nof_prb, k0 = nsc / 2 - 36;
+  uint32_t       n = 0;
+  for (uint32_t sym = 7; sym < 11; sym++)
+    for (uint32_t kk = k0; kk < k0 + 72; kk++) {
+      if (sym < 9 && kk % 3 == c->cell_id % 3) continue; /* CRS of ports 0/1 (symbol 0) and 2/3 (symbol 1), reserved whatever the port count */
+      k[n] = (uint16_t)kk, l[n] = (uint8_t)sym;
+      n++;
+    }
+  return n;
+}
+void lte_mib_pack(uint32_t nof_prb, uint32_t phich_ext, uint32_t phich_res, uint32_t sfn, uint8_t* bits)
+{
+  static const uint32_t BW[6] = {6, 15, 25, 50, 75, 100};
+  uint32_t bw = 0;
+  for (uint32_t i = 0; i < 6; i++)
+    if (BW[i] == nof_prb) bw = i;
+  memset(bits, 0, 24);
+  for (int i = 0; i < 3; i++) bits[i] = (bw >> (2 - i)) & 1;
+  bits[3] = phich_ext & 1;
+  bits[4] = (phich_res >> 1) & 1, bits[5] = phich_res & 1;
+  for (int i = 0; i < 8; i++) bits[6 + i] = ((sfn >> 2) >> (7 - i)) & 1;
+}
+int lte_mib_unpack(const uint8_t* bits, uint32_t* nof_prb, uint32_t* phich_ext, uint32_t* phich_res, uint32_t* sfn)
+{
+  static const uint32_t BW[8] = {6, 15, 25, 50, 75, 100, 0, 0};
+  uint32_t bw = (bits[0] << 2) | (bits[1] << 1) | bits[2], f = 0;
+  for (int i = 0; i < 8; i++) f = (f << 1) | bits[6 + i];
+  *nof_prb = BW[bw], *phich_ext = bits[3], *phich_res = (bits[4] << 1) | bits[5], *sfn = f << 2;
+  return BW[bw] ? 0 : -1;
+}
+uint32_t lte_pbch_crc_mask(uint32_t nof_ports) { return nof_ports == 1 ? 0x0000u : nof_ports == 2 ? 0xFFFFu : nof_ports == 4 ? 0x5555u : 0u; }

@@ -208,6 +208,26 @@ double   lte_rng_gauss(lte_rng_t* r);
 #endif
 #endif
 
+/* ---- PBCH / MIB (36.211 6.6, 36.212 5.3.1, 36.331 MasterInformationBlock): what srsran_ue_mib_decode + srsran_pbch_mib_unpack deliver
+ * at src/src/LTESniffer_Core.cc:382-396 ---- */
+#ifndef LTE_COMMON_PBCH_H
+#define LTE_COMMON_PBCH_H
+#ifdef __cplusplus
+extern "C" {
+#endif
+/* the 240 resource elements of one radio frame's PBCH part: slot 1 of subframe 0, symbols 0..3, the central 72 sub-carriers without the CRS
+ * positions of four ports; symbol-major, ascending sub-carrier */
+uint32_t lte_pbch_re(const lte_cell_t* c, uint16_t* k /* [240] */, uint8_t* l /* [240], 7..10 */);
+/* 24 MIB bits: dl-Bandwidth (3), phich-Duration (1), phich-Resource (2), systemFrameNumber (8 MSBs), 10 spare */
+void lte_mib_pack(uint32_t nof_prb, uint32_t phich_ext, uint32_t phich_res, uint32_t sfn, uint8_t* bits);
+int  lte_mib_unpack(const uint8_t* bits, uint32_t* nof_prb, uint32_t* phich_ext, uint32_t* phich_res, uint32_t* sfn);
+/* CRC mask of the antenna-port count (36.212 Table 5.3.1.1-1): 1 -> 0x0000, 2 -> 0xFFFF, 4 -> 0x5555; 0 for anything else */
+uint32_t lte_pbch_crc_mask(uint32_t nof_ports);
+#ifdef __cplusplus
+}
+#endif
+#endif
+
 /* ================================================================== uplink (PUSCH), 36.211 5.x / 36.213 8 */
 #ifndef LTE_COMMON_UL_H
 #define LTE_COMMON_UL_H

@@ -222,6 +222,26 @@ int lte_sim_subframe(lte_sim_t* s, uint32_t tti, cf_t* iq, lte_sim_truth_t* trut
     map_ctrl(s, d, ks, ls, 16);
   }
 
+  /* ---- PBCH ---- */
+  if (cfg->pbch && sf_idx == 0) {
+    const uint32_t sfn = (tti / 10) % 1024;
+    uint8_t        c40[40], d120[120], *e = (uint8_t*)malloc(1920), *sc = (uint8_t*)malloc(1920);
+    cf_t*          dq = (cf_t*)malloc(sizeof(cf_t) * 960);
+    lte_mib_pack(N, 0, 0, sfn, c40);
+    const uint32_t crc = lte_crc(LTE_CRC16, 16, c40, 24) ^ lte_pbch_crc_mask(cell->nof_ports);
+    for (int i = 0; i < 16; i++) c40[24 + i] = (crc >> (15 - i)) & 1;
+    lte_conv_encode(c40, 40, d120);
+    lte_rm_conv_tx(d120, 40, e, 1920);
+    lte_gold_bits(cell->cell_id, sc, 1920);
+    for (uint32_t i = 0; i < 1920; i++) e[i] ^= sc[i];
+    lte_modulate(e, 960, 2, dq);
+    uint16_t ks[240];
+    uint8_t  ls[240];
+    const uint32_t nre = lte_pbch_re(cell, ks, ls);
+    map_ctrl(s, dq + 240 * (sfn % 4), ks, ls, nre);
+    free(e), free(sc), free(dq);
+  }
+
   /* ---- scheduling ---- */
   uint32_t nof_cce = s->regs.nof_cce[cfi - 1];
   uint32_t search_cce = nof_cce; /* place DCIs anywhere legal; FALCON only searches the first 84 (falcon_pdcch.h:36) */
@@ -532,20 +552,25 @@ int lte_sim_subframe(lte_sim_t* s, uint32_t tti, cf_t* iq, lte_sim_truth_t* trut
     }
   }
   /* ---- channel + AWGN ---- */
+  const double cfo_w = 2.0 * M_PI * (double)cfg->cfo_hz / (15000.0 * (double)s->fft); /* radians per sample */
   if (cfg->harq_retx) lte_rng_seed(&rng, cfg->seed * 0x2545F4914F6CDD1Dull + 31ull * tti + 7); /* a retransmission meets its own noise */
   double sigma = pow(10.0, -cfg->snr_db / 20.0) * M_SQRT1_2;
   for (uint32_t a = 0; a < cell->nof_rx; a++) {
     cf_t* out = iq + (size_t)a * s->sf_len;
     for (uint32_t n = 0; n < s->sf_len; n++) {
-      double re = sigma * lte_rng_gauss(&rng), im = sigma * lte_rng_gauss(&rng);
+      double re = sigma * lte_rng_gauss(&rng), im = sigma * lte_rng_gauss(&rng), sr = 0.0, si = 0.0;
       for (uint32_t p = 0; p < cell->nof_ports; p++) {
         uint32_t dl = s->delay[a][p];
         if (n < dl) continue;
         cf_t x = s->td[p][n - dl];
-        re += (double)s->h_re[a][p] * x.re - (double)s->h_im[a][p] * x.im;
-        im += (double)s->h_re[a][p] * x.im + (double)s->h_im[a][p] * x.re;
+        sr += (double)s->h_re[a][p] * x.re - (double)s->h_im[a][p] * x.im;
+        si += (double)s->h_re[a][p] * x.im + (double)s->h_im[a][p] * x.re;
       }
-      out[n] = (cf_t){(float)re, (float)im};
+      if (cfo_w != 0.0) { /* receiver's oscillator is off by cfo_hz */
+        const double cr = cos(cfo_w * (double)n), ci = sin(cfo_w * (double)n), tr = sr * cr - si * ci;
+        si = sr * ci + si * cr, sr = tr;
+      }
+      out[n] = (cf_t){(float)(re + sr), (float)(im + si)};
     }
   }
   return 0;

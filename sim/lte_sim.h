@@ -31,7 +31,9 @@ typedef struct {
   uint32_t   ul_pusch;     /* 1: DCI-0 grants are decodable PUSCH allocations (L_prb in the DFT set, >= 3, back to back from PRB 0, MCS <= 20) */
   uint32_t   tb_swap;      /* 1: two-TB DCIs (2 / 2A) set the TB-to-codeword swap flag at random */
   uint32_t   harq_retx;    /* 1: subframes with (tti / 8) odd repeat the DCIs and transport blocks of tti - 8 with rv = 2 (same NDI, same HARQ process) */
-  uint32_t   reserved[4];
+  uint32_t   pbch;         /* 1: subframe 0 of every frame carries the PBCH (MIB: bandwidth, PHICH, SFN = tti / 10) */
+  float      cfo_hz;       /* carrier frequency offset applied to the generated samples (phase restarts every subframe, as srsran_cfo_correct sees it) */
+  uint32_t   reserved[2];
 } lte_sim_cfg_t;
 
 #define LTE_SIM_MAX_DCI 32

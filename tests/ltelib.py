@@ -22,7 +22,7 @@ class SimCfg(C.Structure):
                 ("dl_min", C.c_uint32), ("dl_max", C.c_uint32), ("ul_min", C.c_uint32), ("ul_max", C.c_uint32),
                 ("tm", C.c_uint32), ("mcs_min", C.c_uint32), ("mcs_max", C.c_uint32), ("si_period", C.c_uint32),
                 ("snr_db", C.c_float), ("chan_delay", C.c_uint32), ("fixed_L", C.c_uint32), ("full_band", C.c_uint32),
-                ("alt_table", C.c_uint32), ("ul_pusch", C.c_uint32), ("tb_swap", C.c_uint32), ("harq_retx", C.c_uint32), ("reserved", C.c_uint32 * 4)]
+                ("alt_table", C.c_uint32), ("ul_pusch", C.c_uint32), ("tb_swap", C.c_uint32), ("harq_retx", C.c_uint32), ("pbch", C.c_uint32), ("cfo_hz", C.c_float), ("reserved", C.c_uint32 * 2)]
 
 
 class DciTruth(C.Structure):
@@ -254,6 +254,22 @@ class Oracle:
         s, c = self._pp(sym, ce)
         r = self.L.lteo_pdsch_llr(self.h, sf_idx, cfi, rnti, C.byref(grant), s, c, ptr_array(llr), ptr_array(eq))
         return r, llr, eq
+
+    def pbch_decode(self, sym, ce):
+        """-> (found, mib bits[24], nof_ports, frame position q = SFN mod 4)"""
+        s, c = self._pp(sym, ce)
+        mib = np.zeros(24, np.uint8)
+        npo, fq = C.c_uint32(0), C.c_uint32(0)
+        self.L.lteo_pbch_decode.argtypes = None
+        r = self.L.lteo_pbch_decode(self.h, s, c, ptr(mib), C.byref(npo), C.byref(fq))
+        return r, mib, npo.value, fq.value
+
+    def cfo_correct(self, cfo_hz, iq):
+        out = np.zeros_like(iq)
+        self.L.lteo_cfo_correct.argtypes = [C.c_void_p, C.c_float, C.c_void_p, C.c_void_p]
+        for a in range(iq.shape[0]):
+            self.L.lteo_cfo_correct(self.h, cfo_hz, ptr(np.ascontiguousarray(iq[a])), ptr(out[a]))
+        return out
 
     def pdsch_decode_harq(self, sf_idx, cfi, rnti, grant, sym, ce, soft, combine, max_iter=8):
         """soft: [int16 array (16 * HARQ_CB_STRIDE) or None] per TB, combine: [0/1] per TB"""
