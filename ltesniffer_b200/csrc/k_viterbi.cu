@@ -107,15 +107,11 @@ template <int P0> __device__ __forceinline__ void vit_traceback(const uint32_t* 
 #undef TB_SLOW
 }
 
-__global__ void __launch_bounds__(VIT_WARPS * 32) dci_viterbi_kernel(const __grid_constant__ DevCell c, const float* __restrict__ llr_all,
-                                                                      const DevSfInfo* __restrict__ info, ltephy_cand_t* __restrict__ cands,
-                                                                      const VitConst vc)
+// One work item = (subframe, pair of locations, payload size) whose pair holds at least one decodable candidate (vit_worklist_kernel).
+__device__ __forceinline__ void vit_decode_item(const DevCell& c, const float* __restrict__ llr_all, const DevSfInfo* __restrict__ info,
+                                                ltephy_cand_t* __restrict__ cands, const VitConst& vc, VitWarpSmem& sm, const uint32_t lane,
+                                                const uint32_t pair, const uint32_t si, const uint32_t sf)
 {
-  __shared__ VitWarpSmem sm_all[VIT_WARPS];
-  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t pair = blockIdx.x * VIT_WARPS + warp, si = blockIdx.y, sf = blockIdx.z;
-  VitWarpSmem&   sm   = sm_all[warp];
-
   const uint32_t cfi = info[sf].cfi;
   if (cfi < 1 || cfi > 3) return;
   const uint32_t nloc = c.nloc[cfi - 1];
@@ -349,13 +345,78 @@ __global__ void __launch_bounds__(VIT_WARPS * 32) dci_viterbi_kernel(const __gri
   }
 }
 
-extern "C" void launch_viterbi(const DevCell& c, const float* llr, const DevSfInfo* info, ltephy_cand_t* cands, uint32_t n, cudaStream_t st,
-                               uint64_t* launches)
+// Work list of the decoder: every (subframe, pair, size) whose pair has a location that exists and whose CCEs are all above the power floor
+// (the rule the decoder applies itself); table entries of all other pairs are zeroed here, so nothing stale survives a change of CFI.
+// One CTA per subframe, one thread per pair of locations; items = work[16 ...], work[0] = count.
+#define VIT_WORK_HDR 16u
+__global__ void __launch_bounds__(128) vit_worklist_kernel(const __grid_constant__ DevCell c, const DevSfInfo* __restrict__ info, uint32_t* __restrict__ work,
+                                                           ltephy_cand_t* __restrict__ cands)
 {
-  const uint32_t max_pairs = (LTEPHY_MAX_LOC / 2 + VIT_WARPS - 1) / VIT_WARPS;
+  __shared__ uint32_t scan[128];
+  __shared__ uint32_t base_s;
+  const uint32_t sf = blockIdx.x, pair = threadIdx.x, cfi = info[sf].cfi;
+  const uint32_t nloc = (cfi >= 1 && cfi <= 3) ? c.nloc[cfi - 1] : 0;
+  bool           any = false;
+  if (pair < LTEPHY_MAX_LOC / 2) {
+    for (uint32_t cd = 0; cd < 2; cd++) {
+      const uint32_t li = 2 * pair + cd;
+      bool           v  = li < nloc;
+      if (v && (c.flags & LTEPHY_FLAG_SKIP_LOW_POWER)) {
+        const uint32_t e = c.loc_tab[cfi - 1][li], ncce = e & 0xFFu, L = e >> 8;
+        for (uint32_t i = ncce; i < ncce + (1u << L); i++)
+          if (info[sf].cce_power[i] < 0.7f) v = false;
+      }
+      any |= v;
+    }
+    if (!any) {
+      const ltephy_cand_t z{};
+      for (uint32_t cd = 0; cd < 2; cd++)
+        for (uint32_t si = 0; si < c.nsizes; si++) cands[((size_t)sf * LTEPHY_MAX_LOC + 2 * pair + cd) * LTEPHY_MAX_SIZES + si] = z;
+    }
+  }
+  const uint32_t mine = any ? c.nsizes : 0u;
+  scan[threadIdx.x]   = mine;
+  __syncthreads();
+  for (uint32_t off = 1; off < 128; off <<= 1) { // inclusive scan
+    const uint32_t v = threadIdx.x >= off ? scan[threadIdx.x - off] : 0u;
+    __syncthreads();
+    scan[threadIdx.x] += v;
+    __syncthreads();
+  }
+  if (threadIdx.x == 127) base_s = atomicAdd(&work[0], scan[127]);
+  __syncthreads();
+  uint32_t w = VIT_WORK_HDR + base_s + scan[threadIdx.x] - mine;
+  for (uint32_t si = 0; si < mine; si++) work[w + si] = (sf * 128u + pair) * 8u + si;
+}
+
+__global__ void __launch_bounds__(VIT_WARPS * 32) dci_viterbi_kernel(const __grid_constant__ DevCell c, const float* __restrict__ llr_all,
+                                                                      const DevSfInfo* __restrict__ info, ltephy_cand_t* __restrict__ cands,
+                                                                      const uint32_t* __restrict__ work, const VitConst vc)
+{
+  __shared__ VitWarpSmem sm_all[VIT_WARPS];
+  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31, count = work[0];
+  for (uint32_t it = blockIdx.x * VIT_WARPS + warp; it < count; it += gridDim.x * VIT_WARPS) { // every warp of the grid decodes real work
+    const uint32_t item = work[VIT_WORK_HDR + it];
+    vit_decode_item(c, llr_all, info, cands, vc, sm_all[warp], lane, (item >> 3) & 127u, item & 7u, item >> 10);
+    __syncwarp(); // the next item's prologue reuses the decision store
+  }
+}
+
+extern "C" void launch_viterbi(const DevCell& c, const float* llr, const DevSfInfo* info, ltephy_cand_t* cands, uint32_t* work, uint32_t n,
+                               cudaStream_t st, uint64_t* launches)
+{
+  if (!n) return;
   const VitConst vc{1u, 0xFFFFFFFFu};
-  dci_viterbi_kernel<<<dim3(max_pairs, c.nsizes, n), VIT_WARPS * 32, 0, st>>>(c, llr, info, cands, vc);
-  *launches += 1;
+  int            dev = 0, sms = 148, per_sm = 8;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, dci_viterbi_kernel, VIT_WARPS * 32, 0);
+  cudaMemsetAsync(work, 0, VIT_WORK_HDR * sizeof(uint32_t), st);
+  vit_worklist_kernel<<<n, 128, 0, st>>>(c, info, work, cands);
+  const uint32_t max_items = n * (LTEPHY_MAX_LOC / 2) * c.nsizes, want = (max_items + VIT_WARPS - 1) / VIT_WARPS;
+  const uint32_t grid = (uint32_t)sms * (uint32_t)(per_sm > 0 ? per_sm : 1);
+  dci_viterbi_kernel<<<grid < want ? grid : want, VIT_WARPS * 32, 0, st>>>(c, llr, info, cands, work, vc);
+  *launches += 2;
 }
 
 // ---------------------------------------------------------------------------------------------------

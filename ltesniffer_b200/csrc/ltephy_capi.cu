@@ -22,7 +22,7 @@ extern "C" {
 void launch_frontend(const DevCell&, const float2*, float2*, float2*, float*, DevSfInfo*, uint32_t, cudaStream_t, uint64_t*);
 void launch_chest_interp(const DevCell&, const float2*, float2*, uint32_t, cudaStream_t, uint64_t*);
 void launch_pbch(const DevCell&, const float2*, const float2*, const DevSfInfo*, void*, uint32_t, cudaStream_t, uint64_t*);
-void launch_viterbi(const DevCell&, const float*, const DevSfInfo*, ltephy_cand_t*, uint32_t, cudaStream_t, uint64_t*);
+void launch_viterbi(const DevCell&, const float*, const DevSfInfo*, ltephy_cand_t*, uint32_t*, uint32_t, cudaStream_t, uint64_t*);
 void launch_compact(const DevCell&, const DevSfInfo*, const ltephy_cand_t*, ltephy_compact_t*, uint32_t, cudaStream_t, uint64_t*);
 void launch_pdsch_front(const DevCell&, const DevGrant*, uint32_t, uint32_t, const float2*, const float2*, const uint32_t*, const uint32_t*, uint32_t,
                         uint32_t*, short*, cudaStream_t, uint64_t*);
@@ -239,7 +239,7 @@ extern "C" int ltephy_create(const ltephy_cfg_t* cfg, ltephy_t** out)
   }
   const size_t S = cfg->max_subframes, g = (size_t)14 * c.nsc;
   if (h->d_iq.reserve(S * c.nof_rx * c.sf_len) || h->d_sym.reserve(S * c.nof_rx * g) || h->d_pil.reserve(S * c.nof_ports * c.nof_rx * 4 * 2 * c.nof_prb) ||
-      h->d_llr.reserve(S * LLR_STRIDE) || h->d_info.reserve(S) || h->d_cands.reserve(S * LTEPHY_MAX_LOC * LTEPHY_MAX_SIZES) ||
+      h->d_llr.reserve(S * LLR_STRIDE) || h->d_info.reserve(S) || h->d_cands.reserve(S * LTEPHY_MAX_LOC * LTEPHY_MAX_SIZES) || h->d_vwork.reserve(S * (LTEPHY_MAX_LOC / 2) * LTEPHY_MAX_SIZES + 16) ||
       h->h_info.reserve(S) || h->d_compact.reserve(S) || h->h_compact.reserve(S) || h->d_rm.reserve((size_t)16 << 20) || h->d_pi.reserve((size_t)188 * 6144))
     return fail(LTEPHY_ERROR, "device allocation failed");
   CU(cudaMemset(h->d_cands.p, 0, h->d_cands.cap * sizeof(ltephy_cand_t)));
@@ -256,7 +256,7 @@ extern "C" void ltephy_destroy(ltephy_t* h)
   h->d_iq.release(), h->d_sym.release(), h->d_ce.release(), h->d_pil.release(), h->d_llr.release(), h->d_info.release(), h->d_cands.release();
   h->h_info.release(), h->d_compact.release(), h->h_compact.release(), h->d_grants.release(), h->d_cbs.release(), h->d_pairs.release(), h->d_tbs.release(), h->d_pair_pi_off.release();
   h->d_tscratch.release(), h->d_tqueue.release();
-  h->d_seq.release(), h->d_rm.release(), h->d_turbo.release(), h->d_pllr.release(), h->d_pi.release(), h->d_payload.release(), h->d_harq.release(), h->d_cfo.release(), h->d_mib.release();
+  h->d_seq.release(), h->d_rm.release(), h->d_turbo.release(), h->d_pllr.release(), h->d_pi.release(), h->d_payload.release(), h->d_harq.release(), h->d_cfo.release(), h->d_mib.release(), h->d_vwork.release();
   h->d_cb_iters.release(), h->d_cb_crc.release(), h->d_res.release(), h->h_res.release(), h->h_payload.release(), h->h_stage.release();
   h->d_uliq.release(), h->d_ulsym.release(), h->d_ulpool.release(), h->d_ulgrants.release(), h->d_ulchest.release(), h->h_ulchest.release();
   for (auto& e : h->ev)
@@ -342,7 +342,7 @@ static int phase_a_common(ltephy* h, const float2* iq_dev, const float2* iq_host
     last = h->ev_h2d;
   }
   launch_frontend(c, iq_dev, h->d_sym.p, h->d_pil.p, h->d_llr.p, h->d_info.p, n, h->stream, &h->launches);
-  launch_viterbi(c, h->d_llr.p, h->d_info.p, h->d_cands.p, n, h->stream, &h->launches);
+  launch_viterbi(c, h->d_llr.p, h->d_info.p, h->d_cands.p, h->d_vwork.p, n, h->stream, &h->launches);
   launch_compact(c, h->d_info.p, h->d_cands.p, h->d_compact.p, n, h->stream, &h->launches);
   CU(cudaEventRecord(h->ev[1], h->stream));
   CU(cudaGetLastError());
@@ -1045,7 +1045,7 @@ extern "C" int ltephy_dci_sweep(ltephy_t* h, const float* llr, const uint32_t* c
   CU(cudaMemcpyAsync(h->d_info.p, h->h_info.p, n * sizeof(DevSfInfo), cudaMemcpyHostToDevice, h->stream));
   CU(cudaMemcpyAsync(h->d_llr.p, llr, (size_t)n * LLR_STRIDE * sizeof(float), cudaMemcpyHostToDevice, h->stream));
   CU(cudaEventRecord(h->ev[0], h->stream));
-  launch_viterbi(h->dc, h->d_llr.p, h->d_info.p, h->d_cands.p, n, h->stream, &h->launches);
+  launch_viterbi(h->dc, h->d_llr.p, h->d_info.p, h->d_cands.p, h->d_vwork.p, n, h->stream, &h->launches);
   launch_compact(h->dc, h->d_info.p, h->d_cands.p, h->d_compact.p, n, h->stream, &h->launches);
   CU(cudaEventRecord(h->ev[1], h->stream));
   CU(cudaMemcpyAsync(cands, h->d_cands.p, (size_t)n * LTEPHY_MAX_LOC * LTEPHY_MAX_SIZES * sizeof(ltephy_cand_t), cudaMemcpyDeviceToHost, h->stream));

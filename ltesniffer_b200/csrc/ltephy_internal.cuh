@@ -89,6 +89,7 @@ struct ltephy {
   cudaStream_t       stream = nullptr;
   cudaEvent_t        ev[6]{}, mark[2]{}, ev_h2d = nullptr;
   DevBuf<float2>     d_cfo;                  // per-sample rotation of ltephy_set_cfo
+  DevBuf<uint32_t>   d_vwork;                // work list of the Viterbi kernel: count + (subframe, pair, size) items
   DevBuf<uint32_t>   d_mib;                  // 4 words per subframe (pbch_kernel)
   DevBuf<short>      d_harq;                 // HARQ store: harq_slots x LTEPHY_HARQ_SLOT_BYTES
   uint32_t           harq_slots = 0, harq_max_gen = 0;
