@@ -26,13 +26,7 @@ inline uint32_t viaddmax_u(uint32_t a, uint32_t b, uint32_t c)
   const uint32_t s = vadd2(a, b);
   return f2(ulo(s) > ulo(c) ? ulo(s) : ulo(c), uhi(s) > uhi(c) ? uhi(s) : uhi(c));
 }
-inline uint32_t vmax3_u(uint32_t a, uint32_t b, uint32_t c)
-{
-  auto m = [](int x, int y) { return x > y ? x : y; };
-  return f2(m(m(ulo(a), ulo(b)), ulo(c)), m(m(uhi(a), uhi(b)), uhi(c)));
-}
 } // namespace td_host
-#define TD_VMAX3_U(a, b, c) td_host::vmax3_u(a, b, c)
 #define TD_VADD2(a, b) td_host::vadd2(a, b)
 #define TD_VSUB2(a, b) td_host::vsub2(a, b)
 #define TD_VMAXS2(a, b) td_host::vmaxs2(a, b)
@@ -46,7 +40,6 @@ inline uint32_t vmax3_u(uint32_t a, uint32_t b, uint32_t c)
 #define TD_VMINS2(a, b) __vmins2(a, b)
 #define TD_VIADDMAX_S(a, b, c) __viaddmax_s16x2(a, b, c)
 #define TD_VIADDMAX_U(a, b, c) __viaddmax_u16x2(a, b, c)
-#define TD_VMAX3_U(a, b, c) __vimax3_u16x2(a, b, c)
 #endif
 
 #define TD_WL 32
@@ -82,7 +75,6 @@ TD_HD uint32_t vsub(uint32_t a, uint32_t b) { return TD_VSUB2(a, b); }
 TD_HD uint32_t vamax(uint32_t a, uint32_t b, uint32_t c) { return TD_VIADDMAX_S(a, b, c); }  // max(a+b, c), signed fields
 TD_HD uint32_t vamaxu(uint32_t a, uint32_t b, uint32_t c) { return TD_VIADDMAX_U(a, b, c); } // unsigned fields
 TD_HD uint32_t vmax(uint32_t a, uint32_t b) { return TD_VMAXS2(a, b); }
-TD_HD uint32_t vmax3u(uint32_t a, uint32_t b, uint32_t c) { return TD_VMAX3_U(a, b, c); } // three-input max, unsigned fields (VIMNMX3)
 TD_HD uint32_t vmin(uint32_t a, uint32_t b) { return TD_VMINS2(a, b); }
 TD_HD uint32_t pk2(int lo, int hi) { return ((uint32_t)lo & 0xFFFFu) | ((uint32_t)hi << 16); }
 TD_HD int      lo_s(uint32_t v) { return (int)(short)(v & 0xFFFFu); }
@@ -129,15 +121,12 @@ TD_HD void beta_llr_step(const TdConst& c, St8& b, const St8& al, uint32_t X32, 
   c0[5] = add32(c, b.s[6], P32), c1[5] = add32(c, b.s[2], X32);
   c0[6] = b.s[7], c1[6] = add32(c, b.s[3], G032);
   c0[7] = b.s[3], c1[7] = add32(c, b.s[7], G032);
-  // 8 sums per numerator on the FMA pipe, then a tree of three-input maxes: 3 ALU instructions per numerator instead of the 7 fused
-  // add-max of a chain (the ALU pipe is what bounds this kernel)
-  {
-    const uint32_t a1 = vmax3u(add32(c, al.s[0], c1[0]), add32(c, al.s[1], c1[1]), add32(c, al.s[2], c1[2]));
-    const uint32_t b1 = vmax3u(add32(c, al.s[3], c1[3]), add32(c, al.s[4], c1[4]), add32(c, al.s[5], c1[5]));
-    m1                = vmax3u(vamaxu(al.s[6], c1[6], a1), add32(c, al.s[7], c1[7]), b1);
-    const uint32_t a0 = vmax3u(add32(c, al.s[0], c0[0]), add32(c, al.s[1], c0[1]), add32(c, al.s[2], c0[2]));
-    const uint32_t b0 = vmax3u(add32(c, al.s[3], c0[3]), add32(c, al.s[4], c0[4]), add32(c, al.s[5], c0[5]));
-    m0                = vmax3u(vamaxu(al.s[6], c0[6], a0), add32(c, al.s[7], c0[7]), b0);
+  m1    = add32(c, al.s[0], c1[0]);
+  m0    = add32(c, al.s[0], c0[0]);
+#pragma unroll
+  for (int s = 1; s < 8; s++) {
+    m1 = vamaxu(al.s[s], c1[s], m1);
+    m0 = vamaxu(al.s[s], c0[s], m0);
   }
 #pragma unroll
   for (int s = 0; s < 8; s++) b.s[s] = vmax(c0[s], c1[s]);
