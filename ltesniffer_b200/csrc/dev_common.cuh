@@ -9,6 +9,7 @@
 
 struct DevCell {
   uint32_t nof_prb, nof_ports, cell_id, nof_rx, fft, log2n, nsc, sf_len;
+  uint32_t sub;                   // power-of-two transform length: fft, or fft / 3 for a 3 * 2^k symbol size (log2n = log2(sub))
   uint32_t sym_off[14];
   uint32_t nof_cce[3], nloc[3];
   uint32_t crs_off[2][2]; // [port][0: symbol 0 of slot, 1: symbol 4 of slot]
@@ -20,8 +21,9 @@ struct DevCell {
   uint32_t pcfich_scr[10]; // 32 scrambling bits per subframe index
   uint16_t pcfich_idx[16];
   uint32_t pdcch_scr_words;       // words per subframe index
-  const float2*   tw;             // [fft/2]
-  const float2*   tw_st;          // [fft] per-stage tables: tw_st[H + pos] = tw[pos * fft / (2 H)], H = 1, 2, .. fft/2, pos < H
+  const float2*   tw;             // [sub/2]
+  const float2*   tw_st;          // [sub] per-stage tables: tw_st[H + pos] = tw[pos * sub / (2 H)], H = 1, 2, .. sub/2, pos < H
+  const float2*   w3;             // [2][fft] radix-3 twiddles W_N^k, W_N^(2k) of a 3 * 2^k symbol size, nullptr otherwise
   const float2*   ul_rot;         // [fft] exp(-j pi i / N)
   const float2*   crs;            // [10][2][4][2*nof_prb]
   const uint16_t* pdcch_idx[3];   // [nof_cce*9][4]

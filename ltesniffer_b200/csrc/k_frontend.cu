@@ -55,19 +55,21 @@ __device__ __forceinline__ void fft_pass(float2* work, const float2* __restrict_
   }
 }
 
-template <bool UL>
+// R3: the symbol has 3 * 2^k samples (srsRAN's default sampling rates, 1536 at 100 PRB): three power-of-two transforms F_r of x[3 m + r] run
+// side by side (thread = (r, t)), then X[k] = (F0[k mod M] + W_N^k F1[k mod M]) + W_N^(2k) F2[k mod M] -- the oracle's expression.
+template <bool UL, bool R3>
 __global__ void __launch_bounds__(256) ofdm_rx_kernel(const __grid_constant__ DevCell c, const float2* __restrict__ iq, float2* __restrict__ sym)
 {
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  float2*        work = reinterpret_cast<float2*>(smem_raw); // [fft], swizzled
-  const uint32_t l = blockIdx.x, a = blockIdx.y, sf = blockIdx.z, tid = threadIdx.x, nt = blockDim.x, n = c.fft, L = c.log2n;
+  const uint32_t l = blockIdx.x, a = blockIdx.y, sf = blockIdx.z, n = c.fft, M = c.sub, L = c.log2n, q8 = M >> 3;
+  const uint32_t nt = R3 ? blockDim.x / 3 : blockDim.x, r = R3 ? threadIdx.x / nt : 0u, tid = R3 ? threadIdx.x % nt : threadIdx.x;
+  float2*        work = reinterpret_cast<float2*>(smem_raw) + r * M; // [3][M] or [fft], swizzled
   const uint32_t nant = UL ? 1u : c.nof_rx; // the UL carrier is decoded from one antenna (UL_Sniffer_PUSCH.cc:391-392)
   const float2*  src = iq + ((size_t)sf * nant + a) * c.sf_len + c.sym_off[l];
   const float2*  tw_st = c.tw_st;
 
-  // ---- pass 1: stages 1..3 of group g = bitrev(t): A[8 g + j] = x[bitrev3(j) n/8 + t]
+  // ---- pass 1: stages 1..3 of group g = bitrev(t): A[8 g + j] = x_r[bitrev3(j) M/8 + t], x_r[i] = x[3 i + r] (x[i] for a power-of-two symbol)
   {
-    const uint32_t q8 = n >> 3;
     const float2   w1 = __ldg(&tw_st[1]), w20 = __ldg(&tw_st[2]), w21 = __ldg(&tw_st[3]);
     const float2   w40 = __ldg(&tw_st[4]), w41 = __ldg(&tw_st[5]), w42 = __ldg(&tw_st[6]), w43 = __ldg(&tw_st[7]);
     for (uint32_t t = tid; t < q8; t += nt) {
@@ -75,15 +77,15 @@ __global__ void __launch_bounds__(256) ofdm_rx_kernel(const __grid_constant__ De
       float2         v[8];
 #pragma unroll
       for (uint32_t j = 0; j < 8; j++) {
-        const uint32_t m = ((j & 1u) << 2) | (j & 2u) | (j >> 2), idx = t + m * q8;
+        const uint32_t m = ((j & 1u) << 2) | (j & 2u) | (j >> 2), idx = R3 ? 3 * (t + m * q8) + r : t + m * q8;
         float2         x = src[idx];
         if (!UL && c.cfo_rot) { // constant frequency-offset correction of the file samples (srsran_cfo_correct in srsran_ue_sync's file mode)
-          const float2 r = __ldg(&c.cfo_rot[c.sym_off[l] + idx]);
-          x              = make_float2(x.x * r.x - x.y * r.y, x.x * r.y + x.y * r.x);
+          const float2 rr = __ldg(&c.cfo_rot[c.sym_off[l] + idx]);
+          x               = make_float2(x.x * rr.x - x.y * rr.y, x.x * rr.y + x.y * rr.x);
         }
         if (UL) { // remove the 7.5 kHz half-subcarrier shift: multiply by exp(-j pi i / N) (srsran_enb_ul_fft)
-          const float2 r = __ldg(&c.ul_rot[idx]);
-          x              = make_float2(x.x * r.x - x.y * r.y, x.x * r.y + x.y * r.x);
+          const float2 rr = __ldg(&c.ul_rot[idx]);
+          x               = make_float2(x.x * rr.x - x.y * rr.y, x.x * rr.y + x.y * rr.x);
         }
         v[j] = x;
       }
@@ -97,25 +99,34 @@ __global__ void __launch_bounds__(256) ofdm_rx_kernel(const __grid_constant__ De
   __syncthreads();
   uint32_t s = 4;
   while (s + 2 <= L) {
-    fft_pass<3>(work, tw_st, n, s, tid, nt);
+    fft_pass<3>(work, tw_st, M, s, tid, nt);
     __syncthreads();
     s += 3;
   }
   if (s + 1 <= L) {
-    fft_pass<2>(work, tw_st, n, s, tid, nt);
+    fft_pass<2>(work, tw_st, M, s, tid, nt);
     __syncthreads();
     s += 2;
   }
   if (s <= L) {
-    fft_pass<1>(work, tw_st, n, s, tid, nt);
+    fft_pass<1>(work, tw_st, M, s, tid, nt);
     __syncthreads();
   }
   float2*        dst = sym + (((size_t)sf * nant + a) * 14 + l) * c.nsc;
   const uint32_t h   = c.nsc / 2;
-  if (UL) {
-    for (uint32_t k = tid; k < c.nsc; k += nt) dst[k] = work[fft_swz((k + n - h) % n)]; // no DC gap on the uplink
-  } else {
-    for (uint32_t k = tid; k < c.nsc; k += nt) dst[k] = work[fft_swz(k < h ? n - h + k : k - h + 1)];
+  const float2*  all = reinterpret_cast<const float2*>(smem_raw);
+  for (uint32_t k = threadIdx.x; k < c.nsc; k += blockDim.x) {
+    const uint32_t bin = UL ? (k + n - h) % n : (k < h ? n - h + k : k - h + 1); // no DC gap on the uplink
+    if (!R3) {
+      dst[k] = all[fft_swz(bin)];
+    } else {
+      const uint32_t kp = bin % M;
+      const float2   f0 = all[fft_swz(kp)], f1 = all[M + fft_swz(kp)], f2 = all[2 * M + fft_swz(kp)];
+      const float2   u1 = __ldg(&c.w3[bin]), u2 = __ldg(&c.w3[n + bin]);
+      const float    t1r = u1.x * f1.x - u1.y * f1.y, t1i = u1.x * f1.y + u1.y * f1.x;
+      const float    t2r = u2.x * f2.x - u2.y * f2.y, t2i = u2.x * f2.y + u2.y * f2.x;
+      dst[k]             = make_float2((f0.x + t1r) + t2r, (f0.y + t1i) + t2i);
+    }
   }
 }
 
@@ -324,9 +335,11 @@ extern "C" void launch_chest_interp(const DevCell& c, const float2* pil, float2*
 extern "C" void launch_frontend(const DevCell& c, const float2* iq, float2* sym, float2* ce, float* llr, DevSfInfo* info, uint32_t n,
                                 cudaStream_t st, uint64_t* launches)
 {
-  const uint32_t fft_threads = c.fft / 8 < 32 ? 32 : c.fft / 8;
-  const size_t   smem_fft    = (size_t)c.fft * sizeof(float2);
-  ofdm_rx_kernel<false><<<dim3(14, c.nof_rx, n), fft_threads, smem_fft, st>>>(c, iq, sym);
+  const size_t smem_fft = (size_t)c.fft * sizeof(float2);
+  if (c.sub == c.fft)
+    ofdm_rx_kernel<false, false><<<dim3(14, c.nof_rx, n), c.fft / 8 < 32 ? 32 : c.fft / 8, smem_fft, st>>>(c, iq, sym);
+  else
+    ofdm_rx_kernel<false, true><<<dim3(14, c.nof_rx, n), 3 * (c.sub / 8), smem_fft, st>>>(c, iq, sym);
   const size_t smem_ch = (size_t)2 * NPILSYM * 2 * c.nof_prb * sizeof(float2);
   chest_kernel<<<dim3(c.nof_ports * c.nof_rx, n), 256, smem_ch, st>>>(c, sym, ce, info);
   rb_power_kernel<<<n, 128, 0, st>>>(c, sym, info);
@@ -336,8 +349,10 @@ extern "C" void launch_frontend(const DevCell& c, const float2* iq, float2* sym,
 
 extern "C" void launch_ul_ofdm(const DevCell& c, const float2* iq, float2* sym, uint32_t n, cudaStream_t st, uint64_t* launches)
 {
-  const uint32_t fft_threads = c.fft / 8 < 32 ? 32 : c.fft / 8;
-  const size_t   smem_fft    = (size_t)c.fft * sizeof(float2);
-  ofdm_rx_kernel<true><<<dim3(14, 1, n), fft_threads, smem_fft, st>>>(c, iq, sym);
+  const size_t smem_fft = (size_t)c.fft * sizeof(float2);
+  if (c.sub == c.fft)
+    ofdm_rx_kernel<true, false><<<dim3(14, 1, n), c.fft / 8 < 32 ? 32 : c.fft / 8, smem_fft, st>>>(c, iq, sym);
+  else
+    ofdm_rx_kernel<true, true><<<dim3(14, 1, n), 3 * (c.sub / 8), smem_fft, st>>>(c, iq, sym);
   *launches += 1;
 }

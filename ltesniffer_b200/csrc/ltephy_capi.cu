@@ -81,8 +81,13 @@ extern "C" int ltephy_create(const ltephy_cfg_t* cfg, ltephy_t** out)
   if (cfg->nof_prb <= 10 || cfg->nof_prb > 100 || cfg->nof_ports < 1 || cfg->nof_ports > 2 || cfg->nof_rx < 1 || cfg->nof_rx > 2 ||
       cfg->max_subframes == 0)
     return fail(LTEPHY_ERROR_INVALID_INPUTS, "unsupported cell/batch configuration");
-  if (cfg->symbol_sz && cfg->symbol_sz != ltehost::fft_size(cfg->nof_prb))
-    return fail(LTEPHY_ERROR_INVALID_INPUTS, "symbol size %u not supported for %u PRB (standard rate: %u)", cfg->symbol_sz, cfg->nof_prb, ltehost::fft_size(cfg->nof_prb));
+  // 2^k or 3 * 2^k samples per symbol, wide enough for the carrier: the standard LTE rate, or what srsran_symbol_sz answers in srsRAN's default
+  // build (3/4 of it: 1536 at 100 PRB, 768 at 50, 384 at 25 -- the rate LTESniffer records at)
+  if (cfg->symbol_sz) {
+    const uint32_t N = cfg->symbol_sz, M = N % 3 ? N : N / 3;
+    if ((M & (M - 1)) || M < 128 || N > 2048 || N <= 12 * cfg->nof_prb)
+      return fail(LTEPHY_ERROR_INVALID_INPUTS, "symbol size %u not supported for %u PRB (2^k or 3 * 2^k, above %u, at most 2048)", N, cfg->nof_prb, 12 * cfg->nof_prb);
+  }
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(LTEPHY_ERROR, "no CUDA device: this library has no CPU path");
   CU(cudaSetDevice(cfg->device));
@@ -111,8 +116,9 @@ extern "C" int ltephy_create(const ltephy_cfg_t* cfg, ltephy_t** out)
 
   DevCell& c = h->dc;
   c.nof_prb = cfg->nof_prb, c.nof_ports = cfg->nof_ports, c.cell_id = cfg->cell_id, c.nof_rx = cfg->nof_rx;
-  c.fft = ltehost::fft_size(cfg->nof_prb), c.nsc = 12 * cfg->nof_prb, c.sf_len = 15 * c.fft;
-  for (c.log2n = 0; (1u << c.log2n) < c.fft; c.log2n++) {
+  c.fft = cfg->symbol_sz ? cfg->symbol_sz : ltehost::fft_size(cfg->nof_prb), c.nsc = 12 * cfg->nof_prb, c.sf_len = 15 * c.fft;
+  c.sub = c.fft % 3 ? c.fft : c.fft / 3; // length of the power-of-two transforms: the whole symbol, or a third of a 3 * 2^k one
+  for (c.log2n = 0; (1u << c.log2n) < c.sub; c.log2n++) {
   }
   uint32_t pos = 0;
   for (uint32_t l = 0; l < 14; l++) {
@@ -149,16 +155,26 @@ extern "C" int ltephy_create(const ltephy_cfg_t* cfg, ltephy_t** out)
     }
   }
   { // twiddles
-    std::vector<float2> tw(c.fft / 2);
-    for (uint32_t k = 0; k < c.fft / 2; k++) {
-      double a = -2.0 * M_PI * (double)k / (double)c.fft;
+    std::vector<float2> tw(c.sub / 2);
+    for (uint32_t k = 0; k < c.sub / 2; k++) {
+      double a = -2.0 * M_PI * (double)k / (double)c.sub;
       tw[k]    = make_float2((float)std::cos(a), (float)std::sin(a));
     }
     c.tw = upload(h, tw.data(), tw.size());
-    std::vector<float2> tws(c.fft, make_float2(0.0f, 0.0f)); // per-stage contiguous copies: tws[H + pos] = tw[pos * fft / (2 H)]
-    for (uint32_t H = 1; H <= c.fft / 2; H *= 2)
-      for (uint32_t pos = 0; pos < H; pos++) tws[H + pos] = tw[(size_t)pos * (c.fft / (2 * H))];
+    std::vector<float2> tws(c.sub, make_float2(0.0f, 0.0f)); // per-stage contiguous copies: tws[H + pos] = tw[pos * sub / (2 H)]
+    for (uint32_t H = 1; H <= c.sub / 2; H *= 2)
+      for (uint32_t pos = 0; pos < H; pos++) tws[H + pos] = tw[(size_t)pos * (c.sub / (2 * H))];
     c.tw_st = upload(h, tws.data(), tws.size());
+    c.w3    = nullptr;
+    if (c.sub != c.fft) { // radix-3 step of a 3 * 2^k symbol: w3[k] = W_N^k, w3[N + k] = W_N^(2k)
+      std::vector<float2> w3((size_t)2 * c.fft);
+      for (uint32_t k = 0; k < c.fft; k++)
+        for (uint32_t r = 1; r < 3; r++) {
+          const double a = -2.0 * M_PI * (double)((uint64_t)r * k % c.fft) / (double)c.fft;
+          w3[(size_t)(r - 1) * c.fft + k] = make_float2((float)std::cos(a), (float)std::sin(a));
+        }
+      c.w3 = upload(h, w3.data(), w3.size());
+    }
     std::vector<float2> rot(c.fft);
     for (uint32_t i = 0; i < c.fft; i++) {
       double ph = M_PI * (double)i / (double)c.fft;

@@ -14,7 +14,8 @@ static const uint32_t PIL_L[NPILSYM] = {0, 4, 7, 11};
 struct lteo {
   lte_cell_t cell;
   lte_regs_t regs;
-  uint32_t   fft, nsc, sf_len, log2n;
+  uint32_t   fft, nsc, sf_len, log2n, sub; /* sub: length of the power-of-two transforms (fft or fft / 3) */
+  cf_t*      w3;                        /* radix-3 twiddles of a 3 * 2^k symbol size, NULL otherwise */
   float *    tw_re, *tw_im; /* tw[k] = exp(-2 pi i k / N), k < N/2, rounded from double */
   uint16_t*  bitrev;
   uint32_t   sym_off[14];
@@ -50,20 +51,31 @@ lteo_t* lteo_create(const lte_cell_t* cell)
     free(q);
     return NULL;
   }
-  q->fft    = lte_fft_size(cell->nof_prb);
+  q->fft    = lte_cell_fft(cell);
   q->nsc    = 12 * cell->nof_prb;
-  q->sf_len = lte_sf_len(cell->nof_prb);
-  for (q->log2n = 0; (1u << q->log2n) < q->fft; q->log2n++) {
+  q->sf_len = 15u * q->fft;
+  /* 3 * 2^k symbol sizes (srsRAN's default rates): three power-of-two transforms of length sub = fft / 3 and one radix-3 step */
+  q->sub    = q->fft % 3 ? q->fft : q->fft / 3;
+  for (q->log2n = 0; (1u << q->log2n) < q->sub; q->log2n++) {
   }
-  q->tw_re  = (float*)malloc(sizeof(float) * q->fft / 2);
-  q->tw_im  = (float*)malloc(sizeof(float) * q->fft / 2);
-  q->bitrev = (uint16_t*)malloc(sizeof(uint16_t) * q->fft);
-  for (uint32_t k = 0; k < q->fft / 2; k++) {
-    double a    = -2.0 * M_PI * (double)k / (double)q->fft;
+  q->tw_re  = (float*)malloc(sizeof(float) * q->sub / 2);
+  q->tw_im  = (float*)malloc(sizeof(float) * q->sub / 2);
+  q->bitrev = (uint16_t*)malloc(sizeof(uint16_t) * q->sub);
+  for (uint32_t k = 0; k < q->sub / 2; k++) {
+    double a    = -2.0 * M_PI * (double)k / (double)q->sub;
     q->tw_re[k] = (float)cos(a);
     q->tw_im[k] = (float)sin(a);
   }
-  for (uint32_t i = 0; i < q->fft; i++) {
+  q->w3 = NULL;
+  if (q->sub != q->fft) {
+    q->w3 = (cf_t*)malloc(sizeof(cf_t) * 2 * q->fft); /* w3[k] = W_N^k, w3[N + k] = W_N^(2k) */
+    for (uint32_t k = 0; k < q->fft; k++)
+      for (uint32_t r = 1; r < 3; r++) {
+        double a = -2.0 * M_PI * (double)((uint64_t)r * k % q->fft) / (double)q->fft;
+        q->w3[(r - 1) * q->fft + k] = (cf_t){(float)cos(a), (float)sin(a)};
+      }
+  }
+  for (uint32_t i = 0; i < q->sub; i++) {
     uint32_t r = 0;
     for (uint32_t b = 0; b < q->log2n; b++)
       if (i & (1u << b)) r |= 1u << (q->log2n - 1 - b);
@@ -105,7 +117,7 @@ lteo_t* lteo_create(const lte_cell_t* cell)
 void lteo_destroy(lteo_t* q)
 {
   if (!q) return;
-  free(q->tw_re), free(q->tw_im), free(q->bitrev), free(q->crs);
+  free(q->tw_re), free(q->tw_im), free(q->bitrev), free(q->crs), free(q->w3);
   for (int i = 0; i < 10; i++) free(q->pdcch_scr[i]);
   free(q);
 }
@@ -115,12 +127,12 @@ uint32_t lteo_nof_cce(lteo_t* q, uint32_t cfi) { return (cfi >= 1 && cfi <= 3) ?
  * restates srsran_ofdm_rx_sf as reached from srsran_ue_dl_decode_fft_estimate (DCISearch.cc:562):
  * CP removed, forward DFT without scaling, guard bands and DC dropped.
  * FFT = iterative radix-2 decimation-in-time, twiddles from the rounded table. */
-static void fft_fwd(const lteo_t* q, const cf_t* in, float* re, float* im)
+static void fft_pow2(const lteo_t* q, const cf_t* in, uint32_t stride, float* re, float* im)
 {
-  uint32_t n = q->fft;
+  uint32_t n = q->sub;
   for (uint32_t i = 0; i < n; i++) {
-    re[q->bitrev[i]] = in[i].re;
-    im[q->bitrev[i]] = in[i].im;
+    re[q->bitrev[i]] = in[i * stride].re;
+    im[q->bitrev[i]] = in[i * stride].im;
   }
   for (uint32_t s = 1; s <= q->log2n; s++) {
     uint32_t m = 1u << s, h = m >> 1, step = n / m;
@@ -137,6 +149,26 @@ static void fft_fwd(const lteo_t* q, const cf_t* in, float* re, float* im)
         im[j + k + h] = ai - ti;
       }
   }
+}
+/* X[k] = (F0[k mod M] + W_N^k F1[k mod M]) + W_N^(2k) F2[k mod M], F_r = FFT_M of x[3 m + r] (M = N / 3); plain FFT_N when N is a power of two */
+static void fft_fwd(const lteo_t* q, const cf_t* in, float* re, float* im)
+{
+  if (q->sub == q->fft) {
+    fft_pow2(q, in, 1, re, im);
+    return;
+  }
+  const uint32_t N = q->fft, M = q->sub;
+  float*         f = (float*)malloc(sizeof(float) * 6 * M);
+  for (uint32_t r = 0; r < 3; r++) fft_pow2(q, in + r, 3, f + 2 * r * M, f + (2 * r + 1) * M);
+  for (uint32_t k = 0; k < N; k++) {
+    const uint32_t kp = k % M;
+    const cf_t     w1 = q->w3[k], w2 = q->w3[N + k];
+    const float    t1r = w1.re * f[2 * M + kp] - w1.im * f[3 * M + kp], t1i = w1.re * f[3 * M + kp] + w1.im * f[2 * M + kp];
+    const float    t2r = w2.re * f[4 * M + kp] - w2.im * f[5 * M + kp], t2i = w2.re * f[5 * M + kp] + w2.im * f[4 * M + kp];
+    re[k] = (f[kp] + t1r) + t2r;
+    im[k] = (f[M + kp] + t1i) + t2i;
+  }
+  free(f);
 }
 void lteo_ofdm_rx(lteo_t* q, const cf_t* iq, cf_t* sym)
 {

@@ -19,6 +19,7 @@ uint32_t lte_fft_size(uint32_t nof_prb)
 }
 uint32_t lte_cp_len(uint32_t fft, uint32_t symbol_in_slot) { return (symbol_in_slot == 0 ? 160u : 144u) * fft / 2048u; }
 uint32_t lte_sf_len(uint32_t nof_prb) { return 15u * lte_fft_size(nof_prb); }
+uint32_t lte_cell_fft(const lte_cell_t* c) { return c->symbol_sz ? c->symbol_sz : lte_fft_size(c->nof_prb); }
 
 /* ------------------------------------------------------------------ Gold sequence, 36.211 7.2 */
 void lte_gold_bits(uint32_t c_init, uint8_t* c, uint32_t len)

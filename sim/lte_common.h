@@ -31,10 +31,13 @@ typedef struct {
   uint32_t nof_ports; /* 1 or 2 CRS ports */
   uint32_t cell_id;   /* PCI 0..503 */
   uint32_t nof_rx;    /* rx antennas 1 or 2 */
+  uint32_t symbol_sz; /* FFT size; 0 = the standard LTE rate (2048 at 100 PRB).  srsRAN's default build samples at 3/4 of it
+                         (srsran_symbol_sz: 1536 at 100 PRB, 768 at 50, 384 at 25), which is what LTESniffer records with */
 } lte_cell_t;
 
 /* numerology */
 uint32_t lte_fft_size(uint32_t nof_prb);
+uint32_t lte_cell_fft(const lte_cell_t* c); /* symbol_sz, or the standard size when it is 0 */
 uint32_t lte_cp_len(uint32_t fft, uint32_t symbol_in_slot);
 uint32_t lte_sf_len(uint32_t nof_prb);
 

@@ -25,7 +25,7 @@ struct lte_sim {
 };
 
 /* ---------------------------------------------------------------- small helpers */
-static void fft_inplace(double* re, double* im, uint32_t n, int inverse)
+static void fft_pow2(double* re, double* im, uint32_t n, int inverse)
 {
   for (uint32_t i = 1, j = 0; i < n; i++) {
     uint32_t bit = n >> 1;
@@ -52,6 +52,30 @@ static void fft_inplace(double* re, double* im, uint32_t n, int inverse)
         re[i + j + len / 2] = ur - vr, im[i + j + len / 2] = ui - vi;
       }
   }
+}
+
+/* n = 2^k or 3 * 2^k (srsRAN's default sampling rates): one radix-3 decimation-in-time step around three power-of-two transforms */
+static void fft_inplace(double* re, double* im, uint32_t n, int inverse)
+{
+  if (n % 3) {
+    fft_pow2(re, im, n, inverse);
+    return;
+  }
+  const uint32_t m = n / 3;
+  double*        t = (double*)malloc(sizeof(double) * 2 * n);
+  for (uint32_t r = 0; r < 3; r++)
+    for (uint32_t i = 0; i < m; i++) t[r * m + i] = re[3 * i + r], t[n + r * m + i] = im[3 * i + r];
+  for (uint32_t r = 0; r < 3; r++) fft_pow2(t + r * m, t + n + r * m, m, inverse);
+  for (uint32_t k = 0; k < n; k++) {
+    double ar = 0.0, ai = 0.0;
+    for (uint32_t r = 0; r < 3; r++) {
+      const double ang = (inverse ? 2.0 : -2.0) * M_PI * (double)((uint64_t)r * k % n) / (double)n, wr = cos(ang), wi = sin(ang);
+      const double fr = t[r * m + k % m], fi = t[n + r * m + k % m];
+      ar += fr * wr - fi * wi, ai += fr * wi + fi * wr;
+    }
+    re[k] = ar, im[k] = ai;
+  }
+  free(t);
 }
 
 void lte_sim_pdcch_encode(const uint8_t* dci_bits, uint32_t nbits, uint16_t rnti, uint32_t L, uint8_t* e)
@@ -102,9 +126,9 @@ lte_sim_t* lte_sim_create(const lte_sim_cfg_t* cfg)
     free(s);
     return NULL;
   }
-  s->fft    = lte_fft_size(cfg->cell.nof_prb);
+  s->fft    = lte_cell_fft(&cfg->cell);
   s->nsc    = 12 * cfg->cell.nof_prb;
-  s->sf_len = lte_sf_len(cfg->cell.nof_prb);
+  s->sf_len = 15u * s->fft;
   lte_rng_t rng;
   lte_rng_seed(&rng, cfg->seed ^ 0xC0FFEEull);
   s->rntis = (uint16_t*)calloc(cfg->nof_ues ? cfg->nof_ues : 1, sizeof(uint16_t));

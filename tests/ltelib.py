@@ -14,7 +14,11 @@ SIM_MAX_DCI = 32
 
 
 class Cell(C.Structure):
-    _fields_ = [("nof_prb", C.c_uint32), ("nof_ports", C.c_uint32), ("cell_id", C.c_uint32), ("nof_rx", C.c_uint32)]
+    _fields_ = [("nof_prb", C.c_uint32), ("nof_ports", C.c_uint32), ("cell_id", C.c_uint32), ("nof_rx", C.c_uint32), ("symbol_sz", C.c_uint32)]
+
+    def fft(self):
+        """symbol size: symbol_sz, or the standard LTE size when it is 0"""
+        return self.symbol_sz or (128 if self.nof_prb <= 6 else 256 if self.nof_prb <= 15 else 512 if self.nof_prb <= 25 else 1024 if self.nof_prb <= 50 else 2048)
 
 
 class SimCfg(C.Structure):
@@ -166,7 +170,7 @@ class Sim:
         self.cell = cell
         self.h = sim().lte_sim_create(C.byref(cfg))
         assert self.h, "lte_sim_create failed"
-        self.sf_len = sim().lte_sf_len(cell.nof_prb)
+        self.sf_len = 15 * cell.fft()
 
     def rntis(self):
         out = np.zeros(self.cfg.nof_ues, np.uint16)
