@@ -185,43 +185,6 @@ __global__ void __launch_bounds__(256) rm_turbo_rx_kernel(const DevCb* __restric
   }
 }
 
-// The same per code block, but one CTA per code-block PAIR with the pair's stream buffer assembled in shared memory: soft bits are still read in
-// received order (coalesced), the window-transposed scatter -- consecutive soft bits land NW words apart, and the two code blocks of a pair own
-// the two halves of every word -- happens in shared memory, and the buffer leaves as whole coalesced 32-bit words.  The per-code-block kernel
-// above wrote 2-byte pieces into 32-byte sectors: 534 MB of DRAM writes per 1000-subframe step for 290 MB of payload.
-__global__ void __launch_bounds__(256) rm_turbo_rx_pair_kernel(const DevCb* __restrict__ cbs, const DevPair* __restrict__ pairs, const short* __restrict__ llr_pool,
-                                                               const uint32_t* __restrict__ rm_pool, uint32_t* __restrict__ turbo_pool, short* __restrict__ harq_pool)
-{
-  extern __shared__ __align__(16) uint32_t acc_s[];
-  const DevPair& pr = pairs[blockIdx.x];
-  const uint32_t NW = pr.NW, words = 3 * 32 * NW + 16;
-  short*         sh = reinterpret_cast<short*>(acc_s);
-  for (uint32_t i = threadIdx.x; i < words; i += blockDim.x) acc_s[i] = 0u;
-  __syncthreads();
-  for (uint32_t hh = 0; hh < pr.ncb; hh++) {
-    const DevCb     cb  = cbs[pr.cb_index[hh]];
-    const short*    e   = llr_pool + cb.llr_off;
-    const uint32_t* ord = rm_pool + cb.rm_tab;
-    short*          hq  = cb.harq_op ? harq_pool + cb.harq_off : nullptr;
-    for (uint32_t k = threadIdx.x; k < cb.rm_nn; k += blockDim.x) {
-      const uint32_t w = ord[k];
-      int            acc = cb.harq_op == LTEPHY_HARQ_RETX ? (int)hq[w] : 0;
-      for (uint32_t kk = k; kk < cb.E; kk += cb.rm_nn) acc = sat16(acc + (int)e[kk]);
-      if (hq) hq[w] = (short)acc;
-      int v = acc >> cb.shift;
-      v     = v > 255 ? 255 : (v < -255 ? -255 : v);
-      sh[2 * w + hh] = (short)v;
-    }
-    for (uint32_t i = threadIdx.x; i < 2 * cb.F; i += blockDim.x) { // filler bits are known zeros: strong "0" in the systematic and first parity streams
-      const uint32_t st = i / cb.F, ii = i % cb.F, w = st * 32 * NW + (ii & 31u) * NW + (ii >> 5);
-      sh[2 * w + hh] = (short)-255;
-    }
-    __syncthreads();
-  }
-  uint32_t* bw = turbo_pool + pr.buf_off;
-  for (uint32_t i = threadIdx.x; i < words; i += blockDim.x) bw[i] = acc_s[i];
-}
-
 extern "C" void launch_pdsch_front(const DevCell& c, const DevGrant* grants, uint32_t ngrants, uint32_t max_words, const float2* sym,
                                    const float2* ce, const uint32_t* gold_x1, const uint32_t* gold_basis, uint32_t basis_words,
                                    uint32_t* seq_pool, short* llr_pool, cudaStream_t st, uint64_t* launches)
@@ -236,15 +199,5 @@ extern "C" void launch_rm_turbo_rx(const DevCb* cbs, uint32_t ncb, const DevPair
 {
   if (!ncb) return;
   rm_turbo_rx_kernel<<<ncb, 256, 0, st>>>(cbs, pairs, llr_pool, rm_pool, turbo_pool, harq_pool, gen);
-  *launches += 1;
-}
-// every code block of the batch in one launch (no HARQ slot used twice inside the batch): one CTA per pair, max_nw = largest NW of the batch
-extern "C" void launch_rm_turbo_rx_pairs(const DevCb* cbs, const DevPair* pairs, uint32_t npairs, uint32_t max_nw, const short* llr_pool, const uint32_t* rm_pool,
-                                         uint32_t* turbo_pool, short* harq_pool, cudaStream_t st, uint64_t* launches)
-{
-  if (!npairs) return;
-  const size_t smem = ((size_t)3 * 32 * max_nw + 16) * sizeof(uint32_t);
-  cudaFuncSetAttribute(rm_turbo_rx_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (3 * 32 * 192 + 16) * (int)sizeof(uint32_t)); // per device / context
-  rm_turbo_rx_pair_kernel<<<npairs, 256, smem, st>>>(cbs, pairs, llr_pool, rm_pool, turbo_pool, harq_pool);
   *launches += 1;
 }

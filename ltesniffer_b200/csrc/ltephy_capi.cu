@@ -27,7 +27,6 @@ void launch_compact(const DevCell&, const DevSfInfo*, const ltephy_cand_t*, ltep
 void launch_pdsch_front(const DevCell&, const DevGrant*, uint32_t, uint32_t, const float2*, const float2*, const uint32_t*, const uint32_t*, uint32_t,
                         uint32_t*, short*, cudaStream_t, uint64_t*);
 void launch_rm_turbo_rx(const DevCb*, uint32_t, const DevPair*, const short*, const uint32_t*, uint32_t*, short*, uint32_t, cudaStream_t, uint64_t*);
-void launch_rm_turbo_rx_pairs(const DevCb*, const DevPair*, uint32_t, uint32_t, const short*, const uint32_t*, uint32_t*, short*, cudaStream_t, uint64_t*);
 void launch_turbo(const DevPair*, uint32_t, uint32_t, int, uint32_t*, const uint32_t*, uint32_t*, size_t, const uint16_t*, const uint32_t*,
                   const uint32_t*, const uint32_t*, uint8_t*, uint8_t*, uint8_t*, uint32_t, cudaStream_t, uint64_t*);
 void launch_tb_crc(const DevTb*, uint32_t, const uint8_t*, const uint8_t*, const uint8_t*, const uint32_t*, ltephy_tb_result_t*, cudaStream_t,
@@ -684,15 +683,8 @@ static int run_turbo_stage(ltephy* h, uint32_t max_iter)
   stage_and_pull(h, h->d_pairs.p, h->pairs.data(), h->pairs.size() * sizeof(DevPair));
   stage_and_pull(h, h->d_pair_pi_off.p, h->pair_pi_off.data(), h->pairs.size() * 4);
   stage_and_pull(h, h->d_cbs.p, h->cbs.data(), h->cbs.size() * sizeof(DevCb));
-  static const bool rm_per_cb = getenv("LTEPHY_RM_PER_CB") != nullptr; // A/B switch for measurements
-  if (h->harq_max_gen == 0 && !rm_per_cb) { // the usual case: one CTA per code-block pair assembles the pair's buffer in shared memory
-    uint32_t max_nw = 1;
-    for (const DevPair& p : h->pairs) max_nw = std::max(max_nw, p.NW);
-    launch_rm_turbo_rx_pairs(h->d_cbs.p, h->d_pairs.p, (uint32_t)h->pairs.size(), max_nw, h->d_pllr.p, h->d_rm.p, h->d_turbo.p, h->d_harq.p, h->stream, &h->launches);
-  } else { // a HARQ slot is used more than once in this batch: per-code-block launches in order of use
-    for (uint32_t gen = 0; gen <= h->harq_max_gen; gen++)
-      launch_rm_turbo_rx(h->d_cbs.p, (uint32_t)h->cbs.size(), h->d_pairs.p, h->d_pllr.p, h->d_rm.p, h->d_turbo.p, h->d_harq.p, gen, h->stream, &h->launches);
-  }
+  for (uint32_t gen = 0; gen <= h->harq_max_gen; gen++) // one launch unless a HARQ slot is used more than once in this batch
+    launch_rm_turbo_rx(h->d_cbs.p, (uint32_t)h->cbs.size(), h->d_pairs.p, h->d_pllr.p, h->d_rm.p, h->d_turbo.p, h->d_harq.p, gen, h->stream, &h->launches);
   if (ltephy_turbo_scratch(h)) return fail(LTEPHY_ERROR, "device allocation failed");
   CU(cudaMemsetAsync(h->d_tqueue.p, 0, 16 * sizeof(uint32_t), h->stream));
   CU(cudaEventRecord(h->ev[4], h->stream));
