@@ -57,7 +57,7 @@ __device__ __forceinline__ void fft_pass(float2* work, const float2* __restrict_
 
 // R3: the symbol has 3 * 2^k samples (srsRAN's default sampling rates, 1536 at 100 PRB): three power-of-two transforms F_r of x[3 m + r] run
 // side by side (thread = (r, t)), then X[k] = (F0[k mod M] + W_N^k F1[k mod M]) + W_N^(2k) F2[k mod M] -- the oracle's expression.
-template <bool UL, bool R3>
+template <bool UL, bool R3, bool CFO>
 __global__ void __launch_bounds__(256) ofdm_rx_kernel(const __grid_constant__ DevCell c, const float2* __restrict__ iq, float2* __restrict__ sym)
 {
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -79,7 +79,7 @@ __global__ void __launch_bounds__(256) ofdm_rx_kernel(const __grid_constant__ De
       for (uint32_t j = 0; j < 8; j++) {
         const uint32_t m = ((j & 1u) << 2) | (j & 2u) | (j >> 2), idx = R3 ? 3 * (t + m * q8) + r : t + m * q8;
         float2         x = src[idx];
-        if (!UL && c.cfo_rot) { // constant frequency-offset correction of the file samples (srsran_cfo_correct in srsran_ue_sync's file mode)
+        if (CFO) { // constant frequency-offset correction of the file samples (srsran_cfo_correct in srsran_ue_sync's file mode)
           const float2 rr = __ldg(&c.cfo_rot[c.sym_off[l] + idx]);
           x               = make_float2(x.x * rr.x - x.y * rr.y, x.x * rr.y + x.y * rr.x);
         }
@@ -336,10 +336,19 @@ extern "C" void launch_frontend(const DevCell& c, const float2* iq, float2* sym,
                                 cudaStream_t st, uint64_t* launches)
 {
   const size_t smem_fft = (size_t)c.fft * sizeof(float2);
-  if (c.sub == c.fft)
-    ofdm_rx_kernel<false, false><<<dim3(14, c.nof_rx, n), c.fft / 8 < 32 ? 32 : c.fft / 8, smem_fft, st>>>(c, iq, sym);
-  else
-    ofdm_rx_kernel<false, true><<<dim3(14, c.nof_rx, n), 3 * (c.sub / 8), smem_fft, st>>>(c, iq, sym);
+  const dim3   grid(14, c.nof_rx, n);
+  const uint32_t nt2 = c.fft / 8 < 32 ? 32 : c.fft / 8, nt3 = 3 * (c.sub / 8);
+  if (c.sub == c.fft) {
+    if (c.cfo_rot)
+      ofdm_rx_kernel<false, false, true><<<grid, nt2, smem_fft, st>>>(c, iq, sym);
+    else
+      ofdm_rx_kernel<false, false, false><<<grid, nt2, smem_fft, st>>>(c, iq, sym);
+  } else {
+    if (c.cfo_rot)
+      ofdm_rx_kernel<false, true, true><<<grid, nt3, smem_fft, st>>>(c, iq, sym);
+    else
+      ofdm_rx_kernel<false, true, false><<<grid, nt3, smem_fft, st>>>(c, iq, sym);
+  }
   const size_t smem_ch = (size_t)2 * NPILSYM * 2 * c.nof_prb * sizeof(float2);
   chest_kernel<<<dim3(c.nof_ports * c.nof_rx, n), 256, smem_ch, st>>>(c, sym, ce, info);
   rb_power_kernel<<<n, 128, 0, st>>>(c, sym, info);
@@ -351,8 +360,8 @@ extern "C" void launch_ul_ofdm(const DevCell& c, const float2* iq, float2* sym, 
 {
   const size_t smem_fft = (size_t)c.fft * sizeof(float2);
   if (c.sub == c.fft)
-    ofdm_rx_kernel<true, false><<<dim3(14, 1, n), c.fft / 8 < 32 ? 32 : c.fft / 8, smem_fft, st>>>(c, iq, sym);
+    ofdm_rx_kernel<true, false, false><<<dim3(14, 1, n), c.fft / 8 < 32 ? 32 : c.fft / 8, smem_fft, st>>>(c, iq, sym);
   else
-    ofdm_rx_kernel<true, true><<<dim3(14, 1, n), 3 * (c.sub / 8), smem_fft, st>>>(c, iq, sym);
+    ofdm_rx_kernel<true, true, false><<<dim3(14, 1, n), 3 * (c.sub / 8), smem_fft, st>>>(c, iq, sym);
   *launches += 1;
 }
