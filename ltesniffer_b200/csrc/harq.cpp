@@ -86,8 +86,11 @@ extern "C" int ltephy_harq_prepare_grant(ltephy_harq_t* q, const ltephy_dci_fiel
       g->tb[t].harq_op = LTEPHY_HARQ_NEW, g->tb[t].harq_slot = slot;
     else if (status[t] == LTEPHY_HARQ_RE_TX)
       g->tb[t].harq_op = LTEPHY_HARQ_RETX, g->tb[t].harq_slot = slot;
-    else if (status[t] == LTEPHY_HARQ_DECODED)
-      g->tb[t].enabled = 0; // pdsch_cfg->grant.tb[i].enabled = false (DL_Sniffer_PDSCH.cc:970-972)
   }
+  // already decoded: pdsch_cfg->grant.tb[i].enabled = false (DL_Sniffer_PDSCH.cc:970-972).  Only when the block travels alone: switching one of two
+  // codewords off would change the layer de-mapping of the other one, so a decoded block of a two-codeword grant is simply decoded again
+  const int n_en = (g->tb[0].enabled ? 1 : 0) + (g->tb[1].enabled ? 1 : 0);
+  for (int t = 0; t < 2; t++)
+    if (status[t] == LTEPHY_HARQ_DECODED && n_en == 1) g->tb[t].enabled = 0;
   return LTEPHY_SUCCESS;
 }

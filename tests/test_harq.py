@@ -185,3 +185,32 @@ def test_gpu_harq_store_matches_oracle(infra, phylib, split):
                 assert pl == bytes(opl[0][:len(pl)])
         ncomb += op == capi.HARQ_RETX and crc
     assert ncomb >= 15
+
+
+def test_harq_prepare_grant_fills_the_grant(phylib):
+    """ltephy_harq_prepare_grant: classification + the grant fields the rate-dematcher reads; a decoded single-TB grant is disabled as the reference does
+    (pdsch_cfg->grant.tb[i].enabled = false, DL_Sniffer_PDSCH.cc:970-972)"""
+    import ctypes as C
+    L = capi.load_library()
+
+    class Fields(C.Structure):
+        _fields_ = [("rnti", C.c_uint16), ("format", C.c_uint8), ("alloc_type", C.c_uint8), ("mcs", C.c_uint8 * 2), ("rv", C.c_uint8 * 2), ("ndi", C.c_uint8 * 2),
+                    ("harq_pid", C.c_uint8), ("tpc", C.c_uint8), ("tb_cw_swap", C.c_uint8), ("pinfo", C.c_uint8), ("nof_prb", C.c_uint32)]
+    q = capi.Harq(max_rnti=4)
+    L.ltephy_harq_prepare_grant.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]
+    f = Fields(rnti=0x4321, harq_pid=5)
+    f.ndi[0] = 1
+    g = capi.Grant(rnti=0x4321)
+    g.tb[0].enabled, g.tb[0].tbs = 1, 2216
+    st = (C.c_int * 2)()
+    assert L.ltephy_harq_prepare_grant(q.h, C.byref(f), 200, C.byref(g), st) == 0
+    assert (st[0], st[1], g.tb[0].harq_op) == (capi.HARQ_NEW_TX, -1, capi.HARQ_NEW)
+    slot = g.tb[0].harq_slot
+    q.update(0x4321, 5, 0, 1, 0, 2216, 200, False)
+    g.tb[0].harq_op = 0
+    assert L.ltephy_harq_prepare_grant(q.h, C.byref(f), 208, C.byref(g), st) == 0
+    assert (st[0], g.tb[0].harq_op, g.tb[0].harq_slot, g.tb[0].enabled) == (capi.HARQ_RE_TX, capi.HARQ_RETX, slot, 1)
+    q.update(0x4321, 5, 0, 1, 2, 2216, 208, True)
+    assert L.ltephy_harq_prepare_grant(q.h, C.byref(f), 216, C.byref(g), st) == 0
+    assert (st[0], g.tb[0].enabled, g.tb[0].harq_op) == (capi.HARQ_DECODED, 0, capi.HARQ_NONE)
+    q.close()
