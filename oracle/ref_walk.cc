@@ -228,4 +228,31 @@ uint32_t refwalk_locations(refwalk* w, uint32_t cfi, const float* llr, uint16_t*
   }
   return n;
 }
+
+// ---- the reference's HARQ bookkeeping (src/src/HARQ.cc, compiled unmodified): what ltesniffer_b200/csrc/harq.cpp restates -------------------------
+void* refharq_create()
+{
+  HARQ* q = new HARQ();
+  q->init_HARQ(DL_SNIFFER_HARQ_MODE_ON);
+  return q;
+}
+void refharq_destroy(void* q) { delete static_cast<HARQ*>(q); }
+int  refharq_size(void* q) { return static_cast<HARQ*>(q)->harqBufferSize(); }
+// HARQ::is_retransmission with the grant PDSCH_Decoder::decode_dl_mode builds at DL_Sniffer_PDSCH.cc:946-953; *buffer = getHARQBuffer (identity of the store)
+int refharq_is_retransmission(void* q, uint16_t rnti, int pid, int tid, int ndi, int rv, int tbs, uint32_t tti, const void** buffer)
+{
+  dl_sniffer_harq_grant_t g = {};
+  g.last_decoded = false, g.ndi = ndi != 0, g.ndi_present = true, g.rv = rv, g.tbs = tbs, g.is_first_transmission = false;
+  HARQ*     h  = static_cast<HARQ*>(q);
+  const int st = h->is_retransmission(rnti, pid, tid, g, tti / 10, tti % 10);
+  if (buffer) *buffer = (st == DL_SNIFFER_NEW_TX || st == DL_SNIFFER_RE_TX) ? (const void*)h->getHARQBuffer(rnti, pid, tid) : nullptr;
+  return st;
+}
+// HARQ::updateHARQRNTI with the grant built at DL_Sniffer_PDSCH.cc:1008-1014
+void refharq_update(void* q, uint16_t rnti, int pid, int tid, int ndi, int rv, int tbs, uint32_t tti, int decoded)
+{
+  dl_sniffer_harq_grant_t g = {};
+  g.last_decoded = decoded != 0, g.ndi = ndi != 0, g.ndi_present = true, g.rv = rv, g.tbs = tbs, g.is_first_transmission = false;
+  static_cast<HARQ*>(q)->updateHARQRNTI(rnti, pid, tid, tti / 10, tti % 10, g);
+}
 }

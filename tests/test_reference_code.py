@@ -255,3 +255,52 @@ def test_locations_and_cce_power_equal_reference(infra):
         for i in range(n):
             assert (comp["loc"][i]["mask"] != 0) == bool(sp[i]), (cfi, i)
     ref.close()
+
+
+def test_harq_bookkeeping_equals_the_reference_class(infra):
+    """ltephy_harq_classify / _update against the reference's own HARQ class (src/src/HARQ.cc compiled unmodified into oracle/_ref/libfalcon_ref.so) on a
+    random traffic pattern: 40 RNTIs, 8 processes, 2 TBs, retransmissions 8 ms apart with and without NDI toggles / TBS changes, tti wrapping at 10240;
+    same status every time, and "same slot" exactly when the reference hands out the same soft buffer"""
+    from ltesniffer_b200 import capi
+    R = reflib()
+    R.refharq_create.restype = C.c_void_p
+    R.refharq_destroy.argtypes = [C.c_void_p]
+    R.refharq_size.argtypes = [C.c_void_p]
+    R.refharq_is_retransmission.argtypes = [C.c_void_p, C.c_uint16, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint32, C.POINTER(C.c_void_p)]
+    R.refharq_update.argtypes = [C.c_void_p, C.c_uint16, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint32, C.c_int]
+    ref = R.refharq_create()
+    q = capi.Harq(max_rnti=R.refharq_size(ref))
+    rng = np.random.default_rng(12)
+    rntis = [int(x) for x in rng.integers(0x100, 0xFFF0, 40)]
+    pending = {}                     # (rnti, pid, tb) -> (ndi, tbs, tti of the last transmission)
+    buf_of_slot, seen = {}, {0: 0, 1: 0, 3: 0}
+    tti = 10200
+    for step in range(6000):
+        tti = (tti + int(rng.integers(0, 3))) % 10240
+        rnti, pid, tb = rntis[int(rng.integers(0, 40))], int(rng.integers(0, 8)), int(rng.integers(0, 2))
+        key = (rnti, pid, tb)
+        if key in pending and rng.random() < 0.6:     # a repetition: usually 8 ms later, same NDI and size
+            ndi, tbs, last = pending[key]
+            t = (last + (8 if rng.random() < 0.8 else int(rng.integers(1, 20)))) % 10240
+            if rng.random() < 0.15:
+                ndi ^= 1
+            if rng.random() < 0.1:
+                tbs += 8
+        else:
+            ndi, tbs, t = int(rng.integers(0, 2)), int(rng.integers(2, 2000)) * 8, tti
+        rv = int(rng.integers(0, 4))
+        b = C.c_void_p()
+        s_ref = R.refharq_is_retransmission(ref, rnti, pid, tb, ndi, rv, tbs, t, C.byref(b))
+        s_own, slot = q.classify(rnti, pid, tb, ndi, tbs, t)
+        assert s_own == s_ref, (step, hex(rnti), pid, tb, s_own, s_ref)
+        seen[s_ref] = seen.get(s_ref, 0) + 1
+        if s_ref in (capi.HARQ_NEW_TX, capi.HARQ_RE_TX):
+            assert buf_of_slot.setdefault(slot, b.value) == b.value          # one slot <-> one reference buffer
+            decoded = bool(rng.random() < 0.4)
+            R.refharq_update(ref, rnti, pid, tb, ndi, rv, tbs, t, int(decoded))
+            q.update(rnti, pid, tb, ndi, rv, tbs, t, decoded)
+        pending[key] = (ndi, tbs, t)
+    assert len(set(buf_of_slot.values())) == len(buf_of_slot)               # and different slots <-> different buffers
+    assert seen[0] > 1000 and seen[1] > 300 and seen[3] > 100              # new / retransmission / already decoded all exercised
+    R.refharq_destroy(ref)
+    q.close()
