@@ -255,4 +255,15 @@ void refharq_update(void* q, uint16_t rnti, int pid, int tid, int ndi, int rv, i
   g.last_decoded = decoded != 0, g.ndi = ndi != 0, g.ndi_present = true, g.rv = rv, g.tbs = tbs, g.is_first_transmission = false;
   static_cast<HARQ*>(q)->updateHARQRNTI(rnti, pid, tid, tti / 10, tti % 10, g);
 }
+
+// SubframePower::computePower (src/src/SubframePower.cc:18-47, called at DCISearch.cc:565): per-PRB power of antenna 0 in dB
+void refwalk_rb_power(uint32_t nof_prb, const cf_t* sf_symbols, float* out_db)
+{
+  srsran_cell_t cell = {};
+  cell.nof_prb       = nof_prb;
+  SubframePower p(cell);
+  p.computePower(sf_symbols);
+  const std::vector<float>& v = p.getRBPowerDL();
+  for (uint32_t i = 0; i < nof_prb; i++) out_db[i] = v[i];
+}
 }

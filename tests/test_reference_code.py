@@ -304,3 +304,20 @@ def test_harq_bookkeeping_equals_the_reference_class(infra):
     assert seen[0] > 1000 and seen[1] > 300 and seen[3] > 100              # new / retransmission / already decoded all exercised
     R.refharq_destroy(ref)
     q.close()
+
+
+def test_rb_power_equals_reference(infra):
+    """per-PRB power (K10): the oracle's mean |y|^2 per PRB, which the CUDA kernel reproduces bit for bit, in dB == SubframePower::computePower
+    (src/src/SubframePower.cc:18-47, called at DCISearch.cc:565) on the same symbols, up to float rounding of the different summation order"""
+    from helpers import make_capture, oracle_frontend
+    R = reflib()
+    R.refwalk_rb_power.argtypes = [C.c_uint32, C.c_void_p, C.c_void_p]
+    cell = Cell(50, 2, 9, 2)
+    sim, iq, tti, truths, payloads = make_capture(cell, 3, seed=2, cfi=2, nof_ues=4, dl_min=2, dl_max=4, tm=13, snr_db=20.0)
+    o = Oracle(cell)
+    for fe in oracle_frontend(o, iq, tti):
+        sym0 = np.ascontiguousarray(fe["sym"][0], np.complex64)
+        ref = np.zeros(cell.nof_prb, np.float32)
+        R.refwalk_rb_power(cell.nof_prb, sym0.ctypes.data_as(C.c_void_p), ref.ctypes.data_as(C.c_void_p))
+        own = 10.0 * np.log10(np.asarray(fe["rb_power"], np.float64))
+        assert np.abs(own - ref).max() < 1e-3, np.abs(own - ref).max()
