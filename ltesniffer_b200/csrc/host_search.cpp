@@ -904,7 +904,10 @@ extern "C" int ltephy_dci_trace_line(const ltephy_search_t* s, const ltephy_dci_
     ltephy_dci_fields_t f;
     if (ltephy_dci_to_grant(s, d, sf, cfi, use_256qam_table, &g, &f) != LTEPHY_SUCCESS) return LTEPHY_ERROR;
     const bool two  = d->format >= ltehost::F2;
-    const int  tbs0 = g.tb[0].tbs > 0 ? g.tb[0].tbs : 0, tbs1 = g.tb[1].tbs > 0 ? g.tb[1].tbs : 0;
+    // The reference's convert_dl_grant fills BOTH legacy mcs[] entries from the first transport block (ran_dl_grant->tb->tbs,
+    // lib/src/phy/falcon_phch/falcon_dci.c:608-612), so a two-TB line reads "2 x tbs0, tbs0, tbs0" whatever the second block carries: reproduced,
+    // because the trace file is an output format (checked line by line against DCIToFile::printDCICollection in tests/test_reference_code.py)
+    const int  tbs0 = g.tb[0].tbs > 0 ? g.tb[0].tbs : 0, tbs1 = tbs0;
     n = snprintf(out, cap, "%ld.%06ld\t%04d\t%d\t%d\t1\t%d\t%d\t%d\t%d\t%d\t%d\t%d\t%d\t%d\t%d\t%d\t%d\t%d\t%d\t%s\n", (long)ts_sec, (long)ts_usec, (int)sfn,
                  (int)sf, (int)d->rnti, (int)f.mcs[0], (int)f.nof_prb, two ? tbs0 + tbs1 : tbs0, two ? tbs0 : -1, two ? tbs1 : -1, (int)d->format + 1,
                  (int)f.ndi[0], two ? (int)f.ndi[1] : -1, (int)f.harq_pid, (int)d->ncce, (int)d->L, (int)cfi, (int)d->histogram_value, (int)d->nof_bits, hex);

@@ -12,6 +12,7 @@
 // SubframeWorker::work does (src/src/SubframeWorker.cc:142-207).
 #include "include/DCISearch.h"
 #include "include/DCICollection.h"
+#include "include/SubframeInfoConsumer.h"
 #include "include/MCSTracking.h"
 #include "include/HARQ.h"
 #include "include/ULSchedule.h"
@@ -67,6 +68,7 @@ struct refwalk {
   uint32_t             sf_cnt = 0, update_interval = 500;
   bool                 shortcut = true;
   DCIBlindSearchStats  stats;
+  FILE*                trace = nullptr; // DCIToFile target (refwalk_set_trace)
 };
 
 extern "C" {
@@ -107,6 +109,7 @@ refwalk* refwalk_create(uint32_t nof_prb, uint32_t nof_ports, uint32_t cell_id, 
 void refwalk_destroy(refwalk* w)
 {
   if (!w) return;
+  if (w->trace) fclose(w->trace);
   delete w->ulsche;
   delete w->harq;
   delete w->mcs;
@@ -115,6 +118,13 @@ void refwalk_destroy(refwalk* w)
   srsran_ue_dl_free(&w->q);
   delete w->fq;
   delete w;
+}
+// every following subframe's accepted DCIs are written to `path` by the reference's DCIToFile (NULL: stop)
+int refwalk_set_trace(refwalk* w, const char* path)
+{
+  if (w->trace) fclose(w->trace);
+  w->trace = path ? fopen(path, "w") : nullptr;
+  return (path && !w->trace) ? -1 : 0;
 }
 void refwalk_config(refwalk* w, int shortcut, int skip_secondary, uint32_t update_interval)
 {
@@ -142,6 +152,11 @@ int refwalk_subframe(refwalk* w, const ltephy_sf_info_t* info, const ltephy_cand
   search.setShortcutDiscovery(w->shortcut);
   search.search();
   w->stats += search.getStats();
+  if (w->trace) { // the reference's own trace writer, DCIToFile::printDCICollection (SubframeInfoConsumer.cc:66-138)
+    DCIToFile tf(w->trace);
+    tf.consumeDCICollection(subframeInfo);
+    fflush(w->trace);
+  }
   // accepted DCIs: the reference keeps DL and UL in separate containers; both in acceptance order
   uint32_t n = 0;
   DCICollection& col = subframeInfo.getDCICollection();

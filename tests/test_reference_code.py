@@ -174,11 +174,27 @@ def test_product_walk_and_grants_equal_the_reference_code(infra, name, cell, n, 
     ref.L.refwalk_config(ref.h, 1, 0, 10)
     srch.config(1, 0, 10)
     srch_c.config(1, 0, 10)
+    # the reference's own DCI trace file (DCIToFile::printDCICollection, src/src/SubframeInfoConsumer.cc:66-138) against ltephy_dci_trace_line
+    import tempfile
+    trace_path = os.path.join(tempfile.mkdtemp(), "dci_trace.tsv")
+    ref.L.refwalk_set_trace.argtypes = [C.c_void_p, C.c_char_p]
+    assert ref.L.refwalk_set_trace(ref.h, trace_path.encode()) == 0
+    PL = capi.load_library()
+    PL.ltephy_dci_trace_line.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_int, C.c_uint32, C.c_uint32, C.c_char_p, C.c_size_t]
+    own_lines, ntrace = [], 0
     total = nul = 0
     for tti in range(n):
         info, T, llr, tr = phase_a_oracle(s, o, geo, tti)
         want = ref.subframe(info, T, llr)
         got = srch.subframe(info, T)
+        buf = C.create_string_buffer(512)
+        for is_ul in (False, True):          # the reference prints the downlink container first, then the uplink one
+            for d in got:
+                if (d["format"] == 0) != is_ul:
+                    continue
+                row = np.array([d])
+                nb = PL.ltephy_dci_trace_line(srch.h, row.ctypes.data_as(C.c_void_p), info.tti, info.cfi, 0, 0, 0, buf, 512)
+                own_lines.append(buf.value.decode() if nb > 0 else None)
         got_c = srch_c.subframe_compact(info, srch_c.compact_from_table(info, T))
         assert got_c is not None and len(got_c) == len(got) and all(np.array_equal(got_c[k], got[k]) for k in got.dtype.names)
         # the reference keeps DL and UL DCIs in separate containers (each in acceptance order): compare per direction
@@ -196,6 +212,15 @@ def test_product_walk_and_grants_equal_the_reference_code(infra, name, cell, n, 
     rs, ps = ref.stats(), srch.stats()
     assert (rs.nof_decoded_locations, rs.nof_cce, rs.nof_missed_cce, rs.nof_subframes, rs.nof_locations) == \
            (ps.nof_decoded_locations, ps.nof_cce, ps.nof_missed_cce, ps.nof_subframes, ps.nof_locations)
+    ref.L.refwalk_set_trace(ref.h, None)
+    ref_lines = open(trace_path).read().splitlines(keepends=True)
+    own = [l for l in own_lines if l is not None]
+    assert len(ref_lines) == len(own), (name, len(ref_lines), len(own), len(own_lines))
+    for a, b in zip(ref_lines, own):         # everything but the wall-clock timestamp of the first column
+        assert a.split("\t", 1)[1] == b.split("\t", 1)[1], (name, a, b)
+        ntrace += 1
+    if name != "low_snr_gate":
+        assert ntrace >= n // 2
     if name == "low_snr_gate":
         assert total == 0
     else:
