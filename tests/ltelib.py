@@ -264,7 +264,7 @@ class Oracle:
         s, c = self._pp(sym, ce)
         mib = np.zeros(24, np.uint8)
         npo, fq = C.c_uint32(0), C.c_uint32(0)
-        self.L.lteo_pbch_decode.argtypes = None
+        self.L.lteo_pbch_decode.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
         r = self.L.lteo_pbch_decode(self.h, s, c, ptr(mib), C.byref(npo), C.byref(fq))
         return r, mib, npo.value, fq.value
 
@@ -282,7 +282,8 @@ class Oracle:
         s, c = self._pp(sym, ce)
         sp = (C.c_void_p * 2)(*[None if a is None else a.ctypes.data for a in soft])
         cb = (C.c_int * 2)(*combine)
-        self.L.lteo_pdsch_decode_harq.argtypes = None
+        self.L.lteo_pdsch_decode_harq.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint16, C.POINTER(DlGrant), C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p,
+                                                  C.c_void_p, C.c_void_p, C.c_void_p]
         r = self.L.lteo_pdsch_decode_harq(self.h, sf_idx, cfi, rnti, C.byref(grant), s, c, max_iter, ptr_array(pl), ok, sp, cb)
         return r, pl, [ok[0], ok[1]]
 
