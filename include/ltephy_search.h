@@ -116,11 +116,12 @@ void ltephy_harq_update(ltephy_harq_t* q, uint16_t rnti, uint32_t pid, uint32_t 
 int ltephy_harq_prepare_grant(ltephy_harq_t* q, const ltephy_dci_fields_t* f, uint32_t tti, ltephy_grant_t* grant, int status[2]);
 
 /* DCI format 0 -> PUSCH grant (srsran_ra_ul_dci_to_grant as used at falcon_dci.c:222, and ulsniffer_ra_ul_dci_to_grant_256,
- * lib/src/phy/falcon_phch/ul_sniffer_pusch.c:138-172; no hopping).  enable_64qam selects the MCS interpretation, i.e. one of the
+ * lib/src/phy/falcon_phch/ul_sniffer_pusch.c:138-172; type-1 hopping per ul_sniffer_ra_ul_grant_to_grant_prb_allocation, same file :20-87, with the
+ * offset of ltephy_search_set_ul_hopping; a type-2 grant keeps the slot-0 PRBs in both slots as the reference does).  enable_64qam selects the MCS interpretation, i.e. one of the
  * three attempts of PUSCH_Decoder::decode (src/src/UL_Sniffer_PUSCH.cc:498-521): 0 = Table 8.6.1-1 capped at 16QAM, 1 = Table
  * 8.6.1-1 as is (64QAM), 2 = Table 8.6.1-3 (256QAM, Qm up to 8, MCS 26 -> TBS row 32A).  A caller that does not know the UE's
  * table submits the alternatives as separate grants of one ltephy_submit_ul batch and keeps the one whose CRC passes.
- * Returns 0, or LTEPHY_ERROR for hopping / retransmission MCS / invalid RIV / L_prb outside the DFT set or < 3 / no TBS. */
+ * Returns 0, or LTEPHY_ERROR for an invalid hop / retransmission MCS / invalid RIV / L_prb outside the DFT set or < 3 / no TBS. */
 int ltephy_ul_dci_to_grant(const ltephy_search_t* s, const ltephy_dci_t* dci, int enable_64qam, ltephy_ul_grant_t* grant);
 
 /* Whole batch: IQ in host memory -> accepted DCIs + transport blocks.  seq orders concurrent calls on

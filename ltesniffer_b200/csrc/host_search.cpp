@@ -802,6 +802,7 @@ int ltephy_dci_to_grant(const ltephy_search_t* s, const ltephy_dci_t* d, uint32_
   }
   if ((g->tx_scheme == LTEPHY_TX_PORT0 || g->tx_scheme == LTEPHY_TX_DIVERSITY) && g->nof_tb != 1) return LTEPHY_MIMO_LAYER_WRONG;
   if (g->tx_scheme == LTEPHY_TX_CDD && g->nof_tb != 2) return LTEPHY_MIMO_LAYER_WRONG;
+  if (g->tx_scheme == LTEPHY_TX_SPATIALMUX && g->nof_tb != 1 && g->nof_tb != 2) return LTEPHY_MIMO_LAYER_WRONG; // both TBs disabled, dl_sniffer_pdsch.c:229-237
   g->rnti = d->rnti, g->sf = d->sf;
   if (fields) *fields = f;
   return LTEPHY_SUCCESS;

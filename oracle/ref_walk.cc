@@ -281,4 +281,72 @@ void refwalk_rb_power(uint32_t nof_prb, const cf_t* sf_symbols, float* out_db)
   const std::vector<float>& v = p.getRBPowerDL();
   for (uint32_t i = 0; i < nof_prb; i++) out_db[i] = v[i];
 }
+
+// One DCI through the reference's grant conversion, outside any walk (randomised parity tests): srsran_dci_msg_unpack_pdsch, then per MCS table
+// dl_sniffer_ra_dl_dci_to_grant (lib/src/phy/falcon_phch/dl_sniffer_pdsch.c:95-132) + dl_sniffer_config_mimo (:255-276), as falcon_dci.c:271-310
+// and DL_Sniffer_PDSCH.cc:920 do.  bits: one per byte.  Returns -1 if the unpack fails.
+int refgrant_dl(refwalk* w, uint32_t format, uint16_t rnti, const uint8_t* bits, uint32_t nof_bits, uint32_t tti, uint32_t cfi, refwalk_dci_t* out)
+{
+  srsran_dci_msg_t msg;
+  memset(&msg, 0, sizeof(msg));
+  msg.format = falcon_ue_all_formats[format], msg.rnti = rnti, msg.nof_bits = nof_bits;
+  memcpy(msg.payload, bits, nof_bits);
+  srsran_dl_sf_cfg_t sf{};
+  sf.tti = tti, sf.cfi = cfi, sf.sf_type = SRSRAN_SF_NORM;
+  srsran_dci_dl_t dci;
+  memset(&dci, 0, sizeof(dci));
+  memset(out, 0, sizeof(*out));
+  if (srsran_dci_msg_unpack_pdsch(&w->cell, &sf, &w->ue_dl_cfg.cfg.dci, &msg, &dci)) return -1;
+  out->rnti = rnti, out->format = (uint8_t)format, out->nof_bits = (uint16_t)nof_bits;
+  for (int t = 0; t < 2; t++) {
+    srsran_dci_dl_t      d2 = dci;
+    srsran_pdsch_grant_t g;
+    memset(&g, 0, sizeof(g));
+    srsran_dl_sf_cfg_t sf2 = sf;
+    int                r   = dl_sniffer_ra_dl_dci_to_grant(&w->cell, &sf2, t == 1, &d2, &g);
+    if (r == SRSRAN_SUCCESS) r = dl_sniffer_config_mimo(&w->cell, msg.format, &d2, &g);
+    out->grant_ret[t] = r;
+    if (r != SRSRAN_SUCCESS) continue;
+    out->nof_prb = g.nof_prb, out->nof_re[t] = g.nof_re, out->nof_tb[t] = g.nof_tb, out->tx_scheme[t] = scheme_of(g.tx_scheme), out->pmi[t] = g.pmi, out->nof_layers[t] = g.nof_layers;
+    for (int i = 0; i < 2; i++)
+      out->tbs[t][i] = g.tb[i].tbs, out->qm[t][i] = qm_of(g.tb[i].mod), out->rv[t][i] = (uint8_t)g.tb[i].rv, out->tb_en[t][i] = g.tb[i].enabled, out->cw_idx[t][i] = (uint8_t)g.tb[i].cw_idx;
+    if (t == 0)
+      for (int sl = 0; sl < 2; sl++)
+        for (uint32_t p = 0; p < w->cell.nof_prb; p++) out->prb_mask[sl][p] = g.prb_idx[sl][p];
+  }
+  return 0;
+}
+// One format-0 DCI through the reference's own uplink grant conversion with an arbitrary pusch-HoppingOffset: srsran_dci_msg_unpack_pusch, then
+// ul_sniffer_ra_ul_dci_to_grant (Table 8.6.1-1, out table 0) and ulsniffer_ra_ul_dci_to_grant_256 (Table 8.6.1-3, out table 1), both on top of
+// ul_sniffer_ra_ul_grant_to_grant_prb_allocation (lib/src/phy/falcon_phch/ul_sniffer_pusch.c:20-87,138-245).  Returns -1 when the unpack refuses.
+int refgrant_ul(refwalk* w, uint16_t rnti, const uint8_t* bits, uint32_t nof_bits, uint32_t tti, uint32_t n_rb_ho, refwalk_dci_t* out)
+{
+  srsran_dci_msg_t msg;
+  memset(&msg, 0, sizeof(msg));
+  msg.format = SRSRAN_DCI_FORMAT0, msg.rnti = rnti, msg.nof_bits = nof_bits;
+  memcpy(msg.payload, bits, nof_bits);
+  srsran_dl_sf_cfg_t sf{};
+  sf.tti = tti, sf.sf_type = SRSRAN_SF_NORM;
+  srsran_dci_ul_t dci;
+  memset(out, 0, sizeof(*out));
+  if (srsran_dci_msg_unpack_pusch(&w->cell, &sf, &w->ue_dl_cfg.cfg.dci, &msg, &dci)) return -1;
+  out->rnti = rnti, out->format = 0, out->nof_bits = (uint16_t)nof_bits, out->ul_n_dmrs = dci.n_dmrs;
+  for (int t = 0; t < 2; t++) {
+    srsran_dci_ul_t      d2 = dci;
+    srsran_pusch_grant_t g;
+    memset(&g, 0, sizeof(g));
+    srsran_ul_sf_cfg_t ul_sf;
+    memset(&ul_sf, 0, sizeof(ul_sf));
+    ul_sf.tti = tti;
+    srsran_pusch_hopping_cfg_t hop;
+    memset(&hop, 0, sizeof(hop));
+    hop.n_rb_ho = n_rb_ho;
+    out->grant_ret[t] = t == 0 ? ul_sniffer_ra_ul_dci_to_grant(&w->cell, &ul_sf, &hop, &d2, &g) : ulsniffer_ra_ul_dci_to_grant_256(&w->cell, &ul_sf, &hop, &d2, &g);
+    if (out->grant_ret[t]) continue;
+    out->ul_L_prb = g.L_prb, out->ul_n_prb[0] = g.n_prb[0], out->ul_n_prb[1] = g.n_prb[1];
+    out->ul_tbs[t] = g.tb.tbs, out->ul_qm[t] = qm_of(g.tb.mod);
+    out->rv[t][0] = (uint8_t)g.tb.rv, out->tx_scheme[t] = (uint8_t)g.freq_hopping;
+  }
+  return 0;
+}
 }

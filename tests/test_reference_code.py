@@ -346,3 +346,93 @@ def test_rb_power_equals_reference(infra):
         R.refwalk_rb_power(cell.nof_prb, sym0.ctypes.data_as(C.c_void_p), ref.ctypes.data_as(C.c_void_p))
         own = 10.0 * np.log10(np.asarray(fe["rb_power"], np.float64))
         assert np.abs(own - ref).max() < 1e-3, np.abs(own - ref).max()
+
+
+@needs_ref
+@pytest.mark.parametrize("cellp", [(100, 2, 7, 2), (75, 2, 3, 2), (50, 2, 301, 2), (25, 1, 5, 1)])
+def test_random_dcis_grants_equal_reference(infra, cellp):
+    """2 500 random payloads per cell over the downlink formats LTESniffer decodes (1, 1A, 1C, 2, 2A), C-RNTIs and the SI / P / RA-RNTIs, every CFI
+    and subframe index: ltephy_dci_to_grant against the reference's own dl_sniffer_ra_dl_dci_to_grant + dl_sniffer_config_mimo
+    (lib/src/phy/falcon_phch/dl_sniffer_pdsch.c:95-132,255-276) for both MCS tables -- return code, PRB masks, TBS, Qm, rv, codeword mapping, tx scheme, PMI"""
+    cell = Cell(*cellp)
+    R = reflib()
+    R.refgrant_dl.argtypes = [C.c_void_p, C.c_uint32, C.c_uint16, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(RefDci)]
+    ref = RefWalk(cell)
+    srch = capi.Search(cell.nof_prb, cell.nof_ports, cell.cell_id, cell.nof_rx)
+    S = infra.sim()
+    rng = np.random.default_rng(cell.nof_prb)
+    nok = nfail = 0
+    for it in range(2500):
+        f = int(rng.choice([1, 2, 4, 6, 7]))
+        nb = S.lte_dci_sizeof(C.byref(cell), f)
+        bits = rng.integers(0, 2, nb).astype(np.uint8)
+        if f == 2:
+            bits[0] = 1                                   # format 0 / 1A flag
+        if rng.random() < 0.3:                            # plausible MCS / RV fields more often than pure noise gives
+            bits[rng.integers(0, nb, 6)] = 0
+        rnti = int(rng.choice([int(rng.integers(11, 0xFFF3)), 0xFFFF, 0xFFFE, int(rng.integers(1, 11))], p=[0.7, 0.1, 0.1, 0.1]))
+        tti, cfi = int(rng.integers(0, 10240)), int(rng.integers(1, 4))
+        r = RefDci()
+        ru = R.refgrant_dl(ref.h, f, rnti, bits.ctypes.data_as(C.c_void_p), nb, tti, cfi, C.byref(r))
+        v = 0
+        for i, b in enumerate(bits):
+            v |= int(b) << (63 - i)
+        row = np.zeros(1, capi.DCI_DTYPE)
+        row["rnti"], row["format"], row["nof_bits"], row["bits"], row["ncce"], row["L"] = rnti, f, nb, v, 0, 2
+        info = capi.SfInfo()
+        info.tti, info.cfi = tti, cfi
+        if ru != 0:
+            for table in (0, 1):
+                assert srch.dci_to_grant(row[0], tti % 10, cfi, table)[0] != 0
+            nfail += 1
+            continue
+        compare_grants(srch, cell, info, row[0], r)
+        nok += (r.grant_ret[0] == 0)
+    assert nok > 500, (nok, nfail)
+    ref.close()
+
+
+@needs_ref
+@pytest.mark.parametrize("cellp,n_rb_ho", [((100, 2, 7, 2), 0), ((100, 2, 7, 2), 5), ((75, 2, 3, 2), 2), ((50, 2, 301, 2), 8), ((25, 1, 5, 1), 0), ((25, 1, 5, 1), 3)])
+def test_random_format0_grants_equal_reference(infra, cellp, n_rb_ho):
+    """3 000 random format-0 payloads per cell and pusch-HoppingOffset (half of them with the hopping flag set, i.e. all four hop kinds of 36.213
+    Tables 8.4-1/2): ltephy_ul_dci_to_grant against the reference's own ul_sniffer_ra_ul_dci_to_grant / ulsniffer_ra_ul_dci_to_grant_256 over
+    ul_sniffer_ra_ul_grant_to_grant_prb_allocation (lib/src/phy/falcon_phch/ul_sniffer_pusch.c:20-245) -- L_prb, both slots' first PRB, TBS and Qm
+    of Tables 8.6.1-1 and 8.6.1-3, the cyclic-shift field.  The product refuses what PUSCH_Decoder never decodes (L_prb that is no DFT size or < 3,
+    valid_prb_ul at src/src/UL_Sniffer_PUSCH.cc:3-10; retransmission MCS 29-31; no TBS); everything else must agree, refusals included."""
+    cell = Cell(*cellp)
+    R = reflib()
+    R.refgrant_ul.argtypes = [C.c_void_p, C.c_uint16, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(RefDci)]
+    ref = RefWalk(cell)
+    srch = capi.Search(cell.nof_prb, cell.nof_ports, cell.cell_id, cell.nof_rx)
+    srch.L.ltephy_search_set_ul_hopping(srch.h, n_rb_ho)
+    S = infra.sim()
+    nb = S.lte_dci_sizeof(C.byref(cell), 0)
+    rng = np.random.default_rng(cell.nof_prb * 16 + n_rb_ho)
+    dmrs2 = (0, 6, 3, 4, 2, 8, 10, 9)
+    nok = nhop = 0
+    for it in range(3000):
+        bits = rng.integers(0, 2, nb).astype(np.uint8)
+        bits[0] = 0
+        bits[1] = it & 1
+        rnti = int(rng.integers(11, 0xFFF3))
+        r = RefDci()
+        assert R.refgrant_ul(ref.h, rnti, bits.ctypes.data_as(C.c_void_p), nb, int(rng.integers(0, 10240)), n_rb_ho, C.byref(r)) == 0
+        v = 0
+        for i, b in enumerate(bits):
+            v |= int(b) << (63 - i)
+        row = np.zeros(1, capi.DCI_DTYPE)
+        row["rnti"], row["format"], row["nof_bits"], row["bits"], row["L"] = rnti, 0, nb, v, 2
+        mcs = d_mcs(row[0], cell)
+        for table in (0, 1):
+            rc, g = capi.ul_dci_to_grant(srch, row[0], 1 if table == 0 else 2)
+            L = r.ul_L_prb
+            expect = r.grant_ret[table] == 0 and L >= 3 and _dft_size(L) and mcs <= 28 and r.ul_tbs[table] > 0
+            assert (rc == 0) == expect, (it, table, rc, r.grant_ret[table], L, mcs, r.ul_tbs[table])
+            if rc == 0:
+                assert (g.L_prb, g.n_prb, g.n_prb_slot1, g.tbs, g.qm) == (L, r.ul_n_prb[0], r.ul_n_prb[1], r.ul_tbs[table], r.ul_qm[table]), (it, table)
+                assert g.n_dmrs2 == dmrs2[r.ul_n_dmrs] and g.rv == r.rv[table][0] == 0
+                nok += 1
+                nhop += r.ul_n_prb[0] != r.ul_n_prb[1]
+    assert nok > 300 and nhop > 20, (nok, nhop)
+    ref.close()
