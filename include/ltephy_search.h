@@ -63,6 +63,10 @@ void ltephy_search_config(ltephy_search_t* s, int shortcut, int skip_secondary, 
  * they differ, and ltephy_decode_subframes reports the first reading unless only the second passes a CRC (then crc = 2): the
  * batched form of "try the 64QAM table, then the 256QAM table" (src/src/DL_Sniffer_PDSCH.cc:1089-1210).  Off by default. */
 void ltephy_search_speculate_256qam(ltephy_search_t* s, int on);
+/* HARQ mode (-h): ltephy_grants_from_dcis keeps the C-RNTI grants whose first block has a reserved MCS (29-31; 28-31 of the 256QAM table; tbs = 0)
+ * instead of applying decode_dl_mode's "tbs > 0" rule to them; ltephy_harq_prepare_grant then gives the block the size of its process' last
+ * transmission as DCICollection::addCandidate does before that rule (src/src/DCICollection.cc:236-252).  Off by default. */
+void ltephy_search_keep_reserved_mcs(ltephy_search_t* s, int on);
 /* pusch-HoppingOffset of SIB2 (hopping_cfg.n_rb_ho, src/src/DCICollection.cc:166-168), used by ltephy_ul_dci_to_grant for type-1 hopping grants; default 0 */
 void ltephy_search_set_ul_hopping(ltephy_search_t* s, uint32_t n_rb_ho);
 #define LTEPHY_GRANT_ALT_TABLE 0x80000000u
@@ -112,7 +116,10 @@ void           ltephy_harq_destroy(ltephy_harq_t* q);
 int ltephy_harq_classify(ltephy_harq_t* q, uint16_t rnti, uint32_t pid, uint32_t tb, uint32_t ndi, int32_t tbs, uint32_t tti, uint32_t* slot);
 /* after the decode (only for NEW_TX / RE_TX, as at DL_Sniffer_PDSCH.cc:1015-1018) */
 void ltephy_harq_update(ltephy_harq_t* q, uint16_t rnti, uint32_t pid, uint32_t tb, uint32_t ndi, uint32_t rv, int32_t tbs, uint32_t tti, int decoded);
-/* classify + fill grant->tb[t].harq_op / harq_slot of a C-RNTI grant from its DCI fields; DECODED disables the TB as the reference does */
+/* HARQ::getlastTbs (src/src/HARQ.cc:262-274): size of the last recorded transmission of (rnti, pid, tb), 0 if none */
+int32_t ltephy_harq_last_tbs(ltephy_harq_t* q, uint16_t rnti, uint32_t pid, uint32_t tb);
+/* classify + fill grant->tb[t].harq_op / harq_slot of a C-RNTI grant from its DCI fields; DECODED disables the TB as the reference does.  A block with a reserved MCS (tbs = 0 after ltephy_dci_to_grant) first gets
+ * the size of the process' last transmission (DCICollection.cc:236-252); it stays undecoded when there is none. */
 int ltephy_harq_prepare_grant(ltephy_harq_t* q, const ltephy_dci_fields_t* f, uint32_t tti, ltephy_grant_t* grant, int status[2]);
 
 /* DCI format 0 -> PUSCH grant (srsran_ra_ul_dci_to_grant as used at falcon_dci.c:222, and ulsniffer_ra_ul_dci_to_grant_256,

@@ -339,6 +339,7 @@ def _bind_search(L):
     L.ltephy_search_destroy.argtypes = [P]
     L.ltephy_search_config.argtypes = [P, C.c_int, C.c_int, C.c_uint32]
     L.ltephy_search_speculate_256qam.argtypes = [P, C.c_int]
+    L.ltephy_search_keep_reserved_mcs.argtypes = [P, C.c_int]
     L.ltephy_search_set_ul_hopping.argtypes = [P, C.c_uint32]
     L.ltephy_shard_set_gather_capacity.argtypes = [P, C.c_uint32]
     L.ltephy_search_add_evergreen.argtypes = [P, C.c_uint16, C.c_uint16, C.c_uint32]
@@ -537,6 +538,8 @@ class Harq:
         L.ltephy_harq_destroy.argtypes = [C.c_void_p]
         L.ltephy_harq_classify.argtypes = [C.c_void_p, C.c_uint16, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int32, C.c_uint32, C.POINTER(C.c_uint32)]
         L.ltephy_harq_update.argtypes = [C.c_void_p, C.c_uint16, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int32, C.c_uint32, C.c_int]
+        L.ltephy_harq_last_tbs.restype = C.c_int32
+        L.ltephy_harq_last_tbs.argtypes = [C.c_void_p, C.c_uint16, C.c_uint32, C.c_uint32]
         self.h = L.ltephy_harq_create(max_rnti)
         assert self.h
 
@@ -544,6 +547,9 @@ class Harq:
         slot = C.c_uint32(0)
         r = self.L.ltephy_harq_classify(self.h, rnti, pid, tb, ndi, tbs, tti, C.byref(slot))
         return r, slot.value
+
+    def last_tbs(self, rnti, pid, tb):
+        return self.L.ltephy_harq_last_tbs(self.h, rnti, pid, tb)
 
     def update(self, rnti, pid, tb, ndi, rv, tbs, tti, decoded):
         self.L.ltephy_harq_update(self.h, rnti, pid, tb, ndi, rv, tbs, tti, 1 if decoded else 0)

@@ -73,12 +73,24 @@ extern "C" void ltephy_harq_update(ltephy_harq_t* q, uint16_t rnti, uint32_t pid
   s.tti = tti % 10240u, s.ndi = (uint8_t)ndi, s.rv = (uint8_t)rv, s.tbs = tbs, s.is_first_transmission = false, s.last_decoded = decoded != 0;
 }
 
+// HARQ::getlastTbs (HARQ.cc:262-274): size of the last transmission recorded for (rnti, pid, tb); 0 when the RNTI has no entity yet
+extern "C" int32_t ltephy_harq_last_tbs(ltephy_harq_t* q, uint16_t rnti, uint32_t pid, uint32_t tb)
+{
+  if (!q || pid >= 8 || tb >= 2) return 0;
+  Entity *avail, *e = find(q, rnti, &avail);
+  return e ? e->tb[pid][tb].tbs : 0;
+}
+
 extern "C" int ltephy_harq_prepare_grant(ltephy_harq_t* q, const ltephy_dci_fields_t* f, uint32_t tti, ltephy_grant_t* g, int status[2])
 {
   if (!q || !f || !g || !status) return LTEPHY_ERROR_INVALID_INPUTS;
   for (int t = 0; t < 2; t++) {
     status[t] = -1;
     if (!g->tb[t].enabled) continue;
+    // a reserved MCS (29-31, or 28-31 of the 256QAM table) carries no size: ltephy_dci_to_grant leaves tbs = 0 and the reference takes the size of
+    // the process' last transmission (DCICollection::addCandidate, src/src/DCICollection.cc:236-252).  Still 0: nothing known, the block is not decoded
+    if (g->tb[t].tbs == 0) g->tb[t].tbs = ltephy_harq_last_tbs(q, g->rnti, f->harq_pid, (uint32_t)t);
+    if (g->tb[t].tbs <= 0) continue;
     uint32_t slot = 0;
     status[t]     = ltephy_harq_classify(q, g->rnti, f->harq_pid, (uint32_t)t, f->ndi[t], g->tb[t].tbs, tti, &slot);
     g->tb[t].harq_op = LTEPHY_HARQ_NONE, g->tb[t].harq_slot = 0;

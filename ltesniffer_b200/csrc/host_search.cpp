@@ -256,6 +256,7 @@ struct ltephy_search {
   uint32_t           n_primary = 0, n_secondary = 0;
   double             split_ratio     = 0.99;
   bool               skip_secondary  = false, shortcut = true;
+  bool               keep_reserved_mcs = false; // HARQ mode: a C-RNTI grant whose first block has a reserved MCS is kept, ltephy_harq_prepare_grant sizes it
   bool               speculate_256qam = false; // grants_from_dcis emits both MCS-table readings of a C-RNTI DCI (DL_Sniffer_PDSCH.cc:1089-1210)
   uint32_t           update_interval = 500, sf_cnt = 0;
   uint32_t           ul_n_rb_ho = 0; // pusch-HoppingOffset of SIB2 (hopping_cfg.n_rb_ho, src/src/DCICollection.cc:168)
@@ -976,6 +977,10 @@ void ltephy_search_set_ul_hopping(ltephy_search_t* s, uint32_t n_rb_ho)
 {
   if (s) s->ul_n_rb_ho = n_rb_ho;
 }
+void ltephy_search_keep_reserved_mcs(ltephy_search_t* s, int on)
+{
+  if (s) s->keep_reserved_mcs = on != 0;
+}
 void ltephy_search_speculate_256qam(ltephy_search_t* s, int on)
 {
   if (s) s->speculate_256qam = on != 0;
@@ -1142,7 +1147,10 @@ static int grants_from_dcis_impl(const ltephy_search_t* s, TtiCfi tc, const ltep
 {
   uint32_t ng = 0;
   auto eligible = [&](const ltephy_grant_t& g) {
-    if (!(g.tb[0].tbs > 0 && !(s->cell.nof_rx == 1 && g.nof_tb == 2))) return false;
+    // tbs = 0: reserved MCS.  The reference applies this rule after DCICollection gave such a block the size of its HARQ process' last transmission
+    // (DCICollection.cc:236-252), which here is the caller's ltephy_harq_prepare_grant -- so in that mode the grant has to get through
+    const bool sized = g.tb[0].tbs > 0 || (s->keep_reserved_mcs && g.tb[0].enabled && user_rnti(g.rnti));
+    if (!(sized && !(s->cell.nof_rx == 1 && g.nof_tb == 2))) return false;
     if (g.tx_scheme == LTEPHY_TX_SPATIALMUX && (s->cell.nof_ports != 2 || (g.nof_tb == 2 && s->cell.nof_rx != 2))) return false;
     return true;
   };

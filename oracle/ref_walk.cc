@@ -271,6 +271,8 @@ void refharq_update(void* q, uint16_t rnti, int pid, int tid, int ndi, int rv, i
   static_cast<HARQ*>(q)->updateHARQRNTI(rnti, pid, tid, tti / 10, tti % 10, g);
 }
 
+int refharq_last_tbs(void* q, uint16_t rnti, int pid, int tid) { return static_cast<HARQ*>(q)->getlastTbs(rnti, pid, tid); }
+
 // SubframePower::computePower (src/src/SubframePower.cc:18-47, called at DCISearch.cc:565): per-PRB power of antenna 0 in dB
 void refwalk_rb_power(uint32_t nof_prb, const cf_t* sf_symbols, float* out_db)
 {

@@ -214,3 +214,55 @@ def test_harq_prepare_grant_fills_the_grant(phylib):
     assert L.ltephy_harq_prepare_grant(q.h, C.byref(f), 216, C.byref(g), st) == 0
     assert (st[0], g.tb[0].enabled, g.tb[0].harq_op) == (capi.HARQ_DECODED, 0, capi.HARQ_NONE)
     q.close()
+
+
+def test_reserved_mcs_block_is_sized_from_the_harq_process(phylib, infra):
+    """An adaptive retransmission with a reserved MCS (29-31) carries no size: ltephy_dci_to_grant leaves tbs = 0, and in HARQ mode the reference gives
+    the block the size of its process' last transmission before the "tbs > 0" skip rule (DCICollection::addCandidate, src/src/DCICollection.cc:236-252;
+    HARQ::getlastTbs, src/src/HARQ.cc:262-274).  Here: ltephy_search_keep_reserved_mcs lets the grant through ltephy_grants_from_dcis,
+    ltephy_harq_prepare_grant sizes and classifies it; without a recorded transmission it stays at 0 and is not decoded."""
+    import ctypes as C
+    S = infra.sim()
+    L = capi.load_library()
+    capi._bind_search(L)
+    cell = Cell(25, 1, 77, 1)
+    srch = capi.Search(cell.nof_prb, cell.nof_ports, cell.cell_id, cell.nof_rx)
+    rng = np.random.default_rng(4)
+    nb = S.lte_dci_sizeof(C.byref(cell), 1)
+    rnti, tti, cfi = 0x2345, 508, 2
+    row = np.zeros(1, capi.DCI_DTYPE)
+    for _ in range(20000):                                    # a format-1 payload whose MCS field reads 29 and which is a valid grant otherwise
+        bits = rng.integers(0, 2, nb).astype(np.uint8)
+        v = 0
+        for k, b in enumerate(bits):
+            v |= int(b) << (63 - k)
+        row["sf"], row["rnti"], row["format"], row["nof_bits"], row["bits"] = 0, rnti, 1, nb, v
+        rc, g, f = srch.dci_to_grant(row[0], tti % 10, cfi, 0)
+        if rc == 0 and f.mcs[0] == 29:
+            break
+    assert rc == 0 and f.mcs[0] == 29 and g.tb[0].enabled and g.tb[0].tbs == 0 and g.tb[0].qm == 2
+    info = (capi.SfInfo * 1)()
+    info[0].tti, info[0].cfi = tti, cfi
+    grants = (capi.Grant * 4)()
+    gidx = np.zeros(4, np.uint32)
+    ng = C.c_uint32(0)
+
+    def build():
+        assert L.ltephy_grants_from_dcis(srch.h, info, row.ctypes.data_as(C.c_void_p), 1, 1, 0, grants, gidx.ctypes.data_as(C.c_void_p), 4, C.byref(ng)) == 0
+        return ng.value
+    assert build() == 0                                       # decode_dl_mode's skip rule (DL_Sniffer_PDSCH.cc:887)
+    L.ltephy_search_keep_reserved_mcs(srch.h, 1)
+    assert build() == 1 and grants[0].tb[0].tbs == 0 and grants[0].rnti == rnti
+    L.ltephy_harq_prepare_grant.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]
+    q = capi.Harq(max_rnti=4)
+    st = (C.c_int * 2)()
+    gr = capi.Grant.from_buffer_copy(grants[0])
+    assert L.ltephy_harq_prepare_grant(q.h, C.byref(f), tti, C.byref(gr), st) == 0
+    assert (st[0], gr.tb[0].tbs, gr.tb[0].harq_op, gr.tb[0].enabled) == (-1, 0, capi.HARQ_NONE, 1)      # nothing known about this process
+    assert q.classify(rnti, f.harq_pid, 0, f.ndi[0], 2216, tti - 8)[0] == capi.HARQ_NEW_TX               # the first transmission, 8 ms earlier, failed
+    q.update(rnti, f.harq_pid, 0, f.ndi[0], 0, 2216, tti - 8, False)
+    assert q.last_tbs(rnti, f.harq_pid, 0) == 2216 and q.last_tbs(rnti, (f.harq_pid + 1) % 8, 0) == 0 and q.last_tbs(0x999, 0, 0) == 0
+    gr = capi.Grant.from_buffer_copy(grants[0])
+    assert L.ltephy_harq_prepare_grant(q.h, C.byref(f), tti, C.byref(gr), st) == 0
+    assert (st[0], gr.tb[0].tbs, gr.tb[0].harq_op, gr.tb[0].qm) == (capi.HARQ_RE_TX, 2216, capi.HARQ_RETX, 2)
+    q.close()

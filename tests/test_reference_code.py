@@ -293,6 +293,7 @@ def test_harq_bookkeeping_equals_the_reference_class(infra):
     R.refharq_size.argtypes = [C.c_void_p]
     R.refharq_is_retransmission.argtypes = [C.c_void_p, C.c_uint16, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint32, C.POINTER(C.c_void_p)]
     R.refharq_update.argtypes = [C.c_void_p, C.c_uint16, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint32, C.c_int]
+    R.refharq_last_tbs.argtypes = [C.c_void_p, C.c_uint16, C.c_int, C.c_int]
     ref = R.refharq_create()
     q = capi.Harq(max_rnti=R.refharq_size(ref))
     rng = np.random.default_rng(12)
@@ -316,6 +317,7 @@ def test_harq_bookkeeping_equals_the_reference_class(infra):
         rv = int(rng.integers(0, 4))
         b = C.c_void_p()
         s_ref = R.refharq_is_retransmission(ref, rnti, pid, tb, ndi, rv, tbs, t, C.byref(b))
+        assert q.last_tbs(rnti, pid, tb) == R.refharq_last_tbs(ref, rnti, pid, tb)     # HARQ::getlastTbs: what a reserved-MCS block is sized with
         s_own, slot = q.classify(rnti, pid, tb, ndi, tbs, t)
         assert s_own == s_ref, (step, hex(rnti), pid, tb, s_own, s_ref)
         seen[s_ref] = seen.get(s_ref, 0) + 1
