@@ -131,6 +131,18 @@ int ltephy_harq_prepare_grant(ltephy_harq_t* q, const ltephy_dci_fields_t* f, ui
  * Returns 0, or LTEPHY_ERROR for an invalid hop / retransmission MCS / invalid RIV / L_prb outside the DFT set or < 3 / no TBS. */
 int ltephy_ul_dci_to_grant(const ltephy_search_t* s, const ltephy_dci_t* dci, int enable_64qam, ltephy_ul_grant_t* grant);
 
+/* What MCSTracking knows about the UE's uplink table (ul_sniffer_mod_tracking_t, lib/include/falcon/phy/falcon_phch/falcon_dci.h:115-122) */
+#define LTEPHY_UL_MOD_16QAM_MAX 0
+#define LTEPHY_UL_MOD_64QAM_MAX 1
+#define LTEPHY_UL_MOD_256QAM_MAX 2
+#define LTEPHY_UL_MOD_UNKNOWN 3
+/* The decode attempts of PUSCH_Decoder::decode for one accepted format-0 DCI, in the reference's order (src/src/UL_Sniffer_PUSCH.cc:417-570), after its
+ * investigate_valid_ul_grant filter (:894-918): MCS 21-28 -> the known table's reading, or 16QAM, 64QAM, 256QAM when unknown; MCS 0-20 -> 16QAM (= 64QAM)
+ * or 256QAM, or both when unknown.  grants[3] / reading[3] (the enable_64qam value of each) are filled; returns their number (0: the reference does not
+ * decode this DCI) or LTEPHY_ERROR_INVALID_INPUTS.  The reference stops at the first attempt whose CRC passes; submit all of them in one ltephy_submit_ul
+ * batch and keep the first passing one in this order. */
+int ltephy_ul_decode_plan(const ltephy_search_t* s, const ltephy_dci_t* dci, int mcs_mod, ltephy_ul_grant_t* grants, uint8_t* reading);
+
 /* Whole batch: IQ in host memory -> accepted DCIs + transport blocks.  seq orders concurrent calls on
  * different PHY handles that share one search object (the search runs strictly in seq order, starting
  * at 0); pass LTEPHY_SEQ_NONE for a single pipeline.

@@ -364,6 +364,7 @@ def _bind_search(L):
     L.ltephy_search_rnti_reason.argtypes = [P, C.c_uint16]
     L.ltephy_dci_to_grant.argtypes = [P, P, C.c_uint32, C.c_uint32, C.c_int, P, P]
     L.ltephy_ul_dci_to_grant.argtypes = [P, P, C.c_int, P]
+    L.ltephy_ul_decode_plan.argtypes = [P, P, C.c_int, P, P]
     L.ltephy_decode_subframes.argtypes = [P, P, P, P, C.c_uint32, C.c_uint64, P, P, P, C.c_uint32, P, P, P, C.c_size_t]
     L.ltephy_decode_subframes_device.argtypes = [P, P, P, P, C.c_uint32, C.c_uint64, P, P, P, C.c_uint32, P, P, P, C.c_size_t]
     L.ltephy_search_batch.argtypes = [P, P, P, C.c_uint32, P, C.c_uint32, P]
@@ -459,6 +460,18 @@ def ul_dci_to_grant(search, dci_row, enable_64qam=1):
     g = UlGrant()
     r = search.L.ltephy_ul_dci_to_grant(search.h, C.byref(d), enable_64qam, C.byref(g))
     return r, g
+
+
+def ul_decode_plan(search, dci_row, mcs_mod):
+    """the decode attempts PUSCH_Decoder::decode makes for this DCI: [(reading, UlGrant)] via ltephy_ul_decode_plan"""
+    d = DciOut(sf=int(dci_row["sf"]), rnti=int(dci_row["rnti"]), format=int(dci_row["format"]), L=int(dci_row["L"]), ncce=int(dci_row["ncce"]),
+               nof_bits=int(dci_row["nof_bits"]), bits=int(dci_row["bits"]), histogram_value=int(dci_row["histogram_value"]))
+    g = (UlGrant * 3)()
+    rd = (C.c_uint8 * 3)()
+    n = search.L.ltephy_ul_decode_plan(search.h, C.byref(d), mcs_mod, g, rd)
+    if n < 0:
+        raise ValueError("ltephy_ul_decode_plan: %d" % n)
+    return [(int(rd[k]), UlGrant.from_buffer_copy(g[k])) for k in range(n)]
 
 
 def decode_subframes(phy, search, iq, tti, seq=SEQ_NONE, max_dcis=None, scratch=None):

@@ -877,6 +877,42 @@ int ltephy_ul_dci_to_grant(const ltephy_search_t* s, const ltephy_dci_t* d, int 
   return LTEPHY_SUCCESS;
 }
 
+// The readings of one accepted format-0 DCI that PUSCH_Decoder::decode tries, in its order (reference src/src/UL_Sniffer_PUSCH.cc:417-570), given what
+// MCSTracking knows of the UE (mcs_mod = ul_sniffer_mod_tracking_t).  The reference runs them one after the other and stops at the first CRC pass; a
+// batch caller submits them all in one ltephy_submit_ul and keeps the first in this order whose CRC passed -- same outcome, one launch.
+int ltephy_ul_decode_plan(const ltephy_search_t* s, const ltephy_dci_t* d, int mcs_mod, ltephy_ul_grant_t* grants, uint8_t* reading)
+{
+  if (!s || !d || !grants || !reading || mcs_mod < LTEPHY_UL_MOD_16QAM_MAX || mcs_mod > LTEPHY_UL_MOD_UNKNOWN) return LTEPHY_ERROR_INVALID_INPUTS;
+  // investigate_valid_ul_grant (:894-918): RNTI 0, no transport block size in either table (retransmission MCS, failed allocation) or an L_prb that is no DFT
+  // size -> not decoded.  All of it is what makes the Table 8.6.1-1 conversion fail here.
+  ltephy_ul_grant_t g1;
+  if (d->rnti == 0 || ltephy_ul_dci_to_grant(s, d, 1, &g1) != LTEPHY_SUCCESS) return 0;
+  const uint32_t N = s->cell.nof_prb, rivb = clog2(N * (N + 1) / 2);
+  Bits           b{d->bits};
+  b.get(2), b.get(rivb);
+  const uint32_t mcs = b.get(5);
+  int            order[3], n = 0;
+  if (mcs > 20) { // :456-529
+    if (mcs_mod == LTEPHY_UL_MOD_UNKNOWN)
+      order[n++] = 0, order[n++] = 1, order[n++] = 2;
+    else
+      order[n++] = mcs_mod;
+  } else { // :531-569: up to MCS 20 the 16QAM and 64QAM readings are the same grant
+    if (mcs_mod == LTEPHY_UL_MOD_16QAM_MAX || mcs_mod == LTEPHY_UL_MOD_64QAM_MAX)
+      order[n++] = 0;
+    else if (mcs_mod == LTEPHY_UL_MOD_256QAM_MAX)
+      order[n++] = 2;
+    else
+      order[n++] = 0, order[n++] = 2;
+  }
+  int m = 0;
+  for (int k = 0; k < n; k++) { // a reading without a transport block size (MCS 28 has no row in Table 8.6.1-3) cannot pass a CRC in the reference either
+    if (ltephy_ul_dci_to_grant(s, d, order[k], &grants[m]) != LTEPHY_SUCCESS) continue;
+    reading[m++] = (uint8_t)order[k];
+  }
+  return m;
+}
+
 // One line of the DCI trace file, DCIToFile::printDCICollection (reference src/src/SubframeInfoConsumer.cc:66-138); the hex column is
 // sprint_hex of the payload bits (lib/src/phy/falcon_phch/falcon_dci.c:37-58).  Declared in include/ltephy_sinks.h.
 extern "C" int ltephy_dci_trace_line(const ltephy_search_t* s, const ltephy_dci_t* d, uint32_t tti, uint32_t cfi, int use_256qam_table, uint32_t ts_sec,

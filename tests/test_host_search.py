@@ -345,3 +345,52 @@ def test_empty_and_degenerate_inputs(infra):
     row["format"] = 9
     r, g, f = srch.dci_to_grant(row, 0, 2, 0)
     assert r != 0
+
+
+def test_ul_decode_plan_follows_pusch_decoder(infra):
+    """ltephy_ul_decode_plan: the attempts of PUSCH_Decoder::decode (reference src/src/UL_Sniffer_PUSCH.cc:417-570) per MCS range and MCSTracking answer,
+    behind investigate_valid_ul_grant (:894-918).  Expectations written out from the reference's branches:
+      MCS 21..28: 16QAM_MAX -> [16]; 64QAM_MAX -> [64]; 256QAM_MAX -> [256]; unknown -> [16, 64, 256]
+      MCS  0..20: 16QAM_MAX / 64QAM_MAX -> [16]; 256QAM_MAX -> [256]; unknown -> [16, 256]
+      MCS 29..31 (no size), L_prb that is no DFT size, RNTI 0: nothing
+    MCS 28 has no row in Table 8.6.1-3 (I_TBS 34): that reading is dropped (in the reference it runs with tbs = -1 and cannot pass)."""
+    S = infra.sim()
+    cell = Cell(50, 2, 3, 2)
+    srch = capi.Search(cell.nof_prb, cell.nof_ports, cell.cell_id, cell.nof_rx)
+    nb = S.lte_dci_sizeof(C.byref(cell), 0)
+    N = cell.nof_prb
+    rivb = int(np.ceil(np.log2(N * (N + 1) / 2)))
+
+    def dci(L, start, mcs, rnti=0x1234):
+        riv = N * (L - 1) + start if L - 1 <= N // 2 else N * (N - L + 1) + (N - 1 - start)
+        fields = [(0, 1), (0, 1), (riv, rivb), (mcs, 5), (1, 1), (0, 2), (3, 3), (0, 1)]
+        v, pos = 0, 0
+        for val, w in fields:
+            v |= val << (64 - pos - w)
+            pos += w
+        row = np.zeros(1, capi.DCI_DTYPE)
+        row["rnti"], row["format"], row["nof_bits"], row["bits"], row["L"] = rnti, 0, nb, v, 2
+        return row[0]
+    M16, M64, M256, UNK = 0, 1, 2, 3
+    want = {}
+    for mcs in range(32):
+        if mcs > 28:
+            want[mcs] = {m: [] for m in (M16, M64, M256, UNK)}
+        elif mcs > 20:
+            want[mcs] = {M16: [0], M64: [1], M256: [2], UNK: [0, 1, 2]}
+        else:
+            want[mcs] = {M16: [0], M64: [0], M256: [2], UNK: [0, 2]}
+    for mcs in range(32):
+        for mod in (M16, M64, M256, UNK):
+            plan = capi.ul_decode_plan(srch, dci(10, 7, mcs), mod)
+            exp = [r for r in want[mcs][mod] if not (r == 2 and mcs == 28)]
+            assert [r for r, _ in plan] == exp, (mcs, mod, plan)
+            for r, g in plan:
+                rc, gd = capi.ul_dci_to_grant(srch, dci(10, 7, mcs), r)
+                assert rc == 0 and bytes(g) == bytes(gd) and (g.L_prb, g.n_prb, g.rnti) == (10, 7, 0x1234)
+            if mcs in range(21, 28) and mod == UNK:           # the three readings differ where they should
+                assert [g.qm for _, g in plan][:2] == [4, 6] and plan[2][1].qm in (6, 8)
+    assert capi.ul_decode_plan(srch, dci(7, 0, 10), UNK) == []                 # valid_prb_ul[7] is false
+    assert capi.ul_decode_plan(srch, dci(10, 7, 10, rnti=0), UNK) == []
+    with pytest.raises(ValueError):
+        capi.ul_decode_plan(srch, dci(10, 7, 10), 4)
