@@ -143,6 +143,20 @@ int ltephy_ul_dci_to_grant(const ltephy_search_t* s, const ltephy_dci_t* dci, in
  * batch and keep the first passing one in this order. */
 int ltephy_ul_decode_plan(const ltephy_search_t* s, const ltephy_dci_t* dci, int mcs_mod, ltephy_ul_grant_t* grants, uint8_t* reading);
 
+/* What the reference keeps per RNTI for the uplink (MCSTracking::get_ue_config_rnti / find_tracking_info_RNTI_ul, used at UL_Sniffer_PUSCH.cc:433-452) */
+typedef struct {
+  uint16_t rnti;      /* 0: the default entry, for every RNTI without its own */
+  uint8_t  mcs_mod;   /* LTEPHY_UL_MOD_* */
+  uint8_t  I_offset_ack, I_offset_cqi, I_offset_ri; /* ue_config.uci_config; SubframeWorker::setup_default_ul_cfg: 10 / 8 / 11 */
+  uint16_t cqi_len;   /* srsran_cqi_size of the aperiodic report this UE sends when a DCI-0 requests one (0: no CQI region assumed) */
+} ltephy_ul_ue_cfg_t;
+/* UL mode, whole batch: the accepted DCIs of a batch of downlink subframes -> the PUSCH decode attempts to submit 4 subframes later
+ * (SubframeWorker.cc:296-345: nof_ack from the downlink DCIs of the same RNTI and subframe; ULSchedule's n + 4; UL_Sniffer_PUSCH.cc:417-570: validity
+ * filter, CSI request, attempt order).  grants[k].sf = dcis[grant_dci[k]].sf + 4 (indices >= the batch length belong to the next uplink batch);
+ * reading[k] = the enable_64qam value of attempt k; the attempts of one DCI are adjacent and in the reference's order -- keep the first whose CRC passes. */
+int ltephy_ul_grants_from_dcis(const ltephy_search_t* s, const ltephy_sf_info_t* info, const ltephy_dci_t* dcis, uint32_t nd, const ltephy_ul_ue_cfg_t* ue,
+                               uint32_t n_ue, ltephy_ul_grant_t* grants, uint32_t* grant_dci, uint8_t* reading, uint32_t max_grants, uint32_t* n_grants);
+
 /* Whole batch: IQ in host memory -> accepted DCIs + transport blocks.  seq orders concurrent calls on
  * different PHY handles that share one search object (the search runs strictly in seq order, starting
  * at 0); pass LTEPHY_SEQ_NONE for a single pipeline.

@@ -55,6 +55,11 @@ class UlGrant(C.Structure):
                 ("cqi_len", C.c_uint16), ("I_offset_ack", C.c_uint8), ("I_offset_cqi", C.c_uint8), ("I_offset_ri", C.c_uint8), ("flags", C.c_uint8)]
 
 
+class UlUeCfg(C.Structure):
+    _fields_ = [("rnti", C.c_uint16), ("mcs_mod", C.c_uint8), ("I_offset_ack", C.c_uint8), ("I_offset_cqi", C.c_uint8), ("I_offset_ri", C.c_uint8),
+                ("cqi_len", C.c_uint16)]
+
+
 class Mib(C.Structure):
     _fields_ = [("found", C.c_uint8), ("nof_ports", C.c_uint8), ("sfn_offset", C.c_uint8), ("phich_length", C.c_uint8), ("phich_resources", C.c_uint8),
                 ("bch_payload", C.c_uint8 * 3), ("nof_prb", C.c_uint32), ("sfn", C.c_uint32)]
@@ -365,6 +370,7 @@ def _bind_search(L):
     L.ltephy_dci_to_grant.argtypes = [P, P, C.c_uint32, C.c_uint32, C.c_int, P, P]
     L.ltephy_ul_dci_to_grant.argtypes = [P, P, C.c_int, P]
     L.ltephy_ul_decode_plan.argtypes = [P, P, C.c_int, P, P]
+    L.ltephy_ul_grants_from_dcis.argtypes = [P, P, P, C.c_uint32, P, C.c_uint32, P, P, P, C.c_uint32, P]
     L.ltephy_decode_subframes.argtypes = [P, P, P, P, C.c_uint32, C.c_uint64, P, P, P, C.c_uint32, P, P, P, C.c_size_t]
     L.ltephy_decode_subframes_device.argtypes = [P, P, P, P, C.c_uint32, C.c_uint64, P, P, P, C.c_uint32, P, P, P, C.c_size_t]
     L.ltephy_search_batch.argtypes = [P, P, P, C.c_uint32, P, C.c_uint32, P]
@@ -472,6 +478,22 @@ def ul_decode_plan(search, dci_row, mcs_mod):
     if n < 0:
         raise ValueError("ltephy_ul_decode_plan: %d" % n)
     return [(int(rd[k]), UlGrant.from_buffer_copy(g[k])) for k in range(n)]
+
+
+def ul_grants_from_dcis(search, info, dcis, ue_cfgs=()):
+    """accepted DCIs of a downlink batch -> [(dci index, reading, UlGrant)] via ltephy_ul_grants_from_dcis (grant.sf = dci.sf + 4)"""
+    nd = len(dcis)
+    cap = 3 * nd + 1
+    g = (UlGrant * cap)()
+    gd = np.zeros(cap, np.uint32)
+    rd = np.zeros(cap, np.uint8)
+    ng = C.c_uint32(0)
+    ue = (UlUeCfg * max(1, len(ue_cfgs)))(*ue_cfgs)
+    r = search.L.ltephy_ul_grants_from_dcis(search.h, info, dcis.ctypes.data_as(C.c_void_p), nd, ue, len(ue_cfgs), g, gd.ctypes.data_as(C.c_void_p),
+                                            rd.ctypes.data_as(C.c_void_p), cap, C.byref(ng))
+    if r != 0:
+        raise ValueError("ltephy_ul_grants_from_dcis: %d" % r)
+    return [(int(gd[k]), int(rd[k]), UlGrant.from_buffer_copy(g[k])) for k in range(ng.value)]
 
 
 def decode_subframes(phy, search, iq, tti, seq=SEQ_NONE, max_dcis=None, scratch=None):

@@ -1234,6 +1234,58 @@ int ltephy_grants_from_dcis_tc(const ltephy_search_t* s, const uint32_t* tti_cfi
                                grants, grant_dci, max_grants, n_grants);
 }
 
+// UL mode, one batch: what SubframeWorker does per subframe between the search and PUSCH_Decoder::decode (reference src/src/SubframeWorker.cc:296-345)
+// and the attempts that decoder then makes (ltephy_ul_decode_plan), for all DCI-0s of a batch of downlink subframes at once.
+//   * the PUSCH of a DCI-0 seen at tti n is on the air at n + 4 (ULSchedule::pushULSche / get_ul_tti, src/src/ULSchedule.cc:112-124): grant.sf = dci.sf + 4,
+//     an index into the uplink batch that starts at the same tti as the downlink batch -- indices >= the batch length belong to the next one;
+//   * nof_ack = number of transport blocks of a downlink DCI of the same RNTI in the same subframe, the last such DCI winning (SubframeWorker.cc:318-337);
+//   * an aperiodic CSI request (last payload bit, FDD) adds ri_len = 1 and the UE's CQI size (UL_Sniffer_PUSCH.cc:437-450);
+//   * beta offsets and the MCS-table knowledge come per RNTI from ue[] (MCSTracking::get_ue_config_rnti / find_tracking_info_RNTI_ul), entry rnti = 0
+//     being the default; without any: unknown table, 10 / 8 / 11 (SubframeWorker::setup_default_ul_cfg, SubframeWorker.cc:347-352), no CQI size.
+int ltephy_ul_grants_from_dcis(const ltephy_search_t* s, const ltephy_sf_info_t* info, const ltephy_dci_t* dcis, uint32_t nd, const ltephy_ul_ue_cfg_t* ue,
+                               uint32_t n_ue, ltephy_ul_grant_t* grants, uint32_t* grant_dci, uint8_t* reading, uint32_t max_grants, uint32_t* n_grants)
+{
+  if (!s || !info || !dcis || !grants || !grant_dci || !reading || !n_grants || (n_ue && !ue)) return LTEPHY_ERROR_INVALID_INPUTS;
+  const uint32_t N = s->cell.nof_prb, rivb = clog2(N * (N + 1) / 2);
+  uint32_t       ng = 0;
+  for (uint32_t i = 0; i < nd; i++) {
+    const ltephy_dci_t& d = dcis[i];
+    if (d.format != ltehost::F0 || d.rnti == 0) continue;
+    ltephy_ul_ue_cfg_t cfg{0, LTEPHY_UL_MOD_UNKNOWN, 10, 8, 11, 0};
+    for (uint32_t k = 0; k < n_ue; k++)
+      if (ue[k].rnti == 0) cfg = ue[k];
+    for (uint32_t k = 0; k < n_ue; k++)
+      if (ue[k].rnti == d.rnti) cfg = ue[k];
+    ltephy_ul_grant_t g[3];
+    uint8_t           rd[3];
+    const int         n = ltephy_ul_decode_plan(s, &d, cfg.mcs_mod, g, rd);
+    if (n < 0) return n;
+    if (n == 0) continue;
+    uint8_t nof_ack = 0;
+    for (uint32_t j = 0; j < nd; j++) { // the accepted DCIs of one subframe are adjacent, but nothing here relies on it
+      const ltephy_dci_t& dl = dcis[j];
+      if (dl.sf != d.sf || dl.format == ltehost::F0 || dl.rnti != d.rnti) continue;
+      ltephy_grant_t gd;
+      const int      r = ltephy_dci_to_grant(s, &dl, info[dl.sf].tti % 10, info[dl.sf].cfi, 0, &gd, nullptr);
+      // a DCI whose conversion fails has its RNTI zeroed by the reference (falcon_dci.c:286-305); the MIMO checks come later, in the decoder
+      if (r != LTEPHY_SUCCESS && r != LTEPHY_MIMO_NOT_SUPPORT && r != LTEPHY_MIMO_PMI_WRONG && r != LTEPHY_MIMO_LAYER_WRONG) continue;
+      if (gd.nof_tb == 1 || gd.nof_tb == 2) nof_ack = (uint8_t)gd.nof_tb;
+    }
+    Bits b{d.bits};
+    b.get(2), b.get(rivb), b.get(5 + 1 + 2 + 3);
+    const bool cqi_request = b.get(1) != 0;
+    for (int k = 0; k < n; k++) {
+      if (ng >= max_grants) return LTEPHY_ERROR_INVALID_INPUTS;
+      g[k].sf = d.sf + 4, g[k].nof_ack = nof_ack, g[k].ri_len = cqi_request ? 1 : 0, g[k].cqi_len = cqi_request ? cfg.cqi_len : 0;
+      g[k].I_offset_ack = cfg.I_offset_ack, g[k].I_offset_cqi = cfg.I_offset_cqi, g[k].I_offset_ri = cfg.I_offset_ri;
+      grants[ng] = g[k], grant_dci[ng] = i, reading[ng] = rd[k];
+      ng++;
+    }
+  }
+  *n_grants = ng;
+  return LTEPHY_SUCCESS;
+}
+
 // ===================================================================================================
 // Packed survivor form (include/ltephy_shard.h): header + location records + survivor list, back to back.
 size_t ltephy_packed_size(uint32_t nloc, uint32_t count)

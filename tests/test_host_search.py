@@ -394,3 +394,62 @@ def test_ul_decode_plan_follows_pusch_decoder(infra):
     assert capi.ul_decode_plan(srch, dci(10, 7, 10, rnti=0), UNK) == []
     with pytest.raises(ValueError):
         capi.ul_decode_plan(srch, dci(10, 7, 10), 4)
+
+
+def test_ul_grants_from_dcis_follows_subframe_worker(infra):
+    """ltephy_ul_grants_from_dcis: the UL-mode bookkeeping of SubframeWorker (reference src/src/SubframeWorker.cc:296-345) for a batch --
+    PUSCH 4 subframes after its DCI-0 (ULSchedule::get_ul_tti), nof_ack = transport blocks of the same RNTI's downlink DCI in the same subframe (last one
+    wins), CSI request -> ri_len 1 + the UE's CQI size, per-RNTI beta offsets / MCS-table knowledge with a default entry, attempts in PUSCH_Decoder's order."""
+    S = infra.sim()
+    cell = Cell(50, 2, 3, 2)
+    srch = capi.Search(cell.nof_prb, cell.nof_ports, cell.cell_id, cell.nof_rx)
+    N = cell.nof_prb
+    rivb = int(np.ceil(np.log2(N * (N + 1) / 2)))
+    nb0 = S.lte_dci_sizeof(C.byref(cell), 0)
+    rng = np.random.default_rng(8)
+    A, B, Cc, D = 0x1001, 0x1002, 0x1003, 0x1004
+
+    def dci0(sf, rnti, L, start, mcs, cqi_req):
+        riv = N * (L - 1) + start if L - 1 <= N // 2 else N * (N - L + 1) + (N - 1 - start)
+        v, pos = 0, 0
+        for val, w in [(0, 1), (0, 1), (riv, rivb), (mcs, 5), (1, 1), (0, 2), (3, 3), (cqi_req, 1)]:
+            v |= val << (64 - pos - w)
+            pos += w
+        return (sf, rnti, 0, nb0, v)
+
+    def dl(sf, rnti, f, want_tb):
+        nb = S.lte_dci_sizeof(C.byref(cell), f)
+        for _ in range(5000):
+            bits = rng.integers(0, 2, nb).astype(np.uint8)
+            r0, d, g = ltelib.unpack_and_grant(cell, f, rnti, bits, (20 + sf) % 10, 2, 0)
+            if r0 == 0 and g.nof_tb == want_tb and g.tb[0].tbs > 0:
+                break
+        else:
+            raise AssertionError("no payload found")
+        v = 0
+        for k, b in enumerate(bits):
+            v |= int(b) << (63 - k)
+        return (sf, rnti, f, nb, v)
+    rows = [dl(0, A, 1, 1), dl(0, B, 6, 2), dl(0, B, 1, 1), dci0(0, A, 10, 7, 22, 0), dci0(0, B, 12, 20, 5, 0), dci0(0, Cc, 6, 2, 15, 1),
+            dl(1, Cc, 6, 2), dci0(1, Cc, 8, 0, 27, 1), dci0(1, D, 7, 0, 3, 0), dci0(1, A, 10, 7, 30, 0),
+            dl(2, A, 6, 2), dci0(3, A, 10, 7, 22, 0)]
+    dcis = np.zeros(len(rows), capi.DCI_DTYPE)
+    for i, (sf, rnti, f, nb, v) in enumerate(rows):
+        dcis[i]["sf"], dcis[i]["rnti"], dcis[i]["format"], dcis[i]["nof_bits"], dcis[i]["bits"] = sf, rnti, f, nb, v
+    info = (capi.SfInfo * 4)()
+    for i in range(4):
+        info[i].tti, info[i].cfi = 20 + i, 2
+    ue = [capi.UlUeCfg(rnti=A, mcs_mod=1, I_offset_ack=9, I_offset_cqi=6, I_offset_ri=5, cqi_len=0), capi.UlUeCfg(rnti=0, mcs_mod=3, I_offset_ack=10, I_offset_cqi=8, I_offset_ri=11, cqi_len=20)]
+    out = capi.ul_grants_from_dcis(srch, info, dcis, ue)
+    got = [(di, rd, g.sf, g.rnti, g.nof_ack, g.ri_len, g.cqi_len, (g.I_offset_ack, g.I_offset_cqi, g.I_offset_ri), g.L_prb, g.qm) for di, rd, g in out]
+    dflt, ofsA = (10, 8, 11), (9, 6, 5)
+    assert got == [
+        (3, 1, 4, A, 1, 0, 0, ofsA, 10, 6),                               # A: 64QAM known, MCS 22 -> one attempt; one downlink TB in its subframe
+        (4, 0, 4, B, 1, 0, 0, dflt, 12, 2), (4, 2, 4, B, 1, 0, 0, dflt, 12, 2),      # B: unknown, MCS 5 -> 16QAM and 256QAM readings; last downlink DCI (1 TB) wins
+        (5, 0, 4, Cc, 0, 1, 20, dflt, 6, 4), (5, 2, 4, Cc, 0, 1, 20, dflt, 6, 6),    # C: no downlink DCI in subframe 0; CSI request -> RI bit + 20 CQI bits
+        (7, 0, 5, Cc, 2, 1, 20, dflt, 8, 4), (7, 1, 5, Cc, 2, 1, 20, dflt, 8, 6), (7, 2, 5, Cc, 2, 1, 20, dflt, 8, 8),   # MCS 27 unknown: 16, 64, 256; two TBs
+        # D: 7 PRB is no DFT size; A at MCS 30: no size -> neither is decoded (investigate_valid_ul_grant)
+        (11, 1, 7, A, 0, 0, 0, ofsA, 10, 6)]                              # the two-TB DCI of A is in subframe 2, not 3; sf 7 belongs to the next uplink batch
+    assert capi.ul_grants_from_dcis(srch, info, dcis[:3]) == [] and capi.ul_grants_from_dcis(srch, info, dcis[:0]) == []
+    nodef = capi.ul_grants_from_dcis(srch, info, dcis[3:4])               # no UE table at all: unknown table, 10 / 8 / 11
+    assert [(rd, g.I_offset_ack, g.I_offset_cqi, g.I_offset_ri) for _, rd, g in nodef] == [(0, 10, 8, 11), (1, 10, 8, 11), (2, 10, 8, 11)]
