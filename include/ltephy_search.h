@@ -143,6 +143,21 @@ int ltephy_ul_dci_to_grant(const ltephy_search_t* s, const ltephy_dci_t* dci, in
  * batch and keep the first passing one in this order. */
 int ltephy_ul_decode_plan(const ltephy_search_t* s, const ltephy_dci_t* dci, int mcs_mod, ltephy_ul_grant_t* grants, uint8_t* reading);
 
+/* One MAC RAR of a Random Access Response PDU (decoded PDSCH of an RA-RNTI) with the msg-3 PUSCH grant it carries, as
+ * PDSCH_Decoder::unpack_rar_response_ul_mode builds it (src/src/DL_Sniffer_PDSCH.cc:632-665) */
+typedef struct {
+  uint16_t t_crnti;       /* temporary C-RNTI: activate it on the search (ltephy_search_activate, DL_Sniffer_PDSCH.cc:659) */
+  uint16_t ta;            /* 11-bit timing advance command */
+  uint8_t  rapid;         /* preamble index of the subheader */
+  uint8_t  hopping_flag, tpc, ul_delay, cqi_request; /* the other fields of the 20-bit grant (ul_sniffer_dci_rar_unpack, falcon_dci.c:648-657) */
+  uint8_t  valid;         /* 1: grant below is usable (the allocation fits, L_prb is a DFT size >= 3, the MCS has a size) */
+  ltephy_ul_grant_t grant; /* Table 8.6.1-1 reading; sf = 0: the PUSCH is on the air 6 subframes after the RAR (ULSchedule::get_rar_ul_tti,
+                              src/src/ULSchedule.cc:126-138) and is decoded with the 16QAM reading only (UL_Sniffer_PUSCH.cc:531-569 with an empty 256QAM grant) */
+} ltephy_rar_t;
+/* pdu[len] -> out[*n_out]; *backoff = the backoff indicator if the PDU carries one, else -1 (backoff may be NULL).
+ * LTEPHY_ERROR: malformed PDU; LTEPHY_ERROR_INVALID_INPUTS: null argument or more than max_out RARs. */
+int ltephy_rar_unpack(const ltephy_search_t* s, const uint8_t* pdu, uint32_t len, ltephy_rar_t* out, uint32_t max_out, uint32_t* n_out, int* backoff);
+
 /* What the reference keeps per RNTI for the uplink (MCSTracking::get_ue_config_rnti / find_tracking_info_RNTI_ul, used at UL_Sniffer_PUSCH.cc:433-452) */
 typedef struct {
   uint16_t rnti;      /* 0: the default entry, for every RNTI without its own */

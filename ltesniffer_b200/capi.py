@@ -60,6 +60,11 @@ class UlUeCfg(C.Structure):
                 ("cqi_len", C.c_uint16)]
 
 
+class Rar(C.Structure):
+    _fields_ = [("t_crnti", C.c_uint16), ("ta", C.c_uint16), ("rapid", C.c_uint8), ("hopping_flag", C.c_uint8), ("tpc", C.c_uint8), ("ul_delay", C.c_uint8),
+                ("cqi_request", C.c_uint8), ("valid", C.c_uint8), ("grant", UlGrant)]
+
+
 class Mib(C.Structure):
     _fields_ = [("found", C.c_uint8), ("nof_ports", C.c_uint8), ("sfn_offset", C.c_uint8), ("phich_length", C.c_uint8), ("phich_resources", C.c_uint8),
                 ("bch_payload", C.c_uint8 * 3), ("nof_prb", C.c_uint32), ("sfn", C.c_uint32)]
@@ -370,6 +375,7 @@ def _bind_search(L):
     L.ltephy_dci_to_grant.argtypes = [P, P, C.c_uint32, C.c_uint32, C.c_int, P, P]
     L.ltephy_ul_dci_to_grant.argtypes = [P, P, C.c_int, P]
     L.ltephy_ul_decode_plan.argtypes = [P, P, C.c_int, P, P]
+    L.ltephy_rar_unpack.argtypes = [P, P, C.c_uint32, P, C.c_uint32, P, P]
     L.ltephy_ul_grants_from_dcis.argtypes = [P, P, P, C.c_uint32, P, C.c_uint32, P, P, P, C.c_uint32, P]
     L.ltephy_decode_subframes.argtypes = [P, P, P, P, C.c_uint32, C.c_uint64, P, P, P, C.c_uint32, P, P, P, C.c_size_t]
     L.ltephy_decode_subframes_device.argtypes = [P, P, P, P, C.c_uint32, C.c_uint64, P, P, P, C.c_uint32, P, P, P, C.c_size_t]
@@ -478,6 +484,16 @@ def ul_decode_plan(search, dci_row, mcs_mod):
     if n < 0:
         raise ValueError("ltephy_ul_decode_plan: %d" % n)
     return [(int(rd[k]), UlGrant.from_buffer_copy(g[k])) for k in range(n)]
+
+
+def rar_unpack(search, pdu, max_out=16):
+    """MAC RAR PDU -> (return code, [Rar], backoff indicator or -1) via ltephy_rar_unpack"""
+    out = (Rar * max_out)()
+    n = C.c_uint32(0)
+    bo = C.c_int(-1)
+    buf = (C.c_uint8 * max(1, len(pdu))).from_buffer_copy(bytes(pdu) if len(pdu) else b"\0")
+    r = search.L.ltephy_rar_unpack(search.h, buf, len(pdu), out, max_out, C.byref(n), C.byref(bo))
+    return r, [Rar.from_buffer_copy(out[k]) for k in range(n.value)], bo.value
 
 
 def ul_grants_from_dcis(search, info, dcis, ue_cfgs=()):

@@ -809,25 +809,13 @@ int ltephy_dci_to_grant(const ltephy_search_t* s, const ltephy_dci_t* d, uint32_
   return LTEPHY_SUCCESS;
 }
 
-int ltephy_ul_dci_to_grant(const ltephy_search_t* s, const ltephy_dci_t* d, int enable_64qam, ltephy_ul_grant_t* g)
+// fields of a format-0 DCI or of a RAR grant -> PUSCH grant.  hop_kind: 0xFF none, 0 +1/4, 1 -1/4, 2 +1/2 (type 1), 3 type 2
+static int ul_fields_to_grant(const ltephy_search_t* s, uint32_t sf, uint16_t rnti, uint32_t hop_kind, uint32_t riv, uint32_t mcs, uint32_t cs, int enable_64qam,
+                              ltephy_ul_grant_t* g)
 {
   static const uint8_t dmrs2_map[8] = {0, 6, 3, 4, 2, 8, 10, 9}; // 36.211 Table 5.5.2.1.1-1
-  if (!s || !d || !g || d->format != ltehost::F0) return LTEPHY_ERROR_INVALID_INPUTS;
-  const uint32_t N = s->cell.nof_prb, rivb = clog2(N * (N + 1) / 2);
-  Bits           b{d->bits};
-  if (b.get(1) != 0) return LTEPHY_ERROR;            // format 0/1A flag
-  const uint32_t hop = b.get(1);                     // frequency hopping flag
-  uint32_t       riv = b.get(rivb), hop_kind = 0xFF;
-  const uint32_t mcs = b.get(5);
-  b.get(1);                                          // ndi
-  b.get(2);                                          // tpc
-  const uint32_t cs = b.get(3);
-  if (hop) { // the N_UL_hop most significant bits of the allocation select the hop (36.213 Tables 8.4-1 / 8.4-2): 0 +1/4, 1 -1/4, 2 +1/2, 3 type 2
-    const uint32_t nh = N < 50 ? 1 : 2, hb = riv >> (rivb - nh);
-    riv &= (1u << (rivb - nh)) - 1;
-    hop_kind = nh == 1 ? (hb == 0 ? 2 : 3) : hb;
-  }
-  uint32_t L, S;
+  const uint32_t       N = s->cell.nof_prb;
+  uint32_t             L, S;
   riv_decode(riv, N, L, S);
   if (L < 3 || L > N || S >= N || S + L > N) return LTEPHY_ERROR;
   uint32_t t = L;
@@ -872,8 +860,63 @@ int ltephy_ul_dci_to_grant(const ltephy_search_t* s, const ltephy_dci_t* d, int 
     g->tbs = lte_tbs_table[itbs][L - 1];
   }
   if (g->tbs <= 0) return LTEPHY_ERROR;
-  g->sf = d->sf, g->rnti = d->rnti, g->rv = 0, g->L_prb = L, g->n_prb = S, g->n_dmrs2 = dmrs2_map[cs & 7];
+  g->sf = sf, g->rnti = rnti, g->rv = 0, g->L_prb = L, g->n_prb = S, g->n_dmrs2 = dmrs2_map[cs & 7];
   g->n_prb_slot1 = S1, g->flags = LTEPHY_UL_FLAG_SLOT1;
+  return LTEPHY_SUCCESS;
+}
+int ltephy_ul_dci_to_grant(const ltephy_search_t* s, const ltephy_dci_t* d, int enable_64qam, ltephy_ul_grant_t* g)
+{
+  if (!s || !d || !g || d->format != ltehost::F0) return LTEPHY_ERROR_INVALID_INPUTS;
+  const uint32_t N = s->cell.nof_prb, rivb = clog2(N * (N + 1) / 2);
+  Bits           b{d->bits};
+  if (b.get(1) != 0) return LTEPHY_ERROR;            // format 0/1A flag
+  const uint32_t hop = b.get(1);                     // frequency hopping flag
+  uint32_t       riv = b.get(rivb), hop_kind = 0xFF;
+  const uint32_t mcs = b.get(5);
+  b.get(1);                                          // ndi
+  b.get(2);                                          // tpc
+  const uint32_t cs = b.get(3);
+  if (hop) { // the N_UL_hop most significant bits of the allocation select the hop (36.213 Tables 8.4-1 / 8.4-2): 0 +1/4, 1 -1/4, 2 +1/2, 3 type 2
+    const uint32_t nh = N < 50 ? 1 : 2, hb = riv >> (rivb - nh);
+    riv &= (1u << (rivb - nh)) - 1;
+    hop_kind = nh == 1 ? (hb == 0 ? 2 : 3) : hb;
+  }
+  return ul_fields_to_grant(s, d->sf, d->rnti, hop_kind, riv, mcs, cs, enable_64qam, g);
+}
+
+// MAC Random Access Response PDU (36.321 6.1.5 / 6.2.2 / 6.2.3; srsran::rar_pdu in the reference) -> one entry per MAC RAR with its msg-3 PUSCH grant, as
+// PDSCH_Decoder::unpack_rar_response_ul_mode builds it (reference src/src/DL_Sniffer_PDSCH.cc:632-665): the 20-bit grant is split by ul_sniffer_dci_rar_unpack,
+// turned into an uplink DCI by ul_sniffer_dci_rar_to_ul_dci (lib/src/phy/falcon_phch/falcon_dci.c:648-684: RIV = the 10 allocation bits as they are, MCS = the
+// truncated MCS, a set hopping flag read as hop value 1) and into a grant by ul_sniffer_ra_ul_dci_to_grant (Table 8.6.1-1).
+int ltephy_rar_unpack(const ltephy_search_t* s, const uint8_t* pdu, uint32_t len, ltephy_rar_t* out, uint32_t max_out, uint32_t* n_out, int* backoff)
+{
+  if (!s || !pdu || !out || !n_out) return LTEPHY_ERROR_INVALID_INPUTS;
+  *n_out = 0;
+  if (backoff) *backoff = -1;
+  uint8_t  rapid[64];
+  uint32_t nr = 0, pos = 0;
+  for (bool more = true; more;) { // subheaders: E | T | RAPID(6), or E | T=0 | R R | BI(4)
+    if (pos >= len) return LTEPHY_ERROR;
+    const uint8_t h = pdu[pos++];
+    more            = (h & 0x80) != 0;
+    if (h & 0x40) {
+      if (nr >= 64) return LTEPHY_ERROR;
+      rapid[nr++] = h & 0x3F;
+    } else if (backoff)
+      *backoff = h & 0x0F;
+  }
+  if (pos + 6 * (size_t)nr > len) return LTEPHY_ERROR;
+  for (uint32_t k = 0; k < nr; k++, pos += 6) {
+    if (*n_out >= max_out) return LTEPHY_ERROR_INVALID_INPUTS;
+    const uint8_t* r = pdu + pos; // R(1) TA(11) UL grant(20) T-CRNTI(16)
+    ltephy_rar_t&  o = out[(*n_out)++];
+    memset(&o, 0, sizeof(o));
+    o.rapid = rapid[k], o.ta = (uint16_t)(((r[0] & 0x7Fu) << 4) | (r[1] >> 4)), o.t_crnti = (uint16_t)((r[4] << 8) | r[5]);
+    const uint32_t gr = ((r[1] & 0x0Fu) << 16) | ((uint32_t)r[2] << 8) | r[3];
+    o.hopping_flag = (gr >> 19) & 1, o.tpc = (gr >> 2) & 7, o.ul_delay = (gr >> 1) & 1, o.cqi_request = gr & 1;
+    const uint32_t rba = (gr >> 9) & 0x3FF, mcs = (gr >> 5) & 0xF;
+    o.valid = ul_fields_to_grant(s, 0, o.t_crnti, o.hopping_flag ? 1u : 0xFFu, rba, mcs, 0, 1, &o.grant) == LTEPHY_SUCCESS;
+  }
   return LTEPHY_SUCCESS;
 }
 

@@ -351,4 +351,33 @@ int refgrant_ul(refwalk* w, uint16_t rnti, const uint8_t* bits, uint32_t nof_bit
   }
   return 0;
 }
+// One 20-bit RAR grant (one bit per byte, as srsran::rar_subh::get_sched_grant hands it over) through the reference's own conversion:
+// ul_sniffer_dci_rar_unpack + ul_sniffer_dci_rar_to_ul_dci (lib/src/phy/falcon_phch/falcon_dci.c:648-684) + ul_sniffer_ra_ul_dci_to_grant, as at
+// src/src/DL_Sniffer_PDSCH.cc:646-658.  out: grant_ret[0], ul_L_prb, ul_n_prb[2], ul_tbs[0], ul_qm[0], rv[0][0]
+int refgrant_rar(refwalk* w, const uint8_t* grant_bits, uint16_t t_crnti, uint32_t tti, uint32_t n_rb_ho, refwalk_dci_t* out)
+{
+  uint8_t bits[SRSRAN_RAR_GRANT_LEN];
+  memcpy(bits, grant_bits, SRSRAN_RAR_GRANT_LEN);
+  srsran_dci_rar_grant_t rar;
+  memset(&rar, 0, sizeof(rar));
+  ul_sniffer_dci_rar_unpack(bits, &rar);
+  srsran_dci_ul_t dci;
+  ul_sniffer_dci_rar_to_ul_dci(&w->cell, &rar, &dci);
+  dci.rnti = t_crnti, dci.format = SRSRAN_DCI_FORMAT_RAR;
+  srsran_ul_sf_cfg_t ul_sf;
+  memset(&ul_sf, 0, sizeof(ul_sf));
+  ul_sf.tti = tti;
+  srsran_pusch_hopping_cfg_t hop;
+  memset(&hop, 0, sizeof(hop));
+  hop.n_rb_ho = n_rb_ho;
+  srsran_pusch_grant_t g;
+  memset(&g, 0, sizeof(g));
+  memset(out, 0, sizeof(*out));
+  out->rnti = t_crnti;
+  out->grant_ret[0] = ul_sniffer_ra_ul_dci_to_grant(&w->cell, &ul_sf, &hop, &dci, &g);
+  if (out->grant_ret[0]) return 0;
+  out->ul_L_prb = g.L_prb, out->ul_n_prb[0] = g.n_prb[0], out->ul_n_prb[1] = g.n_prb[1], out->ul_tbs[0] = g.tb.tbs, out->ul_qm[0] = qm_of(g.tb.mod);
+  out->rv[0][0] = (uint8_t)g.tb.rv, out->ul_n_dmrs = dci.n_dmrs;
+  return 0;
+}
 }

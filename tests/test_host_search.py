@@ -1,6 +1,7 @@
 """Host search (product, table-driven) against the oracle walk (lazy decodes + the reference's own
 RNTIManager) on the same captures; search-space validation and DCI->grant against the oracle's versions."""
 import ctypes as C
+import os
 import numpy as np
 import pytest
 import ltelib
@@ -453,3 +454,40 @@ def test_ul_grants_from_dcis_follows_subframe_worker(infra):
     assert capi.ul_grants_from_dcis(srch, info, dcis[:3]) == [] and capi.ul_grants_from_dcis(srch, info, dcis[:0]) == []
     nodef = capi.ul_grants_from_dcis(srch, info, dcis[3:4])               # no UE table at all: unknown table, 10 / 8 / 11
     assert [(rd, g.I_offset_ack, g.I_offset_cqi, g.I_offset_ri) for _, rd, g in nodef] == [(0, 10, 8, 11), (1, 10, 8, 11), (2, 10, 8, 11)]
+
+
+def test_rar_unpack_known_answers_from_the_references_captures(infra):
+    """ltephy_rar_unpack on the two Random Access Responses in the reference's own example captures (pcap_file_example/ltesniffer_dl_mode.pcap, record of
+    RA-RNTI 2 at tti 5636; ltesniffer_ul_mode.pcap, tti 8516), quoted here.  In the UL-mode capture the msg 3 the grant schedules is there too: an uplink
+    record of RNTI 70 exactly 6 subframes later (ULSchedule::get_rar_ul_tti) with 7 bytes = the 56-bit transport block of MCS 0 on 3 PRB -- what the grant
+    decodes to.  Where /root/reference is mounted the records are read from the files themselves."""
+    srch = capi.Search(100, 2, 1, 2)
+    for hexpdu, rapid in (("620011940c004600000000", 34), ("720011940c004600000000", 50)):
+        r, rars, bo = capi.rar_unpack(srch, bytes.fromhex(hexpdu))
+        assert r == 0 and bo == -1 and len(rars) == 1
+        x = rars[0]
+        assert (x.rapid, x.ta, x.t_crnti, x.hopping_flag, x.tpc, x.ul_delay, x.cqi_request, x.valid) == (rapid, 1, 70, 0, 3, 0, 0, 1)
+        g = x.grant
+        assert (g.rnti, g.L_prb, g.n_prb, g.n_prb_slot1, g.tbs, g.qm, g.rv, g.n_dmrs2, g.sf) == (70, 3, 2, 2, 56, 2, 0, 0, 0)
+    path = "/root/reference/pcap_file_example/ltesniffer_ul_mode.pcap"
+    if os.path.exists(path):
+        import test_sinks
+        _, recs = test_sinks.parse(path)
+        rar = [x for x in recs if x["rnti_type"] == 2]
+        assert len(rar) == 1 and rar[0]["pdu"].hex() == "720011940c004600000000"
+        r, rars, _ = capi.rar_unpack(srch, rar[0]["pdu"])
+        msg3 = [x for x in recs if x["direction"] == 0 and x["rnti"] == rars[0].t_crnti and x["tti"] == (rar[0]["tti"] + 6) % 10240]
+        assert len(msg3) == 1 and len(msg3[0]["pdu"]) * 8 == rars[0].grant.tbs
+    # a backoff-indicator subheader, then two RARs; the second grant hops and asks for CSI
+    g2 = (1 << 19) | (((100 * 5 + 30) & 0x3FF) << 9) | (7 << 5) | (5 << 2) | (1 << 1) | 1
+    pdu = bytes([0x80 | 0x09, 0xC0 | 3, 0x40 | 61]) + bytes([0x12, 0x31, 0x94, 0x0C, 0xAB, 0xCD]) + bytes([0x7F, 0xF0 | (g2 >> 16), (g2 >> 8) & 255, g2 & 255, 0x00, 0x63]) + b"\0\0"
+    r, rars, bo = capi.rar_unpack(srch, pdu)
+    assert r == 0 and bo == 9 and [(x.rapid, x.t_crnti, x.ta) for x in rars] == [(3, 0xABCD, 0x123), (61, 0x63, 0x7FF)]
+    assert (rars[1].hopping_flag, rars[1].tpc, rars[1].ul_delay, rars[1].cqi_request) == (1, 5, 1, 1)
+    riv = (100 * 5 + 30) & 0x3FF                                        # the 10 allocation bits as they are (falcon_dci.c:672-680)
+    L, S = riv // 100 + 1, riv % 100
+    assert rars[1].valid == 1 and (rars[1].grant.L_prb, rars[1].grant.n_prb, rars[1].grant.qm) == (L, S, 2)
+    assert rars[1].grant.n_prb_slot1 == (S - 25 if S >= 25 else 100 + S - 25)          # hopping flag read as hop value 1: -1/4 of the band (n_rb_ho = 0)
+    # malformed: no subheader end, RAR body cut short; more RARs than the caller has room for
+    assert capi.rar_unpack(srch, bytes([0xC1]))[0] == -1 and capi.rar_unpack(srch, bytes([0x41, 0, 0, 0]))[0] == -1 and capi.rar_unpack(srch, b"")[0] == -1
+    assert capi.rar_unpack(srch, pdu, max_out=1)[0] == -2

@@ -438,3 +438,47 @@ def test_random_format0_grants_equal_reference(infra, cellp, n_rb_ho):
                 nhop += r.ul_n_prb[0] != r.ul_n_prb[1]
     assert nok > 300 and nhop > 20, (nok, nhop)
     ref.close()
+
+
+@needs_ref
+@pytest.mark.parametrize("cellp,n_rb_ho", [((100, 2, 7, 2), 0), ((100, 2, 7, 2), 6), ((50, 2, 301, 2), 0), ((25, 1, 5, 1), 2)])
+def test_random_rar_grants_equal_reference(infra, cellp, n_rb_ho):
+    """4 000 random 20-bit RAR grants per cell (inside random MAC RAR PDUs of 1-3 RARs): ltephy_rar_unpack against the reference's own
+    ul_sniffer_dci_rar_unpack + ul_sniffer_dci_rar_to_ul_dci + ul_sniffer_ra_ul_dci_to_grant (falcon_dci.c:648-684, ul_sniffer_pusch.c:205-245, called at
+    DL_Sniffer_PDSCH.cc:646-658) -- L_prb, both slots' first PRB (a set hopping flag is read as hop value 1), TBS, Qm.  valid = 0 exactly where the
+    reference's conversion fails or yields what PUSCH_Decoder cannot decode (L_prb no DFT size or < 3)."""
+    cell = Cell(*cellp)
+    R = reflib()
+    R.refgrant_rar.argtypes = [C.c_void_p, C.c_void_p, C.c_uint16, C.c_uint32, C.c_uint32, C.POINTER(RefDci)]
+    ref = RefWalk(cell)
+    srch = capi.Search(cell.nof_prb, cell.nof_ports, cell.cell_id, cell.nof_rx)
+    srch.L.ltephy_search_set_ul_hopping(srch.h, n_rb_ho)
+    rng = np.random.default_rng(cell.nof_prb + n_rb_ho)
+    nvalid = nhop = 0
+    for it in range(1600):
+        k = int(rng.integers(1, 4))
+        grants = [int(rng.integers(0, 1 << 20)) for _ in range(k)]
+        if it % 3 == 0:                                   # small allocations and MCS are what msg 3 really uses
+            grants = [(g & ~(0x3FF << 9)) | (int(rng.integers(0, 6 * cell.nof_prb)) & 0x3FF) << 9 for g in grants]
+        rntis = [int(rng.integers(1, 0xFFF0)) for _ in range(k)]
+        tas = [int(rng.integers(0, 2048)) for _ in range(k)]
+        pdu = bytes([(0x80 if j < k - 1 else 0) | 0x40 | int(rng.integers(0, 64)) for j in range(k)])
+        for g, rn, ta in zip(grants, rntis, tas):
+            pdu += bytes([ta >> 4, ((ta & 15) << 4) | (g >> 16), (g >> 8) & 255, g & 255, rn >> 8, rn & 255])
+        rc, rars, _ = capi.rar_unpack(srch, pdu + bytes(int(rng.integers(0, 3))))
+        assert rc == 0 and [(x.t_crnti, x.ta) for x in rars] == list(zip(rntis, tas))
+        for x, g, rn in zip(rars, grants, rntis):
+            bits = np.array([(g >> (19 - i)) & 1 for i in range(20)], np.uint8)
+            r = RefDci()
+            R.refgrant_rar(ref.h, bits.ctypes.data_as(C.c_void_p), rn, 100, n_rb_ho, C.byref(r))
+            L = r.ul_L_prb
+            expect = r.grant_ret[0] == 0 and L >= 3 and _dft_size(L) and r.ul_tbs[0] > 0
+            assert bool(x.valid) == expect, (hex(g), r.grant_ret[0], L, r.ul_tbs[0])
+            assert (x.hopping_flag, x.tpc, x.ul_delay, x.cqi_request) == (g >> 19, (g >> 2) & 7, (g >> 1) & 1, g & 1)
+            if x.valid:
+                assert (x.grant.rnti, x.grant.L_prb, x.grant.n_prb, x.grant.n_prb_slot1, x.grant.tbs, x.grant.qm, x.grant.rv, x.grant.n_dmrs2) == \
+                    (rn, L, r.ul_n_prb[0], r.ul_n_prb[1], r.ul_tbs[0], r.ul_qm[0], r.rv[0][0], 0), hex(g)
+                nvalid += 1
+                nhop += r.ul_n_prb[0] != r.ul_n_prb[1]
+    assert nvalid > 200 and nhop > 20, (nvalid, nhop)
+    ref.close()
