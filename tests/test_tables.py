@@ -41,3 +41,20 @@ def test_anchors_in_reference_tree():
     hdr = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include", "lte_tables.h")).read()
     m = re.search(r"lte_tbs_row_32a\[LTE_TBS_NOF_PRB\]\s*=\s*\{(.*?)\};", hdr, re.S)
     assert [int(x) for x in re.findall(r"\d+", m.group(1))] == row32a.tolist()      # our copy of the row == the reference's
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="reference tree not mounted (GPU box)")
+def test_transport_block_sizes_of_the_references_captures_are_in_the_table():
+    """Real-network anchor for the TBS table (36.213 Table 7.1.7.2.1-1, restated from the specification because srsRAN is absent): every MAC PDU in the
+    reference's example captures (pcap_file_example/*.pcap, written from live cells by the reference) is a decoded transport block, so its size must be an
+    entry of the table -- 86 distinct sizes, down- and uplink.  A random byte size hits the table with probability < 1/3 in that range."""
+    import test_sinks
+    _, _, tbs, f1c = check_tables.load()
+    allT = set(np.array(tbs).ravel().tolist())
+    sizes = set()
+    for path in test_sinks.FILES:
+        _, recs = test_sinks.parse(path)
+        sizes |= {len(r["pdu"]) * 8 for r in recs}
+    assert len(sizes) >= 80 and sizes <= allT, sorted(sizes - allT)
+    lim = max(sizes)
+    assert sum(1 for v in range(16, lim + 1, 8) if v in allT) * 3 < (lim - 8) // 8
