@@ -158,12 +158,18 @@ typedef struct {
  * LTEPHY_ERROR: malformed PDU; LTEPHY_ERROR_INVALID_INPUTS: null argument or more than max_out RARs. */
 int ltephy_rar_unpack(const ltephy_search_t* s, const uint8_t* pdu, uint32_t len, ltephy_rar_t* out, uint32_t max_out, uint32_t* n_out, int* backoff);
 
+/* Bits of the aperiodic CQI report as the reference configures it (UL_Sniffer_PUSCH.cc:434-445; no PMI, rank 1): cqi_type = srsran_cqi_type_t,
+ * 0 wideband -> 4, 3 subbands configured by higher layers (the default, MCSTracking.cc:1538) -> 4 + 2 N with N = ul_sniffer_cqi_hl_get_no_subbands
+ * (lib/src/phy/falcon_phch/dl_sniffer_pdsch.c:277-302).  Other types / nof_prb < 7: LTEPHY_ERROR_INVALID_INPUTS. */
+int ltephy_ul_cqi_len(uint32_t nof_prb, int cqi_type);
+
 /* What the reference keeps per RNTI for the uplink (MCSTracking::get_ue_config_rnti / find_tracking_info_RNTI_ul, used at UL_Sniffer_PUSCH.cc:433-452) */
 typedef struct {
   uint16_t rnti;      /* 0: the default entry, for every RNTI without its own */
   uint8_t  mcs_mod;   /* LTEPHY_UL_MOD_* */
   uint8_t  I_offset_ack, I_offset_cqi, I_offset_ri; /* ue_config.uci_config; SubframeWorker::setup_default_ul_cfg: 10 / 8 / 11 */
-  uint16_t cqi_len;   /* srsran_cqi_size of the aperiodic report this UE sends when a DCI-0 requests one (0: no CQI region assumed) */
+  uint16_t cqi_len;   /* srsran_cqi_size of the aperiodic report this UE sends when a DCI-0 requests one; 0: the reference's default report type,
+                         ltephy_ul_cqi_len(nof_prb, 3) */
 } ltephy_ul_ue_cfg_t;
 /* UL mode, whole batch: the accepted DCIs of a batch of downlink subframes -> the PUSCH decode attempts to submit 4 subframes later
  * (SubframeWorker.cc:296-345: nof_ack from the downlink DCIs of the same RNTI and subframe; ULSchedule's n + 4; UL_Sniffer_PUSCH.cc:417-570: validity

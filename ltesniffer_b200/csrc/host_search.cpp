@@ -1277,6 +1277,18 @@ int ltephy_grants_from_dcis_tc(const ltephy_search_t* s, const uint32_t* tti_cfi
                                grants, grant_dci, max_grants, n_grants);
 }
 
+// Size of the aperiodic CQI report multiplexed into a PUSCH whose DCI-0 requests one, for the report types the reference configures
+// (UL_Sniffer_PUSCH.cc:434-445: uci_cfg.cqi.type from the UE's RRC configuration, default SRSRAN_CQI_TYPE_SUBBAND_HL, MCSTracking.cc:1538; N =
+// ul_sniffer_cqi_hl_get_no_subbands, lib/src/phy/falcon_phch/dl_sniffer_pdsch.c:277-302; no PMI, rank 1): 36.212 Tables 5.2.2.6.1-1 (wideband, 4 bits)
+// and 5.2.2.6.2-1 (higher-layer configured subbands, 4 + 2 N bits).  cqi_type: srsran_cqi_type_t (0 wideband, 3 subband HL).
+int ltephy_ul_cqi_len(uint32_t nof_prb, int cqi_type)
+{
+  if (cqi_type == 0) return 4;
+  if (cqi_type != 3 || nof_prb < 7 || nof_prb > 110) return LTEPHY_ERROR_INVALID_INPUTS;
+  const uint32_t k = nof_prb <= 26 ? 4 : nof_prb <= 63 ? 6 : 8;
+  return (int)(4 + 2 * ((nof_prb + k - 1) / k));
+}
+
 // UL mode, one batch: what SubframeWorker does per subframe between the search and PUSCH_Decoder::decode (reference src/src/SubframeWorker.cc:296-345)
 // and the attempts that decoder then makes (ltephy_ul_decode_plan), for all DCI-0s of a batch of downlink subframes at once.
 //   * the PUSCH of a DCI-0 seen at tti n is on the air at n + 4 (ULSchedule::pushULSche / get_ul_tti, src/src/ULSchedule.cc:112-124): grant.sf = dci.sf + 4,
@@ -1284,7 +1296,8 @@ int ltephy_grants_from_dcis_tc(const ltephy_search_t* s, const uint32_t* tti_cfi
 //   * nof_ack = number of transport blocks of a downlink DCI of the same RNTI in the same subframe, the last such DCI winning (SubframeWorker.cc:318-337);
 //   * an aperiodic CSI request (last payload bit, FDD) adds ri_len = 1 and the UE's CQI size (UL_Sniffer_PUSCH.cc:437-450);
 //   * beta offsets and the MCS-table knowledge come per RNTI from ue[] (MCSTracking::get_ue_config_rnti / find_tracking_info_RNTI_ul), entry rnti = 0
-//     being the default; without any: unknown table, 10 / 8 / 11 (SubframeWorker::setup_default_ul_cfg, SubframeWorker.cc:347-352), no CQI size.
+//     being the default; without any: unknown table, 10 / 8 / 11 (SubframeWorker::setup_default_ul_cfg, SubframeWorker.cc:347-352); cqi_len 0 = the
+//     reference's default report (subband CQI configured by higher layers, ltephy_ul_cqi_len).
 int ltephy_ul_grants_from_dcis(const ltephy_search_t* s, const ltephy_sf_info_t* info, const ltephy_dci_t* dcis, uint32_t nd, const ltephy_ul_ue_cfg_t* ue,
                                uint32_t n_ue, ltephy_ul_grant_t* grants, uint32_t* grant_dci, uint8_t* reading, uint32_t max_grants, uint32_t* n_grants)
 {
@@ -1317,9 +1330,11 @@ int ltephy_ul_grants_from_dcis(const ltephy_search_t* s, const ltephy_sf_info_t*
     Bits b{d.bits};
     b.get(2), b.get(rivb), b.get(5 + 1 + 2 + 3);
     const bool cqi_request = b.get(1) != 0;
+    const int  dflt        = ltephy_ul_cqi_len(N, 3); // the reference's default report type (MCSTracking::set_default_of_default_config)
+    const uint16_t cqi_len = cfg.cqi_len ? cfg.cqi_len : (uint16_t)(dflt > 0 ? dflt : 0);
     for (int k = 0; k < n; k++) {
       if (ng >= max_grants) return LTEPHY_ERROR_INVALID_INPUTS;
-      g[k].sf = d.sf + 4, g[k].nof_ack = nof_ack, g[k].ri_len = cqi_request ? 1 : 0, g[k].cqi_len = cqi_request ? cfg.cqi_len : 0;
+      g[k].sf = d.sf + 4, g[k].nof_ack = nof_ack, g[k].ri_len = cqi_request ? 1 : 0, g[k].cqi_len = cqi_request ? cqi_len : 0;
       g[k].I_offset_ack = cfg.I_offset_ack, g[k].I_offset_cqi = cfg.I_offset_cqi, g[k].I_offset_ri = cfg.I_offset_ri;
       grants[ng] = g[k], grant_dci[ng] = i, reading[ng] = rd[k];
       ng++;

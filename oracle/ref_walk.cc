@@ -380,4 +380,5 @@ int refgrant_rar(refwalk* w, const uint8_t* grant_bits, uint16_t t_crnti, uint32
   out->rv[0][0] = (uint8_t)g.tb.rv, out->ul_n_dmrs = dci.n_dmrs;
   return 0;
 }
+int refcqi_no_subbands(int nof_prb) { return ul_sniffer_cqi_hl_get_no_subbands(nof_prb); }
 }

@@ -491,3 +491,23 @@ def test_rar_unpack_known_answers_from_the_references_captures(infra):
     # malformed: no subheader end, RAR body cut short; more RARs than the caller has room for
     assert capi.rar_unpack(srch, bytes([0xC1]))[0] == -1 and capi.rar_unpack(srch, bytes([0x41, 0, 0, 0]))[0] == -1 and capi.rar_unpack(srch, b"")[0] == -1
     assert capi.rar_unpack(srch, pdu, max_out=1)[0] == -2
+
+
+def test_ul_default_cqi_report_size(infra):
+    """without a UE entry a CSI request is sized as the reference's default report (subband CQI configured by higher layers, 4 + 2 N bits)"""
+    L = capi.load_library()
+    capi._bind_search(L)
+    assert [L.ltephy_ul_cqi_len(n, 3) for n in (15, 25, 50, 75, 100)] == [12, 18, 22, 24, 30] and L.ltephy_ul_cqi_len(50, 0) == 4
+    assert L.ltephy_ul_cqi_len(6, 3) == -2 and L.ltephy_ul_cqi_len(50, 1) == -2
+    srch = capi.Search(50, 2, 3, 2)
+    N, rivb = 50, 11
+    v, pos = 0, 0
+    for val, w in [(0, 1), (0, 1), (N * 5 + 2, rivb), (15, 5), (1, 1), (0, 2), (3, 3), (1, 1)]:
+        v |= val << (64 - pos - w)
+        pos += w
+    dcis = np.zeros(1, capi.DCI_DTYPE)
+    dcis[0]["rnti"], dcis[0]["format"], dcis[0]["nof_bits"], dcis[0]["bits"] = 0x2222, 0, 27, v
+    info = (capi.SfInfo * 1)()
+    info[0].tti, info[0].cfi = 20, 2
+    out = capi.ul_grants_from_dcis(srch, info, dcis)
+    assert [(rd, g.ri_len, g.cqi_len) for _, rd, g in out] == [(0, 1, 22), (2, 1, 22)]

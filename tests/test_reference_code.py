@@ -482,3 +482,13 @@ def test_random_rar_grants_equal_reference(infra, cellp, n_rb_ho):
                 nhop += r.ul_n_prb[0] != r.ul_n_prb[1]
     assert nvalid > 200 and nhop > 20, (nvalid, nhop)
     ref.close()
+
+
+@needs_ref
+def test_cqi_subband_count_equals_reference(infra):
+    """ltephy_ul_cqi_len's subband count == the reference's ul_sniffer_cqi_hl_get_no_subbands (lib/src/phy/falcon_phch/dl_sniffer_pdsch.c:277-302), 7..110 PRB"""
+    R = reflib()
+    L = capi.load_library()
+    capi._bind_search(L)
+    for n in range(7, 111):
+        assert L.ltephy_ul_cqi_len(n, 3) == 4 + 2 * R.refcqi_no_subbands(n), n
