@@ -63,6 +63,13 @@ void ltephy_search_config(ltephy_search_t* s, int shortcut, int skip_secondary, 
  * they differ, and ltephy_decode_subframes reports the first reading unless only the second passes a CRC (then crc = 2): the
  * batched form of "try the 64QAM table, then the 256QAM table" (src/src/DL_Sniffer_PDSCH.cc:1089-1210).  Off by default. */
 void ltephy_search_speculate_256qam(ltephy_search_t* s, int on);
+/* UL mode (-m 1): the downlink side only decodes what the uplink side needs.  ltephy_grants_from_dcis then selects as PDSCH_Decoder::decode_ul_mode does
+ * (src/src/DL_Sniffer_PDSCH.cc:362-457) instead of decode_dl_mode: every RA-RNTI DCI (the Random Access Responses -> ltephy_rar_unpack), and the
+ * format 1 / 1A DCIs of any RNTI but the SI-RNTI (target_rnti as ULSchedule::get_rnti, 0 = none), read with the 64QAM table only. */
+void ltephy_search_set_ul_mode(ltephy_search_t* s, int on, uint16_t target_rnti);
+/* rv of a format-1C SI-RNTI transmission at tti as PDSCH_Decoder::decode_SIB computes it (DL_Sniffer_PDSCH.cc:505-511: k = (SFN / 2) % 4, ceil(1.5 k) % 4);
+ * ltephy_dci_to_grant itself writes 0 for format 1C as decode_dl_mode does (:891-898).  For a caller acquiring SIBs: grant.tb[0].rv = this. */
+uint32_t ltephy_si_format1c_rv(uint32_t tti);
 /* HARQ mode (-h): ltephy_grants_from_dcis keeps the C-RNTI grants whose first block has a reserved MCS (29-31; 28-31 of the 256QAM table; tbs = 0)
  * instead of applying decode_dl_mode's "tbs > 0" rule to them; ltephy_harq_prepare_grant then gives the block the size of its process' last
  * transmission as DCICollection::addCandidate does before that rule (src/src/DCICollection.cc:236-252).  Off by default. */

@@ -350,6 +350,7 @@ def _bind_search(L):
     L.ltephy_search_config.argtypes = [P, C.c_int, C.c_int, C.c_uint32]
     L.ltephy_search_speculate_256qam.argtypes = [P, C.c_int]
     L.ltephy_search_keep_reserved_mcs.argtypes = [P, C.c_int]
+    L.ltephy_search_set_ul_mode.argtypes = [P, C.c_int, C.c_uint16]
     L.ltephy_search_set_ul_hopping.argtypes = [P, C.c_uint32]
     L.ltephy_shard_set_gather_capacity.argtypes = [P, C.c_uint32]
     L.ltephy_search_add_evergreen.argtypes = [P, C.c_uint16, C.c_uint16, C.c_uint32]

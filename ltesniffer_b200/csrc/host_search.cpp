@@ -256,6 +256,8 @@ struct ltephy_search {
   uint32_t           n_primary = 0, n_secondary = 0;
   double             split_ratio     = 0.99;
   bool               skip_secondary  = false, shortcut = true;
+  bool               ul_mode = false;           // ltephy_grants_from_dcis selects as PDSCH_Decoder::decode_ul_mode does instead of decode_dl_mode
+  uint16_t           ul_target_rnti = 0;
   bool               keep_reserved_mcs = false; // HARQ mode: a C-RNTI grant whose first block has a reserved MCS is kept, ltephy_harq_prepare_grant sizes it
   bool               speculate_256qam = false; // grants_from_dcis emits both MCS-table readings of a C-RNTI DCI (DL_Sniffer_PDSCH.cc:1089-1210)
   uint32_t           update_interval = 500, sf_cnt = 0;
@@ -1056,6 +1058,18 @@ void ltephy_search_set_ul_hopping(ltephy_search_t* s, uint32_t n_rb_ho)
 {
   if (s) s->ul_n_rb_ho = n_rb_ho;
 }
+// Redundancy version of a format-1C SI-RNTI transmission, which carries no rv field (srsRAN leaves tb.rv = -1): PDSCH_Decoder::decode_SIB (the SIB
+// acquisition of the UL mode, DL_Sniffer_PDSCH.cc:505-511) uses k = (SFN / 2) % 4, rv = ceil(1.5 k) % 4 (36.321 5.3.1), while decode_dl_mode uses 0
+// (:891-898), which is what ltephy_dci_to_grant writes.
+uint32_t ltephy_si_format1c_rv(uint32_t tti)
+{
+  static const uint8_t rv_of_k[4] = {0, 2, 3, 1};
+  return rv_of_k[((tti / 10) / 2) % 4];
+}
+void ltephy_search_set_ul_mode(ltephy_search_t* s, int on, uint16_t target_rnti)
+{
+  if (s) s->ul_mode = on != 0, s->ul_target_rnti = target_rnti;
+}
 void ltephy_search_keep_reserved_mcs(ltephy_search_t* s, int on)
 {
   if (s) s->keep_reserved_mcs = on != 0;
@@ -1241,7 +1255,12 @@ static int grants_from_dcis_impl(const ltephy_search_t* s, TtiCfi tc, const ltep
     uint32_t tti_sf, cfi_sf;
     tc(d.sf, tti_sf, cfi_sf);
     ok[0] = ltephy_dci_to_grant(s, &d, tti_sf % 10, cfi_sf, 0, &g[0], nullptr) == LTEPHY_SUCCESS && eligible(g[0]);
-    if (s->speculate_256qam && user_rnti(d.rnti)) { // MCS table of the UE unknown: 64QAM reading first, then the 256QAM one
+    if (s->ul_mode) { // PDSCH_Decoder::decode_ul_mode (DL_Sniffer_PDSCH.cc:362-457): Random Access Responses, and format 1 / 1A of everything but the SI-RNTI,
+                      // with the 64QAM table only
+      const bool rar = d.rnti >= RARNTI_START && d.rnti <= RARNTI_END;
+      const bool sel = d.rnti == s->ul_target_rnti || s->ul_target_rnti == 0 || d.rnti > RARNTI_END;
+      if (!rar && !(sel && (d.format == ltehost::F1 || d.format == ltehost::F1A) && d.rnti != 0xFFFF)) ok[0] = false;
+    } else if (s->speculate_256qam && user_rnti(d.rnti)) { // MCS table of the UE unknown: 64QAM reading first, then the 256QAM one
       ok[1] = ltephy_dci_to_grant(s, &d, tti_sf % 10, cfi_sf, 1, &g[1], nullptr) == LTEPHY_SUCCESS && eligible(g[1]);
       if (ok[0] && ok[1]) {
         bool same = g[0].nof_tb == g[1].nof_tb;

@@ -302,6 +302,16 @@ def test_grants_from_dcis_speculation_and_sharding_filters(infra):
             assert 0x000A < rows[di][1] < 0xFFF4                  # user RNTIs only
             assert spec[k - 1][0] == di and spec[k - 1][1] == 0  # adjacent to its primary, after it
             assert (x[4], x[5]) != (spec[k - 1][4], spec[k - 1][5])
+    # UL mode (PDSCH_Decoder::decode_ul_mode, DL_Sniffer_PDSCH.cc:362-457): the RA-RNTI DCIs and format 1 / 1A of everything but the SI-RNTI, 64QAM table only
+    L.ltephy_search_set_ul_mode(srch.h, 1, 0)
+    ulm = run(1, 0)
+    assert all(a == 0 for _, a, *_ in ulm)
+    assert sorted(di for di, *_ in ulm) == sorted(di for di, *_ in plain if rows[di][1] != 0xFFFF and rows[di][2] in (1, 2))
+    assert {rows[di][1] for di, *_ in ulm} >= {0x0004} and 0xFFFF not in {rows[di][1] for di, *_ in ulm}
+    L.ltephy_search_set_ul_mode(srch.h, 0, 0)
+    assert run(1, 0) == spec
+    L.ltephy_si_format1c_rv.argtypes = [C.c_uint32]
+    assert [L.ltephy_si_format1c_rv(10 * sfn + 5) for sfn in range(10)] == [int(np.ceil(1.5 * ((sfn // 2) % 4))) % 4 for sfn in range(10)] == [0, 0, 2, 2, 3, 3, 1, 1, 0, 0]
 
 
 def test_empty_and_degenerate_inputs(infra):
