@@ -492,3 +492,79 @@ def test_cqi_subband_count_equals_reference(infra):
     capi._bind_search(L)
     for n in range(7, 111):
         assert L.ltephy_ul_cqi_len(n, 3) == 4 + 2 * R.refcqi_no_subbands(n), n
+
+
+@needs_ref
+@pytest.mark.parametrize("cellp", [(100, 2, 7, 2), (50, 2, 301, 2), (25, 1, 5, 1), (15, 2, 9, 2)])
+def test_edge_case_dcis_grants_equal_reference(infra, cellp):
+    """Structured companion of the random-payload test: random payloads are unpacked, their fields pushed to the edges (MCS 0 / 9 / 10 / 27 / 28 / 29 / 31,
+    disabled blocks in every combination, every precoding value, empty / full / single-RBG bitmaps, RIVs at 0, at the last valid value, one past it and all
+    ones, both gaps, the N_PRB^1A bit) and packed again; product and the reference's conversion must agree on every one of them, refusals included."""
+    cell = Cell(*cellp)
+    R = reflib()
+    R.refgrant_dl.argtypes = [C.c_void_p, C.c_uint32, C.c_uint16, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(RefDci)]
+    ref = RefWalk(cell)
+    srch = capi.Search(cell.nof_prb, cell.nof_ports, cell.cell_id, cell.nof_rx)
+    S = infra.sim()
+    S.lte_dci_unpack.argtypes = [C.c_void_p, C.c_int, C.c_uint16, C.c_void_p, C.c_uint32, C.c_void_p]
+    S.lte_dci_pack.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    rng = np.random.default_rng(1000 + cell.nof_prb)
+    N = cell.nof_prb
+    P = 1 if N <= 10 else 2 if N <= 26 else 3 if N <= 63 else 4
+    nrbg = (N + P - 1) // P
+    seen = {"ok": 0, "ref_fail": 0, "two_off": 0, "mimo_err": 0}
+    for it in range(3000):
+        f = int(rng.choice([1, 2, 4, 6, 7]))
+        nb = S.lte_dci_sizeof(C.byref(cell), f)
+        bits = rng.integers(0, 2, nb).astype(np.uint8)
+        if f == 2:
+            bits[0] = 1
+        rnti = int(rng.choice([int(rng.integers(11, 0xFFF3)), 0xFFFF, 0xFFFE, int(rng.integers(1, 11))], p=[0.7, 0.1, 0.1, 0.1]))
+        d = ltelib.Dci()
+        if S.lte_dci_unpack(C.byref(cell), f, rnti, bits.ctypes.data_as(C.c_void_p), nb, C.byref(d)) != 0:
+            continue
+        for t in range(2):
+            if rng.random() < 0.5:
+                d.mcs[t] = int(rng.choice([0, 9, 10, 16, 17, 27, 28, 29, 31]))
+            if rng.random() < 0.3:
+                d.rv[t] = int(rng.choice([0, 1]))
+            d.tb_en[t] = 0 if (rng.random() < 0.25 and f >= 6) else 1
+        if rng.random() < 0.5:
+            d.pinfo = int(rng.integers(0, 8))
+        if rng.random() < 0.4:
+            if d.alloc_type == 0:
+                d.rbg_bitmask = int(rng.choice([0, (1 << nrbg) - 1, 1, 1 << (nrbg - 1), 1 << int(rng.integers(0, nrbg))]))
+            elif d.alloc_type == 1:
+                d.t1_vrb_bitmask = int(rng.choice([0, 1, 0xFFFFFFFF & ((1 << 20) - 1)]))
+            else:
+                lim = N * (N + 1) // 2
+                d.riv = int(rng.choice([0, N - 1, lim - 1, lim, (1 << 13) - 1, int(rng.integers(0, lim))]))
+                d.t2_ngap2 = int(rng.integers(0, 2))
+                d.n_prb1a = int(rng.choice([2, 3]))
+        out = np.zeros(64, np.uint8)
+        nbo = C.c_uint32(0)
+        if S.lte_dci_pack(C.byref(cell), C.byref(d), out.ctypes.data_as(C.c_void_p), C.byref(nbo)) != 0:
+            continue
+        assert nbo.value == nb
+        bits = out[:nb].copy()
+        tti, cfi = int(rng.integers(0, 10240)), int(rng.integers(1, 4))
+        r = RefDci()
+        ru = R.refgrant_dl(ref.h, f, rnti, bits.ctypes.data_as(C.c_void_p), nb, tti, cfi, C.byref(r))
+        v = 0
+        for i, b in enumerate(bits):
+            v |= int(b) << (63 - i)
+        row = np.zeros(1, capi.DCI_DTYPE)
+        row["rnti"], row["format"], row["nof_bits"], row["bits"], row["L"] = rnti, f, nb, v, 2
+        info = capi.SfInfo()
+        info.tti, info.cfi = tti, cfi
+        if ru != 0:
+            for table in (0, 1):
+                assert srch.dci_to_grant(row[0], tti % 10, cfi, table)[0] != 0
+            seen["ref_fail"] += 1
+            continue
+        compare_grants(srch, cell, info, row[0], r)
+        seen["ok"] += r.grant_ret[0] == 0
+        seen["mimo_err"] += r.grant_ret[0] in (-1, -2, -3) and f >= 6
+        seen["two_off"] += f >= 6 and d.tb_en[0] == 0 and d.tb_en[1] == 0
+    assert seen["ok"] > 800 and seen["two_off"] > 20 and seen["mimo_err"] > 50, seen
+    ref.close()
