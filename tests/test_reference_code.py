@@ -568,3 +568,63 @@ def test_edge_case_dcis_grants_equal_reference(infra, cellp):
         seen["two_off"] += f >= 6 and d.tb_en[0] == 0 and d.tb_en[1] == 0
     assert seen["ok"] > 800 and seen["two_off"] > 20 and seen["mimo_err"] > 50, seen
     ref.close()
+
+
+@needs_ref
+@pytest.mark.parametrize("cellp,seed,shortcut,skip2,thr", [((100, 2, 7, 2), 1, 1, 0, 5), ((50, 1, 3, 1), 2, 1, 0, 5), ((25, 2, 11, 2), 3, 1, 0, 5), ((75, 2, 200, 1), 4, 1, 0, 5),
+                                                           ((50, 2, 3, 2), 5, 0, 0, 5), ((50, 2, 3, 2), 6, 1, 1, 5), ((100, 2, 7, 2), 7, 1, 0, 2), ((25, 1, 4, 1), 8, 0, 1, 9)])
+def test_product_walk_equals_reference_code_on_adversarial_tables(infra, cellp, seed, shortcut, skip2, thr):
+    """The walk against the reference's own DCISearch.cc on candidate tables no transmitter produces (the generator of tests/test_survivor_fuzz.py): RNTIs
+    from a small pool so that histograms cross the threshold, the same RNTI in a location and its first children (shortcut, disambiguation), RNTI 0,
+    undecoded entries, RA / paging / SI / reserved RNTIs at random places, low-power CCEs, all CFIs, subframes under the 6 dB gate, meta-format re-splits every
+    7 subframes, and from subframe 200 on a RAR-activated RNTI (the temp_dci0 rule); also with shortcut discovery off, secondary formats skipped and other
+    histogram thresholds.  Same DCIs in the same order, same histogram values, same statistics."""
+    from test_survivor_fuzz import _random_table
+    L = capi.load_library()
+    capi._bind_search(L)
+    rng = np.random.default_rng(seed)
+    cell = Cell(*cellp)
+    ref = RefWalk(cell, threshold=thr)
+    srch = capi.Search(*cellp, threshold=thr)
+    ref.L.refwalk_config(ref.h, shortcut, skip2, 7)
+    srch.config(shortcut, skip2, 7)
+    S = infra.sim()
+    sizes_n = len({S.lte_dci_sizeof(C.byref(cell), f) for f in range(9)})
+    o = ltelib.Oracle(cell)
+    pool = rng.integers(0x100, 0xFFF0, 12)
+    ndci = nul = 0
+    for sf in range(int(os.environ.get("WALK_FUZZ_SF", "260"))):
+        cfi = int(rng.integers(1, 4))
+        nof_cce = int(infra.oracle().lteo_nof_cce(o.h, cfi))
+        info = capi.SfInfo()
+        info.tti, info.cfi, info.nof_cce = sf, cfi, nof_cce
+        info.snr_db = 20.0 if rng.random() > 0.03 else 3.0
+        amp = np.where(rng.random(nof_cce) < 0.15, 0.3, 1.2).astype(np.float32)
+        llr = (np.repeat(amp, 72) * rng.choice([-1.0, 1.0], 72 * nof_cce)).astype(np.float32)
+        pw = np.zeros(nof_cce, np.float32)
+        ltelib.oracle().lteo_cce_power(ltelib.ptr(llr), nof_cce, ltelib.ptr(pw))
+        for c in range(nof_cce):
+            info.cce_power[c] = pw[c]
+        if sf == 200:
+            rar = 0x7A7A
+            L.ltephy_search_activate(srch.h, rar, 0, 2)
+            ref.L.refwalk_activate(ref.h, rar, 0, 2)
+            pool = np.append(pool, rar)
+        T = _random_table(rng, L, nof_cce, sf % 10, pool, sizes_n)
+        want = ref.subframe(info, T, llr)
+        got = srch.subframe(info, T, max_out=256)
+        for is_ul in (False, True):
+            a = [d for d in got if (d["format"] == 0) == is_ul]
+            b = [r for r in want if (r.format == 0) == is_ul]
+            assert len(a) == len(b), (cellp, sf, is_ul, len(a), len(b))
+            for d, r in zip(a, b):
+                assert (int(d["rnti"]), int(d["format"]), int(d["L"]), int(d["ncce"]), int(d["nof_bits"]), int(d["histogram_value"])) == \
+                       (r.rnti, r.format, r.L, r.ncce, r.nof_bits, r.histval), (cellp, sf, is_ul)
+                assert np.array_equal(capi.cand_bits(d["bits"], r.nof_bits), np.frombuffer(bytes(r.bits), np.uint8)[:r.nof_bits])
+                nul += is_ul
+        ndci += len(got)
+    rs, ps = ref.stats(), srch.stats()
+    assert (rs.nof_decoded_locations, rs.nof_cce, rs.nof_missed_cce, rs.nof_subframes, rs.nof_locations) == \
+           (ps.nof_decoded_locations, ps.nof_cce, ps.nof_missed_cce, ps.nof_subframes, ps.nof_locations)
+    assert ndci > 200 and (nul > 10 or skip2), (ndci, nul)
+    ref.close()
