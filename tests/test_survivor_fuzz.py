@@ -101,3 +101,76 @@ def test_full_and_survivor_walks_agree_on_random_tables(infra, cellp, seed):
     assert (sa.nof_decoded_locations, sa.nof_cce, sa.nof_missed_cce, sa.nof_subframes, sa.nof_locations) == \
            (sb.nof_decoded_locations, sb.nof_cce, sb.nof_missed_cce, sb.nof_subframes, sb.nof_locations)
     assert ndci > 200 and refused >= 1
+
+
+@pytest.mark.parametrize("world,seed", [(2, 11), (3, 12), (8, 13)])
+def test_packed_walk_of_a_sharded_batch_agrees_on_random_tables(infra, world, seed):
+    """The walk turn of the sharded path (ltephy_pack_subframes per rank -> ltephy_search_batch_packed over all ranks' records, global subframe g = local
+    index * world + rank) against the plain full-table walk in global order, on the adversarial tables above: same DCIs with global subframe indices, same
+    (tti, cfi) table, same statistics; after a RAR activation ltephy_packed_needs_full_table says so on every rank's view and the walk refuses the records
+    until the full tables come with them."""
+    L = capi.load_library()
+    capi._bind_search(L)
+    rng = np.random.default_rng(seed)
+    cellp = (50, 2, 21, 2)
+    plain, packed = capi.Search(*cellp), capi.Search(*cellp)
+    plain.config(1, 0, 7)
+    packed.config(1, 0, 7)
+    S = infra.sim()
+    cell = Cell(*cellp)
+    sizes_n = len({S.lte_dci_sizeof(C.byref(cell), f) for f in range(9)})
+    o = ltelib.Oracle(cell)
+    pool = rng.integers(0x100, 0xFFF0, 12)
+    n_loc, tti0 = 6, 0
+    for batch in range(6):
+        if batch == 4:
+            for s in (plain, packed):
+                L.ltephy_search_activate(s.h, 0x7A7A, 0, 2)
+            pool = np.append(pool, 0x7A7A)
+        N = n_loc * world
+        infos = (capi.SfInfo * N)()
+        tables = np.zeros((N, capi.MAX_LOC, capi.MAX_SIZES), capi.CAND_DTYPE)
+        for g in range(N):
+            cfi = int(rng.integers(1, 4))
+            nof_cce = int(infra.oracle().lteo_nof_cce(o.h, cfi))
+            infos[g].tti, infos[g].cfi, infos[g].nof_cce = (tti0 + g) % 10240, cfi, nof_cce
+            infos[g].snr_db = 20.0 if rng.random() > 0.05 else 3.0
+            for pp in range(2):                                  # the packed header carries the sums the SNR is formed from (DESIGN.md section 2)
+                for aa in range(2):
+                    infos[g].noise[pp][aa], infos[g].rsrp[pp][aa] = 1.0, 100.0 if infos[g].snr_db > 6 else 2.0
+            pw = np.where(rng.random(nof_cce) < 0.15, 0.3, 1.2).astype(np.float32)
+            for c in range(nof_cce):
+                infos[g].cce_power[c] = pw[c]
+            tables[g] = _random_table(rng, L, nof_cce, infos[g].tti % 10, pool, sizes_n)
+        tti0 += N
+        want = []
+        for g in range(N):
+            for d in plain.subframe(infos[g], tables[g], max_out=256):
+                want.append((g, int(d["rnti"]), int(d["format"]), int(d["L"]), int(d["ncce"]), int(d["nof_bits"]), int(d["bits"]), int(d["histogram_value"])))
+        bufs, offs, fulls = [], [], []
+        for r in range(world):
+            li = (capi.SfInfo * n_loc)(*[infos[i * world + r] for i in range(n_loc)])
+            comp = np.zeros(n_loc, capi.COMPACT_DTYPE)
+            for i in range(n_loc):
+                comp[i] = packed.compact_from_table(infos[i * world + r], tables[i * world + r])[0]
+            rec, of = capi.pack_subframes(packed, li, comp)
+            pad = np.zeros(n_loc * capi.PACK_MAX_BYTES, np.uint8)
+            pad[:len(rec)] = rec
+            bufs.append(pad), offs.append(np.ascontiguousarray(of))
+            fulls.append(np.ascontiguousarray(tables[r::world]))
+        bp = (C.c_void_p * world)(*[b.ctypes.data for b in bufs])
+        op = (C.c_void_p * world)(*[x.ctypes.data for x in offs])
+        need = L.ltephy_packed_needs_full_table(packed.h, bp, op, world, n_loc)
+        over = any(int(packed.compact_from_table(infos[g], tables[g])["count"][0]) > capi.COMPACT_CAP for g in range(N))
+        assert need == (1 if batch >= 4 or over else 0)
+        pk = capi.search_batch_packed(packed, bufs, offs, n_loc, 256 * N)
+        if need:
+            assert pk is None                                    # refused as a whole, nothing consumed
+            pk = capi.search_batch_packed(packed, bufs, offs, n_loc, 256 * N, full=fulls)
+        dcis, tc = pk
+        got = [(int(d["sf"]), int(d["rnti"]), int(d["format"]), int(d["L"]), int(d["ncce"]), int(d["nof_bits"]), int(d["bits"]), int(d["histogram_value"])) for d in dcis]
+        assert got == want, (world, batch)
+        assert [(int(a), int(b)) for a, b in tc] == [(infos[g].tti, infos[g].cfi) for g in range(N)]
+    sa, sb = plain.stats(), packed.stats()
+    assert (sa.nof_decoded_locations, sa.nof_cce, sa.nof_missed_cce, sa.nof_subframes, sa.nof_locations) == \
+           (sb.nof_decoded_locations, sb.nof_cce, sb.nof_missed_cce, sb.nof_subframes, sb.nof_locations)
