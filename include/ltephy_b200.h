@@ -225,7 +225,8 @@ int ltephy_harq_reserve(ltephy_t* h, uint32_t nslots);
 
 /* ---- uplink: PUSCH (PUSCH_Decoder::decode / decode_run, src/src/UL_Sniffer_PUSCH.cc:250-263,389-392) ------------ */
 typedef struct {
-  uint32_t n_dmrs1;       /* cyclicShift of SIB2 (ULSchedule::set_config, src/src/ULSchedule.cc:140-158) */
+  uint32_t n_dmrs1;       /* cyclicShift of SIB2, 0..7, as ULSchedule::set_config hands it to srsRAN (dmrs_cfg.cyclic_shift, src/src/ULSchedule.cc:143);
+                             n_DMRS^(1) = {0, 2, 3, 4, 6, 8, 9, 10}[cyclicShift] (36.211 Table 5.5.2.1.1-2) is looked up inside */
   uint32_t delta_ss;      /* groupAssignmentPUSCH */
   uint32_t group_hopping; /* groupHoppingEnabled    (dmrs_cfg.group_hopping_en, ULSchedule.cc:145): u = (f_gh(ns) + f_ss) mod 30 */
   uint32_t seq_hopping;   /* sequenceHoppingEnabled (dmrs_cfg.sequence_hopping_en, :146): v = c(ns) from 6 PRB on when group hopping is off */

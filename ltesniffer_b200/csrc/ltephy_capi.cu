@@ -846,6 +846,7 @@ extern "C" int ltephy_harq_reserve(ltephy_t* h, uint32_t nslots)
 extern "C" int ltephy_set_ul_cfg(ltephy_t* h, const ltephy_ul_cfg_t* cfg)
 {
   if (!h || !cfg) return fail(LTEPHY_ERROR_INVALID_INPUTS, "set_ul_cfg: bad arguments");
+  if (cfg->n_dmrs1 > 7 || cfg->delta_ss > 29) return fail(LTEPHY_ERROR_INVALID_INPUTS, "set_ul_cfg: cyclicShift is 0..7, groupAssignmentPUSCH 0..29");
   h->ulcfg = *cfg, h->ulcfg_set = true;
   const uint32_t fss = ((h->cell.cell_id % 30) + cfg->delta_ss) % 30;
   auto           cw  = ltehost::gold_words((h->cell.cell_id / 30) * 32 + fss, 8 * 7 * 20 + 8);
@@ -959,7 +960,8 @@ extern "C" int ltephy_submit_ul(ltephy_t* h, const float* iq_ul, const uint32_t*
     d.sf = g.sf, d.sf_idx = tti[g.sf] % 10, d.rnti = g.rnti, d.M = M, d.k0[0] = 12 * g.n_prb, d.k0[1] = 12 * n_prb1, d.qm = g.qm;
     d.qp_ack = L.Qp_ack, d.qp_ri = L.Qp_ri, d.qp_cqi = L.Qp_cqi;
     for (uint32_t sl = 0; sl < 2; sl++) {
-      const uint32_t ns = 2 * d.sf_idx + sl, ncs = (h->ulcfg.n_dmrs1 + g.n_dmrs2 + h->n_prs[ns]) % 12;
+      static const uint8_t n_dmrs1_of[8] = {0, 2, 3, 4, 6, 8, 9, 10}; // cyclicShift of SIB2 -> n_DMRS^(1), 36.211 Table 5.5.2.1.1-2
+      const uint32_t ns = 2 * d.sf_idx + sl, ncs = (n_dmrs1_of[h->ulcfg.n_dmrs1 & 7u] + g.n_dmrs2 + h->n_prs[ns]) % 12;
       if (ul_table_for(h, 0, M, ncs, h->ul_u[ns], M >= 72 ? h->ul_v[ns] : 0, d.dmrs_off[sl])) return fail(LTEPHY_ERROR, "UL table upload failed");
     }
     if (ul_table_for(h, 1, M, 0, 0, 0, d.idft_off)) return fail(LTEPHY_ERROR, "UL table upload failed");

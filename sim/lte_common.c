@@ -1011,7 +1011,8 @@ int lte_pusch_dmrs(const lte_cell_t* c, const lte_ul_cfg_t* u, uint32_t ns, uint
   lte_gold_bits((c->cell_id / 30) * 32 + fss, cbits, 8 * 7 * 20 + 8);
   uint32_t nprs = 0;
   for (uint32_t i = 0; i < 8; i++) nprs += (uint32_t)cbits[8 * 7 * ns + i] << i;
-  uint32_t ncs = (u->n_dmrs1 + n_dmrs2 + nprs) % 12;
+  static const uint8_t n_dmrs1_of[8] = {0, 2, 3, 4, 6, 8, 9, 10}; /* cyclicShift -> n_DMRS^(1), 36.211 Table 5.5.2.1.1-2 */
+  uint32_t ncs = (n_dmrs1_of[u->n_dmrs1 & 7u] + n_dmrs2 + nprs) % 12;
   uint32_t Nzc = lte_largest_prime_below(M);
   double   qb  = (double)Nzc * (useq + 1) / 31.0;
   uint32_t q   = (uint32_t)floor(qb + 0.5);

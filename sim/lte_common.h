@@ -238,7 +238,7 @@ uint32_t lte_pbch_crc_mask(uint32_t nof_ports);
 extern "C" {
 #endif
 typedef struct {
-  uint32_t n_dmrs1;       /* cyclicShift (SIB2 -> ULSchedule::set_config, src/src/ULSchedule.cc:140-158) */
+  uint32_t n_dmrs1;       /* cyclicShift of SIB2, 0..7 (ULSchedule::set_config, src/src/ULSchedule.cc:140-158); n_DMRS^(1) by Table 5.5.2.1.1-2 */
   uint32_t delta_ss;      /* groupAssignmentPUSCH */
   uint32_t group_hopping; /* groupHoppingEnabled: u = (f_gh(ns) + f_ss) mod 30, 36.211 5.5.1.3 */
   uint32_t seq_hopping;   /* sequenceHoppingEnabled: v = c(ns) for M_sc >= 72 when group hopping is off, 36.211 5.5.1.4 */

@@ -1,0 +1,208 @@
+"""The 3GPP primitives that the synthetic transmitter (sim/) and the CPU oracle SHARE (sim/lte_common.c) against implementations that are not ours.
+A mistake in one of them would be invisible to every transmitter -> oracle -> CUDA comparison, because both ends would make it; srsRAN, which would pin
+them, is absent.  Third-party code / published constants used here:
+  * CRC: binascii.crc_hqx (CRC-16/XMODEM = gCRC16 of 36.212 5.1.1) and the check values of the CRC catalogue for CRC-24/LTE-A, CRC-24/LTE-B, CRC-8/LTE;
+  * Gold sequences (36.211 7.2): scipy.signal.max_len_seq as the LFSR;
+  * OFDM demodulation: numpy.fft;
+and, where no library exists, a formulation in another domain than the shift-register loops of lte_common.c (polynomial products over GF(2) with
+numpy.convolve for the convolutional and turbo encoders, closed-form constellation and Zadoff-Chu expressions of 36.211 evaluated in float64)."""
+import binascii
+import ctypes as C
+import os
+import sys
+import numpy as np
+import pytest
+import ltelib
+from ltelib import Cell
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+import check_tables  # noqa: E402
+
+
+@pytest.fixture(scope="module")
+def S(infra):
+    L = infra.sim()
+    L.lte_crc.restype = C.c_uint32
+    L.lte_crc.argtypes = [C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint32]
+    L.lte_gold_bits.argtypes = [C.c_uint32, C.c_void_p, C.c_uint32]
+    L.lte_conv_encode.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p]
+    L.lte_turbo_encode.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.lte_qpp.argtypes = [C.c_uint32, C.c_void_p]
+    L.lte_modulate.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p]
+    L.lte_crs.restype = C.c_uint32
+    L.lte_crs.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p]
+    L.lte_pusch_dmrs.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p]
+    return L
+
+
+def bits_of(data):
+    return np.unpackbits(np.frombuffer(bytes(data), np.uint8))
+
+
+def test_crc_polynomials_against_binascii_and_catalogue_check_values(S):
+    check = bits_of(b"123456789")
+    p = ltelib.ptr
+    # published check values (CRC RevEng catalogue): CRC-24/LTE-A, CRC-24/LTE-B, CRC-16/XMODEM, CRC-8/LTE
+    assert S.lte_crc(0x1864CFB, 24, p(check), 72) == 0xCDE703
+    assert S.lte_crc(0x1800063, 24, p(check), 72) == 0x23EF52
+    assert S.lte_crc(0x11021, 16, p(check), 72) == 0x31C3
+    assert S.lte_crc(0x19B, 8, p(check), 72) == 0xEA
+    rng = np.random.default_rng(0)
+    for n in (1, 2, 7, 31, 100, 753):
+        data = rng.integers(0, 256, n, dtype=np.uint8).tobytes()
+        b = bits_of(data)
+        assert S.lte_crc(0x11021, 16, p(b), 8 * n) == binascii.crc_hqx(data, 0)
+    # bit lengths that are no multiple of 8 (DCI payloads): a CRC of the zero-extended message through the library, undone by the linearity of the code
+    for nb in (27, 31, 43):
+        b = rng.integers(0, 2, nb).astype(np.uint8)
+        padded = np.concatenate([np.zeros((-nb) % 8, np.uint8), b])           # leading zeros do not change a zero-initialised CRC
+        assert S.lte_crc(0x11021, 16, p(b), nb) == binascii.crc_hqx(np.packbits(padded).tobytes(), 0)
+
+
+def gold_scipy(c_init, n):
+    from scipy.signal import max_len_seq
+    x1 = np.zeros(31, np.int8)
+    x1[0] = 1
+    x2 = np.array([(c_init >> i) & 1 for i in range(31)], np.int8)
+    s1 = max_len_seq(31, state=x1, length=1600 + n, taps=[3])[0]            # x1(n+31) = x1(n+3) + x1(n)
+    s2 = max_len_seq(31, state=x2, length=1600 + n, taps=[1, 2, 3])[0]      # x2(n+31) = x2(n+3) + x2(n+2) + x2(n+1) + x2(n)
+    return (s1[1600:] ^ s2[1600:]).astype(np.uint8)
+
+
+def test_gold_sequence_against_scipy_lfsr(S):
+    rng = np.random.default_rng(1)
+    for c_init in [1, 0x7FFFFFFF, (0x1234 << 14) + (3 << 9) + 301] + [int(x) for x in rng.integers(1, 1 << 31, 6)]:
+        n = 5000
+        out = np.zeros(n, np.uint8)
+        S.lte_gold_bits(c_init, ltelib.ptr(out), n)
+        assert np.array_equal(out, gold_scipy(c_init, n)), hex(c_init)
+
+
+def test_crs_values_follow_the_gold_sequence(S):
+    """36.211 6.10.1.1: r(m) = ((1 - 2 c(2m)) + j (1 - 2 c(2m+1))) / sqrt 2, c_init = 2^10 (7 (ns+1) + l + 1)(2 N_id + 1) + 2 N_id + N_CP, the 2 nof_prb values
+    of the cell cut from the middle of the 220 of the maximum bandwidth"""
+    for cellp in ((100, 2, 301, 2), (25, 1, 5, 1), (50, 2, 167, 2)):
+        cell = Cell(*cellp)
+        for ns, l in ((0, 0), (7, 4), (19, 0), (12, 4)):
+            pil = np.zeros(2 * cell.nof_prb, np.complex64)
+            for port in range(cell.nof_ports):                            # frequency position: k = 6 m + (v + v_shift) mod 6, v = 0 / 3 by port and symbol
+                off = S.lte_crs(C.byref(cell), port, ns, l, ltelib.ptr(pil))
+                assert off == (((0 if l == 0 else 3) if port == 0 else (3 if l == 0 else 0)) + cell.cell_id % 6) % 6
+            c_init = (1 << 10) * (7 * (ns + 1) + l + 1) * (2 * cell.cell_id + 1) + 2 * cell.cell_id + 1
+            c = gold_scipy(c_init, 440).astype(np.float64)
+            r = ((1 - 2 * c[0::2]) + 1j * (1 - 2 * c[1::2])) / np.sqrt(2)
+            m0 = 110 - cell.nof_prb
+            assert np.allclose(pil, r[m0:m0 + 2 * cell.nof_prb], atol=1e-6)
+
+
+def test_tail_biting_convolutional_encoder_is_a_circular_gf2_convolution(S):
+    """36.212 5.1.3.1: generators 133, 171, 165 (octal), register initialised with the last six bits = circular convolution of the block with each generator"""
+    gens = [[1, 0, 1, 1, 0, 1, 1], [1, 1, 1, 1, 0, 0, 1], [1, 1, 1, 0, 1, 0, 1]]
+    rng = np.random.default_rng(2)
+    for K in (27, 31, 43, 40, 56):
+        c = rng.integers(0, 2, K).astype(np.uint8)
+        out = np.zeros(3 * K, np.uint8)
+        S.lte_conv_encode(ltelib.ptr(c), K, ltelib.ptr(out))
+        for i, g in enumerate(gens):
+            d = sum(g[j] * np.roll(c.astype(np.int64), j) for j in range(7)) % 2
+            assert np.array_equal(out[i * K:(i + 1) * K], d), (K, i)
+
+
+def rsc_numpy(x):
+    """constituent encoder of 36.212 5.1.3.2.1, g0 = 1 + D^2 + D^3 (feedback), g1 = 1 + D + D^3, as power-series products over GF(2):
+    a = x / g0 = x * (1 / g0), z = a * g1, plus the three termination steps (input = feedback, so that the register empties)"""
+    K = len(x)
+    inv = np.zeros(K + 3, np.int64)          # 1 / g0: s_k = s_{k-2} + s_{k-3}, s_0 = 1 (period 7)
+    for k in range(K + 3):
+        inv[k] = 1 if k == 0 else (inv[k - 2] if k >= 2 else 0) ^ (inv[k - 3] if k >= 3 else 0)
+    a = np.convolve(x.astype(np.int64), inv)[:K] % 2
+    a_ext = np.concatenate([a, np.zeros(3, np.int64)])                      # a_K .. a_{K+2} = 0 by construction of the termination
+    xt = [int(a_ext[K + i - 2] ^ a_ext[K + i - 3]) for i in range(3)]       # tail inputs = the feedback value
+    z = np.convolve(a_ext, [1, 1, 0, 1])[:K + 3] % 2
+    return z[:K].astype(np.uint8), xt, [int(v) for v in z[K:K + 3]]
+
+
+def test_turbo_encoder_against_power_series_formulation(S):
+    f1, f2, _, _ = check_tables.load()
+    Ks = check_tables.K_TABLE if hasattr(check_tables, "K_TABLE") else None
+    rng = np.random.default_rng(3)
+    for K in (40, 104, 512, 1056, 6144, 5824):
+        pi = np.zeros(K, np.uint16)
+        S.lte_qpp(K, ltelib.ptr(pi))
+        assert sorted(pi.tolist()) == list(range(K))                        # a permutation ...
+        idx = [i for i in range(188) if (40 + 8 * i if i < 60 else 512 + 16 * (i - 59) if i < 92 else 1024 + 32 * (i - 91) if i < 124 else 2048 + 64 * (i - 123)) == K][0]
+        i = np.arange(K, dtype=np.int64)
+        assert np.array_equal(pi, (f1[idx] * i + f2[idx] * i * i) % K)      # ... and the quadratic one of 36.212 Table 5.1.3-3
+        x = rng.integers(0, 2, K).astype(np.uint8)
+        d = [np.zeros(K + 4, np.uint8) for _ in range(3)]
+        S.lte_turbo_encode(ltelib.ptr(x), K, ltelib.ptr(d[0]), ltelib.ptr(d[1]), ltelib.ptr(d[2]))
+        z, xt, zt = rsc_numpy(x)
+        zp, xpt, zpt = rsc_numpy(x[pi])
+        assert np.array_equal(d[0][:K], x) and np.array_equal(d[1][:K], z) and np.array_equal(d[2][:K], zp), K
+        # trellis termination multiplexing, 36.212 5.1.3.2.2
+        assert [int(v) for v in d[0][K:]] == [xt[0], zt[1], xpt[0], zpt[1]]
+        assert [int(v) for v in d[1][K:]] == [zt[0], xt[2], zpt[0], xpt[2]]
+        assert [int(v) for v in d[2][K:]] == [xt[1], zt[2], xpt[1], zpt[2]]
+
+
+def test_modulation_mapper_against_closed_forms(S):
+    """36.211 7.1.2 - 7.1.5 written as formulas instead of tables: every axis is a Gray-coded PAM, I from the even bits, Q from the odd ones"""
+    def pam(bits):                                                          # bits[0] = sign, the following ones fold the amplitude
+        v = np.zeros(bits.shape[1])
+        for k in range(bits.shape[0] - 1, 0, -1):
+            v = (1 << (bits.shape[0] - k)) - (1 - 2.0 * bits[k]) * (v if k < bits.shape[0] - 1 else 1.0)
+        return (1 - 2.0 * bits[0]) * (v if bits.shape[0] > 1 else 1.0)
+    rng = np.random.default_rng(4)
+    for qm, norm in ((2, 2.0), (4, 10.0), (6, 42.0), (8, 170.0)):
+        n = 4096
+        b = rng.integers(0, 2, n * qm).astype(np.uint8)
+        b[:qm * (1 << qm)] = np.array([[(s >> (qm - 1 - k)) & 1 for k in range(qm)] for s in range(1 << qm)], np.uint8).ravel()   # every point once
+        out = np.zeros(n, np.complex64)
+        S.lte_modulate(ltelib.ptr(b), n, qm, ltelib.ptr(out))
+        bb = b.reshape(n, qm).T.astype(np.float64)
+        ref = (pam(bb[0::2]) + 1j * pam(bb[1::2])) / np.sqrt(norm)
+        assert np.allclose(out, ref, atol=1e-6), qm
+        assert abs(np.mean(np.abs(out[:1 << qm]) ** 2) - 1.0) < 1e-5         # unit average power over the constellation
+
+
+def test_pusch_dmrs_against_zadoff_chu_formula(S):
+    """36.211 5.5.1.1 / 5.5.2.1.1 for M_sc >= 36 without hopping: r(n) = exp(j alpha n) x_q(n mod N_zc), x_q(m) = exp(-j pi q m (m+1) / N_zc),
+    q from u = (cell_id mod 30 + delta_ss) mod 30, alpha = 2 pi ((n_dmrs1 + n_dmrs2 + n_prs(ns)) mod 12) / 12"""
+    n1_map = [0, 2, 3, 4, 6, 8, 9, 10]                                      # cyclicShift -> n_DMRS^(1), Table 5.5.2.1.1-2
+    for cell_id, delta_ss, cs, n2, nprb, ns in ((301, 0, 0, 0, 3, 0), (5, 7, 3, 6, 10, 11), (167, 29, 7, 9, 25, 19), (40, 3, 5, 4, 48, 4)):
+        cell = Cell(50, 1, cell_id, 1)
+        ucfg = (C.c_uint32 * 5)(cs, delta_ss, 0, 0, 0)
+        M = 12 * nprb
+        r = np.zeros(M, np.complex64)
+        assert S.lte_pusch_dmrs(C.byref(cell), ucfg, ns, n2, M, ltelib.ptr(r)) == 0
+        nzc = max(p for p in range(2, M) if all(p % d for d in range(2, int(p ** 0.5) + 1)))
+        u = ((cell_id % 30) + delta_ss) % 30
+        qbar = nzc * (u + 1) / 31.0
+        q = int(np.floor(qbar + 0.5))                                        # v = 0
+        m = np.arange(M) % nzc
+        base = np.exp(-1j * np.pi * q * m * (m + 1) / nzc)
+        c = gold_scipy((cell_id // 30) * 32 + ((cell_id % 30) + delta_ss) % 30, 8 * 7 * 20 + 8)
+        nprs = sum(int(c[8 * 7 * ns + i]) << i for i in range(8))
+        alpha = 2 * np.pi * ((n1_map[cs] + n2 + nprs) % 12) / 12
+        assert np.allclose(r, np.exp(1j * alpha * np.arange(M)) * base, atol=2e-4), (cell_id, nprb)
+
+
+def test_ofdm_demodulator_against_numpy_fft(infra):
+    """K1 of the oracle: cyclic prefixes 160 / 144 (scaled), FFT of symbol_sz points, the 12 nof_prb carriers around DC (DC itself skipped), no scaling"""
+    rng = np.random.default_rng(5)
+    for cellp, symsz in (((25, 1, 5, 1), 0), ((50, 2, 3, 2), 0), ((100, 2, 1, 2), 0), ((100, 2, 1, 2), 1536)):
+        cell = Cell(*cellp, symsz)
+        o = ltelib.Oracle(cell)
+        N = cell.fft()
+        sf_len = 15 * N
+        iq = (rng.standard_normal(sf_len) + 1j * rng.standard_normal(sf_len)).astype(np.complex64)
+        sym = o.ofdm(np.stack([iq] * cell.nof_rx))[0].reshape(14, 12 * cell.nof_prb)
+        nsc = 12 * cell.nof_prb
+        pos = 0
+        for l in range(14):
+            cp = (160 if l % 7 == 0 else 144) * N // 2048
+            X = np.fft.fft(iq[pos + cp:pos + cp + N].astype(np.complex128))
+            ref = np.concatenate([X[N - nsc // 2:], X[1:nsc // 2 + 1]])
+            assert np.allclose(sym[l], ref, atol=2e-5 * np.sqrt(N)), (cellp, symsz, l)      # fp32 butterflies against float64
+            pos += cp + N
+        assert pos == sf_len
