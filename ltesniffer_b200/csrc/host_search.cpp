@@ -999,10 +999,31 @@ extern "C" int ltephy_dci_trace_line(const ltephy_search_t* s, const ltephy_dci_
 }
 
 // ===================================================================================================
+// Control-region geometry of a cell as the PHY uses it (tables uploaded by ltephy_create): for one CFI the grid indices l * 12 nof_prb + k of the four REs of
+// every PDCCH quadruplet in CCE order (36.211 6.8.5: interleaver and cell-specific shift applied; PCFICH and PHICH REGs left out), and the 16 PCFICH REs.
+int ltephy_ctrl_region_map(uint32_t nof_prb, uint32_t nof_ports, uint32_t cell_id, uint32_t phich_resources, uint32_t cfi, uint16_t* pdcch_idx, uint32_t cap,
+                           uint32_t* nof_cce, uint16_t* pcfich_idx)
+{
+  if (cfi < 1 || cfi > 3 || !nof_cce) return LTEPHY_ERROR_INVALID_INPUTS;
+  ltehost::CtrlMap cm;
+  if (!ltehost::build_ctrl_map(ltehost::Cell{nof_prb, nof_ports, cell_id, 1, phich_resources}, cm)) return LTEPHY_ERROR_INVALID_INPUTS;
+  *nof_cce = cm.nof_cce[cfi - 1];
+  if (pdcch_idx) {
+    if (cap < cm.pdcch_idx[cfi - 1].size()) return LTEPHY_ERROR_INVALID_INPUTS;
+    memcpy(pdcch_idx, cm.pdcch_idx[cfi - 1].data(), cm.pdcch_idx[cfi - 1].size() * sizeof(uint16_t));
+  }
+  if (pcfich_idx) memcpy(pcfich_idx, cm.pcfich_idx, sizeof(cm.pcfich_idx));
+  return LTEPHY_SUCCESS;
+}
 ltephy_search_t* ltephy_search_create_cell(uint32_t nof_prb, uint32_t nof_ports, uint32_t cell_id, uint32_t nof_rx, uint32_t histogram_threshold)
 {
+  return ltephy_search_create_cell_ng(nof_prb, nof_ports, cell_id, nof_rx, 0, histogram_threshold);
+}
+ltephy_search_t* ltephy_search_create_cell_ng(uint32_t nof_prb, uint32_t nof_ports, uint32_t cell_id, uint32_t nof_rx, uint32_t phich_resources,
+                                              uint32_t histogram_threshold)
+{
   ltehost::CtrlMap cm;
-  ltehost::Cell    cell{nof_prb, nof_ports, cell_id, nof_rx};
+  ltehost::Cell    cell{nof_prb, nof_ports, cell_id, nof_rx, phich_resources};
   if (!ltehost::build_ctrl_map(cell, cm)) return nullptr;
   ltephy_search* s = new ltephy_search();
   s->cell          = cell;
@@ -1051,7 +1072,7 @@ ltephy_search_t* ltephy_search_create(const ltephy_t* h, uint32_t histogram_thre
   if (!h) return nullptr;
   uint32_t a, b, c, d;
   ltephy_cell_of(h, &a, &b, &c, &d);
-  return ltephy_search_create_cell(a, b, c, d, histogram_threshold);
+  return ltephy_search_create_cell_ng(a, b, c, d, ltephy_phich_resources(h), histogram_threshold);
 }
 void ltephy_search_destroy(ltephy_search_t* s) { delete s; }
 void ltephy_search_set_ul_hopping(ltephy_search_t* s, uint32_t n_rb_ho)

@@ -117,7 +117,7 @@ struct Reg {
 
 bool build_ctrl_map(const Cell& c, CtrlMap& out)
 {
-  if (c.nof_prb <= 10 || c.nof_prb > 110 || c.nof_ports < 1 || c.nof_ports > 2) return false;
+  if (c.nof_prb <= 10 || c.nof_prb > 110 || c.nof_ports < 1 || c.nof_ports > 2 || c.phich_ng > 3) return false;
   const uint32_t   nsc = 12 * c.nof_prb, v3 = c.cell_id % 3;
   std::vector<Reg> regs;
   uint32_t         sym_base[4] = {0, 0, 0, 0};
@@ -146,12 +146,15 @@ bool build_ctrl_map(const Cell& c, CtrlMap& out)
     regs[j].kind = 1;
     for (int q = 0; q < 4; q++) out.pcfich_idx[4 * i + q] = regs[j].k[q];
   }
-  // PHICH: normal duration, Ng = 1/6 (file mode assumption, src/src/LTESniffer_Core.cc:242-247)
+  // PHICH, normal duration (36.211 6.9): N_group = ceil(Ng N_RB / 8), Ng = 1/6, 1/2, 1, 2 from the MIB (srsran_cell_t.phich_resources; the
+  // reference's file mode presets 1/6, src/src/LTESniffer_Core.cc:242-247, its live mode takes the MIB's value, :196, :389)
   {
     std::vector<uint32_t> free0;
     for (uint32_t j = sym_base[0]; j < sym_base[1]; j++)
       if (regs[j].kind == 0) free0.push_back(j);
-    const uint32_t n0 = (uint32_t)free0.size(), ngroups = (c.nof_prb + 47) / 48;
+    static const uint32_t ng_x6[4] = {1, 3, 6, 12};
+    const uint32_t        n0 = (uint32_t)free0.size(), ngroups = (ng_x6[c.phich_ng] * c.nof_prb + 47) / 48;
+    if (3 * ngroups > n0) return false;
     for (uint32_t m = 0; m < ngroups; m++)
       for (uint32_t i = 0; i < 3; i++) regs[free0[(c.cell_id + m + i * n0 / 3) % n0]].kind = 2;
   }

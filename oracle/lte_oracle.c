@@ -469,6 +469,19 @@ uint32_t lteo_pdcch_extract_llr(lteo_t* q, uint32_t sf_idx, uint32_t cfi, const 
   }
   return nof_cce;
 }
+/* geometry only: grid index l * nsc + k of every RE lteo_pdcch_extract_llr reads, in its order (test accessor) */
+uint32_t lteo_pdcch_re_index(lteo_t* q, uint32_t cfi, uint16_t* idx, uint16_t* pcfich_idx)
+{
+  uint32_t nq = q->regs.nof_cce[cfi - 1] * 9;
+  for (uint32_t qq = 0; qq < nq; qq++) {
+    const lte_reg_t* rg = &q->regs.regs[q->regs.pdcch_map[cfi - 1][qq]];
+    for (int j = 0; j < 4; j++) idx[4 * qq + j] = (uint16_t)(rg->l * q->nsc + rg->k[j]);
+  }
+  if (pcfich_idx)
+    for (int i = 0; i < 4; i++)
+      for (int j = 0; j < 4; j++) pcfich_idx[4 * i + j] = q->regs.regs[q->regs.pcfich_reg[i]].k[j];
+  return q->regs.nof_cce[cfi - 1];
+}
 void lteo_cce_power(const float* llr, uint32_t nof_cce, float* pwr)
 {
   for (uint32_t c = 0; c < nof_cce; c++) {

@@ -45,6 +45,8 @@ float lteo_det_sum(const float* x, uint32_t n);
 
 /* K1: one antenna-subframe: iq[sf_len] -> sym[14*12*nof_prb] */
 void lteo_ofdm_rx(lteo_t* q, const cf_t* iq, cf_t* sym);
+/* geometry of the control region: grid indices of the PDCCH REs in CCE order for this CFI, and of the 16 PCFICH REs (may be NULL); returns nof_cce */
+uint32_t lteo_pdcch_re_index(lteo_t* q, uint32_t cfi, uint16_t* idx, uint16_t* pcfich_idx);
 /* K2: sym[ant] -> ce[port*nof_rx+ant][14*nsc] */
 void lteo_chest(lteo_t* q, uint32_t sf_idx, const cf_t* const* sym, cf_t* const* ce, lteo_chest_res_t* res);
 /* K10: per-PRB mean RE power of antenna 0 (linear) -- SubframePower::computePower, src/src/SubframePower.cc:18-58 */

@@ -87,7 +87,7 @@ int lte_regs_init(lte_regs_t* r, const lte_cell_t* cell)
 {
   memset(r, 0, sizeof(*r));
   r->cell = *cell;
-  if (cell->nof_prb <= 10 || cell->nof_prb > LTE_MAX_PRB || cell->nof_ports < 1 || cell->nof_ports > 2) return -1;
+  if (cell->nof_prb <= 10 || cell->nof_prb > LTE_MAX_PRB || cell->nof_ports < 1 || cell->nof_ports > 2 || cell->phich_ng > 3) return -1;
   uint32_t n = 0, vs3 = cell->cell_id % 3;
   for (uint32_t l = 0; l < 3; l++) {
     uint32_t cnt = 0;
@@ -120,11 +120,13 @@ int lte_regs_init(lte_regs_t* r, const lte_cell_t* cell)
       }
     if (!found) return -2;
   }
-  /* PHICH, normal duration, Ng = 1/6 (LTESniffer_Core.cc:242-247), 36.211 6.9.3 */
-  r->nof_phich_groups = (cell->nof_prb + 47) / 48;
+  /* PHICH, normal duration, 36.211 6.9: N_group = ceil(Ng N_RB / 8), Ng = 1/6 (the reference's file mode, LTESniffer_Core.cc:242-247), 1/2, 1 or 2 */
+  static const uint32_t ng_x6[4] = {1, 3, 6, 12};
+  r->nof_phich_groups = (ng_x6[cell->phich_ng] * cell->nof_prb + 47) / 48;
   uint32_t n0 = 0, idx0[2 * LTE_MAX_PRB];
   for (uint32_t j = 0; j < r->nof_regs_sym[0]; j++)
     if (r->regs[j].kind != 1) idx0[n0++] = j;
+  if (3 * r->nof_phich_groups > n0 || r->nof_phich_groups > 28) return -2;
   for (uint32_t m = 0; m < r->nof_phich_groups; m++)
     for (uint32_t i = 0; i < 3; i++) {
       uint32_t ni                       = (cell->cell_id + m + (i * n0) / 3) % n0;

@@ -33,6 +33,7 @@ typedef struct {
   uint32_t nof_rx;    /* rx antennas 1 or 2 */
   uint32_t symbol_sz; /* FFT size; 0 = the standard LTE rate (2048 at 100 PRB).  srsRAN's default build samples at 3/4 of it
                          (srsran_symbol_sz: 1536 at 100 PRB, 768 at 50, 384 at 25), which is what LTESniffer records with */
+  uint32_t phich_ng;  /* phich-Resource of the MIB as srsran_phich_r_t: 0 = Ng 1/6, 1 = 1/2, 2 = 1, 3 = 2; normal PHICH duration */
 } lte_cell_t;
 
 /* numerology */
@@ -71,7 +72,7 @@ typedef struct {
   uint32_t   nof_regs_total;
   uint32_t   pcfich_reg[4]; /* indices into regs[] */
   uint32_t   nof_phich_groups;
-  uint32_t   phich_reg[3 * 16];
+  uint32_t   phich_reg[3 * 28]; /* up to ceil(2 * 110 / 8) groups */
   /* per CFI: */
   uint32_t nof_pdcch_regs[3]; /* (N_reg/9)*9 */
   uint32_t nof_cce[3];
