@@ -206,3 +206,72 @@ def test_ofdm_demodulator_against_numpy_fft(infra):
             assert np.allclose(sym[l], ref, atol=2e-5 * np.sqrt(N)), (cellp, symsz, l)      # fp32 butterflies against float64
             pos += cp + N
         assert pos == sf_len
+
+
+P_TURBO = [0, 16, 8, 24, 4, 20, 12, 28, 2, 18, 10, 26, 6, 22, 14, 30, 1, 17, 9, 25, 5, 21, 13, 29, 3, 19, 11, 27, 7, 23, 15, 31]   # 36.212 Table 5.1.4-1
+P_CONV = [1, 17, 9, 25, 5, 21, 13, 29, 3, 19, 11, 27, 7, 23, 15, 31, 0, 16, 8, 24, 4, 20, 12, 28, 2, 18, 10, 26, 6, 22, 14, 30]    # Table 5.1.4-2
+
+
+def subblock(y, P):
+    """sub-block interleaver as the matrix of 36.212 5.1.4.1.1: NULLs (-1) in front, rows of 32, columns permuted, read column by column"""
+    D = len(y)
+    R = -(-D // 32)
+    m = np.concatenate([np.full(32 * R - D, -1, np.int64), np.asarray(y, np.int64)]).reshape(R, 32)
+    return m[:, P].T.reshape(-1), R
+
+
+def test_turbo_rate_matching_against_matrix_formulation(S):
+    S.lte_rm_turbo_tx.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint32]
+    rng = np.random.default_rng(6)
+    for K, F in ((40, 0), (104, 8), (1056, 0), (6144, 0), (5824, 24)):
+        D = K + 4
+        d = rng.integers(0, 2, 3 * D).astype(np.uint8)
+        lab = [np.arange(s * D, (s + 1) * D, dtype=np.int64) for s in range(3)]          # interleave positions, then look the bits up
+        for s in (0, 1):
+            lab[s][:F] = -1                                                 # filler bits are NULL in the systematic and first parity stream
+        v0, R = subblock(lab[0], P_TURBO)
+        v1, _ = subblock(lab[1], P_TURBO)
+        Kpi = 32 * R
+        y2 = np.concatenate([np.full(Kpi - D, -1, np.int64), lab[2]])
+        k = np.arange(Kpi)
+        v2 = y2[(np.array(P_TURBO)[k // R] + 32 * (k % R) + 1) % Kpi]      # second parity: the same permutation shifted by one
+        w = np.empty(3 * Kpi, np.int64)
+        w[:Kpi] = v0
+        w[Kpi::2] = v1
+        w[Kpi + 1::2] = v2
+        for rv in range(4):
+            k0 = R * (2 * -(-3 * Kpi // (8 * R)) * rv + 2)
+            ring = np.concatenate([w[k0:], w, w, w])
+            ring = ring[ring >= 0]
+            for E in (D // 2 * 2, 3 * D - 12, 5 * D):
+                e = np.zeros(E, np.uint8)
+                S.lte_rm_turbo_tx(ltelib.ptr(d), K, F, rv, ltelib.ptr(e), E)
+                assert np.array_equal(e, d[ring[:E]]), (K, F, rv, E)
+
+
+def test_convolutional_rate_matching_against_matrix_formulation(S):
+    S.lte_rm_conv_tx.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32]
+    rng = np.random.default_rng(7)
+    for K in (27 + 16, 31 + 16, 43 + 16, 40):
+        d = rng.integers(0, 2, 3 * K).astype(np.uint8)
+        w = np.concatenate([subblock(np.arange(s * K, (s + 1) * K), P_CONV)[0] for s in range(3)])      # 5.1.4.2.2: the three streams one after the other
+        w = w[w >= 0]
+        for E in (72, 144, 288, 576):
+            e = np.zeros(E, np.uint8)
+            S.lte_rm_conv_tx(ltelib.ptr(d), K, ltelib.ptr(e), E)
+            assert np.array_equal(e, d[np.resize(w, E)]), (K, E)
+
+
+def test_code_block_segmentation_against_python_restatement(S):
+    """lte_cbsegm (C, shared by transmitter and oracle) against tools/check_tables.segm (Python, written from 36.212 5.1.2 for the table checks) on every
+    transport block size of the table and on sizes with filler bits"""
+    class Segm(C.Structure):
+        _fields_ = [(n, C.c_uint32) for n in ("tbs", "C", "Kp", "Km", "Cp", "Cm", "F")]
+    S.lte_cbsegm.argtypes = [C.c_void_p, C.c_uint32]
+    _, _, tbs, _ = check_tables.load()
+    sizes = sorted(set(int(v) for v in np.array(tbs).ravel())) + [40 - 24, 6120, 6144 - 24 + 8, 12960, 100000, 101840]
+    for v in sizes:
+        s = Segm()
+        assert S.lte_cbsegm(C.byref(s), v) == 0, v
+        Cn, Kp, Km, Cp, Cm, F = check_tables.segm(v)
+        assert (s.C, s.Kp, s.Cp, s.Cm, s.F) == (Cn, Kp, Cp, Cm, F) and (s.Km == Km or Cm == 0), (v, check_tables.segm(v))
