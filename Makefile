@@ -17,8 +17,11 @@ oracle/liblteoracle.so: oracle/lte_oracle.c oracle/lte_oracle.h sim/lte_common.c
 examples/offline_decode: examples/offline_decode.cpp include/ltephy_b200.h include/ltephy_search.h include/ltephy_sinks.h
 	$(CXX) -O2 -std=c++17 -Wall -Iinclude -o $@ examples/offline_decode.cpp -Lltesniffer_b200 -lltephy_b200 -Wl,-rpath,'$$ORIGIN/../ltesniffer_b200'
 
+examples/offline_ul: examples/offline_ul.cpp include/ltephy_b200.h include/ltephy_search.h include/ltephy_sinks.h
+	$(CXX) -O2 -std=c++17 -Wall -Iinclude -o $@ examples/offline_ul.cpp -Lltesniffer_b200 -lltephy_b200 -Wl,-rpath,'$$ORIGIN/../ltesniffer_b200'
+
 examples/compat_check: examples/compat_check.cpp compat/srsran/srsran.h include/ltephy_b200.h
 	$(CXX) -O2 -std=c++17 -Wall -Iinclude -Icompat -o $@ examples/compat_check.cpp -Lltesniffer_b200 -lltephy_srsran_compat -lltephy_b200 -Wl,-rpath,'$$ORIGIN/../ltesniffer_b200'
 
 clean:
-	rm -f sim/*.so oracle/*.so examples/offline_decode examples/compat_check
+	rm -f sim/*.so oracle/*.so examples/offline_decode examples/offline_ul examples/compat_check

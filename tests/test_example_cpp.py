@@ -71,3 +71,24 @@ def test_example_matches_python_pipeline(infra, phylib, tmp_path):
     lines = open(tsv).read().splitlines()
     assert len(lines) >= ndci * 0.9 and all(len(l.split("\t")) == 20 for l in lines)
     assert ("subframes %d " % n) in r.stdout
+
+
+def test_ul_mode_example_builds_and_refuses_to_run_without_a_gpu(infra, tmp_path):
+    """examples/offline_ul.cpp: the UL mode as a C++ caller of the C-ABI (ltephy_search_set_ul_mode, ltephy_rar_unpack, ltephy_ul_grants_from_dcis,
+    ltephy_submit_ul ...): it compiles against the headers as they are, links, and without a GPU fails in ltephy_create"""
+    capi.load_library()
+    subprocess.run(["make", "-s", "-C", ROOT, "examples/offline_ul"], check=True)
+    exe = os.path.join(ROOT, "examples", "offline_ul")
+    assert os.path.exists(exe)
+    try:
+        import torch
+        has_gpu = torch.cuda.is_available()
+    except Exception:
+        has_gpu = False
+    if has_gpu:
+        pytest.skip("a GPU is present")
+    for name in ("d.cf32", "u.cf32"):
+        (tmp_path / name).write_bytes(b"\0" * 8 * 7680)
+    r = subprocess.run([exe, str(tmp_path / "d.cf32"), str(tmp_path / "u.cf32"), "25", "1", "1", str(tmp_path / "o.pcap")], capture_output=True, text=True)
+    assert r.returncode == 1 and "ltephy_create" in r.stderr, (r.returncode, r.stderr)
+    assert subprocess.run([exe], capture_output=True).returncode == 2
