@@ -107,8 +107,12 @@ int main(int argc, char** argv)
         return 1;
       }
       // the attempts of one DCI-0 are adjacent and in the reference's order: keep the first that passed (PUSCH_Decoder::decode stops there)
-      for (size_t k = 0; k < now.size(); k++)
-        if (ures[k].crc && k > 0 && now[k - 1].rnti == now[k].rnti && now[k - 1].sf == now[k].sf && ures[k - 1].crc) ures[k].crc = 0;
+      bool passed = false;
+      for (size_t k = 0; k < now.size(); k++) {
+        if (k == 0 || now[k - 1].rnti != now[k].rnti || now[k - 1].sf != now[k].sf) passed = false;
+        if (ures[k].crc && passed) ures[k].crc = 0;
+        passed = passed || ures[k].crc != 0;
+      }
       const int wu = ltephy_pcap_write_ul_batch(pcap, ttis.data(), now.data(), (uint32_t)now.size(), ures.data(), upayload.data(), 0, ts_s, ts_us);
       if (wu < 0) return 1;
       n_ul_ok += (unsigned)wu;
