@@ -65,7 +65,10 @@ def gold_scipy(c_init, n):
     x1[0] = 1
     x2 = np.array([(c_init >> i) & 1 for i in range(31)], np.int8)
     s1 = max_len_seq(31, state=x1, length=1600 + n, taps=[3])[0]            # x1(n+31) = x1(n+3) + x1(n)
-    s2 = max_len_seq(31, state=x2, length=1600 + n, taps=[1, 2, 3])[0]      # x2(n+31) = x2(n+3) + x2(n+2) + x2(n+1) + x2(n)
+    if c_init == 0:                                                        # the all-zero register stays zero (scipy refuses to run it)
+        s2 = np.zeros(1600 + n, s1.dtype)
+    else:
+        s2 = max_len_seq(31, state=x2, length=1600 + n, taps=[1, 2, 3])[0]  # x2(n+31) = x2(n+3) + x2(n+2) + x2(n+1) + x2(n)
     return (s1[1600:] ^ s2[1600:]).astype(np.uint8)
 
 
@@ -275,3 +278,33 @@ def test_code_block_segmentation_against_python_restatement(S):
         assert S.lte_cbsegm(C.byref(s), v) == 0, v
         Cn, Kp, Km, Cp, Cm, F = check_tables.segm(v)
         assert (s.C, s.Kp, s.Cp, s.Cm, s.F) == (Cn, Kp, Cp, Cm, F) and (s.Km == Km or Cm == 0), (v, check_tables.segm(v))
+
+
+def test_pusch_dmrs_group_and_sequence_hopping_against_formulas(S):
+    """36.211 5.5.1.3 / 5.5.1.4 with the Gold bits from scipy: u = (f_gh(ns) + f_ss) mod 30 with f_gh = (sum_i c(8 ns + i) 2^i) mod 30, c_init = floor(N_id / 30);
+    without group hopping and from 6 PRB on v = c(ns), c_init = floor(N_id / 30) 2^5 + f_ss; q = floor(qbar + 1/2) + v (-1)^floor(2 qbar)"""
+    n1_map = [0, 2, 3, 4, 6, 8, 9, 10]
+    nv = 0
+    for cell_id, delta_ss, cs, n2, nprb, gh, sh in ((301, 4, 2, 3, 6, 1, 0), (77, 0, 1, 0, 12, 1, 1), (150, 9, 6, 8, 8, 0, 1), (9, 29, 0, 10, 25, 0, 1), (222, 1, 7, 2, 5, 0, 1)):
+        cell = Cell(50, 1, cell_id, 1)
+        M = 12 * nprb
+        nzc = max(p for p in range(2, M) if all(p % d for d in range(2, int(p ** 0.5) + 1)))
+        fss = ((cell_id % 30) + delta_ss) % 30
+        c_gh = gold_scipy(cell_id // 30, 8 * 20)
+        c_ss = gold_scipy((cell_id // 30) * 32 + fss, 8 * 7 * 20 + 8)
+        for ns in (0, 3, 10, 19):
+            ucfg = (C.c_uint32 * 5)(cs, delta_ss, gh, sh, 0)
+            r = np.zeros(M, np.complex64)
+            assert S.lte_pusch_dmrs(C.byref(cell), ucfg, ns, n2, M, ltelib.ptr(r)) == 0
+            fgh = sum(int(c_gh[8 * ns + i]) << i for i in range(8)) % 30 if gh else 0
+            u = (fgh + fss) % 30
+            v = int(c_ss[ns]) if (not gh and sh and M >= 72) else 0
+            nv += v
+            qbar = nzc * (u + 1) / 31.0
+            q = int(np.floor(qbar + 0.5)) + v * (-1) ** int(np.floor(2 * qbar))
+            m = np.arange(M) % nzc
+            nprs = sum(int(c_ss[8 * 7 * ns + i]) << i for i in range(8))
+            alpha = 2 * np.pi * ((n1_map[cs] + n2 + nprs) % 12) / 12
+            ref = np.exp(1j * alpha * np.arange(M)) * np.exp(-1j * np.pi * q * m * (m + 1) / nzc)
+            assert np.allclose(r, ref, atol=2e-4), (cell_id, nprb, gh, sh, ns)
+    assert nv >= 2                                                         # the second base sequence (v = 1) was exercised
