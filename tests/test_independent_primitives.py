@@ -308,3 +308,47 @@ def test_pusch_dmrs_group_and_sequence_hopping_against_formulas(S):
             ref = np.exp(1j * alpha * np.arange(M)) * np.exp(-1j * np.pi * q * m * (m + 1) / nzc)
             assert np.allclose(r, ref, atol=2e-4), (cell_id, nprb, gh, sh, ns)
     assert nv >= 2                                                         # the second base sequence (v = 1) was exercised
+
+
+def test_pusch_channel_interleaver_against_the_procedure_of_36212(S):
+    """lte_uci_map (shared by transmitter and oracle) against 36.212 5.2.2.8 written down step by step in Python: rank-indication symbols from the bottom row up
+    in columns {1, 4, 7, 10} taken in the order j = 0, 3, 2, 1; CQI then data row by row around them; HARQ-ACK symbols overwriting from the bottom row up in
+    columns {2, 3, 8, 9} in the same order"""
+    class Layout(C.Structure):
+        _fields_ = [("Qp_ack", C.c_uint32), ("Qp_ri", C.c_uint32), ("Qp_cqi", C.c_uint32), ("G", C.c_uint32)]
+    S.lte_uci_map.argtypes = [C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]
+    for M, qa, qr, qc in ((36, 0, 0, 0), (36, 5, 0, 0), (36, 0, 7, 0), (72, 9, 6, 40), (120, 33, 17, 101), (48, 4 * 48, 4 * 48, 30), (36, 1, 1, 1)):
+        R = M
+        kind = np.zeros(R * 12, np.int64)
+        pos = np.full(R * 12, -1, np.int64)
+        for cols, q, k in (((1, 4, 7, 10), qr, 2),):
+            i, j, r = 0, 0, R - 1
+            while i < q:
+                kind[r * 12 + cols[j]] = k
+                i += 1
+                r = R - 1 - i // 4
+                j = (j + 3) % 4
+        stream = [(1, i) for i in range(qc)] + [(0, i) for i in range(12 * R - qr - qc)]
+        it = iter(stream)
+        for r in range(R):
+            for c in range(12):
+                if kind[r * 12 + c] == 2:
+                    continue
+                kk, p = next(it)
+                kind[r * 12 + c], pos[r * 12 + c] = kk, p
+        under = kind.copy()
+        i, j, r = 0, 0, R - 1
+        cols = (2, 3, 8, 9)
+        while i < qa:
+            kind[r * 12 + cols[j]] = 3
+            i += 1
+            r = R - 1 - i // 4
+            j = (j + 3) % 4
+        L = Layout(qa, qr, qc, 0)
+        k_out = np.zeros(R * 12, np.uint8)
+        d_out = np.zeros(R * 12, np.uint32)
+        S.lte_uci_map(M, C.byref(L), ltelib.ptr(k_out), ltelib.ptr(d_out))
+        assert np.array_equal(k_out == 4, (kind == 3) & (under == 1))       # lte_uci_map labels an ACK symbol that punctures CQI instead of data with 4
+        assert np.array_equal(np.where(k_out == 4, 3, k_out), kind), (M, qa, qr, qc)
+        sel = (kind == 0) | (kind == 1) | ((kind == 3) & (under == 0))
+        assert np.array_equal(d_out[sel].astype(np.int64), pos[sel]), (M, qa, qr, qc)
