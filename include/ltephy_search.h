@@ -173,6 +173,11 @@ typedef struct {
  * LTEPHY_ERROR: malformed PDU; LTEPHY_ERROR_INVALID_INPUTS: null argument or more than max_out RARs. */
 int ltephy_rar_unpack(const ltephy_search_t* s, const uint8_t* pdu, uint32_t len, ltephy_rar_t* out, uint32_t max_out, uint32_t* n_out, int* backoff);
 
+/* The control-information layout ltephy_submit_ul uses for this grant (36.212 5.2.2.6 as srsRAN evaluates it, in float): modulation symbols Q' of HARQ-ACK,
+ * rank indication and CQI / PMI, and the UL-SCH bits G left for the transport block.  Any output pointer may be NULL.  LTEPHY_ERROR_INVALID_INPUTS for a
+ * grant without a size or with a reserved beta-offset index. */
+int ltephy_ul_uci_layout(const ltephy_ul_grant_t* grant, uint32_t* qp_ack, uint32_t* qp_ri, uint32_t* qp_cqi, uint32_t* G);
+
 /* Bits of the aperiodic CQI report as the reference configures it (UL_Sniffer_PUSCH.cc:434-445; no PMI, rank 1): cqi_type = srsran_cqi_type_t,
  * 0 wideband -> 4, 3 subbands configured by higher layers (the default, MCSTracking.cc:1538) -> 4 + 2 N with N = ul_sniffer_cqi_hl_get_no_subbands
  * (lib/src/phy/falcon_phch/dl_sniffer_pdsch.c:277-302).  Other types / nof_prb < 7: LTEPHY_ERROR_INVALID_INPUTS. */

@@ -381,6 +381,7 @@ def _bind_search(L):
     L.ltephy_ul_decode_plan.argtypes = [P, P, C.c_int, P, P]
     L.ltephy_rar_unpack.argtypes = [P, P, C.c_uint32, P, C.c_uint32, P, P]
     L.ltephy_ul_cqi_len.argtypes = [C.c_uint32, C.c_int]
+    L.ltephy_ul_uci_layout.argtypes = [P, P, P, P, P]
     L.ltephy_ul_grants_from_dcis.argtypes = [P, P, P, C.c_uint32, P, C.c_uint32, P, P, P, C.c_uint32, P]
     L.ltephy_decode_subframes.argtypes = [P, P, P, P, C.c_uint32, C.c_uint64, P, P, P, C.c_uint32, P, P, P, C.c_size_t]
     L.ltephy_decode_subframes_device.argtypes = [P, P, P, P, C.c_uint32, C.c_uint64, P, P, P, C.c_uint32, P, P, P, C.c_size_t]

@@ -1317,6 +1317,21 @@ int ltephy_grants_from_dcis_tc(const ltephy_search_t* s, const uint32_t* tti_cfi
                                grants, grant_dci, max_grants, n_grants);
 }
 
+// What ltephy_submit_ul reserves for the control information of a grant (36.212 5.2.2.6; srsRAN Q_prime_ri_ack / Q_prime_cqi): the numbers of modulation
+// symbols Q' of HARQ-ACK, rank indication and CQI, and the UL-SCH bits G that are left -- for a caller that sizes buffers or wants to know the code rate.
+int ltephy_ul_uci_layout(const ltephy_ul_grant_t* g, uint32_t* qp_ack, uint32_t* qp_ri, uint32_t* qp_cqi, uint32_t* G)
+{
+  if (!g || g->tbs <= 0 || g->L_prb == 0) return LTEPHY_ERROR_INVALID_INPUTS;
+  ltehost::UciLayout L;
+  if (!ltehost::uci_layout(g->L_prb, g->qm, (uint32_t)g->tbs, g->nof_ack, g->ri_len, g->cqi_len, g->I_offset_ack, g->I_offset_ri, g->I_offset_cqi, L))
+    return LTEPHY_ERROR_INVALID_INPUTS;
+  if (qp_ack) *qp_ack = L.Qp_ack;
+  if (qp_ri) *qp_ri = L.Qp_ri;
+  if (qp_cqi) *qp_cqi = L.Qp_cqi;
+  if (G) *G = L.G;
+  return LTEPHY_SUCCESS;
+}
+
 // Size of the aperiodic CQI report multiplexed into a PUSCH whose DCI-0 requests one, for the report types the reference configures
 // (UL_Sniffer_PUSCH.cc:434-445: uci_cfg.cqi.type from the UE's RRC configuration, default SRSRAN_CQI_TYPE_SUBBAND_HL, MCSTracking.cc:1538; N =
 // ul_sniffer_cqi_hl_get_no_subbands, lib/src/phy/falcon_phch/dl_sniffer_pdsch.c:277-302; no PMI, rank 1): 36.212 Tables 5.2.2.6.1-1 (wideband, 4 bits)

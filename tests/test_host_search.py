@@ -521,3 +521,48 @@ def test_ul_default_cqi_report_size(infra):
     info[0].tti, info[0].cfi = 20, 2
     out = capi.ul_grants_from_dcis(srch, info, dcis)
     assert [(rd, g.ri_len, g.cqi_len) for _, rd, g in out] == [(0, 1, 22), (2, 1, 22)]
+
+
+def test_ul_uci_layout_matches_oracle_side_and_formula(infra):
+    """ltephy_ul_uci_layout (= what ltephy_submit_ul reserves, ltehost::uci_layout) on 4 000 random grants against the simulator / oracle's lte_uci_layout (an
+    independent C restatement) and against 36.212 5.2.2.6 evaluated in Python float32: Q' = min(ceil(O M_sc N_symb beta / sum K_r), 4 M_sc) for HARQ-ACK and
+    RI, min(ceil((O + L) M_sc N_symb beta / sum K_r), M_sc N_symb - Q'_RI) with L = 8 from 12 bits on for CQI, G = (M_sc N_symb - Q'_CQI - Q'_RI) Qm"""
+    import sys as _sys
+    _sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+    import check_tables
+    L = capi.load_library()
+    capi._bind_search(L)
+    B_ACK = [2.0, 2.5, 3.125, 4.0, 5.0, 6.25, 8.0, 10.0, 12.625, 15.875, 20.0, 31.0, 50.0, 80.0, 126.0]
+    B_RI = [1.25, 1.625, 2.0, 2.5, 3.125, 4.0, 5.0, 6.25, 8.0, 10.0, 12.625, 15.875, 20.0]
+    B_CQI = [None, None, 1.125, 1.25, 1.375, 1.625, 1.75, 2.0, 2.25, 2.5, 2.875, 3.125, 3.5, 4.0, 5.0, 6.25]
+    _, _, tbs_tab, _ = check_tables.load()
+    T = np.array(tbs_tab).reshape(34, 110)
+    rng = np.random.default_rng(77)
+    valid_L = [l for l in range(1, 101) if ltelib.sim().lte_ul_valid_prb(l)]
+    f32 = np.float32
+    n = 0
+    for _ in range(4000):
+        Lp = int(rng.choice(valid_L))
+        qm = int(rng.choice([2, 4, 6, 8]))
+        tbs = int(T[int(rng.integers(0, 27)), Lp - 1])
+        nack, ri, cqi = int(rng.integers(0, 3)), int(rng.integers(0, 2)), int(rng.choice([0, 0, 4, 11, 12, 20, 30, 64]))
+        ia, ir, ic = int(rng.integers(0, 15)), int(rng.integers(0, 13)), int(rng.integers(2, 16))
+        g = capi.UlGrant(rnti=1, qm=qm, L_prb=Lp, n_prb=0, tbs=tbs, nof_ack=nack, ri_len=ri, cqi_len=cqi, I_offset_ack=ia, I_offset_cqi=ic, I_offset_ri=ir)
+        out = [C.c_uint32(0) for _ in range(4)]
+        assert L.ltephy_ul_uci_layout(C.byref(g), *[C.byref(o) for o in out]) == 0
+        got = tuple(o.value for o in out)
+        og = ltelib.UlGrant(rnti=1, L_prb=Lp, qm=qm, tbs=tbs, nof_ack=nack, ri_len=ri, cqi_len=cqi, I_offset_ack=ia, I_offset_ri=ir, I_offset_cqi=ic)
+        ol = ltelib.uci_layout(og)
+        assert got == (ol.Qp_ack, ol.Qp_ri, ol.Qp_cqi, ol.G), (Lp, qm, tbs, nack, ri, cqi)
+        Cn, Kp, Km, Cp, Cm, F = check_tables.segm(tbs)
+        ksum = f32(Cp * Kp + Cm * Km)
+        M = 12 * Lp
+        qp = lambda O, b: int(np.ceil(f32(O) * f32(M) * f32(12) * f32(b) / ksum))
+        q_ri = min(qp(ri, B_RI[ir]), 4 * M) if ri else 0
+        q_ack = min(qp(nack, B_ACK[ia]), 4 * M) if nack else 0
+        q_cqi = min(qp(cqi + (8 if cqi > 11 else 0), B_CQI[ic]), 12 * M - q_ri) if cqi else 0
+        assert got == (q_ack, q_ri, q_cqi, (12 * M - q_cqi - q_ri) * qm), (Lp, qm, tbs, nack, ri, cqi, got)
+        n += bool(nack or ri or cqi)
+    assert n > 2500
+    g = capi.UlGrant(rnti=1, qm=2, L_prb=10, tbs=1000, cqi_len=20, I_offset_cqi=1)
+    assert L.ltephy_ul_uci_layout(C.byref(g), None, None, None, None) == -2           # reserved beta offset index
