@@ -213,7 +213,8 @@ typedef struct {
   uint8_t  nof_ports;       /* 1, 2 or 4: from the CRC mask */
   uint8_t  sfn_offset;      /* position of this frame in the 40 ms PBCH period = SFN mod 4 */
   uint8_t  phich_length;    /* 0 normal, 1 extended    (srsran_cell_t.phich_length) */
-  uint8_t  phich_resources; /* 0: 1/6, 1: 1/2, 2: 1, 3: 2 (srsran_cell_t.phich_resources) */
+  uint8_t  phich_resources; /* 0: 1/6, 1: 1/2, 2: 1, 3: 2 (srsran_cell_t.phich_resources); the value to create the decoding handle with
+                               (ltephy_cfg_t.phich_resources), as the reference's live mode does through srsran_pbch_mib_unpack + srsran_ue_dl_set_cell */
   uint8_t  bch_payload[3];  /* the 24 MIB bits, first bit in bit 7 of byte 0 (bch_payload of srsran_ue_mib_decode, packed) */
   uint32_t nof_prb;         /* 6, 15, 25, 50, 75, 100 */
   uint32_t sfn;             /* (8 MSBs << 2) + sfn_offset, as LTESniffer_Core.cc:390-392 computes it */
