@@ -227,7 +227,7 @@ uint32_t srsran_re_x_prb(uint32_t ns, uint32_t symbol, uint32_t nof_ports, uint3
 uint32_t srsran_max_cce(uint32_t nof_prb) { return nof_prb <= 6 ? 7 : nof_prb <= 15 ? 20 : nof_prb <= 25 ? 21 : nof_prb <= 50 ? 43 : nof_prb <= 75 ? 65 : 87; }
 
 // ---------------------------------------------------------------------------------------------------- dci.c
-static ltehost::Cell host_cell(const srsran_cell_t* c) { return ltehost::Cell{c->nof_prb, c->nof_ports, c->id, 1, (uint32_t)c->phich_resources}; }
+static ltehost::Cell host_cell(const srsran_cell_t* c) { return ltehost::Cell{c->nof_prb, c->nof_ports, c->id, 1, (uint32_t)c->phich_resources, (uint32_t)c->phich_length}; }
 // srsran_dci_format_sizeof (falcon_pdcch.c:133): payload bits of a format for this cell (FDD, no carrier indicator, no SRS request)
 uint32_t srsran_dci_format_sizeof(const srsran_cell_t* cell, srsran_dl_sf_cfg_t* sf, srsran_dci_cfg_t* cfg, srsran_dci_format_t format)
 {

@@ -61,11 +61,11 @@ int srsran_ue_dl_set_cell(srsran_ue_dl_t* q, srsran_cell_t cell)
 {
   DlPriv* p = P(q);
   if (!p || cell.cp != SRSRAN_CP_NORM || cell.nof_prb < 15 || cell.nof_prb > 100 || cell.nof_ports < 1 || cell.nof_ports > 2) return SRSRAN_ERROR_INVALID_INPUTS;
-  if (cell.phich_length != SRSRAN_PHICH_NORM || (uint32_t)cell.phich_resources > 3) return SRSRAN_ERROR_INVALID_INPUTS; // extended PHICH duration is not built
+  if ((uint32_t)cell.phich_length > 1 || (uint32_t)cell.phich_resources > 3) return SRSRAN_ERROR_INVALID_INPUTS;
   if (p->phy) ltephy_destroy(p->phy), p->phy = nullptr;
   // geometry from the host tables only: the CUDA handle is created with the first subframe that is really decoded, so a search
   // fed with ltephy_compat_inject needs no GPU
-  const ltehost::Cell hc{cell.nof_prb, cell.nof_ports, cell.id, q->nof_rx_antennas, (uint32_t)cell.phich_resources};
+  const ltehost::Cell hc{cell.nof_prb, cell.nof_ports, cell.id, q->nof_rx_antennas, (uint32_t)cell.phich_resources, (uint32_t)cell.phich_length};
   ltehost::CtrlMap    cm;
   if (!ltehost::build_ctrl_map(hc, cm)) return SRSRAN_ERROR;
   p->st     = ltehost::dci_size_table(hc);
@@ -141,7 +141,7 @@ int srsran_ue_dl_decode_fft_estimate(srsran_ue_dl_t* q, srsran_dl_sf_cfg_t* sf, 
   if (!p->phy) {
     ltephy_cfg_t c{};
     c.nof_prb = q->cell.nof_prb, c.nof_ports = q->cell.nof_ports, c.cell_id = q->cell.id, c.nof_rx = q->nof_rx_antennas;
-    c.phich_resources = (uint32_t)q->cell.phich_resources;
+    c.phich_resources = (uint32_t)q->cell.phich_resources, c.phich_length = (uint32_t)q->cell.phich_length;
     c.max_subframes = 1, c.turbo_max_iter = 8, c.flags = 0; // every location is decoded: the caller decides which ones it asks for
     c.symbol_sz = p->symbol_sz;                             // what srsran_symbol_sz() says (standard or 3/4 rate)
     if (ltephy_create(&c, &p->phy) != LTEPHY_SUCCESS) return SRSRAN_ERROR;

@@ -54,8 +54,9 @@ typedef struct {
                               samples 25 / 50 / 100 PRB at 3/4 of that (384 / 768 / 1536, srsran_symbol_sz): pass that value then. */
   uint32_t phich_resources; /* phich-Resource of the MIB as srsran_phich_r_t (srsran_cell_t.phich_resources): 0 = Ng 1/6 (what the reference presets in file
                                mode, src/src/LTESniffer_Core.cc:242-247), 1 = 1/2, 2 = 1, 3 = 2.  Sets the PHICH groups of symbol 0 and with them the
-                               CCE grid of the PDCCH.  Normal PHICH duration only. */
-  uint32_t reserved[5];
+                               CCE grid of the PDCCH. */
+  uint32_t phich_length;    /* phich-Duration of the MIB (srsran_cell_t.phich_length): 0 normal, 1 extended (PHICH REGs in symbols 0, 1 and 2) */
+  uint32_t reserved[4];
 } ltephy_cfg_t;
 
 #define LTEPHY_FLAG_SKIP_LOW_POWER 1u /* do not decode locations covering a CCE with mean|LLR| < 0.7 (they are never consulted) */

@@ -47,9 +47,10 @@ enum { LTEPHY_ACT_UNSET = 0, LTEPHY_ACT_EVERGREEN, LTEPHY_ACT_RAR, LTEPHY_ACT_SH
 
 /* geometry helper used by the search (implemented next to the PHY handle) */
 void ltephy_cell_of(const ltephy_t* h, uint32_t* nof_prb, uint32_t* nof_ports, uint32_t* cell_id, uint32_t* nof_rx);
-uint32_t ltephy_phich_resources(const ltephy_t* h);
+uint32_t ltephy_phich_resources(const ltephy_t* h); /* phich_resources | phich_length << 8 of the handle's configuration */
 /* the control region as the PHY maps it: pdcch_idx[nof_cce * 36] = grid index l * 12 nof_prb + k of every RE of the PDCCH in CCE order for this CFI (what
- * srsran_pdcch_extract_llr walks; 36.211 6.8.5), pcfich_idx[16] the PCFICH REs; either may be NULL.  cap = room in pdcch_idx (uint16 elements). */
+ * srsran_pdcch_extract_llr walks; 36.211 6.8.5), pcfich_idx[16] the PCFICH REs; either may be NULL.  cap = room in pdcch_idx (uint16 elements).
+ * phich_resources as for ltephy_search_create_cell_ng (| phich_length << 8). */
 int ltephy_ctrl_region_map(uint32_t nof_prb, uint32_t nof_ports, uint32_t cell_id, uint32_t phich_resources, uint32_t cfi, uint16_t* pdcch_idx, uint32_t cap,
                            uint32_t* nof_cce, uint16_t* pcfich_idx);
 
@@ -59,7 +60,8 @@ int ltephy_ctrl_region_map(uint32_t nof_prb, uint32_t nof_ports, uint32_t cell_i
 ltephy_search_t* ltephy_search_create(const ltephy_t* h, uint32_t histogram_threshold);
 /* same without a GPU handle (host-only use: unit tests, or a search running beside a remote PHY) */
 ltephy_search_t* ltephy_search_create_cell(uint32_t nof_prb, uint32_t nof_ports, uint32_t cell_id, uint32_t nof_rx, uint32_t histogram_threshold);
-/* same for a cell whose MIB announces another PHICH resource than 1/6 (ltephy_cfg_t.phich_resources): the CCE counts per CFI follow from it */
+/* same for a cell whose MIB announces another PHICH configuration than Ng = 1/6, normal duration: the CCE counts per CFI follow from it.
+ * phich_resources: ltephy_cfg_t.phich_resources | ltephy_cfg_t.phich_length << 8 */
 ltephy_search_t* ltephy_search_create_cell_ng(uint32_t nof_prb, uint32_t nof_ports, uint32_t cell_id, uint32_t nof_rx, uint32_t phich_resources,
                                               uint32_t histogram_threshold);
 void             ltephy_search_destroy(ltephy_search_t* s);

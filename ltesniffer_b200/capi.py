@@ -17,7 +17,7 @@ FLAG_SKIP_LOW_POWER = 1
 class Cfg(C.Structure):
     _fields_ = [("nof_prb", C.c_uint32), ("nof_ports", C.c_uint32), ("cell_id", C.c_uint32), ("nof_rx", C.c_uint32),
                 ("max_subframes", C.c_uint32), ("max_grants", C.c_uint32), ("turbo_max_iter", C.c_uint32), ("device", C.c_int32),
-                ("flags", C.c_uint32), ("symbol_sz", C.c_uint32), ("phich_resources", C.c_uint32), ("reserved", C.c_uint32 * 5)]
+                ("flags", C.c_uint32), ("symbol_sz", C.c_uint32), ("phich_resources", C.c_uint32), ("phich_length", C.c_uint32), ("reserved", C.c_uint32 * 4)]
 
 
 class SfInfo(C.Structure):
@@ -149,10 +149,10 @@ def _p(a):
 class LtePhy:
     """One PHY context (cell + batch capacity) on one GPU."""
 
-    def __init__(self, nof_prb, nof_ports, cell_id, nof_rx, max_subframes=16, turbo_max_iter=8, device=0, flags=0, symbol_sz=0, phich_resources=0):
+    def __init__(self, nof_prb, nof_ports, cell_id, nof_rx, max_subframes=16, turbo_max_iter=8, device=0, flags=0, symbol_sz=0, phich_resources=0, phich_length=0):
         self.L = load_library()
         cfg = Cfg(nof_prb=nof_prb, nof_ports=nof_ports, cell_id=cell_id, nof_rx=nof_rx, max_subframes=max_subframes,
-                  turbo_max_iter=turbo_max_iter, device=device, flags=flags, symbol_sz=symbol_sz, phich_resources=phich_resources)
+                  turbo_max_iter=turbo_max_iter, device=device, flags=flags, symbol_sz=symbol_sz, phich_resources=phich_resources, phich_length=phich_length)
         self.cfg = cfg
         self.h = C.c_void_p()
         r = self.L.ltephy_create(C.byref(cfg), C.byref(self.h))

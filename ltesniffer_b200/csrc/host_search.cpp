@@ -1006,7 +1006,7 @@ int ltephy_ctrl_region_map(uint32_t nof_prb, uint32_t nof_ports, uint32_t cell_i
 {
   if (cfi < 1 || cfi > 3 || !nof_cce) return LTEPHY_ERROR_INVALID_INPUTS;
   ltehost::CtrlMap cm;
-  if (!ltehost::build_ctrl_map(ltehost::Cell{nof_prb, nof_ports, cell_id, 1, phich_resources}, cm)) return LTEPHY_ERROR_INVALID_INPUTS;
+  if (!ltehost::build_ctrl_map(ltehost::Cell{nof_prb, nof_ports, cell_id, 1, phich_resources & 0xFFu, phich_resources >> 8}, cm)) return LTEPHY_ERROR_INVALID_INPUTS;
   *nof_cce = cm.nof_cce[cfi - 1];
   if (pdcch_idx) {
     if (cap < cm.pdcch_idx[cfi - 1].size()) return LTEPHY_ERROR_INVALID_INPUTS;
@@ -1023,7 +1023,7 @@ ltephy_search_t* ltephy_search_create_cell_ng(uint32_t nof_prb, uint32_t nof_por
                                               uint32_t histogram_threshold)
 {
   ltehost::CtrlMap cm;
-  ltehost::Cell    cell{nof_prb, nof_ports, cell_id, nof_rx, phich_resources};
+  ltehost::Cell    cell{nof_prb, nof_ports, cell_id, nof_rx, phich_resources & 0xFFu, phich_resources >> 8};
   if (!ltehost::build_ctrl_map(cell, cm)) return nullptr;
   ltephy_search* s = new ltephy_search();
   s->cell          = cell;

@@ -117,7 +117,7 @@ struct Reg {
 
 bool build_ctrl_map(const Cell& c, CtrlMap& out)
 {
-  if (c.nof_prb <= 10 || c.nof_prb > 110 || c.nof_ports < 1 || c.nof_ports > 2 || c.phich_ng > 3) return false;
+  if (c.nof_prb <= 10 || c.nof_prb > 110 || c.nof_ports < 1 || c.nof_ports > 2 || c.phich_ng > 3 || c.phich_ext > 1) return false;
   const uint32_t   nsc = 12 * c.nof_prb, v3 = c.cell_id % 3;
   std::vector<Reg> regs;
   uint32_t         sym_base[4] = {0, 0, 0, 0};
@@ -155,8 +155,18 @@ bool build_ctrl_map(const Cell& c, CtrlMap& out)
     static const uint32_t ng_x6[4] = {1, 3, 6, 12};
     const uint32_t        n0 = (uint32_t)free0.size(), ngroups = (ng_x6[c.phich_ng] * c.nof_prb + 47) / 48;
     if (3 * ngroups > n0) return false;
-    for (uint32_t m = 0; m < ngroups; m++)
-      for (uint32_t i = 0; i < 3; i++) regs[free0[(c.cell_id + m + i * n0 / 3) % n0]].kind = 2;
+    if (!c.phich_ext) {
+      for (uint32_t m = 0; m < ngroups; m++)
+        for (uint32_t i = 0; i < 3; i++) regs[free0[(c.cell_id + m + i * n0 / 3) % n0]].kind = 2;
+    } else { // extended duration, ordinary FDD subframes (36.211 6.9.3): quadruplet i of a group goes to symbol l' = i, to the REG numbered
+             // (floor(N_id n_l' / n_0) + m' + floor(i n_l' / 3)) mod n_l' among the n_l' REGs of that symbol that do not carry the PCFICH
+      for (uint32_t m = 0; m < ngroups; m++)
+        for (uint32_t i = 0; i < 3; i++) {
+          const uint32_t nl = i == 0 ? n0 : sym_base[i + 1] - sym_base[i];
+          const uint32_t ni = (uint32_t)(((uint64_t)c.cell_id * nl / n0 + m + i * nl / 3) % nl);
+          regs[i == 0 ? free0[ni] : sym_base[i] + ni].kind = 2;
+        }
+    }
   }
   for (uint32_t cfi = 1; cfi <= 3; cfi++) {
     std::vector<uint32_t> F;

@@ -12,7 +12,8 @@ namespace ltehost {
 
 struct Cell {
   uint32_t nof_prb = 0, nof_ports = 1, cell_id = 0, nof_rx = 1;
-  uint32_t phich_ng = 0; // phich-Resource of the MIB as srsran_phich_r_t: 0 = 1/6, 1 = 1/2, 2 = 1, 3 = 2 (normal PHICH duration)
+  uint32_t phich_ng = 0;  // phich-Resource of the MIB as srsran_phich_r_t: 0 = 1/6, 1 = 1/2, 2 = 1, 3 = 2
+  uint32_t phich_ext = 0; // phich-Duration of the MIB: 0 normal (symbol 0), 1 extended (one REG of every group in each of symbols 0, 1, 2)
 };
 
 // ---- numerology

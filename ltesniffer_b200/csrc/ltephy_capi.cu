@@ -103,8 +103,9 @@ extern "C" int ltephy_create(const ltephy_cfg_t* cfg, ltephy_t** out)
   h->cfg    = *cfg;
   if (!h->cfg.turbo_max_iter) h->cfg.turbo_max_iter = 8;
   if (!h->cfg.max_grants) h->cfg.max_grants = 24 * cfg->max_subframes;
-  if (cfg->phich_resources > 3) return fail(LTEPHY_ERROR_INVALID_INPUTS, "phich_resources %u: 0 (Ng = 1/6), 1 (1/2), 2 (1) or 3 (2)", cfg->phich_resources);
-  h->cell = {cfg->nof_prb, cfg->nof_ports, cfg->cell_id, cfg->nof_rx, cfg->phich_resources};
+  if (cfg->phich_resources > 3 || cfg->phich_length > 1)
+    return fail(LTEPHY_ERROR_INVALID_INPUTS, "phich_resources %u / phich_length %u: 0 (Ng = 1/6), 1 (1/2), 2 (1) or 3 (2); 0 normal or 1 extended", cfg->phich_resources, cfg->phich_length);
+  h->cell = {cfg->nof_prb, cfg->nof_ports, cfg->cell_id, cfg->nof_rx, cfg->phich_resources, cfg->phich_length};
   if (!ltehost::build_ctrl_map(h->cell, h->cm)) return fail(LTEPHY_ERROR_INVALID_INPUTS, "control region map failed");
   h->st = ltehost::dci_size_table(h->cell);
   memset(h->rm_fast, 0xFF, sizeof(h->rm_fast));
@@ -306,7 +307,7 @@ extern "C" void ltephy_cell_of(const ltephy_t* h, uint32_t* a, uint32_t* b, uint
 {
   *a = h->cell.nof_prb, *b = h->cell.nof_ports, *c = h->cell.cell_id, *d = h->cell.nof_rx;
 }
-extern "C" uint32_t ltephy_phich_resources(const ltephy_t* h) { return h ? h->cell.phich_ng : 0; }
+extern "C" uint32_t ltephy_phich_resources(const ltephy_t* h) { return h ? h->cell.phich_ng | (h->cell.phich_ext << 8) : 0; }
 extern "C" int ltephy_mark(ltephy_t* h, int slot)
 {
   if (!h || slot < 0 || slot > 1) return LTEPHY_ERROR_INVALID_INPUTS;

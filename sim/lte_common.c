@@ -87,7 +87,7 @@ int lte_regs_init(lte_regs_t* r, const lte_cell_t* cell)
 {
   memset(r, 0, sizeof(*r));
   r->cell = *cell;
-  if (cell->nof_prb <= 10 || cell->nof_prb > LTE_MAX_PRB || cell->nof_ports < 1 || cell->nof_ports > 2 || cell->phich_ng > 3) return -1;
+  if (cell->nof_prb <= 10 || cell->nof_prb > LTE_MAX_PRB || cell->nof_ports < 1 || cell->nof_ports > 2 || cell->phich_ng > 3 || cell->phich_ext > 1) return -1;
   uint32_t n = 0, vs3 = cell->cell_id % 3;
   for (uint32_t l = 0; l < 3; l++) {
     uint32_t cnt = 0;
@@ -129,9 +129,15 @@ int lte_regs_init(lte_regs_t* r, const lte_cell_t* cell)
   if (3 * r->nof_phich_groups > n0 || r->nof_phich_groups > 28) return -2;
   for (uint32_t m = 0; m < r->nof_phich_groups; m++)
     for (uint32_t i = 0; i < 3; i++) {
-      uint32_t ni                       = (cell->cell_id + m + (i * n0) / 3) % n0;
-      r->regs[idx0[ni]].kind            = 2;
-      r->phich_reg[3 * m + i]           = idx0[ni];
+      uint32_t reg;
+      if (!cell->phich_ext || i == 0) { /* symbol 0: the REGs that do not carry the PCFICH, numbered upwards in frequency */
+        reg = idx0[(cell->cell_id + m + (i * n0) / 3) % n0];
+      } else { /* extended duration (36.211 6.9.3, FDD, no MBSFN): quadruplet i in symbol i, every REG of that symbol counts */
+        uint32_t first = r->nof_regs_sym[0] + (i == 2 ? r->nof_regs_sym[1] : 0), nl = r->nof_regs_sym[i];
+        reg            = first + (uint32_t)(((uint64_t)cell->cell_id * nl / n0 + m + (i * nl) / 3) % nl);
+      }
+      r->regs[reg].kind       = 2;
+      r->phich_reg[3 * m + i] = reg;
     }
   /* PDCCH REG order and interleaver, 36.211 6.8.5 */
   for (uint32_t cfi = 1; cfi <= 3; cfi++) {

@@ -33,7 +33,8 @@ typedef struct {
   uint32_t nof_rx;    /* rx antennas 1 or 2 */
   uint32_t symbol_sz; /* FFT size; 0 = the standard LTE rate (2048 at 100 PRB).  srsRAN's default build samples at 3/4 of it
                          (srsran_symbol_sz: 1536 at 100 PRB, 768 at 50, 384 at 25), which is what LTESniffer records with */
-  uint32_t phich_ng;  /* phich-Resource of the MIB as srsran_phich_r_t: 0 = Ng 1/6, 1 = 1/2, 2 = 1, 3 = 2; normal PHICH duration */
+  uint32_t phich_ng;  /* phich-Resource of the MIB as srsran_phich_r_t: 0 = Ng 1/6, 1 = 1/2, 2 = 1, 3 = 2 */
+  uint32_t phich_ext; /* phich-Duration of the MIB: 0 normal, 1 extended */
 } lte_cell_t;
 
 /* numerology */

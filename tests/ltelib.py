@@ -15,7 +15,7 @@ SIM_MAX_DCI = 32
 
 class Cell(C.Structure):
     _fields_ = [("nof_prb", C.c_uint32), ("nof_ports", C.c_uint32), ("cell_id", C.c_uint32), ("nof_rx", C.c_uint32), ("symbol_sz", C.c_uint32),
-                ("phich_ng", C.c_uint32)]
+                ("phich_ng", C.c_uint32), ("phich_ext", C.c_uint32)]
 
     def fft(self):
         """symbol size: symbol_sz, or the standard LTE size when it is 0"""

@@ -5,7 +5,8 @@ built on the host and uploaded as a table (the kernels only gather through it), 
   * group and CCE counts against the closed forms of 36.211 6.9 / 6.8.1,
   * the product's map (ltephy_ctrl_region_map) against the oracle's (an independent C restatement in sim/lte_common.c), RE by RE, for every Ng / CFI,
   * the synthetic eNB -> oracle receiver loop at Ng = 1/2, 1 and 2 (every DCI found again),
-  * Ng = 1/6 is the zero value of the field: nothing changes for existing callers."""
+  * Ng = 1/6 is the zero value of the field: nothing changes for existing callers,
+  * the same for phich-Duration extended (ltephy_cfg_t.phich_length; REGs of every group in symbols 0, 1 and 2)."""
 import ctypes as C
 import math
 import numpy as np
@@ -17,13 +18,13 @@ from ltesniffer_b200 import capi
 NG = {0: 1 / 6, 1: 1 / 2, 2: 1.0, 3: 2.0}
 
 
-def product_map(cellp, ng, cfi):
+def product_map(cellp, ng, cfi, ext=0):
     L = capi.load_library()
     capi._bind_search(L)
     idx = np.zeros(88 * 36, np.uint16)
     pc = np.zeros(16, np.uint16)
     n = C.c_uint32(0)
-    r = L.ltephy_ctrl_region_map(cellp[0], cellp[1], cellp[2], ng, cfi, idx.ctypes.data_as(C.c_void_p), len(idx), C.byref(n), pc.ctypes.data_as(C.c_void_p))
+    r = L.ltephy_ctrl_region_map(cellp[0], cellp[1], cellp[2], ng | (ext << 8), cfi, idx.ctypes.data_as(C.c_void_p), len(idx), C.byref(n), pc.ctypes.data_as(C.c_void_p))
     assert r == 0, (cellp, ng, cfi, r)
     return n.value, idx[:36 * n.value].copy(), pc
 
@@ -102,3 +103,50 @@ def test_transmitter_to_oracle_loop_with_other_phich_resources(infra, ng):
                 else:
                     found16 += ok
     assert total >= 15 and found == total and found16 < total // 2, (total, found, found16)
+
+
+@pytest.mark.parametrize("cellp", [(100, 2, 301, 2), (75, 2, 17, 2), (50, 1, 9, 1), (25, 2, 150, 2), (15, 1, 503, 1)])
+def test_extended_phich_duration_map_equals_oracle(infra, cellp):
+    """phich-Duration extended: one REG of every PHICH group in each of the first three symbols (36.211 6.9.3), so symbol 0 loses one REG per group instead of
+    three and symbols 1 and 2 one each: CCE counts by closed form, the product's map against the oracle's RE by RE for every Ng and CFI"""
+    O = infra.oracle()
+    O.lteo_pdcch_re_index.restype = C.c_uint32
+    O.lteo_pdcch_re_index.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]
+    nprb = cellp[0]
+    for ng in range(4):
+        o = Oracle(Cell(*cellp, 0, ng, 1))
+        groups = math.ceil(NG[ng] * nprb / 8 - 1e-9)
+        for cfi in (1, 2, 3):
+            nregs = nprb * (2 + (3 if cfi >= 2 else 0) + (3 if cfi >= 3 else 0))
+            want_cce = (nregs - 4 - cfi * groups) // 9                      # one PHICH REG per group in each symbol of the control region
+            n, idx, pc = product_map(cellp, ng, cfi, ext=1)
+            assert n == want_cce == O.lteo_nof_cce(o.h, cfi), (cellp, ng, cfi, n, want_cce)
+            oidx = np.zeros(88 * 36, np.uint16)
+            opc = np.zeros(16, np.uint16)
+            assert O.lteo_pdcch_re_index(o.h, cfi, ltelib.ptr(oidx), ltelib.ptr(opc)) == n
+            assert np.array_equal(idx, oidx[:36 * n]) and np.array_equal(pc, opc), (cellp, ng, cfi)
+            assert len(set(idx.tolist())) == len(idx) and not set(idx.tolist()) & set(pc.tolist())
+            if cfi == 3 and groups:
+                assert not np.array_equal(idx, product_map(cellp, ng, cfi, ext=0)[1])      # a different grid than with the normal duration
+
+
+def test_transmitter_to_oracle_loop_with_extended_phich(infra):
+    from helpers import make_capture
+    cell = Cell(50, 2, 21, 2, 0, 2, 1)                                       # Ng = 1, extended duration, CFI 3 (the duration is the lower bound of the CFI)
+    sim, iq, tti, truths, payloads = make_capture(cell, 5, seed=40, cfi=3, nof_ues=6, dl_min=3, dl_max=5, tm=2, mcs_min=4, mcs_max=12, snr_db=25.0)
+    o = Oracle(cell)
+    found = total = 0
+    for sf in range(5):
+        sym = o.ofdm(iq[sf])
+        ce, res = o.chest(int(tti[sf]) % 10, sym)
+        cfi, corr = o.pcfich(int(tti[sf]) % 10, sym, ce)
+        assert cfi == 3
+        llr = o.pdcch_llr(int(tti[sf]) % 10, cfi, sym, ce)
+        for i in range(truths[sf].nof_dci):
+            d = truths[sf].dci[i]
+            total += 1
+            r, bits, crc = o.dci_decode(llr[72 * d.ncce:72 * (d.ncce + (1 << d.L))], d.nbits)
+            found += r == 0 and crc == d.rnti and np.array_equal(bits, np.frombuffer(bytes(d.bits), np.uint8)[:d.nbits])
+    assert total >= 12 and found == total, (total, found)
+    L = capi.load_library()
+    assert L.ltephy_search_create_cell_ng(50, 2, 21, 2, 2 | (1 << 8), 5) and L.ltephy_search_create_cell_ng(50, 2, 21, 2, 2 | (2 << 8), 5) is None
