@@ -11,9 +11,13 @@
  *       tail-biting Viterbi (3 concatenated copies, uint8 quantisation with gain 32), CRC16
  *   srsran_ue_dl_decode_pdsch (src/src/DL_Sniffer_PDSCH.cc:997): RE gather, predecoding, soft demod,
  *       descrambling, turbo rate-dematch, max-log-MAP turbo decode, CRC24B/CRC24A
- * -- from 3GPP TS 36.211/212/213 and the in-tree glue.  It is pinned by (i) ground truth from the
- * synthetic eNB in sim/ (CRC-self-validating), (ii) 3GPP structural checks (tests/test_tables.py)
- * and (iii) the reference's own RNTIManager compiled into oracle/_ref (tests/test_rnti_manager.py).
+ * -- from 3GPP TS 36.211/212/213 and the in-tree glue.  The signal arithmetic therefore stays PARITY UNPINNED by the reference; what
+ * stands in for it: (i) ground truth from the synthetic eNB in sim/ (CRC-self-validating), (ii) 3GPP structural checks of the tables and the
+ * transport block sizes of the reference's example captures (tests/test_tables.py), (iii) the primitives this receiver SHARES with that
+ * transmitter (sim/lte_common.c: CRCs, Gold sequences, CRS, encoders, rate matching, constellations, DMRS, interleavers, OFDM numerology)
+ * checked against third-party code and other-domain formulations (tests/test_independent_primitives.py), so that a shared mistake cannot
+ * cancel out.  The DECISION logic around it (search walk, grants, RAR, HARQ bookkeeping, trace lines) is pinned on the reference's own code
+ * compiled into oracle/_ref (tests/test_reference_code.py, tests/test_rnti_manager.py).
  *
  * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
  * load this library.  Every float expression below has a fixed evaluation order (build with
