@@ -196,7 +196,8 @@ typedef struct {
 /* UL mode, whole batch: the accepted DCIs of a batch of downlink subframes -> the PUSCH decode attempts to submit 4 subframes later
  * (SubframeWorker.cc:296-345: nof_ack from the downlink DCIs of the same RNTI and subframe; ULSchedule's n + 4; UL_Sniffer_PUSCH.cc:417-570: validity
  * filter, CSI request, attempt order).  grants[k].sf = dcis[grant_dci[k]].sf + 4 (indices >= the batch length belong to the next uplink batch);
- * reading[k] = the enable_64qam value of attempt k; the attempts of one DCI are adjacent and in the reference's order -- keep the first whose CRC passes. */
+ * reading[k] = the enable_64qam value of attempt k; the attempts of one DCI are adjacent and in the reference's order -- keep the first whose CRC passes.
+ * dcis[] as the search returns them (the DCIs of one subframe adjacent). */
 int ltephy_ul_grants_from_dcis(const ltephy_search_t* s, const ltephy_sf_info_t* info, const ltephy_dci_t* dcis, uint32_t nd, const ltephy_ul_ue_cfg_t* ue,
                                uint32_t n_ue, ltephy_ul_grant_t* grants, uint32_t* grant_dci, uint8_t* reading, uint32_t max_grants, uint32_t* n_grants);
 

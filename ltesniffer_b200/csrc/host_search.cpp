@@ -1373,9 +1373,12 @@ int ltephy_ul_grants_from_dcis(const ltephy_search_t* s, const ltephy_sf_info_t*
     if (n < 0) return n;
     if (n == 0) continue;
     uint8_t nof_ack = 0;
-    for (uint32_t j = 0; j < nd; j++) { // the accepted DCIs of one subframe are adjacent, but nothing here relies on it
+    uint32_t lo = i, hi = i + 1; // the accepted DCIs of one subframe are adjacent (the search emits subframe after subframe)
+    while (lo > 0 && dcis[lo - 1].sf == d.sf) lo--;
+    while (hi < nd && dcis[hi].sf == d.sf) hi++;
+    for (uint32_t j = lo; j < hi; j++) {
       const ltephy_dci_t& dl = dcis[j];
-      if (dl.sf != d.sf || dl.format == ltehost::F0 || dl.rnti != d.rnti) continue;
+      if (dl.format == ltehost::F0 || dl.rnti != d.rnti) continue;
       ltephy_grant_t gd;
       const int      r = ltephy_dci_to_grant(s, &dl, info[dl.sf].tti % 10, info[dl.sf].cfi, 0, &gd, nullptr);
       // a DCI whose conversion fails has its RNTI zeroed by the reference (falcon_dci.c:286-305); the MIMO checks come later, in the decoder
