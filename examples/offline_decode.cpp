@@ -4,6 +4,7 @@
 // DCI trace.  Host code only; every computation happens in the library (there is no CPU fallback: without a GPU ltephy_create fails).
 //
 //   offline_decode <iq.cf32> <nof_prb> <nof_ports> <cell_id> <nof_rx> <out.pcap> <out_dci.tsv> [batch=500] [first_tti=0] [speculate_256qam=0]
+//                  [phich_resources=0] [phich_length=0]      (the MIB's PHICH configuration; the reference's file mode presets 1/6, normal)
 //
 // File layout: subframe after subframe, antenna after antenna, lte sf_len complex float32 samples each (what
 // srsran_filesource_read_multi hands SubframeWorker, src/src/SubframeWorker.cc:89).
@@ -27,6 +28,7 @@ int main(int argc, char** argv)
   uint32_t       tti       = argc > 9 ? (uint32_t)atoi(argv[9]) : 0;
   const int      speculate = argc > 10 ? atoi(argv[10]) : 0;
   cfg.max_subframes = B, cfg.turbo_max_iter = 8, cfg.flags = LTEPHY_FLAG_SKIP_LOW_POWER;
+  cfg.phich_resources = argc > 11 ? (uint32_t)atoi(argv[11]) : 0, cfg.phich_length = argc > 12 ? (uint32_t)atoi(argv[12]) : 0;
 
   ltephy_t* phy = nullptr;
   if (ltephy_create(&cfg, &phy) != LTEPHY_SUCCESS) {
