@@ -73,11 +73,17 @@ struct refwalk {
 
 extern "C" {
 
+refwalk* refwalk_create_phich(uint32_t nof_prb, uint32_t nof_ports, uint32_t cell_id, uint32_t nof_rx, uint32_t threshold, uint32_t phich_resources, uint32_t phich_length);
 refwalk* refwalk_create(uint32_t nof_prb, uint32_t nof_ports, uint32_t cell_id, uint32_t nof_rx, uint32_t threshold)
+{
+  return refwalk_create_phich(nof_prb, nof_ports, cell_id, nof_rx, threshold, SRSRAN_PHICH_R_1_6, SRSRAN_PHICH_NORM); // file mode, LTESniffer_Core.cc:242-247
+}
+// the cell as the live mode gets it from the MIB (srsran_pbch_mib_unpack, LTESniffer_Core.cc:389)
+refwalk* refwalk_create_phich(uint32_t nof_prb, uint32_t nof_ports, uint32_t cell_id, uint32_t nof_rx, uint32_t threshold, uint32_t phich_resources, uint32_t phich_length)
 {
   refwalk* w           = new refwalk();
   w->cell.nof_prb      = nof_prb, w->cell.nof_ports = nof_ports, w->cell.id = cell_id, w->cell.cp = SRSRAN_CP_NORM;
-  w->cell.phich_length = SRSRAN_PHICH_NORM, w->cell.phich_resources = SRSRAN_PHICH_R_1_6; // file mode, LTESniffer_Core.cc:242-247
+  w->cell.phich_length = (srsran_phich_length_t)phich_length, w->cell.phich_resources = (srsran_phich_r_t)phich_resources;
   static cf_t dummy[2][4];
   w->in[0] = dummy[0], w->in[1] = dummy[1];
   if (srsran_ue_dl_init(&w->q, w->in, nof_prb, nof_rx) || srsran_ue_dl_set_cell(&w->q, w->cell)) {

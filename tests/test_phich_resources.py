@@ -150,3 +150,43 @@ def test_transmitter_to_oracle_loop_with_extended_phich(infra):
     assert total >= 12 and found == total, (total, found)
     L = capi.load_library()
     assert L.ltephy_search_create_cell_ng(50, 2, 21, 2, 2 | (1 << 8), 5) and L.ltephy_search_create_cell_ng(50, 2, 21, 2, 2 | (2 << 8), 5) is None
+
+
+@pytest.mark.parametrize("ng,ext,cfi", [(2, 0, 2), (3, 0, 3), (1, 1, 3)])
+def test_reference_walk_through_the_compat_layer_with_the_mibs_phich_configuration(infra, ng, ext, cfi):
+    """tier 2 with a cell as the reference's live mode gets it from the MIB: the reference's own DCISearch.cc runs on srsran_ue_dl_set_cell(cell with
+    phich_resources / phich_length) of the compat layer and walks the locations of THAT CCE grid; the product search created with the same configuration must
+    accept the same DCIs on the same candidate tables (synthetic eNB with this configuration -> oracle -> tables)"""
+    import os as _os
+    from test_reference_code import RefWalk, reflib, phase_a_oracle, REF_SO
+    from test_host_search import host_geometry
+    if not (_os.path.exists(REF_SO) or _os.path.isdir("/root/reference")):
+        pytest.skip("reference sources not available")
+    cell = Cell(50, 2, 77, 2, 0, ng, ext)
+    R = reflib()
+    R.refwalk_create_phich.restype = C.c_void_p
+    R.refwalk_create_phich.argtypes = [C.c_uint32] * 7
+    ref = RefWalk.__new__(RefWalk)
+    ref.L = R
+    ref.h = R.refwalk_create_phich(cell.nof_prb, cell.nof_ports, cell.cell_id, cell.nof_rx, 5, ng, ext)
+    assert ref.h
+    srch = capi.Search(cell.nof_prb, cell.nof_ports, cell.cell_id, cell.nof_rx, phich_resources=ng | (ext << 8))
+    s = Sim(cell=cell, seed=50 + ng, cfi=cfi, nof_ues=6, dl_min=3, dl_max=5, ul_min=1, ul_max=2, tm=2, mcs_min=4, mcs_max=12, snr_db=25.0, fixed_L=2)
+    o = Oracle(cell)
+    geo = host_geometry(cell)
+    total = 0
+    for tti in range(24):
+        info, T, llr, tr = phase_a_oracle(s, o, geo, tti)
+        assert info.nof_cce == product_map((50, 2, 77, 2), ng, info.cfi, ext)[0]
+        want = ref.subframe(info, T, llr)
+        got = srch.subframe(info, T)
+        for is_ul in (False, True):
+            a = [d for d in got if (d["format"] == 0) == is_ul]
+            b = [r for r in want if (r.format == 0) == is_ul]
+            assert [(int(d["rnti"]), int(d["format"]), int(d["L"]), int(d["ncce"]), int(d["histogram_value"])) for d in a] == \
+                   [(r.rnti, r.format, r.L, r.ncce, r.histval) for r in b], (ng, ext, tti, is_ul)
+        total += len(got)
+    rs, ps = ref.stats(), srch.stats()
+    assert (rs.nof_decoded_locations, rs.nof_cce, rs.nof_locations) == (ps.nof_decoded_locations, ps.nof_cce, ps.nof_locations)
+    assert total >= 24
+    ref.close()
