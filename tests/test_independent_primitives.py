@@ -352,3 +352,53 @@ def test_pusch_channel_interleaver_against_the_procedure_of_36212(S):
         assert np.array_equal(np.where(k_out == 4, 3, k_out), kind), (M, qa, qr, qc)
         sel = (kind == 0) | (kind == 1) | ((kind == 3) & (under == 0))
         assert np.array_equal(d_out[sel].astype(np.int64), pos[sel]), (M, qa, qr, qc)
+
+
+def test_turbo_decoder_waterfall_is_where_the_literature_puts_it(infra):
+    """An external yardstick for the oracle's decoder (the thing every CUDA turbo result is compared with): the rate-1/3 LTE turbo code with K = 6144 on BPSK /
+    AWGN reaches a block error rate of 1e-2 near Eb/N0 = 0.5 dB with log-MAP and some tenths of a dB later with max-log-MAP at 8 iterations (3GPP R1 turbo-code
+    evaluations; Shannon limit of the rate: -0.5 dB).  So every block must decode at 1.0 dB and none at 0.0 dB; a broken extrinsic exchange, interleaver or
+    termination moves the waterfall by far more than that."""
+    S, O = infra.sim(), infra.oracle()
+    rng = np.random.default_rng(11)
+    tbs, qm, G = 6120, 2, 3 * (6144 + 4)
+    res = {}
+    for ebn0 in (0.0, 1.0):
+        sigma = np.sqrt(1 / (2 * 10 ** ((ebn0 + 10 * np.log10(tbs / G)) / 10)))
+        ok = 0
+        for _ in range(10):
+            pl = rng.integers(0, 256, tbs // 8).astype(np.uint8)
+            e = np.zeros(G, np.uint8)
+            assert S.lte_sim_dlsch_encode(ltelib.ptr(pl), tbs, 0, G, qm, 1, ltelib.ptr(e)) == 0
+            x = 2.0 * e - 1.0 + sigma * rng.standard_normal(G)
+            llr = np.clip(np.round(x * 8 / sigma ** 2), -32000, 32000).astype(np.int16)
+            out = np.zeros(tbs // 8 + 8, np.uint8)
+            it = np.zeros(32, np.uint32)
+            r = O.lteo_dlsch_decode(ltelib.ptr(llr), G, tbs, 0, qm, 1, 8, 1, ltelib.ptr(out), ltelib.ptr(it))
+            ok += int(r == 1 and np.array_equal(out[:tbs // 8], pl))
+        res[ebn0] = ok
+    assert res == {0.0: 0, 1.0: 10}, res
+
+
+def test_tail_biting_viterbi_performance_is_where_the_literature_puts_it(infra):
+    """the same yardstick for the oracle's DCI decoder (rate-dematch, 8-bit quantisation, tail-biting Viterbi over three copies, CRC16): the K = 7, rate-1/3
+    tail-biting code with a 43-bit block reaches a block error rate of 1e-2 near Eb/N0 = 2 - 2.5 dB (3GPP short-block evaluations).  Measured here once:
+    15 % of the blocks at -2 dB, 64 % at 0 dB, 98.7 % at 2 dB, all at 4 dB."""
+    S = infra.sim()
+    o = ltelib.Oracle(Cell(100, 2, 5, 1))
+    rng = np.random.default_rng(2)
+    nb, L = 27, 1
+    E = 72 << L
+    res = {}
+    for ebn0 in (-2.0, 4.0):
+        sigma = np.sqrt(1 / (2 * 10 ** ((ebn0 + 10 * np.log10((nb + 16) / E)) / 10)))
+        ok = 0
+        for _ in range(150):
+            b = rng.integers(0, 2, nb).astype(np.uint8)
+            rnti = int(rng.integers(1, 65535))
+            e = np.zeros(E, np.uint8)
+            S.lte_sim_pdcch_encode(ltelib.ptr(b), nb, rnti, L, ltelib.ptr(e))
+            r, bits, crc = o.dci_decode((2.0 * e - 1.0 + sigma * rng.standard_normal(E)).astype(np.float32), nb)
+            ok += int(r == 0 and crc == rnti and np.array_equal(bits, b))
+        res[ebn0] = ok
+    assert res[4.0] >= 149 and res[-2.0] <= 45, res
