@@ -265,3 +265,25 @@ def test_pusch_type1_hopping_and_timing_offset(infra):
         _, ref = ltelib.oracle_ul(o, ucfg, 7, gr, x)
         for r, opl, crc, ch, _ in ref:
             assert crc and abs(ch.ta_us - ta) < 0.05
+
+
+@pytest.mark.parametrize("mcs,snr_ok,snr_fail", [(9, 7.0, 0.0), (16, 14.0, 6.0), (28, 25.0, 17.0)])
+def test_receiver_sensitivity_is_in_the_expected_range(infra, mcs, snr_ok, snr_fail):
+    """A yardstick from outside for the whole oracle receiver (estimator, equaliser, soft demodulator, rate-dematching, turbo): on a flat single-antenna channel
+    the 10 % block-error points of LTE link-level tables are near 2.5 dB (QPSK, rate 0.58), 8 dB (16QAM, 0.56) and 18.5 dB (64QAM, 0.89); this receiver, which
+    estimates the channel from the CRS as srsRAN does, was measured about 2 dB later (4 / 10 / 20.5 dB).  Every block must decode some dB above that and none
+    some dB below the ideal point: a wrong LLR scale, constellation threshold or noise estimate costs far more than the margin left here."""
+    from helpers import make_capture, truth_grants, oracle_frontend
+    cell = Cell(25, 1, 7, 1)
+    res = {}
+    for snr in (snr_ok, snr_fail):
+        sim, iq, tti, truths, payloads = make_capture(cell, 6, seed=100 + mcs, cfi=2, nof_ues=4, dl_min=2, dl_max=2, tm=1, mcs_min=mcs, mcs_max=mcs, snr_db=snr, full_band=1)
+        o = Oracle(cell)
+        fe = oracle_frontend(o, iq, tti)
+        ok = n = 0
+        for sf, d, g in truth_grants(cell, truths, tti):
+            r, pl, okk = o.pdsch_decode(int(tti[sf]) % 10, fe[sf]["cfi"], d.rnti, g, fe[sf]["sym"], fe[sf]["ce"], 8)
+            n += 1
+            ok += int(okk[0])
+        res[snr] = (ok, n)
+    assert res[snr_ok][0] == res[snr_ok][1] >= 10 and res[snr_fail][0] == 0, res
