@@ -271,7 +271,8 @@ def test_pusch_type1_hopping_and_timing_offset(infra):
 def test_receiver_sensitivity_is_in_the_expected_range(infra, mcs, snr_ok, snr_fail):
     """A yardstick from outside for the whole oracle receiver (estimator, equaliser, soft demodulator, rate-dematching, turbo): on a flat single-antenna channel
     the 10 % block-error points of LTE link-level tables are near 2.5 dB (QPSK, rate 0.58), 8 dB (16QAM, 0.56) and 18.5 dB (64QAM, 0.89); this receiver, which
-    estimates the channel from the CRS as srsRAN does, was measured about 2 dB later (4 / 10 / 20.5 dB).  Every block must decode some dB above that and none
+    estimates the channel from the CRS as srsRAN does, was measured about 1 dB later (16QAM: 10 % at 8.8 dB; 7.8 dB when it is given the channel, i.e. the
+    demodulator and decoder sit on the theoretical curve and the rest is estimation noise).  Every block must decode some dB above that and none
     some dB below the ideal point: a wrong LLR scale, constellation threshold or noise estimate costs far more than the margin left here."""
     from helpers import make_capture, truth_grants, oracle_frontend
     cell = Cell(25, 1, 7, 1)
