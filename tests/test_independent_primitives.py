@@ -402,3 +402,26 @@ def test_tail_biting_viterbi_performance_is_where_the_literature_puts_it(infra):
             ok += int(r == 0 and crc == rnti and np.array_equal(bits, b))
         res[ebn0] = ok
     assert res[4.0] >= 149 and res[-2.0] <= 45, res
+
+
+def test_uplink_ofdm_demodulator_against_numpy_fft(infra):
+    """K1-UL of the oracle: the half-subcarrier shift of SC-FDMA (36.211 5.6) removed by exp(-j pi n / N) before the FFT, carriers k - N_sc / 2 without a DC gap"""
+    O = infra.oracle()
+    O.lteo_ul_ofdm.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    rng = np.random.default_rng(8)
+    for cellp, symsz in (((25, 1, 5, 1), 0), ((100, 1, 1, 1), 0), ((50, 1, 3, 1), 768)):
+        cell = Cell(*cellp, symsz)
+        o = ltelib.Oracle(cell)
+        N, nsc = cell.fft(), 12 * cell.nof_prb
+        iq = (rng.standard_normal(15 * N) + 1j * rng.standard_normal(15 * N)).astype(np.complex64)
+        sym = np.zeros(14 * nsc, np.complex64)
+        O.lteo_ul_ofdm(o.h, ltelib.ptr(iq), ltelib.ptr(sym))
+        sym = sym.reshape(14, nsc)
+        pos = 0
+        n = np.arange(N)
+        for l in range(14):
+            cp = (160 if l % 7 == 0 else 144) * N // 2048
+            X = np.fft.fft(iq[pos + cp:pos + cp + N].astype(np.complex128) * np.exp(-1j * np.pi * n / N))
+            ref = X[(np.arange(nsc) + N - nsc // 2) % N]
+            assert np.allclose(sym[l], ref, atol=2e-5 * np.sqrt(N)), (cellp, symsz, l)
+            pos += cp + N
