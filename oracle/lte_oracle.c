@@ -1017,6 +1017,23 @@ static cf_t* idft_mixed(const cf_t* W, uint32_t M, cf_t* a, cf_t* b)
   }
   return src;
 }
+/* test accessor: the M-point inverse DFT of the transform de-precoder exactly as lteo_pusch_decode runs it (unscaled); M = 2^a 3^b 5^c */
+int lteo_idft(uint32_t M, const cf_t* in, cf_t* out)
+{
+  if (!lte_ul_valid_prb(M / 12) || M % 12) return -1;
+  cf_t* W = (cf_t*)malloc(sizeof(cf_t) * M);
+  cf_t* a = (cf_t*)malloc(sizeof(cf_t) * M);
+  cf_t* b = (cf_t*)malloc(sizeof(cf_t) * M);
+  for (uint32_t m = 0; m < M; m++) {
+    double ph = 2.0 * M_PI * (double)m / (double)M;
+    W[m]      = (cf_t){(float)cos(ph), (float)sin(ph)};
+  }
+  memcpy(a, in, sizeof(cf_t) * M);
+  const cf_t* z = idft_mixed(W, M, a, b);
+  memcpy(out, z, sizeof(cf_t) * M);
+  free(W), free(a), free(b);
+  return 0;
+}
 
 int lteo_pusch_decode(lteo_t* q, const lte_ul_cfg_t* ucfg, uint32_t sf_idx, const lte_ul_grant_t* g, const cf_t* sym, uint32_t max_iter,
                       uint8_t* payload, int* crc_ok, lteo_ul_chest_t* chest, int16_t* llr_out)

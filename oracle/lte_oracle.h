@@ -114,6 +114,8 @@ typedef struct {
 } lteo_ul_chest_t;
 /* K1-UL: iq[sf_len] -> sym[14*nsc] with the 7.5 kHz shift removed */
 void lteo_ul_ofdm(lteo_t* q, const cf_t* iq, cf_t* sym);
+/* test accessor: the unscaled M-point inverse DFT of the transform de-precoder (M = 12 L_prb, L_prb = 2^a 3^b 5^c); 0 ok */
+int lteo_idft(uint32_t M, const cf_t* in, cf_t* out);
 /* K9: one PUSCH grant; llr_out (optional) receives the nof_bits descrambled, de-interleaved int16 soft bits */
 int lteo_pusch_decode(lteo_t* q, const lte_ul_cfg_t* ucfg, uint32_t sf_idx, const lte_ul_grant_t* g, const cf_t* sym, uint32_t max_iter,
                       uint8_t* payload, int* crc_ok, lteo_ul_chest_t* chest, int16_t* llr_out);

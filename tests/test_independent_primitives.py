@@ -425,3 +425,17 @@ def test_uplink_ofdm_demodulator_against_numpy_fft(infra):
             ref = X[(np.arange(nsc) + N - nsc // 2) % N]
             assert np.allclose(sym[l], ref, atol=2e-5 * np.sqrt(N)), (cellp, symsz, l)
             pos += cp + N
+
+
+def test_transform_deprecoder_idft_against_numpy(infra):
+    """the mixed-radix (5, 3, 4, 2) Stockham inverse DFT of the PUSCH path -- the expression tree the CUDA kernel reproduces bit for bit -- against numpy.fft.ifft"""
+    O = infra.oracle()
+    O.lteo_idft.argtypes = [C.c_uint32, C.c_void_p, C.c_void_p]
+    rng = np.random.default_rng(9)
+    for L in (3, 4, 5, 6, 8, 9, 10, 12, 15, 16, 18, 20, 24, 25, 27, 30, 32, 36, 40, 45, 48, 50, 54, 60, 64, 72, 75, 80, 81, 90, 96, 100):
+        M = 12 * L
+        x = (rng.standard_normal(M) + 1j * rng.standard_normal(M)).astype(np.complex64)
+        y = np.zeros(M, np.complex64)
+        assert O.lteo_idft(M, ltelib.ptr(x), ltelib.ptr(y)) == 0
+        assert np.allclose(y, np.fft.ifft(x.astype(np.complex128)) * M, atol=3e-5 * np.sqrt(M) * 3), L
+    assert O.lteo_idft(12 * 7, ltelib.ptr(x), ltelib.ptr(y)) == -1
