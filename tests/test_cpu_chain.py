@@ -288,3 +288,32 @@ def test_receiver_sensitivity_is_in_the_expected_range(infra, mcs, snr_ok, snr_f
             ok += int(okk[0])
         res[snr] = (ok, n)
     assert res[snr_ok][0] == res[snr_ok][1] >= 10 and res[snr_fail][0] == 0, res
+
+
+def test_channel_estimate_on_noiseless_channels(infra):
+    """the CRS estimator of the oracle on channels it should get exactly: without noise a flat path of gain g gives |ce| = g sqrt(N) on every RE (direct paths 1.0,
+    cross paths 0.35 in the simulator), constant over the 14 symbols; a path delayed by d samples gives a phase ramp of -2 pi d / N per sub-carrier.  Pins pilot
+    positions and values, the interpolation over frequency and time and the port / antenna ordering against physics rather than against the transmitter's code."""
+    from helpers import make_capture, oracle_frontend
+    cell = Cell(50, 2, 21, 2)
+    N = cell.fft()
+    for delay in (0, 3):
+        sim, iq, tti, truths, payloads = make_capture(cell, 2, seed=7, cfi=2, nof_ues=4, dl_min=2, dl_max=3, tm=2, mcs_min=4, mcs_max=10, snr_db=100.0, chan_delay=delay)
+        fe = oracle_frontend(Oracle(cell), iq, tti)
+        ce = fe[1]["ce"].reshape(2, 2, 14, 12 * cell.nof_prb)                # [port][antenna][symbol][sub-carrier]
+        delays = []
+        for p in range(2):
+            for a in range(2):
+                c = ce[p, a]
+                gain = 1.0 if a == p else 0.35
+                assert abs(np.abs(c).mean() / (gain * np.sqrt(N)) - 1) < (2e-2 if delay else 5e-3), (delay, p, a, np.abs(c).mean())   # linear interpolation between
+                # pilots 6 sub-carriers apart shortens a rotating phasor a little
+                step = np.angle(c[:, 1:] / c[:, :-1])
+                assert step.std() < 2e-3                                     # one slope over the whole band and every symbol
+                d = -step.mean() * N / (2 * np.pi)
+                assert abs(d - round(d)) < 0.05 and 0 <= round(d) <= delay, (delay, p, a, d)
+                delays.append(int(round(d)))
+                if delay == 0:
+                    assert np.abs(c - c.mean()).max() < 2e-3 * np.abs(c).mean()
+        if delay:
+            assert max(delays) >= 1                                          # at least one path was really delayed
